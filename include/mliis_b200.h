@@ -1,0 +1,220 @@
+/*
+ * mliis_b200.h - C ABI of the B200-native inner-loop adaptation engine for ml4ai/mliis.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own:
+ * its "operator API" is the model-object contract consumed by the meta-learner, i.e.
+ *   sess.run(model.minimize_op, {input_ph, label_ph[, lr_ph, drop_rate_ph]})
+ *       (meta_learners/supervised_reptile/supervised_reptile/reptile.py:115-121, :269-279, :639-643)
+ *   sess.run(model.predictions, {input_ph, is_training_ph: False})          (reptile.py:503-506, :520)
+ *   VariableState.export_variables() / import_variables()                     (meta_learners/variables.py:70-80)
+ *   numpy list arithmetic of the meta-update                                  (meta_learners/variables.py:9-45)
+ * Each entry point below names the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C, no C++ types or exceptions cross the boundary;
+ *   - every function returns 0 on success, a negative mliis_status otherwise;
+ *     mliis_last_error() returns a thread-local message for the last failure;
+ *   - every pointer marked "dev" is a DEVICE pointer into caller-owned memory (the Python host
+ *     owns all buffers through torch); the library never frees caller memory;
+ *   - "stream" is a cudaStream_t passed as void*; NULL means the legacy default stream;
+ *   - tensors are fp32 NHWC exactly as the reference feeds them (images in [0,255],
+ *     labels [B,H,W,2] with channel 1 = class of interest);
+ *   - one ctx per (process, GPU); a ctx is not thread-safe; distinct ctxs are independent;
+ *   - there is NO CPU fallback: on a device that is not sm_100 every compute call fails with
+ *     MLIIS_ERR_DEVICE.
+ */
+#ifndef MLIIS_B200_H_
+#define MLIIS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mliis_ctx mliis_ctx;
+
+enum mliis_status {
+  MLIIS_OK = 0,
+  MLIIS_ERR_ARG = -1,      /* bad argument (ValueError in the reference)               */
+  MLIIS_ERR_CUDA = -2,     /* a CUDA runtime call or kernel launch failed               */
+  MLIIS_ERR_DEVICE = -3,   /* not an sm_100 device / no device: no fallback exists      */
+  MLIIS_ERR_STATE = -4     /* call sequence error (e.g. backward without forward)       */
+};
+
+enum mliis_optimizer {     /* meta_learners/args.py:151-154 */
+  MLIIS_OPT_ADAM = 0,      /* tf.train.AdamOptimizer(beta1=0) */
+  MLIIS_OPT_SGD = 1        /* tf.train.GradientDescentOptimizer (--sgd) */
+};
+
+enum mliis_loss_flags {    /* models/efficientlab.py:294-313 */
+  MLIIS_LOSS_DICE = 1,     /* loss = CE - ln(2 IoU/(IoU+1))  (--loss_name bce_dice) */
+  MLIIS_LOSS_L2 = 2        /* + 0.0005 * sum l2_loss(non-BN vars)  (--l2)           */
+};
+
+enum mliis_gemm_mode {     /* numeric mode of the dense contractions */
+  MLIIS_GEMM_FP32 = 0,     /* fp32 FFMA kernels (exact-order reference mode)                */
+  MLIIS_GEMM_TF32 = 1,     /* tcgen05 kind::tf32, fp32 accumulate in TMEM                   */
+  MLIIS_GEMM_TF32X3 = 2    /* tcgen05 3xTF32 split (fp32-class accuracy)                    */
+};
+
+typedef struct mliis_config {
+  int32_t image_size;          /* --image_size (square); must be a multiple of 32          */
+  int32_t max_batch;           /* largest batch any call will use (inner batch / query set) */
+  int32_t n_slots;             /* independent task slots (each has its own state/workspace) */
+  int32_t optimizer;           /* mliis_optimizer                                           */
+  int32_t loss_flags;          /* mliis_loss_flags                                          */
+  int32_t gemm_mode;           /* mliis_gemm_mode                                           */
+  float   label_smoothing;     /* --label_smoothing                                         */
+  float   final_dropout_rate;  /* --final_layer_dropout_rate (0 = layer absent)             */
+  int32_t rsd[4];              /* --rsd reduction indices, 0-terminated (canonical {2,4})   */
+} mliis_config;
+
+/* One trainable variable of the reference graph (tf.trainable_variables() order). */
+typedef struct mliis_param_info {
+  const char* name;            /* expected TF variable name                                */
+  int64_t     offset;          /* float offset into the engine's flat parameter buffer     */
+  int64_t     size;            /* number of floats                                         */
+  int32_t     ndim;
+  int32_t     shape[4];        /* TF layout: HWIO kernels, [k,k,C,1] depthwise, [C] vectors */
+  int32_t     l2;              /* 1 if included in regularizers.l2_term                    */
+} mliis_param_info;
+
+/* One BatchNorm layer: moving_mean at bn_state[offset..], moving_variance at bn_state[n_bn+offset..]. */
+typedef struct mliis_bn_info {
+  const char* scope;
+  int32_t     channels;
+  int32_t     offset;
+  int32_t     fused;           /* 1 = decoder FusedBatchNorm (Bessel-corrected EMA variance) */
+} mliis_bn_info;
+
+const char* mliis_last_error(void);
+const char* mliis_version(void);
+
+/* ---- context ------------------------------------------------------------------------------
+ * Replaces: EfficientLab.__init__/build_model graph construction (models/efficientlab.py:23-119)
+ * and tf.Session() (run_metasegnet.py:109).  device < 0 builds a table-only ctx (no CUDA call is
+ * made; used to query the variable tables on a machine without a GPU). */
+int mliis_ctx_create(const mliis_config* cfg, int device, mliis_ctx** out);
+int mliis_ctx_destroy(mliis_ctx* ctx);
+
+int64_t mliis_num_params(const mliis_ctx* ctx);        /* P = 2 071 714 for the canonical config */
+int32_t mliis_num_param_tensors(const mliis_ctx* ctx); /* 169 */
+int32_t mliis_num_bn_layers(const mliis_ctx* ctx);     /* 39  */
+int32_t mliis_num_bn_channels(const mliis_ctx* ctx);   /* 8752 */
+int32_t mliis_num_dc_blocks(const mliis_ctx* ctx);     /* 6 blocks with drop-connect */
+int mliis_param_table(const mliis_ctx* ctx, mliis_param_info* out, int32_t capacity);
+int mliis_bn_table(const mliis_ctx* ctx, mliis_bn_info* out, int32_t capacity);
+/* bytes of device workspace ONE slot needs (activations, gradients, scratch). */
+int64_t mliis_workspace_bytes(const mliis_ctx* ctx);
+/* floats in one slot's state vector: [theta | moving_mean n_bn | moving_variance n_bn | adam_v | beta1_power,
+ * beta2_power, 2 pad], where theta / adam_v are mliis_theta_floats() long: the P parameters laid out with the
+ * L2-regularised tensors first and every tensor 16-byte aligned (offsets: mliis_param_table). */
+int64_t mliis_state_floats(const mliis_ctx* ctx);
+int64_t mliis_theta_floats(const mliis_ctx* ctx);
+
+/* Attach caller-owned device memory to a slot.  state: mliis_state_floats() floats;
+ * workspace: mliis_workspace_bytes() bytes, 256-byte aligned. */
+int mliis_slot_bind(mliis_ctx* ctx, int32_t slot, float* dev_state, void* dev_workspace);
+
+/* ---- state save / restore -----------------------------------------------------------------
+ * Replaces VariableState.export_variables/import_variables round trips through host numpy
+ * (meta_learners/variables.py:70-80; reptile.py:258, :293, :102, :123).  Device-to-device. */
+int mliis_state_copy(mliis_ctx* ctx, float* dev_dst, const float* dev_src, int32_t what, void* stream);
+enum { MLIIS_STATE_TRAINABLES = 1, MLIIS_STATE_BN = 2, MLIIS_STATE_OPT = 4, MLIIS_STATE_ALL = 7 };
+
+/* ---- one inner step: sess.run(minimize_op, feed_dict) ---------------------------------------
+ * Replaces reptile.py:115-121 / :269-279 / :639-643 -> models/efficientlab.py:315-317
+ * (forward, loss, backward, BN moving-average UPDATE_OPS, optimizer apply).
+ *   dev_images  [n_pool,H,W,3] fp32 in [0,255]; dev_labels [n_pool,H,W,2] fp32
+ *   dev_index   [B] int32: rows of the pool forming this mini-batch (NULL = 0..B-1)
+ *   dev_dc_mask [n_dc_blocks*B] fp32 {0,1} drop-connect binary_tensor (NULL = all keep)
+ *   dev_drop_mask [B*h*w*D] fp32 {0,1} final-layer dropout keep mask (NULL: rate must be 0,
+ *                 or a counter-based device RNG keyed by `seed` is used when rate > 0)
+ *   pre_decay_rate: reptile.py:112-113 pre_step_op (var *= rate); 1 = none
+ *   dev_loss_out [1] fp32 (may be NULL). */
+typedef struct mliis_step_args {
+  const float*   dev_images;
+  const float*   dev_labels;
+  const int32_t* dev_index;
+  int32_t        batch;
+  float          lr;
+  float          pre_decay_rate;
+  const float*   dev_dc_mask;
+  const float*   dev_drop_mask;
+  uint64_t       seed;
+  float*         dev_loss_out;
+} mliis_step_args;
+int mliis_train_step(mliis_ctx* ctx, int32_t slot, const mliis_step_args* args, void* stream);
+
+/* The pieces of a step, exposed for parity tests (same buffers as mliis_train_step). */
+int mliis_forward(mliis_ctx* ctx, int32_t slot, const float* dev_images, const int32_t* dev_index,
+                  int32_t batch, int32_t training, const float* dev_dc_mask, const float* dev_drop_mask,
+                  uint64_t seed, float* dev_logits_out /* [B,H,W,2] or NULL */, void* stream);
+int mliis_loss_backward(mliis_ctx* ctx, int32_t slot, const float* dev_labels, const int32_t* dev_index,
+                        int32_t batch, float* dev_grads_out /* [P] or NULL */, float* dev_loss_out, void* stream);
+int mliis_optimizer_step(mliis_ctx* ctx, int32_t slot, float lr, float pre_decay_rate, void* stream);
+
+/* ---- predictions + IoU: sess.run(predictions, {input_ph, is_training_ph: False}) -------------
+ * Replaces reptile.py:482-524 (_test_predictions), models/efficientlab.py:291-292 (threshold) and
+ * the integer part of Gecko._iou (reptile.py:526-549).  BN uses moving statistics.
+ *   dev_pred_out  [B,H,W,2] fp32 {0,1} (the reference's `predictions` tensor) or NULL
+ *   dev_inter_out / dev_union_out [B] uint32 counts on channel 1 (need dev_labels) or NULL. */
+int mliis_predict(mliis_ctx* ctx, int32_t slot, const float* dev_images, const float* dev_labels,
+                  const int32_t* dev_index, int32_t batch, float* dev_pred_out, float* dev_logits_out,
+                  uint32_t* dev_inter_out, uint32_t* dev_union_out, void* stream);
+
+/* ---- whole task: Gecko._evaluate (reptile.py:235-294) on device ------------------------------
+ * state <- init_state (full state incl. optimizer slots, like _full_state export/import), then
+ * n_steps inner steps with mini-batches dev_batch_index[n_steps*batch] drawn from the task pool,
+ * then transductive prediction + IoU counts on the query rows dev_query_index[n_query]. */
+typedef struct mliis_task_args {
+  const float*   dev_init_state;   /* mliis_state_floats() floats, not modified              */
+  const float*   dev_images;       /* task pool [n_pool,H,W,3]                               */
+  const float*   dev_labels;       /* task pool [n_pool,H,W,2]                               */
+  const int32_t* dev_batch_index;  /* [n_steps*batch]                                        */
+  const float*   dev_lr;           /* [n_steps] per-step learning rate (lr_scheduler)        */
+  int32_t        n_steps;
+  int32_t        batch;
+  const int32_t* dev_query_index;  /* [n_query]                                              */
+  int32_t        n_query;
+  const float*   dev_dc_mask;      /* [n_steps*n_dc_blocks*batch] or NULL                    */
+  uint64_t       seed;
+  float          pre_decay_rate;
+  uint32_t*      dev_inter_out;    /* [n_query]                                              */
+  uint32_t*      dev_union_out;    /* [n_query]                                              */
+  float*         dev_loss_out;     /* [n_steps] or NULL                                      */
+} mliis_task_args;
+int mliis_adapt_eval_task(mliis_ctx* ctx, int32_t slot, const mliis_task_args* args, void* stream);
+
+/* ---- meta-update (meta_learners/variables.py:9-45; reptile.py:122-125, :644-647) --------------
+ * delta_sum += (theta_a - theta_b)             [Reptile: a = adapted, b = old; FOMAML: a = theta_T, b = theta_{T-1}]
+ * theta     += scale * delta_sum               [scale = meta_step_size / meta_batch_size]
+ * All buffers are flat [P] fp32 in the engine's parameter order. */
+int mliis_delta_accumulate(mliis_ctx* ctx, float* dev_delta_sum, const float* dev_theta_a,
+                           const float* dev_theta_b, int32_t first /* 1: overwrite */, void* stream);
+int mliis_meta_apply(mliis_ctx* ctx, float* dev_theta, const float* dev_delta_sum, float scale, void* stream);
+
+/* ---- per-kernel entry points (unit tests / micro-benchmarks) --------------------------------- */
+int mliis_dwconv_fwd(const float* dev_x, const float* dev_w, float* dev_y, int32_t B, int32_t H, int32_t W,
+                     int32_t C, int32_t k, int32_t stride, const float* dev_bn_a, const float* dev_bn_b,
+                     void* stream);
+int mliis_gemm_nn(const float* dev_a, const float* dev_w, float* dev_c, int32_t M, int32_t K, int32_t N,
+                  int32_t mode, void* stream);
+int mliis_conv3x3_fwd(const float* dev_x, const float* dev_w, const float* dev_bias, float* dev_y, int32_t B,
+                      int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t dilation, int32_t mode,
+                      void* stream);
+int mliis_bilinear_fwd(const float* dev_x, float* dev_y, int32_t B, int32_t Hin, int32_t Win, int32_t Hout,
+                       int32_t Wout, int32_t C, void* stream);
+int mliis_adam_step(float* dev_theta, float* dev_v, const float* dev_grad, int64_t n, int64_t n_l2, float lr,
+                    float beta2_power, float l2_coef, void* stream);
+
+/* ---- debugging: copy a named activation / gradient buffer of a slot (tests only) -------------- */
+int mliis_debug_buffer(mliis_ctx* ctx, int32_t slot, const char* name, const float** dev_ptr,
+                       int64_t* rows_per_image, int32_t* channels, int32_t* ld);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLIIS_B200_H_ */

@@ -1,0 +1,71 @@
+"""In-tree build of libmliis_b200.so (nvcc, sm_100a only).  The built library travels to the GPU box with the
+repo snapshot; there is no JIT cache and no CPU fallback."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libmliis_b200.so")
+HEADER = os.path.join(HERE, "..", "include", "mliis_b200.h")
+SOURCES = ["engine.cu", "k_rowchan.cu", "k_conv.cu", "k_gemm.cu", "k_misc.cu", "k_tc.cu", "plan.cpp"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-cudart", "static"]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    return "nvcc"
+
+
+def sources():
+    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def _headers():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] + [HEADER]
+
+
+def is_stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(d) > t for d in sources() + _headers())
+
+
+def build(force=False, verbose=True):
+    """Compile every CUDA source for sm_100a into mliis_b200/libmliis_b200.so."""
+    if not force and not is_stale():
+        return LIB
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = _nvcc()
+    hdr_t = max(os.path.getmtime(h) for h in _headers())
+    procs, objs = [], []
+    for src in sources():
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        objs.append(obj)
+        if (not force) and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+            continue
+        cmd = [nvcc] + NVCC_FLAGS + ["-x", "cu", "-c", src, "-o", obj]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s" % (src, out.decode()))
+        if verbose and out.strip():
+            print(out.decode(), file=sys.stderr)
+    cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", LIB] + objs
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv)
+    print(LIB)

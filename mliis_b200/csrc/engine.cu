@@ -1,0 +1,800 @@
+// mliis_b200 engine: the C ABI of include/mliis_b200.h on top of the kernels in this directory.
+// One inner step = forward (train-mode BN) -> fused loss -> backward -> BN EMA -> optimizer, all on one
+// CUDA stream with every tensor resident in the slot's workspace; nothing crosses to the host.
+//
+// Reference call sites replaced: see include/mliis_b200.h.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mliis_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "plan.h"
+
+using namespace mliis;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+struct Slot {
+  float* state = nullptr;
+  float* ws = nullptr;
+  int fwd_batch = 0;
+  bool fwd_training = false;
+  const float* fwd_images = nullptr;
+  const int32_t* fwd_index = nullptr;
+  const float* fwd_drop_mask = nullptr;
+  bool grads_zeroed = false;
+};
+
+struct Tab {
+  int32_t *lo = nullptr, *hi = nullptr, *g_lo = nullptr, *g_hi = nullptr;
+  float* lerp = nullptr;
+  ResizeTab rt() const { return ResizeTab{lo, hi, lerp, g_lo, g_hi}; }
+};
+
+}  // namespace
+
+struct mliis_ctx {
+  mliis_config cfg;
+  Plan plan;
+  int device = -1;
+  std::vector<Slot> slots;
+  int32_t* d_gamma_idx = nullptr;
+  int32_t* d_beta_idx = nullptr;
+  std::vector<Tab> tabs;
+  std::vector<void*> owned;
+  float keep[16];
+};
+
+namespace {
+
+// TF ResizeBilinear(align_corners=True) tables, computed in float32 exactly like the oracle [TF-ext]
+void host_tables(int n_in, int n_out, std::vector<int32_t>& lo, std::vector<int32_t>& hi, std::vector<float>& lerp,
+                 std::vector<int32_t>& g_lo, std::vector<int32_t>& g_hi) {
+  lo.resize(n_out); hi.resize(n_out); lerp.resize(n_out);
+  g_lo.assign(n_in, n_out); g_hi.assign(n_in, -1);
+  const float scale = n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.f;
+  for (int i = 0; i < n_out; ++i) {
+    const float src = (float)i * scale;
+    const int l = (int)floorf(src);
+    int h = (int)ceilf(src);
+    if (h > n_in - 1) h = n_in - 1;
+    lo[i] = l; hi[i] = h; lerp[i] = src - (float)l;
+    for (int j : {l, h}) {
+      if (i < g_lo[j]) g_lo[j] = i;
+      if (i > g_hi[j]) g_hi[j] = i;
+    }
+  }
+}
+
+template <typename T>
+T* upload(mliis_ctx* c, const std::vector<T>& v) {
+  T* d = nullptr;
+  if (cudaMalloc(&d, v.size() * sizeof(T)) != cudaSuccess) return nullptr;
+  cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  if (c) c->owned.push_back(d);
+  return d;
+}
+
+bool make_tab(mliis_ctx* c, int n_in, int n_out, Tab* t) {
+  std::vector<int32_t> lo, hi, glo, ghi;
+  std::vector<float> lerp;
+  host_tables(n_in, n_out, lo, hi, lerp, glo, ghi);
+  t->lo = upload(c, lo); t->hi = upload(c, hi); t->lerp = upload(c, lerp);
+  t->g_lo = upload(c, glo); t->g_hi = upload(c, ghi);
+  return t->lo && t->hi && t->lerp && t->g_lo && t->g_hi;
+}
+
+int check_cuda(const char* where) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MLIIS_ERR_CUDA, "%s: %s", where, cudaGetErrorString(e));
+  return MLIIS_OK;
+}
+
+__global__ void dcs_kernel(const float* __restrict__ mask, float* __restrict__ dcs, int n_dc, int B, int maxB,
+                           float k0, float k1, float k2, float k3, float k4, float k5, float k6, float k7) {
+  const float keep[8] = {k0, k1, k2, k3, k4, k5, k6, k7};
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_dc * B) return;
+  int d = i / B, b = i - d * B;
+  // utils.py:157-170: tf.div(inputs, keep_prob) * binary_tensor
+  dcs[d * maxB + b] = (mask ? mask[i] : 1.f) / keep[d];
+}
+
+__global__ void set_scalar_kernel(float* p, float v) { *p = v; }
+
+struct Run {
+  mliis_ctx* c;
+  Slot* sl;
+  const Plan& p;
+  int B;
+  cudaStream_t st;
+  float* theta;
+  float* mm;
+  float* mv;
+  float* adam_v;
+  float* powers;
+  float* W(int64_t off) const { return sl->ws + off; }
+  float* T(int64_t off) const { return theta + off; }
+  float* G(int64_t off) const { return sl->ws + p.grads + off; }
+  Run(mliis_ctx* ctx, int slot, int batch, cudaStream_t s)
+      : c(ctx), sl(&ctx->slots[slot]), p(ctx->plan), B(batch), st(s) {
+    theta = sl->state;
+    mm = sl->state + p.n_theta;
+    mv = mm + p.n_bn_ch;
+    adam_v = mv + p.n_bn_ch;
+    powers = adam_v + p.n_theta;
+  }
+  float* bn_a(const BnRef& r) const { return W(p.bn_a + r.off); }
+  float* bn_b(const BnRef& r) const { return W(p.bn_b + r.off); }
+  float* bn_mean(const BnRef& r) const { return W(p.bn_mean + r.off); }
+  float* bn_rstd(const BnRef& r) const { return W(p.bn_rstd + r.off); }
+
+  // train-mode batch statistics of one BN layer (+ EMA of the moving statistics)
+  void bn_train(const BnRef& r, const float* x, int ld, int M, bool pre_swish) const {
+    bn_stats(x, ld, M, r.C, pre_swish, W(p.partials), st);
+    bn_finalize(W(p.partials), rc_num_chunks(M, r.C), r.C, M, T(r.gamma), T(r.beta), mm + r.off, mv + r.off, 1,
+                r.fused, bn_mean(r), bn_rstd(r), bn_a(r), bn_b(r), st);
+  }
+};
+
+GemmA plainA(const float* ptr, int ld) {
+  GemmA a{};
+  a.ptr = ptr; a.ld = ld;
+  return a;
+}
+GemmA convA(const float* ptr, int ld, int H, int W, int C, int dil) {
+  GemmA a{};
+  a.ptr = ptr; a.ld = ld; a.conv = 1; a.H = H; a.W = W; a.C = C; a.dil = dil;
+  return a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+void run_forward(const Run& r, const float* images, const int32_t* index, bool training, const float* dc_mask,
+                 const float* drop_mask, uint64_t seed) {
+  const Plan& p = r.p;
+  const int B = r.B;
+  cudaStream_t st = r.st;
+  if (!training)
+    bn_eval_coeffs(r.theta, r.c->d_gamma_idx, r.c->d_beta_idx, r.mm, r.mv, p.n_bn_ch, r.W(p.bn_a), r.W(p.bn_b), st);
+  if (training && p.n_dc > 0) {
+    const float* k = r.c->keep;
+    dcs_kernel<<<cdiv(p.n_dc * B, 128), 128, 0, st>>>(dc_mask, r.W(p.dcs), p.n_dc, B, p.maxB, k[0], k[1], k[2], k[3],
+                                                      k[4], k[5], k[6], k[7]);
+  }
+  // stem (efficientnet_model.py:410-412); its BN+swish is fused into block 0's depthwise loader
+  stem_fwd(images, index, r.T(p.w_stem), r.W(p.S0.off), B, p.image_size, p.image_size, p.Hs, p.Ws, p.stem_pad_t,
+           p.stem_pad_l, st);
+  if (training) r.bn_train(p.bn_stem, r.W(p.S0.off), 32, B * p.Hs * p.Ws, false);
+
+  const float* X = nullptr;   // materialised block input (output of the previous block)
+  int Xld = 0;
+  for (size_t i = 0; i < p.blocks.size(); ++i) {
+    const BlockPlan& b = p.blocks[i];
+    const int Mi = B * b.Hin * b.Win, Mo = B * b.Hout * b.Wout, HWo = b.Hout * b.Wout;
+    const float *dw_in, *dw_a, *dw_b;
+    if (b.expand) {
+      gemm_nn(plainA(X, Xld), r.T(b.w_expand), nullptr, r.W(b.E.off), b.ce, Mi, b.cin, b.ce, b.Hin * b.Win, 0, st);
+      if (training) r.bn_train(b.bn0, r.W(b.E.off), b.ce, Mi, false);
+      dw_in = r.W(b.E.off); dw_a = r.bn_a(b.bn0); dw_b = r.bn_b(b.bn0);
+    } else {
+      dw_in = r.W(p.S0.off); dw_a = r.bn_a(p.bn_stem); dw_b = r.bn_b(p.bn_stem);
+    }
+    dw_fwd(dw_in, dw_a, dw_b, r.T(b.w_dw), r.W(b.D.off), B, b.Hin, b.Win, b.ce, b.k, b.stride, b.Hout, b.Wout, b.pad_t,
+           b.pad_l, st);
+    if (training) r.bn_train(b.bn1, r.W(b.D.off), b.ce, Mo, false);
+    // squeeze-excite (efficientnet_model.py:238-251)
+    se_pool(r.W(b.D.off), b.ce, r.bn_a(b.bn1), r.bn_b(b.bn1), B, HWo, b.ce, r.W(p.partials), st);
+    se_fc_fwd(r.W(p.partials), rc_num_img_chunks(HWo, b.ce), B, HWo, b.ce, b.cr, r.T(b.w_se1), r.T(b.b_se1),
+              r.T(b.w_se2), r.T(b.b_se2), r.W(b.pool), r.W(b.hidpre), r.W(b.gate), st);
+    // project conv consumes swish(BN1(dw)) * gate, recomputed in the A-operand loader
+    GemmA A = plainA(r.W(b.D.off), b.ce);
+    A.pa = r.bn_a(b.bn1); A.pb = r.bn_b(b.bn1); A.gate = r.W(b.gate);
+    gemm_nn(A, r.T(b.w_proj), nullptr, r.W(b.P.off), b.cout, Mo, b.ce, b.cout, HWo, 0, st);
+    if (training) r.bn_train(b.bn2, r.W(b.P.off), b.cout, Mo, false);
+    const float* dcs = (training && b.dc_idx >= 0) ? r.W(p.dcs + (int64_t)b.dc_idx * p.maxB) : nullptr;
+    block_out(r.W(b.P.off), b.cout, r.bn_a(b.bn2), r.bn_b(b.bn2), dcs, b.skip ? X : nullptr, Xld, r.W(b.Y.off),
+              b.cout, Mo, b.cout, HWo, st);
+    X = r.W(b.Y.off);
+    Xld = b.cout;
+  }
+
+  // decoder (efficientlab.py:153-231)
+  const float* deep = X;
+  int deep_ld = Xld;
+  for (const RsdPlan& d : p.rsds) {
+    const int HW = d.h * d.w, M = B * HW, D = d.D;
+    float* cat = r.W(d.cat.off);
+    if (d.identity_up)
+      add3(cat, d.catC, deep, deep_ld, nullptr, 0, nullptr, 0, M, D, HW, st);
+    else
+      bilinear_fwd(deep, deep_ld, cat, d.catC, B, d.hin, d.win, d.h, d.w, D, r.c->tabs[d.tab].rt(),
+                   r.c->tabs[d.tab].rt(), st);
+    const BlockPlan& sb = p.blocks[d.skip_block];
+    add3(cat + D, d.catC, r.W(sb.Y.off), sb.cout, nullptr, 0, nullptr, 0, M, d.skipC, HW, st);
+    float* pyr = r.W(d.pyr.off);
+    // branch_0: 1x1 (+bias) -> swish -> BN
+    gemm_nn(plainA(cat, d.catC), r.T(d.w0), r.T(d.b0), r.W(d.c0.off), D, M, d.catC, D, HW, 0, st);
+    if (training) r.bn_train(d.bn[0], r.W(d.c0.off), D, M, true);
+    dec_bn_apply(r.W(d.c0.off), D, r.bn_a(d.bn[0]), r.bn_b(d.bn[0]), nullptr, 0, pyr, d.pyrC, M, D, st);
+    // branch_1: 3x3 dilation 2
+    gemm_nn(convA(cat, d.catC, d.h, d.w, d.catC, 2), r.T(d.w1), r.T(d.b1), r.W(d.c1.off), D, M, 9 * d.catC, D, HW, 0,
+            st);
+    if (training) r.bn_train(d.bn[1], r.W(d.c1.off), D, M, true);
+    dec_bn_apply(r.W(d.c1.off), D, r.bn_a(d.bn[1]), r.bn_b(d.bn[1]), nullptr, 0, pyr + D, d.pyrC, M, D, st);
+    // branch_2: image-level mean, tiled (efficientlab.py:192-197)
+    img_colsum(cat, d.catC, B, HW, d.catC, 1.f / (float)HW, r.W(p.partials), r.W(d.pooled), d.catC, st);
+    bcast_rows(r.W(d.pooled), d.catC, pyr + 2 * D, d.pyrC, B, HW, d.catC, st);
+    // 3x3 over the pyramid, + residual
+    gemm_nn(convA(pyr, d.pyrC, d.h, d.w, d.pyrC, 1), r.T(d.w2), r.T(d.b2), r.W(d.c2.off), D, M, 9 * d.pyrC, D, HW, 0,
+            st);
+    if (training) r.bn_train(d.bn[2], r.W(d.c2.off), D, M, true);
+    dec_bn_apply(r.W(d.c2.off), D, r.bn_a(d.bn[2]), r.bn_b(d.bn[2]), cat, d.catC, r.W(d.out.off), D, M, D, st);
+    deep = r.W(d.out.off);
+    deep_ld = D;
+  }
+  // head: dropout -> 1x1 -> (bilinear + softmax are fused into the loss / predict kernels)
+  const float rate = r.c->cfg.final_dropout_rate;
+  const float* mask = nullptr;
+  if (training && rate > 0.f) {
+    if (drop_mask) mask = drop_mask;
+    else {
+      fill_dropout_mask(r.W(p.dropmask), (int64_t)B * p.hl * p.wl * p.D, rate, seed, st);
+      mask = r.W(p.dropmask);
+    }
+  }
+  r.sl->fwd_drop_mask = mask;
+  head_fwd(deep, deep_ld, r.T(p.w_head), r.T(p.b_head), mask, 1.f / (1.f - rate), r.W(p.z_lo), B * p.hl * p.wl, p.D,
+           st);
+  r.sl->fwd_batch = B;
+  r.sl->fwd_training = training;
+  r.sl->fwd_images = images;
+  r.sl->fwd_index = index;
+}
+
+// ------------------------------------------------------------------------------------------------
+// loss + backward
+// ------------------------------------------------------------------------------------------------
+void run_backward(const Run& r, const float* labels, const int32_t* index, float* loss_out) {
+  const Plan& p = r.p;
+  const int B = r.B;
+  cudaStream_t st = r.st;
+  const Tab& tf = r.c->tabs[p.tab_final];
+  if (!r.sl->grads_zeroed) {   // padding holes of the flat gradient buffer must read as zero
+    cudaMemsetAsync(r.G(0), 0, p.n_theta * sizeof(float), st);
+    r.sl->grads_zeroed = true;
+  }
+  LossArgs la{};
+  la.z_lo = r.W(p.z_lo); la.labels = labels; la.index = index;
+  la.B = B; la.h = p.hl; la.w = p.wl; la.H = p.image_size; la.W = p.image_size;
+  la.ty = tf.rt(); la.tx = tf.rt();
+  la.dice = (r.c->cfg.loss_flags & MLIIS_LOSS_DICE) ? 1 : 0;
+  la.label_smoothing = r.c->cfg.label_smoothing;
+  la.p1 = r.W(p.p1); la.partials = r.W(p.partials); la.coef = r.W(p.loss_coef); la.dz_hi = r.W(p.dz_hi);
+  la.loss_out = loss_out;
+  la.theta = r.theta; la.n_l2 = p.n_l2;
+  la.l2_coef = (r.c->cfg.loss_flags & MLIIS_LOSS_L2) ? 0.0005f : 0.f;
+  loss_fwd_bwd(la, st);
+  bilinear_bwd(r.W(p.dz_hi), 2, r.W(p.dz_lo), 2, B, p.hl, p.wl, p.image_size, p.image_size, 2, tf.rt(), tf.rt(), st);
+
+  // head
+  const RsdPlan& last = p.rsds.back();
+  const float rate = r.c->cfg.final_dropout_rate;
+  head_bwd(r.W(last.out.off), p.D, r.T(p.w_head), r.sl->fwd_drop_mask, 1.f / (1.f - rate), r.W(p.dz_lo), r.W(p.g_out),
+           p.D, r.W(p.partials), r.G(p.w_head), r.G(p.b_head), B * p.hl * p.wl, p.D, st);
+
+  // decoder, reverse order
+  float* gOut = r.W(p.g_out);
+  for (int di = (int)p.rsds.size() - 1; di >= 0; --di) {
+    const RsdPlan& d = p.rsds[di];
+    const int HW = d.h * d.w, M = B * HW, D = d.D;
+    const float* cat = r.W(d.cat.off);
+    const float* pyr = r.W(d.pyr.off);
+    auto dec_bn_bwd = [&](const BnRef& bn, const float* x, const float* g, int ldg, float* dx) {
+      BnBwdArgs a{};
+      a.x = x; a.ldx = D; a.g = g; a.ldg = ldg; a.dx = dx; a.lddx = D; a.M = M; a.C = D; a.HW = HW;
+      a.mean = r.bn_mean(bn); a.rstd = r.bn_rstd(bn); a.a = r.bn_a(bn); a.b = r.bn_b(bn); a.gamma = r.T(bn.gamma);
+      a.partials = r.W(p.partials); a.k = r.W(p.bn_k); a.dgamma = r.G(bn.gamma); a.dbeta = r.G(bn.beta);
+      bn_bwd(BN_DEC, a, st);
+    };
+    // out = BN2(swish(c2)) + up
+    dec_bn_bwd(d.bn[2], r.W(d.c2.off), gOut, D, r.W(p.g_c));
+    gemm_tn(convA(pyr, d.pyrC, d.h, d.w, d.pyrC, 1), r.W(p.g_c), D, r.G(d.w2), r.G(d.b2), r.W(p.tn_scratch), M,
+            9 * d.pyrC, D, HW, st);
+    flip_transpose_w3x3(r.T(d.w2), r.W(p.wT), d.pyrC, D, st);
+    gemm_nn(convA(r.W(p.g_c), D, d.h, d.w, D, 1), r.W(p.wT), nullptr, r.W(p.g_pyr), d.pyrC, M, 9 * D, d.pyrC, HW, 0, st);
+    const float* gpyr = r.W(p.g_pyr);
+    dec_bn_bwd(d.bn[0], r.W(d.c0.off), gpyr, d.pyrC, r.W(p.g_c0));
+    dec_bn_bwd(d.bn[1], r.W(d.c1.off), gpyr + D, d.pyrC, r.W(p.g_c1));
+    img_colsum(gpyr + 2 * D, d.pyrC, B, HW, d.catC, 1.f / (float)HW, r.W(p.partials), r.W(d.dpooled), d.catC, st);
+    // branch_0 1x1
+    gemm_tn(plainA(cat, d.catC), r.W(p.g_c0), D, r.G(d.w0), r.G(d.b0), r.W(p.tn_scratch), M, d.catC, D, HW, st);
+    transpose_w(r.T(d.w0), r.W(p.wT), d.catC, D, st);
+    gemm_nn(plainA(r.W(p.g_c0), D), r.W(p.wT), nullptr, r.W(p.g_cat), d.catC, M, D, d.catC, HW, 0, st);
+    // branch_1 3x3 dil 2 (accumulates into g_cat)
+    gemm_tn(convA(cat, d.catC, d.h, d.w, d.catC, 2), r.W(p.g_c1), D, r.G(d.w1), r.G(d.b1), r.W(p.tn_scratch), M,
+            9 * d.catC, D, HW, st);
+    flip_transpose_w3x3(r.T(d.w1), r.W(p.wT), d.catC, D, st);
+    gemm_nn(convA(r.W(p.g_c1), D, d.h, d.w, D, 2), r.W(p.wT), nullptr, r.W(p.g_cat), d.catC, M, 9 * D, d.catC, HW, 1, st);
+    // d_up = gOut + g_cat[:, :D] + dpooled[:, :D]      d_skip = g_cat[:, D:] + dpooled[:, D:]
+    const float* gcat = r.W(p.g_cat);
+    const float* dpl = r.W(d.dpooled);
+    add3(r.W(p.g_up), D, gOut, D, gcat, d.catC, dpl, d.catC, M, D, HW, st);
+    const BlockPlan& sb = p.blocks[d.skip_block];
+    float* extra = r.W(sb.extra_grad);
+    if (d.identity_up && di == 0 && d.skip_block == (int)p.blocks.size() - 1) {
+      // deep input and skip are the same tensor (reduction_4): both gradients land on it
+      add3(r.W(p.g_skip), d.skipC, gcat + D, d.catC, nullptr, 0, dpl + D, d.catC, M, d.skipC, HW, st);
+      add3(extra, D, r.W(p.g_up), D, r.W(p.g_skip), d.skipC, nullptr, 0, M, D, HW, st);
+    } else {
+      add3(extra, d.skipC, gcat + D, d.catC, nullptr, 0, dpl + D, d.catC, M, d.skipC, HW, st);
+      float* gdeep = di == 0 ? r.W(p.blocks.back().extra_grad) : r.W(p.g_deep);
+      if (d.identity_up)
+        add3(gdeep, D, r.W(p.g_up), D, nullptr, 0, nullptr, 0, M, D, HW, st);
+      else
+        bilinear_bwd(r.W(p.g_up), D, gdeep, D, B, d.hin, d.win, d.h, d.w, D, r.c->tabs[d.tab].rt(),
+                     r.c->tabs[d.tab].rt(), st);
+      gOut = gdeep;
+    }
+  }
+
+  // backbone, reverse order.  gY[cur] holds dL/dY of the current block.
+  int cur = 0;
+  const int nb = (int)p.blocks.size();
+  for (int i = nb - 1; i >= 0; --i) {
+    const BlockPlan& b = p.blocks[i];
+    const int Mi = B * b.Hin * b.Win, Mo = B * b.Hout * b.Wout, HWo = b.Hout * b.Wout, HWi = b.Hin * b.Win;
+    float* gY = r.W(p.gY[cur]);
+    if (i == nb - 1) {
+      gY = r.W(b.extra_grad);
+    } else if (b.extra_grad >= 0) {
+      add3(gY, b.cout, gY, b.cout, r.W(b.extra_grad), b.cout, nullptr, 0, Mo, b.cout, HWo, st);
+    }
+    const float* X = i > 0 ? r.W(p.blocks[i - 1].Y.off) : nullptr;
+    // Y = BN2(P) * dcs + X
+    {
+      BnBwdArgs a{};
+      a.x = r.W(b.P.off); a.ldx = b.cout; a.g = gY; a.ldg = b.cout; a.dx = r.W(p.gP); a.lddx = b.cout;
+      a.M = Mo; a.C = b.cout; a.HW = HWo;
+      a.mean = r.bn_mean(b.bn2); a.rstd = r.bn_rstd(b.bn2); a.a = r.bn_a(b.bn2); a.b = r.bn_b(b.bn2);
+      a.gamma = r.T(b.bn2.gamma);
+      a.dcs = b.dc_idx >= 0 ? r.W(p.dcs + (int64_t)b.dc_idx * p.maxB) : nullptr;
+      a.partials = r.W(p.partials); a.k = r.W(p.bn_k); a.dgamma = r.G(b.bn2.gamma); a.dbeta = r.G(b.bn2.beta);
+      bn_bwd(BN_PLAIN, a, st);
+    }
+    // project conv: wgrad on swish(BN1(D))*gate (recomputed), dgrad into gD
+    GemmA Ap = plainA(r.W(b.D.off), b.ce);
+    Ap.pa = r.bn_a(b.bn1); Ap.pb = r.bn_b(b.bn1); Ap.gate = r.W(b.gate);
+    gemm_tn(Ap, r.W(p.gP), b.cout, r.G(b.w_proj), nullptr, r.W(p.tn_scratch), Mo, b.ce, b.cout, HWo, st);
+    transpose_w(r.T(b.w_proj), r.W(p.wT), b.ce, b.cout, st);
+    gemm_nn(plainA(r.W(p.gP), b.cout), r.W(p.wT), nullptr, r.W(p.gD), b.ce, Mo, b.cout, b.ce, HWo, 0, st);
+    // squeeze-excite backward
+    se_bwd_reduce(r.W(b.D.off), b.ce, r.W(p.gD), b.ce, r.bn_a(b.bn1), r.bn_b(b.bn1), B, HWo, b.ce, r.W(p.partials), st);
+    se_fc_bwd(r.W(p.partials), rc_num_img_chunks(HWo, b.ce), B, HWo, b.ce, b.cr, r.T(b.w_se1), r.T(b.w_se2),
+              r.W(b.pool), r.W(b.hidpre), r.W(b.gate), r.G(b.w_se1), r.G(b.b_se1), r.G(b.w_se2), r.G(b.b_se2),
+              r.W(b.dpool), st);
+    {
+      BnBwdArgs a{};
+      a.x = r.W(b.D.off); a.ldx = b.ce; a.g = r.W(p.gD); a.ldg = b.ce; a.dx = r.W(p.gD); a.lddx = b.ce;
+      a.M = Mo; a.C = b.ce; a.HW = HWo;
+      a.mean = r.bn_mean(b.bn1); a.rstd = r.bn_rstd(b.bn1); a.a = r.bn_a(b.bn1); a.b = r.bn_b(b.bn1);
+      a.gamma = r.T(b.bn1.gamma); a.gate = r.W(b.gate); a.dpool = r.W(b.dpool);
+      a.partials = r.W(p.partials); a.k = r.W(p.bn_k); a.dgamma = r.G(b.bn1.gamma); a.dbeta = r.G(b.bn1.beta);
+      bn_bwd(BN_SWISH_SE, a, st);
+    }
+    // depthwise
+    const float *dw_in, *dw_a, *dw_b;
+    const BnRef& bnin = b.expand ? b.bn0 : p.bn_stem;
+    dw_in = b.expand ? r.W(b.E.off) : r.W(p.S0.off);
+    dw_a = r.bn_a(bnin); dw_b = r.bn_b(bnin);
+    dw_bwd_weight(dw_in, dw_a, dw_b, r.W(p.gD), r.W(p.partials), r.G(b.w_dw), B, b.Hin, b.Win, b.ce, b.k, b.stride,
+                  b.Hout, b.Wout, b.pad_t, b.pad_l, st);
+    dw_bwd_data(r.W(p.gD), r.T(b.w_dw), r.W(p.gE), B, b.Hin, b.Win, b.ce, b.k, b.stride, b.Hout, b.Wout, b.pad_t,
+                b.pad_l, st);
+    {
+      BnBwdArgs a{};
+      a.x = dw_in; a.ldx = b.ce; a.g = r.W(p.gE); a.ldg = b.ce; a.dx = r.W(p.gE); a.lddx = b.ce;
+      a.M = Mi; a.C = b.ce; a.HW = HWi;
+      a.mean = r.bn_mean(bnin); a.rstd = r.bn_rstd(bnin); a.a = dw_a; a.b = dw_b; a.gamma = r.T(bnin.gamma);
+      a.partials = r.W(p.partials); a.k = r.W(p.bn_k); a.dgamma = r.G(bnin.gamma); a.dbeta = r.G(bnin.beta);
+      bn_bwd(BN_SWISH, a, st);
+    }
+    if (b.expand) {
+      gemm_tn(plainA(X, b.cin), r.W(p.gE), b.ce, r.G(b.w_expand), nullptr, r.W(p.tn_scratch), Mi, b.cin, b.ce, HWi, st);
+      transpose_w(r.T(b.w_expand), r.W(p.wT), b.cin, b.ce, st);
+      // dX = dE * We^T (+ dY through the identity skip: same shape, accumulate in place)
+      float* gX = b.skip ? gY : r.W(p.gY[cur ^ 1]);
+      gemm_nn(plainA(r.W(p.gE), b.ce), r.W(p.wT), nullptr, gX, b.cin, Mi, b.ce, b.cin, HWi, b.skip ? 1 : 0, st);
+      if (b.skip && gY != r.W(p.gY[cur])) {
+        // gradient lived in the decoder's extra buffer: move it into the ping-pong chain
+        add3(r.W(p.gY[cur]), b.cin, gX, b.cin, nullptr, 0, nullptr, 0, Mi, b.cin, HWi, st);
+      } else if (!b.skip) {
+        cur ^= 1;
+      }
+    } else {
+      // block 0: gE is dL/d(stem conv output) after the stem BN backward above
+      stem_wgrad(r.sl->fwd_images, r.sl->fwd_index, r.W(p.gE), r.W(p.partials), r.G(p.w_stem), B, p.image_size,
+                 p.image_size, p.Hs, p.Ws, p.stem_pad_t, p.stem_pad_l, st);
+    }
+  }
+}
+
+int validate(mliis_ctx* ctx, int slot, int batch) {
+  if (!ctx) return fail(MLIIS_ERR_ARG, "null ctx");
+  if (ctx->device < 0) return fail(MLIIS_ERR_DEVICE, "table-only ctx (no sm_100 device): there is no CPU fallback");
+  if (slot < 0 || slot >= (int)ctx->slots.size()) return fail(MLIIS_ERR_ARG, "slot %d out of range", slot);
+  if (!ctx->slots[slot].state || !ctx->slots[slot].ws) return fail(MLIIS_ERR_STATE, "slot %d not bound", slot);
+  if (batch < 1 || batch > ctx->plan.maxB) return fail(MLIIS_ERR_ARG, "batch %d not in [1, %d]", batch, ctx->plan.maxB);
+  return MLIIS_OK;
+}
+
+void set_lr(const Run& r, float lr) { set_scalar_kernel<<<1, 1, 0, r.st>>>(r.W(r.p.lr_dev), lr); }
+
+void run_optimizer(const Run& r, const float* lr_dev) {
+  const Plan& p = r.p;
+  const float l2 = (r.c->cfg.loss_flags & MLIIS_LOSS_L2) ? 0.0005f : 0.f;
+  adam_step(r.theta, r.adam_v, r.G(0), p.n_theta, p.n_l2, lr_dev, r.powers, l2, r.c->cfg.optimizer == MLIIS_OPT_SGD,
+            r.st);
+}
+
+}  // namespace
+
+// ==================================================================================================
+// C ABI
+// ==================================================================================================
+extern "C" {
+
+const char* mliis_last_error(void) { return g_err.c_str(); }
+const char* mliis_version(void) { return "mliis_b200 0.1 (sm_100a)"; }
+
+int mliis_ctx_create(const mliis_config* cfg, int device, mliis_ctx** out) {
+  if (!cfg || !out) return fail(MLIIS_ERR_ARG, "null argument");
+  mliis_ctx* c = new mliis_ctx();
+  c->cfg = *cfg;
+  try {
+    c->plan.build(cfg->image_size, cfg->max_batch, cfg->rsd, cfg->final_dropout_rate);
+  } catch (const std::exception& e) {
+    delete c;
+    return fail(MLIIS_ERR_ARG, "%s", e.what());
+  }
+  if (cfg->n_slots < 1 || cfg->n_slots > 1024) { delete c; return fail(MLIIS_ERR_ARG, "n_slots must be in [1,1024]"); }
+  if (cfg->final_dropout_rate < 0.f || cfg->final_dropout_rate >= 1.f) { delete c; return fail(MLIIS_ERR_ARG, "bad dropout rate"); }
+  if (c->plan.n_dc > 8) { delete c; return fail(MLIIS_ERR_ARG, "too many drop-connect blocks"); }
+  c->slots.resize(cfg->n_slots);
+  for (int i = 0; i < 16; ++i) c->keep[i] = 1.f;
+  for (const BlockPlan& b : c->plan.blocks)
+    if (b.dc_idx >= 0) c->keep[b.dc_idx] = 1.f - b.dc_rate;
+  c->device = device;
+  if (device >= 0) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+      delete c;
+      return fail(MLIIS_ERR_DEVICE, "no CUDA device %d: %s (no CPU fallback exists)", device,
+                  cudaGetErrorString(cudaGetLastError()));
+    }
+    if (prop.major != 10) {
+      delete c;
+      return fail(MLIIS_ERR_DEVICE, "device %d is sm_%d%d, this library is sm_100a only (no fallback)", device,
+                  prop.major, prop.minor);
+    }
+    cudaSetDevice(device);
+    const Plan& p = c->plan;
+    std::vector<int32_t> gi(p.n_bn_ch), bi(p.n_bn_ch);
+    auto fill = [&](const BnRef& r) {
+      if (r.idx < 0) return;
+      for (int ch = 0; ch < r.C; ++ch) { gi[r.off + ch] = (int32_t)(r.gamma + ch); bi[r.off + ch] = (int32_t)(r.beta + ch); }
+    };
+    fill(p.bn_stem);
+    for (const BlockPlan& b : p.blocks) { fill(b.bn0); fill(b.bn1); fill(b.bn2); }
+    for (const RsdPlan& d : p.rsds) for (int j = 0; j < 3; ++j) fill(d.bn[j]);
+    c->d_gamma_idx = upload(c, gi);
+    c->d_beta_idx = upload(c, bi);
+    c->tabs.resize(p.resize_pairs.size());
+    bool ok = c->d_gamma_idx && c->d_beta_idx;
+    for (size_t i = 0; ok && i < p.resize_pairs.size(); ++i)
+      ok = make_tab(c, p.resize_pairs[i].first, p.resize_pairs[i].second, &c->tabs[i]);
+    if (!ok) { mliis_ctx_destroy(c); return fail(MLIIS_ERR_CUDA, "device table allocation failed"); }
+  }
+  *out = c;
+  return MLIIS_OK;
+}
+
+int mliis_ctx_destroy(mliis_ctx* ctx) {
+  if (!ctx) return MLIIS_OK;
+  for (void* p : ctx->owned) cudaFree(p);
+  delete ctx;
+  return MLIIS_OK;
+}
+
+int64_t mliis_num_params(const mliis_ctx* c) { return c ? c->plan.n_params : -1; }
+int32_t mliis_num_param_tensors(const mliis_ctx* c) { return c ? (int32_t)c->plan.params.size() : -1; }
+int32_t mliis_num_bn_layers(const mliis_ctx* c) { return c ? (int32_t)c->plan.bns.size() : -1; }
+int32_t mliis_num_bn_channels(const mliis_ctx* c) { return c ? c->plan.n_bn_ch : -1; }
+int32_t mliis_num_dc_blocks(const mliis_ctx* c) { return c ? c->plan.n_dc : -1; }
+
+int mliis_param_table(const mliis_ctx* c, mliis_param_info* out, int32_t capacity) {
+  if (!c || !out) return fail(MLIIS_ERR_ARG, "null argument");
+  if (capacity < (int)c->plan.params.size()) return fail(MLIIS_ERR_ARG, "capacity too small");
+  for (size_t i = 0; i < c->plan.params.size(); ++i) {
+    const ParamEntry& e = c->plan.params[i];
+    out[i].name = e.name.c_str();
+    out[i].offset = e.offset;
+    out[i].size = e.size;
+    out[i].ndim = e.ndim;
+    for (int j = 0; j < 4; ++j) out[i].shape[j] = e.shape[j];
+    out[i].l2 = e.l2;
+  }
+  return MLIIS_OK;
+}
+
+int mliis_bn_table(const mliis_ctx* c, mliis_bn_info* out, int32_t capacity) {
+  if (!c || !out) return fail(MLIIS_ERR_ARG, "null argument");
+  if (capacity < (int)c->plan.bns.size()) return fail(MLIIS_ERR_ARG, "capacity too small");
+  for (size_t i = 0; i < c->plan.bns.size(); ++i) {
+    out[i].scope = c->plan.bns[i].scope.c_str();
+    out[i].channels = c->plan.bns[i].C;
+    out[i].offset = c->plan.bns[i].off;
+    out[i].fused = c->plan.bns[i].fused;
+  }
+  return MLIIS_OK;
+}
+
+int64_t mliis_workspace_bytes(const mliis_ctx* c) { return c ? c->plan.ws_floats * (int64_t)sizeof(float) : -1; }
+int64_t mliis_state_floats(const mliis_ctx* c) {
+  return c ? 2 * c->plan.n_theta + 2 * (int64_t)c->plan.n_bn_ch + 4 : -1;
+}
+int64_t mliis_theta_floats(const mliis_ctx* c) { return c ? c->plan.n_theta : -1; }
+
+int mliis_slot_bind(mliis_ctx* ctx, int32_t slot, float* dev_state, void* dev_workspace) {
+  if (!ctx) return fail(MLIIS_ERR_ARG, "null ctx");
+  if (slot < 0 || slot >= (int)ctx->slots.size()) return fail(MLIIS_ERR_ARG, "slot out of range");
+  if (((uintptr_t)dev_state & 15) || ((uintptr_t)dev_workspace & 255)) return fail(MLIIS_ERR_ARG, "misaligned buffers");
+  ctx->slots[slot] = Slot();
+  ctx->slots[slot].state = dev_state;
+  ctx->slots[slot].ws = (float*)dev_workspace;
+  return MLIIS_OK;
+}
+
+int mliis_state_copy(mliis_ctx* ctx, float* dst, const float* src, int32_t what, void* stream) {
+  if (!ctx || !dst || !src) return fail(MLIIS_ERR_ARG, "null argument");
+  if (ctx->device < 0) return fail(MLIIS_ERR_DEVICE, "table-only ctx");
+  const Plan& p = ctx->plan;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t o_bn = p.n_theta, o_opt = p.n_theta + 2 * p.n_bn_ch;
+  if (what & MLIIS_STATE_TRAINABLES) cudaMemcpyAsync(dst, src, p.n_theta * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  if (what & MLIIS_STATE_BN)
+    cudaMemcpyAsync(dst + o_bn, src + o_bn, 2 * (size_t)p.n_bn_ch * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  if (what & MLIIS_STATE_OPT)
+    cudaMemcpyAsync(dst + o_opt, src + o_opt, ((size_t)p.n_theta + 4) * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  return check_cuda("state_copy");
+}
+
+int mliis_forward(mliis_ctx* ctx, int32_t slot, const float* images, const int32_t* index, int32_t batch,
+                  int32_t training, const float* dc_mask, const float* drop_mask, uint64_t seed, float* logits_out,
+                  void* stream) {
+  int rc = validate(ctx, slot, batch);
+  if (rc) return rc;
+  if (!images) return fail(MLIIS_ERR_ARG, "null images");
+  Run r(ctx, slot, batch, (cudaStream_t)stream);
+  run_forward(r, images, index, training != 0, dc_mask, drop_mask, seed);
+  if (logits_out) {
+    const Plan& p = ctx->plan;
+    const Tab& tf = ctx->tabs[p.tab_final];
+    predict_mask_iou(r.W(p.z_lo), nullptr, nullptr, batch, p.hl, p.wl, p.image_size, p.image_size, tf.rt(), tf.rt(),
+                     nullptr, logits_out, nullptr, nullptr, r.st);
+  }
+  return check_cuda("forward");
+}
+
+int mliis_loss_backward(mliis_ctx* ctx, int32_t slot, const float* labels, const int32_t* index, int32_t batch,
+                        float* grads_out, float* loss_out, void* stream) {
+  int rc = validate(ctx, slot, batch);
+  if (rc) return rc;
+  Slot& sl = ctx->slots[slot];
+  if (!sl.fwd_training || sl.fwd_batch != batch) return fail(MLIIS_ERR_STATE, "loss_backward needs a training forward of the same batch");
+  if (!labels) return fail(MLIIS_ERR_ARG, "null labels");
+  Run r(ctx, slot, batch, (cudaStream_t)stream);
+  run_backward(r, labels, index, loss_out);
+  if (grads_out)
+    cudaMemcpyAsync(grads_out, r.G(0), ctx->plan.n_theta * sizeof(float), cudaMemcpyDeviceToDevice, r.st);
+  return check_cuda("loss_backward");
+}
+
+int mliis_optimizer_step(mliis_ctx* ctx, int32_t slot, float lr, float pre_decay_rate, void* stream) {
+  int rc = validate(ctx, slot, 1);
+  if (rc) return rc;
+  (void)pre_decay_rate;
+  Run r(ctx, slot, 1, (cudaStream_t)stream);
+  set_lr(r, lr);
+  run_optimizer(r, r.W(ctx->plan.lr_dev));
+  return check_cuda("optimizer_step");
+}
+
+int mliis_train_step(mliis_ctx* ctx, int32_t slot, const mliis_step_args* a, void* stream) {
+  if (!a) return fail(MLIIS_ERR_ARG, "null args");
+  int rc = validate(ctx, slot, a->batch);
+  if (rc) return rc;
+  if (!a->dev_images || !a->dev_labels) return fail(MLIIS_ERR_ARG, "null images/labels");
+  Run r(ctx, slot, a->batch, (cudaStream_t)stream);
+  // reptile.py:112-113 pre_step_op: var *= rate, before the step's forward pass
+  if (a->pre_decay_rate != 1.f && a->pre_decay_rate != 0.f) scale_buffer(r.theta, ctx->plan.n_theta, a->pre_decay_rate, r.st);
+  run_forward(r, a->dev_images, a->dev_index, true, a->dev_dc_mask, a->dev_drop_mask, a->seed);
+  run_backward(r, a->dev_labels, a->dev_index, a->dev_loss_out);
+  set_lr(r, a->lr);
+  run_optimizer(r, r.W(ctx->plan.lr_dev));
+  return check_cuda("train_step");
+}
+
+int mliis_predict(mliis_ctx* ctx, int32_t slot, const float* images, const float* labels, const int32_t* index,
+                  int32_t batch, float* pred_out, float* logits_out, uint32_t* inter_out, uint32_t* union_out,
+                  void* stream) {
+  int rc = validate(ctx, slot, batch);
+  if (rc) return rc;
+  if (!images) return fail(MLIIS_ERR_ARG, "null images");
+  if ((inter_out || union_out) && !(inter_out && union_out && labels))
+    return fail(MLIIS_ERR_ARG, "IoU counts need labels, inter_out and union_out");
+  Run r(ctx, slot, batch, (cudaStream_t)stream);
+  run_forward(r, images, index, false, nullptr, nullptr, 0);
+  const Plan& p = ctx->plan;
+  const Tab& tf = ctx->tabs[p.tab_final];
+  predict_mask_iou(r.W(p.z_lo), labels, index, batch, p.hl, p.wl, p.image_size, p.image_size, tf.rt(), tf.rt(), pred_out,
+                   logits_out, inter_out, union_out, r.st);
+  return check_cuda("predict");
+}
+
+int mliis_adapt_eval_task(mliis_ctx* ctx, int32_t slot, const mliis_task_args* a, void* stream) {
+  if (!a) return fail(MLIIS_ERR_ARG, "null args");
+  int rc = validate(ctx, slot, a->batch);
+  if (rc) return rc;
+  if (a->n_query < 1 || a->n_query > ctx->plan.maxB) return fail(MLIIS_ERR_ARG, "n_query out of range");
+  if (!a->dev_init_state || !a->dev_images || !a->dev_labels || !a->dev_batch_index || !a->dev_lr || !a->dev_query_index)
+    return fail(MLIIS_ERR_ARG, "null task argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Plan& p = ctx->plan;
+  rc = mliis_state_copy(ctx, ctx->slots[slot].state, a->dev_init_state, MLIIS_STATE_ALL, stream);
+  if (rc) return rc;
+  for (int t = 0; t < a->n_steps; ++t) {
+    Run r(ctx, slot, a->batch, st);
+    if (a->pre_decay_rate != 1.f && a->pre_decay_rate != 0.f) scale_buffer(r.theta, p.n_theta, a->pre_decay_rate, st);
+    const int32_t* idx = a->dev_batch_index + (size_t)t * a->batch;
+    const float* dcm = a->dev_dc_mask ? a->dev_dc_mask + (size_t)t * p.n_dc * a->batch : nullptr;
+    run_forward(r, a->dev_images, idx, true, dcm, nullptr, a->seed + (uint64_t)t);
+    run_backward(r, a->dev_labels, idx, a->dev_loss_out ? a->dev_loss_out + t : nullptr);
+    run_optimizer(r, a->dev_lr + t);
+  }
+  Run r(ctx, slot, a->n_query, st);
+  run_forward(r, a->dev_images, a->dev_query_index, false, nullptr, nullptr, 0);
+  const Tab& tf = ctx->tabs[p.tab_final];
+  predict_mask_iou(r.W(p.z_lo), a->dev_labels, a->dev_query_index, a->n_query, p.hl, p.wl, p.image_size, p.image_size,
+                   tf.rt(), tf.rt(), nullptr, nullptr, a->dev_inter_out, a->dev_union_out, st);
+  return check_cuda("adapt_eval_task");
+}
+
+int mliis_delta_accumulate(mliis_ctx* ctx, float* dsum, const float* ta, const float* tb, int32_t first, void* stream) {
+  if (!ctx || !dsum || !ta || !tb) return fail(MLIIS_ERR_ARG, "null argument");
+  if (ctx->device < 0) return fail(MLIIS_ERR_DEVICE, "table-only ctx");
+  delta_accumulate(dsum, ta, tb, ctx->plan.n_theta, first, (cudaStream_t)stream);
+  return check_cuda("delta_accumulate");
+}
+int mliis_meta_apply(mliis_ctx* ctx, float* theta, const float* dsum, float scale, void* stream) {
+  if (!ctx || !theta || !dsum) return fail(MLIIS_ERR_ARG, "null argument");
+  if (ctx->device < 0) return fail(MLIIS_ERR_DEVICE, "table-only ctx");
+  meta_apply(theta, dsum, scale, ctx->plan.n_theta, (cudaStream_t)stream);
+  return check_cuda("meta_apply");
+}
+
+// ---- per-kernel entry points ----
+static int require_sm100() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(MLIIS_ERR_DEVICE, "no CUDA device (no CPU fallback exists)");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10)
+    return fail(MLIIS_ERR_DEVICE, "not an sm_100 device (no fallback)");
+  return MLIIS_OK;
+}
+
+int mliis_dwconv_fwd(const float* x, const float* w, float* y, int32_t B, int32_t H, int32_t W, int32_t C, int32_t k,
+                     int32_t stride, const float* bn_a, const float* bn_b, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if ((k != 3 && k != 5) || (stride != 1 && stride != 2) || C % 4) return fail(MLIIS_ERR_ARG, "unsupported depthwise shape");
+  int pt, pb;
+  same_pad(H, k, stride, 1, &pt, &pb);
+  int pl, pr;
+  same_pad(W, k, stride, 1, &pl, &pr);
+  dw_fwd(x, bn_a, bn_b, w, y, B, H, W, C, k, stride, (H + stride - 1) / stride, (W + stride - 1) / stride, pt, pl,
+         (cudaStream_t)stream);
+  return check_cuda("dwconv_fwd");
+}
+
+int mliis_gemm_nn(const float* a, const float* w, float* c, int32_t M, int32_t K, int32_t N, int32_t mode, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (K % 8 || N % 4) return fail(MLIIS_ERR_ARG, "K must be a multiple of 8 and N of 4");
+  (void)mode;
+  gemm_nn(plainA(a, K), w, nullptr, c, N, M, K, N, M, 0, (cudaStream_t)stream);
+  return check_cuda("gemm_nn");
+}
+
+int mliis_conv3x3_fwd(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t H, int32_t W,
+                      int32_t Cin, int32_t Cout, int32_t dilation, int32_t mode, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (Cin % 8 || Cout % 4) return fail(MLIIS_ERR_ARG, "Cin must be a multiple of 8 and Cout of 4");
+  (void)mode;
+  gemm_nn(convA(x, Cin, H, W, Cin, dilation), w, bias, y, Cout, B * H * W, 9 * Cin, Cout, H * W, 0, (cudaStream_t)stream);
+  return check_cuda("conv3x3_fwd");
+}
+
+int mliis_bilinear_fwd(const float* x, float* y, int32_t B, int32_t Hin, int32_t Win, int32_t Hout, int32_t Wout,
+                       int32_t C, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (C % 4) return fail(MLIIS_ERR_ARG, "C must be a multiple of 4");
+  Tab ty, tx;
+  if (!make_tab(nullptr, Hin, Hout, &ty) || !make_tab(nullptr, Win, Wout, &tx)) return fail(MLIIS_ERR_CUDA, "table alloc");
+  bilinear_fwd(x, C, y, C, B, Hin, Win, Hout, Wout, C, ty.rt(), tx.rt(), (cudaStream_t)stream);
+  cudaStreamSynchronize((cudaStream_t)stream);
+  for (Tab* t : {&ty, &tx}) { cudaFree(t->lo); cudaFree(t->hi); cudaFree(t->lerp); cudaFree(t->g_lo); cudaFree(t->g_hi); }
+  return check_cuda("bilinear_fwd");
+}
+
+int mliis_adam_step(float* theta, float* v, const float* grad, int64_t n, int64_t n_l2, float lr, float beta2_power,
+                    float l2_coef, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  float* tmp = nullptr;
+  if (cudaMalloc(&tmp, 4 * sizeof(float)) != cudaSuccess) return fail(MLIIS_ERR_CUDA, "alloc");
+  const float h[4] = {0.f, beta2_power, lr, 0.f};
+  cudaMemcpy(tmp, h, sizeof h, cudaMemcpyHostToDevice);
+  adam_step(theta, v, grad, n, n_l2, tmp + 2, tmp, l2_coef, 0, (cudaStream_t)stream);
+  cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(tmp);
+  return check_cuda("adam_step");
+}
+
+int mliis_debug_buffer(mliis_ctx* ctx, int32_t slot, const char* name, const float** dev_ptr, int64_t* rows_per_image,
+                       int32_t* channels, int32_t* ld) {
+  if (!ctx || !name || !dev_ptr) return fail(MLIIS_ERR_ARG, "null argument");
+  if (slot < 0 || slot >= (int)ctx->slots.size() || !ctx->slots[slot].ws) return fail(MLIIS_ERR_STATE, "slot not bound");
+  const Plan& p = ctx->plan;
+  if (std::strcmp(name, "grads") == 0) {
+    *dev_ptr = ctx->slots[slot].ws + p.grads;
+    if (rows_per_image) *rows_per_image = 1;
+    if (channels) *channels = (int32_t)p.n_theta;
+    if (ld) *ld = (int32_t)p.n_theta;
+    return MLIIS_OK;
+  }
+  for (const Plan::Named& n : p.named) {
+    if (n.name == name) {
+      *dev_ptr = ctx->slots[slot].ws + n.buf.off;
+      if (rows_per_image) *rows_per_image = n.buf.HW;
+      if (channels) *channels = n.buf.C;
+      if (ld) *ld = n.buf.ld;
+      return MLIIS_OK;
+    }
+  }
+  return fail(MLIIS_ERR_ARG, "unknown buffer '%s'", name);
+}
+
+}  // extern "C"

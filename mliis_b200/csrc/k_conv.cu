@@ -1,0 +1,436 @@
+// Stem conv (normalise + 3x3 s2) and depthwise k x k convolutions, forward / dgrad / wgrad.
+//
+// Depthwise kernels are HBM-bound stencils.  Design: one CTA = one image x one output tile x 32
+// channels.  The input tile (with halo) is staged ONCE in shared memory - the producing BatchNorm's
+// normalise + swish is applied while staging (prologue fusion: the activated tensor never exists in
+// HBM) - and every thread then produces a strip of 7 consecutive outputs for one float4 of channels,
+// re-using each shared-memory operand across the strip (K + 6S loads for 7K FMAs per filter row).
+// All spatial sizes of the canonical network (112, 56, 28, 14) are multiples of 7.
+//
+// Reference: efficientnet_model.py:190-196 (DepthwiseConv2D, SAME), :359-366 (stem), TF SAME padding
+// is asymmetric for stride 2 (pad_lo = total/2) and is passed in as pad_t/pad_l.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mliis {
+
+// =============================================================================================
+// stem
+// =============================================================================================
+__device__ __forceinline__ void load_norm_pixel(const float* px, float& r, float& g, float& b) {
+  r = (px[0] - kMeanR) / kStdR;
+  g = (px[1] - kMeanG) / kStdG;
+  b = (px[2] - kMeanB) / kStdB;
+}
+
+__global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__ images,
+                                                        const int32_t* __restrict__ index,
+                                                        const float* __restrict__ w, float* __restrict__ y, int B,
+                                                        int H, int W, int Ho, int Wo, int pad_t, int pad_l) {
+  __shared__ __align__(16) float ws[27 * 32];
+  for (int i = threadIdx.x; i < 27 * 32; i += 256) ws[i] = w[i];
+  __syncthreads();
+  const int p = blockIdx.x * 64 + (threadIdx.x >> 2);
+  const int cg = threadIdx.x & 3;
+  if (p >= B * Ho * Wo) return;
+  const int b = p / (Ho * Wo), rem = p - b * (Ho * Wo), oy = rem / Wo, ox = rem - oy * Wo;
+  const int img = index ? index[b] : b;
+  const float* im = images + (size_t)img * H * W * 3;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * 2 - pad_t + ky;
+    if (iy < 0 || iy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ox * 2 - pad_l + kx;
+      if (ix < 0 || ix >= W) continue;
+      float v[3];
+      load_norm_pixel(im + ((size_t)iy * W + ix) * 3, v[0], v[1], v[2]);
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float* wr = ws + ((ky * 3 + kx) * 3 + ci) * 32 + cg * 8;
+        const float4 w0 = ld4(wr), w1 = ld4(wr + 4);
+        acc[0] = fmaf(v[ci], w0.x, acc[0]); acc[1] = fmaf(v[ci], w0.y, acc[1]);
+        acc[2] = fmaf(v[ci], w0.z, acc[2]); acc[3] = fmaf(v[ci], w0.w, acc[3]);
+        acc[4] = fmaf(v[ci], w1.x, acc[4]); acc[5] = fmaf(v[ci], w1.y, acc[5]);
+        acc[6] = fmaf(v[ci], w1.z, acc[6]); acc[7] = fmaf(v[ci], w1.w, acc[7]);
+      }
+    }
+  }
+  float* o = y + (size_t)p * 32 + cg * 8;
+  st4(o, f4(acc[0], acc[1], acc[2], acc[3]));
+  st4(o + 4, f4(acc[4], acc[5], acc[6], acc[7]));
+}
+
+void stem_fwd(const float* images, const int32_t* index, const float* w, float* y, int B, int H, int W, int Ho, int Wo,
+              int pad_t, int pad_l, cudaStream_t s) {
+  stem_fwd_kernel<<<cdiv(B * Ho * Wo, 64), 256, 0, s>>>(images, index, w, y, B, H, W, Ho, Wo, pad_t, pad_l);
+}
+
+constexpr int kStemWgPix = 512;   // output pixels per CTA
+int stem_wgrad_blocks(int B, int Ho, int Wo) { return cdiv(B * Ho * Wo, kStemWgPix); }
+
+// dW[k = tap*3+ci][co] partial per CTA.  288 threads: co = t%32, kg = t/32 -> k = kg*3 + {0,1,2}.
+__global__ void __launch_bounds__(288) stem_wgrad_kernel(const float* __restrict__ images,
+                                                          const int32_t* __restrict__ index,
+                                                          const float* __restrict__ dy, float* __restrict__ partials,
+                                                          int B, int H, int W, int Ho, int Wo, int pad_t, int pad_l) {
+  __shared__ float xs[64][28];
+  __shared__ float gs[64][32];
+  const int tid = threadIdx.x, co = tid & 31, kg = tid >> 5;
+  const int total = B * Ho * Wo;
+  const int p_begin = blockIdx.x * kStemWgPix;
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+  for (int base = p_begin; base < min(total, p_begin + kStemWgPix); base += 64) {
+    for (int i = tid; i < 64 * 27; i += 288) {
+      const int lp = i / 27, k = i - lp * 27;
+      const int p = base + lp;
+      float v = 0.f;
+      if (p < total) {
+        const int b = p / (Ho * Wo), rem = p - b * (Ho * Wo), oy = rem / Wo, ox = rem - oy * Wo;
+        const int tap = k / 3, ci = k - tap * 3, ky = tap / 3, kx = tap - ky * 3;
+        const int iy = oy * 2 - pad_t + ky, ix = ox * 2 - pad_l + kx;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+          const int img = index ? index[b] : b;
+          const float raw = images[(((size_t)img * H + iy) * W + ix) * 3 + ci];
+          const float mean = ci == 0 ? kMeanR : (ci == 1 ? kMeanG : kMeanB);
+          const float sd = ci == 0 ? kStdR : (ci == 1 ? kStdG : kStdB);
+          v = (raw - mean) / sd;
+        }
+      }
+      xs[lp][k] = v;
+    }
+    for (int i = tid; i < 64 * 32; i += 288) {
+      const int lp = i >> 5, c = i & 31;
+      const int p = base + lp;
+      gs[lp][c] = p < total ? dy[(size_t)p * 32 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int lp = 0; lp < 64; ++lp) {
+      const float g = gs[lp][co];
+      acc0 = fmaf(xs[lp][kg * 3 + 0], g, acc0);
+      acc1 = fmaf(xs[lp][kg * 3 + 1], g, acc1);
+      acc2 = fmaf(xs[lp][kg * 3 + 2], g, acc2);
+    }
+    __syncthreads();
+  }
+  float* o = partials + (size_t)blockIdx.x * 864;
+  o[(kg * 3 + 0) * 32 + co] = acc0;
+  o[(kg * 3 + 1) * 32 + co] = acc1;
+  o[(kg * 3 + 2) * 32 + co] = acc2;
+}
+
+void stem_wgrad(const float* images, const int32_t* index, const float* dy, float* partials, float* dw, int B, int H,
+                int W, int Ho, int Wo, int pad_t, int pad_l, cudaStream_t s) {
+  int G = stem_wgrad_blocks(B, Ho, Wo);
+  stem_wgrad_kernel<<<G, 288, 0, s>>>(images, index, dy, partials, B, H, W, Ho, Wo, pad_t, pad_l);
+  reduce_partials(partials, G, 864, dw, s);
+}
+
+// =============================================================================================
+// depthwise
+// =============================================================================================
+constexpr int QC = 8;  // float4 channel groups per CTA (32 channels)
+
+template <int K, int S>
+struct DwGeom {
+  static constexpr int TO = (S == 1) ? 14 : 7;          // output tile edge
+  static constexpr int SPR = TO / 7;                    // strips per tile row
+  static constexpr int NSTRIP = TO * SPR;               // 28 | 7
+  static constexpr int NT = (S == 1) ? 224 : 64;        // threads (S=2: 56 active + 8 idle, warp aligned)
+  static constexpr int TI = (TO - 1) * S + K;           // staged input tile edge
+  static constexpr int NIN = 6 * S + K;                 // inputs per strip row
+  static constexpr size_t smem_bytes() { return (size_t)(TI * TI + K * K) * QC * sizeof(float4); }
+};
+
+// stage swish(a*x+b) (or x when a == null) of the input tile into shared memory
+template <int K, int S>
+__device__ __forceinline__ void dw_stage_input(float4* tile, const float* __restrict__ x,
+                                               const float* __restrict__ a, const float* __restrict__ b, int img,
+                                               int H, int W, int C, int c0, int iy0, int ix0) {
+  using G = DwGeom<K, S>;
+  const int tid = threadIdx.x, q = tid % QC;
+  const bool cvalid = c0 + q * 4 < C;
+  float4 av = f4s(1.f), bv = f4s(0.f);
+  if (a && cvalid) { av = ld4(a + c0 + q * 4); bv = ld4(b + c0 + q * 4); }
+  for (int i = tid; i < G::TI * G::TI * QC; i += G::NT) {
+    const int pix = i / QC, ly = pix / G::TI, lx = pix - ly * G::TI;
+    const int gy = iy0 + ly, gx = ix0 + lx;
+    float4 v = f4s(0.f);
+    if (cvalid && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      v = ld4(x + (((size_t)img * H + gy) * W + gx) * C + c0 + q * 4);
+      if (a) v = swish4(affine4(v, av, bv));
+    }
+    tile[i] = v;
+  }
+}
+
+// FLIP: use w[K-1-ky][K-1-kx] (stride-1 dgrad == correlation with the flipped filter)
+template <int K, int S, bool FLIP>
+__global__ void __launch_bounds__(DwGeom<K, S>::NT) dw_fwd_kernel(const float* __restrict__ x,
+                                                                   const float* __restrict__ a,
+                                                                   const float* __restrict__ b,
+                                                                   const float* __restrict__ w, float* __restrict__ y,
+                                                                   int H, int W, int C, int Ho, int Wo, int pad_t,
+                                                                   int pad_l, int tiles_x) {
+  using G = DwGeom<K, S>;
+  extern __shared__ float4 smem4[];
+  float4* tile = smem4;
+  float4* wsm = smem4 + G::TI * G::TI * QC;
+  const int tid = threadIdx.x, q = tid % QC, strip = tid / QC;
+  const int ty0 = (blockIdx.x / tiles_x) * G::TO, tx0 = (blockIdx.x % tiles_x) * G::TO;
+  const int c0 = blockIdx.y * (QC * 4), img = blockIdx.z;
+  for (int i = tid; i < K * K * QC; i += G::NT) {
+    const int qq = i % QC, tap = i / QC;
+    const int src = FLIP ? (K * K - 1 - tap) : tap;
+    wsm[i] = (c0 + qq * 4 < C) ? ld4(w + (size_t)src * C + c0 + qq * 4) : f4s(0.f);
+  }
+  dw_stage_input<K, S>(tile, x, a, b, img, H, W, C, c0, ty0 * S - pad_t, tx0 * S - pad_l);
+  __syncthreads();
+  if (strip >= G::NSTRIP) return;
+  const int oy = strip / G::SPR, ox0 = (strip % G::SPR) * 7;
+  float4 acc[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) acc[j] = f4s(0.f);
+#pragma unroll
+  for (int ky = 0; ky < K; ++ky) {
+    const float4* row = tile + ((size_t)(oy * S + ky) * G::TI + ox0 * S) * QC + q;
+    float4 in[G::NIN];
+#pragma unroll
+    for (int j = 0; j < G::NIN; ++j) in[j] = row[j * QC];
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) {
+      const float4 wv = wsm[(ky * K + kx) * QC + q];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) fma4(acc[j], in[j * S + kx], wv);
+    }
+  }
+  const int gy = ty0 + oy;
+  if (gy < Ho && c0 + q * 4 < C) {
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int gx = tx0 + ox0 + j;
+      if (gx < Wo) st4(y + (((size_t)img * Ho + gy) * Wo + gx) * C + c0 + q * 4, acc[j]);
+    }
+  }
+}
+
+template <int K, int S, bool FLIP>
+static void dw_fwd_launch(const float* x, const float* a, const float* b, const float* w, float* y, int B, int H, int W,
+                          int C, int Ho, int Wo, int pad_t, int pad_l, cudaStream_t s) {
+  using G = DwGeom<K, S>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(dw_fwd_kernel<K, S, FLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes());
+    attr_done = true;
+  }
+  const int tiles_x = cdiv(Wo, G::TO), tiles_y = cdiv(Ho, G::TO);
+  dim3 grid(tiles_x * tiles_y, cdiv(C, QC * 4), B);
+  dw_fwd_kernel<K, S, FLIP><<<grid, G::NT, G::smem_bytes(), s>>>(x, a, b, w, y, H, W, C, Ho, Wo, pad_t, pad_l, tiles_x);
+}
+
+void dw_fwd(const float* x, const float* a, const float* b, const float* w, float* y, int B, int H, int W, int C, int k,
+            int stride, int Ho, int Wo, int pad_t, int pad_l, cudaStream_t s) {
+  if (k == 3 && stride == 1) dw_fwd_launch<3, 1, false>(x, a, b, w, y, B, H, W, C, Ho, Wo, pad_t, pad_l, s);
+  else if (k == 3 && stride == 2) dw_fwd_launch<3, 2, false>(x, a, b, w, y, B, H, W, C, Ho, Wo, pad_t, pad_l, s);
+  else if (k == 5 && stride == 1) dw_fwd_launch<5, 1, false>(x, a, b, w, y, B, H, W, C, Ho, Wo, pad_t, pad_l, s);
+  else dw_fwd_launch<5, 2, false>(x, a, b, w, y, B, H, W, C, Ho, Wo, pad_t, pad_l, s);
+}
+
+// ---- stride-2 dgrad: dx[iy,ix] = sum_{ky,kx : parity ok} dy[(iy+pad_t-ky)/2, (ix+pad_l-kx)/2] * w[ky,kx]
+template <int K>
+struct DwBd2 {
+  static constexpr int TO = 14;                       // dx tile edge
+  static constexpr int TD = 7 + (K + 1) / 2 + 1;      // staged dy tile edge (10 | 11)
+  static constexpr int NT = 224;
+  static constexpr size_t smem_bytes() { return (size_t)(TD * TD + K * K) * QC * sizeof(float4); }
+};
+
+template <int K>
+__global__ void __launch_bounds__(224) dw_bwd_data_s2_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                              float* __restrict__ dx, int H, int W, int C, int Ho,
+                                                              int Wo, int pad_t, int pad_l, int tiles_x) {
+  using G = DwBd2<K>;
+  extern __shared__ float4 smem4[];
+  float4* tile = smem4;
+  float4* wsm = smem4 + G::TD * G::TD * QC;
+  const int tid = threadIdx.x, q = tid % QC, strip = tid / QC;
+  const int ty0 = (blockIdx.x / tiles_x) * G::TO, tx0 = (blockIdx.x % tiles_x) * G::TO;
+  const int c0 = blockIdx.y * (QC * 4), img = blockIdx.z;
+  const bool cvalid = c0 + q * 4 < C;
+  for (int i = tid; i < K * K * QC; i += G::NT) {
+    const int qq = i % QC, tap = i / QC;
+    wsm[i] = (c0 + qq * 4 < C) ? ld4(w + (size_t)tap * C + c0 + qq * 4) : f4s(0.f);
+  }
+  // first dy row/col that any dx of this tile can touch (floor division, may be negative)
+  const int oy_lo = (ty0 + pad_t - (K - 1)) >> 1, ox_lo = (tx0 + pad_l - (K - 1)) >> 1;
+  for (int i = tid; i < G::TD * G::TD * QC; i += G::NT) {
+    const int pix = i / QC, ly = pix / G::TD, lx = pix - ly * G::TD;
+    const int gy = oy_lo + ly, gx = ox_lo + lx;
+    float4 v = f4s(0.f);
+    if (cvalid && gy >= 0 && gy < Ho && gx >= 0 && gx < Wo)
+      v = ld4(dy + (((size_t)img * Ho + gy) * Wo + gx) * C + c0 + q * 4);
+    tile[i] = v;
+  }
+  __syncthreads();
+  const int iy = ty0 + strip / 2, ix0 = tx0 + (strip & 1) * 7;
+  float4 acc[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) acc[j] = f4s(0.f);
+#pragma unroll
+  for (int ky = 0; ky < K; ++ky) {
+    const int t = iy + pad_t - ky;
+    if (t & 1) continue;
+    const int ly = (t >> 1) - oy_lo;
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) {
+      const float4 wv = wsm[(ky * K + kx) * QC + q];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const int u = ix0 + j + pad_l - kx;
+        if ((u & 1) == 0) {
+          const int lx = (u >> 1) - ox_lo;
+          fma4(acc[j], tile[((size_t)ly * G::TD + lx) * QC + q], wv);
+        }
+      }
+    }
+  }
+  if (iy < H && cvalid) {
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int gx = ix0 + j;
+      if (gx < W) st4(dx + (((size_t)img * H + iy) * W + gx) * C + c0 + q * 4, acc[j]);
+    }
+  }
+}
+
+template <int K>
+static void dw_bwd_data_s2_launch(const float* dy, const float* w, float* dx, int B, int H, int W, int C, int Ho, int Wo,
+                                  int pad_t, int pad_l, cudaStream_t s) {
+  using G = DwBd2<K>;
+  const int tiles_x = cdiv(W, G::TO), tiles_y = cdiv(H, G::TO);
+  dim3 grid(tiles_x * tiles_y, cdiv(C, QC * 4), B);
+  dw_bwd_data_s2_kernel<K><<<grid, G::NT, G::smem_bytes(), s>>>(dy, w, dx, H, W, C, Ho, Wo, pad_t, pad_l, tiles_x);
+}
+
+void dw_bwd_data(const float* dy, const float* w, float* dx, int B, int H, int W, int C, int k, int stride, int Ho,
+                 int Wo, int pad_t, int pad_l, cudaStream_t s) {
+  if (stride == 1) {
+    // dx = correlate(dy, flip(w)) with pad' = k-1-pad ; output size == input size
+    if (k == 3) dw_fwd_launch<3, 1, true>(dy, nullptr, nullptr, w, dx, B, Ho, Wo, C, H, W, k - 1 - pad_t, k - 1 - pad_l, s);
+    else dw_fwd_launch<5, 1, true>(dy, nullptr, nullptr, w, dx, B, Ho, Wo, C, H, W, k - 1 - pad_t, k - 1 - pad_l, s);
+  } else {
+    if (k == 3) dw_bwd_data_s2_launch<3>(dy, w, dx, B, H, W, C, Ho, Wo, pad_t, pad_l, s);
+    else dw_bwd_data_s2_launch<5>(dy, w, dx, B, H, W, C, Ho, Wo, pad_t, pad_l, s);
+  }
+}
+
+// ---- wgrad: dW[ky,kx,c] = sum_{b,oy,ox} act(x)[oy*S-pad+ky, ox*S-pad+kx, c] * dy[oy,ox,c]
+int dw_wgrad_blocks(int B, int Ho, int Wo, int stride) {
+  const int TO = stride == 1 ? 14 : 7;
+  return B * cdiv(Ho, TO) * cdiv(Wo, TO);
+}
+
+template <int K, int S>
+__global__ void __launch_bounds__(DwGeom<K, S>::NT) dw_wgrad_kernel(const float* __restrict__ x,
+                                                                     const float* __restrict__ a,
+                                                                     const float* __restrict__ b,
+                                                                     const float* __restrict__ dy,
+                                                                     float* __restrict__ partials, int H, int W, int C,
+                                                                     int Ho, int Wo, int pad_t, int pad_l,
+                                                                     int tiles_x, int tiles) {
+  using G = DwGeom<K, S>;
+  constexpr int NW = G::NT / 32;
+  extern __shared__ float4 smem4[];
+  float4* tile = smem4;
+  const int tid = threadIdx.x, q = tid % QC, strip = tid / QC;
+  const int ty0 = (blockIdx.x / tiles_x) * G::TO, tx0 = (blockIdx.x % tiles_x) * G::TO;
+  const int c0 = blockIdx.y * (QC * 4), img = blockIdx.z;
+  const bool cvalid = c0 + q * 4 < C;
+  dw_stage_input<K, S>(tile, x, a, b, img, H, W, C, c0, ty0 * S - pad_t, tx0 * S - pad_l);
+  __syncthreads();
+  float4 wacc[K * K];
+#pragma unroll
+  for (int t = 0; t < K * K; ++t) wacc[t] = f4s(0.f);
+  if (strip < G::NSTRIP) {
+    const int oy = strip / G::SPR, ox0 = (strip % G::SPR) * 7;
+    float4 g[7];
+    const int gy = ty0 + oy;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int gx = tx0 + ox0 + j;
+      g[j] = (cvalid && gy < Ho && gx < Wo) ? ld4(dy + (((size_t)img * Ho + gy) * Wo + gx) * C + c0 + q * 4)
+                                             : f4s(0.f);
+    }
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+      const float4* row = tile + ((size_t)(oy * S + ky) * G::TI + ox0 * S) * QC + q;
+      float4 in[G::NIN];
+#pragma unroll
+      for (int j = 0; j < G::NIN; ++j) in[j] = row[j * QC];
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+        for (int j = 0; j < 7; ++j) fma4(wacc[ky * K + kx], in[j * S + kx], g[j]);
+    }
+  }
+  // reduce across the 4 strips of a warp (lane = strip_local*8 + q), then across warps via smem
+#pragma unroll
+  for (int t = 0; t < K * K; ++t) {
+    float4 v = wacc[t];
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+      v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+      v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
+      v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+    }
+    wacc[t] = v;
+  }
+  __syncthreads();   // everyone is done reading the tile: reuse it as reduction scratch
+  float4* red = smem4;  // [K*K][NW][QC]
+  const int warp = tid >> 5, lane = tid & 31;
+  if (lane < QC) {
+#pragma unroll
+    for (int t = 0; t < K * K; ++t) red[((size_t)t * NW + warp) * QC + lane] = wacc[t];
+  }
+  __syncthreads();
+  for (int i = tid; i < K * K * QC; i += G::NT) {
+    const int t = i / QC, qq = i - t * QC;
+    if (c0 + qq * 4 >= C) continue;
+    float4 s4 = red[((size_t)t * NW) * QC + qq];
+    for (int wv = 1; wv < NW; ++wv) s4 = s4 + red[((size_t)t * NW + wv) * QC + qq];
+    const size_t blk = (size_t)img * tiles + blockIdx.x;
+    st4(partials + (blk * (K * K) + t) * C + c0 + qq * 4, s4);
+  }
+}
+
+template <int K, int S>
+static void dw_wgrad_launch(const float* x, const float* a, const float* b, const float* dy, float* partials, float* dw,
+                            int B, int H, int W, int C, int Ho, int Wo, int pad_t, int pad_l, cudaStream_t s) {
+  using G = DwGeom<K, S>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(dw_wgrad_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes());
+    attr_done = true;
+  }
+  const int tiles_x = cdiv(Wo, G::TO), tiles_y = cdiv(Ho, G::TO), tiles = tiles_x * tiles_y;
+  dim3 grid(tiles, cdiv(C, QC * 4), B);
+  dw_wgrad_kernel<K, S><<<grid, G::NT, G::smem_bytes(), s>>>(x, a, b, dy, partials, H, W, C, Ho, Wo, pad_t, pad_l,
+                                                             tiles_x, tiles);
+  reduce_partials(partials, B * tiles, K * K * C, dw, s);
+}
+
+void dw_bwd_weight(const float* x, const float* a, const float* b, const float* dy, float* partials, float* dw, int B,
+                   int H, int W, int C, int k, int stride, int Ho, int Wo, int pad_t, int pad_l, cudaStream_t s) {
+  if (k == 3 && stride == 1) dw_wgrad_launch<3, 1>(x, a, b, dy, partials, dw, B, H, W, C, Ho, Wo, pad_t, pad_l, s);
+  else if (k == 3 && stride == 2) dw_wgrad_launch<3, 2>(x, a, b, dy, partials, dw, B, H, W, C, Ho, Wo, pad_t, pad_l, s);
+  else if (k == 5 && stride == 1) dw_wgrad_launch<5, 1>(x, a, b, dy, partials, dw, B, H, W, C, Ho, Wo, pad_t, pad_l, s);
+  else dw_wgrad_launch<5, 2>(x, a, b, dy, partials, dw, B, H, W, C, Ho, Wo, pad_t, pad_l, s);
+}
+
+}  // namespace mliis

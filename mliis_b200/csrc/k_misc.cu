@@ -1,0 +1,476 @@
+// Bilinear resize (align_corners=True) fwd/bwd, logits head, fused softmax-CE / soft-dice loss and its
+// gradient, prediction threshold + integer IoU counts, multi-tensor Adam/SGD, meta-update kernels.
+//
+// Reference: models/efficientlab.py:161-177 (dropout, head, resize, softmax), :291-327 (threshold, loss),
+// :329-396 (soft IoU); reptile.py:526-549 (_iou); meta_learners/variables.py:9-45; args.py:151-154.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mliis {
+
+// =============================================================================================
+// generic partial reducer (fixed order, double accumulation)
+// =============================================================================================
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int G, int n, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int g = 0; g < G; ++g) s += (double)partials[(size_t)g * n + i];
+  out[i] = (float)s;
+}
+void reduce_partials(const float* partials, int G, int n, float* out, cudaStream_t s) {
+  reduce_partials_kernel<<<cdiv(n, 256), 256, 0, s>>>(partials, G, n, out);
+}
+
+// =============================================================================================
+// bilinear, align_corners=True.  out = top + (bottom - top) * ylerp ; top = tl + (tr - tl) * xlerp [TF-ext]
+// =============================================================================================
+__global__ void bilinear_fwd_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int B,
+                                    int Hi, int Wi, int Ho, int Wo, ResizeTab ty, ResizeTab tx, int rows_per_block) {
+  const int cq = threadIdx.x;
+  const int M = B * Ho * Wo;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    const int b = r / (Ho * Wo), rem = r - b * (Ho * Wo), oy = rem / Wo, ox = rem - oy * Wo;
+    const int y0 = ty.lo[oy], y1 = ty.hi[oy], x0 = tx.lo[ox], x1 = tx.hi[ox];
+    const float yl = ty.lerp[oy], xl = tx.lerp[ox];
+    const float* base = x + (size_t)b * Hi * Wi * ldx + cq * 4;
+    const float4 tl = ld4(base + ((size_t)y0 * Wi + x0) * ldx), tr = ld4(base + ((size_t)y0 * Wi + x1) * ldx);
+    const float4 bl = ld4(base + ((size_t)y1 * Wi + x0) * ldx), br = ld4(base + ((size_t)y1 * Wi + x1) * ldx);
+    const float4 top = tl + (tr - tl) * xl, bot = bl + (br - bl) * xl;
+    st4(y + (size_t)r * ldy + cq * 4, top + (bot - top) * yl);
+  }
+}
+void bilinear_fwd(const float* x, int ldx, float* y, int ldy, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                  ResizeTab ty, ResizeTab tx, cudaStream_t s) {
+  int c4 = C / 4, R = 256 / c4;
+  if (R < 1) R = 1;
+  if (R > 64) R = 64;
+  dim3 blk(c4, R);
+  int rpb = R * 4;
+  bilinear_fwd_kernel<<<cdiv(B * Ho * Wo, rpb), blk, 0, s>>>(x, ldx, y, ldy, B, Hi, Wi, Ho, Wo, ty, tx, rpb);
+}
+
+__device__ __forceinline__ float gather_w(const ResizeTab& t, int o, int i) {
+  const float l = t.lerp[o];
+  return (t.lo[o] == i ? 1.f - l : 0.f) + (t.hi[o] == i ? l : 0.f);
+}
+
+// gather form of the adjoint: dx[iy,ix] = sum_{oy,ox} wy(oy,iy) * wx(ox,ix) * dy[oy,ox]
+template <int VEC>
+__global__ void bilinear_bwd_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx, int B,
+                                    int Hi, int Wi, int Ho, int Wo, ResizeTab ty, ResizeTab tx, int rows_per_block) {
+  const int cq = threadIdx.x;
+  const int M = B * Hi * Wi;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    const int b = r / (Hi * Wi), rem = r - b * (Hi * Wi), iy = rem / Wi, ix = rem - iy * Wi;
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    const int oy0 = ty.g_lo[iy], oy1 = ty.g_hi[iy], ox0 = tx.g_lo[ix], ox1 = tx.g_hi[ix];
+    for (int oy = oy0; oy <= oy1; ++oy) {
+      const float wy = gather_w(ty, oy, iy);
+      if (wy == 0.f) continue;
+      const float* rowp = dy + ((size_t)(b * Ho + oy) * Wo) * lddy + cq * VEC;
+      for (int ox = ox0; ox <= ox1; ++ox) {
+        const float w = wy * gather_w(tx, ox, ix);
+        const float* p = rowp + (size_t)ox * lddy;
+        if (VEC == 4) {
+          const float4 g = ld4(p);
+          acc[0] = fmaf(w, g.x, acc[0]); acc[1] = fmaf(w, g.y, acc[1]);
+          acc[2 % VEC] = fmaf(w, g.z, acc[2 % VEC]); acc[3 % VEC] = fmaf(w, g.w, acc[3 % VEC]);
+        } else {
+          const float2 g = *reinterpret_cast<const float2*>(p);
+          acc[0] = fmaf(w, g.x, acc[0]); acc[1] = fmaf(w, g.y, acc[1]);
+        }
+      }
+    }
+    float* o = dx + (size_t)r * lddx + cq * VEC;
+    if (VEC == 4) st4(o, f4(acc[0], acc[1], acc[2 % VEC], acc[3 % VEC]));
+    else *reinterpret_cast<float2*>(o) = make_float2(acc[0], acc[1]);
+  }
+}
+void bilinear_bwd(const float* dy, int lddy, float* dx, int lddx, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                  ResizeTab ty, ResizeTab tx, cudaStream_t s) {
+  if (C == 2) {
+    dim3 blk(1, 128);
+    int rpb = 128;
+    bilinear_bwd_kernel<2><<<cdiv(B * Hi * Wi, rpb), blk, 0, s>>>(dy, lddy, dx, lddx, B, Hi, Wi, Ho, Wo, ty, tx, rpb);
+  } else {
+    int c4 = C / 4, R = 256 / c4;
+    if (R < 1) R = 1;
+    if (R > 64) R = 64;
+    dim3 blk(c4, R);
+    int rpb = R;
+    bilinear_bwd_kernel<4><<<cdiv(B * Hi * Wi, rpb), blk, 0, s>>>(dy, lddy, dx, lddx, B, Hi, Wi, Ho, Wo, ty, tx, rpb);
+  }
+}
+
+// =============================================================================================
+// logits head: dropout -> 1x1 conv C->2 + bias       (efficientlab.py:161-167)
+// =============================================================================================
+__global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ x, int ldx,
+                                                        const float* __restrict__ w, const float* __restrict__ bias,
+                                                        const float* __restrict__ mask, float keep_scale,
+                                                        float* __restrict__ z, int M, int C) {
+  const int l8 = threadIdx.x & 7;
+  const int p = blockIdx.x * 32 + (threadIdx.x >> 3);
+  float a0 = 0.f, a1 = 0.f;
+  if (p < M) {
+    for (int c4 = l8; c4 < C / 4; c4 += 8) {
+      float4 v = ld4(x + (size_t)p * ldx + c4 * 4);
+      if (mask) v = v * ld4(mask + (size_t)p * C + c4 * 4) * keep_scale;
+      const float4 w0 = ld4(w + c4 * 8), w1 = ld4(w + c4 * 8 + 4);   // w[c][j], j in {0,1}
+      a0 += v.x * w0.x + v.y * w0.z + v.z * w1.x + v.w * w1.z;
+      a1 += v.x * w0.y + v.y * w0.w + v.z * w1.y + v.w * w1.w;
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+  }
+  if (p < M && l8 == 0) *reinterpret_cast<float2*>(z + (size_t)p * 2) = make_float2(a0 + bias[0], a1 + bias[1]);
+}
+void head_fwd(const float* x, int ldx, const float* w, const float* bias, const float* drop_mask, float keep_scale,
+              float* z, int M, int C, cudaStream_t s) {
+  head_fwd_kernel<<<cdiv(M, 32), 256, 0, s>>>(x, ldx, w, bias, drop_mask, keep_scale, z, M, C);
+}
+
+// dx = (dz . w^T) * mask*scale ; dW[c][j] = sum_p xd[p,c] dz[p,j] ; db[j] = sum_p dz[p,j]
+__global__ void head_bwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
+                                const float* __restrict__ mask, float keep_scale, const float* __restrict__ dz,
+                                float* __restrict__ dx, int lddx, float* __restrict__ partials, int M, int C,
+                                int rows_per_chunk) {
+  extern __shared__ float4 sm[];
+  const int cq = threadIdx.x, C4 = blockDim.x, R = blockDim.y, ty = threadIdx.y;
+  const float4 w0 = ld4(w + cq * 8), w1 = ld4(w + cq * 8 + 4);
+  const float4 wj0 = f4(w0.x, w0.z, w1.x, w1.z), wj1 = f4(w0.y, w0.w, w1.y, w1.w);
+  const int r0 = blockIdx.x * rows_per_chunk, r1 = min(M, r0 + rows_per_chunk);
+  float4 g0 = f4s(0.f), g1 = f4s(0.f);
+  float sb0 = 0.f, sb1 = 0.f;
+  for (int r = r0 + ty; r < r1; r += R) {
+    const float2 d = *reinterpret_cast<const float2*>(dz + (size_t)r * 2);
+    float4 v = ld4(x + (size_t)r * ldx + cq * 4);
+    float4 g = wj0 * d.x + wj1 * d.y;
+    if (mask) {
+      const float4 mk = ld4(mask + (size_t)r * C + cq * 4) * keep_scale;
+      v = v * mk;
+      g = g * mk;
+    }
+    st4(dx + (size_t)r * lddx + cq * 4, g);
+    g0 = g0 + v * d.x;
+    g1 = g1 + v * d.y;
+    sb0 += d.x;
+    sb1 += d.y;
+  }
+  // reduce over ty
+  sm[ty * C4 + cq] = g0;
+  sm[(R + ty) * C4 + cq] = g1;
+  float* sbm = reinterpret_cast<float*>(sm + 2 * R * C4);
+  if (cq == 0) { sbm[ty * 2] = sb0; sbm[ty * 2 + 1] = sb1; }
+  __syncthreads();
+  if (ty == 0) {
+    for (int j = 1; j < R; ++j) { g0 = g0 + sm[j * C4 + cq]; g1 = g1 + sm[(R + j) * C4 + cq]; }
+    float* o = partials + (size_t)blockIdx.x * (C * 2 + 2);
+    o[(cq * 4 + 0) * 2] = g0.x; o[(cq * 4 + 0) * 2 + 1] = g1.x;
+    o[(cq * 4 + 1) * 2] = g0.y; o[(cq * 4 + 1) * 2 + 1] = g1.y;
+    o[(cq * 4 + 2) * 2] = g0.z; o[(cq * 4 + 2) * 2 + 1] = g1.z;
+    o[(cq * 4 + 3) * 2] = g0.w; o[(cq * 4 + 3) * 2 + 1] = g1.w;
+    if (cq == 0) {
+      for (int j = 1; j < R; ++j) { sb0 += sbm[j * 2]; sb1 += sbm[j * 2 + 1]; }
+      o[C * 2] = sb0;
+      o[C * 2 + 1] = sb1;
+    }
+  }
+}
+void head_bwd(const float* x, int ldx, const float* w, const float* drop_mask, float keep_scale, const float* dz,
+              float* dx, int lddx, float* partials, float* dw, float* db, int M, int C, cudaStream_t s) {
+  // dw and db are contiguous in theta? not necessarily: reduce them separately from one partial buffer
+  int c4 = C / 4, R = 256 / c4;
+  if (R < 1) R = 1;
+  if (R > 64) R = 64;
+  int G = cdiv(M, R * 8);
+  if (G > 296) G = 296;
+  dim3 blk(c4, R);
+  size_t smem = 2 * (size_t)R * c4 * sizeof(float4) + 2 * R * sizeof(float);
+  head_bwd_kernel<<<G, blk, smem, s>>>(x, ldx, w, drop_mask, keep_scale, dz, dx, lddx, partials, M, C, cdiv(M, G));
+  // partial rows are [C*2 | 2]; reduce into a staging area right after the partials, then scatter
+  float* stage = partials + (size_t)G * (C * 2 + 2);
+  reduce_partials(partials, G, C * 2 + 2, stage, s);
+  cudaMemcpyAsync(dw, stage, (size_t)C * 2 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  cudaMemcpyAsync(db, stage + C * 2, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+}
+
+// =============================================================================================
+// loss: softmax CE (+ label smoothing) - ln(dice) ; fused with the final bilinear upsample
+// =============================================================================================
+struct Up2 { float z0, z1; };
+__device__ __forceinline__ Up2 upsample_logits(const float* __restrict__ z_lo, int b, int h, int w, int Y, int X,
+                                               const ResizeTab& ty, const ResizeTab& tx) {
+  const int y0 = ty.lo[Y], y1 = ty.hi[Y], x0 = tx.lo[X], x1 = tx.hi[X];
+  const float yl = ty.lerp[Y], xl = tx.lerp[X];
+  const float2* base = reinterpret_cast<const float2*>(z_lo) + (size_t)b * h * w;
+  const float2 tl = base[y0 * w + x0], tr = base[y0 * w + x1], bl = base[y1 * w + x0], br = base[y1 * w + x1];
+  Up2 r;
+  float top = tl.x + (tr.x - tl.x) * xl, bot = bl.x + (br.x - bl.x) * xl;
+  r.z0 = top + (bot - top) * yl;
+  top = tl.y + (tr.y - tl.y) * xl; bot = bl.y + (br.y - bl.y) * xl;
+  r.z1 = top + (bot - top) * yl;
+  return r;
+}
+
+constexpr int kLossChunks = 32;   // row chunks per image
+
+__global__ void __launch_bounds__(256) loss_fwd_kernel(LossArgs a) {
+  __shared__ float red[8][4];
+  const int b = blockIdx.y, g = blockIdx.x;
+  const int img = a.index ? a.index[b] : b;
+  const int rows_per = (a.H + kLossChunks - 1) / kLossChunks;
+  const int Y0 = g * rows_per, Y1 = min(a.H, Y0 + rows_per);
+  const float ls = a.label_smoothing;
+  float s_ce = 0.f, s_i = 0.f, s_p = 0.f, s_y = 0.f;
+  const int npix = (Y1 - Y0) * a.W;
+  for (int i = threadIdx.x; i < npix; i += 256) {
+    const int Y = Y0 + i / a.W, X = i - (i / a.W) * a.W;
+    const Up2 z = upsample_logits(a.z_lo, b, a.h, a.w, Y, X, a.ty, a.tx);
+    const float m = fmaxf(z.z0, z.z1);
+    const float e0 = expf(z.z0 - m), e1 = expf(z.z1 - m);
+    const float sum = e0 + e1;
+    const float p1 = e1 / sum;
+    const float lse = m + logf(sum);
+    const float2 y = *reinterpret_cast<const float2*>(a.labels + (((size_t)img * a.H + Y) * a.W + X) * 2);
+    const float yc0 = y.x * (1.f - ls) + 0.5f * ls, yc1 = y.y * (1.f - ls) + 0.5f * ls;
+    s_ce += yc0 * (lse - z.z0) + yc1 * (lse - z.z1);
+    s_i += p1 * y.y;
+    s_p += p1;
+    s_y += y.y;
+    a.p1[((size_t)b * a.H + Y) * a.W + X] = p1;
+  }
+  s_ce = warp_sum(s_ce); s_i = warp_sum(s_i); s_p = warp_sum(s_p); s_y = warp_sum(s_y);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[warp][0] = s_ce; red[warp][1] = s_i; red[warp][2] = s_p; red[warp][3] = s_y; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float s = 0.f;
+    for (int wv = 0; wv < 8; ++wv) s += red[wv][threadIdx.x];
+    a.partials[((size_t)b * kLossChunks + g) * 4 + threadIdx.x] = s;
+  }
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out /*[gridDim.x]*/) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    s = fmaf(x[i], x[i], s);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int wv = 0; wv < 8; ++wv) t += red[wv];
+    out[blockIdx.x] = t;
+  }
+}
+
+// single thread: per-image IoU, dice, loss value and the per-image gradient coefficients
+__global__ void loss_finalize_kernel(LossArgs a, const float* __restrict__ l2_partials, int n_l2_partials) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double eps = 1e-7;
+  double ce = 0.0, iou = 0.0;
+  for (int b = 0; b < a.B; ++b) {
+    double I = 0.0, P = 0.0, Yv = 0.0;
+    for (int g = 0; g < kLossChunks; ++g) {
+      const float* p = a.partials + ((size_t)b * kLossChunks + g) * 4;
+      ce += p[0]; I += p[1]; P += p[2]; Yv += p[3];
+    }
+    const double U = P + Yv - I;
+    iou += (I + eps) / (U + eps);
+    a.coef[b * 2 + 0] = (float)I;     // stash, rewritten below
+    a.coef[b * 2 + 1] = (float)U;
+  }
+  iou /= a.B;
+  double loss = ce / ((double)a.B * a.H * a.W);
+  double dLdiou = 0.0;
+  if (a.dice) {
+    loss -= log(2.0 * iou / (iou + 1.0));
+    dLdiou = -1.0 / (iou * (iou + 1.0));
+  }
+  for (int b = 0; b < a.B; ++b) {
+    const double I = a.coef[b * 2 + 0], U = a.coef[b * 2 + 1];
+    a.coef[b * 2 + 0] = (float)(dLdiou / (a.B * (U + eps)));                       // d loss / d I_b
+    a.coef[b * 2 + 1] = (float)(-dLdiou * (I + eps) / (a.B * (U + eps) * (U + eps)));  // d loss / d U_b
+  }
+  if (a.loss_out) {
+    double l2 = 0.0;
+    for (int i = 0; i < n_l2_partials; ++i) l2 += l2_partials[i];
+    *a.loss_out = (float)(loss + 0.5 * (double)a.l2_coef * l2);
+  }
+}
+
+__global__ void __launch_bounds__(256) loss_bwd_kernel(LossArgs a) {
+  const int b = blockIdx.y;
+  const int img = a.index ? a.index[b] : b;
+  const float cI = a.coef[b * 2 + 0], cU = a.coef[b * 2 + 1];
+  const float inv = 1.f / ((float)a.B * (float)a.H * (float)a.W);
+  const float ls = a.label_smoothing;
+  const int npix = a.H * a.W;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < npix; i += gridDim.x * 256) {
+    const float p1 = a.p1[(size_t)b * npix + i];
+    const float2 y = *reinterpret_cast<const float2*>(a.labels + ((size_t)img * npix + i) * 2);
+    const float yc0 = y.x * (1.f - ls) + 0.5f * ls, yc1 = y.y * (1.f - ls) + 0.5f * ls;
+    // d loss / d p1 = cI * y1 + cU * (1 - y1)      (dI/dp1 = y1, dU/dp1 = 1 - y1)
+    const float t = (cI * y.y + cU * (1.f - y.y)) * p1 * (1.f - p1);
+    // TF SoftmaxCrossEntropyWithLogits backprop = softmax - labels  [TF-ext]
+    const float d1 = (p1 - yc1) * inv + t;
+    const float d0 = ((1.f - p1) - yc0) * inv - t;
+    *reinterpret_cast<float2*>(a.dz_hi + ((size_t)b * npix + i) * 2) = make_float2(d0, d1);
+  }
+}
+
+void loss_fwd_bwd(const LossArgs& a, cudaStream_t s) {
+  loss_fwd_kernel<<<dim3(kLossChunks, a.B), 256, 0, s>>>(a);
+  float* l2p = a.partials + (size_t)a.B * kLossChunks * 4;
+  int nl2 = 0;
+  if (a.loss_out && a.l2_coef != 0.f && a.n_l2 > 0) {
+    nl2 = 148;
+    sumsq_kernel<<<nl2, 256, 0, s>>>(a.theta, a.n_l2, l2p);
+  }
+  loss_finalize_kernel<<<1, 32, 0, s>>>(a, l2p, nl2);
+  loss_bwd_kernel<<<dim3(cdiv(a.H * a.W, 256 * 4), a.B), 256, 0, s>>>(a);
+}
+
+// =============================================================================================
+// predictions: float(p > 0.5) on both channels + integer IoU counts on channel 1
+// =============================================================================================
+__global__ void __launch_bounds__(256) predict_kernel(const float* __restrict__ z_lo, const float* __restrict__ labels,
+                                                       const int32_t* __restrict__ index, int h, int w, int H, int W,
+                                                       ResizeTab ty, ResizeTab tx, float* __restrict__ pred,
+                                                       float* __restrict__ logits, uint32_t* __restrict__ inter,
+                                                       uint32_t* __restrict__ uni) {
+  __shared__ uint32_t red[8][2];
+  const int b = blockIdx.y;
+  const int img = index ? index[b] : b;
+  const int npix = H * W;
+  uint32_t ci = 0, cu = 0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < npix; i += gridDim.x * 256) {
+    const int Y = i / W, X = i - Y * W;
+    const Up2 z = upsample_logits(z_lo, b, h, w, Y, X, ty, tx);
+    const float m = fmaxf(z.z0, z.z1);
+    const float e0 = expf(z.z0 - m), e1 = expf(z.z1 - m);
+    const float sum = e0 + e1;
+    const bool q0 = e0 / sum > 0.5f, q1 = e1 / sum > 0.5f;
+    if (pred) *reinterpret_cast<float2*>(pred + ((size_t)b * npix + i) * 2) = make_float2(q0 ? 1.f : 0.f, q1 ? 1.f : 0.f);
+    if (logits) *reinterpret_cast<float2*>(logits + ((size_t)b * npix + i) * 2) = make_float2(z.z0, z.z1);
+    if (labels) {
+      // np.round(label) on [0,1] data: 1 iff label > 0.5 (round-half-even sends 0.5 to 0)
+      const bool l1 = labels[((size_t)img * npix + i) * 2 + 1] > 0.5f;
+      ci += (q1 && l1) ? 1u : 0u;
+      cu += (q1 || l1) ? 1u : 0u;
+    }
+  }
+  if (inter) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ci += __shfl_xor_sync(0xffffffffu, ci, o);
+      cu += __shfl_xor_sync(0xffffffffu, cu, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = ci; red[threadIdx.x >> 5][1] = cu; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t ti = 0, tu = 0;
+      for (int wv = 0; wv < 8; ++wv) { ti += red[wv][0]; tu += red[wv][1]; }
+      atomicAdd(inter + b, ti);
+      atomicAdd(uni + b, tu);
+    }
+  }
+}
+void predict_mask_iou(const float* z_lo, const float* labels, const int32_t* index, int B, int h, int w, int H, int W,
+                      ResizeTab ty, ResizeTab tx, float* pred_out, float* logits_out, uint32_t* inter, uint32_t* uni,
+                      cudaStream_t s) {
+  if (inter) {
+    cudaMemsetAsync(inter, 0, B * sizeof(uint32_t), s);
+    cudaMemsetAsync(uni, 0, B * sizeof(uint32_t), s);
+  }
+  predict_kernel<<<dim3(cdiv(H * W, 256 * 4), B), 256, 0, s>>>(z_lo, inter ? labels : nullptr, index, h, w, H, W, ty, tx,
+                                                              pred_out, logits_out, inter, uni);
+}
+
+// =============================================================================================
+// optimizer + meta-update over the flat parameter buffer
+// =============================================================================================
+__global__ void scale_kernel(float* __restrict__ x, int64_t n, float s) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i * 4 + 3 < n) st4(x + i * 4, ld4(x + i * 4) * s);
+  else for (int64_t j = i * 4; j < n; ++j) x[j] *= s;
+}
+void scale_buffer(float* x, int64_t n, float sc, cudaStream_t st) {
+  scale_kernel<<<(unsigned)cdiv64(cdiv64(n, 4), 256), 256, 0, st>>>(x, n, sc);
+}
+
+// TF ApplyAdam with beta1 = 0 (m == g) / ApplyGradientDescent.  g' = g + l2*theta on the first n_l2 floats
+// (gradient of 0.0005 * sum l2_loss(v), regularizers.py:4-10).  powers = {beta1_power, beta2_power}.
+__global__ void adam_kernel(float* __restrict__ theta, float* __restrict__ v, const float* __restrict__ g, int64_t n,
+                            int64_t n_l2, const float* __restrict__ lr_dev, const float* __restrict__ powers,
+                            float l2_coef, int sgd) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float lr = *lr_dev;
+  const float th = theta[i];
+  const float gi = g[i] + (i < n_l2 ? l2_coef * th : 0.f);
+  if (sgd) {
+    theta[i] = th - lr * gi;
+  } else {
+    const float b2 = 0.999f, eps = 1e-8f;
+    const float alpha = lr * sqrtf(1.f - powers[1]) / (1.f - powers[0]);
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    v[i] = vi;
+    theta[i] = th - alpha * gi / (sqrtf(vi) + eps);
+  }
+}
+__global__ void adam_finish_kernel(float* powers) {
+  powers[0] *= 0.0f;      // beta1 = 0
+  powers[1] *= 0.999f;
+}
+void adam_step(float* theta, float* v, const float* g, int64_t n, int64_t n_l2, const float* lr_dev, float* powers,
+               float l2_coef, int sgd, cudaStream_t s) {
+  adam_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(theta, v, g, n, n_l2, lr_dev, powers, l2_coef, sgd);
+  if (!sgd) adam_finish_kernel<<<1, 1, 0, s>>>(powers);
+}
+
+__global__ void delta_acc_kernel(float* __restrict__ d, const float* __restrict__ a, const float* __restrict__ b,
+                                 int64_t n, int first) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = a[i] - b[i];
+  d[i] = first ? v : d[i] + v;
+}
+void delta_accumulate(float* dsum, const float* a, const float* b, int64_t n, int first, cudaStream_t s) {
+  delta_acc_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(dsum, a, b, n, first);
+}
+__global__ void meta_apply_kernel(float* __restrict__ th, const float* __restrict__ d, float scale, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) th[i] = fmaf(scale, d[i], th[i]);
+}
+void meta_apply(float* theta, const float* dsum, float scale, int64_t n, cudaStream_t s) {
+  meta_apply_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(theta, dsum, scale, n);
+}
+
+// Keras Dropout keep mask: keep where U >= rate [TF-ext]; U from a counter-based hash (the reference's
+// stream is unseeded, so any uniform stream is a valid draw; tests inject masks instead).
+__global__ void dropout_mask_kernel(float* __restrict__ mask, int64_t n, float rate, uint64_t seed) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = (float)(z >> 40) * (1.f / 16777216.f);
+  mask[i] = u >= rate ? 1.f : 0.f;
+}
+void fill_dropout_mask(float* mask, int64_t n, float rate, uint64_t seed, cudaStream_t s) {
+  dropout_mask_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(mask, n, rate, seed);
+}
+
+}  // namespace mliis

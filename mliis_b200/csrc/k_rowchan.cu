@@ -1,0 +1,495 @@
+// Row-channel kernels: everything that walks an NHWC tensor as [rows, C] once or twice and is bound
+// by HBM bandwidth - train-mode BatchNorm statistics / normalise / backward, swish, squeeze-excite
+// pooling and gating gradients, residual + drop-connect, concat plumbing.
+//
+// Thread mapping: blockDim = (C/4, R).  threadIdx.x owns one float4 of channels, so a warp reads
+// consecutive 16-byte words of consecutive rows (fully coalesced for any C % 4 == 0, ld == C) and the
+// per-channel coefficients live in registers for the whole kernel.  Reductions over rows are done
+// thread-serially, then across threadIdx.y through shared memory in a fixed order, then across blocks
+// by a tiny finalize kernel in double precision -> deterministic, no float atomics.
+//
+// Reference semantics: models/efficientnet/utils.py:87-134 (non-fused BN), efficientnet_model.py:238-290
+// (SE, block tail), models/efficientlab.py:185-197 (decoder conv->swish->BN, pooled features).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mliis {
+
+static inline int rc_R(int C) {
+  int c4 = C / 4;
+  int R = 256 / c4;
+  if (R < 1) R = 1;
+  if (R > 64) R = 64;
+  return R;
+}
+static inline dim3 rc_block(int C) { return dim3(C / 4, rc_R(C)); }
+
+int rc_num_chunks(int M, int C) {
+  int R = rc_R(C);
+  int G = cdiv(M, R * 8);
+  if (G > 296) G = 296;
+  if (G < 1) G = 1;
+  return G;
+}
+int rc_num_img_chunks(int HW, int C) {
+  int R = rc_R(C);
+  int G = cdiv(HW, R * 8);
+  if (G > 32) G = 32;
+  if (G < 1) G = 1;
+  return G;
+}
+
+// block-level reduction of two float4 accumulators across threadIdx.y (fixed order)
+__device__ __forceinline__ void block_reduce2(float4& s0, float4& s1, float4* sm) {
+  const int C4 = blockDim.x, R = blockDim.y, cq = threadIdx.x, ty = threadIdx.y;
+  sm[ty * C4 + cq] = s0;
+  sm[(R + ty) * C4 + cq] = s1;
+  __syncthreads();
+  if (ty == 0) {
+    for (int j = 1; j < R; ++j) {
+      s0 = s0 + sm[j * C4 + cq];
+      s1 = s1 + sm[(R + j) * C4 + cq];
+    }
+  }
+}
+__device__ __forceinline__ void block_reduce1(float4& s0, float4* sm) {
+  const int C4 = blockDim.x, R = blockDim.y, cq = threadIdx.x, ty = threadIdx.y;
+  sm[ty * C4 + cq] = s0;
+  __syncthreads();
+  if (ty == 0)
+    for (int j = 1; j < R; ++j) s0 = s0 + sm[j * C4 + cq];
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN statistics
+// ------------------------------------------------------------------------------------------------
+template <bool PRE_SWISH>
+__global__ void bn_stats_kernel(const float* __restrict__ x, int ld, int M, int C, int rows_per_chunk,
+                                float* __restrict__ partials) {
+  extern __shared__ float4 sm[];
+  const int cq = threadIdx.x;
+  const int r0 = blockIdx.x * rows_per_chunk;
+  const int r1 = min(M, r0 + rows_per_chunk);
+  float4 s = f4s(0.f), ss = f4s(0.f);
+  for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    float4 v = ld4(x + (size_t)r * ld + cq * 4);
+    if (PRE_SWISH) v = swish4(v);
+    s = s + v;
+    fma4(ss, v, v);
+  }
+  block_reduce2(s, ss, sm);
+  if (threadIdx.y == 0) {
+    st4(partials + ((size_t)blockIdx.x * 2 + 0) * C + cq * 4, s);
+    st4(partials + ((size_t)blockIdx.x * 2 + 1) * C + cq * 4, ss);
+  }
+}
+
+void bn_stats(const float* x, int ld, int M, int C, bool pre_swish, float* partials, cudaStream_t s) {
+  int G = rc_num_chunks(M, C);
+  int rpc = cdiv(M, G);
+  dim3 blk = rc_block(C);
+  size_t smem = 2 * blk.x * blk.y * sizeof(float4);
+  if (pre_swish)
+    bn_stats_kernel<true><<<G, blk, smem, s>>>(x, ld, M, C, rpc, partials);
+  else
+    bn_stats_kernel<false><<<G, blk, smem, s>>>(x, ld, M, C, rpc, partials);
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, int G, int C, int M,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ mm, float* __restrict__ mv, int ema, int bessel,
+                                   float* __restrict__ mean_o, float* __restrict__ rstd_o, float* __restrict__ a_o,
+                                   float* __restrict__ b_o) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, ss = 0.0;
+  for (int g = 0; g < G; ++g) {
+    s += (double)partials[((size_t)g * 2 + 0) * C + c];
+    ss += (double)partials[((size_t)g * 2 + 1) * C + c];
+  }
+  double mean = s / M;
+  double var = ss / M - mean * mean;   // biased (tf.nn.moments)
+  if (var < 0.0) var = 0.0;
+  float rstd = (float)(1.0 / sqrt(var + (double)kBnEps));
+  float a = gamma[c] * rstd;
+  mean_o[c] = (float)mean;
+  rstd_o[c] = rstd;
+  a_o[c] = a;
+  b_o[c] = beta[c] - (float)mean * a;
+  if (ema) {
+    // moving -= (moving - batch) * (1 - momentum)   [TF-ext assign_moving_average, no zero-debias]
+    float bv = (float)(bessel ? var * ((double)M / (double)(M - 1)) : var);
+    float m0 = mm[c], v0 = mv[c];
+    mm[c] = m0 - (m0 - (float)mean) * (1.f - kBnMomentum);
+    mv[c] = v0 - (v0 - bv) * (1.f - kBnMomentum);
+  }
+}
+
+void bn_finalize(const float* partials, int G, int C, int M, const float* gamma, const float* beta, float* mm,
+                 float* mv, int ema, int bessel, float* mean, float* rstd, float* a, float* b, cudaStream_t s) {
+  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(partials, G, C, M, gamma, beta, mm, mv, ema, bessel, mean, rstd,
+                                                  a, b);
+}
+
+__global__ void bn_eval_coeffs_kernel(const float* __restrict__ theta, const int32_t* __restrict__ gi,
+                                      const int32_t* __restrict__ bi, const float* __restrict__ mm,
+                                      const float* __restrict__ mv, int n, float* __restrict__ a,
+                                      float* __restrict__ b) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  float inv = rsqrtf(mv[c] + kBnEps) * theta[gi[c]];
+  a[c] = inv;
+  b[c] = theta[bi[c]] - mm[c] * inv;
+}
+void bn_eval_coeffs(const float* theta, const int32_t* gi, const int32_t* bi, const float* mm, const float* mv,
+                    int n, float* a, float* b, cudaStream_t s) {
+  bn_eval_coeffs_kernel<<<cdiv(n, 256), 256, 0, s>>>(theta, gi, bi, mm, mv, n, a, b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// elementwise appliers
+// ------------------------------------------------------------------------------------------------
+__global__ void dec_bn_apply_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ a,
+                                    const float* __restrict__ b, const float* __restrict__ res, int ldres,
+                                    float* __restrict__ y, int ldy, int M, int rows_per_block) {
+  const int cq = threadIdx.x;
+  const float4 av = ld4(a + cq * 4), bv = ld4(b + cq * 4);
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    float4 v = affine4(swish4(ld4(x + (size_t)r * ldx + cq * 4)), av, bv);
+    if (res) v = v + ld4(res + (size_t)r * ldres + cq * 4);
+    st4(y + (size_t)r * ldy + cq * 4, v);
+  }
+}
+void dec_bn_apply(const float* x, int ldx, const float* a, const float* b, const float* res, int ldres, float* y,
+                  int ldy, int M, int C, cudaStream_t s) {
+  dim3 blk = rc_block(C);
+  int rpb = blk.y * 4;
+  dec_bn_apply_kernel<<<cdiv(M, rpb), blk, 0, s>>>(x, ldx, a, b, res, ldres, y, ldy, M, rpb);
+}
+
+__global__ void block_out_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ a,
+                                 const float* __restrict__ b, const float* __restrict__ dcs,
+                                 const float* __restrict__ res, int ldres, float* __restrict__ y, int ldy, int M,
+                                 int HW, int rows_per_block) {
+  const int cq = threadIdx.x;
+  const float4 av = ld4(a + cq * 4), bv = ld4(b + cq * 4);
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    float4 v = affine4(ld4(x + (size_t)r * ldx + cq * 4), av, bv);
+    if (dcs) v = v * dcs[r / HW];
+    if (res) v = v + ld4(res + (size_t)r * ldres + cq * 4);
+    st4(y + (size_t)r * ldy + cq * 4, v);
+  }
+}
+void block_out(const float* x, int ldx, const float* a, const float* b, const float* dcs, const float* res,
+               int ldres, float* y, int ldy, int M, int C, int HW, cudaStream_t s) {
+  dim3 blk = rc_block(C);
+  int rpb = blk.y * 4;
+  block_out_kernel<<<cdiv(M, rpb), blk, 0, s>>>(x, ldx, a, b, dcs, res, ldres, y, ldy, M, HW, rpb);
+}
+
+// ------------------------------------------------------------------------------------------------
+// squeeze-excite
+// ------------------------------------------------------------------------------------------------
+// MODE 0: sum swish(a*x+b)        (SE squeeze)
+// MODE 1: sum g * swish(a*x+b)    (dgate)
+// MODE 2: sum x                   (plain per-image column sum)
+template <int MODE>
+__global__ void img_reduce_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ g, int ldg,
+                                  const float* __restrict__ a, const float* __restrict__ b, int HW, int C,
+                                  int rows_per_chunk, float* __restrict__ partial) {
+  extern __shared__ float4 sm[];
+  const int cq = threadIdx.x, img = blockIdx.y, G = gridDim.x;
+  float4 av = f4s(1.f), bv = f4s(0.f);
+  if (MODE != 2) { av = ld4(a + cq * 4); bv = ld4(b + cq * 4); }
+  const int r0 = blockIdx.x * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
+  float4 s = f4s(0.f);
+  for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    size_t row = (size_t)img * HW + r;
+    float4 v = ld4(x + row * ldx + cq * 4);
+    if (MODE != 2) v = swish4(affine4(v, av, bv));
+    if (MODE == 1) v = v * ld4(g + row * ldg + cq * 4);
+    s = s + v;
+  }
+  block_reduce1(s, sm);
+  if (threadIdx.y == 0) st4(partial + ((size_t)img * G + blockIdx.x) * C + cq * 4, s);
+}
+
+void se_pool(const float* x, int ldx, const float* a, const float* b, int B, int HW, int C, float* partial,
+             cudaStream_t s) {
+  int G = rc_num_img_chunks(HW, C);
+  dim3 blk = rc_block(C);
+  img_reduce_kernel<0><<<dim3(G, B), blk, blk.x * blk.y * sizeof(float4), s>>>(x, ldx, nullptr, 0, a, b, HW, C,
+                                                                               cdiv(HW, G), partial);
+}
+void se_bwd_reduce(const float* x, int ldx, const float* gup, int ldg, const float* a, const float* b, int B, int HW,
+                   int C, float* partial, cudaStream_t s) {
+  int G = rc_num_img_chunks(HW, C);
+  dim3 blk = rc_block(C);
+  img_reduce_kernel<1><<<dim3(G, B), blk, blk.x * blk.y * sizeof(float4), s>>>(x, ldx, gup, ldg, a, b, HW, C,
+                                                                               cdiv(HW, G), partial);
+}
+
+__global__ void img_colsum_finalize_kernel(const float* __restrict__ partial, int G, int C, float scale,
+                                           float* __restrict__ out, int ldo) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x, img = blockIdx.y;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int g = 0; g < G; ++g) s += (double)partial[((size_t)img * G + g) * C + c];
+  out[(size_t)img * ldo + c] = (float)(s * (double)scale);
+}
+void img_colsum(const float* x, int ldx, int B, int HW, int C, float scale, float* partial, float* out, int ldo,
+                cudaStream_t s) {
+  int G = rc_num_img_chunks(HW, C);
+  dim3 blk = rc_block(C);
+  img_reduce_kernel<2><<<dim3(G, B), blk, blk.x * blk.y * sizeof(float4), s>>>(x, ldx, nullptr, 0, nullptr, nullptr,
+                                                                               HW, C, cdiv(HW, G), partial);
+  img_colsum_finalize_kernel<<<dim3(cdiv(C, 128), B), 128, 0, s>>>(partial, G, C, scale, out, ldo);
+}
+
+// One block per image.  pool -> reduce FC (+bias, swish) -> expand FC (+bias) -> sigmoid.
+__global__ void se_fc_fwd_kernel(const float* __restrict__ partial, int G, int HW, int C, int Cr,
+                                 const float* __restrict__ w1, const float* __restrict__ b1,
+                                 const float* __restrict__ w2, const float* __restrict__ b2,
+                                 float* __restrict__ pool_o, float* __restrict__ hidpre_o,
+                                 float* __restrict__ gate_o) {
+  extern __shared__ float smf[];
+  float* pool = smf;          // [C]
+  float* hid = smf + C;       // [Cr]
+  const int img = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const float inv = 1.f / (float)HW;
+  for (int c = tid; c < C; c += nt) {
+    float s = 0.f;
+    for (int g = 0; g < G; ++g) s += partial[((size_t)img * G + g) * C + c];
+    s *= inv;
+    pool[c] = s;
+    pool_o[(size_t)img * C + c] = s;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  for (int r = warp; r < Cr; r += nw) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(pool[c], w1[(size_t)c * Cr + r], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      s += b1[r];
+      hidpre_o[(size_t)img * Cr + r] = s;
+      hid[r] = swish_f(s);
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += nt) {
+    float s = b2[c];
+    for (int r = 0; r < Cr; ++r) s = fmaf(hid[r], w2[(size_t)r * C + c], s);
+    gate_o[(size_t)img * C + c] = sigmoid_f(s);
+  }
+}
+void se_fc_fwd(const float* partial, int G, int B, int HW, int C, int Cr, const float* w1, const float* b1,
+               const float* w2, const float* b2, float* pool, float* hidpre, float* gate, cudaStream_t s) {
+  se_fc_fwd_kernel<<<B, 256, (C + Cr) * sizeof(float), s>>>(partial, G, HW, C, Cr, w1, b1, w2, b2, pool, hidpre,
+                                                            gate);
+}
+
+// Single block: gradients of the two SE FCs and of the pooled input.
+__global__ void se_fc_bwd_kernel(const float* __restrict__ partial, int G, int B, int HW, int C, int Cr,
+                                 const float* __restrict__ w1, const float* __restrict__ w2,
+                                 const float* __restrict__ pool, const float* __restrict__ hidpre,
+                                 const float* __restrict__ gate, float* __restrict__ dw1, float* __restrict__ db1,
+                                 float* __restrict__ dw2, float* __restrict__ db2, float* __restrict__ dpool) {
+  extern __shared__ float smf[];
+  float* dgp = smf;                 // [B][C]   d(gate pre-activation)
+  float* hid = dgp + (size_t)B * C;   // [B][Cr]
+  float* dhp = hid + (size_t)B * Cr;  // [B][Cr]  d(hidden pre-activation)
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < B * C; i += nt) {
+    int b = i / C, c = i - b * C;
+    float s = 0.f;
+    for (int g = 0; g < G; ++g) s += partial[((size_t)b * G + g) * C + c];
+    float gt = gate[i];
+    dgp[i] = s * gt * (1.f - gt);
+  }
+  for (int i = tid; i < B * Cr; i += nt) hid[i] = swish_f(hidpre[i]);
+  __syncthreads();
+  for (int c = tid; c < C; c += nt) {
+    float sb = 0.f;
+    for (int b = 0; b < B; ++b) sb += dgp[b * C + c];
+    db2[c] = sb;
+    for (int r = 0; r < Cr; ++r) {
+      float s = 0.f;
+      for (int b = 0; b < B; ++b) s = fmaf(hid[b * Cr + r], dgp[b * C + c], s);
+      dw2[(size_t)r * C + c] = s;
+    }
+  }
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  for (int i = warp; i < B * Cr; i += nw) {
+    int b = i / Cr, r = i - b * Cr;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(w2[(size_t)r * C + c], dgp[b * C + c], s);
+    s = warp_sum(s);
+    if (lane == 0) dhp[i] = s * swish_grad_f(hidpre[i]);
+  }
+  __syncthreads();
+  for (int r = tid; r < Cr; r += nt) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dhp[b * Cr + r];
+    db1[r] = s;
+  }
+  for (int i = tid; i < C * Cr; i += nt) {
+    int c = i / Cr, r = i - c * Cr;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s = fmaf(pool[(size_t)b * C + c], dhp[b * Cr + r], s);
+    dw1[i] = s;
+  }
+  const float inv = 1.f / (float)HW;
+  for (int i = tid; i < B * C; i += nt) {
+    int b = i / C, c = i - b * C;
+    float s = 0.f;
+    for (int r = 0; r < Cr; ++r) s = fmaf(w1[(size_t)c * Cr + r], dhp[b * Cr + r], s);
+    dpool[i] = s * inv;
+  }
+}
+void se_fc_bwd(const float* partial, int G, int B, int HW, int C, int Cr, const float* w1, const float* w2,
+               const float* pool, const float* hidpre, const float* gate, float* dw1, float* db1, float* dw2,
+               float* db2, float* dpool, cudaStream_t s) {
+  size_t smem = ((size_t)B * C + 2 * (size_t)B * Cr) * sizeof(float);
+  se_fc_bwd_kernel<<<1, 512, smem, s>>>(partial, G, B, HW, C, Cr, w1, w2, pool, hidpre, gate, dw1, db1, dw2, db2,
+                                        dpool);
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN backward (train mode): dgamma = sum g*xhat, dbeta = sum g, dx = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat))
+// ------------------------------------------------------------------------------------------------
+template <int VAR>
+__device__ __forceinline__ void bn_bwd_elem(const BnBwdArgs& p, size_t r, int cq, float4 mean, float4 rstd, float4 av,
+                                            float4 bv, float4& geff, float4& xhat, float4& post) {
+  float4 x = ld4(p.x + r * p.ldx + cq * 4);
+  float4 g = ld4(p.g + r * p.ldg + cq * 4);
+  post = f4s(1.f);
+  if (VAR == BN_PLAIN) {
+    if (p.dcs) g = g * p.dcs[r / p.HW];
+    geff = g;
+    xhat = (x - mean) * rstd;
+  } else if (VAR == BN_SWISH) {
+    geff = g * swish_grad4(affine4(x, av, bv));
+    xhat = (x - mean) * rstd;
+  } else if (VAR == BN_SWISH_SE) {
+    size_t ic = (r / p.HW) * (size_t)p.C + cq * 4;
+    float4 dz = g * ld4(p.gate + ic) + ld4(p.dpool + ic);
+    geff = dz * swish_grad4(affine4(x, av, bv));
+    xhat = (x - mean) * rstd;
+  } else {  // BN_DEC: s = swish(x); y = BN(s)
+    xhat = (swish4(x) - mean) * rstd;
+    geff = g;
+    post = swish_grad4(x);
+  }
+}
+
+template <int VAR>
+__global__ void bn_bwd_reduce_kernel(BnBwdArgs p, int rows_per_chunk) {
+  extern __shared__ float4 sm[];
+  const int cq = threadIdx.x;
+  const float4 mean = ld4(p.mean + cq * 4), rstd = ld4(p.rstd + cq * 4);
+  const float4 av = ld4(p.a + cq * 4), bv = ld4(p.b + cq * 4);
+  const int r0 = blockIdx.x * rows_per_chunk, r1 = min(p.M, r0 + rows_per_chunk);
+  float4 s0 = f4s(0.f), s1 = f4s(0.f);
+  for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    float4 ge, xh, po;
+    bn_bwd_elem<VAR>(p, (size_t)r, cq, mean, rstd, av, bv, ge, xh, po);
+    s0 = s0 + ge;
+    fma4(s1, ge, xh);
+  }
+  block_reduce2(s0, s1, sm);
+  if (threadIdx.y == 0) {
+    st4(p.partials + ((size_t)blockIdx.x * 2 + 0) * p.C + cq * 4, s0);
+    st4(p.partials + ((size_t)blockIdx.x * 2 + 1) * p.C + cq * 4, s1);
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int G, int C, int M,
+                                       float* __restrict__ k, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int g = 0; g < G; ++g) {
+    s0 += (double)partials[((size_t)g * 2 + 0) * C + c];
+    s1 += (double)partials[((size_t)g * 2 + 1) * C + c];
+  }
+  dbeta[c] = (float)s0;
+  dgamma[c] = (float)s1;
+  k[c] = (float)(s0 / M);
+  k[C + c] = (float)(s1 / M);
+}
+
+template <int VAR>
+__global__ void bn_bwd_apply_kernel(BnBwdArgs p, int rows_per_block) {
+  const int cq = threadIdx.x;
+  const float4 mean = ld4(p.mean + cq * 4), rstd = ld4(p.rstd + cq * 4);
+  const float4 av = ld4(p.a + cq * 4), bv = ld4(p.b + cq * 4);
+  const float4 ga = ld4(p.gamma + cq * 4) * rstd;
+  const float4 k1 = ld4(p.k + cq * 4), k2 = ld4(p.k + p.C + cq * 4);
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(p.M, r0 + rows_per_block);
+  for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    float4 ge, xh, po;
+    bn_bwd_elem<VAR>(p, (size_t)r, cq, mean, rstd, av, bv, ge, xh, po);
+    float4 d = ga * (ge - k1 - xh * k2);
+    if (VAR == BN_DEC) d = d * po;
+    st4(p.dx + (size_t)r * p.lddx + cq * 4, d);
+  }
+}
+
+template <int VAR>
+static void bn_bwd_t(const BnBwdArgs& p, cudaStream_t s) {
+  int G = rc_num_chunks(p.M, p.C);
+  dim3 blk = rc_block(p.C);
+  bn_bwd_reduce_kernel<VAR><<<G, blk, 2 * blk.x * blk.y * sizeof(float4), s>>>(p, cdiv(p.M, G));
+  bn_bwd_finalize_kernel<<<cdiv(p.C, 128), 128, 0, s>>>(p.partials, G, p.C, p.M, p.k, p.dgamma, p.dbeta);
+  int rpb = blk.y * 4;
+  bn_bwd_apply_kernel<VAR><<<cdiv(p.M, rpb), blk, 0, s>>>(p, rpb);
+}
+void bn_bwd(int var, const BnBwdArgs& p, cudaStream_t s) {
+  switch (var) {
+    case BN_PLAIN: bn_bwd_t<BN_PLAIN>(p, s); break;
+    case BN_SWISH: bn_bwd_t<BN_SWISH>(p, s); break;
+    case BN_SWISH_SE: bn_bwd_t<BN_SWISH_SE>(p, s); break;
+    default: bn_bwd_t<BN_DEC>(p, s); break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// concat / broadcast plumbing
+// ------------------------------------------------------------------------------------------------
+__global__ void bcast_rows_kernel(const float* __restrict__ pimg, int ldp, float* __restrict__ y, int ldy, int M,
+                                  int HW, int rows_per_block) {
+  const int cq = threadIdx.x;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y)
+    st4(y + (size_t)r * ldy + cq * 4, ld4(pimg + (size_t)(r / HW) * ldp + cq * 4));
+}
+void bcast_rows(const float* pimg, int ldp, float* y, int ldy, int B, int HW, int C, cudaStream_t s) {
+  dim3 blk = rc_block(C);
+  int rpb = blk.y * 4, M = B * HW;
+  bcast_rows_kernel<<<cdiv(M, rpb), blk, 0, s>>>(pimg, ldp, y, ldy, M, HW, rpb);
+}
+
+__global__ void add3_kernel(float* __restrict__ dst, int ldd, const float* __restrict__ a, int lda,
+                            const float* __restrict__ b, int ldb, const float* __restrict__ pimg, int ldp, int M,
+                            int HW, int rows_per_block) {
+  const int cq = threadIdx.x;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    float4 v = ld4(a + (size_t)r * lda + cq * 4);
+    if (b) v = v + ld4(b + (size_t)r * ldb + cq * 4);
+    if (pimg) v = v + ld4(pimg + (size_t)(r / HW) * ldp + cq * 4);
+    st4(dst + (size_t)r * ldd + cq * 4, v);
+  }
+}
+void add3(float* dst, int ldd, const float* a, int lda, const float* b, int ldb, const float* pimg, int ldp, int M,
+          int C, int HW, cudaStream_t s) {
+  dim3 blk = rc_block(C);
+  int rpb = blk.y * 4;
+  add3_kernel<<<cdiv(M, rpb), blk, 0, s>>>(dst, ldd, a, lda, b, ldb, pimg, ldp, M, HW, rpb);
+}
+
+}  // namespace mliis

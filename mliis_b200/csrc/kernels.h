@@ -1,0 +1,150 @@
+// Host-side launchers of the mliis_b200 kernels.  All pointers are device pointers; all tensors are
+// fp32 NHWC viewed as [rows = B*H*W, C] with an explicit row stride `ld` (floats) so that producers can
+// write straight into channel slices of concat buffers (the reference's tf.concat is never materialised
+// by a copy of its own).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mliis {
+
+// ---------------- row-channel kernels (k_rowchan.cu) : HBM-bound ----------------
+enum BnVar { BN_PLAIN = 0, BN_SWISH = 1, BN_SWISH_SE = 2, BN_DEC = 3 };
+
+int rc_num_chunks(int M, int C);              // #row chunks used by the whole-tensor reductions
+int rc_num_img_chunks(int HW, int C);         // #row chunks per image used by the per-image reductions
+
+// batch statistics of x (pre_swish: of swish(x)) -> partials [G][2][C]
+void bn_stats(const float* x, int ld, int M, int C, bool pre_swish, float* partials, cudaStream_t s);
+// partials -> mean,rstd,a,b (+EMA into moving_mean/var when ema != 0; bessel: n/(n-1) corrected variance)
+void bn_finalize(const float* partials, int G, int C, int M, const float* gamma, const float* beta,
+                 float* moving_mean, float* moving_var, int ema, int bessel, float* mean, float* rstd, float* a,
+                 float* b, cudaStream_t s);
+// eval mode coefficients for ALL layers at once: a = gamma*rsqrt(mv+eps), b = beta - mm*a
+void bn_eval_coeffs(const float* theta, const int32_t* gamma_idx, const int32_t* beta_idx, const float* moving_mean,
+                    const float* moving_var, int n_ch, float* a, float* b, cudaStream_t s);
+
+// decoder: y = a*swish(x)+b (+res)
+void dec_bn_apply(const float* x, int ldx, const float* a, const float* b, const float* res, int ldres, float* y,
+                  int ldy, int M, int C, cudaStream_t s);
+// backbone block output: y = (a*x+b)*dcs[img] + res   (dcs, res nullable)
+void block_out(const float* x, int ldx, const float* a, const float* b, const float* dcs, const float* res,
+               int ldres, float* y, int ldy, int M, int C, int HW, cudaStream_t s);
+
+// SE squeeze: partial[b][g][C] = sum_rows swish(a*x+b)
+void se_pool(const float* x, int ldx, const float* a, const float* b, int B, int HW, int C, float* partial,
+             cudaStream_t s);
+// SE FCs: pool, hidden pre-activation, gate (efficientnet_model.py:238-251)
+void se_fc_fwd(const float* partial, int G, int B, int HW, int C, int Cr, const float* w1, const float* b1,
+               const float* w2, const float* b2, float* pool, float* hidpre, float* gate, cudaStream_t s);
+// dgate partial[b][g][C] = sum_rows gup * swish(a*x+b)
+void se_bwd_reduce(const float* x, int ldx, const float* gup, int ldg, const float* a, const float* b, int B,
+                   int HW, int C, float* partial, cudaStream_t s);
+void se_fc_bwd(const float* partial, int G, int B, int HW, int C, int Cr, const float* w1, const float* w2,
+               const float* pool, const float* hidpre, const float* gate, float* dw1, float* db1, float* dw2,
+               float* db2, float* dpool /* [B][C], already / HW */, cudaStream_t s);
+
+struct BnBwdArgs {
+  const float* x; int ldx;      // pre-BN tensor
+  const float* g; int ldg;      // upstream gradient
+  float* dx; int lddx;          // output (may alias g)
+  int M, C, HW;
+  const float* mean; const float* rstd; const float* a; const float* b; const float* gamma;
+  const float* dcs;             // [B] or null (BN_PLAIN)
+  const float* gate;            // [B][C] (BN_SWISH_SE)
+  const float* dpool;           // [B][C] (BN_SWISH_SE)
+  float* partials;              // [G][2][C]
+  float* k;                     // [2][C]  mean(g), mean(g*xhat)
+  float* dgamma; float* dbeta;  // [C] gradient outputs
+};
+void bn_bwd(int var, const BnBwdArgs& p, cudaStream_t s);  // reduce + finalize + apply
+
+// per-image column sums: out[b][c] = scale * sum_rows x ; and helpers for concat/pool plumbing
+void img_colsum(const float* x, int ldx, int B, int HW, int C, float scale, float* partial, float* out, int ldo,
+                cudaStream_t s);
+void bcast_rows(const float* pimg, int ldp, float* y, int ldy, int B, int HW, int C, cudaStream_t s);
+// dst = a + b + pimg[img]  (b, pimg nullable)
+void add3(float* dst, int ldd, const float* a, int lda, const float* b, int ldb, const float* pimg, int ldp, int M,
+          int C, int HW, cudaStream_t s);
+
+// ---------------- convolution kernels (k_conv.cu) ----------------
+// stem: normalise + conv3x3 s2 (efficientlab.py:113-114, efficientnet_model.py:359-366)
+void stem_fwd(const float* images, const int32_t* index, const float* w, float* y, int B, int H, int W, int Ho,
+              int Wo, int pad_t, int pad_l, cudaStream_t s);
+void stem_wgrad(const float* images, const int32_t* index, const float* dy, float* partials, float* dw, int B, int H,
+                int W, int Ho, int Wo, int pad_t, int pad_l, cudaStream_t s);
+int stem_wgrad_blocks(int B, int Ho, int Wo);
+
+// depthwise k x k, stride 1|2, TF SAME.  Input is swish(a*x+b) when a != null (prologue fusion).
+void dw_fwd(const float* x, const float* a, const float* b, const float* w, float* y, int B, int H, int W, int C,
+            int k, int stride, int Ho, int Wo, int pad_t, int pad_l, cudaStream_t s);
+void dw_bwd_data(const float* dy, const float* w, float* dx, int B, int H, int W, int C, int k, int stride, int Ho,
+                 int Wo, int pad_t, int pad_l, cudaStream_t s);
+int dw_wgrad_blocks(int B, int Ho, int Wo, int stride);
+void dw_bwd_weight(const float* x, const float* a, const float* b, const float* dy, float* partials, float* dw,
+                   int B, int H, int W, int C, int k, int stride, int Ho, int Wo, int pad_t, int pad_l,
+                   cudaStream_t s);
+
+// ---------------- dense contractions, fp32 FFMA (k_gemm.cu) ----------------
+struct GemmA {              // A operand description: rows m = (b,y,x) of an NHWC tensor
+  const float* ptr; int ld;
+  // prologue: v = swish(pa[k]*v + pb[k]) * gate[img*K + k]   (pa null = none; gate null = none)
+  const float* pa; const float* pb; const float* gate;
+  // implicit 3x3 conv: K = 9*C, tap (ty,tx) reads pixel (y+(ty-1)*dil, x+(tx-1)*dil), zero outside
+  int conv;                 // 0: plain [M,K];  1: 3x3 taps
+  int H, W, C, dil;
+};
+// C[M,N] (ldc) = A[M,K] * Wt[K,N] (+bias[n]) (+C if accumulate)
+void gemm_nn(const GemmA& A, const float* Wt, const float* bias, float* Cout, int ldc, int M, int K, int N,
+             int HW, int accumulate, cudaStream_t s);
+// dW[K,N] = sum_m A[m,k] * G[m,n]; conv=1: K = 9*C taps; partial scratch sized by gemm_tn_scratch()
+size_t gemm_tn_scratch(int M, int K, int N, int conv);
+void gemm_tn(const GemmA& A, const float* G, int ldg, float* dW, float* dbias /* nullable: sum_m G */, float* scratch,
+             int M, int K, int N, int HW, cudaStream_t s);
+// Wt[N,K] <- W[K,N]   and   3x3: Wf[tap][n][c] <- W[8-tap][c][n]
+void transpose_w(const float* w, float* wt, int K, int N, cudaStream_t s);
+void flip_transpose_w3x3(const float* w, float* wt, int C, int N, cudaStream_t s);
+
+// ---------------- misc (k_misc.cu) ----------------
+struct ResizeTab { const int32_t* lo; const int32_t* hi; const float* lerp;   // [n_out]
+                   const int32_t* g_lo; const int32_t* g_hi; };                // [n_in] gather ranges (bwd)
+void bilinear_fwd(const float* x, int ldx, float* y, int ldy, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                  ResizeTab ty, ResizeTab tx, cudaStream_t s);
+void bilinear_bwd(const float* dy, int lddy, float* dx, int lddx, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                  ResizeTab ty, ResizeTab tx, cudaStream_t s);
+
+void head_fwd(const float* x, int ldx, const float* w, const float* bias, const float* drop_mask, float keep_scale,
+              float* z, int M, int C, cudaStream_t s);
+void head_bwd(const float* x, int ldx, const float* w, const float* drop_mask, float keep_scale, const float* dz,
+              float* dx, int lddx, float* partials, float* dw, float* db, int M, int C, cudaStream_t s);
+
+struct LossArgs {
+  const float* z_lo;          // [B,h,w,2] low-res logits
+  const float* labels;        // pool [n,H,W,2]
+  const int32_t* index;       // [B] or null
+  int B, h, w, H, W;
+  ResizeTab ty, tx;
+  int dice; float label_smoothing;
+  float* p1;                  // [B,H,W] scratch: softmax prob of channel 1
+  float* partials;            // [B][G][4]
+  float* coef;                // [B][2] + loss at [2B]
+  float* dz_hi;               // [B,H,W,2]
+  float* loss_out;            // nullable
+  const float* theta; int64_t n_l2; float l2_coef;   // for the reported loss value only
+};
+void loss_fwd_bwd(const LossArgs& a, cudaStream_t s);
+
+void predict_mask_iou(const float* z_lo, const float* labels, const int32_t* index, int B, int h, int w, int H,
+                      int W, ResizeTab ty, ResizeTab tx, float* pred_out, float* logits_out, uint32_t* inter,
+                      uint32_t* uni, cudaStream_t s);
+
+// optimizer (ApplyAdam beta1=0 / ApplyGradientDescent) over the flat buffer; hyper = {b1p, b2p} device scalars
+void scale_buffer(float* x, int64_t n, float s, cudaStream_t st);
+void adam_step(float* theta, float* v, const float* g, int64_t n, int64_t n_l2, const float* lr_dev, float* powers,
+               float l2_coef, int sgd, cudaStream_t s);
+void delta_accumulate(float* dsum, const float* a, const float* b, int64_t n, int first, cudaStream_t s);
+void meta_apply(float* theta, const float* dsum, float scale, int64_t n, cudaStream_t s);
+void reduce_partials(const float* partials, int G, int n, float* out, cudaStream_t s);
+void fill_dropout_mask(float* mask, int64_t n, float rate, uint64_t seed, cudaStream_t s);
+
+}  // namespace mliis
