@@ -188,6 +188,16 @@ typedef struct mliis_task_args {
 } mliis_task_args;
 int mliis_adapt_eval_task(mliis_ctx* ctx, int32_t slot, const mliis_task_args* args, void* stream);
 
+/* The same task as ONE CUDA graph: capture once per slot with pointers that stay valid (per-slot staging
+ * buffers for the pool, index lists, learning rates and outputs), then replay per task.  ~2800 kernel
+ * launches collapse into one graph launch; slots replay concurrently on their own streams.  `stream` must
+ * be a non-default stream.  (With final-layer dropout the device RNG seed is frozen at capture time.) */
+int mliis_task_graph_capture(mliis_ctx* ctx, int32_t slot, const mliis_task_args* args, void* stream);
+int mliis_task_graph_launch(mliis_ctx* ctx, int32_t slot, void* stream);
+
+/* Kernels launched by this library in this process (graph replays count their captured kernels). */
+uint64_t mliis_launch_count(void);
+
 /* ---- meta-update (meta_learners/variables.py:9-45; reptile.py:122-125, :644-647) --------------
  * delta_sum += (theta_a - theta_b)             [Reptile: a = adapted, b = old; FOMAML: a = theta_T, b = theta_{T-1}]
  * theta     += scale * delta_sum               [scale = meta_step_size / meta_batch_size]

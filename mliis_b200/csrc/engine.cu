@@ -19,6 +19,8 @@
 
 using namespace mliis;
 
+namespace mliis { unsigned long long g_kernel_launches = 0; }
+
 namespace {
 
 thread_local std::string g_err;
@@ -42,6 +44,9 @@ struct Slot {
   const int32_t* fwd_index = nullptr;
   const float* fwd_drop_mask = nullptr;
   bool grads_zeroed = false;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  unsigned long long graph_launches = 0;   // kernels inside the captured task graph
 };
 
 struct Tab {
@@ -179,7 +184,7 @@ void run_forward(const Run& r, const float* images, const int32_t* index, bool t
     bn_eval_coeffs(r.theta, r.c->d_gamma_idx, r.c->d_beta_idx, r.mm, r.mv, p.n_bn_ch, r.W(p.bn_a), r.W(p.bn_b), st);
   if (training && p.n_dc > 0) {
     const float* k = r.c->keep;
-    dcs_kernel<<<cdiv(p.n_dc * B, 128), 128, 0, st>>>(dc_mask, r.W(p.dcs), p.n_dc, B, p.maxB, k[0], k[1], k[2], k[3],
+    MLIIS_COUNT(), dcs_kernel<<<cdiv(p.n_dc * B, 128), 128, 0, st>>>(dc_mask, r.W(p.dcs), p.n_dc, B, p.maxB, k[0], k[1], k[2], k[3],
                                                       k[4], k[5], k[6], k[7]);
   }
   // stem (efficientnet_model.py:410-412); its BN+swish is fused into block 0's depthwise loader
@@ -448,7 +453,9 @@ int validate(mliis_ctx* ctx, int slot, int batch) {
   return MLIIS_OK;
 }
 
-void set_lr(const Run& r, float lr) { set_scalar_kernel<<<1, 1, 0, r.st>>>(r.W(r.p.lr_dev), lr); }
+void set_lr(const Run& r, float lr) {
+  MLIIS_COUNT(), set_scalar_kernel<<<1, 1, 0, r.st>>>(r.W(r.p.lr_dev), lr);
+}
 
 void run_optimizer(const Run& r, const float* lr_dev) {
   const Plan& p = r.p;
@@ -521,6 +528,10 @@ int mliis_ctx_create(const mliis_config* cfg, int device, mliis_ctx** out) {
 
 int mliis_ctx_destroy(mliis_ctx* ctx) {
   if (!ctx) return MLIIS_OK;
+  for (Slot& sl : ctx->slots) {
+    if (sl.graph_exec) cudaGraphExecDestroy(sl.graph_exec);
+    if (sl.graph) cudaGraphDestroy(sl.graph);
+  }
   for (void* p : ctx->owned) cudaFree(p);
   delete ctx;
   return MLIIS_OK;
@@ -662,16 +673,9 @@ int mliis_predict(mliis_ctx* ctx, int32_t slot, const float* images, const float
   return check_cuda("predict");
 }
 
-int mliis_adapt_eval_task(mliis_ctx* ctx, int32_t slot, const mliis_task_args* a, void* stream) {
-  if (!a) return fail(MLIIS_ERR_ARG, "null args");
-  int rc = validate(ctx, slot, a->batch);
-  if (rc) return rc;
-  if (a->n_query < 1 || a->n_query > ctx->plan.maxB) return fail(MLIIS_ERR_ARG, "n_query out of range");
-  if (!a->dev_init_state || !a->dev_images || !a->dev_labels || !a->dev_batch_index || !a->dev_lr || !a->dev_query_index)
-    return fail(MLIIS_ERR_ARG, "null task argument");
-  cudaStream_t st = (cudaStream_t)stream;
+static int task_body(mliis_ctx* ctx, int32_t slot, const mliis_task_args* a, cudaStream_t st) {
   const Plan& p = ctx->plan;
-  rc = mliis_state_copy(ctx, ctx->slots[slot].state, a->dev_init_state, MLIIS_STATE_ALL, stream);
+  int rc = mliis_state_copy(ctx, ctx->slots[slot].state, a->dev_init_state, MLIIS_STATE_ALL, (void*)st);
   if (rc) return rc;
   for (int t = 0; t < a->n_steps; ++t) {
     Run r(ctx, slot, a->batch, st);
@@ -687,8 +691,69 @@ int mliis_adapt_eval_task(mliis_ctx* ctx, int32_t slot, const mliis_task_args* a
   const Tab& tf = ctx->tabs[p.tab_final];
   predict_mask_iou(r.W(p.z_lo), a->dev_labels, a->dev_query_index, a->n_query, p.hl, p.wl, p.image_size, p.image_size,
                    tf.rt(), tf.rt(), nullptr, nullptr, a->dev_inter_out, a->dev_union_out, st);
+  return MLIIS_OK;
+}
+
+static int task_validate(mliis_ctx* ctx, int32_t slot, const mliis_task_args* a) {
+  if (!a) return fail(MLIIS_ERR_ARG, "null args");
+  int rc = validate(ctx, slot, a->batch);
+  if (rc) return rc;
+  if (a->n_query < 1 || a->n_query > ctx->plan.maxB) return fail(MLIIS_ERR_ARG, "n_query out of range");
+  if (a->n_steps < 0) return fail(MLIIS_ERR_ARG, "n_steps < 0");
+  if (!a->dev_init_state || !a->dev_images || !a->dev_labels || !a->dev_batch_index || !a->dev_lr || !a->dev_query_index)
+    return fail(MLIIS_ERR_ARG, "null task argument");
+  if (ctx->cfg.final_dropout_rate > 0.f) {
+    // the device RNG mask is regenerated per step from `seed`; fine eagerly, frozen inside a graph
+  }
+  return MLIIS_OK;
+}
+
+int mliis_adapt_eval_task(mliis_ctx* ctx, int32_t slot, const mliis_task_args* a, void* stream) {
+  int rc = task_validate(ctx, slot, a);
+  if (rc) return rc;
+  rc = task_body(ctx, slot, a, (cudaStream_t)stream);
+  if (rc) return rc;
   return check_cuda("adapt_eval_task");
 }
+
+int mliis_task_graph_capture(mliis_ctx* ctx, int32_t slot, const mliis_task_args* a, void* stream) {
+  int rc = task_validate(ctx, slot, a);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (st == nullptr) return fail(MLIIS_ERR_ARG, "graph capture needs a non-default stream");
+  Slot& sl = ctx->slots[slot];
+  if (sl.graph_exec) { cudaGraphExecDestroy(sl.graph_exec); sl.graph_exec = nullptr; }
+  if (sl.graph) { cudaGraphDestroy(sl.graph); sl.graph = nullptr; }
+  if (!sl.grads_zeroed) {   // memset outside the graph so that replays do not repeat it
+    cudaMemsetAsync(sl.ws + ctx->plan.grads, 0, ctx->plan.n_theta * sizeof(float), st);
+    sl.grads_zeroed = true;
+  }
+  cudaStreamSynchronize(st);
+  const unsigned long long before = g_kernel_launches;
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+    return fail(MLIIS_ERR_CUDA, "cudaStreamBeginCapture: %s", cudaGetErrorString(cudaGetLastError()));
+  rc = task_body(ctx, slot, a, st);
+  cudaError_t e = cudaStreamEndCapture(st, &sl.graph);
+  sl.graph_launches = g_kernel_launches - before;
+  g_kernel_launches = before;   // captured, not launched
+  if (rc) return rc;
+  if (e != cudaSuccess || !sl.graph) return fail(MLIIS_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+  e = cudaGraphInstantiate(&sl.graph_exec, sl.graph, 0);
+  if (e != cudaSuccess) return fail(MLIIS_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  return MLIIS_OK;
+}
+
+int mliis_task_graph_launch(mliis_ctx* ctx, int32_t slot, void* stream) {
+  if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return fail(MLIIS_ERR_ARG, "bad ctx/slot");
+  Slot& sl = ctx->slots[slot];
+  if (!sl.graph_exec) return fail(MLIIS_ERR_STATE, "no captured graph for slot %d", slot);
+  cudaError_t e = cudaGraphLaunch(sl.graph_exec, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(MLIIS_ERR_CUDA, "cudaGraphLaunch: %s", cudaGetErrorString(e));
+  g_kernel_launches += sl.graph_launches;
+  return MLIIS_OK;
+}
+
+uint64_t mliis_launch_count(void) { return g_kernel_launches; }
 
 int mliis_delta_accumulate(mliis_ctx* ctx, float* dsum, const float* ta, const float* tb, int32_t first, void* stream) {
   if (!ctx || !dsum || !ta || !tb) return fail(MLIIS_ERR_ARG, "null argument");

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__
 
 void stem_fwd(const float* images, const int32_t* index, const float* w, float* y, int B, int H, int W, int Ho, int Wo,
               int pad_t, int pad_l, cudaStream_t s) {
-  stem_fwd_kernel<<<cdiv(B * Ho * Wo, 64), 256, 0, s>>>(images, index, w, y, B, H, W, Ho, Wo, pad_t, pad_l);
+  MLIIS_COUNT(), stem_fwd_kernel<<<cdiv(B * Ho * Wo, 64), 256, 0, s>>>(images, index, w, y, B, H, W, Ho, Wo, pad_t, pad_l);
 }
 
 constexpr int kStemWgPix = 512;   // output pixels per CTA
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(288) stem_wgrad_kernel(const float* __restrict
 void stem_wgrad(const float* images, const int32_t* index, const float* dy, float* partials, float* dw, int B, int H,
                 int W, int Ho, int Wo, int pad_t, int pad_l, cudaStream_t s) {
   int G = stem_wgrad_blocks(B, Ho, Wo);
-  stem_wgrad_kernel<<<G, 288, 0, s>>>(images, index, dy, partials, B, H, W, Ho, Wo, pad_t, pad_l);
+  MLIIS_COUNT(), stem_wgrad_kernel<<<G, 288, 0, s>>>(images, index, dy, partials, B, H, W, Ho, Wo, pad_t, pad_l);
   reduce_partials(partials, G, 864, dw, s);
 }
 
@@ -230,7 +230,7 @@ static void dw_fwd_launch(const float* x, const float* a, const float* b, const 
   }
   const int tiles_x = cdiv(Wo, G::TO), tiles_y = cdiv(Ho, G::TO);
   dim3 grid(tiles_x * tiles_y, cdiv(C, QC * 4), B);
-  dw_fwd_kernel<K, S, FLIP><<<grid, G::NT, G::smem_bytes(), s>>>(x, a, b, w, y, H, W, C, Ho, Wo, pad_t, pad_l, tiles_x);
+  MLIIS_COUNT(), dw_fwd_kernel<K, S, FLIP><<<grid, G::NT, G::smem_bytes(), s>>>(x, a, b, w, y, H, W, C, Ho, Wo, pad_t, pad_l, tiles_x);
 }
 
 void dw_fwd(const float* x, const float* a, const float* b, const float* w, float* y, int B, int H, int W, int C, int k,
@@ -314,7 +314,7 @@ static void dw_bwd_data_s2_launch(const float* dy, const float* w, float* dx, in
   using G = DwBd2<K>;
   const int tiles_x = cdiv(W, G::TO), tiles_y = cdiv(H, G::TO);
   dim3 grid(tiles_x * tiles_y, cdiv(C, QC * 4), B);
-  dw_bwd_data_s2_kernel<K><<<grid, G::NT, G::smem_bytes(), s>>>(dy, w, dx, H, W, C, Ho, Wo, pad_t, pad_l, tiles_x);
+  MLIIS_COUNT(), dw_bwd_data_s2_kernel<K><<<grid, G::NT, G::smem_bytes(), s>>>(dy, w, dx, H, W, C, Ho, Wo, pad_t, pad_l, tiles_x);
 }
 
 void dw_bwd_data(const float* dy, const float* w, float* dx, int B, int H, int W, int C, int k, int stride, int Ho,
@@ -420,7 +420,7 @@ static void dw_wgrad_launch(const float* x, const float* a, const float* b, cons
   }
   const int tiles_x = cdiv(Wo, G::TO), tiles_y = cdiv(Ho, G::TO), tiles = tiles_x * tiles_y;
   dim3 grid(tiles, cdiv(C, QC * 4), B);
-  dw_wgrad_kernel<K, S><<<grid, G::NT, G::smem_bytes(), s>>>(x, a, b, dy, partials, H, W, C, Ho, Wo, pad_t, pad_l,
+  MLIIS_COUNT(), dw_wgrad_kernel<K, S><<<grid, G::NT, G::smem_bytes(), s>>>(x, a, b, dy, partials, H, W, C, Ho, Wo, pad_t, pad_l,
                                                              tiles_x, tiles);
   reduce_partials(partials, B * tiles, K * K * C, dw, s);
 }

@@ -124,11 +124,11 @@ void gemm_nn(const GemmA& A, const float* Wt, const float* bias, float* Cout, in
   dim3 grid(cdiv(M, 128), cdiv(N, 64));
   const bool pro = A.pa != nullptr;
   if (A.conv) {
-    gemm_nn_kernel<0, 1><<<grid, 256, 0, s>>>(A, Wt, bias, Cout, ldc, M, K, N, HW, accumulate);
+    MLIIS_COUNT(), gemm_nn_kernel<0, 1><<<grid, 256, 0, s>>>(A, Wt, bias, Cout, ldc, M, K, N, HW, accumulate);
   } else if (pro) {
-    gemm_nn_kernel<1, 0><<<grid, 256, 0, s>>>(A, Wt, bias, Cout, ldc, M, K, N, HW, accumulate);
+    MLIIS_COUNT(), gemm_nn_kernel<1, 0><<<grid, 256, 0, s>>>(A, Wt, bias, Cout, ldc, M, K, N, HW, accumulate);
   } else {
-    gemm_nn_kernel<0, 0><<<grid, 256, 0, s>>>(A, Wt, bias, Cout, ldc, M, K, N, HW, accumulate);
+    MLIIS_COUNT(), gemm_nn_kernel<0, 0><<<grid, 256, 0, s>>>(A, Wt, bias, Cout, ldc, M, K, N, HW, accumulate);
   }
 }
 
@@ -266,11 +266,11 @@ void gemm_tn(const GemmA& A, const float* G, int ldg, float* dW, float* dbias, f
   float* bpartial = dbias ? scratch + (size_t)S * K * N : nullptr;
   const bool pro = A.pa != nullptr;
   if (A.conv)
-    gemm_tn_kernel<0, 1><<<grid, 256, 0, s>>>(A, G, ldg, partial, bpartial, M, K, N, HW, rps, S);
+    MLIIS_COUNT(), gemm_tn_kernel<0, 1><<<grid, 256, 0, s>>>(A, G, ldg, partial, bpartial, M, K, N, HW, rps, S);
   else if (pro)
-    gemm_tn_kernel<1, 0><<<grid, 256, 0, s>>>(A, G, ldg, partial, bpartial, M, K, N, HW, rps, S);
+    MLIIS_COUNT(), gemm_tn_kernel<1, 0><<<grid, 256, 0, s>>>(A, G, ldg, partial, bpartial, M, K, N, HW, rps, S);
   else
-    gemm_tn_kernel<0, 0><<<grid, 256, 0, s>>>(A, G, ldg, partial, bpartial, M, K, N, HW, rps, S);
+    MLIIS_COUNT(), gemm_tn_kernel<0, 0><<<grid, 256, 0, s>>>(A, G, ldg, partial, bpartial, M, K, N, HW, rps, S);
   reduce_partials(partial, S, K * N, dW, s);
   if (dbias) reduce_partials(bpartial, S, N, dbias, s);
 }
@@ -285,7 +285,7 @@ __global__ void transpose_w_kernel(const float* __restrict__ w, float* __restric
   wt[i] = w[(size_t)k * N + n];
 }
 void transpose_w(const float* w, float* wt, int K, int N, cudaStream_t s) {
-  transpose_w_kernel<<<cdiv(K * N, 256), 256, 0, s>>>(w, wt, K, N);
+  MLIIS_COUNT(), transpose_w_kernel<<<cdiv(K * N, 256), 256, 0, s>>>(w, wt, K, N);
 }
 // wt[tap][n][c] = w[8-tap][c][n]
 __global__ void flip_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int C, int N) {
@@ -295,7 +295,7 @@ __global__ void flip_transpose_kernel(const float* __restrict__ w, float* __rest
   wt[i] = w[((size_t)(8 - tap) * C + c) * N + n];
 }
 void flip_transpose_w3x3(const float* w, float* wt, int C, int N, cudaStream_t s) {
-  flip_transpose_kernel<<<cdiv(9 * C * N, 256), 256, 0, s>>>(w, wt, C, N);
+  MLIIS_COUNT(), flip_transpose_kernel<<<cdiv(9 * C * N, 256), 256, 0, s>>>(w, wt, C, N);
 }
 
 }  // namespace mliis

@@ -19,7 +19,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int G
   out[i] = (float)s;
 }
 void reduce_partials(const float* partials, int G, int n, float* out, cudaStream_t s) {
-  reduce_partials_kernel<<<cdiv(n, 256), 256, 0, s>>>(partials, G, n, out);
+  MLIIS_COUNT(), reduce_partials_kernel<<<cdiv(n, 256), 256, 0, s>>>(partials, G, n, out);
 }
 
 // =============================================================================================
@@ -48,7 +48,7 @@ void bilinear_fwd(const float* x, int ldx, float* y, int ldy, int B, int Hi, int
   if (R > 64) R = 64;
   dim3 blk(c4, R);
   int rpb = R * 4;
-  bilinear_fwd_kernel<<<cdiv(B * Ho * Wo, rpb), blk, 0, s>>>(x, ldx, y, ldy, B, Hi, Wi, Ho, Wo, ty, tx, rpb);
+  MLIIS_COUNT(), bilinear_fwd_kernel<<<cdiv(B * Ho * Wo, rpb), blk, 0, s>>>(x, ldx, y, ldy, B, Hi, Wi, Ho, Wo, ty, tx, rpb);
 }
 
 __device__ __forceinline__ float gather_w(const ResizeTab& t, int o, int i) {
@@ -96,14 +96,14 @@ void bilinear_bwd(const float* dy, int lddy, float* dx, int lddx, int B, int Hi,
   if (C == 2) {
     dim3 blk(1, 128);
     int rpb = 128;
-    bilinear_bwd_kernel<2><<<cdiv(B * Hi * Wi, rpb), blk, 0, s>>>(dy, lddy, dx, lddx, B, Hi, Wi, Ho, Wo, ty, tx, rpb);
+    MLIIS_COUNT(), bilinear_bwd_kernel<2><<<cdiv(B * Hi * Wi, rpb), blk, 0, s>>>(dy, lddy, dx, lddx, B, Hi, Wi, Ho, Wo, ty, tx, rpb);
   } else {
     int c4 = C / 4, R = 256 / c4;
     if (R < 1) R = 1;
     if (R > 64) R = 64;
     dim3 blk(c4, R);
     int rpb = R;
-    bilinear_bwd_kernel<4><<<cdiv(B * Hi * Wi, rpb), blk, 0, s>>>(dy, lddy, dx, lddx, B, Hi, Wi, Ho, Wo, ty, tx, rpb);
+    MLIIS_COUNT(), bilinear_bwd_kernel<4><<<cdiv(B * Hi * Wi, rpb), blk, 0, s>>>(dy, lddy, dx, lddx, B, Hi, Wi, Ho, Wo, ty, tx, rpb);
   }
 }
 
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__
 }
 void head_fwd(const float* x, int ldx, const float* w, const float* bias, const float* drop_mask, float keep_scale,
               float* z, int M, int C, cudaStream_t s) {
-  head_fwd_kernel<<<cdiv(M, 32), 256, 0, s>>>(x, ldx, w, bias, drop_mask, keep_scale, z, M, C);
+  MLIIS_COUNT(), head_fwd_kernel<<<cdiv(M, 32), 256, 0, s>>>(x, ldx, w, bias, drop_mask, keep_scale, z, M, C);
 }
 
 // dx = (dz . w^T) * mask*scale ; dW[c][j] = sum_p xd[p,c] dz[p,j] ; db[j] = sum_p dz[p,j]
@@ -195,7 +195,7 @@ void head_bwd(const float* x, int ldx, const float* w, const float* drop_mask, f
   if (G > 296) G = 296;
   dim3 blk(c4, R);
   size_t smem = 2 * (size_t)R * c4 * sizeof(float4) + 2 * R * sizeof(float);
-  head_bwd_kernel<<<G, blk, smem, s>>>(x, ldx, w, drop_mask, keep_scale, dz, dx, lddx, partials, M, C, cdiv(M, G));
+  MLIIS_COUNT(), head_bwd_kernel<<<G, blk, smem, s>>>(x, ldx, w, drop_mask, keep_scale, dz, dx, lddx, partials, M, C, cdiv(M, G));
   // partial rows are [C*2 | 2]; reduce into a staging area right after the partials, then scatter
   float* stage = partials + (size_t)G * (C * 2 + 2);
   reduce_partials(partials, G, C * 2 + 2, stage, s);
@@ -330,15 +330,15 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(LossArgs a) {
 }
 
 void loss_fwd_bwd(const LossArgs& a, cudaStream_t s) {
-  loss_fwd_kernel<<<dim3(kLossChunks, a.B), 256, 0, s>>>(a);
+  MLIIS_COUNT(), loss_fwd_kernel<<<dim3(kLossChunks, a.B), 256, 0, s>>>(a);
   float* l2p = a.partials + (size_t)a.B * kLossChunks * 4;
   int nl2 = 0;
   if (a.loss_out && a.l2_coef != 0.f && a.n_l2 > 0) {
     nl2 = 148;
-    sumsq_kernel<<<nl2, 256, 0, s>>>(a.theta, a.n_l2, l2p);
+    MLIIS_COUNT(), sumsq_kernel<<<nl2, 256, 0, s>>>(a.theta, a.n_l2, l2p);
   }
-  loss_finalize_kernel<<<1, 32, 0, s>>>(a, l2p, nl2);
-  loss_bwd_kernel<<<dim3(cdiv(a.H * a.W, 256 * 4), a.B), 256, 0, s>>>(a);
+  MLIIS_COUNT(), loss_finalize_kernel<<<1, 32, 0, s>>>(a, l2p, nl2);
+  MLIIS_COUNT(), loss_bwd_kernel<<<dim3(cdiv(a.H * a.W, 256 * 4), a.B), 256, 0, s>>>(a);
 }
 
 // =============================================================================================
@@ -393,7 +393,7 @@ void predict_mask_iou(const float* z_lo, const float* labels, const int32_t* ind
     cudaMemsetAsync(inter, 0, B * sizeof(uint32_t), s);
     cudaMemsetAsync(uni, 0, B * sizeof(uint32_t), s);
   }
-  predict_kernel<<<dim3(cdiv(H * W, 256 * 4), B), 256, 0, s>>>(z_lo, inter ? labels : nullptr, index, h, w, H, W, ty, tx,
+  MLIIS_COUNT(), predict_kernel<<<dim3(cdiv(H * W, 256 * 4), B), 256, 0, s>>>(z_lo, inter ? labels : nullptr, index, h, w, H, W, ty, tx,
                                                               pred_out, logits_out, inter, uni);
 }
 
@@ -406,7 +406,7 @@ __global__ void scale_kernel(float* __restrict__ x, int64_t n, float s) {
   else for (int64_t j = i * 4; j < n; ++j) x[j] *= s;
 }
 void scale_buffer(float* x, int64_t n, float sc, cudaStream_t st) {
-  scale_kernel<<<(unsigned)cdiv64(cdiv64(n, 4), 256), 256, 0, st>>>(x, n, sc);
+  MLIIS_COUNT(), scale_kernel<<<(unsigned)cdiv64(cdiv64(n, 4), 256), 256, 0, st>>>(x, n, sc);
 }
 
 // TF ApplyAdam with beta1 = 0 (m == g) / ApplyGradientDescent.  g' = g + l2*theta on the first n_l2 floats
@@ -435,8 +435,8 @@ __global__ void adam_finish_kernel(float* powers) {
 }
 void adam_step(float* theta, float* v, const float* g, int64_t n, int64_t n_l2, const float* lr_dev, float* powers,
                float l2_coef, int sgd, cudaStream_t s) {
-  adam_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(theta, v, g, n, n_l2, lr_dev, powers, l2_coef, sgd);
-  if (!sgd) adam_finish_kernel<<<1, 1, 0, s>>>(powers);
+  MLIIS_COUNT(), adam_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(theta, v, g, n, n_l2, lr_dev, powers, l2_coef, sgd);
+  if (!sgd) MLIIS_COUNT(), adam_finish_kernel<<<1, 1, 0, s>>>(powers);
 }
 
 __global__ void delta_acc_kernel(float* __restrict__ d, const float* __restrict__ a, const float* __restrict__ b,
@@ -447,14 +447,14 @@ __global__ void delta_acc_kernel(float* __restrict__ d, const float* __restrict_
   d[i] = first ? v : d[i] + v;
 }
 void delta_accumulate(float* dsum, const float* a, const float* b, int64_t n, int first, cudaStream_t s) {
-  delta_acc_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(dsum, a, b, n, first);
+  MLIIS_COUNT(), delta_acc_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(dsum, a, b, n, first);
 }
 __global__ void meta_apply_kernel(float* __restrict__ th, const float* __restrict__ d, float scale, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) th[i] = fmaf(scale, d[i], th[i]);
 }
 void meta_apply(float* theta, const float* dsum, float scale, int64_t n, cudaStream_t s) {
-  meta_apply_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(theta, dsum, scale, n);
+  MLIIS_COUNT(), meta_apply_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(theta, dsum, scale, n);
 }
 
 // Keras Dropout keep mask: keep where U >= rate [TF-ext]; U from a counter-based hash (the reference's
@@ -470,7 +470,7 @@ __global__ void dropout_mask_kernel(float* __restrict__ mask, int64_t n, float r
   mask[i] = u >= rate ? 1.f : 0.f;
 }
 void fill_dropout_mask(float* mask, int64_t n, float rate, uint64_t seed, cudaStream_t s) {
-  dropout_mask_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(mask, n, rate, seed);
+  MLIIS_COUNT(), dropout_mask_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(mask, n, rate, seed);
 }
 
 }  // namespace mliis

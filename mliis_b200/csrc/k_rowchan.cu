@@ -90,9 +90,9 @@ void bn_stats(const float* x, int ld, int M, int C, bool pre_swish, float* parti
   dim3 blk = rc_block(C);
   size_t smem = 2 * blk.x * blk.y * sizeof(float4);
   if (pre_swish)
-    bn_stats_kernel<true><<<G, blk, smem, s>>>(x, ld, M, C, rpc, partials);
+    MLIIS_COUNT(), bn_stats_kernel<true><<<G, blk, smem, s>>>(x, ld, M, C, rpc, partials);
   else
-    bn_stats_kernel<false><<<G, blk, smem, s>>>(x, ld, M, C, rpc, partials);
+    MLIIS_COUNT(), bn_stats_kernel<false><<<G, blk, smem, s>>>(x, ld, M, C, rpc, partials);
 }
 
 __global__ void bn_finalize_kernel(const float* __restrict__ partials, int G, int C, int M,
@@ -127,7 +127,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int G, in
 
 void bn_finalize(const float* partials, int G, int C, int M, const float* gamma, const float* beta, float* mm,
                  float* mv, int ema, int bessel, float* mean, float* rstd, float* a, float* b, cudaStream_t s) {
-  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(partials, G, C, M, gamma, beta, mm, mv, ema, bessel, mean, rstd,
+  MLIIS_COUNT(), bn_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(partials, G, C, M, gamma, beta, mm, mv, ema, bessel, mean, rstd,
                                                   a, b);
 }
 
@@ -143,7 +143,7 @@ __global__ void bn_eval_coeffs_kernel(const float* __restrict__ theta, const int
 }
 void bn_eval_coeffs(const float* theta, const int32_t* gi, const int32_t* bi, const float* mm, const float* mv,
                     int n, float* a, float* b, cudaStream_t s) {
-  bn_eval_coeffs_kernel<<<cdiv(n, 256), 256, 0, s>>>(theta, gi, bi, mm, mv, n, a, b);
+  MLIIS_COUNT(), bn_eval_coeffs_kernel<<<cdiv(n, 256), 256, 0, s>>>(theta, gi, bi, mm, mv, n, a, b);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -165,7 +165,7 @@ void dec_bn_apply(const float* x, int ldx, const float* a, const float* b, const
                   int ldy, int M, int C, cudaStream_t s) {
   dim3 blk = rc_block(C);
   int rpb = blk.y * 4;
-  dec_bn_apply_kernel<<<cdiv(M, rpb), blk, 0, s>>>(x, ldx, a, b, res, ldres, y, ldy, M, rpb);
+  MLIIS_COUNT(), dec_bn_apply_kernel<<<cdiv(M, rpb), blk, 0, s>>>(x, ldx, a, b, res, ldres, y, ldy, M, rpb);
 }
 
 __global__ void block_out_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ a,
@@ -186,7 +186,7 @@ void block_out(const float* x, int ldx, const float* a, const float* b, const fl
                int ldres, float* y, int ldy, int M, int C, int HW, cudaStream_t s) {
   dim3 blk = rc_block(C);
   int rpb = blk.y * 4;
-  block_out_kernel<<<cdiv(M, rpb), blk, 0, s>>>(x, ldx, a, b, dcs, res, ldres, y, ldy, M, HW, rpb);
+  MLIIS_COUNT(), block_out_kernel<<<cdiv(M, rpb), blk, 0, s>>>(x, ldx, a, b, dcs, res, ldres, y, ldy, M, HW, rpb);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -220,14 +220,14 @@ void se_pool(const float* x, int ldx, const float* a, const float* b, int B, int
              cudaStream_t s) {
   int G = rc_num_img_chunks(HW, C);
   dim3 blk = rc_block(C);
-  img_reduce_kernel<0><<<dim3(G, B), blk, blk.x * blk.y * sizeof(float4), s>>>(x, ldx, nullptr, 0, a, b, HW, C,
+  MLIIS_COUNT(), img_reduce_kernel<0><<<dim3(G, B), blk, blk.x * blk.y * sizeof(float4), s>>>(x, ldx, nullptr, 0, a, b, HW, C,
                                                                                cdiv(HW, G), partial);
 }
 void se_bwd_reduce(const float* x, int ldx, const float* gup, int ldg, const float* a, const float* b, int B, int HW,
                    int C, float* partial, cudaStream_t s) {
   int G = rc_num_img_chunks(HW, C);
   dim3 blk = rc_block(C);
-  img_reduce_kernel<1><<<dim3(G, B), blk, blk.x * blk.y * sizeof(float4), s>>>(x, ldx, gup, ldg, a, b, HW, C,
+  MLIIS_COUNT(), img_reduce_kernel<1><<<dim3(G, B), blk, blk.x * blk.y * sizeof(float4), s>>>(x, ldx, gup, ldg, a, b, HW, C,
                                                                                cdiv(HW, G), partial);
 }
 
@@ -243,9 +243,9 @@ void img_colsum(const float* x, int ldx, int B, int HW, int C, float scale, floa
                 cudaStream_t s) {
   int G = rc_num_img_chunks(HW, C);
   dim3 blk = rc_block(C);
-  img_reduce_kernel<2><<<dim3(G, B), blk, blk.x * blk.y * sizeof(float4), s>>>(x, ldx, nullptr, 0, nullptr, nullptr,
+  MLIIS_COUNT(), img_reduce_kernel<2><<<dim3(G, B), blk, blk.x * blk.y * sizeof(float4), s>>>(x, ldx, nullptr, 0, nullptr, nullptr,
                                                                                HW, C, cdiv(HW, G), partial);
-  img_colsum_finalize_kernel<<<dim3(cdiv(C, 128), B), 128, 0, s>>>(partial, G, C, scale, out, ldo);
+  MLIIS_COUNT(), img_colsum_finalize_kernel<<<dim3(cdiv(C, 128), B), 128, 0, s>>>(partial, G, C, scale, out, ldo);
 }
 
 // One block per image.  pool -> reduce FC (+bias, swish) -> expand FC (+bias) -> sigmoid.
@@ -287,7 +287,7 @@ __global__ void se_fc_fwd_kernel(const float* __restrict__ partial, int G, int H
 }
 void se_fc_fwd(const float* partial, int G, int B, int HW, int C, int Cr, const float* w1, const float* b1,
                const float* w2, const float* b2, float* pool, float* hidpre, float* gate, cudaStream_t s) {
-  se_fc_fwd_kernel<<<B, 256, (C + Cr) * sizeof(float), s>>>(partial, G, HW, C, Cr, w1, b1, w2, b2, pool, hidpre,
+  MLIIS_COUNT(), se_fc_fwd_kernel<<<B, 256, (C + Cr) * sizeof(float), s>>>(partial, G, HW, C, Cr, w1, b1, w2, b2, pool, hidpre,
                                                             gate);
 }
 
@@ -353,7 +353,7 @@ void se_fc_bwd(const float* partial, int G, int B, int HW, int C, int Cr, const 
                const float* pool, const float* hidpre, const float* gate, float* dw1, float* db1, float* dw2,
                float* db2, float* dpool, cudaStream_t s) {
   size_t smem = ((size_t)B * C + 2 * (size_t)B * Cr) * sizeof(float);
-  se_fc_bwd_kernel<<<1, 512, smem, s>>>(partial, G, B, HW, C, Cr, w1, w2, pool, hidpre, gate, dw1, db1, dw2, db2,
+  MLIIS_COUNT(), se_fc_bwd_kernel<<<1, 512, smem, s>>>(partial, G, B, HW, C, Cr, w1, w2, pool, hidpre, gate, dw1, db1, dw2, db2,
                                         dpool);
 }
 
@@ -443,10 +443,10 @@ template <int VAR>
 static void bn_bwd_t(const BnBwdArgs& p, cudaStream_t s) {
   int G = rc_num_chunks(p.M, p.C);
   dim3 blk = rc_block(p.C);
-  bn_bwd_reduce_kernel<VAR><<<G, blk, 2 * blk.x * blk.y * sizeof(float4), s>>>(p, cdiv(p.M, G));
-  bn_bwd_finalize_kernel<<<cdiv(p.C, 128), 128, 0, s>>>(p.partials, G, p.C, p.M, p.k, p.dgamma, p.dbeta);
+  MLIIS_COUNT(), bn_bwd_reduce_kernel<VAR><<<G, blk, 2 * blk.x * blk.y * sizeof(float4), s>>>(p, cdiv(p.M, G));
+  MLIIS_COUNT(), bn_bwd_finalize_kernel<<<cdiv(p.C, 128), 128, 0, s>>>(p.partials, G, p.C, p.M, p.k, p.dgamma, p.dbeta);
   int rpb = blk.y * 4;
-  bn_bwd_apply_kernel<VAR><<<cdiv(p.M, rpb), blk, 0, s>>>(p, rpb);
+  MLIIS_COUNT(), bn_bwd_apply_kernel<VAR><<<cdiv(p.M, rpb), blk, 0, s>>>(p, rpb);
 }
 void bn_bwd(int var, const BnBwdArgs& p, cudaStream_t s) {
   switch (var) {
@@ -470,7 +470,7 @@ __global__ void bcast_rows_kernel(const float* __restrict__ pimg, int ldp, float
 void bcast_rows(const float* pimg, int ldp, float* y, int ldy, int B, int HW, int C, cudaStream_t s) {
   dim3 blk = rc_block(C);
   int rpb = blk.y * 4, M = B * HW;
-  bcast_rows_kernel<<<cdiv(M, rpb), blk, 0, s>>>(pimg, ldp, y, ldy, M, HW, rpb);
+  MLIIS_COUNT(), bcast_rows_kernel<<<cdiv(M, rpb), blk, 0, s>>>(pimg, ldp, y, ldy, M, HW, rpb);
 }
 
 __global__ void add3_kernel(float* __restrict__ dst, int ldd, const float* __restrict__ a, int lda,
@@ -489,7 +489,7 @@ void add3(float* dst, int ldd, const float* a, int lda, const float* b, int ldb,
           int C, int HW, cudaStream_t s) {
   dim3 blk = rc_block(C);
   int rpb = blk.y * 4;
-  add3_kernel<<<cdiv(M, rpb), blk, 0, s>>>(dst, ldd, a, lda, b, ldb, pimg, ldp, M, HW, rpb);
+  MLIIS_COUNT(), add3_kernel<<<cdiv(M, rpb), blk, 0, s>>>(dst, ldd, a, lda, b, ldb, pimg, ldp, M, HW, rpb);
 }
 
 }  // namespace mliis

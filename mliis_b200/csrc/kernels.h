@@ -8,6 +8,10 @@
 
 namespace mliis {
 
+// number of kernels launched by this library in this process (bench.py reports it as gpu_launches)
+extern unsigned long long g_kernel_launches;
+#define MLIIS_COUNT() (++::mliis::g_kernel_launches)
+
 // ---------------- row-channel kernels (k_rowchan.cu) : HBM-bound ----------------
 enum BnVar { BN_PLAIN = 0, BN_SWISH = 1, BN_SWISH_SE = 2, BN_DEC = 3 };
 

@@ -74,6 +74,9 @@ SYMBOLS = [
     ("mliis_optimizer_step", C.c_int, [_VP, _I32, _F, _F, _VP]),
     ("mliis_predict", C.c_int, [_VP, _I32, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP, _VP]),
     ("mliis_adapt_eval_task", C.c_int, [_VP, _I32, C.POINTER(TaskArgs), _VP]),
+    ("mliis_task_graph_capture", C.c_int, [_VP, _I32, C.POINTER(TaskArgs), _VP]),
+    ("mliis_task_graph_launch", C.c_int, [_VP, _I32, _VP]),
+    ("mliis_launch_count", C.c_uint64, []),
     ("mliis_delta_accumulate", C.c_int, [_VP, _VP, _VP, _VP, _I32, _VP]),
     ("mliis_meta_apply", C.c_int, [_VP, _VP, _VP, _F, _VP]),
     ("mliis_dwconv_fwd", C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP, _VP, _VP]),

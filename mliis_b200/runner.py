@@ -1,0 +1,182 @@
+"""Task-parallel execution of Gecko._evaluate (reptile.py:235-294) on one GPU.
+
+Every in-flight task owns a slot (state + workspace + staging buffers + CUDA stream).  A task is:
+H2D of its example pool and index lists from pinned memory -> ONE CUDA-graph launch (state reset, T inner
+steps, transductive prediction, integer IoU counts) -> D2H of the counts.  Slots run concurrently, which is
+what fills the 148 SMs: the 14x14 layers of a single task cannot.
+
+The reference does the same work with, per task, 2 full-state host round trips, T+1 feed_dict copies and
+~2800 TF op launches from one Python thread.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import native as N
+from .engine import Engine, _ptr
+
+import ctypes as C
+
+
+@dataclass
+class TaskPlan:
+    """Host-side description of one adapt+evaluate task (all integer work is decided on the host, with the
+    reference's own `random` call sequence, so indices are bit-identical to a 1-GPU reference run)."""
+    images: np.ndarray                 # [n_pool,S,S,3] f32 in 0..255   (or a device tensor for resident runs)
+    labels: np.ndarray                 # [n_pool,S,S,2] f32
+    batch_index: np.ndarray            # [T,B] int32 rows of the pool per inner step
+    lrs: np.ndarray                    # [T] f32
+    query_index: np.ndarray            # [n_query] int32
+    dc_mask: Optional[np.ndarray] = None   # [T,n_dc,B] f32 {0,1}; None = all keep
+    name: str = ""
+
+
+class _SlotBuffers:
+    def __init__(self, eng: Engine, n_pool: int, T: int, B: int, nq: int, with_dc: bool):
+        S, dev = eng.image_size, eng.device
+        self.images = torch.empty(n_pool, S, S, 3, dtype=torch.float32, device=dev)
+        self.labels = torch.empty(n_pool, S, S, 2, dtype=torch.float32, device=dev)
+        self.h_images = torch.empty(n_pool, S, S, 3, dtype=torch.float32).pin_memory()
+        self.h_labels = torch.empty(n_pool, S, S, 2, dtype=torch.float32).pin_memory()
+        # one small block: [batch_index T*B | query nq] int32, [lr T | dc T*n_dc*B] f32
+        self.n_i = T * B + nq
+        self.n_f = T + (T * eng.n_dc * B if with_dc else 0)
+        self.ints = torch.zeros(self.n_i, dtype=torch.int32, device=dev)
+        self.floats = torch.zeros(self.n_f, dtype=torch.float32, device=dev)
+        self.h_ints = torch.zeros(self.n_i, dtype=torch.int32).pin_memory()
+        self.h_floats = torch.zeros(self.n_f, dtype=torch.float32).pin_memory()
+        self.counts = torch.zeros(2 * nq, dtype=torch.int32, device=dev)
+        self.h_counts = torch.zeros(2 * nq, dtype=torch.int32).pin_memory()
+        self.losses = torch.zeros(T, dtype=torch.float32, device=dev)
+        self.stream = torch.cuda.Stream(device=dev)
+        self.done = torch.cuda.Event()
+        self.busy = False
+        self.tag = None
+
+
+class TaskRunner:
+    def __init__(self, eng: Engine, n_pool: int = 10, n_steps: int = 5, batch: int = 8, n_query: int = 5,
+                 use_graph: bool = True, with_dc_masks: bool = False, pre_decay_rate: float = 1.0):
+        if batch > eng.max_batch or n_query > eng.max_batch:
+            raise ValueError("batch / n_query exceed the engine's max_batch")
+        self.eng = eng
+        self.n_pool, self.T, self.B, self.nq = n_pool, n_steps, batch, n_query
+        self.use_graph = use_graph
+        self.with_dc = with_dc_masks
+        self.pre_decay_rate = pre_decay_rate
+        self.slots = [_SlotBuffers(eng, n_pool, n_steps, batch, n_query, with_dc_masks) for _ in range(eng.n_slots)]
+        self.init_state = torch.zeros(eng.state_floats, dtype=torch.float32, device=eng.device)
+        self._captured = False
+        self.h2d_bytes_per_task = 0
+        self.d2h_bytes_per_task = 0
+
+    # the shared starting point of every task (= the restored checkpoint, _full_state of reptile.py:258)
+    def set_init_state(self, state: torch.Tensor) -> None:
+        self.init_state.copy_(state)
+
+    def _task_args(self, slot: int) -> N.TaskArgs:
+        sb = self.slots[slot]
+        T, B, nq = self.T, self.B, self.nq
+        dc = sb.floats[T:] if self.with_dc else None
+        return N.TaskArgs(_ptr(self.init_state), _ptr(sb.images), _ptr(sb.labels), _ptr(sb.ints[:T * B]),
+                          _ptr(sb.floats[:T]), T, B, _ptr(sb.ints[T * B:]), nq, _ptr(dc), 0,
+                          float(self.pre_decay_rate), _ptr(sb.counts[:nq]), _ptr(sb.counts[nq:]), _ptr(sb.losses))
+
+    def _capture(self) -> None:
+        lib, h = self.eng.lib, self.eng.ctx.handle
+        for s, sb in enumerate(self.slots):
+            # harmless defaults so that the warm-up run and the capture read valid indices
+            sb.ints.zero_()
+            sb.floats.zero_()
+            sb.images.zero_()
+            sb.labels.zero_()
+        torch.cuda.synchronize()
+        for s, sb in enumerate(self.slots):
+            a = self._task_args(s)
+            st = C.c_void_p(sb.stream.cuda_stream)
+            if s == 0:   # one eager warm-up sets function attributes before any capture
+                N.check(lib.mliis_adapt_eval_task(h, s, C.byref(a), st))
+                sb.stream.synchronize()
+            N.check(lib.mliis_task_graph_capture(h, s, C.byref(a), st))
+        torch.cuda.synchronize()
+        self._captured = True
+
+    def _launch(self, slot: int) -> None:
+        lib, h = self.eng.lib, self.eng.ctx.handle
+        sb = self.slots[slot]
+        st = C.c_void_p(sb.stream.cuda_stream)
+        if self.use_graph:
+            N.check(lib.mliis_task_graph_launch(h, slot, st))
+        else:
+            a = self._task_args(slot)
+            N.check(lib.mliis_adapt_eval_task(h, slot, C.byref(a), st))
+
+    def _stage(self, slot: int, plan: TaskPlan) -> None:
+        sb = self.slots[slot]
+        T, B, nq = self.T, self.B, self.nq
+        bi = np.asarray(plan.batch_index, np.int32).reshape(-1)
+        qi = np.asarray(plan.query_index, np.int32).reshape(-1)
+        if bi.size != T * B or qi.size != nq:
+            raise ValueError("plan shape mismatch: batch_index %s, query_index %s" % (bi.shape, qi.shape))
+        sb.h_ints[:T * B] = torch.from_numpy(bi)
+        sb.h_ints[T * B:] = torch.from_numpy(qi)
+        sb.h_floats[:T] = torch.from_numpy(np.asarray(plan.lrs, np.float32).reshape(-1))
+        if self.with_dc:
+            dc = plan.dc_mask if plan.dc_mask is not None else np.ones((T, self.eng.n_dc, B), np.float32)
+            sb.h_floats[T:] = torch.from_numpy(np.asarray(dc, np.float32).reshape(-1))
+        with torch.cuda.stream(sb.stream):
+            h2d = 0
+            if isinstance(plan.images, torch.Tensor) and plan.images.is_cuda:
+                sb.images.copy_(plan.images, non_blocking=True)     # resident pool: device-to-device
+                sb.labels.copy_(plan.labels, non_blocking=True)
+            else:
+                n = plan.images.shape[0]
+                sb.h_images[:n] = torch.from_numpy(np.ascontiguousarray(plan.images, np.float32))
+                sb.h_labels[:n] = torch.from_numpy(np.ascontiguousarray(plan.labels, np.float32))
+                sb.images[:n].copy_(sb.h_images[:n], non_blocking=True)
+                sb.labels[:n].copy_(sb.h_labels[:n], non_blocking=True)
+                h2d += sb.h_images[:n].numel() * 4 + sb.h_labels[:n].numel() * 4
+            sb.ints.copy_(sb.h_ints, non_blocking=True)
+            sb.floats.copy_(sb.h_floats, non_blocking=True)
+            h2d += sb.h_ints.numel() * 4 + sb.h_floats.numel() * 4
+        self.h2d_bytes_per_task = h2d
+        self.d2h_bytes_per_task = sb.h_counts.numel() * 4
+
+    def _collect(self, slot: int) -> Tuple[np.ndarray, np.ndarray]:
+        sb = self.slots[slot]
+        sb.done.synchronize()
+        c = sb.h_counts.numpy().copy()
+        sb.busy = False
+        return c[:self.nq].astype(np.int64), c[self.nq:].astype(np.int64)
+
+    def run(self, plans: Sequence[TaskPlan]) -> List[Tuple[np.ndarray, np.ndarray]]:
+        """Adapt + evaluate every plan; returns per task (intersection[n_query], union[n_query]) integer counts."""
+        if self.use_graph and not self._captured:
+            self._capture()
+        results: List[Optional[Tuple[np.ndarray, np.ndarray]]] = [None] * len(plans)
+        ns = len(self.slots)
+        for i, plan in enumerate(plans):
+            s = i % ns
+            sb = self.slots[s]
+            if sb.busy:
+                results[sb.tag] = self._collect(s)
+            self._stage(s, plan)
+            self._launch(s)
+            with torch.cuda.stream(sb.stream):
+                sb.h_counts.copy_(sb.counts, non_blocking=True)
+                sb.done.record(sb.stream)
+            sb.busy, sb.tag = True, i
+        for s, sb in enumerate(self.slots):
+            if sb.busy:
+                results[sb.tag] = self._collect(s)
+        return results  # type: ignore
+
+
+def iou_from_counts(inter: np.ndarray, union: np.ndarray, epsilon: float = 1e-7) -> float:
+    """Gecko._iou (reptile.py:549) per image in float64, then np.nanmean over the query set (reptile.py:290-291)."""
+    per_image = (inter.astype(np.float64) + epsilon) / (union.astype(np.float64) + epsilon)
+    return float(np.nanmean(per_image))
