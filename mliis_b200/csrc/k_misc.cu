@@ -11,15 +11,22 @@ namespace mliis {
 // =============================================================================================
 // generic partial reducer (fixed order, double accumulation)
 // =============================================================================================
-__global__ void reduce_partials_kernel(const float* __restrict__ partials, int G, int n, float* __restrict__ out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// blockDim = (32 outputs, 8 partial lanes); coalesced over outputs, fixed-order combine over lanes.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int G, int n,
+                                                              float* __restrict__ out) {
+  __shared__ double red[8][33];
+  const int i = blockIdx.x * 32 + threadIdx.x;
   double s = 0.0;
-  for (int g = 0; g < G; ++g) s += (double)partials[(size_t)g * n + i];
+  if (i < n)
+    for (int g = threadIdx.y; g < G; g += 8) s += (double)partials[(size_t)g * n + i];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y != 0 || i >= n) return;
+  for (int j = 1; j < 8; ++j) s += red[j][threadIdx.x];
   out[i] = (float)s;
 }
 void reduce_partials(const float* partials, int G, int n, float* out, cudaStream_t s) {
-  MLIIS_COUNT(), reduce_partials_kernel<<<cdiv(n, 256), 256, 0, s>>>(partials, G, n, out);
+  MLIIS_COUNT(), reduce_partials_kernel<<<cdiv(n, 32), dim3(32, 8), 0, s>>>(partials, G, n, out);
 }
 
 // =============================================================================================

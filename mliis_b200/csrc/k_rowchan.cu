@@ -95,18 +95,27 @@ void bn_stats(const float* x, int ld, int M, int C, bool pre_swish, float* parti
     MLIIS_COUNT(), bn_stats_kernel<false><<<G, blk, smem, s>>>(x, ld, M, C, rpc, partials);
 }
 
-__global__ void bn_finalize_kernel(const float* __restrict__ partials, int G, int C, int M,
+// blockDim = (32 channels, 16 partial lanes): each thread sums every 16th partial in double, then the 16
+// lanes are combined in a fixed order through shared memory (deterministic).
+__global__ void __launch_bounds__(512) bn_finalize_kernel(const float* __restrict__ partials, int G, int C, int M,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ mm, float* __restrict__ mv, int ema, int bessel,
                                    float* __restrict__ mean_o, float* __restrict__ rstd_o, float* __restrict__ a_o,
                                    float* __restrict__ b_o) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ double red[2][16][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   double s = 0.0, ss = 0.0;
-  for (int g = 0; g < G; ++g) {
-    s += (double)partials[((size_t)g * 2 + 0) * C + c];
-    ss += (double)partials[((size_t)g * 2 + 1) * C + c];
+  if (c < C) {
+    for (int g = threadIdx.y; g < G; g += 16) {
+      s += (double)partials[((size_t)g * 2 + 0) * C + c];
+      ss += (double)partials[((size_t)g * 2 + 1) * C + c];
+    }
   }
+  red[0][threadIdx.y][threadIdx.x] = s;
+  red[1][threadIdx.y][threadIdx.x] = ss;
+  __syncthreads();
+  if (threadIdx.y != 0 || c >= C) return;
+  for (int j = 1; j < 16; ++j) { s += red[0][j][threadIdx.x]; ss += red[1][j][threadIdx.x]; }
   double mean = s / M;
   double var = ss / M - mean * mean;   // biased (tf.nn.moments)
   if (var < 0.0) var = 0.0;
@@ -127,8 +136,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int G, in
 
 void bn_finalize(const float* partials, int G, int C, int M, const float* gamma, const float* beta, float* mm,
                  float* mv, int ema, int bessel, float* mean, float* rstd, float* a, float* b, cudaStream_t s) {
-  MLIIS_COUNT(), bn_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(partials, G, C, M, gamma, beta, mm, mv, ema, bessel, mean, rstd,
-                                                  a, b);
+  MLIIS_COUNT(), bn_finalize_kernel<<<cdiv(C, 32), dim3(32, 16), 0, s>>>(partials, G, C, M, gamma, beta, mm, mv, ema,
+                                                                        bessel, mean, rstd, a, b);
 }
 
 __global__ void bn_eval_coeffs_kernel(const float* __restrict__ theta, const int32_t* __restrict__ gi,
@@ -291,70 +300,81 @@ void se_fc_fwd(const float* partial, int G, int B, int HW, int C, int Cr, const 
                                                             gate);
 }
 
-// Single block: gradients of the two SE FCs and of the pooled input.
-__global__ void se_fc_bwd_kernel(const float* __restrict__ partial, int G, int B, int HW, int C, int Cr,
-                                 const float* __restrict__ w1, const float* __restrict__ w2,
-                                 const float* __restrict__ pool, const float* __restrict__ hidpre,
-                                 const float* __restrict__ gate, float* __restrict__ dw1, float* __restrict__ db1,
-                                 float* __restrict__ dw2, float* __restrict__ db2, float* __restrict__ dpool) {
+// SE FC backward, phase A (one block per image): d(gate pre-act), d(hidden pre-act), d(pool).
+__global__ void __launch_bounds__(256) se_fc_bwd_img_kernel(const float* __restrict__ partial, int G, int HW, int C,
+                                                             int Cr, const float* __restrict__ w1,
+                                                             const float* __restrict__ w2,
+                                                             const float* __restrict__ hidpre,
+                                                             const float* __restrict__ gate, float* __restrict__ dgp_o,
+                                                             float* __restrict__ dhp_o, float* __restrict__ dpool) {
   extern __shared__ float smf[];
-  float* dgp = smf;                 // [B][C]   d(gate pre-activation)
-  float* hid = dgp + (size_t)B * C;   // [B][Cr]
-  float* dhp = hid + (size_t)B * Cr;  // [B][Cr]  d(hidden pre-activation)
-  const int tid = threadIdx.x, nt = blockDim.x;
-  for (int i = tid; i < B * C; i += nt) {
-    int b = i / C, c = i - b * C;
+  float* dgp = smf;        // [C]
+  float* dhp = smf + C;    // [Cr]
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  for (int c = tid; c < C; c += nt) {
     float s = 0.f;
     for (int g = 0; g < G; ++g) s += partial[((size_t)b * G + g) * C + c];
-    float gt = gate[i];
-    dgp[i] = s * gt * (1.f - gt);
+    const float gt = gate[(size_t)b * C + c];
+    const float v = s * gt * (1.f - gt);
+    dgp[c] = v;
+    dgp_o[(size_t)b * C + c] = v;
   }
-  for (int i = tid; i < B * Cr; i += nt) hid[i] = swish_f(hidpre[i]);
   __syncthreads();
-  for (int c = tid; c < C; c += nt) {
-    float sb = 0.f;
-    for (int b = 0; b < B; ++b) sb += dgp[b * C + c];
-    db2[c] = sb;
-    for (int r = 0; r < Cr; ++r) {
-      float s = 0.f;
-      for (int b = 0; b < B; ++b) s = fmaf(hid[b * Cr + r], dgp[b * C + c], s);
-      dw2[(size_t)r * C + c] = s;
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  for (int r = warp; r < Cr; r += nw) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(w2[(size_t)r * C + c], dgp[c], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      const float v = s * swish_grad_f(hidpre[(size_t)b * Cr + r]);
+      dhp[r] = v;
+      dhp_o[(size_t)b * Cr + r] = v;
     }
   }
-  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-  for (int i = warp; i < B * Cr; i += nw) {
-    int b = i / Cr, r = i - b * Cr;
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s = fmaf(w2[(size_t)r * C + c], dgp[b * C + c], s);
-    s = warp_sum(s);
-    if (lane == 0) dhp[i] = s * swish_grad_f(hidpre[i]);
-  }
   __syncthreads();
-  for (int r = tid; r < Cr; r += nt) {
-    float s = 0.f;
-    for (int b = 0; b < B; ++b) s += dhp[b * Cr + r];
-    db1[r] = s;
-  }
-  for (int i = tid; i < C * Cr; i += nt) {
-    int c = i / Cr, r = i - c * Cr;
-    float s = 0.f;
-    for (int b = 0; b < B; ++b) s = fmaf(pool[(size_t)b * C + c], dhp[b * Cr + r], s);
-    dw1[i] = s;
-  }
   const float inv = 1.f / (float)HW;
-  for (int i = tid; i < B * C; i += nt) {
-    int b = i / C, c = i - b * C;
+  for (int c = tid; c < C; c += nt) {
     float s = 0.f;
-    for (int r = 0; r < Cr; ++r) s = fmaf(w1[(size_t)c * Cr + r], dhp[b * Cr + r], s);
-    dpool[i] = s * inv;
+    for (int r = 0; r < Cr; ++r) s = fmaf(w1[(size_t)c * Cr + r], dhp[r], s);
+    dpool[(size_t)b * C + c] = s * inv;
+  }
+}
+// phase B (grid over channel chunks): weight / bias gradients, summed over the batch in a fixed order.
+__global__ void __launch_bounds__(128) se_fc_bwd_w_kernel(int B, int C, int Cr, const float* __restrict__ pool,
+                                                           const float* __restrict__ hidpre,
+                                                           const float* __restrict__ dgp, const float* __restrict__ dhp,
+                                                           float* __restrict__ dw1, float* __restrict__ db1,
+                                                           float* __restrict__ dw2, float* __restrict__ db2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    float sb = 0.f;
+    for (int b = 0; b < B; ++b) sb += dgp[(size_t)b * C + c];
+    db2[c] = sb;
+    for (int r = 0; r < Cr; ++r) {
+      float s2 = 0.f, s1 = 0.f;
+      for (int b = 0; b < B; ++b) {
+        s2 = fmaf(swish_f(hidpre[(size_t)b * Cr + r]), dgp[(size_t)b * C + c], s2);
+        s1 = fmaf(pool[(size_t)b * C + c], dhp[(size_t)b * Cr + r], s1);
+      }
+      dw2[(size_t)r * C + c] = s2;
+      dw1[(size_t)c * Cr + r] = s1;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < Cr) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dhp[(size_t)b * Cr + threadIdx.x];
+    db1[threadIdx.x] = s;
   }
 }
 void se_fc_bwd(const float* partial, int G, int B, int HW, int C, int Cr, const float* w1, const float* w2,
                const float* pool, const float* hidpre, const float* gate, float* dw1, float* db1, float* dw2,
                float* db2, float* dpool, cudaStream_t s) {
-  size_t smem = ((size_t)B * C + 2 * (size_t)B * Cr) * sizeof(float);
-  MLIIS_COUNT(), se_fc_bwd_kernel<<<1, 512, smem, s>>>(partial, G, B, HW, C, Cr, w1, w2, pool, hidpre, gate, dw1, db1, dw2, db2,
-                                        dpool);
+  // scratch for dgp [B][C] and dhp [B][Cr] lives right after the dgate partials
+  float* dgp = const_cast<float*>(partial) + (size_t)B * G * C;
+  float* dhp = dgp + (size_t)B * C;
+  MLIIS_COUNT(), se_fc_bwd_img_kernel<<<B, 256, (C + Cr) * sizeof(float), s>>>(partial, G, HW, C, Cr, w1, w2, hidpre, gate, dgp,
+                                                                              dhp, dpool);
+  MLIIS_COUNT(), se_fc_bwd_w_kernel<<<cdiv(C, 128), 128, 0, s>>>(B, C, Cr, pool, hidpre, dgp, dhp, dw1, db1, dw2, db2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -406,16 +426,23 @@ __global__ void bn_bwd_reduce_kernel(BnBwdArgs p, int rows_per_chunk) {
   }
 }
 
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int G, int C, int M,
+__global__ void __launch_bounds__(512) bn_bwd_finalize_kernel(const float* __restrict__ partials, int G, int C, int M,
                                        float* __restrict__ k, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ double red[2][16][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   double s0 = 0.0, s1 = 0.0;
-  for (int g = 0; g < G; ++g) {
-    s0 += (double)partials[((size_t)g * 2 + 0) * C + c];
-    s1 += (double)partials[((size_t)g * 2 + 1) * C + c];
+  if (c < C) {
+    for (int g = threadIdx.y; g < G; g += 16) {
+      s0 += (double)partials[((size_t)g * 2 + 0) * C + c];
+      s1 += (double)partials[((size_t)g * 2 + 1) * C + c];
+    }
   }
+  red[0][threadIdx.y][threadIdx.x] = s0;
+  red[1][threadIdx.y][threadIdx.x] = s1;
+  __syncthreads();
+  if (threadIdx.y != 0 || c >= C) return;
+  for (int j = 1; j < 16; ++j) { s0 += red[0][j][threadIdx.x]; s1 += red[1][j][threadIdx.x]; }
   dbeta[c] = (float)s0;
   dgamma[c] = (float)s1;
   k[c] = (float)(s0 / M);
@@ -444,7 +471,7 @@ static void bn_bwd_t(const BnBwdArgs& p, cudaStream_t s) {
   int G = rc_num_chunks(p.M, p.C);
   dim3 blk = rc_block(p.C);
   MLIIS_COUNT(), bn_bwd_reduce_kernel<VAR><<<G, blk, 2 * blk.x * blk.y * sizeof(float4), s>>>(p, cdiv(p.M, G));
-  MLIIS_COUNT(), bn_bwd_finalize_kernel<<<cdiv(p.C, 128), 128, 0, s>>>(p.partials, G, p.C, p.M, p.k, p.dgamma, p.dbeta);
+  MLIIS_COUNT(), bn_bwd_finalize_kernel<<<cdiv(p.C, 32), dim3(32, 16), 0, s>>>(p.partials, G, p.C, p.M, p.k, p.dgamma, p.dbeta);
   int rpb = blk.y * 4;
   MLIIS_COUNT(), bn_bwd_apply_kernel<VAR><<<cdiv(p.M, rpb), blk, 0, s>>>(p, rpb);
 }

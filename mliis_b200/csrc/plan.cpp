@@ -261,7 +261,7 @@ void Plan::build(int image_size_, int max_batch, const int* rsd, float final_dro
     upd(max_partials, (int64_t)rc_num_chunks(B * HWi, bp.ce) * 2 * bp.ce);
     upd(max_partials, (int64_t)rc_num_chunks(B * HWo, bp.ce) * 2 * bp.ce);
     upd(max_partials, (int64_t)rc_num_chunks(B * HWo, bp.cout) * 2 * bp.cout);
-    upd(max_partials, (int64_t)B * rc_num_img_chunks(HWo, bp.ce) * bp.ce);
+    upd(max_partials, (int64_t)B * rc_num_img_chunks(HWo, bp.ce) * bp.ce + (int64_t)B * (bp.ce + bp.cr) + 64);
     upd(max_partials, (int64_t)dw_wgrad_blocks(B, bp.Hout, bp.Wout, bp.stride) * bp.k * bp.k * bp.ce);
     if (bp.expand) {
       upd(max_tn, (int64_t)gemm_tn_scratch(B * HWi, bp.cin, bp.ce, 0));

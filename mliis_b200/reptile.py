@@ -1,0 +1,417 @@
+"""Gecko (Reptile) and FOMLIS (FOMAML) meta-learners for image segmentation.
+
+Mirror of /root/reference/meta_learners/supervised_reptile/supervised_reptile/reptile.py: the same classes,
+constructor and method signatures, the same order of calls into Python's ``random`` (so task / split /
+mini-batch indices are bit-identical to the reference under the same seed), the same return values.
+
+Two execution paths produce the same results:
+  * the Session path follows the reference line by line (sess.run per inner step, export/import of variables
+    through host numpy) - used when a feature outside the device fast path is requested (augmentation,
+    per-task checkpoints, non-transductive evaluation);
+  * the device fast path keeps theta / BN statistics / optimizer slots on the GPU: `evaluate` turns every task
+    into a TaskPlan executed by runner.TaskRunner (one CUDA graph per task, tasks sharded over slots and
+    ranks), `train_step` accumulates the per-task deltas with mliis_delta_accumulate, all-reduces them over
+    NCCL when world_size > 1 and applies theta += eps/M * sum(delta) with mliis_meta_apply.
+"""
+from __future__ import annotations
+
+import os
+import random
+from typing import Dict, List, Optional, Tuple, Union
+
+import numpy as np
+
+from . import native as N
+from .metaseg import (DEFAULT_NUM_TEST_EXAMPLES, _mini_batches, _sample_mini_image_segmentation_dataset,
+                      _sample_task_indices, _sample_train_test_segmentation_with_replacement,
+                      _split_train_test_segmentation)
+from .variables import (VariableState, add_vars, average_vars, interpolate_vars, scale_vars, subtract_vars)
+
+DEFAULT_ITER_RANGE = [1, 5, 10, 25, 50, 100, 200]
+
+
+def _dist():
+    """(rank, world) of the task-parallel group; (0, 1) when torch.distributed is not initialised."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return 0, 1
+
+
+class Gecko:
+    """A meta-learning session for image segmentation that extends Reptile (reptile.py:23-62)."""
+
+    def __init__(self, session, variables=None, transductive=False, pre_step_op=None, lr_scheduler=None,
+                 augment: bool = False, aug_rate: Optional[float] = None, fast_path: bool = True):
+        self.session = session
+        model = session.model
+        self._model = model
+        self._model_state = VariableState(session, variables or model.trainable_variables())
+        self._full_state = VariableState(session, model.global_variables())
+        self._transductive = transductive
+        self._pre_step_op = pre_step_op
+        self.eval_sample_number = 0
+        self.lr_scheduler = lr_scheduler
+        if augment:
+            raise NotImplementedError("numpy augmentations (augmenters/np_augmenters.py) are out of scope: they use "
+                                      "the unseeded np.random stream; parity configs run with --augment off")
+        self.augmenter = None
+        self.aug_rate = aug_rate
+        self.fast_path = fast_path
+        self._runner = None
+        print("Augmentation rate {}".format(self.aug_rate))
+        print("Using transduction in meta-learning." if transductive else "Not using transduction in meta-learning.")
+        self.meta_fn = "Reptile"
+        print("Reptile meta-learning session instantiated.")
+
+    # ------------------------------------------------------------------------------------------
+    # helpers shared by both paths
+    # ------------------------------------------------------------------------------------------
+    def _next_seed(self) -> int:
+        # dropout seeds come from a private counter: Python's `random` stream must stay reference-identical
+        self._seed_counter = getattr(self, "_seed_counter", 0) + 1
+        return self._seed_counter
+
+    def _pre_decay(self) -> float:
+        return float(self._pre_step_op.rate) if self._pre_step_op is not None else 1.0
+
+    def _inner_lr(self, lr_ph, lr, step: int, eval_mode: bool) -> float:
+        """Learning rate one inner step runs with (reptile.py:269-279 for evaluation, :114-121 for training)."""
+        default = self._model.lr_ph.default
+        if lr_ph is not None and lr is not None:
+            return float(lr)
+        if lr_ph is not None and self.lr_scheduler is not None:
+            return float(self.lr_scheduler.cur_lr(cur_step=step))
+        return float(default)
+
+    def _get_runner(self, n_pool, n_steps, batch, n_query):
+        from .runner import TaskRunner
+        key = (n_pool, n_steps, batch, n_query, self._pre_decay())
+        if self._runner is None or self._runner[0] != key:
+            eng = self._model.engine()
+            self._runner = (key, TaskRunner(eng, n_pool, n_steps, batch, n_query, use_graph=True,
+                                            pre_decay_rate=self._pre_decay()))
+        return self._runner[1]
+
+    # ------------------------------------------------------------------------------------------
+    # meta-training step (reptile.py:64-125)
+    # ------------------------------------------------------------------------------------------
+    def train_step(self, dataset, input_ph, label_ph, minimize_op, num_classes, num_shots, inner_batch_size,
+                   inner_iters, replacement, meta_step_size, meta_batch_size, lr_ph=None, lr=None, verbose=False):
+        num_classes = 1      # hardcoded binary Gecko (reptile.py:99-100)
+        if self.fast_path:
+            return self._train_step_device(dataset, num_shots, inner_batch_size, inner_iters, replacement,
+                                           meta_step_size, meta_batch_size, lr_ph, lr, fomaml=False)
+        old_vars = self._model_state.export_variables()
+        new_vars = []
+        for _ in range(meta_batch_size):
+            mini_dataset = _sample_mini_image_segmentation_dataset(self.session, dataset, num_classes, num_shots)
+            for i, batch in enumerate(_mini_batches(mini_dataset, inner_batch_size, inner_iters, replacement,
+                                                    augmenter=self.augmenter)):
+                inputs, labels = zip(*batch)
+                if self._pre_step_op:
+                    self.session.run(self._pre_step_op)
+                # NB the reference's `if ... if ... else` (reptile.py:114-121): with lr given and no scheduler the
+                # minimize op runs TWICE per batch (once with lr, once with the default lr)
+                if (lr_ph is not None) and (lr is not None):
+                    self.session.run(minimize_op, feed_dict={input_ph: inputs, label_ph: labels, lr_ph: lr})
+                if (lr_ph is not None) and (self.lr_scheduler is not None):
+                    self.session.run(minimize_op, feed_dict={input_ph: inputs, label_ph: labels,
+                                                             lr_ph: self.lr_scheduler.cur_lr(cur_step=i)})
+                else:
+                    self.session.run(minimize_op, feed_dict={input_ph: inputs, label_ph: labels})
+            new_vars.append(self._model_state.export_variables())
+            self._model_state.import_variables(old_vars)
+        new_vars = average_vars(new_vars)
+        self._model_state.import_variables(interpolate_vars(old_vars, new_vars, meta_step_size))
+
+    def _task_batches_for_training(self, rows, inner_batch_size, inner_iters, replacement):
+        """Index batches of one meta-training task; overridden by FOMLIS (tail batch)."""
+        return list(_mini_batches(rows, inner_batch_size, inner_iters, replacement, augmenter=None))
+
+    def _train_lrs(self, lr_ph, lr, n_batches) -> List[List[float]]:
+        """Per batch, the learning rates of the minimize runs the reference performs (reptile.py:114-121)."""
+        out = []
+        for i in range(n_batches):
+            runs = []
+            if (lr_ph is not None) and (lr is not None):
+                runs.append(float(lr))
+            if (lr_ph is not None) and (self.lr_scheduler is not None):
+                runs.append(float(self.lr_scheduler.cur_lr(cur_step=i)))
+            else:
+                runs.append(float(self._model.lr_ph.default))
+            out.append(runs)
+        return out
+
+    def _train_step_device(self, dataset, num_shots, inner_batch_size, inner_iters, replacement, meta_step_size,
+                           meta_batch_size, lr_ph, lr, fomaml: bool):
+        """Device-resident meta-step.  world_size == 1 reproduces the reference's sequential carry-over of the
+        optimizer slots / BN moving statistics between the tasks of a meta-batch exactly; with more ranks the
+        tasks are dealt round-robin, each rank carries its own slots, and the summed deltas (and the BN moving
+        statistics) are all-reduced once per meta-step."""
+        import torch
+        eng = self._model.engine()
+        rank, world = _dist()
+        theta = eng.theta(0)
+        old = theta.clone()
+        dsum = torch.zeros_like(theta)
+        backup = torch.empty_like(theta) if fomaml else None
+        n_local = 0
+        for t in range(meta_batch_size):
+            # every rank draws every task so that the `random` stream stays identical across ranks
+            task, rows = _sample_task_indices(dataset, num_shots)
+            batches = self._task_batches_for_training(rows, inner_batch_size, inner_iters, replacement)
+            if t % world != rank:
+                continue
+            images, labels = task.arrays()
+            x = torch.from_numpy(images[:len(rows)]).to(eng.device, non_blocking=True)
+            y = torch.from_numpy(labels[:len(rows)]).to(eng.device, non_blocking=True)
+            lrs = self._fomaml_lrs(lr_ph, lr, len(batches)) if fomaml else self._train_lrs(lr_ph, lr, len(batches))
+            for j, batch in enumerate(batches):
+                idx = torch.tensor(batch, dtype=torch.int32, device=eng.device)
+                if fomaml and j == inner_iters - 1:
+                    backup.copy_(theta)                      # last_backup (reptile.py:635-636)
+                for k, step_lr in enumerate(lrs[j]):
+                    eng.train_step(0, x, y, step_lr, index=idx, pre_decay_rate=self._pre_decay() if k == 0 else 1.0,
+                                   seed=self._next_seed())
+            eng.delta_accumulate(dsum, theta, backup if fomaml else old, first=(n_local == 0))
+            n_local += 1
+            theta.copy_(old)                                 # import_variables(old_vars): trainables only
+        from .runner import allreduce_meta
+        allreduce_meta(dsum, eng.bn_state(0))                # one all-reduce of P floats per meta-step
+        eng.meta_apply(theta, dsum, float(meta_step_size) / float(meta_batch_size))
+
+    def _fomaml_lrs(self, lr_ph, lr, n_batches):
+        d = float(self._model.lr_ph.default)
+        return [[float(lr)] if (lr_ph is not None and lr is not None) else [d] for _ in range(n_batches)]
+
+    # ------------------------------------------------------------------------------------------
+    # evaluation (reptile.py:127-294)
+    # ------------------------------------------------------------------------------------------
+    def evaluate(self, dataset, input_ph, label_ph, minimize_op, predictions, num_classes, num_shots,
+                 inner_batch_size, inner_iters, replacement, eval_all_tasks=False, num_tasks_to_sample=1,
+                 test_shots=DEFAULT_NUM_TEST_EXAMPLES, verbose=False, save_fine_tuned_checkpoints=False,
+                 save_fine_tuned_checkpoints_dir: Optional[str] = None, eval_sample_num: Optional[int] = None,
+                 is_training_ph=None, lr_ph=None, lr: Optional[float] = None, drop_rate_ph=None,
+                 drop_rate: Optional[float] = None, aug_rate: Optional[float] = None) -> Tuple[float, Dict[str, float]]:
+        print("Evaluating {} meta-learning.".format(self.meta_fn))
+        if aug_rate is None:
+            aug_rate = self.aug_rate
+        if eval_all_tasks:
+            sampled_tasks = dataset
+        else:
+            random.shuffle(dataset)        # in place, like the reference (reptile.py:186-188)
+            sampled_tasks = dataset[:num_tasks_to_sample]
+        print("Evaluating {} {}-shot tasks.".format(len(sampled_tasks), num_shots))
+        if save_fine_tuned_checkpoints:
+            raise NotImplementedError("per-task fine-tuned checkpoints (utils/util.py:72-81) are out of scope")
+        device_ok = (self.fast_path and self._transductive and is_training_ph is not None and drop_rate is None
+                     and inner_iters > 0 and all(hasattr(t, "arrays") for t in sampled_tasks))
+        if device_ok:
+            ious, task_iou_map = self._evaluate_device(sampled_tasks, num_shots, test_shots, inner_batch_size,
+                                                       inner_iters, replacement, lr_ph, lr)
+        else:
+            ious, task_iou_map = [], {}
+            for sampled_task in sampled_tasks:
+                sampled, task_name = _sample_mini_image_segmentation_dataset(
+                    self.session, [sampled_task], num_classes, num_shots + test_shots, return_task_name=True)
+                print("Evaluating {}".format(task_name))
+                train_set, test_set = _split_train_test_segmentation(sampled, test_shots)
+                task_iou = self._evaluate(train_set, test_set, input_ph, label_ph, minimize_op, predictions,
+                                          inner_batch_size, inner_iters, replacement, verbose=verbose,
+                                          is_training_ph=is_training_ph, lr_ph=lr_ph, lr=lr, task_name=task_name,
+                                          drop_rate_ph=drop_rate_ph, drop_rate=drop_rate, aug_rate=aug_rate)
+                ious.append(task_iou)
+                task_iou_map[task_name] = task_iou
+        mean_iou_score = np.nanmean(ious)
+        print("Evaluated {} task/s".format(len(sampled_tasks)))
+        print("Mean IoU from train on {} images and evaluate on {} test images: {}".format(num_shots, test_shots,
+                                                                                             mean_iou_score))
+        return mean_iou_score, task_iou_map
+
+    def _evaluate_device(self, sampled_tasks, num_shots, test_shots, inner_batch_size, inner_iters, replacement,
+                         lr_ph, lr):
+        """All tasks of one evaluation pass on the device, sharded over slots and ranks.  The host draws the
+        plans sequentially (same `random` consumption as the reference), the device adapts them concurrently."""
+        from .runner import TaskPlan, iou_from_counts
+        import torch
+        rank, world = _dist()
+        plans, names = [], []
+        for task in sampled_tasks:
+            obj, rows = _sample_task_indices([task], num_shots + test_shots)
+            names.append(obj.name)
+            print("Evaluating {}".format(obj.name))
+            train, test = _split_train_test_segmentation(rows, test_shots)
+            batches = list(_mini_batches(train, inner_batch_size, inner_iters, replacement, augmenter=None))
+            lrs = [self._inner_lr(lr_ph, lr, s, True) for s in range(inner_iters)]
+            plans.append((obj, np.asarray(batches, np.int32), np.asarray(lrs, np.float32), np.asarray(test, np.int32)))
+        n_pool = num_shots + test_shots
+        runner = self._get_runner(n_pool, inner_iters, inner_batch_size, test_shots)
+        eng = self._model.engine()
+        runner.set_init_state(eng.states[0])          # old_vars = _full_state.export_variables() (reptile.py:258)
+        from .runner import gather_owned, owned_indices
+        mine = owned_indices(len(plans), rank, world)
+        task_plans = []
+        for i in mine:
+            obj, bi, lrs, qi = plans[i]
+            images, labels = obj.arrays()
+            task_plans.append(TaskPlan(images[:n_pool], labels[:n_pool], bi, lrs, qi, None, obj.name))
+        results = runner.run(task_plans)
+        eng.states[0].copy_(runner.init_state)        # slot 0 doubles as a task slot: put the model state back
+        ious_local = np.full(len(plans), np.nan, np.float64)
+        for i, (inter, uni) in zip(mine, results):
+            ious_local[i] = iou_from_counts(inter, uni)
+        ious_local = gather_owned(ious_local, eng.device)
+        ious = [float(v) for v in ious_local]
+        for n, v in zip(names, ious):
+            print("Mean task IoU: {}".format(v))
+        # the engine state was never touched (tasks ran on slot copies): _full_state.import_variables is a no-op
+        return ious, dict(zip(names, ious))
+
+    def _evaluate(self, train_set, test_set, input_ph, label_ph, minimize_op, predictions, inner_batch_size,
+                  inner_iters, replacement, verbose=False, save_fine_tuned_checkpoints=False,
+                  save_fine_tuned_checkpoints_dir: Optional[str] = None, eval_sample_num: Optional[int] = None,
+                  is_training_ph=None, lr_ph=None, lr: Optional[float] = None, drop_rate_ph=None,
+                  drop_rate: Optional[float] = None, aug_rate: Optional[float] = None,
+                  task_name: Optional[str] = None):
+        """Evaluates a single task's train-test split through the Session (reptile.py:235-294)."""
+        snap = self._full_state.snapshot()         # device-side stand-in for export_variables (reptile.py:258)
+        for inner_iter, batch in enumerate(_mini_batches(train_set, inner_batch_size, num_batches=inner_iters,
+                                                         replacement=replacement, augmenter=self.augmenter,
+                                                         aug_rate=aug_rate)):
+            inputs, labels = zip(*batch)
+            if self._pre_step_op:
+                self.session.run(self._pre_step_op)
+            feed = {input_ph: inputs, label_ph: labels}
+            if (lr_ph is not None) and (lr is not None) and (drop_rate_ph is not None) and (drop_rate is not None):
+                feed[drop_rate_ph] = drop_rate
+                feed[lr_ph] = lr
+            elif (lr_ph is not None) and (lr is not None):
+                feed[lr_ph] = lr
+            elif (lr_ph is not None) and (self.lr_scheduler is not None):
+                feed[lr_ph] = self.lr_scheduler.cur_lr(cur_step=inner_iter)
+            self.session.run(minimize_op, feed_dict=feed)
+        test_preds = self._test_predictions(train_set, test_set, input_ph, predictions, is_training_ph,
+                                            task_name=task_name)
+        class_iou = [self._iou(test_preds[j], test_set[j][1]) for j in range(len(test_preds))]
+        class_iou = np.nanmean(class_iou)
+        print("Mean task IoU: {}".format(class_iou))
+        self._full_state.restore(snap)             # import_variables(old_vars) (reptile.py:293)
+        return class_iou
+
+    def _test_predictions(self, train_set, test_set, input_ph, predictions, is_training_ph=None,
+                          task_name: Optional[str] = None):
+        """reptile.py:482-524."""
+        if os.environ.get("SAVE_PREDICTIONS"):
+            raise NotImplementedError("SAVE_PREDICTIONS visualisation (utils/viz.py) is out of scope")
+        if self._transductive:
+            inputs, _ = zip(*test_set)
+            feed = {input_ph: inputs}
+            if is_training_ph is not None:
+                feed[is_training_ph] = False
+            return self.session.run(predictions, feed_dict=feed)
+        res = []
+        for test_sample in test_set:
+            inputs, _ = zip(*train_set)
+            inputs += (test_sample[0],)
+            feed = {input_ph: inputs}
+            if is_training_ph is not None:
+                feed[is_training_ph] = False
+            res.append(self.session.run(predictions, feed_dict=feed)[-1])
+        return res
+
+    @staticmethod
+    def _iou(prediction: np.ndarray, label: np.ndarray, epsilon: float = 1e-7,
+             class_of_interest_channel: Optional[Union[int, slice]] = 1, round_labels: bool = True):
+        """IoU of two binary masks of ONE image (reptile.py:526-549)."""
+        if len(prediction.shape) > 3:
+            raise ValueError("Function is intended for single image masks, not batches.")
+        if prediction.shape != label.shape:
+            raise ValueError("prediction shape and label shape must be equal but are: {} and {} respectively.".format(
+                prediction.shape, label.shape))
+        if class_of_interest_channel is not None:
+            prediction = prediction[:, :, class_of_interest_channel]
+            label = label[:, :, class_of_interest_channel]
+        prediction = np.round(prediction)
+        if round_labels:
+            label = np.round(label)
+        intersection = np.logical_and(prediction, label)
+        union = np.logical_or(label, prediction)
+        return (np.sum(intersection) + epsilon) / (np.sum(union) + epsilon)
+
+
+def measure(y_in, pred_in, thresh: float = .5):
+    """Shaban et al. confusion counts (reptile.py:555-562), kept as the cross-check metric."""
+    y, pred = y_in > thresh, pred_in > thresh
+    tp = np.logical_and(y, pred).sum()
+    tn = np.logical_and(np.logical_not(y), np.logical_not(pred)).sum()
+    fp = np.logical_and(np.logical_not(y), pred).sum()
+    fn = np.logical_and(y, np.logical_not(pred)).sum()
+    return tp, tn, fp, fn
+
+
+def iou_img(tp, fp, fn):
+    return tp / float(max(tp + fp + fn, 1))
+
+
+class FOMLIS(Gecko):
+    """First-order MAML for image segmentation (reptile.py:569-663): the update direction of a task is the
+    last inner step, theta_T - theta_{T-1}; with tail_shots the last mini-batch is a held-out tail set."""
+
+    def __init__(self, *args, train_shots: Optional[int] = None, tail_shots: Optional[int] = None,
+                 sample_train_val_with_replacement: bool = False, **kwargs):
+        super(FOMLIS, self).__init__(*args, **kwargs)
+        self.train_shots = train_shots - tail_shots if tail_shots is not None else train_shots
+        self.tail_shots = tail_shots
+        self.sample_train_val_with_replacement = sample_train_val_with_replacement
+        if sample_train_val_with_replacement:
+            print("Sampling train val with replacement.")
+        self.meta_fn = "FOMAML"
+        print("Specializing meta-learner to FOMAML.")
+
+    def train_step(self, dataset, input_ph, label_ph, minimize_op, num_classes, num_shots, inner_batch_size,
+                   inner_iters, replacement, meta_step_size, meta_batch_size, verbose=False, lr_ph=None, lr=None):
+        if self.fast_path:
+            return self._train_step_device(dataset, num_shots, inner_batch_size, inner_iters, replacement,
+                                           meta_step_size, meta_batch_size, lr_ph, lr, fomaml=True)
+        old_vars = self._model_state.export_variables()
+        updates = []
+        for _ in range(meta_batch_size):
+            mini_dataset = _sample_mini_image_segmentation_dataset(self.session, dataset, num_classes, num_shots)
+            for j, batch in enumerate(self._mini_batches(mini_dataset, inner_batch_size, inner_iters, replacement)):
+                inputs, labels = zip(*batch)
+                if j == inner_iters - 1:
+                    last_backup = self._model_state.export_variables()
+                if self._pre_step_op:
+                    self.session.run(self._pre_step_op)
+                feed = {input_ph: inputs, label_ph: labels}
+                if (lr_ph is not None) and (lr is not None):
+                    feed[lr_ph] = lr
+                self.session.run(minimize_op, feed_dict=feed)
+            updates.append(subtract_vars(self._model_state.export_variables(), last_backup))
+            self._model_state.import_variables(old_vars)
+        update = average_vars(updates)
+        self._model_state.import_variables(add_vars(old_vars, scale_vars(update, meta_step_size)))
+
+    def _mini_batches(self, mini_dataset, inner_batch_size, inner_iters, replacement):
+        """reptile.py:649-663: T-1 batches from the train part, then the un-augmented tail set as the last batch."""
+        if self.tail_shots is None:
+            for value in _mini_batches(mini_dataset, inner_batch_size, inner_iters, replacement,
+                                       augmenter=self.augmenter, aug_rate=self.aug_rate):
+                yield value
+            return
+        if self.sample_train_val_with_replacement:
+            train, tail = _sample_train_test_segmentation_with_replacement(mini_dataset, train_shots=self.train_shots,
+                                                                           test_shots=self.tail_shots)
+        else:
+            train, tail = _split_train_test_segmentation(mini_dataset, test_shots=self.tail_shots)
+        for batch in _mini_batches(train, inner_batch_size, inner_iters - 1, replacement, augmenter=self.augmenter,
+                                   aug_rate=self.aug_rate):
+            yield batch
+        yield tail
+
+    def _task_batches_for_training(self, rows, inner_batch_size, inner_iters, replacement):
+        return list(self._mini_batches(rows, inner_batch_size, inner_iters, replacement))

@@ -180,3 +180,34 @@ def iou_from_counts(inter: np.ndarray, union: np.ndarray, epsilon: float = 1e-7)
     """Gecko._iou (reptile.py:549) per image in float64, then np.nanmean over the query set (reptile.py:290-291)."""
     per_image = (inter.astype(np.float64) + epsilon) / (union.astype(np.float64) + epsilon)
     return float(np.nanmean(per_image))
+
+
+# ---- task-parallel plumbing (one process per GPU; torch.distributed is the transport) ------------------------
+def owned_indices(n: int, rank: int, world: int) -> List[int]:
+    """Round-robin ownership of n independent units (tasks) by `world` ranks."""
+    return [i for i in range(n) if i % world == rank]
+
+
+def gather_owned(values: np.ndarray, device=None) -> np.ndarray:
+    """values: float64 [n] with NaN at indices this rank does not own -> the complete vector on every rank.
+    Every index is owned by exactly one rank, so a SUM all-reduce of the NaN-zeroed vectors is exact."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return values
+    t = torch.from_numpy(np.nan_to_num(values, nan=0.0))
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t)
+    return t.cpu().numpy()
+
+
+def allreduce_meta(delta_sum: torch.Tensor, bn_state: Optional[torch.Tensor] = None) -> None:
+    """The one exchange step of a meta-update: SUM of the per-rank task deltas (8.29 MB fp32) and, for world > 1,
+    the average of the BN moving statistics."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    dist.all_reduce(delta_sum)
+    if bn_state is not None:
+        dist.all_reduce(bn_state)
+        bn_state.div_(dist.get_world_size())

@@ -1,0 +1,128 @@
+#!/usr/bin/env python
+"""Meta-trains and evaluates image segmentation models on the B200 engine.
+
+Drop-in for /root/reference/run_metasegnet.py: same flags (mliis_b200/args.py), same flow (:28-211) - build the
+model, load the tasks, restore the checkpoint or meta-train, evaluate on the training and meta-test tasks, print
+the greppable summary line and write <checkpoint>/meta-test_results.json.
+
+Differences: the task shards are synthetic FSS-1000-shaped tasks unless tfrecord shards are readable
+(`--synthetic_tasks N`, or no --data-dir); hyper-parameter search and the k-shot-curve experiment are out of
+scope.  Multi-GPU: launch with torchrun - tasks are sharded across ranks (mliis_b200/reptile.py).
+"""
+import datetime
+import json
+import os
+import random
+
+import numpy as np
+
+
+def main():
+    from mliis_b200.args import argument_parser, evaluate_kwargs, model_kwargs, train_kwargs
+    from mliis_b200.efficientlab import EfficientLab
+    from mliis_b200.eval import evaluate_gecko
+    from mliis_b200.lr_schedulers import supported_learning_rate_schedulers
+    from mliis_b200.metaseg import read_synthetic_dataset
+    from mliis_b200.session import Session
+    from mliis_b200.train import train_gecko
+    from mliis_b200.checkpoint import Saver
+    from mliis_b200.util import latest_checkpoint, validate_datasets
+
+    verbose = True
+    eval_train_tasks = True
+    start_time = datetime.datetime.now()
+    print("Experiment started at: {}".format(start_time))
+    args = argument_parser().parse_args()
+    if args.optimize_update_hyperparms_on_val_set or args.run_k_shot_learning_curves_experiment:
+        raise NotImplementedError("hyper-parameter search / k-shot curves are out of scope (SURVEY.md 8f-4)")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+
+    random.seed(args.seed)          # the ONLY seed the reference sets (run_metasegnet.py:43)
+    print("Defining model architecture:")
+    mk = model_kwargs(args)
+    print("Using loss {}".format(mk["loss_name"]))
+    restore_ckpt_dir = mk["restore_ckpt_dir"]
+    model = EfficientLab(**mk)
+    lr_scheduler = None
+    sched_cls = supported_learning_rate_schedulers[args.learning_rate_scheduler]
+    if sched_cls is not None:
+        sk = {"decay_rate": args.step_decay_rate, "decay_after_n_steps": args.decay_after_n_steps} \
+            if "step" in args.learning_rate_scheduler else {}
+        lr_scheduler = sched_cls(args.learning_rate, train_kwargs(args)["eval_inner_iters"], **sk)
+    print("{} instantiated.".format(args.model_name))
+    print("Model contains {} trainable parameters.".format(model.n_params))
+    print("Meta-learning with algorithm:")
+    print("FOMAML" if args.foml else "Reptile")
+
+    print("Setting up meta-learning dataset")
+    n_test = args.synthetic_tasks or 240
+    train_set, val_set, test_set, _, _, test_task_names = read_synthetic_dataset(
+        num_train_tasks=max(8, 760 if not args.synthetic_tasks else 4 * n_test), num_test_tasks=n_test,
+        n_examples=max(10, args.shots + 5, (args.train_shots or 0)), image_size=args.image_size)
+    val_set = None
+    validate_datasets(args, train_set, val_set, test_set)
+    if verbose:
+        print("Found {} testing tasks:".format(len(test_set)))
+        print("Found {} training tasks:".format(len(train_set)))
+
+    with Session(model) as sess:
+        if restore_ckpt_dir is not None and not args.pretrained:
+            print("Restoring from checkpoint {}".format(restore_ckpt_dir))
+            model.restore_model(sess, restore_ckpt_dir, filter_to_scopes=[model.feature_extractor_name])
+        if not args.pretrained:
+            print("Meta-training...")
+            if args.continue_training_from_checkpoint is not None:
+                ckpt = latest_checkpoint(args.continue_training_from_checkpoint)
+                print("Continuing meta-training from checkpoint: {}".format(ckpt))
+                Saver(model).restore(sess, ckpt)
+            train_gecko(sess, model, train_set, val_set or test_set, args.checkpoint, lr_scheduler=lr_scheduler,
+                        augment=args.augment, **train_kwargs(args))
+        else:
+            if args.do_not_restore_final_layer_weights:
+                print("Restoring from checkpoint: {}".format(args.checkpoint))
+                model.restore_model(sess, args.checkpoint, filter_out_scope=model.final_layer_scope,
+                                    convert_ckpt_to_rel_path=True)
+            else:
+                ckpt = latest_checkpoint(args.checkpoint)
+                print("Restoring from checkpoint: {}".format(ckpt))
+                Saver(model).restore(sess, ckpt)
+
+        eval_kwargs = evaluate_kwargs(args)
+        del eval_kwargs["eval_tasks_with_median_early_stopping_iterations"]
+        print("Evaluating {}-shot learning on training tasks.".format(args.shots))
+        mean_train_iou = None
+        if eval_train_tasks:
+            keep = eval_kwargs["save_fine_tuned_checkpoints"]
+            eval_kwargs["save_fine_tuned_checkpoints"] = args.save_fine_tuned_checkpoints_train
+            mean_train_iou, _ = evaluate_gecko(sess, model, train_set, visualize_predicted_segmentations=False,
+                                               lr_scheduler=lr_scheduler, serially_eval_all_tasks=False, **eval_kwargs)
+            eval_kwargs["save_fine_tuned_checkpoints"] = keep
+        print("Evaluating {}-shot learning on meta-test tasks.".format(args.shots))
+        mean_test_iou, task_name_iou_map = evaluate_gecko(
+            sess, model, test_set, visualize_predicted_segmentations=False, lr_scheduler=lr_scheduler,
+            serially_eval_all_tasks=args.serially_eval_all_test_tasks, **eval_kwargs)
+        print("Evaluated meta-test tasks:")
+        print(task_name_iou_map)
+        if eval_train_tasks:
+            print("Mean meta-train IoU: {}".format(mean_train_iou))
+        # Do NOT change this print (it's used to grep logs)  -- run_metasegnet.py:199-200
+        print("Mean IoU over all meta-test tasks: {}".format(mean_test_iou))
+        if int(os.environ.get("RANK", "0")) == 0:
+            os.makedirs(args.checkpoint, exist_ok=True)
+            results_path = os.path.join(args.checkpoint, "meta-test_results.json")
+            with open(results_path, "w") as f:
+                json.dump(task_name_iou_map, f)
+            print("Wrote results to {}".format(results_path))
+
+    end_time = datetime.datetime.now()
+    print("Experiment finished at: {}, taking {}".format(end_time, end_time - start_time))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,154 @@
+"""The reference-facing Python surface on the GPU: Session idioms, VariableState, Gecko / FOMLIS on both the
+Session path and the device fast path, evaluate_gecko / train_gecko, checkpoint save + restore."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SIZE = 64
+
+
+def _model(**kw):
+    from mliis_b200.efficientlab import EfficientLab
+    args = dict(rsd=[2, 4], l2=True, dice=True, final_layer_dropout_rate=0.0, n_rows=SIZE, n_cols=SIZE,
+                learning_rate=1e-3, label_smoothing=0.0, optimizer="adam", task_slots=3)
+    args.update(kw)
+    m = EfficientLab(**args)
+    m.initialize(seed=0)
+    return m
+
+
+def _tasks(n, first=0, n_examples=10):
+    from mliis_b200.synthetic import SyntheticSegmentationTask
+    return [SyntheticSegmentationTask(first + i, n_examples, SIZE) for i in range(n)]
+
+
+def _warm(sess, m, steps=3):
+    t = _tasks(1, 900)[0]
+    s = t.sample(sess, 8)
+    x, y = zip(*s)
+    for _ in range(steps):
+        sess.run(m.minimize_op, feed_dict={m.input_ph: x, m.label_ph: y})
+
+
+def test_session_idioms_and_variable_state():
+    from mliis_b200.session import Session
+    from mliis_b200.variables import VariableState, weight_decay
+    m = _model()
+    sess = Session(m)
+    vs = VariableState(sess, m.trainable_variables())
+    full = VariableState(sess, m.global_variables())
+    v0 = vs.export_variables()
+    assert len(v0) == 169 and v0[0].shape == (3, 3, 3, 32)
+    f0 = full.export_variables()
+    t = _tasks(1)[0]
+    x, y = zip(*t.sample(sess, 8))
+    sess.run(m.minimize_op, feed_dict={m.input_ph: x, m.label_ph: y, m.lr_ph: 1e-3})
+    v1 = vs.export_variables()
+    assert any(not np.array_equal(a, b) for a, b in zip(v0, v1))
+    pred = sess.run(m.predictions, feed_dict={m.input_ph: x[:5], m.is_training_ph: False})
+    assert pred.shape == (5, SIZE, SIZE, 2) and set(np.unique(pred)) <= {0.0, 1.0}
+    full.import_variables(f0)                       # restores weights, BN statistics and optimizer slots
+    f0b = full.export_variables()
+    assert all(np.array_equal(a, b) for a, b in zip(f0, f0b))
+    # pre_step_op: var <- var * rate, applied before the step
+    sess.run(weight_decay(0.5))
+    sess.run(m.minimize_op, feed_dict={m.input_ph: x, m.label_ph: y, m.lr_ph: 0.0})
+    v2 = vs.export_variables()
+    assert np.allclose(v2[0], 0.5 * v0[0], atol=1e-7)
+    with pytest.raises(ValueError):
+        sess.run(m.minimize_op, feed_dict={m.input_ph: [np.zeros((SIZE, SIZE))], m.label_ph: y})
+
+
+def test_evaluate_fast_path_equals_session_path():
+    from mliis_b200.reptile import Gecko
+    from mliis_b200.session import Session
+    m = _model()
+    sess = Session(m)
+    _warm(sess, m)
+    tasks = _tasks(5, 100)
+    kw = dict(num_classes=1, num_shots=5, inner_batch_size=8, inner_iters=3, replacement=False, eval_all_tasks=True,
+              is_training_ph=m.is_training_ph, lr_ph=m.lr_ph)
+    before = m.engine().states[0].clone()
+    random.seed(11)
+    fast = Gecko(sess, transductive=True, fast_path=True)
+    mi_f, map_f = fast.evaluate(tasks, m.input_ph, m.label_ph, m.minimize_op, m.predictions, **kw)
+    after_rng = random.random()
+    assert torch.equal(before, m.engine().states[0])        # evaluation leaves the model state untouched
+    random.seed(11)
+    slow = Gecko(sess, transductive=True, fast_path=False)
+    mi_s, map_s = slow.evaluate(tasks, m.input_ph, m.label_ph, m.minimize_op, m.predictions, **kw)
+    assert after_rng == random.random()                     # same consumption of the `random` stream
+    assert torch.equal(before, m.engine().states[0])
+    assert map_f.keys() == map_s.keys()
+    for k in map_f:
+        assert abs(map_f[k] - map_s[k]) < 1e-12, (k, map_f[k], map_s[k])
+    assert abs(mi_f - mi_s) < 1e-12
+
+
+@pytest.mark.parametrize("foml", [False, True])
+def test_meta_train_step_fast_equals_session_path(foml):
+    from mliis_b200.reptile import FOMLIS, Gecko
+    from mliis_b200.session import Session
+    results = []
+    for fast in (True, False):
+        m = _model(optimizer="sgd")
+        sess = Session(m)
+        tasks = _tasks(6, 200)
+        random.seed(3)
+        if foml:
+            learner = FOMLIS(sess, train_shots=10, tail_shots=5, fast_path=fast)
+        else:
+            learner = Gecko(sess, fast_path=fast)
+        for _ in range(2):
+            learner.train_step(tasks, m.input_ph, m.label_ph, m.minimize_op, num_classes=1, num_shots=10 if foml else 5,
+                               inner_batch_size=4, inner_iters=3, replacement=False, meta_step_size=0.5,
+                               meta_batch_size=3, lr_ph=m.lr_ph, lr=None)
+        eng = m.engine()
+        results.append((eng.tf_order_vector(eng.theta(0)).cpu().double(), eng.bn_state(0).cpu().double(), random.random()))
+    (tf_, bf, rf), (ts, bs, rs) = results
+    assert rf == rs
+    rel = ((tf_ - ts).norm() / ts.norm()).item()
+    assert rel < 1e-6, rel                  # host numpy mean/interpolation vs fused device kernels: rounding only
+    assert ((bf - bs).abs().max() / bs.abs().max()).item() < 1e-5
+
+
+def test_evaluate_gecko_and_train_gecko_with_checkpoints(tmp_path):
+    from mliis_b200.checkpoint import Saver, read_index
+    from mliis_b200.eval import evaluate_gecko
+    from mliis_b200.session import Session
+    from mliis_b200.train import train_gecko
+    from mliis_b200.reptile import FOMLIS
+    from functools import partial
+    from mliis_b200.util import latest_checkpoint
+    m = _model()
+    sess = Session(m)
+    train, test = _tasks(6, 300), _tasks(4, 400)
+    random.seed(0)
+    save_dir = str(tmp_path / "ckpt")
+    meta_fn = partial(FOMLIS, train_shots=10, tail_shots=5)
+    train_gecko(sess, m, train, test, save_dir, num_classes=1, num_shots=5, inner_batch_size=4, inner_iters=3,
+                meta_step_size=0.1, meta_step_size_final=0.01, meta_batch_size=2, meta_iters=2, eval_inner_batch_size=4,
+                eval_inner_iters=2, eval_interval=1, train_shots=10, transductive=True, meta_fn=meta_fn,
+                num_tasks_to_eval=2)
+    prefix = latest_checkpoint(save_dir)
+    assert prefix.endswith("model.ckpt-1")
+    idx = read_index(prefix + ".index")
+    assert "decode/final_layer_weights/kernel" in idx and "beta2_power" in idx
+    assert "efficientnet-b0/model/stem/tpu_batch_normalization/moving_variance" in idx
+    mean_iou, iou_map = evaluate_gecko(sess, m, test, num_classes=1, num_shots=5, eval_inner_batch_size=4,
+                                       eval_inner_iters=2, num_samples=2, transductive=True, serially_eval_all_tasks=True)
+    assert len(iou_map) == 4 and all(len(v) == 2 for v in iou_map.values()) and 0.0 <= mean_iou <= 1.0
+    # restore into a fresh model: identical state
+    state = m.engine().states[0].clone()
+    m2 = _model()
+    Saver(m2).restore(Session(m2), prefix)
+    s2 = m2.engine().states[0]
+    eng = m.engine()
+    assert torch.equal(state[:eng.n_theta], s2[:eng.n_theta])
+    assert torch.equal(state[eng.o_bn:eng.o_bn + 2 * eng.n_bn], s2[eng.o_bn:eng.o_bn + 2 * eng.n_bn])
+    assert torch.equal(state[eng.o_v:eng.o_pow + 2], s2[eng.o_v:eng.o_pow + 2])
