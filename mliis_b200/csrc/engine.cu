@@ -172,6 +172,44 @@ GemmA convA(const float* ptr, int ld, int H, int W, int C, int dil) {
   return a;
 }
 
+
+// Dense contraction dispatch: tcgen05 (TF32) when the ctx asks for it and the shape is supported, else fp32 FFMA.
+// w_hwio is the TF-layout kernel [taps][Cin][Cout]; scratch receives the re-laid-out tensor-core operand.
+struct Dense {
+  const Run& r;
+  bool tc() const { return r.c->cfg.gemm_mode != MLIIS_GEMM_FP32; }
+  // forward: out[M, Cout] = conv(A[.., Cin]) + bias
+  void fwd(const float* A, int lda, int conv, int H, int W, int Cin, int dil, const float* w_hwio, const float* bias,
+           float* out, int ldc, int Cout, int M, int HW) const {
+    const int taps = conv ? 9 : 1;
+    if (tc() && tc_supported(conv, W, Cin, Cout)) {
+      float* wt = r.W(r.p.wT);
+      tc_prep_weights(w_hwio, wt, taps, Cin, Cout, 0, r.st);
+      if (tc_conv(A, lda, wt, bias, out, ldc, conv, M, r.B, H, W, Cin, taps, dil, Cout, 0, r.st)) return;
+    }
+    GemmA a = conv ? convA(A, lda, H, W, Cin, dil) : plainA(A, lda);
+    gemm_nn(a, w_hwio, bias, out, ldc, M, taps * Cin, Cout, HW, 0, r.st);
+  }
+  // dgrad: dA[M, Cin] (+)= conv^T(G[.., Cout])
+  void dgrad(const float* G, int ldg, int conv, int H, int W, int Cin, int dil, const float* w_hwio, float* dA, int ldd,
+             int Cout, int M, int HW, int accumulate) const {
+    const int taps = conv ? 9 : 1;
+    float* wt = r.W(r.p.wT);
+    if (tc() && tc_supported(conv, W, Cout, Cin)) {
+      const float* bop = w_hwio;            // 1x1: W[Cin][Cout] already is the K-major B operand [N=Cin][K=Cout]
+      if (conv) { tc_prep_weights(w_hwio, wt, taps, Cin, Cout, 1, r.st); bop = wt; }
+      if (tc_conv(G, ldg, bop, nullptr, dA, ldd, conv, M, r.B, H, W, Cout, taps, dil, Cin, accumulate, r.st)) return;
+    }
+    if (conv) {
+      flip_transpose_w3x3(w_hwio, wt, Cin, Cout, r.st);
+      gemm_nn(convA(G, ldg, H, W, Cout, dil), wt, nullptr, dA, ldd, M, 9 * Cout, Cin, HW, accumulate, r.st);
+    } else {
+      transpose_w(w_hwio, wt, Cin, Cout, r.st);
+      gemm_nn(plainA(G, ldg), wt, nullptr, dA, ldd, M, Cout, Cin, HW, accumulate, r.st);
+    }
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
@@ -239,20 +277,19 @@ void run_forward(const Run& r, const float* images, const int32_t* index, bool t
     add3(cat + D, d.catC, r.W(sb.Y.off), sb.cout, nullptr, 0, nullptr, 0, M, d.skipC, HW, st);
     float* pyr = r.W(d.pyr.off);
     // branch_0: 1x1 (+bias) -> swish -> BN
-    gemm_nn(plainA(cat, d.catC), r.T(d.w0), r.T(d.b0), r.W(d.c0.off), D, M, d.catC, D, HW, 0, st);
+    const Dense dense{r};
+    dense.fwd(cat, d.catC, 0, d.h, d.w, d.catC, 1, r.T(d.w0), r.T(d.b0), r.W(d.c0.off), D, D, M, HW);
     if (training) r.bn_train(d.bn[0], r.W(d.c0.off), D, M, true);
     dec_bn_apply(r.W(d.c0.off), D, r.bn_a(d.bn[0]), r.bn_b(d.bn[0]), nullptr, 0, pyr, d.pyrC, M, D, st);
     // branch_1: 3x3 dilation 2
-    gemm_nn(convA(cat, d.catC, d.h, d.w, d.catC, 2), r.T(d.w1), r.T(d.b1), r.W(d.c1.off), D, M, 9 * d.catC, D, HW, 0,
-            st);
+    dense.fwd(cat, d.catC, 1, d.h, d.w, d.catC, 2, r.T(d.w1), r.T(d.b1), r.W(d.c1.off), D, D, M, HW);
     if (training) r.bn_train(d.bn[1], r.W(d.c1.off), D, M, true);
     dec_bn_apply(r.W(d.c1.off), D, r.bn_a(d.bn[1]), r.bn_b(d.bn[1]), nullptr, 0, pyr + D, d.pyrC, M, D, st);
     // branch_2: image-level mean, tiled (efficientlab.py:192-197)
     img_colsum(cat, d.catC, B, HW, d.catC, 1.f / (float)HW, r.W(p.partials), r.W(d.pooled), d.catC, st);
     bcast_rows(r.W(d.pooled), d.catC, pyr + 2 * D, d.pyrC, B, HW, d.catC, st);
     // 3x3 over the pyramid, + residual
-    gemm_nn(convA(pyr, d.pyrC, d.h, d.w, d.pyrC, 1), r.T(d.w2), r.T(d.b2), r.W(d.c2.off), D, M, 9 * d.pyrC, D, HW, 0,
-            st);
+    dense.fwd(pyr, d.pyrC, 1, d.h, d.w, d.pyrC, 1, r.T(d.w2), r.T(d.b2), r.W(d.c2.off), D, D, M, HW);
     if (training) r.bn_train(d.bn[2], r.W(d.c2.off), D, M, true);
     dec_bn_apply(r.W(d.c2.off), D, r.bn_a(d.bn[2]), r.bn_b(d.bn[2]), cat, d.catC, r.W(d.out.off), D, M, D, st);
     deep = r.W(d.out.off);
@@ -326,21 +363,19 @@ void run_backward(const Run& r, const float* labels, const int32_t* index, float
     dec_bn_bwd(d.bn[2], r.W(d.c2.off), gOut, D, r.W(p.g_c));
     gemm_tn(convA(pyr, d.pyrC, d.h, d.w, d.pyrC, 1), r.W(p.g_c), D, r.G(d.w2), r.G(d.b2), r.W(p.tn_scratch), M,
             9 * d.pyrC, D, HW, st);
-    flip_transpose_w3x3(r.T(d.w2), r.W(p.wT), d.pyrC, D, st);
-    gemm_nn(convA(r.W(p.g_c), D, d.h, d.w, D, 1), r.W(p.wT), nullptr, r.W(p.g_pyr), d.pyrC, M, 9 * D, d.pyrC, HW, 0, st);
+    const Dense dense{r};
+    dense.dgrad(r.W(p.g_c), D, 1, d.h, d.w, d.pyrC, 1, r.T(d.w2), r.W(p.g_pyr), d.pyrC, D, M, HW, 0);
     const float* gpyr = r.W(p.g_pyr);
     dec_bn_bwd(d.bn[0], r.W(d.c0.off), gpyr, d.pyrC, r.W(p.g_c0));
     dec_bn_bwd(d.bn[1], r.W(d.c1.off), gpyr + D, d.pyrC, r.W(p.g_c1));
     img_colsum(gpyr + 2 * D, d.pyrC, B, HW, d.catC, 1.f / (float)HW, r.W(p.partials), r.W(d.dpooled), d.catC, st);
     // branch_0 1x1
     gemm_tn(plainA(cat, d.catC), r.W(p.g_c0), D, r.G(d.w0), r.G(d.b0), r.W(p.tn_scratch), M, d.catC, D, HW, st);
-    transpose_w(r.T(d.w0), r.W(p.wT), d.catC, D, st);
-    gemm_nn(plainA(r.W(p.g_c0), D), r.W(p.wT), nullptr, r.W(p.g_cat), d.catC, M, D, d.catC, HW, 0, st);
+    dense.dgrad(r.W(p.g_c0), D, 0, d.h, d.w, d.catC, 1, r.T(d.w0), r.W(p.g_cat), d.catC, D, M, HW, 0);
     // branch_1 3x3 dil 2 (accumulates into g_cat)
     gemm_tn(convA(cat, d.catC, d.h, d.w, d.catC, 2), r.W(p.g_c1), D, r.G(d.w1), r.G(d.b1), r.W(p.tn_scratch), M,
             9 * d.catC, D, HW, st);
-    flip_transpose_w3x3(r.T(d.w1), r.W(p.wT), d.catC, D, st);
-    gemm_nn(convA(r.W(p.g_c1), D, d.h, d.w, D, 2), r.W(p.wT), nullptr, r.W(p.g_cat), d.catC, M, 9 * D, d.catC, HW, 1, st);
+    dense.dgrad(r.W(p.g_c1), D, 1, d.h, d.w, d.catC, 2, r.T(d.w1), r.W(p.g_cat), d.catC, D, M, HW, 1);
     // d_up = gOut + g_cat[:, :D] + dpooled[:, :D]      d_skip = g_cat[:, D:] + dpooled[:, D:]
     const float* gcat = r.W(p.g_cat);
     const float* dpl = r.W(d.dpooled);
@@ -796,7 +831,17 @@ int mliis_gemm_nn(const float* a, const float* w, float* c, int32_t M, int32_t K
   int rc = require_sm100();
   if (rc) return rc;
   if (K % 8 || N % 4) return fail(MLIIS_ERR_ARG, "K must be a multiple of 8 and N of 4");
-  (void)mode;
+  if (mode != MLIIS_GEMM_FP32) {
+    if (!tc_supported(0, 0, K, N)) return fail(MLIIS_ERR_ARG, "shape not supported by the tcgen05 path");
+    float* wt = nullptr;
+    if (cudaMalloc(&wt, (size_t)K * N * sizeof(float)) != cudaSuccess) return fail(MLIIS_ERR_CUDA, "alloc");
+    tc_prep_weights(w, wt, 1, K, N, 0, (cudaStream_t)stream);
+    bool ok = tc_conv(a, K, wt, nullptr, c, N, 0, M, 1, 1, 1, K, 1, 1, N, 0, (cudaStream_t)stream);
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(wt);
+    if (!ok) return fail(MLIIS_ERR_CUDA, "tc_conv setup failed (tensor map encode)");
+    return check_cuda("gemm_nn(tc)");
+  }
   gemm_nn(plainA(a, K), w, nullptr, c, N, M, K, N, M, 0, (cudaStream_t)stream);
   return check_cuda("gemm_nn");
 }
@@ -806,7 +851,17 @@ int mliis_conv3x3_fwd(const float* x, const float* w, const float* bias, float* 
   int rc = require_sm100();
   if (rc) return rc;
   if (Cin % 8 || Cout % 4) return fail(MLIIS_ERR_ARG, "Cin must be a multiple of 8 and Cout of 4");
-  (void)mode;
+  if (mode != MLIIS_GEMM_FP32) {
+    if (!tc_supported(1, W, Cin, Cout)) return fail(MLIIS_ERR_ARG, "shape not supported by the tcgen05 path");
+    float* wt = nullptr;
+    if (cudaMalloc(&wt, (size_t)9 * Cin * Cout * sizeof(float)) != cudaSuccess) return fail(MLIIS_ERR_CUDA, "alloc");
+    tc_prep_weights(w, wt, 9, Cin, Cout, 0, (cudaStream_t)stream);
+    bool ok = tc_conv(x, Cin, wt, bias, y, Cout, 1, B * H * W, B, H, W, Cin, 9, dilation, Cout, 0, (cudaStream_t)stream);
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(wt);
+    if (!ok) return fail(MLIIS_ERR_CUDA, "tc_conv setup failed (tensor map encode)");
+    return check_cuda("conv3x3_fwd(tc)");
+  }
   gemm_nn(convA(x, Cin, H, W, Cin, dilation), w, bias, y, Cout, B * H * W, 9 * Cin, Cout, H * W, 0, (cudaStream_t)stream);
   return check_cuda("conv3x3_fwd");
 }

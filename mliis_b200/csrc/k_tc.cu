@@ -1,0 +1,361 @@
+// Dense contractions on the 5th-generation tensor cores (sm_100a): tcgen05.mma kind::tf32 issued by one
+// thread, operands staged in shared memory by TMA (cp.async.bulk.tensor, 128-byte swizzle, K-major),
+// fp32 accumulator in TMEM, read back with tcgen05.ld for the epilogue (bias, optional accumulate).
+//
+//   C[m, n] = sum_{tap, c} A[pixel(m) + offset(tap), c] * Wt[n][tap][c]  (+ bias[n]) (+ C[m, n])
+//
+// * 3x3 (dilated) convolutions are implicit GEMMs: for every filter tap the producer issues one 4-D TMA
+//   box {32 channels, W, BH rows, 1 image} whose start coordinate is shifted by the tap; out-of-bounds
+//   rows/columns are zero-filled by the TMA unit, which IS TensorFlow's SAME zero padding - no im2col
+//   buffer, no halo logic, no predicates in the kernel.
+// * 1x1 convolutions / plain GEMMs are the taps == 1 case with a 2-D map {K, M} and a {32, 128} box.
+// * dgrad is the same kernel on a gradient tensor and re-laid-out weights (tc_prep_weights).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (each owns the TMEM lane quarter warp_id % 4).
+// Reference ops replaced: tf.layers.conv2d of models/efficientlab.py:185-188, :218-224 and their
+// Conv2DBackpropInput [TF-ext].
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mliis {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded spin: a protocol bug traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 26)) asm volatile("trap;");
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, M = 128, N from the instruction descriptor, K = 8
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (ignored for swizzled K-major, set to 1) |
+//   [32,46) SBO >> 4 = 1024 B between 8-row groups | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct TcParams {
+  int conv;          // 0: plain [M,K] (2-D map), 1: NHWC taps (4-D map)
+  int M;             // plain: number of rows
+  int H, W, BH;      // conv: image size, image rows per tile (tile = BH x W pixels <= 128)
+  int tiles_per_image;
+  int C;             // K per tap
+  int taps, dil;
+  int N, BN, ldc, accumulate;
+  int stages;
+  int a_box_bytes;   // bytes one A box delivers
+};
+
+constexpr int kTcThreads = 192;
+constexpr int kABytes = 128 * 128;   // 128 rows x 32 fp32
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const float* __restrict__ bias, float* __restrict__ out, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;              // SWIZZLE_128B atoms need 1024-byte alignment
+  uint8_t* smem = smem_raw + (base - raw);
+  const int b_bytes = p.BN * 128;
+  const int stage_bytes = kABytes + b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  const uint32_t bar0 = base + (uint32_t)p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (p.stages + s); };
+  const uint32_t tmem_full_bar = bar0 + 8u * (2 * p.stages);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t ncols = 32;
+  while ((int)ncols < p.BN) ncols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  // tile coordinates
+  int img = 0, y0 = 0, m0 = 0;
+  if (p.conv) {
+    img = blockIdx.x / p.tiles_per_image;
+    y0 = (blockIdx.x - img * p.tiles_per_image) * p.BH;
+  } else {
+    m0 = blockIdx.x * 128;
+  }
+  const int n0 = blockIdx.y * p.BN;
+  const int kchunks = (p.C + 31) / 32;
+  const int KB = p.taps * kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % p.stages;
+        mbar_wait(empty_bar(s), ((kb / p.stages) & 1) ^ 1);
+        const int tap = kb / kchunks, kc = kb - tap * kchunks;
+        const uint32_t sa = base + (uint32_t)s * stage_bytes, sb = sa + kABytes;
+        mbar_expect_tx(full_bar(s), (uint32_t)(p.a_box_bytes + b_bytes));
+        if (p.conv) {
+          const int dy = (tap / 3 - 1) * p.dil, dx = (tap % 3 - 1) * p.dil;
+          tma_load_4d(sa, &tmA, full_bar(s), kc * 32, dx, y0 + dy, img);
+        } else {
+          tma_load_2d(sa, &tmA, full_bar(s), kc * 32, m0);
+        }
+        tma_load_3d(sb, &tmB, full_bar(s), kc * 32, tap, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format TF32 [7,10)=[10,13)=2,
+      // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % p.stages;
+        mbar_wait(full_bar(s), (kb / p.stages) & 1);
+        tc_fence_after();
+        const int kc = kb % kchunks;
+        const int rem = p.C - kc * 32;
+        const int nk = rem >= 32 ? 4 : (rem + 7) / 8;
+        const uint32_t sa = base + (uint32_t)s * stage_bytes, sb = sa + kABytes;
+        const uint64_t da = make_kmajor_sw128_desc(sa), db = make_kmajor_sw128_desc(sb);
+        for (int k = 0; k < nk; ++k)   // advance 32 bytes (8 tf32) along K inside the 128-byte swizzle atom
+          tc_mma_tf32(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+        tc_commit(empty_bar(s));      // frees the stage once these MMAs have read it
+      }
+      tc_commit(tmem_full_bar);       // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> global ----------------
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;          // accumulator row == TMEM lane
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    bool valid;
+    size_t row;
+    if (p.conv) {
+      const int ly = r / p.W, lx = r - ly * p.W;
+      valid = r < p.BH * p.W && (y0 + ly) < p.H;
+      row = ((size_t)img * p.H + (y0 + ly)) * p.W + lx;
+    } else {
+      valid = m0 + r < p.M;
+      row = (size_t)m0 + r;
+    }
+    float* orow = out + row * p.ldc;
+    const uint32_t tbase = tmem_acc + ((uint32_t)(quarter * 32) << 16);
+    for (int c = 0; c < p.BN; c += 16) {
+      uint32_t v[16];
+      __syncwarp();
+      tc_ld16(tbase + (uint32_t)c, v);          // warp-collective: executed by all 32 lanes, converged
+      if (valid) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int n = n0 + c + q * 4;
+          if (n < p.N) {
+            float4 o = f4(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
+                          __uint_as_float(v[q * 4 + 3]));
+            if (bias) o = o + ld4(bias + n);
+            if (p.accumulate) o = o + ld4(orow + n);
+            st4(orow + n, o);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(ncols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static bool encode(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                   const cuuint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+int tc_pick_bn(int N) {
+  int tiles = (N + 255) / 256;
+  int bn = (N + tiles - 1) / tiles;
+  return (bn + 15) / 16 * 16;
+}
+
+bool tc_supported(int conv, int W, int C, int N) {
+  if (C % 4 || N % 4) return false;
+  if (conv && (W > 128 || W < 1)) return false;
+  return encode_fn() != nullptr;
+}
+
+// Wt layout expected by the kernel: [N][taps][C]  (K-major rows of B)
+bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float* out, int ldc, int conv, int M, int B,
+             int H, int W, int C, int taps, int dil, int N, int accumulate, cudaStream_t s) {
+  TcParams p{};
+  p.conv = conv; p.M = M; p.H = H; p.W = W; p.C = C; p.taps = taps; p.dil = dil; p.N = N; p.ldc = ldc;
+  p.accumulate = accumulate;
+  p.BN = tc_pick_bn(N);
+  CUtensorMap tmA, tmB;
+  int grid_x;
+  if (conv) {
+    p.BH = 128 / W;
+    if (p.BH > H) p.BH = H;
+    p.tiles_per_image = (H + p.BH - 1) / p.BH;
+    p.a_box_bytes = p.BH * W * 128;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t str[3] = {(cuuint64_t)lda * 4, (cuuint64_t)W * lda * 4, (cuuint64_t)H * W * lda * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)W, (cuuint32_t)p.BH, 1};
+    if (!encode(&tmA, A, 4, dims, str, box)) return false;
+    grid_x = B * p.tiles_per_image;
+  } else {
+    p.a_box_bytes = kABytes;
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)M};
+    cuuint64_t str[1] = {(cuuint64_t)lda * 4};
+    cuuint32_t box[2] = {32, 128};
+    if (!encode(&tmA, A, 2, dims, str, box)) return false;
+    grid_x = (M + 127) / 128;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)taps, (cuuint64_t)N};
+    cuuint64_t str[2] = {(cuuint64_t)C * 4, (cuuint64_t)taps * C * 4};
+    cuuint32_t box[3] = {32, 1, (cuuint32_t)p.BN};
+    if (!encode(&tmB, Wt, 3, dims, str, box)) return false;
+  }
+  const int stage_bytes = kABytes + p.BN * 128;
+  p.stages = (200 * 1024) / stage_bytes;
+  if (p.stages > 6) p.stages = 6;
+  if (p.stages < 2) return false;
+  const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 2) * 8 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr = true;
+  }
+  dim3 grid(grid_x, (N + p.BN - 1) / p.BN);
+  MLIIS_COUNT(), tc_conv_kernel<<<grid, kTcThreads, smem, s>>>(tmA, tmB, bias, out, p);
+  return true;
+}
+
+// weights W[tap][ci][co] (HWIO) -> forward operand Wt[co][tap][ci]   or   dgrad operand Wt[ci][8-tap][co]
+__global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ wt, int taps, int Ci, int Co,
+                                       int dgrad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= taps * Ci * Co) return;
+  if (!dgrad) {
+    const int co = i / (taps * Ci), rem = i - co * taps * Ci, tap = rem / Ci, ci = rem - tap * Ci;
+    wt[i] = w[((size_t)tap * Ci + ci) * Co + co];
+  } else {
+    const int ci = i / (taps * Co), rem = i - ci * taps * Co, tap = rem / Co, co = rem - tap * Co;
+    wt[i] = w[((size_t)(taps - 1 - tap) * Ci + ci) * Co + co];
+  }
+}
+void tc_prep_weights(const float* w, float* wt, int taps, int Ci, int Co, int dgrad, cudaStream_t s) {
+  const int n = taps * Ci * Co;
+  MLIIS_COUNT(), tc_prep_weights_kernel<<<cdiv(n, 256), 256, 0, s>>>(w, wt, taps, Ci, Co, dgrad);
+}
+
+}  // namespace mliis

@@ -302,3 +302,96 @@ def test_full_size_one_step():
     g = eng.tf_order_vector(grads).cpu().double()
     assert rel_l2(g, g_data) < 1e-4
     assert abs(loss.item() - loss_ref.item()) < 1e-4 * max(1.0, abs(loss_ref.item()))
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 / TMA / TMEM path (kind::tf32): the hardware reads the top 19 bits of every fp32 operand
+# ------------------------------------------------------------------------------------------------
+def _tf32_trunc(x):
+    """What tcgen05.mma kind::tf32 sees: fp32 with the low 13 mantissa bits ignored."""
+    return (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("M,K,N_", [(1568, 224, 112), (25088, 136, 112), (300, 112, 360), (128, 32, 16), (77, 8, 24)])
+def test_tc_gemm_nn(M, K, N_):
+    from mliis_b200 import native as N
+    g = torch.Generator().manual_seed(M + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(K, N_, generator=g)
+    ref_t = _tf32_trunc(a).double() @ _tf32_trunc(w).double()
+    ref = a.double() @ w.double()
+    ad, wd = _dev(a), _dev(w)
+    c = torch.full((M, N_), float("nan"), device="cuda")
+    N.check(N.lib().mliis_gemm_nn(ad.data_ptr(), wd.data_ptr(), c.data_ptr(), M, K, N_, 1, None))
+    torch.cuda.synchronize()
+    assert rel_err(c, ref_t) < 2e-5, "layout / descriptor error"
+    assert rel_err(c, ref) < 5e-3
+
+
+@pytest.mark.parametrize("H,Cin,Cout,dil,B", [(56, 136, 112, 2, 2), (56, 360, 112, 1, 1), (14, 224, 112, 2, 3),
+                                              (14, 448, 112, 1, 2), (56, 112, 360, 1, 1), (14, 112, 448, 2, 2),
+                                              (20, 40, 16, 1, 2), (80, 16, 16, 1, 1)])
+def test_tc_conv3x3(H, Cin, Cout, dil, B):
+    from mliis_b200 import native as N
+    g = torch.Generator().manual_seed(H + Cin + Cout)
+    x = torch.randn(B, H, H, Cin, generator=g)
+    w = torch.randn(3, 3, Cin, Cout, generator=g) * 0.05
+    bias = torch.randn(Cout, generator=g)
+    ref_t = conv2d_same(_tf32_trunc(x).double().permute(0, 3, 1, 2), _tf32_trunc(w).double(), dilation=dil,
+                        bias=bias.double()).permute(0, 2, 3, 1)
+    xd, wd, bd = _dev(x), _dev(w), _dev(bias)
+    y = torch.full((B, H, H, Cout), float("nan"), device="cuda")
+    N.check(N.lib().mliis_conv3x3_fwd(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), y.data_ptr(), B, H, H, Cin, Cout,
+                                      dil, 1, None))
+    torch.cuda.synchronize()
+    assert rel_err(y, ref_t) < 2e-5, "layout / descriptor / padding error"
+
+
+def _tf32_network_errors(size, B, steps):
+    from mliis_b200 import native as N
+    arch, theta, bn, images, labels = make_problem(size, 10)
+    orc = EfficientLabOracle(arch, torch.float64)
+    opt = OptState(arch.n_params, torch.float64)
+    eng = make_engine(arch, theta, bn, size, B, gemm_mode=N.GEMM_TF32)
+    xd, yd = _dev(images), _dev(labels)
+    # forward + gradient of the first batch
+    idx0 = np.arange(B, dtype=np.int32)
+    loss_ref, g_ref, _, logits_ref = orc.loss_and_grad(theta, bn, torch.from_numpy(images[idx0]), torch.from_numpy(labels[idx0]))
+    g_data = g_ref - 0.0005 * arch.l2_mask() * theta
+    logits = eng.forward(0, xd, True, index=torch.from_numpy(idx0).cuda())
+    loss, grads = eng.loss_backward(0, yd, B, index=torch.from_numpy(idx0).cuda())
+    torch.cuda.synchronize()
+    e_logits = (logits.cpu().double() - logits_ref).abs().max().item()
+    e_grad = rel_l2(eng.tf_order_vector(grads).cpu().double(), g_data)
+    # adapted weights after `steps` Adam steps
+    eng.init_state(0, split_vars(arch, theta), bn[0].numpy(), bn[1].numpy())
+    rng = np.random.default_rng(0)
+    th, bns = theta, bn
+    for s in range(steps):
+        idx = rng.permutation(5)[:B].astype(np.int32) if B <= 5 else rng.integers(0, 5, B).astype(np.int32)
+        _, g, bns, _ = orc.loss_and_grad(th, bns, torch.from_numpy(images[idx]), torch.from_numpy(labels[idx]))
+        th = opt.apply(th, g, 1e-3)
+        eng.train_step(0, xd, yd, 1e-3, index=torch.from_numpy(idx).cuda())
+    q = torch.arange(5, 10, dtype=torch.int32).cuda()
+    pred, lg, inter, uni = eng.predict(0, xd, yd, index=q, want_logits=True)
+    torch.cuda.synchronize()
+    pred_ref, lg_ref = orc.predict(th.float().double(), bns.float().double(), torch.from_numpy(images[5:10]))
+    e_theta = rel_l2(eng.tf_order_vector(eng.theta(0)).cpu().double(), th)
+    e_pred_logits = (lg.cpu().double() - lg_ref).abs().max().item()
+    ious_e, ious_r = [], []
+    for j in range(5):
+        ious_e.append((inter[j].item() + 1e-7) / (uni[j].item() + 1e-7))
+        i_r, u_r = iou_counts(pred_ref.numpy()[j], labels[5 + j])
+        ious_r.append((i_r + 1e-7) / (u_r + 1e-7))
+    return dict(logits=e_logits, grad=e_grad, theta=e_theta, pred_logits=e_pred_logits,
+                miou_engine=float(np.mean(ious_e)), miou_oracle=float(np.mean(ious_r)))
+
+
+@pytest.mark.parametrize("size,B", [(64, 4), (224, 8)])
+def test_tf32_network_within_north_star_tolerances(size, B):
+    e = _tf32_network_errors(size, B, steps=5)
+    print("TF32 mode, %dx%d B=%d: %s" % (size, size, B, e))
+    assert e["logits"] < 1e-2            # logits max-abs
+    assert e["theta"] < 1e-3             # adapted weights rel-L2 after 5 inner Adam steps
+    assert e["pred_logits"] < 1e-2
+    assert abs(e["miou_engine"] - e["miou_oracle"]) < 0.005     # per-task mIoU within 0.5 points
