@@ -178,14 +178,15 @@ GemmA convA(const float* ptr, int ld, int H, int W, int C, int dil) {
 struct Dense {
   const Run& r;
   bool tc() const { return r.c->cfg.gemm_mode != MLIIS_GEMM_FP32; }
+  int split() const { return r.c->cfg.gemm_mode == MLIIS_GEMM_TF32X3 ? 3 : 1; }
   // forward: out[M, Cout] = conv(A[.., Cin]) + bias
   void fwd(const float* A, int lda, int conv, int H, int W, int Cin, int dil, const float* w_hwio, const float* bias,
            float* out, int ldc, int Cout, int M, int HW) const {
     const int taps = conv ? 9 : 1;
     if (tc() && tc_supported(conv, W, Cin, Cout)) {
       float* wt = r.W(r.p.wT);
-      tc_prep_weights(w_hwio, wt, taps, Cin, Cout, 0, r.st);
-      if (tc_conv(A, lda, wt, bias, out, ldc, conv, M, r.B, H, W, Cin, taps, dil, Cout, 0, r.st)) return;
+      tc_prep_weights(w_hwio, wt, taps, Cin, Cout, 0, split(), r.st);
+      if (tc_conv(A, lda, wt, bias, out, ldc, conv, M, r.B, H, W, Cin, taps, dil, Cout, 0, split(), r.st)) return;
     }
     GemmA a = conv ? convA(A, lda, H, W, Cin, dil) : plainA(A, lda);
     gemm_nn(a, w_hwio, bias, out, ldc, M, taps * Cin, Cout, HW, 0, r.st);
@@ -196,9 +197,8 @@ struct Dense {
     const int taps = conv ? 9 : 1;
     float* wt = r.W(r.p.wT);
     if (tc() && tc_supported(conv, W, Cout, Cin)) {
-      const float* bop = w_hwio;            // 1x1: W[Cin][Cout] already is the K-major B operand [N=Cin][K=Cout]
-      if (conv) { tc_prep_weights(w_hwio, wt, taps, Cin, Cout, 1, r.st); bop = wt; }
-      if (tc_conv(G, ldg, bop, nullptr, dA, ldd, conv, M, r.B, H, W, Cout, taps, dil, Cin, accumulate, r.st)) return;
+      tc_prep_weights(w_hwio, wt, taps, Cin, Cout, 1, split(), r.st);
+      if (tc_conv(G, ldg, wt, nullptr, dA, ldd, conv, M, r.B, H, W, Cout, taps, dil, Cin, accumulate, split(), r.st)) return;
     }
     if (conv) {
       flip_transpose_w3x3(w_hwio, wt, Cin, Cout, r.st);
@@ -834,9 +834,10 @@ int mliis_gemm_nn(const float* a, const float* w, float* c, int32_t M, int32_t K
   if (mode != MLIIS_GEMM_FP32) {
     if (!tc_supported(0, 0, K, N)) return fail(MLIIS_ERR_ARG, "shape not supported by the tcgen05 path");
     float* wt = nullptr;
-    if (cudaMalloc(&wt, (size_t)K * N * sizeof(float)) != cudaSuccess) return fail(MLIIS_ERR_CUDA, "alloc");
-    tc_prep_weights(w, wt, 1, K, N, 0, (cudaStream_t)stream);
-    bool ok = tc_conv(a, K, wt, nullptr, c, N, 0, M, 1, 1, 1, K, 1, 1, N, 0, (cudaStream_t)stream);
+    const int split = mode == MLIIS_GEMM_TF32X3 ? 3 : 1;
+    if (cudaMalloc(&wt, (size_t)2 * K * N * sizeof(float)) != cudaSuccess) return fail(MLIIS_ERR_CUDA, "alloc");
+    tc_prep_weights(w, wt, 1, K, N, 0, split, (cudaStream_t)stream);
+    bool ok = tc_conv(a, K, wt, nullptr, c, N, 0, M, 1, 1, 1, K, 1, 1, N, 0, split, (cudaStream_t)stream);
     cudaStreamSynchronize((cudaStream_t)stream);
     cudaFree(wt);
     if (!ok) return fail(MLIIS_ERR_CUDA, "tc_conv setup failed (tensor map encode)");
@@ -854,9 +855,11 @@ int mliis_conv3x3_fwd(const float* x, const float* w, const float* bias, float* 
   if (mode != MLIIS_GEMM_FP32) {
     if (!tc_supported(1, W, Cin, Cout)) return fail(MLIIS_ERR_ARG, "shape not supported by the tcgen05 path");
     float* wt = nullptr;
-    if (cudaMalloc(&wt, (size_t)9 * Cin * Cout * sizeof(float)) != cudaSuccess) return fail(MLIIS_ERR_CUDA, "alloc");
-    tc_prep_weights(w, wt, 9, Cin, Cout, 0, (cudaStream_t)stream);
-    bool ok = tc_conv(x, Cin, wt, bias, y, Cout, 1, B * H * W, B, H, W, Cin, 9, dilation, Cout, 0, (cudaStream_t)stream);
+    const int split = mode == MLIIS_GEMM_TF32X3 ? 3 : 1;
+    if (cudaMalloc(&wt, (size_t)2 * 9 * Cin * Cout * sizeof(float)) != cudaSuccess) return fail(MLIIS_ERR_CUDA, "alloc");
+    tc_prep_weights(w, wt, 9, Cin, Cout, 0, split, (cudaStream_t)stream);
+    bool ok = tc_conv(x, Cin, wt, bias, y, Cout, 1, B * H * W, B, H, W, Cin, 9, dilation, Cout, 0, split,
+                      (cudaStream_t)stream);
     cudaStreamSynchronize((cudaStream_t)stream);
     cudaFree(wt);
     if (!ok) return fail(MLIIS_ERR_CUDA, "tc_conv setup failed (tensor map encode)");

@@ -111,11 +111,22 @@ struct TcParams {
   int N, BN, ldc, accumulate;
   int stages;
   int a_box_bytes;   // bytes one A box delivers
+  int split;         // 1: TF32 (operands rounded to nearest)  3: 3xTF32 (hi/lo split, fp32-class accuracy)
 };
 
 constexpr int kTcThreads = 192;
 constexpr int kABytes = 128 * 128;   // 128 rows x 32 fp32
 
+__device__ __forceinline__ float rn_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Stage layout: [A (hi) 16 KB][A lo 16 KB if split==3][B hi BN*128][B lo BN*128 if split==3]
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const float* __restrict__ bias, float* __restrict__ out, const TcParams p) {
@@ -123,14 +134,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;              // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* smem = smem_raw + (base - raw);
+  const bool x3 = p.split == 3;
   const int b_bytes = p.BN * 128;
-  const int stage_bytes = kABytes + b_bytes;
+  const int a_off_lo = kABytes;
+  const int b_off = x3 ? 2 * kABytes : kABytes;
+  const int stage_bytes = b_off + (x3 ? 2 : 1) * b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   const uint32_t bar0 = base + (uint32_t)p.stages * stage_bytes;
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (p.stages + s); };
-  const uint32_t tmem_full_bar = bar0 + 8u * (2 * p.stages);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };                      // TMA -> transform warps
+  auto empty_bar = [&](int s) { return bar0 + 8u * (p.stages + s); };        // MMA -> TMA
+  auto ready_bar = [&](int s) { return bar0 + 8u * (2 * p.stages + s); };    // transform warps -> MMA
+  const uint32_t tmem_full_bar = bar0 + 8u * (3 * p.stages);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t ncols = 32;
@@ -139,7 +154,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(ready_bar(s), 128);
+    }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -172,15 +191,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int s = kb % p.stages;
         mbar_wait(empty_bar(s), ((kb / p.stages) & 1) ^ 1);
         const int tap = kb / kchunks, kc = kb - tap * kchunks;
-        const uint32_t sa = base + (uint32_t)s * stage_bytes, sb = sa + kABytes;
-        mbar_expect_tx(full_bar(s), (uint32_t)(p.a_box_bytes + b_bytes));
+        const uint32_t sa = base + (uint32_t)s * stage_bytes, sb = sa + b_off;
+        mbar_expect_tx(full_bar(s), (uint32_t)(p.a_box_bytes + (x3 ? 2 : 1) * b_bytes));
         if (p.conv) {
           const int dy = (tap / 3 - 1) * p.dil, dx = (tap % 3 - 1) * p.dil;
           tma_load_4d(sa, &tmA, full_bar(s), kc * 32, dx, y0 + dy, img);
         } else {
           tma_load_2d(sa, &tmA, full_bar(s), kc * 32, m0);
         }
-        tma_load_3d(sb, &tmB, full_bar(s), kc * 32, tap, n0);
+        tma_load_4d(sb, &tmB, full_bar(s), kc * 32, tap, n0, 0);
+        if (x3) tma_load_4d(sb + b_bytes, &tmB, full_bar(s), kc * 32, tap, n0, 1);
       }
     }
   } else if (warp == 1) {
@@ -191,21 +211,46 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % p.stages;
-        mbar_wait(full_bar(s), (kb / p.stages) & 1);
+        mbar_wait(ready_bar(s), (kb / p.stages) & 1);
         tc_fence_after();
         const int kc = kb % kchunks;
         const int rem = p.C - kc * 32;
         const int nk = rem >= 32 ? 4 : (rem + 7) / 8;
-        const uint32_t sa = base + (uint32_t)s * stage_bytes, sb = sa + kABytes;
+        const uint32_t sa = base + (uint32_t)s * stage_bytes, sb = sa + b_off;
         const uint64_t da = make_kmajor_sw128_desc(sa), db = make_kmajor_sw128_desc(sb);
-        for (int k = 0; k < nk; ++k)   // advance 32 bytes (8 tf32) along K inside the 128-byte swizzle atom
-          tc_mma_tf32(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+        const uint64_t dal = make_kmajor_sw128_desc(sa + a_off_lo), dbl = make_kmajor_sw128_desc(sb + b_bytes);
+        for (int k = 0; k < nk; ++k) {  // advance 32 bytes (8 tf32) along K inside the 128-byte swizzle atom
+          const uint64_t adv = (uint64_t)(2 * k);
+          tc_mma_tf32(tmem_acc, da + adv, db + adv, idesc, (kb | k) ? 1u : 0u);
+          if (x3) {   // a*b ~= ah*bh + al*bh + ah*bl   (al*bl ~ 2^-22 relative, dropped)
+            tc_mma_tf32(tmem_acc, dal + adv, db + adv, idesc, 1u);
+            tc_mma_tf32(tmem_acc, da + adv, dbl + adv, idesc, 1u);
+          }
+        }
         tc_commit(empty_bar(s));      // frees the stage once these MMAs have read it
       }
       tc_commit(tmem_full_bar);       // accumulator complete
     }
   } else {
-    // ---------------- epilogue: TMEM -> registers -> global ----------------
+    // ---------------- operand transform (during the main loop), then epilogue ----------------
+    const int t = threadIdx.x - 64;   // 0..127
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % p.stages;
+      mbar_wait(full_bar(s), (kb / p.stages) & 1);
+      float4* a_hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
+      float4* a_lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + a_off_lo);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = t + 128 * j;     // float4 index inside the 16 KB A tile (layout-agnostic: elementwise)
+        const float4 v = a_hi[i];
+        const float4 h = f4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w));
+        a_hi[i] = h;
+        if (x3) a_lo[i] = f4(rn_tf32(v.x - h.x), rn_tf32(v.y - h.y), rn_tf32(v.z - h.z), rn_tf32(v.w - h.w));
+      }
+      // generic-proxy writes must be visible to the async proxy (tcgen05.mma reads smem through it)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(ready_bar(s));
+    }
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;          // accumulator row == TMEM lane
     mbar_wait(tmem_full_bar, 0);
@@ -294,8 +339,9 @@ bool tc_supported(int conv, int W, int C, int N) {
 
 // Wt layout expected by the kernel: [N][taps][C]  (K-major rows of B)
 bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float* out, int ldc, int conv, int M, int B,
-             int H, int W, int C, int taps, int dil, int N, int accumulate, cudaStream_t s) {
+             int H, int W, int C, int taps, int dil, int N, int accumulate, int split, cudaStream_t s) {
   TcParams p{};
+  p.split = split == 3 ? 3 : 1;
   p.conv = conv; p.M = M; p.H = H; p.W = W; p.C = C; p.taps = taps; p.dil = dil; p.N = N; p.ldc = ldc;
   p.accumulate = accumulate;
   p.BN = tc_pick_bn(N);
@@ -320,16 +366,17 @@ bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float*
     grid_x = (M + 127) / 128;
   }
   {
-    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)taps, (cuuint64_t)N};
-    cuuint64_t str[2] = {(cuuint64_t)C * 4, (cuuint64_t)taps * C * 4};
-    cuuint32_t box[3] = {32, 1, (cuuint32_t)p.BN};
-    if (!encode(&tmB, Wt, 3, dims, str, box)) return false;
+    // operand planes: [hi][N][taps][C] and, for split == 3, [lo][N][taps][C] right behind it
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)taps, (cuuint64_t)N, (cuuint64_t)(p.split == 3 ? 2 : 1)};
+    cuuint64_t str[3] = {(cuuint64_t)C * 4, (cuuint64_t)taps * C * 4, (cuuint64_t)N * taps * C * 4};
+    cuuint32_t box[4] = {32, 1, (cuuint32_t)p.BN, 1};
+    if (!encode(&tmB, Wt, 4, dims, str, box)) return false;
   }
-  const int stage_bytes = kABytes + p.BN * 128;
+  const int stage_bytes = (p.split == 3 ? 2 : 1) * (kABytes + p.BN * 128);
   p.stages = (200 * 1024) / stage_bytes;
   if (p.stages > 6) p.stages = 6;
   if (p.stages < 2) return false;
-  const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 2) * 8 + 1024;
+  const size_t smem = (size_t)p.stages * stage_bytes + (3 * p.stages + 2) * 8 + 1024;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -340,22 +387,28 @@ bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float*
   return true;
 }
 
-// weights W[tap][ci][co] (HWIO) -> forward operand Wt[co][tap][ci]   or   dgrad operand Wt[ci][8-tap][co]
+// weights W[tap][ci][co] (HWIO) -> forward operand Wt[co][tap][ci]   or   dgrad operand Wt[ci][taps-1-tap][co],
+// rounded to nearest TF32; split == 3 also writes the residual plane lo = rn(w - hi) behind the hi plane.
 __global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ wt, int taps, int Ci, int Co,
-                                       int dgrad) {
+                                       int dgrad, int split) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= taps * Ci * Co) return;
+  const int n = taps * Ci * Co;
+  if (i >= n) return;
+  float v;
   if (!dgrad) {
     const int co = i / (taps * Ci), rem = i - co * taps * Ci, tap = rem / Ci, ci = rem - tap * Ci;
-    wt[i] = w[((size_t)tap * Ci + ci) * Co + co];
+    v = w[((size_t)tap * Ci + ci) * Co + co];
   } else {
     const int ci = i / (taps * Co), rem = i - ci * taps * Co, tap = rem / Co, co = rem - tap * Co;
-    wt[i] = w[((size_t)(taps - 1 - tap) * Ci + ci) * Co + co];
+    v = w[((size_t)(taps - 1 - tap) * Ci + ci) * Co + co];
   }
+  const float h = rn_tf32(v);
+  wt[i] = h;
+  if (split == 3) wt[(size_t)n + i] = rn_tf32(v - h);
 }
-void tc_prep_weights(const float* w, float* wt, int taps, int Ci, int Co, int dgrad, cudaStream_t s) {
+void tc_prep_weights(const float* w, float* wt, int taps, int Ci, int Co, int dgrad, int split, cudaStream_t s) {
   const int n = taps * Ci * Co;
-  MLIIS_COUNT(), tc_prep_weights_kernel<<<cdiv(n, 256), 256, 0, s>>>(w, wt, taps, Ci, Co, dgrad);
+  MLIIS_COUNT(), tc_prep_weights_kernel<<<cdiv(n, 256), 256, 0, s>>>(w, wt, taps, Ci, Co, dgrad, split);
 }
 
 }  // namespace mliis

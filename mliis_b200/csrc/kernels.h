@@ -114,10 +114,12 @@ void flip_transpose_w3x3(const float* w, float* wt, int C, int N, cudaStream_t s
 // conv=1: A is NHWC [B,H,W,C] (row stride lda), taps = 9 (3x3, dilation dil); conv=0: A is [M,C], taps = 1.
 // Returns false when the shape is not supported (caller falls back to the fp32 FFMA kernels of k_gemm.cu).
 bool tc_supported(int conv, int W, int C, int N);
+// split = 1: TF32 with round-to-nearest operands; split = 3: 3xTF32 (hi/lo planes, fp32-class accuracy).
 bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float* out, int ldc, int conv, int M, int B,
-             int H, int W, int C, int taps, int dil, int N, int accumulate, cudaStream_t s);
-// W[tap][ci][co] (HWIO) -> Wt[co][tap][ci] (dgrad=0)  or  Wt[ci][taps-1-tap][co] (dgrad=1)
-void tc_prep_weights(const float* w, float* wt, int taps, int Ci, int Co, int dgrad, cudaStream_t s);
+             int H, int W, int C, int taps, int dil, int N, int accumulate, int split, cudaStream_t s);
+// W[tap][ci][co] (HWIO) -> Wt[co][tap][ci] (dgrad=0)  or  Wt[ci][taps-1-tap][co] (dgrad=1), rn(tf32);
+// split == 3 appends the residual plane (wt must hold 2 * taps*Ci*Co floats)
+void tc_prep_weights(const float* w, float* wt, int taps, int Ci, int Co, int dgrad, int split, cudaStream_t s);
 
 // ---------------- misc (k_misc.cu) ----------------
 struct ResizeTab { const int32_t* lo; const int32_t* hi; const float* lerp;   // [n_out]

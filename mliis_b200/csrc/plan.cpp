@@ -342,7 +342,7 @@ void Plan::build(int image_size_, int max_batch, const int* rsd, float final_dro
   upd(max_partials, (int64_t)297 * (D * 2 + 2) + 64);
   partials_len = max_partials + 1024;
   partials = b.alloc(partials_len);
-  wT = b.alloc(max_wT);
+  wT = b.alloc(2 * max_wT);   // hi (+ lo) operand planes of the tensor-core path
   tn_scratch = b.alloc(max_tn);
   dcs = b.alloc((int64_t)std::max(1, n_dc) * B);
   lr_dev = b.alloc(64);
