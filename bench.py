@@ -234,20 +234,26 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    mode = {"auto": N.GEMM_FP32, "fp32": N.GEMM_FP32, "tf32": N.GEMM_TF32, "tf32x3": N.GEMM_TF32X3}[args.gemm_mode]
+    # default: 3xTF32 on the tcgen05 path - the fastest mode that meets every north-star tolerance literally
+    mode = {"auto": N.GEMM_TF32X3, "fp32": N.GEMM_FP32, "tf32": N.GEMM_TF32, "tf32x3": N.GEMM_TF32X3}[args.gemm_mode]
     eng = Engine(image_size=IMAGE_SIZE, max_batch=INNER_BATCH, n_slots=args.slots, sgd=args.sgd, gemm_mode=mode,
                  device=local)
-    # "checkpoint": random init (reference initialisers) + 20 inner steps on task 0 so that BN moving
-    # statistics and logits are not degenerate; identical on every rank.
+    # "checkpoint": random init (reference initialisers) + 60 inner steps on task 0, then the BN moving statistics
+    # (momentum 0.99: they lag ~100s of steps) are replaced by the batch statistics of that task so that eval-mode
+    # predictions are not degenerate; identical on every rank.
     random.seed(0)
     eng.init_state(0, initial_variables(eng.ctx.params, 0), *initial_bn_state(eng.n_bn))
     warm = make_plans(1, 0)[0]
     xi = torch.from_numpy(warm.images).cuda()
     yi = torch.from_numpy(warm.labels).cuda()
     rng = np.random.default_rng(0)
-    for s in range(20):
+    for s in range(60):
         idx = torch.from_numpy(rng.integers(0, POOL, INNER_BATCH).astype(np.int32)).cuda()
         eng.train_step(0, xi, yi, LR, index=idx)
+    b0 = eng.bn_state(0).clone()
+    eng.forward(0, xi, True, batch=INNER_BATCH, want_logits=False)      # one EMA update towards the batch statistics
+    torch.cuda.synchronize()
+    eng.bn_state(0).copy_(b0 + (eng.bn_state(0) - b0) / (1.0 - 0.99))   # setup-time plumbing, outside any timing
     torch.cuda.synchronize()
     init_state = eng.states[0].clone()
     init_state[eng.o_v:eng.o_v + eng.n_theta] = 0        # tasks start from a fresh optimizer (no slots in ckpt)
@@ -332,7 +338,7 @@ def run_b200(args):
         "metric": "meta-test adapted-tasks/s (5-shot, 224x224, EfficientLab-6-3, 5 inner Adam steps)",
         "value": value, "unit": "tasks/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if mode == N.GEMM_FP32 else "tf32", "data": "synthetic",
+        "dtype": {N.GEMM_FP32: "f32", N.GEMM_TF32: "tf32", N.GEMM_TF32X3: "tf32x3 (fp32-class)"}[mode], "data": "synthetic",
         "config": {"workload": "meta-test sweep, 5-shot 224x224 synthetic FSS-1000-shaped tasks: per task state reset, "
                                "5 inner %s steps (batch 8), transductive predict of 5 query images, IoU counts"
                                % ("SGD" if args.sgd else "Adam"),
