@@ -204,13 +204,20 @@ def time_dominant_kernel(eng, gemm_mode):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     lib = N.lib()
     st = torch.cuda.current_stream().cuda_stream
+    wt = torch.empty(2 * 9 * Cin * Cout, device="cuda")
+    if gemm_mode != N.GEMM_FP32:     # weight re-layout is a separate (tiny) kernel, done once per step in the engine
+        N.check(lib.mliis_tc_prep_weights(w.data_ptr(), wt.data_ptr(), 9, Cin, Cout, 0, gemm_mode, st))
     times = []
-    for it in range(8):
+    for it in range(10):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        N.check(lib.mliis_conv3x3_fwd(x.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), B, H, H, Cin, Cout, 1,
+        if gemm_mode != N.GEMM_FP32:
+            N.check(lib.mliis_tc_conv(x.data_ptr(), wt.data_ptr(), bias.data_ptr(), y.data_ptr(), B, H, H, Cin, Cout, 9, 1,
                                       gemm_mode, st))
+        else:
+            N.check(lib.mliis_conv3x3_fwd(x.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), B, H, H, Cin, Cout,
+                                          1, gemm_mode, st))
         e1.record()
         e1.synchronize()
         if it >= 3:
@@ -238,27 +245,28 @@ def run_b200(args):
     mode = {"auto": N.GEMM_TF32X3, "fp32": N.GEMM_FP32, "tf32": N.GEMM_TF32, "tf32x3": N.GEMM_TF32X3}[args.gemm_mode]
     eng = Engine(image_size=IMAGE_SIZE, max_batch=INNER_BATCH, n_slots=args.slots, sgd=args.sgd, gemm_mode=mode,
                  device=local)
-    # "checkpoint": random init (reference initialisers) + 60 inner steps on task 0, then the BN moving statistics
-    # (momentum 0.99: they lag ~100s of steps) are replaced by the batch statistics of that task so that eval-mode
-    # predictions are not degenerate; identical on every rank.
+    # "checkpoint": random init (reference initialisers) + 100 Adam steps over 8 synthetic "meta-train" tasks, then
+    # the BN moving statistics (momentum 0.99: they lag 100s of steps) are replaced by the batch statistics of one
+    # image per task so that eval-mode predictions are not degenerate.  Same on every rank.
     random.seed(0)
     eng.init_state(0, initial_variables(eng.ctx.params, 0), *initial_bn_state(eng.n_bn))
-    warm = make_plans(1, 0)[0]
-    xi = torch.from_numpy(warm.images).cuda()
-    yi = torch.from_numpy(warm.labels).cuda()
+    from mliis_b200.synthetic import make_task_arrays, parse_records
+    pools = [parse_records(*make_task_arrays(100000 + t, 6, IMAGE_SIZE)) for t in range(8)]    # 8 "meta-train" tasks
+    xi = torch.from_numpy(np.concatenate([p[0] for p in pools])).cuda()
+    yi = torch.from_numpy(np.concatenate([p[1] for p in pools])).cuda()
     rng = np.random.default_rng(0)
-    for s in range(60):
-        idx = torch.from_numpy(rng.integers(0, POOL, INNER_BATCH).astype(np.int32)).cuda()
+    for s in range(100):
+        idx = torch.from_numpy(rng.integers(0, xi.shape[0], INNER_BATCH).astype(np.int32)).cuda()
         eng.train_step(0, xi, yi, LR, index=idx)
     b0 = eng.bn_state(0).clone()
-    eng.forward(0, xi, True, batch=INNER_BATCH, want_logits=False)      # one EMA update towards the batch statistics
+    ridx = torch.arange(0, 48, 6, dtype=torch.int32).cuda()              # one image of each pre-training task
+    eng.forward(0, xi, True, index=ridx, want_logits=False)             # one EMA update towards the batch statistics
     torch.cuda.synchronize()
     eng.bn_state(0).copy_(b0 + (eng.bn_state(0) - b0) / (1.0 - 0.99))   # setup-time plumbing, outside any timing
     torch.cuda.synchronize()
+    del xi, yi
     init_state = eng.states[0].clone()
-    init_state[eng.o_v:eng.o_v + eng.n_theta] = 0        # tasks start from a fresh optimizer (no slots in ckpt)
-    init_state[eng.o_pow] = 0.0
-    init_state[eng.o_pow + 1] = 0.999
+    # the checkpoint keeps its optimizer slots: Gecko._full_state covers every global variable (reptile.py:35-36)
 
     runner = TaskRunner(eng, POOL, INNER_STEPS, INNER_BATCH, N_QUERY, use_graph=not args.no_graph)
     runner.set_init_state(init_state)

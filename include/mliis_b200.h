@@ -215,6 +215,13 @@ int mliis_gemm_nn(const float* dev_a, const float* dev_w, float* dev_c, int32_t 
 int mliis_conv3x3_fwd(const float* dev_x, const float* dev_w, const float* dev_bias, float* dev_y, int32_t B,
                       int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t dilation, int32_t mode,
                       void* stream);
+/* The tcgen05 / TMA / TMEM contraction alone (no allocation, no synchronisation): re-lay-out the HWIO kernel
+ * once with mliis_tc_prep_weights (dev_wt: taps*Cin*Cout floats, twice that for MLIIS_GEMM_TF32X3), then run
+ * y[B,H,W,Cout] = conv(x[B,H,W,Cin]) + bias with taps = 9 (3x3, SAME, dilation) or taps = 1 (1x1 / GEMM). */
+int mliis_tc_prep_weights(const float* dev_w, float* dev_wt, int32_t taps, int32_t Cin, int32_t Cout, int32_t dgrad,
+                          int32_t mode, void* stream);
+int mliis_tc_conv(const float* dev_x, const float* dev_wt, const float* dev_bias, float* dev_y, int32_t B, int32_t H,
+                  int32_t W, int32_t Cin, int32_t Cout, int32_t taps, int32_t dilation, int32_t mode, void* stream);
 int mliis_bilinear_fwd(const float* dev_x, float* dev_y, int32_t B, int32_t Hin, int32_t Win, int32_t Hout,
                        int32_t Wout, int32_t C, void* stream);
 int mliis_adam_step(float* dev_theta, float* dev_v, const float* dev_grad, int64_t n, int64_t n_l2, float lr,

@@ -869,6 +869,28 @@ int mliis_conv3x3_fwd(const float* x, const float* w, const float* bias, float* 
   return check_cuda("conv3x3_fwd");
 }
 
+int mliis_tc_prep_weights(const float* w, float* wt, int32_t taps, int32_t Cin, int32_t Cout, int32_t dgrad,
+                          int32_t mode, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (mode == MLIIS_GEMM_FP32) return fail(MLIIS_ERR_ARG, "mode must be a tensor-core mode");
+  tc_prep_weights(w, wt, taps, Cin, Cout, dgrad, mode == MLIIS_GEMM_TF32X3 ? 3 : 1, (cudaStream_t)stream);
+  return check_cuda("tc_prep_weights");
+}
+
+int mliis_tc_conv(const float* x, const float* wt, const float* bias, float* y, int32_t B, int32_t H, int32_t W,
+                  int32_t Cin, int32_t Cout, int32_t taps, int32_t dilation, int32_t mode, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (mode == MLIIS_GEMM_FP32 || (taps != 1 && taps != 9)) return fail(MLIIS_ERR_ARG, "bad mode / taps");
+  const int conv = taps == 9;
+  if (!tc_supported(conv, W, Cin, Cout)) return fail(MLIIS_ERR_ARG, "shape not supported by the tcgen05 path");
+  if (!tc_conv(x, Cin, wt, bias, y, Cout, conv, B * H * W, B, H, W, Cin, taps, dilation, Cout, 0,
+               mode == MLIIS_GEMM_TF32X3 ? 3 : 1, (cudaStream_t)stream))
+    return fail(MLIIS_ERR_CUDA, "tc_conv setup failed (tensor map encode)");
+  return check_cuda("tc_conv");
+}
+
 int mliis_bilinear_fwd(const float* x, float* y, int32_t B, int32_t Hin, int32_t Win, int32_t Hout, int32_t Wout,
                        int32_t C, void* stream) {
   int rc = require_sm100();

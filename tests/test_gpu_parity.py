@@ -330,7 +330,7 @@ def test_tc_gemm_nn(M, K, N_):
     c.fill_(float("nan"))
     N.check(N.lib().mliis_gemm_nn(ad.data_ptr(), wd.data_ptr(), c.data_ptr(), M, K, N_, 2, None))   # 3xTF32
     torch.cuda.synchronize()
-    assert rel_err(c, ref) < 2e-5
+    assert rel_err(c, ref) < 1e-4
 
 
 @pytest.mark.parametrize("H,Cin,Cout,dil,B", [(56, 136, 112, 2, 2), (56, 360, 112, 1, 1), (14, 224, 112, 2, 3),
@@ -355,7 +355,7 @@ def test_tc_conv3x3(H, Cin, Cout, dil, B):
     N.check(N.lib().mliis_conv3x3_fwd(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), y.data_ptr(), B, H, H, Cin, Cout,
                                       dil, 2, None))                                                   # 3xTF32
     torch.cuda.synchronize()
-    assert rel_err(y, ref) < 2e-5      # fp32 accumulation over 3*9*Cin terms
+    assert rel_err(y, ref) < 1e-4      # fp32 accumulation over 3*9*Cin terms in the tensor-core adder
 
 
 def _tf32_network_errors(size, B, steps, mode, warm=0):
@@ -428,31 +428,38 @@ def test_adaptation_from_pretrained_state_all_modes():
     second task: 5 Adam steps of batch 8 on 5 support images, transductive prediction of 5 query images.  Every
     numeric mode must agree with the float64 oracle on adapted weights, query logits and per-task mIoU."""
     from mliis_b200 import native as N
+    from mliis_b200.synthetic import make_task_arrays, parse_records
+    from oracle.efficientlab_oracle import BN_MOMENTUM
     size, B, T = 64, 8, 5
-    arch, theta, bn, images0, labels0 = make_problem(size, 10, task_id=0)
+    arch, theta, bn, _, _ = make_problem(size, 2, task_id=0)
+    pools = [parse_records(*make_task_arrays(t, 6, size)) for t in range(8)]          # pre-train on 8 tasks
+    x0 = torch.from_numpy(np.concatenate([p[0] for p in pools]))
+    y0 = torch.from_numpy(np.concatenate([p[1] for p in pools]))
     o32 = EfficientLabOracle(arch, torch.float32)
     th, bns = theta.float(), bn.float()
     opt = OptState(arch.n_params, torch.float32)
     g = torch.Generator().manual_seed(0)
-    x0, y0 = torch.from_numpy(images0), torch.from_numpy(labels0)
-    for s in range(80):
-        idx = torch.randint(0, 10, (8,), generator=g)
+    for s in range(100):
+        idx = torch.randint(0, x0.shape[0], (8,), generator=g)
         _, gr, bns, _ = o32.loss_and_grad(th, bns, x0[idx], y0[idx])
         th = opt.apply(th, gr, 1e-3)
-    # BN recalibration: the moving statistics (momentum 0.99) lag far behind after 80 steps; replace them by the
-    # batch statistics of the pre-training set so that eval-mode predictions are meaningful
-    from oracle.efficientlab_oracle import BN_MOMENTUM
+    # BN recalibration: the moving statistics (momentum 0.99) lag far behind after 100 steps; replace them by the
+    # batch statistics of 16 images drawn across the pre-training tasks so that eval-mode predictions are meaningful
     o64 = EfficientLabOracle(arch, torch.float64)
     b0 = bns.double()
-    _, nb = o64.forward(th.double(), b0, x0, True)
+    _, nb = o64.forward(th.double(), b0, x0[torch.arange(0, 48, 3)], True)
     theta = th.double()
     bn = (b0 + (nb - b0) / (1 - BN_MOMENTUM)).float().double()
-    _, _, _, images, labels = make_problem(size, 10, task_id=1)
+    images, labels = parse_records(*make_task_arrays(20, 10, size))                    # the held-out task
     orc = EfficientLabOracle(arch, torch.float64)
     rng = np.random.default_rng(0)
     batches = [rng.integers(0, 5, B).astype(np.int32) for _ in range(T)]
     tho, bno = theta, bn
+    # the pre-trained "checkpoint" carries its optimizer slots (Gecko._full_state covers all global variables)
     oo = OptState(arch.n_params, torch.float64)
+    oo.v = opt.v.double().clone()
+    oo.b1p, oo.b2p = opt.b1p, float(np.float32(opt.b2p))
+    v_slots, b2p0 = opt.v.double().clone(), oo.b2p
     for b in batches:
         _, gr, bno, _ = orc.loss_and_grad(tho, bno, torch.from_numpy(images[b]), torch.from_numpy(labels[b]))
         tho = oo.apply(tho, gr, 1e-3)
@@ -464,6 +471,8 @@ def test_adaptation_from_pretrained_state_all_modes():
     rows = []
     for mode in (N.GEMM_FP32, N.GEMM_TF32X3, N.GEMM_TF32):
         eng = make_engine(arch, theta, bn, size, B, gemm_mode=mode)
+        eng.init_state(0, split_vars(arch, theta), bn[0].numpy(), bn[1].numpy(), adam_v=split_vars(arch, v_slots),
+                       beta1_power=0.0, beta2_power=b2p0)
         for b in batches:
             eng.train_step(0, xd, yd, 1e-3, index=torch.from_numpy(b).cuda())
         _, lg, inter, uni = eng.predict(0, xd, yd, index=q, want_pred=False, want_logits=True)
