@@ -191,6 +191,19 @@ struct Dense {
     GemmA a = conv ? convA(A, lda, H, W, Cin, dil) : plainA(A, lda);
     gemm_nn(a, w_hwio, bias, out, ldc, M, taps * Cin, Cout, HW, 0, r.st);
   }
+  // MBConv project conv: out[M, Cout] = (swish(pa*A+pb) * gate[img]) * W
+  void fwd_pro(const float* A, int lda, int Cin, const float* w_hwio, float* out, int ldc, int Cout, int M, int HW,
+               const float* pa, const float* pb, const float* gate) const {
+    if (tc() && tc_supported(0, 0, Cin, Cout)) {
+      float* wt = r.W(r.p.wT);
+      tc_prep_weights(w_hwio, wt, 1, Cin, Cout, 0, split(), r.st);
+      if (tc_conv(A, lda, wt, nullptr, out, ldc, 0, M, r.B, 1, 1, Cin, 1, 1, Cout, 0, split(), r.st, pa, pb, gate, HW))
+        return;
+    }
+    GemmA a = plainA(A, lda);
+    a.pa = pa; a.pb = pb; a.gate = gate;
+    gemm_nn(a, w_hwio, nullptr, out, ldc, M, Cin, Cout, HW, 0, r.st);
+  }
   // dgrad: dA[M, Cin] (+)= conv^T(G[.., Cout])
   void dgrad(const float* G, int ldg, int conv, int H, int W, int Cin, int dil, const float* w_hwio, float* dA, int ldd,
              int Cout, int M, int HW, int accumulate) const {
@@ -237,7 +250,8 @@ void run_forward(const Run& r, const float* images, const int32_t* index, bool t
     const int Mi = B * b.Hin * b.Win, Mo = B * b.Hout * b.Wout, HWo = b.Hout * b.Wout;
     const float *dw_in, *dw_a, *dw_b;
     if (b.expand) {
-      gemm_nn(plainA(X, Xld), r.T(b.w_expand), nullptr, r.W(b.E.off), b.ce, Mi, b.cin, b.ce, b.Hin * b.Win, 0, st);
+      Dense{r}.fwd(X, Xld, 0, b.Hin, b.Win, b.cin, 1, r.T(b.w_expand), nullptr, r.W(b.E.off), b.ce, b.ce, Mi,
+                   b.Hin * b.Win);
       if (training) r.bn_train(b.bn0, r.W(b.E.off), b.ce, Mi, false);
       dw_in = r.W(b.E.off); dw_a = r.bn_a(b.bn0); dw_b = r.bn_b(b.bn0);
     } else {
@@ -251,9 +265,8 @@ void run_forward(const Run& r, const float* images, const int32_t* index, bool t
     se_fc_fwd(r.W(p.partials), rc_num_img_chunks(HWo, b.ce), B, HWo, b.ce, b.cr, r.T(b.w_se1), r.T(b.b_se1),
               r.T(b.w_se2), r.T(b.b_se2), r.W(b.pool), r.W(b.hidpre), r.W(b.gate), st);
     // project conv consumes swish(BN1(dw)) * gate, recomputed in the A-operand loader
-    GemmA A = plainA(r.W(b.D.off), b.ce);
-    A.pa = r.bn_a(b.bn1); A.pb = r.bn_b(b.bn1); A.gate = r.W(b.gate);
-    gemm_nn(A, r.T(b.w_proj), nullptr, r.W(b.P.off), b.cout, Mo, b.ce, b.cout, HWo, 0, st);
+    Dense{r}.fwd_pro(r.W(b.D.off), b.ce, b.ce, r.T(b.w_proj), r.W(b.P.off), b.cout, b.cout, Mo, HWo, r.bn_a(b.bn1),
+                     r.bn_b(b.bn1), r.W(b.gate));
     if (training) r.bn_train(b.bn2, r.W(b.P.off), b.cout, Mo, false);
     const float* dcs = (training && b.dc_idx >= 0) ? r.W(p.dcs + (int64_t)b.dc_idx * p.maxB) : nullptr;
     block_out(r.W(b.P.off), b.cout, r.bn_a(b.bn2), r.bn_b(b.bn2), dcs, b.skip ? X : nullptr, Xld, r.W(b.Y.off),
@@ -426,8 +439,7 @@ void run_backward(const Run& r, const float* labels, const int32_t* index, float
     GemmA Ap = plainA(r.W(b.D.off), b.ce);
     Ap.pa = r.bn_a(b.bn1); Ap.pb = r.bn_b(b.bn1); Ap.gate = r.W(b.gate);
     gemm_tn(Ap, r.W(p.gP), b.cout, r.G(b.w_proj), nullptr, r.W(p.tn_scratch), Mo, b.ce, b.cout, HWo, st);
-    transpose_w(r.T(b.w_proj), r.W(p.wT), b.ce, b.cout, st);
-    gemm_nn(plainA(r.W(p.gP), b.cout), r.W(p.wT), nullptr, r.W(p.gD), b.ce, Mo, b.cout, b.ce, HWo, 0, st);
+    Dense{r}.dgrad(r.W(p.gP), b.cout, 0, b.Hout, b.Wout, b.ce, 1, r.T(b.w_proj), r.W(p.gD), b.ce, b.cout, Mo, HWo, 0);
     // squeeze-excite backward
     se_bwd_reduce(r.W(b.D.off), b.ce, r.W(p.gD), b.ce, r.bn_a(b.bn1), r.bn_b(b.bn1), B, HWo, b.ce, r.W(p.partials), st);
     se_fc_bwd(r.W(p.partials), rc_num_img_chunks(HWo, b.ce), B, HWo, b.ce, b.cr, r.T(b.w_se1), r.T(b.w_se2),
@@ -461,10 +473,10 @@ void run_backward(const Run& r, const float* labels, const int32_t* index, float
     }
     if (b.expand) {
       gemm_tn(plainA(X, b.cin), r.W(p.gE), b.ce, r.G(b.w_expand), nullptr, r.W(p.tn_scratch), Mi, b.cin, b.ce, HWi, st);
-      transpose_w(r.T(b.w_expand), r.W(p.wT), b.cin, b.ce, st);
       // dX = dE * We^T (+ dY through the identity skip: same shape, accumulate in place)
       float* gX = b.skip ? gY : r.W(p.gY[cur ^ 1]);
-      gemm_nn(plainA(r.W(p.gE), b.ce), r.W(p.wT), nullptr, gX, b.cin, Mi, b.ce, b.cin, HWi, b.skip ? 1 : 0, st);
+      Dense{r}.dgrad(r.W(p.gE), b.ce, 0, b.Hin, b.Win, b.cin, 1, r.T(b.w_expand), gX, b.cin, b.ce, Mi, HWi,
+                     b.skip ? 1 : 0);
       if (b.skip && gY != r.W(p.gY[cur])) {
         // gradient lived in the decoder's extra buffer: move it into the ping-pong chain
         add3(r.W(p.gY[cur]), b.cin, gX, b.cin, nullptr, 0, nullptr, 0, Mi, b.cin, HWi, st);

@@ -112,6 +112,9 @@ struct TcParams {
   int stages;
   int a_box_bytes;   // bytes one A box delivers
   int split;         // 1: TF32 (operands rounded to nearest)  3: 3xTF32 (hi/lo split, fp32-class accuracy)
+  // A-operand prologue applied by the transform warps (plain mode): a <- swish(pa[k]*a + pb[k]) * gate[img][k]
+  const float* pa; const float* pb; const float* gate;
+  int HW;
 };
 
 constexpr int kTcThreads = 192;
@@ -127,7 +130,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 
 // Stage layout: [A (hi) 16 KB][A lo 16 KB if split==3][B hi BN*128][B lo BN*128 if split==3]
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const float* __restrict__ bias, float* __restrict__ out, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -239,10 +242,24 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(full_bar(s), (kb / p.stages) & 1);
       float4* a_hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
       float4* a_lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + a_off_lo);
+      const int kc32 = (kb % kchunks) * 32;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int i = t + 128 * j;     // float4 index inside the 16 KB A tile (layout-agnostic: elementwise)
-        const float4 v = a_hi[i];
+        const int i = t + 128 * j;     // float4 index inside the 16 KB A tile: row = i/8, physical 16-byte chunk = i%8
+        float4 v = a_hi[i];
+        if (p.pa) {
+          // SWIZZLE_128B: logical chunk = physical chunk XOR (row & 7)  ->  channel of this float4
+          const int row = i >> 3;
+          const int k = kc32 + (((i & 7) ^ (row & 7)) << 2);
+          if (k < p.C) {
+            v = swish4(affine4(v, ld4(p.pa + k), ld4(p.pb + k)));
+            if (p.gate) {
+              const int m = m0 + row;
+              const int im = m < p.M ? m / p.HW : 0;
+              v = v * ld4(p.gate + (size_t)im * p.C + k);
+            }
+          }
+        }
         const float4 h = f4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w));
         a_hi[i] = h;
         if (x3) a_lo[i] = f4(rn_tf32(v.x - h.x), rn_tf32(v.y - h.y), rn_tf32(v.z - h.z), rn_tf32(v.w - h.w));
@@ -339,9 +356,12 @@ bool tc_supported(int conv, int W, int C, int N) {
 
 // Wt layout expected by the kernel: [N][taps][C]  (K-major rows of B)
 bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float* out, int ldc, int conv, int M, int B,
-             int H, int W, int C, int taps, int dil, int N, int accumulate, int split, cudaStream_t s) {
+             int H, int W, int C, int taps, int dil, int N, int accumulate, int split, cudaStream_t s,
+             const float* pa, const float* pb, const float* gate, int HW) {
   TcParams p{};
   p.split = split == 3 ? 3 : 1;
+  if (pa && conv) return false;
+  p.pa = pa; p.pb = pb; p.gate = gate; p.HW = HW > 0 ? HW : 1;
   p.conv = conv; p.M = M; p.H = H; p.W = W; p.C = C; p.taps = taps; p.dil = dil; p.N = N; p.ldc = ldc;
   p.accumulate = accumulate;
   p.BN = tc_pick_bn(N);
@@ -375,7 +395,9 @@ bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float*
   const int stage_bytes = (p.split == 3 ? 2 : 1) * (kABytes + p.BN * 128);
   p.stages = (200 * 1024) / stage_bytes;
   if (p.stages > 6) p.stages = 6;
-  if (p.stages < 2) return false;
+  const int KB = taps * ((C + 31) / 32);
+  if (p.stages > KB) p.stages = KB;        // small-K problems: less shared memory -> several CTAs per SM
+  if (p.stages < 1) return false;
   const size_t smem = (size_t)p.stages * stage_bytes + (3 * p.stages + 2) * 8 + 1024;
   static bool attr = false;
   if (!attr) {

@@ -115,8 +115,11 @@ void flip_transpose_w3x3(const float* w, float* wt, int C, int N, cudaStream_t s
 // Returns false when the shape is not supported (caller falls back to the fp32 FFMA kernels of k_gemm.cu).
 bool tc_supported(int conv, int W, int C, int N);
 // split = 1: TF32 with round-to-nearest operands; split = 3: 3xTF32 (hi/lo planes, fp32-class accuracy).
+// Optional A prologue (conv = 0 only): a <- swish(pa[k]*a + pb[k]) * gate[row / HW][k], applied in shared memory by
+// the transform warps (MBConv project conv: BN1 + swish + squeeze-excite gate never touch HBM).
 bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float* out, int ldc, int conv, int M, int B,
-             int H, int W, int C, int taps, int dil, int N, int accumulate, int split, cudaStream_t s);
+             int H, int W, int C, int taps, int dil, int N, int accumulate, int split, cudaStream_t s,
+             const float* pa = nullptr, const float* pb = nullptr, const float* gate = nullptr, int HW = 0);
 // W[tap][ci][co] (HWIO) -> Wt[co][tap][ci] (dgrad=0)  or  Wt[ci][taps-1-tap][co] (dgrad=1), rn(tf32);
 // split == 3 appends the residual plane (wt must hold 2 * taps*Ci*Co floats)
 void tc_prep_weights(const float* w, float* wt, int taps, int Ci, int Co, int dgrad, int split, cudaStream_t s);
