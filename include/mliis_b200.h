@@ -222,6 +222,10 @@ int mliis_tc_prep_weights(const float* dev_w, float* dev_wt, int32_t taps, int32
                           int32_t mode, void* stream);
 int mliis_tc_conv(const float* dev_x, const float* dev_wt, const float* dev_bias, float* dev_y, int32_t B, int32_t H,
                   int32_t W, int32_t Cin, int32_t Cout, int32_t taps, int32_t dilation, int32_t mode, void* stream);
+/* Weight gradient on the tensor cores: dev_dw[taps*Cin, Cout] = sum over pixels of a[pixel+tap, :]^T g[pixel, :]
+ * (a: [B,H,W,Cin], g: [B,H,W,Cout]; taps = 9 for a 3x3 SAME conv with `dilation`, 1 for a 1x1 conv). */
+int mliis_tc_wgrad(const float* dev_a, const float* dev_g, float* dev_dw, int32_t B, int32_t H, int32_t W, int32_t Cin,
+                   int32_t Cout, int32_t taps, int32_t dilation, int32_t mode, void* stream);
 int mliis_bilinear_fwd(const float* dev_x, float* dev_y, int32_t B, int32_t Hin, int32_t Win, int32_t Hout,
                        int32_t Wout, int32_t C, void* stream);
 int mliis_adam_step(float* dev_theta, float* dev_v, const float* dev_grad, int64_t n, int64_t n_l2, float lr,

@@ -204,6 +204,30 @@ struct Dense {
     a.pa = pa; a.pb = pb; a.gate = gate;
     gemm_nn(a, w_hwio, nullptr, out, ldc, M, Cin, Cout, HW, 0, r.st);
   }
+  // wgrad: dW[taps*Cin, Cout] = sum_pixels A^T G (+ dbias = column sums of G).  `swap`: compute dW^T with the roles
+  // of A and G exchanged (MBConv expand conv: Cout = 6*Cin > 256 would not fit one N tile), then transpose.
+  void wgrad(const float* A, int lda, int conv, int H, int W, int Cin, int dil, const float* G, int ldg, int Cout,
+             float* dW, float* dbias, int M, int HW, const float* pa = nullptr, const float* pb = nullptr,
+             const float* gate = nullptr, bool swap = false) const {
+    const int taps = conv ? 9 : 1;
+    float* scratch = r.W(r.p.tn_scratch);
+    bool done = false;
+    if (tc()) {
+      if (!swap && tc_wgrad_supported(conv, W, Cin, Cout)) {
+        done = tc_wgrad(A, lda, G, ldg, dW, scratch, conv, M, r.B, H, W, Cin, taps, dil, Cout, split(), r.st, pa, pb, gate, HW);
+      } else if (swap && !conv && !pa && tc_wgrad_supported(0, W, Cout, Cin)) {
+        float* tmp = r.W(r.p.wT);      // dW^T [Cout][Cin]
+        done = tc_wgrad(G, ldg, A, lda, tmp, scratch, 0, M, r.B, H, W, Cout, 1, 1, Cin, split(), r.st);
+        if (done) transpose_w(tmp, dW, Cout, Cin, r.st);
+      }
+      if (done && dbias) img_colsum(G, ldg, 1, M, Cout, 1.f, r.W(r.p.partials), dbias, Cout, r.st);
+    }
+    if (!done) {
+      GemmA a = conv ? convA(A, lda, H, W, Cin, dil) : plainA(A, lda);
+      a.pa = pa; a.pb = pb; a.gate = gate;
+      gemm_tn(a, G, ldg, dW, dbias, scratch, M, taps * Cin, Cout, HW, r.st);
+    }
+  }
   // dgrad: dA[M, Cin] (+)= conv^T(G[.., Cout])
   void dgrad(const float* G, int ldg, int conv, int H, int W, int Cin, int dil, const float* w_hwio, float* dA, int ldd,
              int Cout, int M, int HW, int accumulate) const {
@@ -374,20 +398,18 @@ void run_backward(const Run& r, const float* labels, const int32_t* index, float
     };
     // out = BN2(swish(c2)) + up
     dec_bn_bwd(d.bn[2], r.W(d.c2.off), gOut, D, r.W(p.g_c));
-    gemm_tn(convA(pyr, d.pyrC, d.h, d.w, d.pyrC, 1), r.W(p.g_c), D, r.G(d.w2), r.G(d.b2), r.W(p.tn_scratch), M,
-            9 * d.pyrC, D, HW, st);
     const Dense dense{r};
+    dense.wgrad(pyr, d.pyrC, 1, d.h, d.w, d.pyrC, 1, r.W(p.g_c), D, D, r.G(d.w2), r.G(d.b2), M, HW);
     dense.dgrad(r.W(p.g_c), D, 1, d.h, d.w, d.pyrC, 1, r.T(d.w2), r.W(p.g_pyr), d.pyrC, D, M, HW, 0);
     const float* gpyr = r.W(p.g_pyr);
     dec_bn_bwd(d.bn[0], r.W(d.c0.off), gpyr, d.pyrC, r.W(p.g_c0));
     dec_bn_bwd(d.bn[1], r.W(d.c1.off), gpyr + D, d.pyrC, r.W(p.g_c1));
     img_colsum(gpyr + 2 * D, d.pyrC, B, HW, d.catC, 1.f / (float)HW, r.W(p.partials), r.W(d.dpooled), d.catC, st);
     // branch_0 1x1
-    gemm_tn(plainA(cat, d.catC), r.W(p.g_c0), D, r.G(d.w0), r.G(d.b0), r.W(p.tn_scratch), M, d.catC, D, HW, st);
+    dense.wgrad(cat, d.catC, 0, d.h, d.w, d.catC, 1, r.W(p.g_c0), D, D, r.G(d.w0), r.G(d.b0), M, HW);
     dense.dgrad(r.W(p.g_c0), D, 0, d.h, d.w, d.catC, 1, r.T(d.w0), r.W(p.g_cat), d.catC, D, M, HW, 0);
     // branch_1 3x3 dil 2 (accumulates into g_cat)
-    gemm_tn(convA(cat, d.catC, d.h, d.w, d.catC, 2), r.W(p.g_c1), D, r.G(d.w1), r.G(d.b1), r.W(p.tn_scratch), M,
-            9 * d.catC, D, HW, st);
+    dense.wgrad(cat, d.catC, 1, d.h, d.w, d.catC, 2, r.W(p.g_c1), D, D, r.G(d.w1), r.G(d.b1), M, HW);
     dense.dgrad(r.W(p.g_c1), D, 1, d.h, d.w, d.catC, 2, r.T(d.w1), r.W(p.g_cat), d.catC, D, M, HW, 1);
     // d_up = gOut + g_cat[:, :D] + dpooled[:, :D]      d_skip = g_cat[:, D:] + dpooled[:, D:]
     const float* gcat = r.W(p.g_cat);
@@ -436,9 +458,8 @@ void run_backward(const Run& r, const float* labels, const int32_t* index, float
       bn_bwd(BN_PLAIN, a, st);
     }
     // project conv: wgrad on swish(BN1(D))*gate (recomputed), dgrad into gD
-    GemmA Ap = plainA(r.W(b.D.off), b.ce);
-    Ap.pa = r.bn_a(b.bn1); Ap.pb = r.bn_b(b.bn1); Ap.gate = r.W(b.gate);
-    gemm_tn(Ap, r.W(p.gP), b.cout, r.G(b.w_proj), nullptr, r.W(p.tn_scratch), Mo, b.ce, b.cout, HWo, st);
+    Dense{r}.wgrad(r.W(b.D.off), b.ce, 0, b.Hout, b.Wout, b.ce, 1, r.W(p.gP), b.cout, b.cout, r.G(b.w_proj), nullptr, Mo,
+                   HWo, r.bn_a(b.bn1), r.bn_b(b.bn1), r.W(b.gate));
     Dense{r}.dgrad(r.W(p.gP), b.cout, 0, b.Hout, b.Wout, b.ce, 1, r.T(b.w_proj), r.W(p.gD), b.ce, b.cout, Mo, HWo, 0);
     // squeeze-excite backward
     se_bwd_reduce(r.W(b.D.off), b.ce, r.W(p.gD), b.ce, r.bn_a(b.bn1), r.bn_b(b.bn1), B, HWo, b.ce, r.W(p.partials), st);
@@ -472,7 +493,8 @@ void run_backward(const Run& r, const float* labels, const int32_t* index, float
       bn_bwd(BN_SWISH, a, st);
     }
     if (b.expand) {
-      gemm_tn(plainA(X, b.cin), r.W(p.gE), b.ce, r.G(b.w_expand), nullptr, r.W(p.tn_scratch), Mi, b.cin, b.ce, HWi, st);
+      Dense{r}.wgrad(X, b.cin, 0, b.Hin, b.Win, b.cin, 1, r.W(p.gE), b.ce, b.ce, r.G(b.w_expand), nullptr, Mi, HWi,
+                     nullptr, nullptr, nullptr, /*swap=*/true);
       // dX = dE * We^T (+ dY through the identity skip: same shape, accumulate in place)
       float* gX = b.skip ? gY : r.W(p.gY[cur ^ 1]);
       Dense{r}.dgrad(r.W(p.gE), b.ce, 0, b.Hin, b.Win, b.cin, 1, r.T(b.w_expand), gX, b.cin, b.ce, Mi, HWi,
@@ -901,6 +923,24 @@ int mliis_tc_conv(const float* x, const float* wt, const float* bias, float* y, 
                mode == MLIIS_GEMM_TF32X3 ? 3 : 1, (cudaStream_t)stream))
     return fail(MLIIS_ERR_CUDA, "tc_conv setup failed (tensor map encode)");
   return check_cuda("tc_conv");
+}
+
+int mliis_tc_wgrad(const float* a, const float* g, float* dw, int32_t B, int32_t H, int32_t W, int32_t Cin,
+                   int32_t Cout, int32_t taps, int32_t dilation, int32_t mode, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (mode == MLIIS_GEMM_FP32 || (taps != 1 && taps != 9)) return fail(MLIIS_ERR_ARG, "bad mode / taps");
+  const int conv = taps == 9, M = B * H * W;
+  if (!tc_wgrad_supported(conv, W, Cin, Cout)) return fail(MLIIS_ERR_ARG, "shape not supported by the tcgen05 wgrad");
+  float* scratch = nullptr;
+  if (cudaMalloc(&scratch, tc_wgrad_scratch(conv, M, B, H, W, Cin, Cout, taps) * sizeof(float)) != cudaSuccess)
+    return fail(MLIIS_ERR_CUDA, "alloc");
+  bool ok = tc_wgrad(a, Cin, g, Cout, dw, scratch, conv, M, B, H, W, Cin, taps, dilation, Cout,
+                     mode == MLIIS_GEMM_TF32X3 ? 3 : 1, (cudaStream_t)stream);
+  cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(scratch);
+  if (!ok) return fail(MLIIS_ERR_CUDA, "tc_wgrad setup failed (tensor map encode)");
+  return check_cuda("tc_wgrad");
 }
 
 int mliis_bilinear_fwd(const float* x, float* y, int32_t B, int32_t Hin, int32_t Win, int32_t Hout, int32_t Wout,

@@ -409,6 +409,282 @@ bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float*
   return true;
 }
 
+// =================================================================================================
+// wgrad on tensor cores:  dW[tap][c][n] = sum_pixels A[pixel + offset(tap), c] * G[pixel, n]
+//
+// The reduction (MMA K) dimension is the pixel index, so both operands are "MN-major": channels are contiguous
+// in memory.  One TMA box {32 channels, 32 pixels} lands as a [32 pixel rows][128 B] 128-byte-swizzled slab, which is
+// exactly the canonical MN-major SWIZZLE_128B atom stack (8 pixel rows x 128 B per atom, SBO = 1024 B between
+// atoms along K, LBO = 4096 B between 32-channel groups along M/N).  One tcgen05.mma (K = 8) consumes one atom
+// per channel group.  grid = (128-channel tiles of A, taps, pixel-range splits); each CTA writes its fp32 partial
+// [128 x N] and the partials are reduced in a fixed order by reduce_partials (deterministic, no atomics).
+// =================================================================================================
+struct TcWgParams {
+  int conv, M;                 // plain: A [M, C], G [M, N]
+  int H, W, BX, BY, tiles_x, tiles_y;   // conv: pixel box BX x BY (= 32 pixels)
+  int C, N, BN, NG;            // NG = 32-channel groups of G
+  int taps, dil;
+  int splits, tiles_total;
+  int stages, split;
+  const float* pa; const float* pb; const float* gate;   // A prologue (plain mode), as in tc_conv_kernel
+  int HW;
+};
+
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+  //  LBO (bits 16..29) = 4096 B >> 4 : stride between 32-element groups along M/N
+  //  SBO (bits 32..45) = 1024 B >> 4 : stride between 8-row atoms along K
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (256ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+constexpr int kWgGroupBytes = 32 * 128;   // one TMA box: 32 pixel rows x 32 channels fp32
+
+__global__ void __launch_bounds__(kTcThreads)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmG,
+                float* __restrict__ partial, const TcWgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const bool x3 = p.split == 3;
+  const int a_bytes = 4 * kWgGroupBytes, g_bytes = p.NG * kWgGroupBytes;
+  const int a_lo = a_bytes;                                  // offset of the A lo plane (x3)
+  const int g_off = x3 ? 2 * a_bytes : a_bytes;
+  const int g_lo = g_off + g_bytes;
+  const int stage_bytes = g_off + (x3 ? 2 : 1) * g_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  const uint32_t bar0 = base + (uint32_t)p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (p.stages + s); };
+  auto ready_bar = [&](int s) { return bar0 + 8u * (2 * p.stages + s); };
+  const uint32_t tmem_full_bar = bar0 + 8u * (3 * p.stages);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t ncols = 32;
+  while ((int)ncols < p.BN) ncols <<= 1;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(ready_bar(s), 128); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  const int c0 = blockIdx.x * 128, tap = blockIdx.y, split = blockIdx.z;
+  const int per = (p.tiles_total + p.splits - 1) / p.splits;
+  const int t_beg = split * per, t_end = min(p.tiles_total, t_beg + per);
+  const int KB = max(t_end - t_beg, 0);
+  const int dy = p.conv ? (tap / 3 - 1) * p.dil : 0, dx = p.conv ? (tap % 3 - 1) * p.dil : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % p.stages;
+        mbar_wait(empty_bar(s), ((kb / p.stages) & 1) ^ 1);
+        const uint32_t sa = base + (uint32_t)s * stage_bytes, sg = sa + g_off;
+        mbar_expect_tx(full_bar(s), (uint32_t)(a_bytes + g_bytes));
+        const int t = t_beg + kb;
+        if (p.conv) {
+          const int per_img = p.tiles_x * p.tiles_y;
+          const int img = t / per_img, rem = t - img * per_img, ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+          const int x0 = tx * p.BX, y0 = ty * p.BY;
+          for (int g = 0; g < 4; ++g) tma_load_4d(sa + g * kWgGroupBytes, &tmA, full_bar(s), c0 + 32 * g, x0 + dx, y0 + dy, img);
+          for (int g = 0; g < p.NG; ++g) tma_load_4d(sg + g * kWgGroupBytes, &tmG, full_bar(s), 32 * g, x0, y0, img);
+        } else {
+          const int m0 = t * 32;
+          for (int g = 0; g < 4; ++g) tma_load_2d(sa + g * kWgGroupBytes, &tmA, full_bar(s), c0 + 32 * g, m0);
+          for (int g = 0; g < p.NG; ++g) tma_load_2d(sg + g * kWgGroupBytes, &tmG, full_bar(s), 32 * g, m0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // TF32, fp32 accumulate, BOTH operands MN-major (bits 15 and 16)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % p.stages;
+        mbar_wait(ready_bar(s), (kb / p.stages) & 1);
+        tc_fence_after();
+        const uint32_t sa = base + (uint32_t)s * stage_bytes;
+        const uint64_t da = make_mnmajor_sw128_desc(sa), dal = make_mnmajor_sw128_desc(sa + a_lo);
+        const uint64_t dg = make_mnmajor_sw128_desc(sa + g_off), dgl = make_mnmajor_sw128_desc(sa + g_lo);
+        for (int k = 0; k < 4; ++k) {            // 4 atoms of 8 pixel rows: +1024 B each
+          const uint64_t adv = (uint64_t)(64 * k);
+          tc_mma_tf32(tmem_acc, da + adv, dg + adv, idesc, (kb | k) ? 1u : 0u);
+          if (x3) {
+            tc_mma_tf32(tmem_acc, dal + adv, dg + adv, idesc, 1u);
+            tc_mma_tf32(tmem_acc, da + adv, dgl + adv, idesc, 1u);
+          }
+        }
+        tc_commit(empty_bar(s));
+      }
+      tc_commit(tmem_full_bar);
+    }
+  } else {
+    const int t = threadIdx.x - 64;
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % p.stages;
+      mbar_wait(full_bar(s), (kb / p.stages) & 1);
+      uint8_t* st = smem + (size_t)s * stage_bytes;
+      float4* a_hi = reinterpret_cast<float4*>(st);
+      float4* a_lop = reinterpret_cast<float4*>(st + a_lo);
+      const int m0 = (t_beg + kb) * 32;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {            // A: 4 groups x 256 float4
+        const int i = t + 128 * j;
+        float4 v = a_hi[i];
+        if (p.pa) {
+          const int g = i >> 8, idx = i & 255, row = idx >> 3;
+          const int k = c0 + 32 * g + (((idx & 7) ^ (row & 7)) << 2);
+          if (k < p.C) {
+            v = swish4(affine4(v, ld4(p.pa + k), ld4(p.pb + k)));
+            if (p.gate) {
+              const int m = m0 + row;
+              const int im = m < p.M ? m / p.HW : 0;
+              v = v * ld4(p.gate + (size_t)im * p.C + k);
+            }
+          }
+        }
+        const float4 h = f4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w));
+        a_hi[i] = h;
+        if (x3) a_lop[i] = f4(rn_tf32(v.x - h.x), rn_tf32(v.y - h.y), rn_tf32(v.z - h.z), rn_tf32(v.w - h.w));
+      }
+      float4* g_hi = reinterpret_cast<float4*>(st + g_off);
+      float4* g_lop = reinterpret_cast<float4*>(st + g_lo);
+      const int ng4 = p.NG * 256;
+      for (int i = t; i < ng4; i += 128) {
+        const float4 v = g_hi[i];
+        const float4 h = f4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w));
+        g_hi[i] = h;
+        if (x3) g_lop[i] = f4(rn_tf32(v.x - h.x), rn_tf32(v.y - h.y), rn_tf32(v.z - h.z), rn_tf32(v.w - h.w));
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(ready_bar(s));
+    }
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int c = c0 + r;
+    float* orow = partial + (((size_t)split * p.taps + tap) * p.C + c) * p.N;
+    if (KB > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t tbase = tmem_acc + ((uint32_t)(quarter * 32) << 16);
+    for (int cc = 0; cc < p.BN; cc += 16) {
+      uint32_t v[16];
+      __syncwarp();
+      if (KB > 0) tc_ld16(tbase + (uint32_t)cc, v);
+      else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = 0u;
+      }
+      if (c < p.C) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int n = cc + q * 4;
+          if (n < p.N)
+            st4(orow + n, f4(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
+                             __uint_as_float(v[q * 4 + 3])));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(ncols) : "memory");
+  }
+}
+
+static int wg_splits(int ctiles, int taps, int tiles_total) {
+  int base = ctiles * taps;
+  int S = 296 / base;
+  if (S < 1) S = 1;
+  if (S > tiles_total / 2) S = tiles_total / 2;   // at least 2 pixel tiles (64 pixels) per CTA
+  if (S > 148) S = 148;
+  if (S < 1) S = 1;
+  return S;
+}
+
+bool tc_wgrad_supported(int conv, int W, int C, int N) {
+  if (C % 4 || N % 4 || N > 256) return false;
+  if (conv && (W < 1)) return false;
+  return encode_fn() != nullptr;
+}
+size_t tc_wgrad_scratch(int conv, int M, int B, int H, int W, int C, int N, int taps) {
+  int tiles;
+  if (conv) { int BX = W > 16 ? 32 : 16, BY = 32 / BX; tiles = B * ((W + BX - 1) / BX) * ((H + BY - 1) / BY); }
+  else tiles = (M + 31) / 32;
+  int S = wg_splits((C + 127) / 128, taps, tiles);
+  return (size_t)S * taps * C * N;
+}
+
+// dW[taps*C, N] = sum A^T G ; scratch holds the per-split partials (tc_wgrad_scratch floats)
+bool tc_wgrad(const float* A, int lda, const float* G, int ldg, float* dW, float* scratch, int conv, int M, int B, int H,
+              int W, int C, int taps, int dil, int N, int split, cudaStream_t s, const float* pa, const float* pb,
+              const float* gate, int HW) {
+  TcWgParams p{};
+  p.conv = conv; p.M = M; p.H = H; p.W = W; p.C = C; p.N = N; p.taps = taps; p.dil = dil;
+  p.split = split == 3 ? 3 : 1;
+  if (pa && conv) return false;
+  p.pa = pa; p.pb = pb; p.gate = gate; p.HW = HW > 0 ? HW : 1;
+  p.BN = (N + 15) / 16 * 16;
+  p.NG = (p.BN + 31) / 32;
+  CUtensorMap tmA, tmG;
+  if (conv) {
+    p.BX = W > 16 ? 32 : 16;
+    p.BY = 32 / p.BX;
+    p.tiles_x = (W + p.BX - 1) / p.BX;
+    p.tiles_y = (H + p.BY - 1) / p.BY;
+    p.tiles_total = B * p.tiles_x * p.tiles_y;
+    cuuint32_t box[4] = {32, (cuuint32_t)p.BX, (cuuint32_t)p.BY, 1};
+    cuuint64_t dA[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t sA[3] = {(cuuint64_t)lda * 4, (cuuint64_t)W * lda * 4, (cuuint64_t)H * W * lda * 4};
+    if (!encode(&tmA, A, 4, dA, sA, box)) return false;
+    cuuint64_t dG[4] = {(cuuint64_t)N, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t sG[3] = {(cuuint64_t)ldg * 4, (cuuint64_t)W * ldg * 4, (cuuint64_t)H * W * ldg * 4};
+    if (!encode(&tmG, G, 4, dG, sG, box)) return false;
+  } else {
+    p.tiles_total = (M + 31) / 32;
+    cuuint32_t box[2] = {32, 32};
+    cuuint64_t dA[2] = {(cuuint64_t)C, (cuuint64_t)M};
+    cuuint64_t sA[1] = {(cuuint64_t)lda * 4};
+    if (!encode(&tmA, A, 2, dA, sA, box)) return false;
+    cuuint64_t dG[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    cuuint64_t sG[1] = {(cuuint64_t)ldg * 4};
+    if (!encode(&tmG, G, 2, dG, sG, box)) return false;
+  }
+  const int ctiles = (C + 127) / 128;
+  p.splits = wg_splits(ctiles, taps, p.tiles_total);
+  const int stage_bytes = (p.split == 3 ? 2 : 1) * (4 + p.NG) * kWgGroupBytes;
+  p.stages = (200 * 1024) / stage_bytes;
+  if (p.stages > 6) p.stages = 6;
+  const int per = (p.tiles_total + p.splits - 1) / p.splits;
+  if (p.stages > per) p.stages = per;
+  if (p.stages < 1) return false;
+  const size_t smem = (size_t)p.stages * stage_bytes + (3 * p.stages + 2) * 8 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr = true;
+  }
+  dim3 grid(ctiles, taps, p.splits);
+  MLIIS_COUNT(), tc_wgrad_kernel<<<grid, kTcThreads, smem, s>>>(tmA, tmG, scratch, p);
+  reduce_partials(scratch, p.splits, taps * C * N, dW, s);
+  return true;
+}
+
 // weights W[tap][ci][co] (HWIO) -> forward operand Wt[co][tap][ci]   or   dgrad operand Wt[ci][taps-1-tap][co],
 // rounded to nearest TF32; split == 3 also writes the residual plane lo = rn(w - hi) behind the hi plane.
 __global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ wt, int taps, int Ci, int Co,

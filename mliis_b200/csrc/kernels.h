@@ -124,6 +124,13 @@ bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float*
 // split == 3 appends the residual plane (wt must hold 2 * taps*Ci*Co floats)
 void tc_prep_weights(const float* w, float* wt, int taps, int Ci, int Co, int dgrad, int split, cudaStream_t s);
 
+// wgrad on tensor cores: dW[taps*C, N] = sum_pixels A[pixel+tap, c] * G[pixel, n]  (A, G channel-contiguous)
+bool tc_wgrad_supported(int conv, int W, int C, int N);
+size_t tc_wgrad_scratch(int conv, int M, int B, int H, int W, int C, int N, int taps);
+bool tc_wgrad(const float* A, int lda, const float* G, int ldg, float* dW, float* scratch, int conv, int M, int B, int H,
+              int W, int C, int taps, int dil, int N, int split, cudaStream_t s, const float* pa = nullptr,
+              const float* pb = nullptr, const float* gate = nullptr, int HW = 0);
+
 // ---------------- misc (k_misc.cu) ----------------
 struct ResizeTab { const int32_t* lo; const int32_t* hi; const float* lerp;   // [n_out]
                    const int32_t* g_lo; const int32_t* g_hi; };                // [n_in] gather ranges (bwd)

@@ -265,9 +265,11 @@ void Plan::build(int image_size_, int max_batch, const int* rsd, float final_dro
     upd(max_partials, (int64_t)dw_wgrad_blocks(B, bp.Hout, bp.Wout, bp.stride) * bp.k * bp.k * bp.ce);
     if (bp.expand) {
       upd(max_tn, (int64_t)gemm_tn_scratch(B * HWi, bp.cin, bp.ce, 0));
+      upd(max_tn, (int64_t)tc_wgrad_scratch(0, B * HWi, B, bp.Hin, bp.Win, bp.ce, bp.cin, 1));   // swapped roles
       upd(max_wT, (int64_t)bp.cin * bp.ce);
     }
     upd(max_tn, (int64_t)gemm_tn_scratch(B * HWo, bp.ce, bp.cout, 0));
+    upd(max_tn, (int64_t)tc_wgrad_scratch(0, B * HWo, B, bp.Hout, bp.Wout, bp.ce, bp.cout, 1));
     upd(max_wT, (int64_t)bp.ce * bp.cout);
   }
   int64_t maxDec = 0, maxPyr = 0, maxCat = 0, maxSkip = 0, maxDeep = 0;
@@ -298,6 +300,9 @@ void Plan::build(int image_size_, int max_batch, const int* rsd, float final_dro
     upd(max_tn, (int64_t)gemm_tn_scratch(B * HW, rp.catC, D, 0));
     upd(max_tn, (int64_t)gemm_tn_scratch(B * HW, 9 * rp.catC, D, 1));
     upd(max_tn, (int64_t)gemm_tn_scratch(B * HW, 9 * rp.pyrC, D, 1));
+    upd(max_tn, (int64_t)tc_wgrad_scratch(0, B * HW, B, rp.h, rp.w, rp.catC, D, 1));
+    upd(max_tn, (int64_t)tc_wgrad_scratch(1, B * HW, B, rp.h, rp.w, rp.catC, D, 9));
+    upd(max_tn, (int64_t)tc_wgrad_scratch(1, B * HW, B, rp.h, rp.w, rp.pyrC, D, 9));
     upd(max_wT, (int64_t)9 * rp.pyrC * D);
     // the decoder's gradient wrt a backbone block output
     BlockPlan& sb = blocks[rp.skip_block];

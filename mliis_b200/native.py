@@ -84,6 +84,7 @@ SYMBOLS = [
     ("mliis_conv3x3_fwd", C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     ("mliis_tc_prep_weights", C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
     ("mliis_tc_conv", C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
+    ("mliis_tc_wgrad", C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     ("mliis_bilinear_fwd", C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     ("mliis_adam_step", C.c_int, [_VP, _VP, _VP, _I64, _I64, _F, _F, _F, _VP]),
     ("mliis_debug_buffer", C.c_int, [_VP, _I32, C.c_char_p, C.POINTER(_VP), C.POINTER(_I64), C.POINTER(_I32),

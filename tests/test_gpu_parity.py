@@ -358,6 +358,27 @@ def test_tc_conv3x3(H, Cin, Cout, dil, B):
     assert rel_err(y, ref) < 1e-4      # fp32 accumulation over 3*9*Cin terms in the tensor-core adder
 
 
+@pytest.mark.parametrize("H,Cin,Cout,taps,dil,B", [(56, 136, 112, 9, 2, 2), (56, 360, 112, 9, 1, 1), (14, 224, 112, 9, 2, 3),
+                                                   (14, 448, 112, 9, 1, 2), (56, 136, 112, 1, 1, 2), (28, 240, 40, 1, 1, 2),
+                                                   (112, 96, 16, 1, 1, 1), (14, 672, 112, 1, 1, 8), (20, 40, 16, 9, 1, 2)])
+def test_tc_wgrad(H, Cin, Cout, taps, dil, B):
+    from mliis_b200 import native as N
+    g = torch.Generator().manual_seed(H + Cin + Cout + taps)
+    a = torch.randn(B, H, H, Cin, generator=g)
+    gr = torch.randn(B, H, H, Cout, generator=g)
+    ad, gd = _dev(a), _dev(gr)
+    # reference: autograd of the SAME-padded conv w.r.t. the weights
+    w = torch.zeros(3 if taps == 9 else 1, 3 if taps == 9 else 1, Cin, Cout, dtype=torch.float64, requires_grad=True)
+    y = conv2d_same(a.double().permute(0, 3, 1, 2), w, dilation=dil)
+    (ref,) = torch.autograd.grad(y, w, gr.double().permute(0, 3, 1, 2))
+    ref = ref.reshape(taps * Cin, Cout)
+    for mode, tol in ((2, 1e-4), (1, 5e-3)):
+        dw = torch.full((taps * Cin, Cout), float("nan"), device="cuda")
+        N.check(N.lib().mliis_tc_wgrad(ad.data_ptr(), gd.data_ptr(), dw.data_ptr(), B, H, H, Cin, Cout, taps, dil, mode, None))
+        torch.cuda.synchronize()
+        assert rel_err(dw, ref) < tol, (mode, rel_err(dw, ref))
+
+
 def _tf32_network_errors(size, B, steps, mode, warm=0):
     from mliis_b200 import native as N
     arch, theta, bn, images, labels = make_problem(size, 10)
