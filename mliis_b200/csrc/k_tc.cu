@@ -332,12 +332,12 @@ static EncodeTiledFn encode_fn() {
 }
 
 static bool encode(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                   const cuuint32_t* box) {
+                   const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -413,10 +413,10 @@ bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float*
 // wgrad on tensor cores:  dW[tap][c][n] = sum_pixels A[pixel + offset(tap), c] * G[pixel, n]
 //
 // The reduction (MMA K) dimension is the pixel index, so both operands are "MN-major": channels are contiguous
-// in memory.  One TMA box {32 channels, 32 pixels} lands as a [32 pixel rows][128 B] 128-byte-swizzled slab, which is
-// exactly the canonical MN-major SWIZZLE_128B atom stack (8 pixel rows x 128 B per atom, SBO = 1024 B between
-// atoms along K, LBO = 4096 B between 32-channel groups along M/N).  One tcgen05.mma (K = 8) consumes one atom
-// per channel group.  grid = (128-channel tiles of A, taps, pixel-range splits); each CTA writes its fp32 partial
+// in memory.  One TMA box {32 channels, 32 pixels} (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) lands as a
+// [32 pixel rows][128 B] slab = the canonical MN-major SWIZZLE_128B_BASE32B atom stack, the only shared-memory layout
+// tcgen05 accepts for MN-major TF32 operands (4 pixel rows x 128 B per atom, SBO = 512 B between atoms along K,
+// LBO = 4096 B between 32-channel groups along M/N).  One tcgen05.mma (K = 8) consumes two atoms per channel group.  grid = (128-channel tiles of A, taps, pixel-range splits); each CTA writes its fp32 partial
 // [128 x N] and the partials are reduced in a fixed order by reduce_partials (deterministic, no atomics).
 // =================================================================================================
 struct TcWgParams {
@@ -431,9 +431,11 @@ struct TcWgParams {
 };
 
 __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
-  //  LBO (bits 16..29) = 4096 B >> 4 : stride between 32-element groups along M/N
-  //  SBO (bits 32..45) = 1024 B >> 4 : stride between 8-row atoms along K
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (256ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+  // MN-major TF32 operands only exist in the SWIZZLE_128B_BASE32B layout (layout type 1): rows of 128 B (32 channels)
+  // whose four 32-byte chunks are XOR-swizzled with (pixel row & 3); atom = 4 pixel rows (512 B).
+  //  LBO (bits 16..29) = 4096 B >> 4 : stride between 32-channel groups along M/N
+  //  SBO (bits 32..45) =  512 B >> 4 : stride between 4-row atoms along K
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (256ull << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
 }
 
 constexpr int kWgGroupBytes = 32 * 128;   // one TMA box: 32 pixel rows x 32 channels fp32
@@ -544,8 +546,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int i = t + 128 * j;
         float4 v = a_hi[i];
         if (p.pa) {
-          const int g = i >> 8, idx = i & 255, row = idx >> 3;
-          const int k = c0 + 32 * g + (((idx & 7) ^ (row & 7)) << 2);
+          // SWIZZLE_128B_ATOM_32B: logical 32-byte chunk = physical chunk XOR (row & 3)
+          const int g = i >> 8, idx = i & 255, row = idx >> 3, f4i = idx & 7;
+          const int k = c0 + 32 * g + ((((((f4i >> 1) ^ (row & 3)) << 1) | (f4i & 1))) << 2);
           if (k < p.C) {
             v = swish4(affine4(v, ld4(p.pa + k), ld4(p.pb + k)));
             if (p.gate) {
@@ -651,19 +654,19 @@ bool tc_wgrad(const float* A, int lda, const float* G, int ldg, float* dW, float
     cuuint32_t box[4] = {32, (cuuint32_t)p.BX, (cuuint32_t)p.BY, 1};
     cuuint64_t dA[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t sA[3] = {(cuuint64_t)lda * 4, (cuuint64_t)W * lda * 4, (cuuint64_t)H * W * lda * 4};
-    if (!encode(&tmA, A, 4, dA, sA, box)) return false;
+    if (!encode(&tmA, A, 4, dA, sA, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return false;
     cuuint64_t dG[4] = {(cuuint64_t)N, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t sG[3] = {(cuuint64_t)ldg * 4, (cuuint64_t)W * ldg * 4, (cuuint64_t)H * W * ldg * 4};
-    if (!encode(&tmG, G, 4, dG, sG, box)) return false;
+    if (!encode(&tmG, G, 4, dG, sG, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return false;
   } else {
     p.tiles_total = (M + 31) / 32;
     cuuint32_t box[2] = {32, 32};
     cuuint64_t dA[2] = {(cuuint64_t)C, (cuuint64_t)M};
     cuuint64_t sA[1] = {(cuuint64_t)lda * 4};
-    if (!encode(&tmA, A, 2, dA, sA, box)) return false;
+    if (!encode(&tmA, A, 2, dA, sA, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return false;
     cuuint64_t dG[2] = {(cuuint64_t)N, (cuuint64_t)M};
     cuuint64_t sG[1] = {(cuuint64_t)ldg * 4};
-    if (!encode(&tmG, G, 2, dG, sG, box)) return false;
+    if (!encode(&tmG, G, 2, dG, sG, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return false;
   }
   const int ctiles = (C + 127) / 128;
   p.splits = wg_splits(ctiles, taps, p.tiles_total);
