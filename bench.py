@@ -29,6 +29,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# one hardware work queue per task slot (the default of 8 would alias slots onto shared queues); must be set
+# before the CUDA context exists
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 N_SHOTS, N_QUERY, INNER_BATCH, INNER_STEPS, LR, IMAGE_SIZE, POOL = 5, 5, 8, 5, 1e-3, 224, 10
 FWD_GFLOP_PER_IMAGE = 3.994937

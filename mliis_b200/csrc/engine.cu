@@ -839,11 +839,20 @@ int mliis_meta_apply(mliis_ctx* ctx, float* theta, const float* dsum, float scal
 
 // ---- per-kernel entry points ----
 static int require_sm100() {
+  // cudaGetDeviceProperties costs milliseconds: query the one attribute and cache it per device
+  static int cached_major[64];
+  static bool cached[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(MLIIS_ERR_DEVICE, "no CUDA device (no CPU fallback exists)");
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10)
-    return fail(MLIIS_ERR_DEVICE, "not an sm_100 device (no fallback)");
+  if (dev < 0 || dev >= 64) return fail(MLIIS_ERR_DEVICE, "bad device ordinal");
+  if (!cached[dev]) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+      return fail(MLIIS_ERR_DEVICE, "cannot query the device (no CPU fallback exists)");
+    cached_major[dev] = major;
+    cached[dev] = true;
+  }
+  if (cached_major[dev] != 10) return fail(MLIIS_ERR_DEVICE, "not an sm_100 device (no fallback)");
   return MLIIS_OK;
 }
 
