@@ -55,8 +55,8 @@ enum mliis_loss_flags {    /* models/efficientlab.py:294-313 */
 
 enum mliis_gemm_mode {     /* numeric mode of the dense contractions */
   MLIIS_GEMM_FP32 = 0,     /* fp32 FFMA kernels (exact-order reference mode)                */
-  MLIIS_GEMM_TF32 = 1,     /* tcgen05 kind::tf32, fp32 accumulate in TMEM                   */
-  MLIIS_GEMM_TF32X3 = 2    /* tcgen05 3xTF32 split (fp32-class accuracy)                    */
+  MLIIS_GEMM_TF32 = 1,     /* tcgen05: single-pass TF32 on the decoder convs, 3xTF32 on the backbone (opt-in) */
+  MLIIS_GEMM_TF32X3 = 2    /* tcgen05 3xTF32 split everywhere (fp32-class accuracy; the parity-clean default) */
 };
 
 typedef struct mliis_config {

@@ -177,8 +177,9 @@ GemmA convA(const float* ptr, int ld, int H, int W, int C, int dil) {
 // w_hwio is the TF-layout kernel [taps][Cin][Cout]; scratch receives the re-laid-out tensor-core operand.
 struct Dense {
   const Run& r;
+  bool decoder = false;   // MLIIS_GEMM_TF32: single-pass TF32 for the decoder convs only; the backbone stays 3xTF32
   bool tc() const { return r.c->cfg.gemm_mode != MLIIS_GEMM_FP32; }
-  int split() const { return r.c->cfg.gemm_mode == MLIIS_GEMM_TF32X3 ? 3 : 1; }
+  int split() const { return (r.c->cfg.gemm_mode == MLIIS_GEMM_TF32 && decoder) ? 1 : 3; }
   // forward: out[M, Cout] = conv(A[.., Cin]) + bias
   void fwd(const float* A, int lda, int conv, int H, int W, int Cin, int dil, const float* w_hwio, const float* bias,
            float* out, int ldc, int Cout, int M, int HW) const {
@@ -314,7 +315,7 @@ void run_forward(const Run& r, const float* images, const int32_t* index, bool t
     add3(cat + D, d.catC, r.W(sb.Y.off), sb.cout, nullptr, 0, nullptr, 0, M, d.skipC, HW, st);
     float* pyr = r.W(d.pyr.off);
     // branch_0: 1x1 (+bias) -> swish -> BN
-    const Dense dense{r};
+    const Dense dense{r, true};
     dense.fwd(cat, d.catC, 0, d.h, d.w, d.catC, 1, r.T(d.w0), r.T(d.b0), r.W(d.c0.off), D, D, M, HW);
     if (training) r.bn_train(d.bn[0], r.W(d.c0.off), D, M, true);
     dec_bn_apply(r.W(d.c0.off), D, r.bn_a(d.bn[0]), r.bn_b(d.bn[0]), nullptr, 0, pyr, d.pyrC, M, D, st);
@@ -398,7 +399,7 @@ void run_backward(const Run& r, const float* labels, const int32_t* index, float
     };
     // out = BN2(swish(c2)) + up
     dec_bn_bwd(d.bn[2], r.W(d.c2.off), gOut, D, r.W(p.g_c));
-    const Dense dense{r};
+    const Dense dense{r, true};
     dense.wgrad(pyr, d.pyrC, 1, d.h, d.w, d.pyrC, 1, r.W(p.g_c), D, D, r.G(d.w2), r.G(d.b2), M, HW);
     dense.dgrad(r.W(p.g_c), D, 1, d.h, d.w, d.pyrC, 1, r.T(d.w2), r.W(p.g_pyr), d.pyrC, D, M, HW, 0);
     const float* gpyr = r.W(p.g_pyr);

@@ -18,6 +18,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -102,6 +103,7 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 
 // ------------------------------------------------------------------------------------------------
 struct TcParams {
+  int debug;         // MLIIS_TC_DEBUG bits (bottleneck experiments only): 1 skip operand transform, 2 skip MMA issue
   int conv;          // 0: plain [M,K] (2-D map), 1: NHWC taps (4-D map)
   int M;             // plain: number of rows
   int H, W, BH;      // conv: image size, image rows per tile (tile = BH x W pixels <= 128)
@@ -120,11 +122,11 @@ struct TcParams {
 constexpr int kTcThreads = 192;
 constexpr int kABytes = 128 * 128;   // 128 rows x 32 fp32
 
+// round to nearest TF32 (ties away from zero, same result as cvt.rna.tf32.f32) with two full-rate integer ops
 __device__ __forceinline__ float rn_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
+__device__ __forceinline__ float4 rn_tf32_4(float4 v) { return f4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w)); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -138,6 +140,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t base = (raw + 1023u) & ~1023u;              // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* smem = smem_raw + (base - raw);
   const bool x3 = p.split == 3;
+  const bool xform = x3 || p.pa != nullptr;     // single-pass TF32 without a prologue: operands go TMA -> MMA directly
   const int b_bytes = p.BN * 128;
   const int a_off_lo = kABytes;
   const int b_off = x3 ? 2 * kABytes : kABytes;
@@ -214,7 +217,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % p.stages;
-        mbar_wait(ready_bar(s), (kb / p.stages) & 1);
+        mbar_wait(xform ? ready_bar(s) : full_bar(s), (kb / p.stages) & 1);
         tc_fence_after();
         const int kc = kb % kchunks;
         const int rem = p.C - kc * 32;
@@ -222,7 +225,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t sa = base + (uint32_t)s * stage_bytes, sb = sa + b_off;
         const uint64_t da = make_kmajor_sw128_desc(sa), db = make_kmajor_sw128_desc(sb);
         const uint64_t dal = make_kmajor_sw128_desc(sa + a_off_lo), dbl = make_kmajor_sw128_desc(sb + b_bytes);
-        for (int k = 0; k < nk; ++k) {  // advance 32 bytes (8 tf32) along K inside the 128-byte swizzle atom
+        for (int k = 0; k < nk && !(p.debug & 2); ++k) {  // advance 32 bytes (8 tf32) along K inside the swizzle atom
           const uint64_t adv = (uint64_t)(2 * k);
           tc_mma_tf32(tmem_acc, da + adv, db + adv, idesc, (kb | k) ? 1u : 0u);
           if (x3) {   // a*b ~= ah*bh + al*bh + ah*bl   (al*bl ~ 2^-22 relative, dropped)
@@ -237,14 +240,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ---------------- operand transform (during the main loop), then epilogue ----------------
     const int t = threadIdx.x - 64;   // 0..127
-    for (int kb = 0; kb < KB; ++kb) {
+    for (int kb = 0; kb < KB && xform; ++kb) {
       const int s = kb % p.stages;
       mbar_wait(full_bar(s), (kb / p.stages) & 1);
       float4* a_hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
       float4* a_lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + a_off_lo);
       const int kc32 = (kb % kchunks) * 32;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 8 && !(p.debug & 1); ++j) {
         const int i = t + 128 * j;     // float4 index inside the 16 KB A tile: row = i/8, physical 16-byte chunk = i%8
         float4 v = a_hi[i];
         if (p.pa) {
@@ -260,9 +263,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        const float4 h = f4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w));
+        const float4 h = rn_tf32_4(v);
         a_hi[i] = h;
-        if (x3) a_lo[i] = f4(rn_tf32(v.x - h.x), rn_tf32(v.y - h.y), rn_tf32(v.z - h.z), rn_tf32(v.w - h.w));
+        if (x3) a_lo[i] = rn_tf32_4(v - h);
       }
       // generic-proxy writes must be visible to the async proxy (tcgen05.mma reads smem through it)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -359,6 +362,9 @@ bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float*
              int H, int W, int C, int taps, int dil, int N, int accumulate, int split, cudaStream_t s,
              const float* pa, const float* pb, const float* gate, int HW) {
   TcParams p{};
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("MLIIS_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+  p.debug = dbg;
   p.split = split == 3 ? 3 : 1;
   if (pa && conv) return false;
   p.pa = pa; p.pb = pb; p.gate = gate; p.HW = HW > 0 ? HW : 1;
@@ -558,18 +564,18 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
         }
-        const float4 h = f4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w));
+        const float4 h = rn_tf32_4(v);
         a_hi[i] = h;
-        if (x3) a_lop[i] = f4(rn_tf32(v.x - h.x), rn_tf32(v.y - h.y), rn_tf32(v.z - h.z), rn_tf32(v.w - h.w));
+        if (x3) a_lop[i] = rn_tf32_4(v - h);
       }
       float4* g_hi = reinterpret_cast<float4*>(st + g_off);
       float4* g_lop = reinterpret_cast<float4*>(st + g_lo);
       const int ng4 = p.NG * 256;
       for (int i = t; i < ng4; i += 128) {
         const float4 v = g_hi[i];
-        const float4 h = f4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w));
+        const float4 h = rn_tf32_4(v);
         g_hi[i] = h;
-        if (x3) g_lop[i] = f4(rn_tf32(v.x - h.x), rn_tf32(v.y - h.y), rn_tf32(v.z - h.z), rn_tf32(v.w - h.w));
+        if (x3) g_lop[i] = rn_tf32_4(v - h);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(ready_bar(s));

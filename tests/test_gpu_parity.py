@@ -307,10 +307,15 @@ def test_full_size_one_step():
 # ------------------------------------------------------------------------------------------------
 # tcgen05 / TMA / TMEM path (kind::tf32): the hardware reads the top 19 bits of every fp32 operand
 # ------------------------------------------------------------------------------------------------
-def _tf32_trunc(x):
-    """What kind::tf32 consumes after the kernel's operand transform: cvt.rna.tf32.f32 (round to nearest, ties away
-    from zero; the hardware then ignores the 13 low mantissa bits, which are zero)."""
+def _tf32_rn(x):
+    """Round to nearest TF32, ties away from zero (what tc_prep_weights / the transform warps produce)."""
     return ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def _tf32_trunc(x):
+    """What tcgen05.mma kind::tf32 does to a raw fp32 operand: the 13 low mantissa bits are ignored.  Single-pass
+    mode feeds activations straight from TMA to the MMA (no transform stage); weights are pre-rounded (RN)."""
+    return (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
 
 
 @pytest.mark.parametrize("M,K,N_", [(1568, 224, 112), (25088, 136, 112), (300, 112, 360), (128, 32, 16), (77, 8, 24)])
@@ -319,7 +324,7 @@ def test_tc_gemm_nn(M, K, N_):
     g = torch.Generator().manual_seed(M + K)
     a = torch.randn(M, K, generator=g)
     w = torch.randn(K, N_, generator=g)
-    ref_t = _tf32_trunc(a).double() @ _tf32_trunc(w).double()
+    ref_t = _tf32_trunc(a).double() @ _tf32_rn(w).double()
     ref = a.double() @ w.double()
     ad, wd = _dev(a), _dev(w)
     c = torch.full((M, N_), float("nan"), device="cuda")
@@ -342,7 +347,7 @@ def test_tc_conv3x3(H, Cin, Cout, dil, B):
     x = torch.randn(B, H, H, Cin, generator=g)
     w = torch.randn(3, 3, Cin, Cout, generator=g) * 0.05
     bias = torch.randn(Cout, generator=g)
-    ref_t = conv2d_same(_tf32_trunc(x).double().permute(0, 3, 1, 2), _tf32_trunc(w).double(), dilation=dil,
+    ref_t = conv2d_same(_tf32_trunc(x).double().permute(0, 3, 1, 2), _tf32_rn(w).double(), dilation=dil,
                         bias=bias.double()).permute(0, 2, 3, 1)
     xd, wd, bd = _dev(x), _dev(w), _dev(bias)
     y = torch.full((B, H, H, Cout), float("nan"), device="cuda")
@@ -443,9 +448,10 @@ def test_tensor_core_modes_within_north_star_tolerances(size, B, mode, warm):
         assert abs(e["miou_engine"] - e["miou_oracle"]) < 0.005     # per-task mIoU within 0.5 points
         assert e["logits"] < 1e-2        # logits max-abs
     else:
-        # single-pass TF32 everywhere is NOT parity-clean (logits ~0.3-0.4, weights up to ~1.3e-3): it is kept as an
-        # opt-in speed mode and only sanity-bounded here; the shipped default is 3xTF32
-        assert e["theta"] < 5e-3 and e["grad"] < 5e-2
+        # MLIIS_GEMM_TF32 = single-pass TF32 on the decoder convs (3xTF32 on the backbone): meets the weight / mIoU
+        # bounds; its same-weights logits error (0.03-0.05 at |z|max ~ 37) is above the literal 1e-2 bound, which is
+        # why it is opt-in and 3xTF32 is the default
+        assert e["theta"] < 1e-3 and e["grad"] < 1e-3 and e["logits"] < 0.1
 
 
 def test_adaptation_from_pretrained_state_all_modes():
@@ -519,9 +525,6 @@ def test_adaptation_from_pretrained_state_all_modes():
     # 1e-2 logits bound is asserted on same-weights forwards (test_forward_layers, test_predict_mask_and_iou_counts,
     # test_tensor_core_modes_*), here the north-star bounds on adapted weights and per-task mIoU are asserted.
     for mode, e_theta, e_logits, iou in rows:
-        if mode == N.GEMM_TF32:            # opt-in speed mode: reported, sanity-bounded only
-            assert e_theta < 5e-3 and abs(iou - iou_ref) < 0.02, (mode, e_theta, iou)
-            continue
         assert e_theta < 1e-3, (mode, e_theta)
         assert abs(iou - iou_ref) < 0.005, (mode, iou, iou_ref)
         assert e_logits < 0.5, (mode, e_logits)
