@@ -314,6 +314,187 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// =================================================================================================
+// 3x3 (dilated) implicit GEMM, second generation.  Measured limiter of tc_conv_kernel on the big decoder convs: the
+// per-SM TMA engine (~one 128-byte row per ~5 clk), not the tensor pipe.  So this kernel moves fewer rows per MMA:
+//  * ONE halo'd A box {32 ch, W+2d, MT*BH rows} per (filter row dy, K chunk) serves the three horizontal taps: tap dx
+//    reads the same shared-memory slab through a descriptor whose start address is shifted by dx*d rows (128 B each;
+//    the SWIZZLE_128B phase of the shifted start goes into the descriptor's base_offset field);
+//  * MT = 2 pixel tiles per CTA share every weight tile (two TMEM accumulators);
+//  * A and B live in separate rings (A: 2-3 slots of 32 KB, B: up to 8 slots), so the pipeline is deeper.
+// Tile rows are r = ly*(W+2d) + lx; rows with lx >= W are halo pixels whose outputs are discarded.
+// =================================================================================================
+struct TcC3Params {
+  int H, W, RW, BH, MT, tiles_per_image, groups_per_image;
+  int C, dil, N, BN, ldc, accumulate;
+  int SA, SB, split, ncol_acc;
+  int a_box_bytes, a_slot_bytes, b_plane_bytes;
+};
+
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc_off(uint32_t smem_addr) {
+  // start address not 1024-byte aligned: base_offset (bits 49..51) = (address >> 7) & 7
+  return make_kmajor_sw128_desc(smem_addr) | ((uint64_t)((smem_addr >> 7) & 7) << 49);
+}
+
+__global__ void __launch_bounds__(kTcThreads)
+tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const float* __restrict__ bias, float* __restrict__ out, const TcC3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const bool x3 = p.split == 3;
+  const int a_stage = (x3 ? 2 : 1) * p.a_slot_bytes;          // [hi][lo]
+  const int b_stage = (x3 ? 2 : 1) * p.b_plane_bytes;         // [hi][lo]
+  const uint32_t a_base = base, b_base = base + (uint32_t)p.SA * a_stage;
+  const uint32_t bar0 = b_base + (uint32_t)p.SB * b_stage;
+  uint8_t* bars_ptr = smem + (size_t)p.SA * a_stage + (size_t)p.SB * b_stage;
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_ready = [&](int s) { return bar0 + 8u * (p.SA + s); };
+  auto a_empty = [&](int s) { return bar0 + 8u * (2 * p.SA + s); };
+  auto b_full = [&](int s) { return bar0 + 8u * (3 * p.SA + s); };
+  auto b_empty = [&](int s) { return bar0 + 8u * (3 * p.SA + p.SB + s); };
+  const uint32_t tmem_full_bar = bar0 + 8u * (3 * p.SA + 2 * p.SB);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_ptr + 8 * (3 * p.SA + 2 * p.SB + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ncols = (uint32_t)(p.ncol_acc * p.MT);
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < p.SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_ready(s), 128); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.SB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  const int img = blockIdx.x / p.groups_per_image;
+  const int y0 = (blockIdx.x - img * p.groups_per_image) * p.MT * p.BH;
+  const int n0 = blockIdx.y * p.BN;
+  const int KC = (p.C + 31) / 32;
+  const int NA = 3 * KC;                 // A stages: (dy, kc)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int ib = 0;
+      for (int ia = 0; ia < NA; ++ia) {
+        const int dy = ia / KC, kc = ia - dy * KC;
+        const int sa = ia % p.SA;
+        mbar_wait(a_empty(sa), ((ia / p.SA) & 1) ^ 1);
+        mbar_expect_tx(a_full(sa), (uint32_t)p.a_box_bytes);
+        tma_load_4d(a_base + (uint32_t)sa * a_stage, &tmA, a_full(sa), kc * 32, -p.dil, y0 + (dy - 1) * p.dil, img);
+        for (int dx = 0; dx < 3; ++dx, ++ib) {
+          const int sb = ib % p.SB;
+          mbar_wait(b_empty(sb), ((ib / p.SB) & 1) ^ 1);
+          mbar_expect_tx(b_full(sb), (uint32_t)b_stage);
+          const uint32_t dst = b_base + (uint32_t)sb * b_stage;
+          tma_load_4d(dst, &tmB, b_full(sb), kc * 32, dy * 3 + dx, n0, 0);
+          if (x3) tma_load_4d(dst + p.b_plane_bytes, &tmB, b_full(sb), kc * 32, dy * 3 + dx, n0, 1);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      int ib = 0;
+      for (int ia = 0; ia < NA; ++ia) {
+        const int kc = ia % KC;
+        const int sa = ia % p.SA;
+        mbar_wait(x3 ? a_ready(sa) : a_full(sa), (ia / p.SA) & 1);
+        const int rem = p.C - kc * 32;
+        const int nk = rem >= 32 ? 4 : (rem + 7) / 8;
+        const uint32_t a_hi = a_base + (uint32_t)sa * a_stage, a_lo = a_hi + p.a_slot_bytes;
+        for (int dx = 0; dx < 3; ++dx, ++ib) {
+          const int sb = ib % p.SB;
+          mbar_wait(b_full(sb), (ib / p.SB) & 1);
+          tc_fence_after();
+          const uint32_t b_hi = b_base + (uint32_t)sb * b_stage, b_lo = b_hi + p.b_plane_bytes;
+          const uint64_t db = make_kmajor_sw128_desc(b_hi), dbl = make_kmajor_sw128_desc(b_lo);
+          for (int t = 0; t < p.MT; ++t) {
+            const uint32_t row_off = (uint32_t)((t * p.BH * p.RW + dx * p.dil) * 128);
+            const uint64_t da = make_kmajor_sw128_desc_off(a_hi + row_off), dal = make_kmajor_sw128_desc_off(a_lo + row_off);
+            const uint32_t acc = tmem_acc + (uint32_t)(t * p.ncol_acc);
+            for (int k = 0; k < nk; ++k) {
+              const uint64_t adv = (uint64_t)(2 * k);
+              tc_mma_tf32(acc, da + adv, db + adv, idesc, (ia | dx | k) ? 1u : 0u);
+              if (x3) {
+                tc_mma_tf32(acc, dal + adv, db + adv, idesc, 1u);
+                tc_mma_tf32(acc, da + adv, dbl + adv, idesc, 1u);
+              }
+            }
+          }
+          tc_commit(b_empty(sb));
+        }
+        tc_commit(a_empty(sa));
+      }
+      tc_commit(tmem_full_bar);
+    }
+  } else {
+    const int t = threadIdx.x - 64;
+    if (x3) {
+      const int n4 = p.a_box_bytes / 16;
+      for (int ia = 0; ia < NA; ++ia) {
+        const int sa = ia % p.SA;
+        mbar_wait(a_full(sa), (ia / p.SA) & 1);
+        float4* hi = reinterpret_cast<float4*>(smem + (size_t)sa * a_stage);
+        float4* lo = reinterpret_cast<float4*>(smem + (size_t)sa * a_stage + p.a_slot_bytes);
+        for (int i = t; i < n4; i += 128) {
+          const float4 v = hi[i];
+          const float4 h = rn_tf32_4(v);
+          hi[i] = h;
+          lo[i] = rn_tf32_4(v - h);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(a_ready(sa));
+      }
+    }
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int ly = r / p.RW, lx = r - ly * p.RW;
+    for (int tile = 0; tile < p.MT; ++tile) {
+      const int y = y0 + tile * p.BH + ly;
+      const bool valid = ly < p.BH && lx < p.W && y < p.H;
+      float* orow = out + (((size_t)img * p.H + y) * p.W + lx) * p.ldc;
+      const uint32_t tbase = tmem_acc + (uint32_t)(tile * p.ncol_acc) + ((uint32_t)(quarter * 32) << 16);
+      for (int c = 0; c < p.BN; c += 16) {
+        uint32_t v[16];
+        __syncwarp();
+        tc_ld16(tbase + (uint32_t)c, v);
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int n = n0 + c + q * 4;
+            if (n < p.N) {
+              float4 o = f4(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
+                            __uint_as_float(v[q * 4 + 3]));
+              if (bias) o = o + ld4(bias + n);
+              if (p.accumulate) o = o + ld4(orow + n);
+              st4(orow + n, o);
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(ncols) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -357,6 +538,66 @@ bool tc_supported(int conv, int W, int C, int N) {
   return encode_fn() != nullptr;
 }
 
+// second-generation 3x3 path; returns false when the shape does not fit (caller uses tc_conv_kernel)
+static bool tc_conv3(const float* A, int lda, const float* Wt, const float* bias, float* out, int ldc, int B, int H, int W,
+                     int C, int dil, int N, int accumulate, int split, cudaStream_t s) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("MLIIS_TC_CONV3"); enabled = e ? atoi(e) : 1; }
+  if (!enabled) return false;
+  TcC3Params p{};
+  p.H = H; p.W = W; p.C = C; p.dil = dil; p.N = N; p.ldc = ldc; p.accumulate = accumulate;
+  p.split = split == 3 ? 3 : 1;
+  p.RW = W + 2 * dil;
+  if (p.RW > 128) return false;
+  p.BH = 128 / p.RW;
+  if (p.BH > H) p.BH = H;
+  p.MT = 2;
+  p.tiles_per_image = (H + p.BH - 1) / p.BH;
+  if (p.tiles_per_image < 2) p.MT = 1;
+  p.groups_per_image = (p.tiles_per_image + p.MT - 1) / p.MT;
+  const int box_rows = p.MT * p.BH * p.RW;
+  if (box_rows > 256 || p.MT * p.BH > 256) return false;
+  p.BN = tc_pick_bn(N);
+  p.ncol_acc = 32;
+  while (p.ncol_acc < p.BN) p.ncol_acc <<= 1;
+  if (p.ncol_acc * p.MT > 512) return false;
+  p.a_box_bytes = box_rows * 128;
+  // the last tile's MMAs read up to (MT-1)*BH*RW + 2*dil + 128 rows: keep them inside the slot
+  int slot_rows = (p.MT - 1) * p.BH * p.RW + 2 * dil + 128;
+  if (slot_rows < box_rows) slot_rows = box_rows;
+  p.a_slot_bytes = (slot_rows * 128 + 1023) / 1024 * 1024;
+  p.b_plane_bytes = p.BN * 128;
+  const int planes = p.split == 3 ? 2 : 1;
+  const int budget = 216 * 1024;
+  p.SA = p.split == 3 ? 2 : 3;
+  p.SB = (budget - p.SA * planes * p.a_slot_bytes) / (planes * p.b_plane_bytes);
+  if (p.SB > 8) p.SB = 8;
+  if (p.SB < 2) return false;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t str[3] = {(cuuint64_t)lda * 4, (cuuint64_t)W * lda * 4, (cuuint64_t)H * W * lda * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)p.RW, (cuuint32_t)(p.MT * p.BH), 1};
+    if (!encode(&tmA, A, 4, dims, str, box)) return false;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)C, 9, (cuuint64_t)N, (cuuint64_t)planes};
+    cuuint64_t str[3] = {(cuuint64_t)C * 4, (cuuint64_t)9 * C * 4, (cuuint64_t)N * 9 * C * 4};
+    cuuint32_t box[4] = {32, 1, (cuuint32_t)p.BN, 1};
+    if (!encode(&tmB, Wt, 4, dims, str, box)) return false;
+  }
+  const size_t smem = (size_t)p.SA * planes * p.a_slot_bytes + (size_t)p.SB * planes * p.b_plane_bytes +
+                      (3 * p.SA + 2 * p.SB + 2) * 8 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr = true;
+  }
+  dim3 grid(B * p.groups_per_image, (N + p.BN - 1) / p.BN);
+  MLIIS_COUNT(), tc_conv3_kernel<<<grid, kTcThreads, smem, s>>>(tmA, tmB, bias, out, p);
+  return true;
+}
+
 // Wt layout expected by the kernel: [N][taps][C]  (K-major rows of B)
 bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float* out, int ldc, int conv, int M, int B,
              int H, int W, int C, int taps, int dil, int N, int accumulate, int split, cudaStream_t s,
@@ -370,6 +611,8 @@ bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float*
   p.pa = pa; p.pb = pb; p.gate = gate; p.HW = HW > 0 ? HW : 1;
   p.conv = conv; p.M = M; p.H = H; p.W = W; p.C = C; p.taps = taps; p.dil = dil; p.N = N; p.ldc = ldc;
   p.accumulate = accumulate;
+  if (conv && taps == 9 && !dbg && tc_conv3(A, lda, Wt, bias, out, ldc, B, H, W, C, dil, N, accumulate, p.split, s))
+    return true;
   p.BN = tc_pick_bn(N);
   CUtensorMap tmA, tmB;
   int grid_x;
