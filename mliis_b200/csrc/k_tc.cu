@@ -318,8 +318,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // 3x3 (dilated) implicit GEMM, second generation.  Measured limiter of tc_conv_kernel on the big decoder convs: the
 // per-SM TMA engine (~one 128-byte row per ~5 clk), not the tensor pipe.  So this kernel moves fewer rows per MMA:
 //  * ONE halo'd A box {32 ch, W+2d, MT*BH rows} per (filter row dy, K chunk) serves the three horizontal taps: tap dx
-//    reads the same shared-memory slab through a descriptor whose start address is shifted by dx*d rows (128 B each;
-//    the SWIZZLE_128B phase of the shifted start goes into the descriptor's base_offset field);
+//    reads the same shared-memory slab through a descriptor whose start address is shifted by dx*d rows (128 B each).
+//    Measured on B200: the SWIZZLE_128B XOR phase is taken from the absolute shared-memory address bits, so a
+//    row-shifted start needs NO base_offset (setting it double-applies the phase and scrambles the K chunks);
 //  * MT = 2 pixel tiles per CTA share every weight tile (two TMEM accumulators);
 //  * A and B live in separate rings (A: 2-3 slots of 32 KB, B: up to 8 slots), so the pipeline is deeper.
 // Tile rows are r = ly*(W+2d) + lx; rows with lx >= W are halo pixels whose outputs are discarded.
@@ -329,6 +330,7 @@ struct TcC3Params {
   int C, dil, N, BN, ldc, accumulate;
   int SA, SB, split, ncol_acc;
   int a_box_bytes, a_slot_bytes, b_plane_bytes;
+  int boff;          // experiment knob: 1 = set the descriptor base_offset field for shifted starts, 0 = leave it 0
 };
 
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc_off(uint32_t smem_addr) {
@@ -421,7 +423,8 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint64_t db = make_kmajor_sw128_desc(b_hi), dbl = make_kmajor_sw128_desc(b_lo);
           for (int t = 0; t < p.MT; ++t) {
             const uint32_t row_off = (uint32_t)((t * p.BH * p.RW + dx * p.dil) * 128);
-            const uint64_t da = make_kmajor_sw128_desc_off(a_hi + row_off), dal = make_kmajor_sw128_desc_off(a_lo + row_off);
+            const uint64_t da = p.boff ? make_kmajor_sw128_desc_off(a_hi + row_off) : make_kmajor_sw128_desc(a_hi + row_off);
+            const uint64_t dal = p.boff ? make_kmajor_sw128_desc_off(a_lo + row_off) : make_kmajor_sw128_desc(a_lo + row_off);
             const uint32_t acc = tmem_acc + (uint32_t)(t * p.ncol_acc);
             for (int k = 0; k < nk; ++k) {
               const uint64_t adv = (uint64_t)(2 * k);
@@ -545,6 +548,9 @@ static bool tc_conv3(const float* A, int lda, const float* Wt, const float* bias
   if (enabled < 0) { const char* e = getenv("MLIIS_TC_CONV3"); enabled = e ? atoi(e) : 1; }
   if (!enabled) return false;
   TcC3Params p{};
+  static int boff = -1;
+  if (boff < 0) { const char* e = getenv("MLIIS_TC_BASEOFF"); boff = e ? atoi(e) : 0; }
+  p.boff = boff;
   p.H = H; p.W = W; p.C = C; p.dil = dil; p.N = N; p.ldc = ldc; p.accumulate = accumulate;
   p.split = split == 3 ? 3 : 1;
   p.RW = W + 2 * dil;
