@@ -331,6 +331,7 @@ struct TcC3Params {
   int SA, SB, split, ncol_acc;
   int a_box_bytes, a_slot_bytes, b_plane_bytes;
   int boff;          // experiment knob: 1 = set the descriptor base_offset field for shifted starts, 0 = leave it 0
+  int debug;         // MLIIS_TC_DEBUG bits: 1 skip operand transform, 2 skip MMA issue, 4 one tile per CTA
 };
 
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc_off(uint32_t smem_addr) {
@@ -426,7 +427,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint64_t da = p.boff ? make_kmajor_sw128_desc_off(a_hi + row_off) : make_kmajor_sw128_desc(a_hi + row_off);
             const uint64_t dal = p.boff ? make_kmajor_sw128_desc_off(a_lo + row_off) : make_kmajor_sw128_desc(a_lo + row_off);
             const uint32_t acc = tmem_acc + (uint32_t)(t * p.ncol_acc);
-            for (int k = 0; k < nk; ++k) {
+            for (int k = 0; k < nk && !(p.debug & 2); ++k) {
               const uint64_t adv = (uint64_t)(2 * k);
               tc_mma_tf32(acc, da + adv, db + adv, idesc, (ia | dx | k) ? 1u : 0u);
               if (x3) {
@@ -450,7 +451,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(a_full(sa), (ia / p.SA) & 1);
         float4* hi = reinterpret_cast<float4*>(smem + (size_t)sa * a_stage);
         float4* lo = reinterpret_cast<float4*>(smem + (size_t)sa * a_stage + p.a_slot_bytes);
-        for (int i = t; i < n4; i += 128) {
+        for (int i = t; i < n4 && !(p.debug & 1); i += 128) {
           const float4 v = hi[i];
           const float4 h = rn_tf32_4(v);
           hi[i] = h;
@@ -548,16 +549,18 @@ static bool tc_conv3(const float* A, int lda, const float* Wt, const float* bias
   if (enabled < 0) { const char* e = getenv("MLIIS_TC_CONV3"); enabled = e ? atoi(e) : 1; }
   if (!enabled) return false;
   TcC3Params p{};
-  static int boff = -1;
+  static int boff = -1, dbg3 = -1;
   if (boff < 0) { const char* e = getenv("MLIIS_TC_BASEOFF"); boff = e ? atoi(e) : 0; }
+  if (dbg3 < 0) { const char* e = getenv("MLIIS_TC_DEBUG"); dbg3 = e ? atoi(e) : 0; }
   p.boff = boff;
+  p.debug = dbg3;
   p.H = H; p.W = W; p.C = C; p.dil = dil; p.N = N; p.ldc = ldc; p.accumulate = accumulate;
   p.split = split == 3 ? 3 : 1;
   p.RW = W + 2 * dil;
   if (p.RW > 128) return false;
   p.BH = 128 / p.RW;
   if (p.BH > H) p.BH = H;
-  p.MT = 2;
+  p.MT = (dbg3 & 4) ? 1 : 2;
   p.tiles_per_image = (H + p.BH - 1) / p.BH;
   if (p.tiles_per_image < 2) p.MT = 1;
   p.groups_per_image = (p.tiles_per_image + p.MT - 1) / p.MT;
@@ -617,7 +620,7 @@ bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float*
   p.pa = pa; p.pb = pb; p.gate = gate; p.HW = HW > 0 ? HW : 1;
   p.conv = conv; p.M = M; p.H = H; p.W = W; p.C = C; p.taps = taps; p.dil = dil; p.N = N; p.ldc = ldc;
   p.accumulate = accumulate;
-  if (conv && taps == 9 && !dbg && tc_conv3(A, lda, Wt, bias, out, ldc, B, H, W, C, dil, N, accumulate, p.split, s))
+  if (conv && taps == 9 && tc_conv3(A, lda, Wt, bias, out, ldc, B, H, W, C, dil, N, accumulate, p.split, s))
     return true;
   p.BN = tc_pick_bn(N);
   CUtensorMap tmA, tmB;
