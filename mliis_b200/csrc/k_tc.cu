@@ -154,8 +154,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // wide: hi and lo weight planes are adjacent in the stage, so one N = 2*BN MMA forms a_hi*b_hi | a_hi*b_lo in two
+  // accumulator column ranges that the epilogue adds (A is fetched from shared memory twice per k-step, not three times)
+  const bool wide = x3 && 2 * p.BN <= 256 && !(p.debug & 8);
   uint32_t ncols = 32;
-  while ((int)ncols < p.BN) ncols <<= 1;
+  while ((int)ncols < (wide ? 2 : 1) * p.BN) ncols <<= 1;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -215,6 +218,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format TF32 [7,10)=[10,13)=2,
       // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc_w = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 2) << 17) | ((128u >> 4) << 24);
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % p.stages;
         mbar_wait(xform ? ready_bar(s) : full_bar(s), (kb / p.stages) & 1);
@@ -227,10 +231,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint64_t dal = make_kmajor_sw128_desc(sa + a_off_lo), dbl = make_kmajor_sw128_desc(sb + b_bytes);
         for (int k = 0; k < nk && !(p.debug & 2); ++k) {  // advance 32 bytes (8 tf32) along K inside the swizzle atom
           const uint64_t adv = (uint64_t)(2 * k);
-          tc_mma_tf32(tmem_acc, da + adv, db + adv, idesc, (kb | k) ? 1u : 0u);
-          if (x3) {   // a*b ~= ah*bh + al*bh + ah*bl   (al*bl ~ 2^-22 relative, dropped)
+          // a*b ~= ah*bh + al*bh + ah*bl   (al*bl ~ 2^-22 relative, dropped)
+          if (wide) {
+            tc_mma_tf32(tmem_acc, da + adv, db + adv, idesc_w, (kb | k) ? 1u : 0u);
             tc_mma_tf32(tmem_acc, dal + adv, db + adv, idesc, 1u);
-            tc_mma_tf32(tmem_acc, da + adv, dbl + adv, idesc, 1u);
+          } else {
+            tc_mma_tf32(tmem_acc, da + adv, db + adv, idesc, (kb | k) ? 1u : 0u);
+            if (x3) {
+              tc_mma_tf32(tmem_acc, dal + adv, db + adv, idesc, 1u);
+              tc_mma_tf32(tmem_acc, da + adv, dbl + adv, idesc, 1u);
+            }
           }
         }
         tc_commit(empty_bar(s));      // frees the stage once these MMAs have read it
@@ -291,6 +301,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t v[16];
       __syncwarp();
       tc_ld16(tbase + (uint32_t)c, v);          // warp-collective: executed by all 32 lanes, converged
+      if (wide) {
+        uint32_t w[16];
+        tc_ld16(tbase + (uint32_t)(p.BN + c), w);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(w[q]));
+      }
       if (valid) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -328,10 +344,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 struct TcC3Params {
   int H, W, RW, BH, MT, tiles_per_image, groups_per_image;
   int C, dil, N, BN, ldc, accumulate;
-  int SA, SB, split, ncol_acc;
+  int SA, SB, split, ncol_acc, ncols_alloc, wide;
   int a_box_bytes, a_slot_bytes, b_plane_bytes;
   int boff;          // experiment knob: 1 = set the descriptor base_offset field for shifted starts, 0 = leave it 0
-  int debug;         // MLIIS_TC_DEBUG bits: 1 skip operand transform, 2 skip MMA issue, 4 one tile per CTA
+  int debug;         // MLIIS_TC_DEBUG bits: 1 skip operand transform, 2 skip MMA issue, 4 one tile per CTA, 8 no wide-B
 };
 
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc_off(uint32_t smem_addr) {
@@ -361,7 +377,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_ptr + 8 * (3 * p.SA + 2 * p.SB + 1));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t ncols = (uint32_t)(p.ncol_acc * p.MT);
+  const uint32_t ncols = (uint32_t)p.ncols_alloc;
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -408,6 +424,9 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      // wide: the hi and lo weight planes sit back to back in the B slot, so one N = 2*BN MMA forms a_hi*b_hi and
+      // a_hi*b_lo in adjacent accumulator column ranges (A is fetched from shared memory once for both products)
+      const uint32_t idesc_w = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 2) << 17) | ((128u >> 4) << 24);
       int ib = 0;
       for (int ia = 0; ia < NA; ++ia) {
         const int kc = ia % KC;
@@ -429,10 +448,15 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t acc = tmem_acc + (uint32_t)(t * p.ncol_acc);
             for (int k = 0; k < nk && !(p.debug & 2); ++k) {
               const uint64_t adv = (uint64_t)(2 * k);
-              tc_mma_tf32(acc, da + adv, db + adv, idesc, (ia | dx | k) ? 1u : 0u);
-              if (x3) {
+              if (p.wide) {
+                tc_mma_tf32(acc, da + adv, db + adv, idesc_w, (ia | dx | k) ? 1u : 0u);
                 tc_mma_tf32(acc, dal + adv, db + adv, idesc, 1u);
-                tc_mma_tf32(acc, da + adv, dbl + adv, idesc, 1u);
+              } else {
+                tc_mma_tf32(acc, da + adv, db + adv, idesc, (ia | dx | k) ? 1u : 0u);
+                if (x3) {
+                  tc_mma_tf32(acc, dal + adv, db + adv, idesc, 1u);
+                  tc_mma_tf32(acc, da + adv, dbl + adv, idesc, 1u);
+                }
               }
             }
           }
@@ -475,6 +499,12 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         uint32_t v[16];
         __syncwarp();
         tc_ld16(tbase + (uint32_t)c, v);
+        if (p.wide) {
+          uint32_t w[16];
+          tc_ld16(tbase + (uint32_t)(p.BN + c), w);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(w[q]));
+        }
         if (valid) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -567,9 +597,11 @@ static bool tc_conv3(const float* A, int lda, const float* Wt, const float* bias
   const int box_rows = p.MT * p.BH * p.RW;
   if (box_rows > 256 || p.MT * p.BH > 256) return false;
   p.BN = tc_pick_bn(N);
-  p.ncol_acc = 32;
-  while (p.ncol_acc < p.BN) p.ncol_acc <<= 1;
-  if (p.ncol_acc * p.MT > 512) return false;
+  p.wide = p.split == 3 && 2 * p.BN <= 256 && 2 * p.BN * p.MT <= 512 && !(dbg3 & 8);
+  p.ncol_acc = p.wide ? 2 * p.BN : p.BN;
+  p.ncols_alloc = 32;
+  while (p.ncols_alloc < p.ncol_acc * p.MT) p.ncols_alloc <<= 1;
+  if (p.ncols_alloc > 512) return false;
   p.a_box_bytes = box_rows * 128;
   // the last tile's MMAs read up to (MT-1)*BH*RW + 2*dil + 128 rows: keep them inside the slot
   int slot_rows = (p.MT - 1) * p.BH * p.RW + 2 * dil + 128;
@@ -616,6 +648,9 @@ bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float*
   if (dbg < 0) { const char* e = getenv("MLIIS_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
   p.debug = dbg;
   p.split = split == 3 ? 3 : 1;
+  static int dbgw = -1;
+  if (dbgw < 0) { const char* e = getenv("MLIIS_TC_DEBUG"); dbgw = e ? atoi(e) : 0; }
+  p.debug = dbgw;
   if (pa && conv) return false;
   p.pa = pa; p.pb = pb; p.gate = gate; p.HW = HW > 0 ? HW : 1;
   p.conv = conv; p.M = M; p.H = H; p.W = W; p.C = C; p.taps = taps; p.dil = dil; p.N = N; p.ldc = ldc;
@@ -684,6 +719,7 @@ struct TcWgParams {
   int taps, dil;
   int splits, tiles_total;
   int stages, split;
+  int debug;                   // MLIIS_TC_DEBUG bits (bottleneck experiments only): 1 skip transform, 2 skip MMA
   const float* pa; const float* pb; const float* gate;   // A prologue (plain mode), as in tc_conv_kernel
   int HW;
 };
@@ -720,8 +756,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // wide: the G lo plane starts right behind the hi plane's last 32-channel group, so [G_hi | G_lo] is one MN-major
+  // operand of 2*NG groups: one N = 64*NG MMA forms a_hi*g_hi | a_hi*g_lo (epilogue adds the two column ranges)
+  const bool wide = x3 && p.NG <= 4;
+  const int wide_off = p.NG * 32;
   uint32_t ncols = 32;
-  while ((int)ncols < p.BN) ncols <<= 1;
+  while ((int)ncols < (wide ? 2 * wide_off : p.BN)) ncols <<= 1;
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
@@ -771,6 +811,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // TF32, fp32 accumulate, BOTH operands MN-major (bits 15 and 16)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc_w = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(2 * wide_off >> 3) << 17) | ((128u >> 4) << 24);
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % p.stages;
         mbar_wait(ready_bar(s), (kb / p.stages) & 1);
@@ -778,12 +820,17 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t sa = base + (uint32_t)s * stage_bytes;
         const uint64_t da = make_mnmajor_sw128_desc(sa), dal = make_mnmajor_sw128_desc(sa + a_lo);
         const uint64_t dg = make_mnmajor_sw128_desc(sa + g_off), dgl = make_mnmajor_sw128_desc(sa + g_lo);
-        for (int k = 0; k < 4; ++k) {            // 4 atoms of 8 pixel rows: +1024 B each
+        for (int k = 0; k < 4 && !(p.debug & 2); ++k) {            // 4 atoms of 8 pixel rows: +1024 B each
           const uint64_t adv = (uint64_t)(64 * k);
-          tc_mma_tf32(tmem_acc, da + adv, dg + adv, idesc, (kb | k) ? 1u : 0u);
-          if (x3) {
+          if (wide) {
+            tc_mma_tf32(tmem_acc, da + adv, dg + adv, idesc_w, (kb | k) ? 1u : 0u);
             tc_mma_tf32(tmem_acc, dal + adv, dg + adv, idesc, 1u);
-            tc_mma_tf32(tmem_acc, da + adv, dgl + adv, idesc, 1u);
+          } else {
+            tc_mma_tf32(tmem_acc, da + adv, dg + adv, idesc, (kb | k) ? 1u : 0u);
+            if (x3) {
+              tc_mma_tf32(tmem_acc, dal + adv, dg + adv, idesc, 1u);
+              tc_mma_tf32(tmem_acc, da + adv, dgl + adv, idesc, 1u);
+            }
           }
         }
         tc_commit(empty_bar(s));
@@ -800,7 +847,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       float4* a_lop = reinterpret_cast<float4*>(st + a_lo);
       const int m0 = (t_beg + kb) * 32;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {            // A: 4 groups x 256 float4
+      for (int j = 0; j < 8 && !(p.debug & 1); ++j) {            // A: 4 groups x 256 float4
         const int i = t + 128 * j;
         float4 v = a_hi[i];
         if (p.pa) {
@@ -823,7 +870,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       float4* g_hi = reinterpret_cast<float4*>(st + g_off);
       float4* g_lop = reinterpret_cast<float4*>(st + g_lo);
       const int ng4 = p.NG * 256;
-      for (int i = t; i < ng4; i += 128) {
+      for (int i = t; i < ng4 && !(p.debug & 1); i += 128) {
         const float4 v = g_hi[i];
         const float4 h = rn_tf32_4(v);
         g_hi[i] = h;
@@ -844,8 +891,15 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int cc = 0; cc < p.BN; cc += 16) {
       uint32_t v[16];
       __syncwarp();
-      if (KB > 0) tc_ld16(tbase + (uint32_t)cc, v);
-      else {
+      if (KB > 0) {
+        tc_ld16(tbase + (uint32_t)cc, v);
+        if (wide) {
+          uint32_t w[16];
+          tc_ld16(tbase + (uint32_t)(wide_off + cc), w);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(w[q]));
+        }
+      } else {
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] = 0u;
       }
