@@ -76,7 +76,7 @@ class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,utilization.gpu,utilization.memory")
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
@@ -108,19 +108,27 @@ class ClockSampler(threading.Thread):
                 pass
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, ug, um, pw = [], [], set(), [], [], []
         for f in self.samples:
             try:
                 sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[3])); ug.append(float(f[9])); um.append(float(f[10]))
+            except (ValueError, IndexError):
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+               "samples": len(sm)}
+        if ug:
+            out.update({"util_gpu_pct": float(np.median(ug)), "util_mem_pct": float(np.median(um)),
+                        "power_w": float(np.median(pw))})
+        return out
 
 
 def measured_peaks():

@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(kTcThreads)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const float* __restrict__ bias, float* __restrict__ out, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
+  if (p.debug & 16) return;   // experiment: cost of everything except the tensor-core kernels
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;              // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* smem = smem_raw + (base - raw);
@@ -359,6 +360,7 @@ __global__ void __launch_bounds__(kTcThreads)
 tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const float* __restrict__ bias, float* __restrict__ out, const TcC3Params p) {
   extern __shared__ uint8_t smem_raw[];
+  if (p.debug & 16) return;   // experiment: cost of everything except the tensor-core kernels
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
@@ -648,9 +650,6 @@ bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float*
   if (dbg < 0) { const char* e = getenv("MLIIS_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
   p.debug = dbg;
   p.split = split == 3 ? 3 : 1;
-  static int dbgw = -1;
-  if (dbgw < 0) { const char* e = getenv("MLIIS_TC_DEBUG"); dbgw = e ? atoi(e) : 0; }
-  p.debug = dbgw;
   if (pa && conv) return false;
   p.pa = pa; p.pb = pb; p.gate = gate; p.HW = HW > 0 ? HW : 1;
   p.conv = conv; p.M = M; p.H = H; p.W = W; p.C = C; p.taps = taps; p.dil = dil; p.N = N; p.ldc = ldc;
@@ -733,11 +732,15 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) 
 }
 
 constexpr int kWgGroupBytes = 32 * 128;   // one TMA box: 32 pixel rows x 32 channels fp32
+// wgrad splits BOTH operands in the kernel (activations and gradients), so it runs 8 transform/epilogue warps
+constexpr int kWgXformThreads = 256;
+constexpr int kWgThreads = 64 + kWgXformThreads;
 
-__global__ void __launch_bounds__(kTcThreads)
+__global__ void __launch_bounds__(kWgThreads)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmG,
                 float* __restrict__ partial, const TcWgParams p) {
   extern __shared__ uint8_t smem_raw[];
+  if (p.debug & 16) return;   // experiment: cost of everything except the tensor-core kernels
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
@@ -765,7 +768,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(ready_bar(s), 128); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(ready_bar(s), kWgXformThreads); }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -847,8 +850,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       float4* a_lop = reinterpret_cast<float4*>(st + a_lo);
       const int m0 = (t_beg + kb) * 32;
 #pragma unroll
-      for (int j = 0; j < 8 && !(p.debug & 1); ++j) {            // A: 4 groups x 256 float4
-        const int i = t + 128 * j;
+      for (int j = 0; j < 1024 / kWgXformThreads && !(p.debug & 1); ++j) {            // A: 4 groups x 256 float4
+        const int i = t + kWgXformThreads * j;
         float4 v = a_hi[i];
         if (p.pa) {
           // SWIZZLE_128B_ATOM_32B: logical 32-byte chunk = physical chunk XOR (row & 3)
@@ -870,7 +873,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       float4* g_hi = reinterpret_cast<float4*>(st + g_off);
       float4* g_lop = reinterpret_cast<float4*>(st + g_lo);
       const int ng4 = p.NG * 256;
-      for (int i = t; i < ng4 && !(p.debug & 1); i += 128) {
+      for (int i = t; i < ng4 && !(p.debug & 1); i += kWgXformThreads) {
         const float4 v = g_hi[i];
         const float4 h = rn_tf32_4(v);
         g_hi[i] = h;
@@ -888,7 +891,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_after();
     }
     const uint32_t tbase = tmem_acc + ((uint32_t)(quarter * 32) << 16);
-    for (int cc = 0; cc < p.BN; cc += 16) {
+    for (int cc = ((warp - 2) >> 2) * 16; cc < p.BN; cc += 16 * (kWgXformThreads / 128)) {   // two warps per TMEM lane quarter
       uint32_t v[16];
       __syncwarp();
       if (KB > 0) {
@@ -951,6 +954,9 @@ bool tc_wgrad(const float* A, int lda, const float* G, int ldg, float* dW, float
               const float* gate, int HW) {
   TcWgParams p{};
   p.conv = conv; p.M = M; p.H = H; p.W = W; p.C = C; p.N = N; p.taps = taps; p.dil = dil;
+  static int dbgw = -1;
+  if (dbgw < 0) { const char* e = getenv("MLIIS_TC_DEBUG"); dbgw = e ? atoi(e) : 0; }
+  p.debug = dbgw;
   p.split = split == 3 ? 3 : 1;
   if (pa && conv) return false;
   p.pa = pa; p.pb = pb; p.gate = gate; p.HW = HW > 0 ? HW : 1;
@@ -995,7 +1001,7 @@ bool tc_wgrad(const float* A, int lda, const float* G, int ldg, float* dW, float
     attr = true;
   }
   dim3 grid(ctiles, taps, p.splits);
-  MLIIS_COUNT(), tc_wgrad_kernel<<<grid, kTcThreads, smem, s>>>(tmA, tmG, scratch, p);
+  MLIIS_COUNT(), tc_wgrad_kernel<<<grid, kWgThreads, smem, s>>>(tmA, tmG, scratch, p);
   reduce_partials(scratch, p.splits, taps * C * N, dW, s);
   return true;
 }
