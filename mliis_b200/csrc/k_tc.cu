@@ -733,7 +733,7 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) 
 
 constexpr int kWgGroupBytes = 32 * 128;   // one TMA box: 32 pixel rows x 32 channels fp32
 // wgrad splits BOTH operands in the kernel (activations and gradients), so it runs 8 transform/epilogue warps
-constexpr int kWgXformThreads = 256;
+constexpr int kWgXformThreads = 512;
 constexpr int kWgThreads = 64 + kWgXformThreads;
 
 __global__ void __launch_bounds__(kWgThreads)
