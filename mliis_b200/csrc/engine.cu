@@ -64,6 +64,7 @@ struct mliis_ctx {
   std::vector<Slot> slots;
   int32_t* d_gamma_idx = nullptr;
   int32_t* d_beta_idx = nullptr;
+  TcPrepJob* d_prep_jobs = nullptr;   // device copy of plan.prep_jobs with the per-layer TF32 split resolved
   std::vector<Tab> tabs;
   std::vector<void*> owned;
   float keep[16];
@@ -180,13 +181,26 @@ struct Dense {
   bool decoder = false;   // MLIIS_GEMM_TF32: single-pass TF32 for the decoder convs only; the backbone stays 3xTF32
   bool tc() const { return r.c->cfg.gemm_mode != MLIIS_GEMM_FP32; }
   int split() const { return (r.c->cfg.gemm_mode == MLIIS_GEMM_TF32 && decoder) ? 1 : 3; }
+  // operand prepared by tc_prep_all at the start of the step (nullptr for a weight outside the plan's job table)
+  float* prepared(const float* w_hwio, int dgrad) const {
+    if (!r.c->d_prep_jobs) return nullptr;
+    const int64_t off = w_hwio - r.theta;
+    for (const Plan::PrepJob& j : r.p.prep_jobs)
+      if (j.w_off == off && j.dgrad == dgrad) return r.W(r.p.wcache + j.dst);
+    return nullptr;
+  }
+  float* operand(const float* w_hwio, int taps, int Cin, int Cout, int dgrad) const {
+    if (float* wt = prepared(w_hwio, dgrad)) return wt;
+    float* wt = r.W(r.p.wT);
+    tc_prep_weights(w_hwio, wt, taps, Cin, Cout, dgrad, split(), r.st);
+    return wt;
+  }
   // forward: out[M, Cout] = conv(A[.., Cin]) + bias
   void fwd(const float* A, int lda, int conv, int H, int W, int Cin, int dil, const float* w_hwio, const float* bias,
            float* out, int ldc, int Cout, int M, int HW) const {
     const int taps = conv ? 9 : 1;
     if (tc() && tc_supported(conv, W, Cin, Cout)) {
-      float* wt = r.W(r.p.wT);
-      tc_prep_weights(w_hwio, wt, taps, Cin, Cout, 0, split(), r.st);
+      float* wt = operand(w_hwio, taps, Cin, Cout, 0);
       if (tc_conv(A, lda, wt, bias, out, ldc, conv, M, r.B, H, W, Cin, taps, dil, Cout, 0, split(), r.st)) return;
     }
     GemmA a = conv ? convA(A, lda, H, W, Cin, dil) : plainA(A, lda);
@@ -196,8 +210,7 @@ struct Dense {
   void fwd_pro(const float* A, int lda, int Cin, const float* w_hwio, float* out, int ldc, int Cout, int M, int HW,
                const float* pa, const float* pb, const float* gate) const {
     if (tc() && tc_supported(0, 0, Cin, Cout)) {
-      float* wt = r.W(r.p.wT);
-      tc_prep_weights(w_hwio, wt, 1, Cin, Cout, 0, split(), r.st);
+      float* wt = operand(w_hwio, 1, Cin, Cout, 0);
       if (tc_conv(A, lda, wt, nullptr, out, ldc, 0, M, r.B, 1, 1, Cin, 1, 1, Cout, 0, split(), r.st, pa, pb, gate, HW))
         return;
     }
@@ -235,8 +248,8 @@ struct Dense {
     const int taps = conv ? 9 : 1;
     float* wt = r.W(r.p.wT);
     if (tc() && tc_supported(conv, W, Cout, Cin)) {
-      tc_prep_weights(w_hwio, wt, taps, Cin, Cout, 1, split(), r.st);
-      if (tc_conv(G, ldg, wt, nullptr, dA, ldd, conv, M, r.B, H, W, Cout, taps, dil, Cin, accumulate, split(), r.st)) return;
+      float* wtc = operand(w_hwio, taps, Cin, Cout, 1);
+      if (tc_conv(G, ldg, wtc, nullptr, dA, ldd, conv, M, r.B, H, W, Cout, taps, dil, Cin, accumulate, split(), r.st)) return;
     }
     if (conv) {
       flip_transpose_w3x3(w_hwio, wt, Cin, Cout, r.st);
@@ -256,6 +269,7 @@ void run_forward(const Run& r, const float* images, const int32_t* index, bool t
   const Plan& p = r.p;
   const int B = r.B;
   cudaStream_t st = r.st;
+  if (r.c->d_prep_jobs) tc_prep_all(r.theta, r.W(p.wcache), r.c->d_prep_jobs, (int)p.prep_jobs.size(), st);
   if (!training)
     bn_eval_coeffs(r.theta, r.c->d_gamma_idx, r.c->d_beta_idx, r.mm, r.mv, p.n_bn_ch, r.W(p.bn_a), r.W(p.bn_b), st);
   if (training && p.n_dc > 0) {
@@ -586,6 +600,13 @@ int mliis_ctx_create(const mliis_config* cfg, int device, mliis_ctx** out) {
     for (const RsdPlan& d : p.rsds) for (int j = 0; j < 3; ++j) fill(d.bn[j]);
     c->d_gamma_idx = upload(c, gi);
     c->d_beta_idx = upload(c, bi);
+    if (c->cfg.gemm_mode != MLIIS_GEMM_FP32 && !p.prep_jobs.empty()) {
+      std::vector<TcPrepJob> jobs;
+      for (const Plan::PrepJob& j : p.prep_jobs)
+        jobs.push_back({(long long)j.w_off, (long long)j.dst, j.taps, j.Ci, j.Co, j.dgrad,
+                        (c->cfg.gemm_mode == MLIIS_GEMM_TF32 && j.decoder) ? 1 : 3, 0});
+      c->d_prep_jobs = upload(c, jobs);
+    }
     c->tabs.resize(p.resize_pairs.size());
     bool ok = c->d_gamma_idx && c->d_beta_idx;
     for (size_t i = 0; ok && i < p.resize_pairs.size(); ++i)

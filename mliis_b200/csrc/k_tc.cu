@@ -1008,11 +1008,8 @@ bool tc_wgrad(const float* A, int lda, const float* G, int ldg, float* dW, float
 
 // weights W[tap][ci][co] (HWIO) -> forward operand Wt[co][tap][ci]   or   dgrad operand Wt[ci][taps-1-tap][co],
 // rounded to nearest TF32; split == 3 also writes the residual plane lo = rn(w - hi) behind the hi plane.
-__global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ wt, int taps, int Ci, int Co,
-                                       int dgrad, int split) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = taps * Ci * Co;
-  if (i >= n) return;
+__device__ __forceinline__ void prep_one(const float* __restrict__ w, float* __restrict__ wt, int i, int n, int taps,
+                                         int Ci, int Co, int dgrad, int split) {
   float v;
   if (!dgrad) {
     const int co = i / (taps * Ci), rem = i - co * taps * Ci, tap = rem / Ci, ci = rem - tap * Ci;
@@ -1024,6 +1021,24 @@ __global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __res
   const float h = rn_tf32(v);
   wt[i] = h;
   if (split == 3) wt[(size_t)n + i] = rn_tf32(v - h);
+}
+__global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ wt, int taps, int Ci, int Co,
+                                       int dgrad, int split) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = taps * Ci * Co;
+  if (i < n) prep_one(w, wt, i, n, taps, Ci, Co, dgrad, split);
+}
+// every dense layer's forward and dgrad operand in ONE launch per step (blockIdx.y = job)
+__global__ void tc_prep_all_kernel(const float* __restrict__ theta, float* __restrict__ wcache,
+                                   const TcPrepJob* __restrict__ jobs) {
+  const TcPrepJob j = jobs[blockIdx.y];
+  const int n = j.taps * j.Ci * j.Co;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    prep_one(theta + j.w_off, wcache + j.dst, i, n, j.taps, j.Ci, j.Co, j.dgrad, j.split);
+}
+void tc_prep_all(const float* theta, float* wcache, const TcPrepJob* dev_jobs, int n_jobs, cudaStream_t s) {
+  if (n_jobs <= 0) return;
+  MLIIS_COUNT(), tc_prep_all_kernel<<<dim3(24, n_jobs), 256, 0, s>>>(theta, wcache, dev_jobs);
 }
 void tc_prep_weights(const float* w, float* wt, int taps, int Ci, int Co, int dgrad, int split, cudaStream_t s) {
   const int n = taps * Ci * Co;

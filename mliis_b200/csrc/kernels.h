@@ -123,6 +123,9 @@ bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float*
 // W[tap][ci][co] (HWIO) -> Wt[co][tap][ci] (dgrad=0)  or  Wt[ci][taps-1-tap][co] (dgrad=1), rn(tf32);
 // split == 3 appends the residual plane (wt must hold 2 * taps*Ci*Co floats)
 void tc_prep_weights(const float* w, float* wt, int taps, int Ci, int Co, int dgrad, int split, cudaStream_t s);
+// one launch per step: operand (re-layout + TF32 hi/lo split) of every dense layer, forward and dgrad
+struct TcPrepJob { long long w_off, dst; int taps, Ci, Co, dgrad, split, pad; };
+void tc_prep_all(const float* theta, float* wcache, const TcPrepJob* dev_jobs, int n_jobs, cudaStream_t s);
 
 // wgrad on tensor cores: dW[taps*C, N] = sum_pixels A[pixel+tap, c] * G[pixel, n]  (A, G channel-contiguous)
 bool tc_wgrad_supported(int conv, int W, int C, int N);

@@ -349,6 +349,26 @@ void Plan::build(int image_size_, int max_batch, const int* rsd, float final_dro
   partials = b.alloc(partials_len);
   wT = b.alloc(2 * max_wT);   // hi (+ lo) operand planes of the tensor-core path
   tn_scratch = b.alloc(max_tn);
+  {
+    int64_t total = 0;
+    auto add = [&](int64_t w_off, int taps, int Ci, int Co, int decoder) {
+      for (int dgrad = 0; dgrad < 2; ++dgrad) {
+        prep_jobs.push_back({w_off, total, taps, Ci, Co, dgrad, decoder});
+        total += ((int64_t)2 * taps * Ci * Co + 31) / 32 * 32;
+      }
+    };
+    for (const BlockPlan& bp : blocks) {
+      if (bp.expand) add(bp.w_expand, 1, bp.cin, bp.ce, 0);
+      add(bp.w_proj, 1, bp.ce, bp.cout, 0);
+    }
+    for (const RsdPlan& rp : rsds) {
+      add(rp.w0, 1, rp.catC, D, 1);
+      add(rp.w1, 9, rp.catC, D, 1);
+      add(rp.w2, 9, rp.pyrC, D, 1);
+    }
+    wcache = b.alloc(total);
+    for (PrepJob& j : prep_jobs) j.dst += 0;   // offsets are relative to wcache
+  }
   dcs = b.alloc((int64_t)std::max(1, n_dc) * B);
   lr_dev = b.alloc(64);
   loss_coef = b.alloc(2 * B + 64);

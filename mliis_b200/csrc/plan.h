@@ -88,6 +88,10 @@ struct Plan {
   int64_t gY[2] = {0, 0}, gP = 0, gD = 0, gE = 0;
   int64_t g_out = 0, g_c = 0, g_c0 = 0, g_c1 = 0, g_pyr = 0, g_cat = 0, g_up = 0, g_skip = 0, g_deep = 0;
   int64_t partials = 0, partials_len = 0, wT = 0, tn_scratch = 0, dcs = 0, lr_dev = 0, loss_coef = 0;
+  // tensor-core operand cache: every dense layer's forward / dgrad operand, rebuilt once per step (tc_prep_all)
+  struct PrepJob { int64_t w_off, dst; int taps, Ci, Co, dgrad, decoder; };
+  std::vector<PrepJob> prep_jobs;
+  int64_t wcache = 0;
   int64_t ws_floats = 0;
   // resize tables needed: (in, out) pairs
   std::vector<std::pair<int, int>> resize_pairs;
