@@ -19,7 +19,24 @@
 
 using namespace mliis;
 
-namespace mliis { unsigned long long g_kernel_launches = 0; }
+namespace mliis {
+unsigned long long g_kernel_launches = 0;
+bool skip_launch(const char* launcher) {
+  static const char* env = getenv("MLIIS_SKIP");
+  if (!env || !*env) return false;
+  const char* p = env;
+  while (*p) {
+    const char* e = strchr(p, ',');
+    const size_t n = e ? (size_t)(e - p) : strlen(p);
+    if (n > 0) {
+      const std::string tok(p, n);
+      if (strstr(launcher, tok.c_str())) return true;
+    }
+    p += n + (e ? 1 : 0);
+  }
+  return false;
+}
+}
 
 namespace {
 

@@ -10,7 +10,10 @@ namespace mliis {
 
 // number of kernels launched by this library in this process (bench.py reports it as gpu_launches)
 extern unsigned long long g_kernel_launches;
-#define MLIIS_COUNT() (++::mliis::g_kernel_launches)
+// MLIIS_SKIP=<comma-separated substrings of launcher function names> drops those launches (bottleneck experiments
+// only: results are garbage); unset in every normal run.
+bool skip_launch(const char* launcher);
+#define MLIIS_COUNT() if (::mliis::skip_launch(__func__)) {} else ++::mliis::g_kernel_launches
 
 // ---------------- row-channel kernels (k_rowchan.cu) : HBM-bound ----------------
 enum BnVar { BN_PLAIN = 0, BN_SWISH = 1, BN_SWISH_SE = 2, BN_DEC = 3 };
