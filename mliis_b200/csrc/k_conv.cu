@@ -145,6 +145,7 @@ struct DwGeom {
   static constexpr int TI = (TO - 1) * S + K;           // staged input tile edge
   static constexpr int NIN = 6 * S + K;                 // inputs per strip row
   static constexpr size_t smem_bytes() { return (size_t)(TI * TI + K * K) * QC * sizeof(float4); }
+  static constexpr size_t wgrad_smem_bytes() { return (size_t)(TI * TI + K * K * (NT / 32)) * QC * sizeof(float4); }
 };
 
 // stage swish(a*x+b) (or x when a == null) of the input tile into shared memory
@@ -153,19 +154,27 @@ __device__ __forceinline__ void dw_stage_input(float4* tile, const float* __rest
                                                const float* __restrict__ a, const float* __restrict__ b, int img,
                                                int H, int W, int C, int c0, int iy0, int ix0) {
   using G = DwGeom<K, S>;
-  const int tid = threadIdx.x, q = tid % QC;
+  constexpr int TOT = G::TI * G::TI * QC, U = 4;
+  const int tid = threadIdx.x, q = tid % QC;     // NT is a multiple of QC: q is the same for every i of a thread
   const bool cvalid = c0 + q * 4 < C;
   float4 av = f4s(1.f), bv = f4s(0.f);
   if (a && cvalid) { av = ld4(a + c0 + q * 4); bv = ld4(b + c0 + q * 4); }
-  for (int i = tid; i < G::TI * G::TI * QC; i += G::NT) {
-    const int pix = i / QC, ly = pix / G::TI, lx = pix - ly * G::TI;
-    const int gy = iy0 + ly, gx = ix0 + lx;
-    float4 v = f4s(0.f);
-    if (cvalid && gy >= 0 && gy < H && gx >= 0 && gx < W) {
-      v = ld4(x + (((size_t)img * H + gy) * W + gx) * C + c0 + q * 4);
-      if (a) v = swish4(affine4(v, av, bv));
+  for (int i0 = tid; i0 < TOT; i0 += U * G::NT) {
+    float4 v[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {      // issue the U global loads before any of them is consumed
+      const int i = i0 + u * G::NT;
+      const int pix = i / QC, ly = pix / G::TI, lx = pix - ly * G::TI;
+      const int gy = iy0 + ly, gx = ix0 + lx;
+      ok[u] = i < TOT && cvalid && gy >= 0 && gy < H && gx >= 0 && gx < W;
+      v[u] = ok[u] ? ld4(x + (((size_t)img * H + gy) * W + gx) * C + c0 + q * 4) : f4s(0.f);
     }
-    tile[i] = v;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * G::NT;
+      if (i < TOT) tile[i] = (a && ok[u]) ? swish4(affine4(v[u], av, bv)) : v[u];
+    }
   }
 }
 
@@ -199,14 +208,17 @@ __global__ void __launch_bounds__(DwGeom<K, S>::NT) dw_fwd_kernel(const float* _
 #pragma unroll
   for (int ky = 0; ky < K; ++ky) {
     const float4* row = tile + ((size_t)(oy * S + ky) * G::TI + ox0 * S) * QC + q;
-    float4 in[G::NIN];
+    float4 wv[K];
 #pragma unroll
-    for (int j = 0; j < G::NIN; ++j) in[j] = row[j * QC];
+    for (int kx = 0; kx < K; ++kx) wv[kx] = wsm[(ky * K + kx) * QC + q];
 #pragma unroll
-    for (int kx = 0; kx < K; ++kx) {
-      const float4 wv = wsm[(ky * K + kx) * QC + q];
+    for (int j = 0; j < G::NIN; ++j) {     // sliding window: input j feeds output (j - kx) / S for every tap kx
+      const float4 v = row[j * QC];
 #pragma unroll
-      for (int j = 0; j < 7; ++j) fma4(acc[j], in[j * S + kx], wv);
+      for (int kx = 0; kx < K; ++kx) {
+        const int t = j - kx;
+        if (t >= 0 && t % S == 0 && t / S < 7) fma4(acc[t / S], v, wv[kx]);
+      }
     }
   }
   const int gy = ty0 + oy;
@@ -353,50 +365,48 @@ __global__ void __launch_bounds__(DwGeom<K, S>::NT) dw_wgrad_kernel(const float*
   const bool cvalid = c0 + q * 4 < C;
   dw_stage_input<K, S>(tile, x, a, b, img, H, W, C, c0, ty0 * S - pad_t, tx0 * S - pad_l);
   __syncthreads();
-  float4 wacc[K * K];
-#pragma unroll
-  for (int t = 0; t < K * K; ++t) wacc[t] = f4s(0.f);
-  if (strip < G::NSTRIP) {
-    const int oy = strip / G::SPR, ox0 = (strip % G::SPR) * 7;
-    float4 g[7];
+  float4* red = smem4 + G::TI * G::TI * QC;  // [K*K][NW][QC]
+  const int warp = tid >> 5, lane = tid & 31;
+  const bool active = strip < G::NSTRIP;     // S == 2: the last 8 threads only take part in the shuffles
+  const int oy = active ? strip / G::SPR : 0, ox0 = active ? (strip % G::SPR) * 7 : 0;
+  float4 g[7];
+  {
     const int gy = ty0 + oy;
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
       const int gx = tx0 + ox0 + j;
-      g[j] = (cvalid && gy < Ho && gx < Wo) ? ld4(dy + (((size_t)img * Ho + gy) * Wo + gx) * C + c0 + q * 4)
-                                             : f4s(0.f);
-    }
-#pragma unroll
-    for (int ky = 0; ky < K; ++ky) {
-      const float4* row = tile + ((size_t)(oy * S + ky) * G::TI + ox0 * S) * QC + q;
-      float4 in[G::NIN];
-#pragma unroll
-      for (int j = 0; j < G::NIN; ++j) in[j] = row[j * QC];
-#pragma unroll
-      for (int kx = 0; kx < K; ++kx)
-#pragma unroll
-        for (int j = 0; j < 7; ++j) fma4(wacc[ky * K + kx], in[j * S + kx], g[j]);
+      g[j] = (active && cvalid && gy < Ho && gx < Wo) ? ld4(dy + (((size_t)img * Ho + gy) * Wo + gx) * C + c0 + q * 4)
+                                                      : f4s(0.f);
     }
   }
-  // reduce across the 4 strips of a warp (lane = strip_local*8 + q), then across warps via smem
 #pragma unroll
-  for (int t = 0; t < K * K; ++t) {
-    float4 v = wacc[t];
+  for (int ky = 0; ky < K; ++ky) {
+    const float4* row = tile + ((size_t)(oy * S + ky) * G::TI + ox0 * S) * QC + q;
+    float4 wrow[K];
 #pragma unroll
-    for (int o = 8; o <= 16; o <<= 1) {
-      v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
-      v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
-      v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
-      v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+    for (int kx = 0; kx < K; ++kx) wrow[kx] = f4s(0.f);
+#pragma unroll
+    for (int j = 0; j < G::NIN; ++j) {
+      const float4 v = row[j * QC];
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const int t = j - kx;
+        if (t >= 0 && t % S == 0 && t / S < 7) fma4(wrow[kx], v, g[t / S]);
+      }
     }
-    wacc[t] = v;
-  }
-  __syncthreads();   // everyone is done reading the tile: reuse it as reduction scratch
-  float4* red = smem4;  // [K*K][NW][QC]
-  const int warp = tid >> 5, lane = tid & 31;
-  if (lane < QC) {
+    // reduce across the 4 strips of a warp (lane = strip_local*8 + q); across warps via smem below
 #pragma unroll
-    for (int t = 0; t < K * K; ++t) red[((size_t)t * NW + warp) * QC + lane] = wacc[t];
+    for (int kx = 0; kx < K; ++kx) {
+      float4 v = wrow[kx];
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+        v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
+        v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+      }
+      if (lane < QC) red[((size_t)(ky * K + kx) * NW + warp) * QC + lane] = v;
+    }
   }
   __syncthreads();
   for (int i = tid; i < K * K * QC; i += G::NT) {
@@ -415,12 +425,12 @@ static void dw_wgrad_launch(const float* x, const float* a, const float* b, cons
   using G = DwGeom<K, S>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(dw_wgrad_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes());
+    cudaFuncSetAttribute(dw_wgrad_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::wgrad_smem_bytes());
     attr_done = true;
   }
   const int tiles_x = cdiv(Wo, G::TO), tiles_y = cdiv(Ho, G::TO), tiles = tiles_x * tiles_y;
   dim3 grid(tiles, cdiv(C, QC * 4), B);
-  MLIIS_COUNT(), dw_wgrad_kernel<K, S><<<grid, G::NT, G::smem_bytes(), s>>>(x, a, b, dy, partials, H, W, C, Ho, Wo, pad_t, pad_l,
+  MLIIS_COUNT(), dw_wgrad_kernel<K, S><<<grid, G::NT, G::wgrad_smem_bytes(), s>>>(x, a, b, dy, partials, H, W, C, Ho, Wo, pad_t, pad_l,
                                                              tiles_x, tiles);
   reduce_partials(partials, B * tiles, K * K * C, dw, s);
 }
