@@ -71,11 +71,22 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int ld, int M, int 
   const int r0 = blockIdx.x * rows_per_chunk;
   const int r1 = min(M, r0 + rows_per_chunk);
   float4 s = f4s(0.f), ss = f4s(0.f);
-  for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-    float4 v = ld4(x + (size_t)r * ld + cq * 4);
-    if (PRE_SWISH) v = swish4(v);
-    s = s + v;
-    fma4(ss, v, v);
+  constexpr int U = 4;   // rows in flight per thread (loads issued before any is consumed; same summation order)
+  for (int rb = r0 + threadIdx.y; rb < r1; rb += U * blockDim.y) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = rb + u * blockDim.y;
+      if (r < r1) v[u] = ld4(x + (size_t)r * ld + cq * 4);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (rb + u * blockDim.y < r1) {
+        const float4 w = PRE_SWISH ? swish4(v[u]) : v[u];
+        s = s + w;
+        fma4(ss, w, w);
+      }
+    }
   }
   block_reduce2(s, ss, sm);
   if (threadIdx.y == 0) {
@@ -214,12 +225,27 @@ __global__ void img_reduce_kernel(const float* __restrict__ x, int ldx, const fl
   if (MODE != 2) { av = ld4(a + cq * 4); bv = ld4(b + cq * 4); }
   const int r0 = blockIdx.x * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
   float4 s = f4s(0.f);
-  for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-    size_t row = (size_t)img * HW + r;
-    float4 v = ld4(x + row * ldx + cq * 4);
-    if (MODE != 2) v = swish4(affine4(v, av, bv));
-    if (MODE == 1) v = v * ld4(g + row * ldg + cq * 4);
-    s = s + v;
+  constexpr int U = 4;
+  for (int rb = r0 + threadIdx.y; rb < r1; rb += U * blockDim.y) {
+    float4 v[U], gv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = rb + u * blockDim.y;
+      if (r < r1) {
+        const size_t row = (size_t)img * HW + r;
+        v[u] = ld4(x + row * ldx + cq * 4);
+        if (MODE == 1) gv[u] = ld4(g + row * ldg + cq * 4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (rb + u * blockDim.y < r1) {
+        float4 w = v[u];
+        if (MODE != 2) w = swish4(affine4(w, av, bv));
+        if (MODE == 1) w = w * gv[u];
+        s = s + w;
+      }
+    }
   }
   block_reduce1(s, sm);
   if (threadIdx.y == 0) st4(partial + ((size_t)img * G + blockIdx.x) * C + cq * 4, s);
@@ -381,10 +407,9 @@ void se_fc_bwd(const float* partial, int G, int B, int HW, int C, int Cr, const 
 // BN backward (train mode): dgamma = sum g*xhat, dbeta = sum g, dx = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat))
 // ------------------------------------------------------------------------------------------------
 template <int VAR>
-__device__ __forceinline__ void bn_bwd_elem(const BnBwdArgs& p, size_t r, int cq, float4 mean, float4 rstd, float4 av,
-                                            float4 bv, float4& geff, float4& xhat, float4& post) {
-  float4 x = ld4(p.x + r * p.ldx + cq * 4);
-  float4 g = ld4(p.g + r * p.ldg + cq * 4);
+__device__ __forceinline__ void bn_bwd_elem(const BnBwdArgs& p, size_t r, int cq, float4 x, float4 g, float4 mean,
+                                            float4 rstd, float4 av, float4 bv, float4& geff, float4& xhat,
+                                            float4& post) {
   post = f4s(1.f);
   if (VAR == BN_PLAIN) {
     if (p.dcs) g = g * p.dcs[r / p.HW];
@@ -413,11 +438,24 @@ __global__ void bn_bwd_reduce_kernel(BnBwdArgs p, int rows_per_chunk) {
   const float4 av = ld4(p.a + cq * 4), bv = ld4(p.b + cq * 4);
   const int r0 = blockIdx.x * rows_per_chunk, r1 = min(p.M, r0 + rows_per_chunk);
   float4 s0 = f4s(0.f), s1 = f4s(0.f);
-  for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-    float4 ge, xh, po;
-    bn_bwd_elem<VAR>(p, (size_t)r, cq, mean, rstd, av, bv, ge, xh, po);
-    s0 = s0 + ge;
-    fma4(s1, ge, xh);
+  constexpr int U = 4;     // rows in flight per thread: the 2*U loads are issued before any is consumed
+  for (int rb = r0 + threadIdx.y; rb < r1; rb += U * blockDim.y) {
+    float4 x[U], g[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = rb + u * blockDim.y;
+      if (r < r1) { x[u] = ld4(p.x + (size_t)r * p.ldx + cq * 4); g[u] = ld4(p.g + (size_t)r * p.ldg + cq * 4); }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = rb + u * blockDim.y;
+      if (r < r1) {
+        float4 ge, xh, po;
+        bn_bwd_elem<VAR>(p, (size_t)r, cq, x[u], g[u], mean, rstd, av, bv, ge, xh, po);
+        s0 = s0 + ge;
+        fma4(s1, ge, xh);
+      }
+    }
   }
   block_reduce2(s0, s1, sm);
   if (threadIdx.y == 0) {
@@ -457,12 +495,25 @@ __global__ void bn_bwd_apply_kernel(BnBwdArgs p, int rows_per_block) {
   const float4 ga = ld4(p.gamma + cq * 4) * rstd;
   const float4 k1 = ld4(p.k + cq * 4), k2 = ld4(p.k + p.C + cq * 4);
   const int r0 = blockIdx.x * rows_per_block, r1 = min(p.M, r0 + rows_per_block);
-  for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-    float4 ge, xh, po;
-    bn_bwd_elem<VAR>(p, (size_t)r, cq, mean, rstd, av, bv, ge, xh, po);
-    float4 d = ga * (ge - k1 - xh * k2);
-    if (VAR == BN_DEC) d = d * po;
-    st4(p.dx + (size_t)r * p.lddx + cq * 4, d);
+  constexpr int U = 4;     // == rows_per_block / blockDim.y: all loads of the block are in flight before the stores
+  for (int rb = r0 + threadIdx.y; rb < r1; rb += U * blockDim.y) {
+    float4 x[U], g[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = rb + u * blockDim.y;
+      if (r < r1) { x[u] = ld4(p.x + (size_t)r * p.ldx + cq * 4); g[u] = ld4(p.g + (size_t)r * p.ldg + cq * 4); }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = rb + u * blockDim.y;
+      if (r < r1) {
+        float4 ge, xh, po;
+        bn_bwd_elem<VAR>(p, (size_t)r, cq, x[u], g[u], mean, rstd, av, bv, ge, xh, po);
+        float4 d = ga * (ge - k1 - xh * k2);
+        if (VAR == BN_DEC) d = d * po;
+        st4(p.dx + (size_t)r * p.lddx + cq * 4, d);
+      }
+    }
   }
 }
 
