@@ -5,8 +5,8 @@ Drop-in for /root/reference/run_metasegnet.py: same flags (mliis_b200/args.py), 
 model, load the tasks, restore the checkpoint or meta-train, evaluate on the training and meta-test tasks, print
 the greppable summary line and write <checkpoint>/meta-test_results.json.
 
-Differences: the task shards are synthetic FSS-1000-shaped tasks unless tfrecord shards are readable
-(`--synthetic_tasks N`, or no --data-dir); hyper-parameter search and the k-shot-curve experiment are out of
+Differences: tasks come from the gzip-TFRecord shards under --data-dir when there are any (read without
+TensorFlow, mliis_b200/fss1000.py), else they are synthetic FSS-1000-shaped tasks (`--synthetic_tasks N`); hyper-parameter search and the k-shot-curve experiment are out of
 scope.  Multi-GPU: launch with torchrun - tasks are sharded across ranks (mliis_b200/reptile.py).
 """
 import datetime
@@ -22,6 +22,7 @@ def main():
     from mliis_b200.efficientlab import EfficientLab
     from mliis_b200.eval import evaluate_gecko
     from mliis_b200.lr_schedulers import supported_learning_rate_schedulers
+    from mliis_b200.fss1000 import get_fss_tasks, read_fss_1000_dataset
     from mliis_b200.metaseg import read_synthetic_dataset
     from mliis_b200.session import Session
     from mliis_b200.train import train_gecko
@@ -61,11 +62,27 @@ def main():
     print("FOMAML" if args.foml else "Reptile")
 
     print("Setting up meta-learning dataset")
-    n_test = args.synthetic_tasks or 240
-    train_set, val_set, test_set, _, _, test_task_names = read_synthetic_dataset(
-        num_train_tasks=max(8, 760 if not args.synthetic_tasks else 4 * n_test), num_test_tasks=n_test,
-        n_examples=max(10, args.shots + 5, (args.train_shots or 0)), image_size=args.image_size)
-    val_set = None
+    data_dir = getattr(args, "data_dir", None)
+    have_shards = bool(data_dir) and os.path.isdir(data_dir) and len(get_fss_tasks(data_dir)) > 0
+    if have_shards and not args.synthetic_tasks:
+        # run_metasegnet.py:84-96: gzip-TFRecord shards, one per class (mliis_b200/fss1000.py, no TensorFlow)
+        if args.fp_k_test_set:
+            ids_file = os.path.join(data_dir, "fp-k_test_set.txt")
+            if not os.path.exists(ids_file):
+                raise FileNotFoundError("--fp_k_test_set needs %s (the reference's data/fp-k_test_set.txt)" % ids_file)
+            print("Holding out FP-k classes listed in {}".format(ids_file))
+            dataset = read_fss_1000_dataset(data_dir, num_val_tasks=args.num_val_tasks, test_task_ids=ids_file,
+                                            image_size=args.image_size)
+        else:
+            dataset = read_fss_1000_dataset(data_dir, num_val_tasks=args.num_val_tasks, image_size=args.image_size)
+        train_set, val_set, test_set, _, _, test_task_names = dataset
+    else:
+        n_test = args.synthetic_tasks or 240
+        train_set, val_set, test_set, _, _, test_task_names = read_synthetic_dataset(
+            num_train_tasks=max(8, 760 if not args.synthetic_tasks else 4 * n_test), num_test_tasks=n_test,
+            n_examples=max(10, args.shots + 5, (args.train_shots or 0)), image_size=args.image_size)
+    if not val_set:
+        val_set = None
     validate_datasets(args, train_set, val_set, test_set)
     if verbose:
         print("Found {} testing tasks:".format(len(test_set)))
