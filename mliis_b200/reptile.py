@@ -56,9 +56,13 @@ class Gecko:
         self.eval_sample_number = 0
         self.lr_scheduler = lr_scheduler
         if augment:
-            raise NotImplementedError("numpy augmentations (augmenters/np_augmenters.py) are out of scope: they use "
-                                      "the unseeded np.random stream; parity configs run with --augment off")
-        self.augmenter = None
+            # host numpy augmentations (reptile.py:48-52): every batch goes through host arrays, so the Session path
+            # is used; the device fast path is for un-augmented (parity / benchmark) configurations
+            from .np_augmenters import Augmenter
+            self.augmenter = Augmenter()
+            fast_path = False
+        else:
+            self.augmenter = None
         self.aug_rate = aug_rate
         self.fast_path = fast_path
         self._runner = None
@@ -301,6 +305,153 @@ class Gecko:
         print("Mean task IoU: {}".format(class_iou))
         self._full_state.restore(snap)             # import_variables(old_vars) (reptile.py:293)
         return class_iou
+
+    # ------------------------------------------------------------------------------------------
+    # early stopping / k-shot learning curves (reptile.py:296-480)
+    # ------------------------------------------------------------------------------------------
+    def _run_minimize(self, minimize_op, input_ph, label_ph, inputs, labels, inner_iter, lr_ph, lr, lr_scheduler,
+                      drop_rate_ph, drop_rate):
+        feed = {input_ph: inputs, label_ph: labels}
+        if (lr_ph is not None) and (lr is not None) and (drop_rate_ph is not None) and (drop_rate is not None):
+            feed[drop_rate_ph] = drop_rate
+            feed[lr_ph] = lr
+        elif (lr_ph is not None) and (lr is not None):
+            feed[lr_ph] = lr
+        elif (lr_ph is not None) and (lr_scheduler is not None):
+            feed[lr_ph] = lr_scheduler.cur_lr(cur_step=inner_iter)
+        self.session.run(minimize_op, feed_dict=feed)
+
+    def _early_stopping_learn(self, train_set, val_set, input_ph, label_ph, minimize_op, predictions,
+                              inner_batch_size, min_steps, max_steps, replacement, is_training_ph=None, lr_ph=None,
+                              lr_scheduler=None, lr=None, drop_rate_ph=None, drop_rate=None, patience=50,
+                              inner_iters=None, aug_rate: Optional[float] = None):
+        """Estimates the number of steps to take when learning a new task: adapt up to max_steps, predict the
+        validation images and score them after EVERY step (one eval-mode forward + fused threshold on the device),
+        stop after `patience` non-improving evaluations (reptile.py:443-480)."""
+        from .hyperparam_search import EarlyStopper
+        del inner_iters
+        if lr_scheduler is not None and lr is not None:
+            raise ValueError("Only lr_scheduler or lr should be speced. Not both.")
+        snap = self._full_state.snapshot()
+        early_stopper = EarlyStopper(patience, min_steps=min_steps)
+        for inner_iter, batch in enumerate(_mini_batches(train_set, inner_batch_size, num_batches=max_steps,
+                                                         replacement=replacement, augmenter=self.augmenter,
+                                                         aug_rate=aug_rate)):
+            inputs, labels = zip(*batch)
+            if self._pre_step_op:
+                self.session.run(self._pre_step_op)
+            self._run_minimize(minimize_op, input_ph, label_ph, inputs, labels, inner_iter, lr_ph, lr, lr_scheduler,
+                               drop_rate_ph, drop_rate)
+            test_preds = self._test_predictions(train_set, val_set, input_ph, predictions, is_training_ph)
+            ious = [self._iou(test_preds[j], val_set[j][1]) for j in range(len(test_preds))]
+            miou = np.nanmean(ious)
+            if not early_stopper.continue_training(miou, inner_iter + 1):
+                break
+        best_num_steps = early_stopper.best_num_steps()
+        best_iou = early_stopper.best_metric()
+        print("Best iteration found: {}, with mean-IoU {}".format(best_num_steps, best_iou))
+        self._full_state.restore(snap)
+        return best_num_steps, best_iou
+
+    def evaluate_with_early_stopping(self, dataset, input_ph, label_ph, minimize_op, predictions, num_classes,
+                                     num_shots, inner_batch_size, min_steps, max_steps, replacement,
+                                     eval_all_tasks=False, num_tasks_to_sample=20,
+                                     test_shots=DEFAULT_NUM_TEST_EXAMPLES, is_training_ph=None, lr_ph=None,
+                                     lr: Optional[float] = None, drop_rate_ph=None, drop_rate: Optional[float] = None,
+                                     aug_rate: Optional[float] = None,
+                                     eval_tasks_with_median_early_stopping_iterations: bool = False
+                                     ) -> Tuple[List[str], List[int], List[float]]:
+        """Samples few-shot tasks, finds each one's best step count by early stopping on its held-out shots and
+        returns (task names, best step counts, IoUs) (reptile.py:296-391)."""
+        print("Evaluating {} meta-learning.".format(self.meta_fn))
+        if eval_all_tasks:
+            sampled_tasks = dataset
+        else:
+            random.shuffle(dataset)
+            sampled_tasks = dataset[:num_tasks_to_sample]
+        print("Evaluating {} {}-shot tasks.".format(len(sampled_tasks), num_shots))
+        task_names, ious = [], []
+        if min_steps != max_steps:
+            num_steps = []
+            for sampled_task in sampled_tasks:
+                sampled, task_name = _sample_mini_image_segmentation_dataset(
+                    self.session, [sampled_task], num_classes, num_shots + test_shots, return_task_name=True)
+                task_names.append(task_name)
+                train_set, test_set = _split_train_test_segmentation(sampled, test_shots)
+                best_n_steps, best_miou = self._early_stopping_learn(
+                    train_set, test_set, input_ph, label_ph, minimize_op, predictions, inner_batch_size,
+                    min_steps=min_steps, max_steps=max_steps, replacement=replacement, is_training_ph=is_training_ph,
+                    lr_ph=lr_ph, lr_scheduler=self.lr_scheduler, lr=lr, drop_rate_ph=drop_rate_ph,
+                    drop_rate=drop_rate, aug_rate=aug_rate)
+                ious.append(best_miou)
+                num_steps.append(best_n_steps)
+            estimated_best_num_steps = int(np.median(num_steps))
+        else:
+            estimated_best_num_steps = min_steps
+            num_steps = [estimated_best_num_steps] * len(sampled_tasks)
+        if eval_tasks_with_median_early_stopping_iterations or min_steps == max_steps:
+            print("Estimated best number of steps {}".format(estimated_best_num_steps))
+            mean_iou_score, task_iou_map = self.evaluate(
+                dataset=sampled_tasks, input_ph=input_ph, label_ph=label_ph, minimize_op=minimize_op,
+                predictions=predictions, num_classes=num_classes, num_shots=num_shots,
+                inner_batch_size=inner_batch_size, inner_iters=estimated_best_num_steps, replacement=replacement,
+                eval_all_tasks=eval_all_tasks, num_tasks_to_sample=num_tasks_to_sample, test_shots=test_shots,
+                is_training_ph=is_training_ph, lr_ph=lr_ph, lr=lr, drop_rate_ph=drop_rate_ph, drop_rate=drop_rate,
+                aug_rate=aug_rate)
+            task_names = list(task_iou_map.keys())
+            ious = list(task_iou_map.values())
+        else:
+            mean_iou_score = np.nanmean(ious)
+        print("Evaluated {} task/s".format(len(sampled_tasks)))
+        print("Mean IoU from train on {} images and evaluate on {} test images: {}".format(num_shots, test_shots,
+                                                                                             mean_iou_score))
+        return task_names, num_steps, ious
+
+    def evaluate_m_k_shot_ranges_all_tasks(self, tasks, k_range, m, input_ph, label_ph, minimize_op, predictions,
+                                           inner_batch_size, inner_iters, replacement, is_training_ph=None,
+                                           lr_ph=None, lr=None, test_samples=20, iter_range=DEFAULT_ITER_RANGE,
+                                           aug_rate: float = 0.5):
+        """m repetitions of the k-shot sweep for every task (reptile.py:393-407)."""
+        assert len(iter_range) == len(k_range)
+        params = {"input_ph": input_ph, "label_ph": label_ph, "minimize_op": minimize_op, "predictions": predictions,
+                  "inner_batch_size": inner_batch_size, "inner_iters": inner_iters, "replacement": replacement,
+                  "is_training_ph": is_training_ph, "lr_ph": lr_ph, "lr": lr, "aug_rate": aug_rate}
+        ks, results = [], []
+        for task in tasks:
+            for _ in range(m):
+                res = self.evaluate_k_shot_range(task, k_range=k_range, iter_range=iter_range,
+                                                 test_samples=test_samples, **params)
+                print("k-shot results {}".format({k: r for k, r in zip(k_range, res)}))
+                results.extend(res)
+                ks.extend(k_range)
+        return ks, results
+
+    def evaluate_k_shot_range(self, task, k_range, iter_range=DEFAULT_ITER_RANGE, test_samples=20,
+                              early_stopping_min_val_samples=5, esimate_inner_iters_with_early_stoppping: bool = True,
+                              **params):
+        """k-shot results of ONE task over a range of ks; from k = 2 * early_stopping_min_val_samples on, 20 % of the
+        training shots are held out to estimate the step count by early stopping (reptile.py:409-441).  As in the
+        reference, the estimated step count then sticks for the larger ks until it is re-estimated."""
+        mious = []
+        sampled_task, task_name = _sample_mini_image_segmentation_dataset(
+            self.session, [task], num_classes=1, num_shots=max(k_range) + test_samples, return_task_name=True)
+        training_examples, test_set = _split_train_test_segmentation(sampled_task, test_shots=test_samples)
+        for i, k in enumerate(k_range):
+            print("Evaluating {}-shot learning".format(k))
+            train_set = training_examples[:k]
+            if esimate_inner_iters_with_early_stoppping:
+                if k >= early_stopping_min_val_samples * 2:
+                    val_shots = int(0.2 * k)
+                    print("Split training dataset into {} train shots and {} val shots for early stopping to "
+                          "estimate number of steps.".format(k - val_shots, val_shots))
+                    d_tr, d_val = _split_train_test_segmentation(train_set, test_shots=val_shots)
+                    inner_iters, _ = self._early_stopping_learn(d_tr, d_val, min_steps=1, max_steps=500, **params)
+                    params["inner_iters"] = inner_iters
+            else:
+                params["inner_iters"] = iter_range[i]
+            mious.append(self._evaluate(train_set, test_set, **params))
+        print("Evaluated task {} over k-range {}".format(task_name, k_range))
+        return mious
 
     def _test_predictions(self, train_set, test_set, input_ph, predictions, is_training_ph=None,
                           task_name: Optional[str] = None):

@@ -152,3 +152,99 @@ def test_evaluate_gecko_and_train_gecko_with_checkpoints(tmp_path):
     assert torch.equal(state[:eng.n_theta], s2[:eng.n_theta])
     assert torch.equal(state[eng.o_bn:eng.o_bn + 2 * eng.n_bn], s2[eng.o_bn:eng.o_bn + 2 * eng.n_bn])
     assert torch.equal(state[eng.o_v:eng.o_pow + 2], s2[eng.o_v:eng.o_pow + 2])
+
+
+def test_early_stopping_k_shot_curves_and_uho(tmp_path):
+    """SURVEY 8f-4 drivers on the real engine: early stopping scores the held-out shots after EVERY inner step."""
+    from mliis_b200.eval import optimize_update_hyperparams, run_k_shot_learning_curves_experiment
+    from mliis_b200.reptile import Gecko
+    from mliis_b200.session import Session
+    m = _model()
+    sess = Session(m)
+    _warm(sess, m, 4)
+    state0 = m.engine().states[0].clone()
+    g = Gecko(sess, transductive=True)
+    tasks = _tasks(3, 500, n_examples=12)
+    random.seed(1)
+    names, steps, ious = g.evaluate_with_early_stopping(
+        tasks, m.input_ph, m.label_ph, m.minimize_op, m.predictions, num_classes=1, num_shots=5, inner_batch_size=4,
+        min_steps=1, max_steps=6, replacement=False, eval_all_tasks=True, test_shots=5,
+        is_training_ph=m.is_training_ph, lr_ph=m.lr_ph, lr=1e-3)
+    assert names == [t.name for t in tasks] and len(steps) == 3 and len(ious) == 3
+    assert all(1 <= s <= 6 for s in steps) and all(0.0 <= v <= 1.0 for v in ious)
+    assert torch.equal(m.engine().states[0], state0)          # every task starts from, and restores, the same state
+    # min_steps == max_steps degenerates to a plain evaluation with that many steps
+    random.seed(1)
+    n2, s2, i2 = g.evaluate_with_early_stopping(
+        tasks, m.input_ph, m.label_ph, m.minimize_op, m.predictions, num_classes=1, num_shots=5, inner_batch_size=4,
+        min_steps=2, max_steps=2, replacement=False, eval_all_tasks=True, test_shots=5,
+        is_training_ph=m.is_training_ph, lr_ph=m.lr_ph, lr=1e-3)
+    random.seed(1)
+    mean_iou, iou_map = g.evaluate(tasks, m.input_ph, m.label_ph, m.minimize_op, m.predictions, num_classes=1,
+                                   num_shots=5, inner_batch_size=4, inner_iters=2, replacement=False,
+                                   eval_all_tasks=True, test_shots=5, is_training_ph=m.is_training_ph, lr_ph=m.lr_ph,
+                                   lr=1e-3)
+    assert s2 == [2, 2, 2] and list(i2) == list(iou_map.values())
+    # k-shot learning curves (small k range; 20 % of the shots validate the step count from k = 4 on)
+    csv_path = str(tmp_path / "k.csv")
+    random.seed(2)
+    ks, res = run_k_shot_learning_curves_experiment(
+        sess, m, tasks[:1], eval_inner_batch_size=4, eval_inner_iters=2, num_samples=1, lr=1e-3, augment=False,
+        csv_outpath=csv_path, k_range=[1, 2, 6], iter_range=[1, 2, 3], test_samples=4)
+    assert ks == [1, 2, 6] and len(res) == 3 and all(0.0 <= v <= 1.0 for v in res)
+    assert open(csv_path).read().splitlines()[0] == "k,mIoU"
+    assert torch.equal(m.engine().states[0], state0)
+    # update-hyperparameter optimisation: 3 configurations on 2 validation tasks
+    random.seed(3)
+    lr, n_steps = optimize_update_hyperparams(
+        sess, m, tasks[:2], num_shots=5, eval_inner_batch_size=4, transductive=True, lr=None,
+        lr_search_range_low=5e-4, lr_search_range_high=5e-3, drop_rate=None, drop_rate_search_range_low=0.2,
+        drop_rate_search_range_high=0.2, min_steps=0, max_steps=3, num_configs_to_sample=3, save_dir=str(tmp_path),
+        seed=0)
+    assert 5e-4 <= lr <= 5e-3 and 1 <= n_steps <= 3
+    assert any(f.startswith("GP_val-set_hyper_param_search_results_5-shot") for f in os.listdir(str(tmp_path)))
+
+
+def test_augmented_adaptation_runs_on_the_session_path():
+    from mliis_b200.reptile import Gecko
+    from mliis_b200.session import Session
+    m = _model()
+    sess = Session(m)
+    _warm(sess, m, 2)
+    g = Gecko(sess, transductive=True, augment=True, aug_rate=0.5)
+    assert g.augmenter is not None and not g.fast_path
+    random.seed(0)
+    np.random.seed(0)
+    mean_iou, iou_map = g.evaluate(_tasks(2, 600), m.input_ph, m.label_ph, m.minimize_op, m.predictions,
+                                   num_classes=1, num_shots=5, inner_batch_size=4, inner_iters=2, replacement=False,
+                                   eval_all_tasks=True, test_shots=5, is_training_ph=m.is_training_ph, lr_ph=m.lr_ph,
+                                   lr=1e-3)
+    assert len(iou_map) == 2 and 0.0 <= mean_iou <= 1.0
+
+
+def test_tfrecord_tasks_equal_synthetic_tasks_on_the_device_fast_path(tmp_path):
+    """FSS-1000 shard reader: the same records through gzip-TFRecords give bit-identical IoUs."""
+    from mliis_b200 import fss1000
+    from mliis_b200.reptile import Gecko
+    from mliis_b200.session import Session
+    from mliis_b200.synthetic import make_task_arrays
+    m = _model()
+    sess = Session(m)
+    _warm(sess, m, 3)
+    syn = _tasks(3, 700)
+    for t in syn:
+        iu8, mu8 = make_task_arrays(t.task_id, 10, SIZE)
+        fss1000.write_task_shard(str(tmp_path / (t.name + ".tfrecord.gzip")), iu8, mu8)
+    _, _, rec, _, _, names = fss1000.read_fss_1000_dataset(
+        str(tmp_path), test_task_ids=[t.name for t in syn], image_size=SIZE)
+    rec = sorted(rec, key=lambda t: t.name)
+    assert [t.name for t in rec] == [t.name + ".tfrecord.gzip" for t in syn] and all(t.batch_size == 10 for t in rec)
+    g = Gecko(sess, transductive=True)
+    out = []
+    for tasks in (syn, rec):
+        random.seed(4)
+        out.append(g.evaluate(list(tasks), m.input_ph, m.label_ph, m.minimize_op, m.predictions, num_classes=1,
+                              num_shots=5, inner_batch_size=4, inner_iters=3, replacement=False, eval_all_tasks=True,
+                              test_shots=5, is_training_ph=m.is_training_ph, lr_ph=m.lr_ph, lr=1e-3))
+    assert out[0][0] == out[1][0]
+    assert list(out[0][1].values()) == list(out[1][1].values())
