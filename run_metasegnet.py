@@ -6,8 +6,9 @@ model, load the tasks, restore the checkpoint or meta-train, evaluate on the tra
 the greppable summary line and write <checkpoint>/meta-test_results.json.
 
 Differences: tasks come from the gzip-TFRecord shards under --data-dir when there are any (read without
-TensorFlow, mliis_b200/fss1000.py), else they are synthetic FSS-1000-shaped tasks (`--synthetic_tasks N`); hyper-parameter search and the k-shot-curve experiment are out of
-scope.  Multi-GPU: launch with torchrun - tasks are sharded across ranks (mliis_b200/reptile.py).
+TensorFlow, mliis_b200/fss1000.py), else they are synthetic FSS-1000-shaped tasks (`--synthetic_tasks N`); the
+update-hyperparameter search uses a scikit-learn GP instead of scikit-optimize (mliis_b200/hyperparam_search.py).
+Multi-GPU: launch with torchrun - tasks are sharded across ranks (mliis_b200/reptile.py).
 """
 import datetime
 import json
@@ -18,11 +19,12 @@ import numpy as np
 
 
 def main():
-    from mliis_b200.args import argument_parser, evaluate_kwargs, model_kwargs, train_kwargs
+    from mliis_b200.args import argument_parser, evaluate_kwargs, hyper_search_kwargs, model_kwargs, train_kwargs
     from mliis_b200.efficientlab import EfficientLab
-    from mliis_b200.eval import evaluate_gecko
+    from mliis_b200.eval import (evaluate_gecko, optimize_update_hyperparams,
+                                 run_k_shot_learning_curves_experiment)
     from mliis_b200.lr_schedulers import supported_learning_rate_schedulers
-    from mliis_b200.fss1000 import get_fss_tasks, read_fss_1000_dataset
+    from mliis_b200.fss1000 import get_fss_tasks, read_fp_k_shot_dataset, read_fss_1000_dataset
     from mliis_b200.metaseg import read_synthetic_dataset
     from mliis_b200.session import Session
     from mliis_b200.train import train_gecko
@@ -34,8 +36,9 @@ def main():
     start_time = datetime.datetime.now()
     print("Experiment started at: {}".format(start_time))
     args = argument_parser().parse_args()
-    if args.optimize_update_hyperparms_on_val_set or args.run_k_shot_learning_curves_experiment:
-        raise NotImplementedError("hyper-parameter search / k-shot curves are out of scope (SURVEY.md 8f-4)")
+    if args.optimize_update_hyperparms_on_val_set:
+        assert args.num_val_tasks > 0, \
+            "Must specify number of validation tasks greater than 0 to optimize update hyperparams."
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
@@ -64,7 +67,10 @@ def main():
     print("Setting up meta-learning dataset")
     data_dir = getattr(args, "data_dir", None)
     have_shards = bool(data_dir) and os.path.isdir(data_dir) and len(get_fss_tasks(data_dir)) > 0
-    if have_shards and not args.synthetic_tasks:
+    if have_shards and not args.synthetic_tasks and args.run_k_shot_learning_curves_experiment:
+        test_set, test_task_names = read_fp_k_shot_dataset(data_dir, image_size=args.image_size)   # :80-83
+        train_set, val_set = None, None
+    elif have_shards and not args.synthetic_tasks:
         # run_metasegnet.py:84-96: gzip-TFRecord shards, one per class (mliis_b200/fss1000.py, no TensorFlow)
         if args.fp_k_test_set:
             ids_file = os.path.join(data_dir, "fp-k_test_set.txt")
@@ -86,7 +92,8 @@ def main():
     validate_datasets(args, train_set, val_set, test_set)
     if verbose:
         print("Found {} testing tasks:".format(len(test_set)))
-        print("Found {} training tasks:".format(len(train_set)))
+        if train_set is not None:
+            print("Found {} training tasks:".format(len(train_set)))
 
     with Session(model) as sess:
         if restore_ckpt_dir is not None and not args.pretrained:
@@ -111,7 +118,42 @@ def main():
                 Saver(model).restore(sess, ckpt)
 
         eval_kwargs = evaluate_kwargs(args)
+        if args.optimize_update_hyperparms_on_val_set:                       # run_metasegnet.py:136-165
+            print("Optimizing the update routine hyperparams on the val set")
+            assert val_set and len(val_set) > 0, "Dev set has no tasks"
+            keep = eval_kwargs["save_fine_tuned_checkpoints"]
+            eval_kwargs["save_fine_tuned_checkpoints"] = False
+            # (the reference also passes b=args.uho_outer_iters, which its own function does not accept)
+            estimated_lr, estimated_steps = optimize_update_hyperparams(
+                sess, model, val_set, lr_scheduler=lr_scheduler,
+                serially_eval_all_tasks=args.serially_eval_all_test_tasks,
+                num_configs_to_sample=args.num_configs_to_sample, save_dir=args.checkpoint,
+                results_csv_name=args.uho_results_csv_name,
+                num_train_val_data_splits_to_sample_per_config=1 if args.fss_1000 else 4,
+                max_steps=args.max_steps, min_steps=args.min_steps, **eval_kwargs, **hyper_search_kwargs(args))
+            eval_kwargs["save_fine_tuned_checkpoints"] = keep
+            eval_kwargs["eval_inner_iters"] = estimated_steps
+            eval_kwargs["lr"] = estimated_lr
+            if args.meta_fine_tune_steps_on_train_val > 0:
+                print("Fine-tuning meta-learned init for {} meta-steps with optimized hyperparameters.".format(
+                    args.meta_fine_tune_steps_on_train_val))
+                tp = train_kwargs(args)
+                tp["inner_iters"], tp["lr"] = estimated_steps, estimated_lr
+                tp["meta_step_size"] = tp["meta_step_size_final"]
+                train_gecko(sess, model, train_set + val_set, test_set,
+                            os.path.join(args.checkpoint, "fine-tuned_on_train_val_with_optimized_update_hyperparams"),
+                            lr_scheduler=lr_scheduler, augment=args.augment, **tp)
         del eval_kwargs["eval_tasks_with_median_early_stopping_iterations"]
+        if args.run_k_shot_learning_curves_experiment:                       # run_metasegnet.py:167-171
+            kk = dict(eval_kwargs)
+            del kk["save_fine_tuned_checkpoints"]
+            del kk["save_fine_tuned_checkpoints_dir"]
+            run_k_shot_learning_curves_experiment(sess, model, test_set, lr_scheduler=lr_scheduler,
+                                                  iter_range=args.k_shot_iter_range, **kk)
+            print("Experiment finished at: {}".format(datetime.datetime.now()))
+            return
+        if args.eval_val_tasks and val_set:
+            test_set = val_set
         print("Evaluating {}-shot learning on training tasks.".format(args.shots))
         mean_train_iou = None
         if eval_train_tasks:
