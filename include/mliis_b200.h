@@ -69,6 +69,11 @@ typedef struct mliis_config {
   float   label_smoothing;     /* --label_smoothing                                         */
   float   final_dropout_rate;  /* --final_layer_dropout_rate (0 = layer absent)             */
   int32_t rsd[4];              /* --rsd reduction indices, 0-terminated (canonical {2,4})   */
+  int32_t n_classes;           /* 0/1: the binary few-shot head (2 channels, dense one-hot labels).  > 1: the
+                                  joint-training head of joint_train.py:307 - n_classes + 1 channels (channel 0 =
+                                  background, --seperate_background_channel), multi-class soft IoU
+                                  (binary_iou_loss=False, efficientlab.py:369-382), SPARSE labels: dev_labels is a
+                                  mask pool [n,H,W] (> 0.5 = foreground) + mliis_set_class_ids             */
 } mliis_config;
 
 /* One trainable variable of the reference graph (tf.trainable_variables() order). */
@@ -155,6 +160,20 @@ int mliis_forward(mliis_ctx* ctx, int32_t slot, const float* dev_images, const i
 int mliis_loss_backward(mliis_ctx* ctx, int32_t slot, const float* dev_labels, const int32_t* dev_index,
                         int32_t batch, float* dev_grads_out /* [P] or NULL */, float* dev_loss_out, void* stream);
 int mliis_optimizer_step(mliis_ctx* ctx, int32_t slot, float lr, float pre_decay_rate, void* stream);
+/* Data-parallel training (joint_train.py): overwrite the slot's flat gradient buffer, e.g. with the
+ * NCCL all-reduced mean of every rank's mliis_loss_backward(dev_grads_out), before mliis_optimizer_step. */
+int mliis_set_grads(mliis_ctx* ctx, int32_t slot, const float* dev_grads /* [mliis_theta_floats] */, void* stream);
+
+/* ---- multi-class head (n_classes > 1; joint_train.py:295-343, efficientlab.py:294-327, :369-396) --------------
+ * Labels are sparse: one foreground class id per pool example (1..n_classes; 0 is the background channel) and a
+ * binary mask.  The reference's dense [H,W,1001] one-hot label / logit / probability tensors are never built.
+ * mliis_forward(dev_logits_out) returns the LOW-resolution head output [B, H/4, W/4, n_classes+1] in this mode. */
+int mliis_set_class_ids(mliis_ctx* ctx, int32_t slot, const int32_t* dev_class_ids /* [n_pool], stays referenced */);
+/* compute_iou_metric / iou_callback (joint_train.py:248-269): eval-mode forward; class_map = argmax channel where its
+ * probability > 0.5 else -1 (the one-hot content of float(p > 0.5)); inter/union = integer counts over all channels */
+int mliis_predict_classes(mliis_ctx* ctx, int32_t slot, const float* dev_images, const float* dev_masks,
+                          const int32_t* dev_index, int32_t batch, int32_t* dev_class_map_out /* [B,H,W] or NULL */,
+                          uint32_t* dev_inter_out, uint32_t* dev_union_out, void* stream);
 
 /* ---- predictions + IoU: sess.run(predictions, {input_ph, is_training_ph: False}) -------------
  * Replaces reptile.py:482-524 (_test_predictions), models/efficientlab.py:291-292 (threshold) and

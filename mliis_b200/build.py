@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmliis_b200.so")
 HEADER = os.path.join(HERE, "..", "include", "mliis_b200.h")
-SOURCES = ["engine.cu", "k_rowchan.cu", "k_conv.cu", "k_gemm.cu", "k_misc.cu", "k_tc.cu", "plan.cpp"]
+SOURCES = ["engine.cu", "k_rowchan.cu", "k_conv.cu", "k_gemm.cu", "k_misc.cu", "k_mc.cu", "k_tc.cu", "plan.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "static"]
 
@@ -32,7 +32,7 @@ def is_stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(d) > t for d in sources() + _headers())
+    return any(os.path.getmtime(d) > t for d in sources() + _headers() + [os.path.abspath(__file__)])
 
 
 def build(force=False, verbose=True):

@@ -60,6 +60,7 @@ struct Slot {
   const float* fwd_images = nullptr;
   const int32_t* fwd_index = nullptr;
   const float* fwd_drop_mask = nullptr;
+  const int32_t* class_ids = nullptr;   // multi-class mode: per-example foreground class (mliis_set_class_ids)
   bool grads_zeroed = false;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
@@ -375,8 +376,22 @@ void run_forward(const Run& r, const float* images, const int32_t* index, bool t
     }
   }
   r.sl->fwd_drop_mask = mask;
-  head_fwd(deep, deep_ld, r.T(p.w_head), r.T(p.b_head), mask, 1.f / (1.f - rate), r.W(p.z_lo), B * p.hl * p.wl, p.D,
-           st);
+  if (p.n_out == 2) {
+    head_fwd(deep, deep_ld, r.T(p.w_head), r.T(p.b_head), mask, 1.f / (1.f - rate), r.W(p.z_lo), B * p.hl * p.wl, p.D,
+             st);
+  } else {
+    // multi-class head (joint training): a dense 1x1 layer D -> Cp on the tensor-core path, weights zero-padded
+    // from n_out to Cp = 4*ceil(n_out/4) columns so that every operand row is 16-byte aligned
+    const int M = B * p.hl * p.wl;
+    mc_pad_head(r.T(p.w_head), r.T(p.b_head), r.W(p.mc_wp), r.W(p.mc_bp), p.D, p.n_out, p.Cp, st);
+    const float* xin = deep;
+    if (mask) {
+      mc_mul_mask(deep, mask, 1.f / (1.f - rate), r.W(p.mc_xdrop), (int64_t)M * p.D, st);
+      xin = r.W(p.mc_xdrop);
+    }
+    Dense{r, true}.fwd(xin, p.D, 0, p.hl, p.wl, p.D, 1, r.W(p.mc_wp), r.W(p.mc_bp), r.W(p.z_lo), p.Cp, p.Cp, M,
+                       p.hl * p.wl);
+  }
   r.sl->fwd_batch = B;
   r.sl->fwd_training = training;
   r.sl->fwd_images = images;
@@ -386,6 +401,43 @@ void run_forward(const Run& r, const float* images, const int32_t* index, bool t
 // ------------------------------------------------------------------------------------------------
 // loss + backward
 // ------------------------------------------------------------------------------------------------
+McLossArgs mc_args(const Run& r, const float* mask, const int32_t* index) {
+  const Plan& p = r.p;
+  const Tab& tf = r.c->tabs[p.tab_final];
+  McLossArgs a{};
+  a.z_lo = r.W(p.z_lo); a.ldz = p.Cp; a.mask = mask; a.cls = r.sl->class_ids; a.index = index;
+  a.B = r.B; a.h = p.hl; a.w = p.wl; a.H = p.image_size; a.W = p.image_size; a.C = p.n_out;
+  a.ty = tf.rt(); a.tx = tf.rt();
+  a.dice = (r.c->cfg.loss_flags & MLIIS_LOSS_DICE) ? 1 : 0;
+  a.label_smoothing = r.c->cfg.label_smoothing;
+  a.lse = r.W(p.mc_lse); a.pt = r.W(p.p1); a.partials = r.W(p.partials); a.coef = r.W(p.loss_coef);
+  a.dz_lo = r.W(p.dz_lo); a.lddz = p.Cp;
+  a.theta = r.theta; a.n_l2 = p.n_l2;
+  a.l2_coef = (r.c->cfg.loss_flags & MLIIS_LOSS_L2) ? 0.0005f : 0.f;
+  return a;
+}
+
+// multi-class loss (sparse labels) + head backward; leaves d loss / d features in g_out like the binary head
+void run_backward_multiclass_head(const Run& r, const float* mask, const int32_t* index, float* loss_out) {
+  const Plan& p = r.p;
+  cudaStream_t st = r.st;
+  const int M = r.B * p.hl * p.wl, HW = p.hl * p.wl;
+  McLossArgs a = mc_args(r, mask, index);
+  a.loss_out = loss_out;
+  mc_loss_fwd_bwd(a, st);
+  const RsdPlan& last = p.rsds.back();
+  const float rate = r.c->cfg.final_dropout_rate;
+  const float* dmask = r.sl->fwd_drop_mask;
+  const float* xin = dmask ? r.W(p.mc_xdrop) : r.W(last.out.off);
+  const Dense dense{r, true};
+  // dW^T via the swapped-role wgrad (Cp > 256 output channels), db = column sums of dz
+  dense.wgrad(xin, p.D, 0, p.hl, p.wl, p.D, 1, r.W(p.dz_lo), p.Cp, p.Cp, r.W(p.mc_gwp), r.W(p.mc_gbp), M, HW,
+              nullptr, nullptr, nullptr, true);
+  dense.dgrad(r.W(p.dz_lo), p.Cp, 0, p.hl, p.wl, p.D, 1, r.W(p.mc_wp), r.W(p.g_out), p.D, p.Cp, M, HW, 0);
+  if (dmask) mc_mul_mask(r.W(p.g_out), dmask, 1.f / (1.f - rate), r.W(p.g_out), (int64_t)M * p.D, st);
+  mc_unpad_grad(r.W(p.mc_gwp), r.W(p.mc_gbp), r.G(p.w_head), r.G(p.b_head), p.D, p.n_out, p.Cp, st);
+}
+
 void run_backward(const Run& r, const float* labels, const int32_t* index, float* loss_out) {
   const Plan& p = r.p;
   const int B = r.B;
@@ -395,6 +447,9 @@ void run_backward(const Run& r, const float* labels, const int32_t* index, float
     cudaMemsetAsync(r.G(0), 0, p.n_theta * sizeof(float), st);
     r.sl->grads_zeroed = true;
   }
+  if (p.n_out != 2) {
+    run_backward_multiclass_head(r, labels, index, loss_out);
+  } else {
   LossArgs la{};
   la.z_lo = r.W(p.z_lo); la.labels = labels; la.index = index;
   la.B = B; la.h = p.hl; la.w = p.wl; la.H = p.image_size; la.W = p.image_size;
@@ -413,6 +468,7 @@ void run_backward(const Run& r, const float* labels, const int32_t* index, float
   const float rate = r.c->cfg.final_dropout_rate;
   head_bwd(r.W(last.out.off), p.D, r.T(p.w_head), r.sl->fwd_drop_mask, 1.f / (1.f - rate), r.W(p.dz_lo), r.W(p.g_out),
            p.D, r.W(p.partials), r.G(p.w_head), r.G(p.b_head), B * p.hl * p.wl, p.D, st);
+  }
 
   // decoder, reverse order
   float* gOut = r.W(p.g_out);
@@ -580,7 +636,8 @@ int mliis_ctx_create(const mliis_config* cfg, int device, mliis_ctx** out) {
   mliis_ctx* c = new mliis_ctx();
   c->cfg = *cfg;
   try {
-    c->plan.build(cfg->image_size, cfg->max_batch, cfg->rsd, cfg->final_dropout_rate);
+    c->plan.build(cfg->image_size, cfg->max_batch, cfg->rsd, cfg->final_dropout_rate,
+                  cfg->n_classes > 1 ? cfg->n_classes + 1 : 2);
   } catch (const std::exception& e) {
     delete c;
     return fail(MLIIS_ERR_ARG, "%s", e.what());
@@ -716,7 +773,13 @@ int mliis_forward(mliis_ctx* ctx, int32_t slot, const float* images, const int32
   if (!images) return fail(MLIIS_ERR_ARG, "null images");
   Run r(ctx, slot, batch, (cudaStream_t)stream);
   run_forward(r, images, index, training != 0, dc_mask, drop_mask, seed);
-  if (logits_out) {
+  if (logits_out && ctx->plan.n_out != 2) {
+    // multi-class head: the full-resolution logits are never materialised; return the LOW-resolution head output
+    // [B, h, w, n_out] (the loss / predict kernels upsample on the fly)
+    const Plan& p = ctx->plan;
+    cudaMemcpy2DAsync(logits_out, (size_t)p.n_out * sizeof(float), r.W(p.z_lo), (size_t)p.Cp * sizeof(float),
+                      (size_t)p.n_out * sizeof(float), (size_t)batch * p.hl * p.wl, cudaMemcpyDeviceToDevice, r.st);
+  } else if (logits_out) {
     const Plan& p = ctx->plan;
     const Tab& tf = ctx->tabs[p.tab_final];
     predict_mask_iou(r.W(p.z_lo), nullptr, nullptr, batch, p.hl, p.wl, p.image_size, p.image_size, tf.rt(), tf.rt(),
@@ -732,11 +795,46 @@ int mliis_loss_backward(mliis_ctx* ctx, int32_t slot, const float* labels, const
   Slot& sl = ctx->slots[slot];
   if (!sl.fwd_training || sl.fwd_batch != batch) return fail(MLIIS_ERR_STATE, "loss_backward needs a training forward of the same batch");
   if (!labels) return fail(MLIIS_ERR_ARG, "null labels");
+  if (ctx->plan.n_out != 2 && !sl.class_ids)
+    return fail(MLIIS_ERR_STATE, "multi-class head: call mliis_set_class_ids first (labels = masks [n,H,W])");
   Run r(ctx, slot, batch, (cudaStream_t)stream);
   run_backward(r, labels, index, loss_out);
   if (grads_out)
     cudaMemcpyAsync(grads_out, r.G(0), ctx->plan.n_theta * sizeof(float), cudaMemcpyDeviceToDevice, r.st);
   return check_cuda("loss_backward");
+}
+
+int mliis_set_grads(mliis_ctx* ctx, int32_t slot, const float* grads, void* stream) {
+  int rc = validate(ctx, slot, 1);
+  if (rc) return rc;
+  if (!grads) return fail(MLIIS_ERR_ARG, "null grads");
+  Run r(ctx, slot, 1, (cudaStream_t)stream);
+  cudaMemcpyAsync(r.G(0), grads, ctx->plan.n_theta * sizeof(float), cudaMemcpyDeviceToDevice, r.st);
+  return check_cuda("set_grads");
+}
+
+int mliis_set_class_ids(mliis_ctx* ctx, int32_t slot, const int32_t* dev_class_ids) {
+  int rc = validate(ctx, slot, 1);
+  if (rc) return rc;
+  if (ctx->plan.n_out == 2) return fail(MLIIS_ERR_STATE, "class ids are only used by the multi-class head (n_classes > 1)");
+  ctx->slots[slot].class_ids = dev_class_ids;
+  return MLIIS_OK;
+}
+
+int mliis_predict_classes(mliis_ctx* ctx, int32_t slot, const float* images, const float* masks, const int32_t* index,
+                          int32_t batch, int32_t* class_map_out, uint32_t* inter_out, uint32_t* union_out,
+                          void* stream) {
+  int rc = validate(ctx, slot, batch);
+  if (rc) return rc;
+  if (ctx->plan.n_out == 2) return fail(MLIIS_ERR_STATE, "mliis_predict_classes needs the multi-class head (n_classes > 1)");
+  if (!images) return fail(MLIIS_ERR_ARG, "null images");
+  if ((inter_out || union_out) && !(inter_out && union_out && masks && ctx->slots[slot].class_ids))
+    return fail(MLIIS_ERR_ARG, "IoU counts need masks, class ids (mliis_set_class_ids), inter_out and union_out");
+  Run r(ctx, slot, batch, (cudaStream_t)stream);
+  run_forward(r, images, index, false, nullptr, nullptr, 0);
+  McLossArgs a = mc_args(r, masks, index);
+  mc_predict(a, class_map_out, inter_out, union_out, r.st);
+  return check_cuda("predict_classes");
 }
 
 int mliis_optimizer_step(mliis_ctx* ctx, int32_t slot, float lr, float pre_decay_rate, void* stream) {
@@ -754,6 +852,8 @@ int mliis_train_step(mliis_ctx* ctx, int32_t slot, const mliis_step_args* a, voi
   int rc = validate(ctx, slot, a->batch);
   if (rc) return rc;
   if (!a->dev_images || !a->dev_labels) return fail(MLIIS_ERR_ARG, "null images/labels");
+  if (ctx->plan.n_out != 2 && !ctx->slots[slot].class_ids)
+    return fail(MLIIS_ERR_STATE, "multi-class head: call mliis_set_class_ids first (labels = masks [n,H,W])");
   Run r(ctx, slot, a->batch, (cudaStream_t)stream);
   // reptile.py:112-113 pre_step_op: var *= rate, before the step's forward pass
   if (a->pre_decay_rate != 1.f && a->pre_decay_rate != 0.f) scale_buffer(r.theta, ctx->plan.n_theta, a->pre_decay_rate, r.st);
@@ -770,6 +870,7 @@ int mliis_predict(mliis_ctx* ctx, int32_t slot, const float* images, const float
   int rc = validate(ctx, slot, batch);
   if (rc) return rc;
   if (!images) return fail(MLIIS_ERR_ARG, "null images");
+  if (ctx->plan.n_out != 2) return fail(MLIIS_ERR_STATE, "binary head only: use mliis_predict_classes");
   if ((inter_out || union_out) && !(inter_out && union_out && labels))
     return fail(MLIIS_ERR_ARG, "IoU counts need labels, inter_out and union_out");
   Run r(ctx, slot, batch, (cudaStream_t)stream);
@@ -783,6 +884,7 @@ int mliis_predict(mliis_ctx* ctx, int32_t slot, const float* images, const float
 
 static int task_body(mliis_ctx* ctx, int32_t slot, const mliis_task_args* a, cudaStream_t st) {
   const Plan& p = ctx->plan;
+  if (p.n_out != 2) return fail(MLIIS_ERR_STATE, "task adaptation runs on the binary head (n_classes <= 1)");
   int rc = mliis_state_copy(ctx, ctx->slots[slot].state, a->dev_init_state, MLIIS_STATE_ALL, (void*)st);
   if (rc) return rc;
   for (int t = 0; t < a->n_steps; ++t) {

@@ -281,6 +281,10 @@ __global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, float* __re
   }
 }
 
+void sumsq_partials(const float* x, int64_t n, float* out, int n_blocks, cudaStream_t s) {
+  MLIIS_COUNT(), sumsq_kernel<<<n_blocks, 256, 0, s>>>(x, n, out);
+}
+
 // single thread: per-image IoU, dice, loss value and the per-image gradient coefficients
 __global__ void loss_finalize_kernel(LossArgs a, const float* __restrict__ l2_partials, int n_l2_partials) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;

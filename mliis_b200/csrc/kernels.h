@@ -166,6 +166,30 @@ struct LossArgs {
 };
 void loss_fwd_bwd(const LossArgs& a, cudaStream_t s);
 
+// multi-class head loss with sparse labels (k_mc.cu): class id per example + binary mask, C = n_classes + 1 channels
+struct McLossArgs {
+  const float* z_lo; int ldz;     // [B*h*w, ldz] low-res logits (columns >= C are padding)
+  const float* mask;              // pool [n,H,W] foreground mask (> 0.5 = foreground); nullable for mc_predict
+  const int32_t* cls;             // pool [n] class id of the foreground, 1..C-1 (channel 0 = background)
+  const int32_t* index;           // [B] or null
+  int B, h, w, H, W, C;
+  ResizeTab ty, tx;
+  int dice; float label_smoothing;
+  float* lse; float* pt;          // [B,H,W] scratch: log-sum-exp and target-class probability per pixel
+  float* partials;                // [B][chunks][2] (+ 148 L2 partials)
+  float* coef;                    // [B]
+  float* dz_lo; int lddz;         // out [B*h*w, lddz]
+  float* loss_out;                // nullable
+  const float* theta; int64_t n_l2; float l2_coef;
+};
+int mc_loss_chunks(int H);
+void mc_loss_fwd_bwd(const McLossArgs& a, cudaStream_t s);
+void mc_predict(const McLossArgs& a, int32_t* class_map, uint32_t* inter, uint32_t* uni, cudaStream_t s);
+void mc_pad_head(const float* w, const float* bias, float* wp, float* bp, int K, int C, int Cp, cudaStream_t s);
+void mc_unpad_grad(const float* gwp, const float* gbp, float* gw, float* gb, int K, int C, int Cp, cudaStream_t s);
+void mc_mul_mask(const float* x, const float* mask, float scale, float* y, int64_t n, cudaStream_t s);
+void sumsq_partials(const float* x, int64_t n, float* out, int n_blocks, cudaStream_t s);
+
 void predict_mask_iou(const float* z_lo, const float* labels, const int32_t* index, int B, int h, int w, int H,
                       int W, ResizeTab ty, ResizeTab tx, float* pred_out, float* logits_out, uint32_t* inter,
                       uint32_t* uni, cudaStream_t s);

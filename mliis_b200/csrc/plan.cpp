@@ -77,7 +77,8 @@ struct Builder {
 
 }  // namespace
 
-void Plan::build(int image_size_, int max_batch, const int* rsd, float final_dropout_rate) {
+void Plan::build(int image_size_, int max_batch, const int* rsd, float final_dropout_rate, int n_out_) {
+  n_out = n_out_;
   image_size = image_size_;
   maxB = max_batch;
   if (image_size % 32 != 0 || image_size < 32) throw std::invalid_argument("image_size must be a positive multiple of 32");
@@ -316,11 +317,27 @@ void Plan::build(int image_size_, int max_batch, const int* rsd, float final_dro
   tab_final = (int)resize_pairs.size();
   resize_pairs.push_back({hl, image_size});
   const int HWl = hl * wl, HWf = image_size * image_size;
-  z_lo = b.alloc((int64_t)B * HWl * 2);
-  { Buf z; z.off = z_lo; z.HW = HWl; z.C = 2; z.ld = 2; named.push_back({"head.logits_lowres", z}); }
-  dz_lo = b.alloc((int64_t)B * HWl * 2);
+  Cp = n_out == 2 ? 2 : (n_out + 3) / 4 * 4;
+  z_lo = b.alloc((int64_t)B * HWl * Cp);
+  { Buf z; z.off = z_lo; z.HW = HWl; z.C = n_out; z.ld = Cp; named.push_back({"head.logits_lowres", z}); }
+  dz_lo = b.alloc((int64_t)B * HWl * Cp);
+  { Buf z; z.off = dz_lo; z.HW = HWl; z.C = n_out; z.ld = Cp; named.push_back({"head.dlogits_lowres", z}); }
   p1 = b.alloc((int64_t)B * HWf);
-  dz_hi = b.alloc((int64_t)B * HWf * 2);
+  if (n_out == 2) {
+    dz_hi = b.alloc((int64_t)B * HWf * 2);
+  } else {
+    mc_lse = b.alloc((int64_t)B * HWf);
+    mc_wp = b.alloc((int64_t)D * Cp);
+    mc_bp = b.alloc(Cp);
+    mc_gwp = b.alloc((int64_t)D * Cp);
+    mc_gbp = b.alloc(Cp);
+    if (final_dropout_rate > 0.f) mc_xdrop = b.alloc((int64_t)B * HWl * D);
+    upd(max_wT, (int64_t)D * Cp);
+    upd(max_tn, (int64_t)gemm_tn_scratch(B * HWl, D, Cp, 0));
+    upd(max_tn, (int64_t)tc_wgrad_scratch(0, B * HWl, B, hl, wl, Cp, D, 1));      // swapped roles
+    upd(max_partials, (int64_t)B * ((image_size + 3) / 4) * 2 + 148 + 64);
+    upd(max_partials, (int64_t)rc_num_img_chunks(B * HWl, Cp) * Cp + 64);
+  }
   dropmask = final_dropout_rate > 0.f ? b.alloc((int64_t)B * HWl * D) : -1;
   bn_mean = b.alloc(n_bn_ch);
   bn_rstd = b.alloc(n_bn_ch);

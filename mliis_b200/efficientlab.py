@@ -46,7 +46,8 @@ class EfficientLab:
                  optimizer=None, rsd: Optional[List[int]] = [2], disable_lsd_residual_connections: bool = False,
                  seperate_background_channel: bool = True, binary_iou_loss: bool = True, **optim_kwargs):
         if images is not None or labels is not None:
-            raise NotImplementedError("graph-fed images/labels (joint_train.py path) are out of scope: SURVEY 8f-1")
+            raise NotImplementedError("there is no TF input graph here: feed batches through mliis_b200.joint_train "
+                                      "(joint_train.py path, SURVEY 8f-1)")
         if feature_extractor_name != "efficientnet-b0":
             raise NotImplementedError("only efficientnet-b0 (EfficientLab-6-3) is built; got %s" % feature_extractor_name)
         for flag, name in ((spatial_pyramid_pooling, "spatial_pyramid_pooling"), (skip_decoding, "skip_decoding"),
@@ -54,8 +55,16 @@ class EfficientLab:
                                                           "disable_lsd_residual_connections")):
             if flag:
                 raise NotImplementedError("%s is not enabled by run.sh / BASELINE configs and is not built" % name)
-        if n_classes != 1 or not seperate_background_channel or not binary_iou_loss:
-            raise NotImplementedError("only the binary (foreground + background channel) head is built")
+        # two heads are built: the few-shot binary head (n_classes=1, binary_iou_loss=True) and the joint-training
+        # head of joint_train.py:307 (n_classes=N, seperate_background_channel=True, binary_iou_loss=False: N+1
+        # channels, multi-class soft IoU, sparse labels on the device)
+        if not seperate_background_channel:
+            raise NotImplementedError("a head without the background channel is not built")
+        if (n_classes == 1) != bool(binary_iou_loss):
+            raise NotImplementedError("built heads: n_classes=1 with binary_iou_loss=True, or n_classes>1 with "
+                                      "binary_iou_loss=False")
+        self.n_classes = int(n_classes)
+        self.binary_iou_loss = bool(binary_iou_loss)
         if n_rows != n_cols:
             raise ValueError("square images only")
         if not rsd:
@@ -117,7 +126,7 @@ class EfficientLab:
         flags = (N.LOSS_DICE if self.dice else 0) | (N.LOSS_L2 if self.l2 else 0)
         return N.make_config(self.n_input_rows, self.max_batch, n_slots,
                              N.OPT_SGD if self.optimizer_name == "sgd" else N.OPT_ADAM, flags, self.gemm_mode,
-                             self.label_smoothing, self.final_layer_dropout_rate, self.rsd)
+                             self.label_smoothing, self.final_layer_dropout_rate, self.rsd, self.n_classes)
 
     def engine(self, device: Optional[int] = None):
         """The CUDA engine (created on first use; raises without an sm_100 GPU - there is no fallback)."""
@@ -129,7 +138,7 @@ class EfficientLab:
                                   sgd=self.optimizer_name == "sgd", dice=self.dice, l2=self.l2,
                                   label_smoothing=self.label_smoothing,
                                   final_dropout_rate=self.final_layer_dropout_rate, rsd=self.rsd,
-                                  gemm_mode=self.gemm_mode, device=device)
+                                  gemm_mode=self.gemm_mode, device=device, n_classes=self.n_classes)
         return self._engine
 
     # ---- variable collections (tf.trainable_variables() / GLOBAL_VARIABLES order) ----

@@ -26,14 +26,16 @@ class Engine:
 
     def __init__(self, image_size: int = 224, max_batch: int = 8, n_slots: int = 1, sgd: bool = False,
                  dice: bool = True, l2: bool = True, label_smoothing: float = 0.0, final_dropout_rate: float = 0.0,
-                 rsd: Sequence[int] = (2, 4), gemm_mode: int = N.GEMM_FP32, device: int = 0):
+                 rsd: Sequence[int] = (2, 4), gemm_mode: int = N.GEMM_FP32, device: int = 0, n_classes: int = 1):
         if not torch.cuda.is_available():
             raise N.MliisError(N.MLIIS_ERR_DEVICE, "no CUDA device: mliis_b200 has no CPU fallback")
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
         flags = (N.LOSS_DICE if dice else 0) | (N.LOSS_L2 if l2 else 0)
         self.cfg = N.make_config(image_size, max_batch, n_slots, N.OPT_SGD if sgd else N.OPT_ADAM, flags, gemm_mode,
-                                 label_smoothing, final_dropout_rate or 0.0, rsd)
+                                 label_smoothing, final_dropout_rate or 0.0, rsd, n_classes)
+        self.n_classes = n_classes
+        self.n_out = n_classes + 1 if n_classes > 1 else 2
         self.ctx = N.Context(self.cfg, device)
         self.lib = N.lib()
         self.image_size = image_size
@@ -140,7 +142,11 @@ class Engine:
                 want_logits: bool = True, stream=None) -> Optional[torch.Tensor]:
         B = int(batch if batch is not None else (index.numel() if index is not None else images.shape[0]))
         H = self.image_size
-        logits = torch.empty(B, H, H, 2, dtype=torch.float32, device=self.device) if want_logits else None
+        if self.n_out == 2:
+            logits = torch.empty(B, H, H, 2, dtype=torch.float32, device=self.device) if want_logits else None
+        else:   # multi-class head: the LOW-resolution head output [B, H/4, W/4, n_out]
+            logits = torch.empty(B, H // 4, H // 4, self.n_out, dtype=torch.float32,
+                                 device=self.device) if want_logits else None
         N.check(self.lib.mliis_forward(self.ctx.handle, slot, _ptr(images), _ptr(index), B, int(training),
                                        _ptr(dc_mask), _ptr(drop_mask), int(seed), _ptr(logits),
                                        self._stream(stream)))
@@ -153,6 +159,32 @@ class Engine:
         N.check(self.lib.mliis_loss_backward(self.ctx.handle, slot, _ptr(labels), _ptr(index), batch, _ptr(grads),
                                              _ptr(loss), self._stream(stream)))
         return loss, grads
+
+    def set_grads(self, slot: int, grads: torch.Tensor, stream=None) -> None:
+        """Overwrites the slot's gradient buffer (data-parallel all-reduce result) before optimizer_step."""
+        N.check(self.lib.mliis_set_grads(self.ctx.handle, slot, _ptr(grads), self._stream(stream)))
+
+    def set_class_ids(self, slot: int, class_ids: torch.Tensor) -> None:
+        """Multi-class head: int32 [n_pool] foreground class of every pool example (kept referenced)."""
+        assert class_ids.dtype == torch.int32 and class_ids.is_cuda
+        self._class_ids = getattr(self, "_class_ids", {})
+        self._class_ids[slot] = class_ids
+        N.check(self.lib.mliis_set_class_ids(self.ctx.handle, slot, _ptr(class_ids)))
+
+    def predict_classes(self, slot: int, images: torch.Tensor, masks: Optional[torch.Tensor] = None,
+                        index: Optional[torch.Tensor] = None, batch: Optional[int] = None,
+                        want_class_map: bool = True, stream=None):
+        """(class map int32 [B,H,W] with -1 = no class above 0.5, inter, union) of the multi-class head."""
+        B = int(batch if batch is not None else (index.numel() if index is not None else images.shape[0]))
+        H = self.image_size
+        cmap = torch.empty(B, H, H, dtype=torch.int32, device=self.device) if want_class_map else None
+        inter = uni = None
+        if masks is not None:
+            inter = torch.zeros(B, dtype=torch.int32, device=self.device)
+            uni = torch.zeros(B, dtype=torch.int32, device=self.device)
+        N.check(self.lib.mliis_predict_classes(self.ctx.handle, slot, _ptr(images), _ptr(masks), _ptr(index), B,
+                                               _ptr(cmap), _ptr(inter), _ptr(uni), self._stream(stream)))
+        return cmap, inter, uni
 
     def optimizer_step(self, slot: int, lr: float, stream=None) -> None:
         N.check(self.lib.mliis_optimizer_step(self.ctx.handle, slot, float(lr), 1.0, self._stream(stream)))

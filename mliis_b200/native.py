@@ -22,7 +22,8 @@ STATE_TRAINABLES, STATE_BN, STATE_OPT, STATE_ALL = 1, 2, 4, 7
 class Config(C.Structure):
     _fields_ = [("image_size", C.c_int32), ("max_batch", C.c_int32), ("n_slots", C.c_int32),
                 ("optimizer", C.c_int32), ("loss_flags", C.c_int32), ("gemm_mode", C.c_int32),
-                ("label_smoothing", C.c_float), ("final_dropout_rate", C.c_float), ("rsd", C.c_int32 * 4)]
+                ("label_smoothing", C.c_float), ("final_dropout_rate", C.c_float), ("rsd", C.c_int32 * 4),
+                ("n_classes", C.c_int32)]
 
 
 class ParamInfo(C.Structure):
@@ -72,6 +73,9 @@ SYMBOLS = [
     ("mliis_forward", C.c_int, [_VP, _I32, _VP, _VP, _I32, _I32, _VP, _VP, _U64, _VP, _VP]),
     ("mliis_loss_backward", C.c_int, [_VP, _I32, _VP, _VP, _I32, _VP, _VP, _VP]),
     ("mliis_optimizer_step", C.c_int, [_VP, _I32, _F, _F, _VP]),
+    ("mliis_set_grads", C.c_int, [_VP, _I32, _VP, _VP]),
+    ("mliis_set_class_ids", C.c_int, [_VP, _I32, _VP]),
+    ("mliis_predict_classes", C.c_int, [_VP, _I32, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP]),
     ("mliis_predict", C.c_int, [_VP, _I32, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP, _VP]),
     ("mliis_adapt_eval_task", C.c_int, [_VP, _I32, C.POINTER(TaskArgs), _VP]),
     ("mliis_task_graph_capture", C.c_int, [_VP, _I32, C.POINTER(TaskArgs), _VP]),
@@ -138,11 +142,12 @@ class BnLayer(NamedTuple):
 
 
 def make_config(image_size=224, max_batch=8, n_slots=1, optimizer=OPT_ADAM, loss_flags=LOSS_DICE | LOSS_L2,
-                gemm_mode=GEMM_FP32, label_smoothing=0.0, final_dropout_rate=0.0, rsd=(2, 4)) -> Config:
+                gemm_mode=GEMM_FP32, label_smoothing=0.0, final_dropout_rate=0.0, rsd=(2, 4), n_classes=1) -> Config:
     cfg = Config()
     cfg.image_size, cfg.max_batch, cfg.n_slots = image_size, max_batch, n_slots
     cfg.optimizer, cfg.loss_flags, cfg.gemm_mode = optimizer, loss_flags, gemm_mode
     cfg.label_smoothing, cfg.final_dropout_rate = label_smoothing, final_dropout_rate
+    cfg.n_classes = n_classes
     r = list(rsd or ())[:4]
     for i in range(4):
         cfg.rsd[i] = r[i] if i < len(r) else 0

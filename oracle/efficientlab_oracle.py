@@ -292,12 +292,15 @@ class EfficientLabOracle:
     """Functional restatement.  State is explicit: theta (flat, TF creation order), bn_state [2,n_bn]."""
 
     def __init__(self, arch: Optional[Arch] = None, dtype=torch.float64, dice: bool = True, l2: bool = True,
-                 label_smoothing: float = 0.0):
+                 label_smoothing: float = 0.0, binary_iou_loss: bool = True):
         self.arch = arch or Arch()
         self.dtype = dtype
         self.dice = dice
         self.l2 = l2
         self.label_smoothing = label_smoothing
+        # efficientlab.py:355-382: binary_iou_loss=True scores channel 1 only (few-shot); False (joint_train.py:307)
+        # scores the flattened (H, W, C) tensors of ALL channels
+        self.binary_iou_loss = binary_iou_loss
         self._l2_mask = self.arch.l2_mask(dtype)
 
     # -- helpers --
@@ -443,8 +446,12 @@ class EfficientLabOracle:
         ce = -(y_ce * logp).sum(-1).mean()      # SUM_BY_NONZERO_WEIGHTS == mean over B*H*W rows [TF-ext]
         loss = ce
         if self.dice:
-            p1 = torch.softmax(logits, dim=-1)[..., 1].reshape(B, -1)
-            y1 = labels[..., 1].reshape(B, -1)
+            if self.binary_iou_loss:
+                p1 = torch.softmax(logits, dim=-1)[..., 1].reshape(B, -1)
+                y1 = labels[..., 1].reshape(B, -1)
+            else:
+                p1 = torch.softmax(logits, dim=-1).reshape(B, -1)
+                y1 = labels.reshape(B, -1)
             inter = (p1 * y1).sum(1)
             den = p1.sum(1) + y1.sum(1) - inter
             iou = ((inter + 1e-7) / (den + 1e-7)).mean()
