@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -411,7 +412,7 @@ McLossArgs mc_args(const Run& r, const float* mask, const int32_t* index) {
   a.dice = (r.c->cfg.loss_flags & MLIIS_LOSS_DICE) ? 1 : 0;
   a.label_smoothing = r.c->cfg.label_smoothing;
   a.lse = r.W(p.mc_lse); a.pt = r.W(p.p1); a.partials = r.W(p.partials); a.coef = r.W(p.loss_coef);
-  a.dz_lo = r.W(p.dz_lo); a.lddz = p.Cp;
+  a.dz_lo = r.W(p.dz_lo); a.lddz = p.Cp; a.cellgrad = r.W(p.mc_cellgrad);
   a.theta = r.theta; a.n_l2 = p.n_l2;
   a.l2_coef = (r.c->cfg.loss_flags & MLIIS_LOSS_L2) ? 0.0005f : 0.f;
   return a;
@@ -636,6 +637,8 @@ int mliis_ctx_create(const mliis_config* cfg, int device, mliis_ctx** out) {
   mliis_ctx* c = new mliis_ctx();
   c->cfg = *cfg;
   try {
+    if (cfg->n_classes > 1 && cfg->max_batch > 256)
+      throw std::invalid_argument("multi-class head: max_batch must be <= 256");
     c->plan.build(cfg->image_size, cfg->max_batch, cfg->rsd, cfg->final_dropout_rate,
                   cfg->n_classes > 1 ? cfg->n_classes + 1 : 2);
   } catch (const std::exception& e) {

@@ -86,54 +86,99 @@ __device__ __forceinline__ int target_of(const McLossArgs& a, int img, int Y, in
   return m > 0.5f ? a.cls[img] : 0;
 }
 
-// grid (ceil(H / kMcRowsPerBlock), B), 256 threads: each warp walks hi-res pixels of the block's rows
+// Executed by a full warp: the contiguous run of hi-res indices whose lo (floor) source index is `c`.
+__device__ __forceinline__ void cell_run(const ResizeTab& t, int c, int& first, int& count) {
+  const int lane = threadIdx.x & 31;
+  const int a0 = t.g_lo[c], a1 = t.g_hi[c];
+  const bool mine = (a0 + lane <= a1) && t.lo[a0 + lane] == c;      // gather ranges are <= 10 wide for H/h ~ 4
+  const unsigned m = __ballot_sync(0xffffffffu, mine);
+  first = a0 + __ffs(m) - 1;
+  count = __popc(m);
+}
+
+// One block per low-res CELL (cy,cx) = the hi-res pixels whose top-left bilinear source is (cy,cx).  The four corner
+// rows of logits (4 x C floats) are staged in shared memory once, so the low-res logits are read from global memory
+// exactly once per step; each warp then walks the cell's hi-res pixels (log-sum-exp over C channels per pixel).
 __global__ void __launch_bounds__(256) mc_loss_fwd_kernel(McLossArgs a) {
+  extern __shared__ float corners[];          // [4][C]
   __shared__ float red[8][2];
-  const int b = blockIdx.y, img = a.index ? a.index[b] : b;
+  const int C = a.C;
+  const int r = blockIdx.x;
+  const int b = r / (a.h * a.w), rem = r - b * (a.h * a.w), cy = rem / a.w, cx = rem - cy * a.w;
+  const int img = a.index ? a.index[b] : b;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int Y0 = blockIdx.x * kMcRowsPerBlock, Y1 = min(a.H, Y0 + kMcRowsPerBlock);
+  const int y1 = min(cy + 1, a.h - 1), x1 = min(cx + 1, a.w - 1);
   const float* zb = a.z_lo + (size_t)b * a.h * a.w * a.ldz;
+  const float* src[4] = {zb + (size_t)(cy * a.w + cx) * a.ldz, zb + (size_t)(cy * a.w + x1) * a.ldz,
+                         zb + (size_t)(y1 * a.w + cx) * a.ldz, zb + (size_t)(y1 * a.w + x1) * a.ldz};
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    for (int c = threadIdx.x; c < C; c += 256) corners[j * C + c] = src[j][c];
+  int Yf, nY, Xf, nX;
+  cell_run(a.ty, cy, Yf, nY);
+  cell_run(a.tx, cx, Xf, nX);
+  __syncthreads();
   const float ls = a.label_smoothing;
   float s_ce = 0.f, s_pt = 0.f;
-  const int npix = (Y1 - Y0) * a.W;
-  for (int i = warp; i < npix; i += 8) {
-    const int Y = Y0 + i / a.W, X = i - (i / a.W) * a.W;
-    const HiPix h = hi_pix(a.ty, a.tx, Y, X);
+  for (int k = warp; k < nY * nX; k += 8) {
+    const int Y = Yf + k / nX, X = Xf + k % nX;
+    const float yl = a.ty.lerp[Y], xl = a.tx.lerp[X];
     const int t = target_of(a, img, Y, X);
-    const PixStats ps = pixel_stats(zb, a.w, a.ldz, a.C, h, t, ls > 0.f, false);
+    float m = -INFINITY, s = 0.f, zs = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float z = lerp4(corners[c], corners[C + c], corners[2 * C + c], corners[3 * C + c], xl, yl);
+      zs += z;
+      if (z > m) {                      // online softmax: rescale the running sum when the max moves
+        s = s * __expf(m - z) + 1.f;
+        m = z;
+      } else {
+        s += __expf(z - m);
+      }
+    }
+    const float M = warp_max(m);
+    s = warp_sum(s * __expf(m - M));
+    if (ls > 0.f) zs = warp_sum(zs);
     if (lane == 0) {
-      const float pt = __expf(ps.zt - ps.lse);
+      const float lse = M + logf(s);
+      const float zt = lerp4(corners[t], corners[C + t], corners[2 * C + t], corners[3 * C + t], xl, yl);
+      const float pt = __expf(zt - lse);
       // -sum_c y_c log p_c with y = onehot*(1-ls) + ls/C
-      s_ce += ps.lse - (1.f - ls) * ps.zt - (ls > 0.f ? ls / (float)a.C * ps.zsum : 0.f);
+      s_ce += lse - (1.f - ls) * zt - (ls > 0.f ? ls / (float)C * zs : 0.f);
       s_pt += pt;
       const size_t o = ((size_t)b * a.H + Y) * a.W + X;
-      a.lse[o] = ps.lse;
+      a.lse[o] = lse;
       a.pt[o] = pt;
     }
   }
   if (lane == 0) { red[warp][0] = s_ce; red[warp][1] = s_pt; }
   __syncthreads();
   if (threadIdx.x < 2) {
-    float s = 0.f;
-    for (int wv = 0; wv < 8; ++wv) s += red[wv][threadIdx.x];
-    a.partials[((size_t)b * gridDim.x + blockIdx.x) * 2 + threadIdx.x] = s;
+    float sum = 0.f;
+    for (int wv = 0; wv < 8; ++wv) sum += red[wv][threadIdx.x];
+    a.partials[(size_t)r * 2 + threadIdx.x] = sum;       // [b][cell][2]
   }
 }
 
-// single thread: per-image soft IoU over all channels, dice, loss value, d loss / d I_b
-__global__ void mc_loss_finalize_kernel(McLossArgs a, int chunks, const float* __restrict__ l2_partials,
-                                        int n_l2_partials) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// one block: thread b sums image b's cell partials (fixed order), thread 0 then forms IoU, dice, the loss value and
+// d loss / d I_b
+__global__ void __launch_bounds__(256) mc_loss_finalize_kernel(McLossArgs a, int chunks,
+                                                               const float* __restrict__ l2_partials,
+                                                               int n_l2_partials) {
+  __shared__ double s_ce[256], s_I[256];
   const double eps = 1e-7, D = 2.0 * (double)a.H * (double)a.W;
+  for (int b = threadIdx.x; b < a.B; b += blockDim.x) {
+    double ce = 0.0, I = 0.0;
+    const float* p = a.partials + (size_t)b * chunks * 2;
+    for (int g = 0; g < chunks; ++g) { ce += p[2 * g]; I += p[2 * g + 1]; }
+    s_ce[b] = ce;
+    s_I[b] = I;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   double ce = 0.0, iou = 0.0;
   for (int b = 0; b < a.B; ++b) {
-    double I = 0.0;
-    for (int g = 0; g < chunks; ++g) {
-      ce += a.partials[((size_t)b * chunks + g) * 2 + 0];
-      I += a.partials[((size_t)b * chunks + g) * 2 + 1];
-    }
-    iou += (I + eps) / (D - I + eps);
-    a.coef[b] = (float)I;
+    ce += s_ce[b];
+    iou += (s_I[b] + eps) / (D - s_I[b] + eps);
   }
   iou /= a.B;
   double loss = ce / ((double)a.B * a.H * a.W);
@@ -143,7 +188,7 @@ __global__ void mc_loss_finalize_kernel(McLossArgs a, int chunks, const float* _
     dLdiou = -1.0 / (iou * (iou + 1.0));
   }
   for (int b = 0; b < a.B; ++b) {
-    const double I = a.coef[b], den = D - I + eps;
+    const double den = D - s_I[b] + eps;
     a.coef[b] = (float)(dLdiou / a.B * (D + 2.0 * eps) / (den * den));     // d loss / d I_b
   }
   if (a.loss_out) {
@@ -153,75 +198,89 @@ __global__ void mc_loss_finalize_kernel(McLossArgs a, int chunks, const float* _
   }
 }
 
-// Backward straight to the LOW-resolution logits (adjoint of the bilinear upsample fused in):
-//   dz_lo[b,y,x,c] = sum_{(Y,X) in footprint(y,x)} wy*wx * ( inv*(p_c - y_c) + coefI_b * p_t * ([c==t] - p_c) )
-// with p_c = exp(z_c(Y,X) - lse(Y,X)) recomputed from the 3x3 low-res neighbourhood staged in shared memory.
-// One block per low-res pixel; threads run over channels.
-struct FootPix { float wgt, lse, ptc, yl, xl; int t, o00, o01, o10, o11; };
-constexpr int kMaxFoot = 100;
+// Backward straight to the LOW-resolution logits (adjoint of the bilinear upsample fused in), in two passes so that
+// every (hi-res pixel, channel) pair is evaluated exactly once:
+//   d(Y,X,c) = inv*(p_c - y_c) + coefI_b * p_t * ([c==t] - p_c),   p_c = exp(z_c(Y,X) - lse(Y,X))
+//   pass 1 (one block per low-res CELL (cy,cx) = the hi-res pixels whose top-left source is (cy,cx); thread = channel):
+//           the four corner logits of the channel live in registers, the cell's <= 36 hi-res pixels are walked once,
+//           and the four corner sums  sum_k w_corner(k) * d(k,c)  go to cellgrad[cell][corner][c]
+//   pass 2: dz_lo[y,x] = cell(y,x).c00 + cell(y,x-1).c01 + cell(y-1,x).c10 + cell(y-1,x-1).c11   (fixed order)
+struct CellPix { float w00, w01, w10, w11; float lse, ptc, yl, xl; int t; };
+constexpr int kMaxCell = 36;
 
-__global__ void __launch_bounds__(256) mc_loss_bwd_kernel(McLossArgs a) {
-  extern __shared__ float sm[];
-  __shared__ FootPix foot[kMaxFoot];
-  __shared__ int nfoot_s;
-  float* nb = sm;                         // [3][3][C] low-res neighbourhood (clamped at the borders)
+__global__ void __launch_bounds__(256) mc_loss_bwd_cell_kernel(McLossArgs a, float* __restrict__ cellgrad) {
+  __shared__ CellPix pix[kMaxCell];
+  __shared__ int npix_s;
   const int C = a.C;
   const int r = blockIdx.x;
-  const int b = r / (a.h * a.w), rem = r - b * (a.h * a.w), y = rem / a.w, x = rem - y * a.w;
+  const int b = r / (a.h * a.w), rem = r - b * (a.h * a.w), cy = rem / a.w, cx = rem - cy * a.w;
   const int img = a.index ? a.index[b] : b;
-  const float* zb = a.z_lo + (size_t)b * a.h * a.w * a.ldz;
-  for (int j = 0; j < 9; ++j) {
-    const int yy = min(max(y + j / 3 - 1, 0), a.h - 1), xx = min(max(x + j % 3 - 1, 0), a.w - 1);
-    const float* src = zb + (size_t)(yy * a.w + xx) * a.ldz;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) nb[j * C + c] = src[c];
-  }
   {
-    // footprint candidates (Y, X) of this low-res pixel, one per thread, kept in a fixed order (deterministic sums);
-    // candidates with zero weight stay in the list and are skipped uniformly
-    const float coefI = a.coef[b];
-    const int Ya = a.ty.g_lo[y], Yb = a.ty.g_hi[y], Xa = a.tx.g_lo[x], Xb = a.tx.g_hi[x];
-    const int nX = Xb - Xa + 1, n = min((Yb - Ya + 1) * nX, kMaxFoot);
+    // the cell's hi-res pixels: (rows with lo == cy) x (columns with lo == cx), listed row-major (fixed order)
+    int Yf, nY, Xf, nX;
+    cell_run(a.ty, cy, Yf, nY);
+    cell_run(a.tx, cx, Xf, nX);
+    const int n = min(nY * nX, kMaxCell);
     if (threadIdx.x < n) {
-      const int Y = Ya + threadIdx.x / nX, X = Xa + threadIdx.x % nX;
-      const int y0 = a.ty.lo[Y], y1 = a.ty.hi[Y], x0 = a.tx.lo[X], x1 = a.tx.hi[X];
+      const int Y = Yf + threadIdx.x / nX, X = Xf + threadIdx.x % nX;
       const float yl = a.ty.lerp[Y], xl = a.tx.lerp[X];
-      const float wy = (y0 == y ? 1.f - yl : 0.f) + (y1 == y ? yl : 0.f);
-      const float wx = (x0 == x ? 1.f - xl : 0.f) + (x1 == x ? xl : 0.f);
-      FootPix f;
-      f.wgt = wy * wx; f.yl = yl; f.xl = xl;
-      f.lse = 0.f; f.ptc = 0.f; f.t = 0; f.o00 = f.o01 = f.o10 = f.o11 = 0;
-      if (f.wgt != 0.f) {
-        const size_t o = ((size_t)b * a.H + Y) * a.W + X;
-        f.lse = a.lse[o]; f.ptc = coefI * a.pt[o];
-        f.t = target_of(a, img, Y, X);
-        // neighbour (yy, xx) sits at ((yy - y + 1) * 3 + (xx - x + 1)) * C inside nb
-        f.o00 = ((y0 - y + 1) * 3 + (x0 - x + 1)) * C; f.o01 = ((y0 - y + 1) * 3 + (x1 - x + 1)) * C;
-        f.o10 = ((y1 - y + 1) * 3 + (x0 - x + 1)) * C; f.o11 = ((y1 - y + 1) * 3 + (x1 - x + 1)) * C;
-      }
-      foot[threadIdx.x] = f;
+      const size_t o = ((size_t)b * a.H + Y) * a.W + X;
+      CellPix c;
+      c.w00 = (1.f - yl) * (1.f - xl); c.w01 = (1.f - yl) * xl; c.w10 = yl * (1.f - xl); c.w11 = yl * xl;
+      c.lse = a.lse[o]; c.ptc = a.coef[b] * a.pt[o]; c.yl = yl; c.xl = xl;
+      c.t = target_of(a, img, Y, X);
+      pix[threadIdx.x] = c;
     }
-    if (threadIdx.x == 0) nfoot_s = n;
+    if (threadIdx.x == 0) npix_s = n;
   }
   __syncthreads();
-  const int nfoot = nfoot_s;
+  const int npix = npix_s;
+  const int y1 = min(cy + 1, a.h - 1), x1 = min(cx + 1, a.w - 1);
+  const float* zb = a.z_lo + (size_t)b * a.h * a.w * a.ldz;
+  const float* r00 = zb + (size_t)(cy * a.w + cx) * a.ldz;
+  const float* r01 = zb + (size_t)(cy * a.w + x1) * a.ldz;
+  const float* r10 = zb + (size_t)(y1 * a.w + cx) * a.ldz;
+  const float* r11 = zb + (size_t)(y1 * a.w + x1) * a.ldz;
   const float inv = 1.f / ((float)a.B * (float)a.H * (float)a.W);
-  const float ls = a.label_smoothing, ybase = ls / (float)C;
-  float* out = a.dz_lo + (size_t)r * a.lddz;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float acc = 0.f;
-    for (int k = 0; k < nfoot; ++k) {
-      const FootPix& f = foot[k];
-      if (f.wgt == 0.f) continue;
-      const float z = lerp4(nb[f.o00 + c], nb[f.o01 + c], nb[f.o10 + c], nb[f.o11 + c], f.xl, f.yl);
-      const float p = __expf(z - f.lse);
-      const float hit = (c == f.t) ? 1.f : 0.f;
-      // TF SoftmaxCrossEntropyWithLogits backprop = softmax - labels [TF-ext]; dI/dz_c = p_t * ([c==t] - p_c)
-      const float d = inv * (p - (hit * (1.f - ls) + ybase)) + f.ptc * (hit - p);
-      acc = fmaf(f.wgt, d, acc);
+  const float ls = a.label_smoothing, ybase = ls / (float)C, yhit = 1.f - ls + ybase;
+  float* out = cellgrad + (size_t)r * 4 * a.lddz;
+  for (int c = threadIdx.x; c < a.lddz; c += blockDim.x) {
+    float g00 = 0.f, g01 = 0.f, g10 = 0.f, g11 = 0.f;
+    if (c < C) {
+      const float z00 = r00[c], z01 = r01[c], z10 = r10[c], z11 = r11[c];
+      for (int k = 0; k < npix; ++k) {
+        const CellPix& f = pix[k];
+        const float z = lerp4(z00, z01, z10, z11, f.xl, f.yl);
+        const float p = __expf(z - f.lse);
+        const bool hit = c == f.t;
+        // TF SoftmaxCrossEntropyWithLogits backprop = softmax - labels [TF-ext]; dI/dz_c = p_t * ([c==t] - p_c)
+        const float d = inv * (p - (hit ? yhit : ybase)) + f.ptc * ((hit ? 1.f : 0.f) - p);
+        g00 = fmaf(f.w00, d, g00); g01 = fmaf(f.w01, d, g01);
+        g10 = fmaf(f.w10, d, g10); g11 = fmaf(f.w11, d, g11);
+      }
     }
-    out[c] = acc;
+    out[c] = g00; out[a.lddz + c] = g01; out[2 * a.lddz + c] = g10; out[3 * a.lddz + c] = g11;
   }
-  for (int c = C + threadIdx.x; c < a.lddz; c += blockDim.x) out[c] = 0.f;     // padded columns
+}
+
+// corner k of cell (cy,cx) is low-res pixel (cy + k/2, cx + k%2), clamped: at the last row / column the clamped
+// corner coincides with the cell's own pixel and carries weight 0 there (lerp == 0), so it is simply skipped
+__global__ void __launch_bounds__(256) mc_loss_bwd_gather_kernel(const float* __restrict__ cellgrad,
+                                                                 float* __restrict__ dz_lo, int B, int h, int w,
+                                                                 int ld4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * h * w * ld4;
+  if (i >= total) return;
+  const int c4 = (int)(i % ld4);
+  const int64_t r = i / ld4;
+  const int x = (int)(r % w), y = (int)((r / w) % h);
+  const float4* cg = reinterpret_cast<const float4*>(cellgrad);
+  auto cell = [&](int64_t rr, int corner) { return cg[((size_t)rr * 4 + corner) * ld4 + c4]; };
+  float4 acc = cell(r, 0);
+  if (x > 0) acc = acc + cell(r - 1, 1);
+  if (y > 0) acc = acc + cell(r - w, 2);
+  if (x > 0 && y > 0) acc = acc + cell(r - w - 1, 3);
+  reinterpret_cast<float4*>(dz_lo)[(size_t)r * ld4 + c4] = acc;
 }
 
 // predictions: class map (argmax if its probability > 0.5, else -1) + integer IoU counts over all channels
@@ -234,8 +293,12 @@ __global__ void __launch_bounds__(256) mc_predict_kernel(McLossArgs a, int32_t* 
   const float* zb = a.z_lo + (size_t)b * a.h * a.w * a.ldz;
   unsigned int n_hit = 0, n_pred = 0;
   const int npix = (Y1 - Y0) * a.W;
-  for (int i = warp; i < npix; i += 8) {
-    const int Y = Y0 + i / a.W, X = i - (i / a.W) * a.W;
+  const int R = Y1 - Y0, nidx = ((a.W + 3) / 4) * 4 * R;
+  for (int i = warp; i < nidx; i += 8) {
+    const int cb = i / (4 * R), q = i - cb * (4 * R);
+    const int wcols = min(4, a.W - cb * 4);
+    const int Y = Y0 + q / wcols, X = cb * 4 + q % wcols;
+    if (Y >= Y1) continue;
     const HiPix h = hi_pix(a.ty, a.tx, Y, X);
     const int t = a.mask ? target_of(a, img, Y, X) : 0;
     const PixStats ps = pixel_stats(zb, a.w, a.ldz, a.C, h, t, false, true);
@@ -287,22 +350,21 @@ __global__ void mc_mul_mask_kernel(const float* __restrict__ x, const float* __r
 int mc_loss_chunks(int H) { return cdiv(H, kMcRowsPerBlock); }
 
 void mc_loss_fwd_bwd(const McLossArgs& a, cudaStream_t s) {
-  const int chunks = mc_loss_chunks(a.H);
-  MLIIS_COUNT(), mc_loss_fwd_kernel<<<dim3(chunks, a.B), 256, 0, s>>>(a);
+  const int chunks = a.h * a.w;                       // one partial pair per low-res cell
+  const size_t smem_fwd = (size_t)4 * a.C * sizeof(float);
+  MLIIS_COUNT(), mc_loss_fwd_kernel<<<a.B * chunks, 256, smem_fwd, s>>>(a);
   float* l2p = a.partials + (size_t)a.B * chunks * 2;
   int nl2 = 0;
   if (a.loss_out && a.l2_coef != 0.f && a.n_l2 > 0) {
     nl2 = 148;
     sumsq_partials(a.theta, a.n_l2, l2p, nl2, s);
   }
-  MLIIS_COUNT(), mc_loss_finalize_kernel<<<1, 32, 0, s>>>(a, chunks, l2p, nl2);
-  const size_t smem = (size_t)9 * a.C * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(mc_loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
-  }
-  MLIIS_COUNT(), mc_loss_bwd_kernel<<<a.B * a.h * a.w, 256, smem, s>>>(a);
+  MLIIS_COUNT(), mc_loss_finalize_kernel<<<1, 256, 0, s>>>(a, chunks, l2p, nl2);
+  MLIIS_COUNT(), mc_loss_bwd_cell_kernel<<<a.B * a.h * a.w, 256, 0, s>>>(a, a.cellgrad);
+  const int ld4 = a.lddz / 4;
+  const int64_t total = (int64_t)a.B * a.h * a.w * ld4;
+  MLIIS_COUNT(), mc_loss_bwd_gather_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, s>>>(a.cellgrad, a.dz_lo, a.B, a.h, a.w,
+                                                                                    ld4);
 }
 
 void mc_predict(const McLossArgs& a, int32_t* class_map, uint32_t* inter, uint32_t* uni, cudaStream_t s) {

@@ -179,6 +179,7 @@ struct McLossArgs {
   float* partials;                // [B][chunks][2] (+ 148 L2 partials)
   float* coef;                    // [B]
   float* dz_lo; int lddz;         // out [B*h*w, lddz]
+  float* cellgrad;                // scratch [B*h*w][4][lddz]: per-cell corner sums of the backward pass
   float* loss_out;                // nullable
   const float* theta; int64_t n_l2; float l2_coef;
 };

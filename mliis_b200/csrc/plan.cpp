@@ -327,6 +327,7 @@ void Plan::build(int image_size_, int max_batch, const int* rsd, float final_dro
     dz_hi = b.alloc((int64_t)B * HWf * 2);
   } else {
     mc_lse = b.alloc((int64_t)B * HWf);
+    mc_cellgrad = b.alloc((int64_t)B * HWl * 4 * Cp);
     mc_wp = b.alloc((int64_t)D * Cp);
     mc_bp = b.alloc(Cp);
     mc_gwp = b.alloc((int64_t)D * Cp);
@@ -335,7 +336,7 @@ void Plan::build(int image_size_, int max_batch, const int* rsd, float final_dro
     upd(max_wT, (int64_t)D * Cp);
     upd(max_tn, (int64_t)gemm_tn_scratch(B * HWl, D, Cp, 0));
     upd(max_tn, (int64_t)tc_wgrad_scratch(0, B * HWl, B, hl, wl, Cp, D, 1));      // swapped roles
-    upd(max_partials, (int64_t)B * ((image_size + 3) / 4) * 2 + 148 + 64);
+    upd(max_partials, (int64_t)B * HWl * 2 + 148 + 64);      // one (CE, I) pair per low-res cell + L2 partials
     upd(max_partials, (int64_t)rc_num_img_chunks(B * HWl, Cp) * Cp + 64);
   }
   dropmask = final_dropout_rate > 0.f ? b.alloc((int64_t)B * HWl * D) : -1;

@@ -85,7 +85,7 @@ struct Plan {
   int64_t z_lo = 0, dz_lo = 0, p1 = 0, dz_hi = 0, dropmask = 0;
   // multi-class head (n_out > 2): logits padded to Cp columns, padded head operand / gradient, lse scratch
   int Cp = 2;
-  int64_t mc_lse = 0, mc_wp = 0, mc_bp = 0, mc_gwp = 0, mc_gbp = 0, mc_xdrop = 0;
+  int64_t mc_lse = 0, mc_wp = 0, mc_bp = 0, mc_gwp = 0, mc_gbp = 0, mc_xdrop = 0, mc_cellgrad = 0;
   int64_t bn_mean = 0, bn_rstd = 0, bn_a = 0, bn_b = 0, bn_k = 0;
   int64_t grads = 0;
   int64_t gY[2] = {0, 0}, gP = 0, gD = 0, gE = 0;
