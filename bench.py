@@ -343,7 +343,10 @@ def run_b200(args):
     achieved = k_flops / (k_ms * 1e-3) / 1e12
     roof = {"bound": "tensor", "kernel": "conv2d_2 3x3 360->112 @56x56 B=8 (implicit GEMM M=25088 N=112 K=3240)",
             "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-            "traffic": None, "peak_source": "%s bf16 burst (kernel timed alone)" % peak_src,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r01e_ncu_full_step.md:
+            # 39.06 MB read, 0.00 MB written - the 11.2 MB output was still in L2); algorithmic bytes 48.8 MB
+            "traffic": 39.06e6 if mode == N.GEMM_TF32X3 else None, "traffic_unit": "bytes per launch",
+            "peak_source": "%s bf16 burst (kernel timed alone)" % peak_src,
             "kernel_ms": k_ms, "algorithmic_gflop": k_flops / 1e9,
             "numeric_mode": {N.GEMM_FP32: "fp32 FFMA", N.GEMM_TF32: "tcgen05 tf32", N.GEMM_TF32X3: "tcgen05 3xtf32"}[mode]}
     cpu = None
