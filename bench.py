@@ -44,8 +44,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--tasks-per-step", type=int, default=16)
-    ap.add_argument("--slots", type=int, default=8)
+    ap.add_argument("--tasks-per-step", type=int, default=24)
+    ap.add_argument("--slots", type=int, default=12)
     ap.add_argument("--gemm-mode", default="auto", choices=["auto", "fp32", "tf32", "tf32x3"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")

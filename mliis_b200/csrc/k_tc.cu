@@ -157,7 +157,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // wide: hi and lo weight planes are adjacent in the stage, so one N = 2*BN MMA forms a_hi*b_hi | a_hi*b_lo in two
   // accumulator column ranges that the epilogue adds (A is fetched from shared memory twice per k-step, not three times)
-  const bool wide = x3 && 2 * p.BN <= 256 && !(p.debug & 8);
+  // (short-K layers are latency-bound, not MMA-bound: they keep the narrow accumulator so that more CTAs fit the
+  //  512 TMEM columns of an SM)
+  const bool wide = x3 && 2 * p.BN <= 256 && !(p.debug & 8) && (p.taps * ((p.C + 31) / 32) >= 4 || 2 * p.BN <= 128);
   uint32_t ncols = 32;
   while ((int)ncols < (wide ? 2 : 1) * p.BN) ncols <<= 1;
 
