@@ -528,3 +528,28 @@ def test_adaptation_from_pretrained_state_all_modes():
         assert e_theta < 1e-3, (mode, e_theta)
         assert abs(iou - iou_ref) < 0.005, (mode, iou, iou_ref)
         assert e_logits < 0.5, (mode, e_logits)
+
+
+def test_engine_against_committed_oracle_fixture():
+    """The CUDA path against the COMMITTED fixture tests/golden/oracle_small.npz (float64 oracle outputs on a seeded
+    32x32 problem; generated by tests/golden/make_golden.py), without running the oracle."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_small.npz"))
+    arch, theta, bn, images, labels = make_problem(32, 2, task_id=3, theta_seed=1)
+    for mode, tol in ((0, 1e-4), (2, 3e-4)):
+        eng = make_engine(arch, theta, bn, 32, 2, gemm_mode=mode)
+        xd, yd = _dev(images), _dev(labels)
+        logits = eng.forward(0, xd, True)
+        loss, grads = eng.loss_backward(0, yd, 2)
+        torch.cuda.synchronize()
+        assert abs(loss.item() - float(gold["loss"])) < 1e-4 * max(1.0, abs(float(gold["loss"])))
+        assert np.abs(logits.cpu().numpy()[:, ::4, ::4, :] - gold["logits"]).max() < 1e-3
+        sel = np.arange(0, arch.n_params, 997)
+        g = eng.tf_order_vector(grads).cpu().double().numpy()
+        assert np.linalg.norm(g[sel] - gold["grad_sel"]) < tol * 10 * np.linalg.norm(gold["grad_sel"])
+        assert abs(np.linalg.norm(g) - float(gold["grad_norm"])) < 1e-3 * float(gold["grad_norm"])
+        eng.optimizer_step(0, 1e-3)
+        torch.cuda.synchronize()
+        th1 = eng.tf_order_vector(eng.theta(0)).cpu().double().numpy()
+        assert np.linalg.norm(th1[sel] - gold["theta1_sel"]) < 1e-3 * np.linalg.norm(gold["theta1_sel"])
+        assert np.abs(eng.bn_state(0)[0, :64].cpu().numpy() - gold["bn_mean_head"]).max() < 1e-5
