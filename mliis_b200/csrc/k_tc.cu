@@ -720,6 +720,9 @@ struct TcWgParams {
   int taps, dil;
   int splits, tiles_total;
   int stages, split;
+  // share: conv mode, one CTA makes the 3 horizontal taps of a filter row from ONE halo'd A box {32 ch, BX+2*dil, BY}
+  // (tap dx = the same slab read through a descriptor start shifted by dx*dil pixel rows); grid.y = 3 filter rows
+  int share, a_group_bytes, a_tx_bytes;
   int debug;                   // MLIIS_TC_DEBUG bits (bottleneck experiments only): 1 skip transform, 2 skip MMA
   const float* pa; const float* pb; const float* gate;   // A prologue (plain mode), as in tc_conv_kernel
   int HW;
@@ -731,6 +734,10 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) 
   //  LBO (bits 16..29) = 4096 B >> 4 : stride between 32-channel groups along M/N
   //  SBO (bits 32..45) =  512 B >> 4 : stride between 4-row atoms along K
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (256ull << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
+}
+
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc_lbo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(lbo_bytes >> 4) << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
 }
 
 constexpr int kWgGroupBytes = 32 * 128;   // one TMA box: 32 pixel rows x 32 channels fp32
@@ -747,7 +754,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   const bool x3 = p.split == 3;
-  const int a_bytes = 4 * kWgGroupBytes, g_bytes = p.NG * kWgGroupBytes;
+  const int a_group = p.share ? p.a_group_bytes : kWgGroupBytes;
+  const int a_bytes = 4 * a_group, g_bytes = p.NG * kWgGroupBytes;
   const int a_lo = a_bytes;                                  // offset of the A lo plane (x3)
   const int g_off = x3 ? 2 * a_bytes : a_bytes;
   const int g_lo = g_off + g_bytes;
@@ -763,10 +771,11 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // wide: the G lo plane starts right behind the hi plane's last 32-channel group, so [G_hi | G_lo] is one MN-major
   // operand of 2*NG groups: one N = 64*NG MMA forms a_hi*g_hi | a_hi*g_lo (epilogue adds the two column ranges)
-  const bool wide = x3 && p.NG <= 4;
+  const bool wide = x3 && p.NG <= 4 && !p.share;       // share: three tap accumulators of BN columns each
   const int wide_off = p.NG * 32;
+  const int ntap = p.share ? 3 : 1;
   uint32_t ncols = 32;
-  while ((int)ncols < (wide ? 2 * wide_off : p.BN)) ncols <<= 1;
+  while ((int)ncols < (p.share ? 3 * p.BN : (wide ? 2 * wide_off : p.BN))) ncols <<= 1;
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
@@ -788,7 +797,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int per = (p.tiles_total + p.splits - 1) / p.splits;
   const int t_beg = split * per, t_end = min(p.tiles_total, t_beg + per);
   const int KB = max(t_end - t_beg, 0);
-  const int dy = p.conv ? (tap / 3 - 1) * p.dil : 0, dx = p.conv ? (tap % 3 - 1) * p.dil : 0;
+  const int dy = p.conv ? ((p.share ? tap : tap / 3) - 1) * p.dil : 0;
+  const int dx = p.conv ? (p.share ? -p.dil : (tap % 3 - 1) * p.dil) : 0;       // share: left edge of the halo box
 
   if (warp == 0) {
     if (lane == 0) {
@@ -796,13 +806,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int s = kb % p.stages;
         mbar_wait(empty_bar(s), ((kb / p.stages) & 1) ^ 1);
         const uint32_t sa = base + (uint32_t)s * stage_bytes, sg = sa + g_off;
-        mbar_expect_tx(full_bar(s), (uint32_t)(a_bytes + g_bytes));
+        mbar_expect_tx(full_bar(s), (uint32_t)((p.share ? p.a_tx_bytes : a_bytes) + g_bytes));
         const int t = t_beg + kb;
         if (p.conv) {
           const int per_img = p.tiles_x * p.tiles_y;
           const int img = t / per_img, rem = t - img * per_img, ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
           const int x0 = tx * p.BX, y0 = ty * p.BY;
-          for (int g = 0; g < 4; ++g) tma_load_4d(sa + g * kWgGroupBytes, &tmA, full_bar(s), c0 + 32 * g, x0 + dx, y0 + dy, img);
+          for (int g = 0; g < 4; ++g) tma_load_4d(sa + g * a_group, &tmA, full_bar(s), c0 + 32 * g, x0 + dx, y0 + dy, img);
           for (int g = 0; g < p.NG; ++g) tma_load_4d(sg + g * kWgGroupBytes, &tmG, full_bar(s), 32 * g, x0, y0, img);
         } else {
           const int m0 = t * 32;
@@ -823,8 +833,26 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(ready_bar(s), (kb / p.stages) & 1);
         tc_fence_after();
         const uint32_t sa = base + (uint32_t)s * stage_bytes;
-        const uint64_t da = make_mnmajor_sw128_desc(sa), dal = make_mnmajor_sw128_desc(sa + a_lo);
         const uint64_t dg = make_mnmajor_sw128_desc(sa + g_off), dgl = make_mnmajor_sw128_desc(sa + g_lo);
+        if (p.share) {
+          // pixel rows of the halo slab: row(y, x) = y * (BX + 2*dil) + x ; tap t starts t*dil rows further right
+          const int rw = p.BX + 2 * p.dil, kpr = p.BX / 8;      // K-steps (8 pixels) per image row of the box
+          for (int t = 0; t < 3 && !(p.debug & 2); ++t) {
+            const uint32_t acc = tmem_acc + (uint32_t)(t * p.BN);
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t row = (uint32_t)((k / kpr) * rw + t * p.dil + (k % kpr) * 8);
+              const uint64_t da = make_mnmajor_sw128_desc_lbo(sa + row * 128u, (uint32_t)a_group);
+              const uint64_t dal = make_mnmajor_sw128_desc_lbo(sa + a_lo + row * 128u, (uint32_t)a_group);
+              const uint64_t adv = (uint64_t)(64 * k);
+              tc_mma_tf32(acc, da, dg + adv, idesc, (kb | k) ? 1u : 0u);
+              if (x3) {
+                tc_mma_tf32(acc, dal, dg + adv, idesc, 1u);
+                tc_mma_tf32(acc, da, dgl + adv, idesc, 1u);
+              }
+            }
+          }
+        } else {
+        const uint64_t da = make_mnmajor_sw128_desc(sa), dal = make_mnmajor_sw128_desc(sa + a_lo);
         for (int k = 0; k < 4 && !(p.debug & 2); ++k) {            // 4 atoms of 8 pixel rows: +1024 B each
           const uint64_t adv = (uint64_t)(64 * k);
           if (wide) {
@@ -837,6 +865,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               tc_mma_tf32(tmem_acc, da + adv, dgl + adv, idesc, 1u);
             }
           }
+        }
         }
         tc_commit(empty_bar(s));
       }
@@ -872,6 +901,15 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         a_hi[i] = h;
         if (x3) a_lop[i] = rn_tf32_4(v - h);
       }
+      if (p.share) {       // halo slab (no prologue in conv mode): 4 groups x a_group bytes, plain hi/lo split
+        const int na4 = a_bytes / 16;
+        for (int i = t + 1024; i < na4 && !(p.debug & 1); i += kWgXformThreads) {
+          const float4 v = a_hi[i];
+          const float4 h = rn_tf32_4(v);
+          a_hi[i] = h;
+          if (x3) a_lop[i] = rn_tf32_4(v - h);
+        }
+      }
       float4* g_hi = reinterpret_cast<float4*>(st + g_off);
       float4* g_lop = reinterpret_cast<float4*>(st + g_lo);
       const int ng4 = p.NG * 256;
@@ -887,34 +925,37 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const int c = c0 + r;
-    float* orow = partial + (((size_t)split * p.taps + tap) * p.C + c) * p.N;
     if (KB > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
     }
-    const uint32_t tbase = tmem_acc + ((uint32_t)(quarter * 32) << 16);
-    for (int cc = ((warp - 2) >> 2) * 16; cc < p.BN; cc += 16 * (kWgXformThreads / 128)) {   // two warps per TMEM lane quarter
-      uint32_t v[16];
-      __syncwarp();
-      if (KB > 0) {
-        tc_ld16(tbase + (uint32_t)cc, v);
-        if (wide) {
-          uint32_t w[16];
-          tc_ld16(tbase + (uint32_t)(wide_off + cc), w);
+    for (int tt = 0; tt < ntap; ++tt) {
+      const int tap_out = p.share ? tap * 3 + tt : tap;
+      float* orow = partial + (((size_t)split * p.taps + tap_out) * p.C + c) * p.N;
+      const uint32_t tbase = tmem_acc + (uint32_t)(tt * p.BN) + ((uint32_t)(quarter * 32) << 16);
+      for (int cc = ((warp - 2) >> 2) * 16; cc < p.BN; cc += 16 * (kWgXformThreads / 128)) {   // warps share a lane quarter
+        uint32_t v[16];
+        __syncwarp();
+        if (KB > 0) {
+          tc_ld16(tbase + (uint32_t)cc, v);
+          if (wide) {
+            uint32_t w[16];
+            tc_ld16(tbase + (uint32_t)(wide_off + cc), w);
 #pragma unroll
-          for (int q = 0; q < 16; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(w[q]));
+            for (int q = 0; q < 16; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(w[q]));
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = 0u;
         }
-      } else {
+        if (c < p.C) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = 0u;
-      }
-      if (c < p.C) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int n = cc + q * 4;
-          if (n < p.N)
-            st4(orow + n, f4(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
-                             __uint_as_float(v[q * 4 + 3])));
+          for (int q = 0; q < 4; ++q) {
+            const int n = cc + q * 4;
+            if (n < p.N)
+              st4(orow + n, f4(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
+                               __uint_as_float(v[q * 4 + 3])));
+          }
         }
       }
     }
@@ -946,7 +987,7 @@ size_t tc_wgrad_scratch(int conv, int M, int B, int H, int W, int C, int N, int 
   int tiles;
   if (conv) { int BX = W > 16 ? 32 : 16, BY = 32 / BX; tiles = B * ((W + BX - 1) / BX) * ((H + BY - 1) / BY); }
   else tiles = (M + 31) / 32;
-  int S = wg_splits((C + 127) / 128, taps, tiles);
+  int S = wg_splits((C + 127) / 128, taps == 9 ? 3 : taps, tiles);   // 3x3: the tap-shared grid has 3 filter rows
   return (size_t)S * taps * C * N;
 }
 
@@ -971,10 +1012,19 @@ bool tc_wgrad(const float* A, int lda, const float* G, int ldg, float* dW, float
     p.tiles_x = (W + p.BX - 1) / p.BX;
     p.tiles_y = (H + p.BY - 1) / p.BY;
     p.tiles_total = B * p.tiles_x * p.tiles_y;
+    static int share_on = -1;
+    if (share_on < 0) { const char* e = getenv("MLIIS_TC_WGRAD_SHARE"); share_on = e ? atoi(e) : 1; }
+    p.share = (share_on && taps == 9 && 3 * p.BN <= 512) ? 1 : 0;
     cuuint32_t box[4] = {32, (cuuint32_t)p.BX, (cuuint32_t)p.BY, 1};
+    cuuint32_t boxA[4] = {32, (cuuint32_t)(p.BX + (p.share ? 2 * dil : 0)), (cuuint32_t)p.BY, 1};
+    if (p.share) {
+      const int rows = (p.BX + 2 * dil) * p.BY;
+      p.a_tx_bytes = 4 * rows * 128;
+      p.a_group_bytes = (rows * 128 + 511) / 512 * 512;        // slabs start on swizzle-atom (512 B) boundaries
+    }
     cuuint64_t dA[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t sA[3] = {(cuuint64_t)lda * 4, (cuuint64_t)W * lda * 4, (cuuint64_t)H * W * lda * 4};
-    if (!encode(&tmA, A, 4, dA, sA, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return false;
+    if (!encode(&tmA, A, 4, dA, sA, boxA, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return false;
     cuuint64_t dG[4] = {(cuuint64_t)N, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t sG[3] = {(cuuint64_t)ldg * 4, (cuuint64_t)W * ldg * 4, (cuuint64_t)H * W * ldg * 4};
     if (!encode(&tmG, G, 4, dG, sG, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return false;
@@ -989,9 +1039,11 @@ bool tc_wgrad(const float* A, int lda, const float* G, int ldg, float* dW, float
     if (!encode(&tmG, G, 2, dG, sG, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return false;
   }
   const int ctiles = (C + 127) / 128;
-  p.splits = wg_splits(ctiles, taps, p.tiles_total);
-  const int stage_bytes = (p.split == 3 ? 2 : 1) * (4 + p.NG) * kWgGroupBytes;
-  p.stages = (200 * 1024) / stage_bytes;
+  const int grid_taps = p.share ? 3 : taps;
+  p.splits = wg_splits(ctiles, grid_taps, p.tiles_total);
+  const int planes = p.split == 3 ? 2 : 1;
+  const int stage_bytes = planes * ((p.share ? 4 * p.a_group_bytes : 4 * kWgGroupBytes) + p.NG * kWgGroupBytes);
+  p.stages = (216 * 1024) / stage_bytes;
   if (p.stages > 6) p.stages = 6;
   const int per = (p.tiles_total + p.splits - 1) / p.splits;
   if (p.stages > per) p.stages = per;
@@ -1002,7 +1054,7 @@ bool tc_wgrad(const float* A, int lda, const float* G, int ldg, float* dW, float
     cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
-  dim3 grid(ctiles, taps, p.splits);
+  dim3 grid(ctiles, grid_taps, p.splits);
   MLIIS_COUNT(), tc_wgrad_kernel<<<grid, kWgThreads, smem, s>>>(tmA, tmG, scratch, p);
   reduce_partials(scratch, p.splits, taps * C * N, dW, s);
   return true;
