@@ -1014,7 +1014,12 @@ bool tc_wgrad(const float* A, int lda, const float* G, int ldg, float* dW, float
     p.tiles_total = B * p.tiles_x * p.tiles_y;
     static int share_on = -1;
     if (share_on < 0) { const char* e = getenv("MLIIS_TC_WGRAD_SHARE"); share_on = e ? atoi(e) : 1; }
-    p.share = (share_on && taps == 9 && 3 * p.BN <= 512) ? 1 : 0;
+    // tap sharing pays when every CTA still walks a long pixel range (>= 8 K-blocks of 32 pixels); the small 14x14
+    // layers keep one tap per CTA (measured: 21 -> 31 us with sharing, three epilogues and a short pipeline per CTA)
+    {
+      const int ct = (C + 127) / 128, s3 = 296 / (ct * 3) > 0 ? 296 / (ct * 3) : 1;
+      p.share = (share_on && taps == 9 && 3 * p.BN <= 512 && p.tiles_total / s3 >= 8) ? 1 : 0;
+    }
     cuuint32_t box[4] = {32, (cuuint32_t)p.BX, (cuuint32_t)p.BY, 1};
     cuuint32_t boxA[4] = {32, (cuuint32_t)(p.BX + (p.share ? 2 * dil : 0)), (cuuint32_t)p.BY, 1};
     if (p.share) {
