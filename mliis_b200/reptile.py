@@ -45,7 +45,8 @@ class Gecko:
     """A meta-learning session for image segmentation that extends Reptile (reptile.py:23-62)."""
 
     def __init__(self, session, variables=None, transductive=False, pre_step_op=None, lr_scheduler=None,
-                 augment: bool = False, aug_rate: Optional[float] = None, fast_path: bool = True):
+                 augment: bool = False, aug_rate: Optional[float] = None, fast_path: bool = True,
+                 meta_task_slots: Optional[int] = None):
         self.session = session
         model = session.model
         self._model = model
@@ -66,6 +67,14 @@ class Gecko:
         self.aug_rate = aug_rate
         self.fast_path = fast_path
         self._runner = None
+        # meta-training: 1 = the reference's sequential order (optimizer slots / BN statistics flow task -> task);
+        # S > 1 = S task slots adapt the tasks of a meta-batch concurrently, each slot carrying its own optimizer
+        # slots, BN statistics averaged over slots after the meta-step - the same documented semantics as S ranks
+        # (SURVEY.md 8e); exact for the trainables under --sgd up to summation order
+        if meta_task_slots is None:
+            meta_task_slots = int(os.environ.get("MLIIS_META_TASK_SLOTS", "1"))
+        self.meta_task_slots = max(1, int(meta_task_slots))
+        self._train_slots = None
         print("Augmentation rate {}".format(self.aug_rate))
         print("Using transduction in meta-learning." if transductive else "Not using transduction in meta-learning.")
         self.meta_fn = "Reptile"
@@ -159,6 +168,9 @@ class Gecko:
         import torch
         eng = self._model.engine()
         rank, world = _dist()
+        if self.meta_task_slots > 1 and eng.n_slots > 1:
+            return self._train_step_slots(dataset, num_shots, inner_batch_size, inner_iters, replacement,
+                                          meta_step_size, meta_batch_size, lr_ph, lr, fomaml)
         theta = eng.theta(0)
         old = theta.clone()
         dsum = torch.zeros_like(theta)
@@ -187,6 +199,38 @@ class Gecko:
         from .runner import allreduce_meta
         allreduce_meta(dsum, eng.bn_state(0))                # one all-reduce of P floats per meta-step
         eng.meta_apply(theta, dsum, float(meta_step_size) / float(meta_batch_size))
+
+    def _train_step_slots(self, dataset, num_shots, inner_batch_size, inner_iters, replacement, meta_step_size,
+                          meta_batch_size, lr_ph, lr, fomaml: bool):
+        """Slot-parallel meta-step: this rank's tasks are dealt round-robin to S task slots; every slot replays one
+        CUDA graph per task (theta <- theta_old, the inner steps, delta accumulation) on its own stream."""
+        import torch
+        from .runner import TrainSlots, allreduce_meta
+        eng = self._model.engine()
+        rank, world = _dist()
+        plans = []
+        for t in range(meta_batch_size):
+            task, rows = _sample_task_indices(dataset, num_shots)        # every rank draws every task
+            batches = self._task_batches_for_training(rows, inner_batch_size, inner_iters, replacement)
+            if t % world == rank:
+                plans.append((task, rows, batches))
+        if plans:
+            n_batches = len(plans[0][2])
+            lrs = self._fomaml_lrs(lr_ph, lr, n_batches) if fomaml else self._train_lrs(lr_ph, lr, n_batches)
+            shape = (len(plans[0][1]), tuple(len(b) for b in plans[0][2]), tuple(tuple(l) for l in lrs), fomaml,
+                     self._pre_decay())
+            if self._train_slots is None or self._train_slots.shape != shape:
+                self._train_slots = TrainSlots(eng, min(self.meta_task_slots, eng.n_slots), shape)
+            ts = self._train_slots
+            ts.begin(eng.theta(0))
+            for i, (task, rows, batches) in enumerate(plans):
+                images, labels = task.arrays()
+                ts.submit(i % ts.n, images[:len(rows)], labels[:len(rows)], batches)
+            dsum = ts.finish()
+        else:
+            dsum = torch.zeros_like(eng.theta(0))
+        allreduce_meta(dsum, eng.bn_state(0))
+        eng.meta_apply(eng.theta(0), dsum, float(meta_step_size) / float(meta_batch_size))
 
     def _fomaml_lrs(self, lr_ph, lr, n_batches):
         d = float(self._model.lr_ph.default)

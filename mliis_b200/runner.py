@@ -201,6 +201,109 @@ def gather_owned(values: np.ndarray, device=None) -> np.ndarray:
     return t.cpu().numpy()
 
 
+class TrainSlots:
+    """S task slots that adapt meta-TRAINING tasks concurrently (Gecko / FOMLIS.train_step, reptile.py:64-125,
+    :605-647).  Per slot one CUDA graph: theta_s <- theta_old (trainables only: optimizer slots, beta powers and BN
+    moving statistics are NOT reset between tasks, reptile.py:34 vs :102,:123), the inner steps, and
+    dsum_s += theta_s - theta_ref (theta_ref = theta_old for Reptile, the weights before the last step for FOMAML).
+    Inputs live in per-slot staging buffers so that the graph can be replayed for every task."""
+
+    def __init__(self, eng: Engine, n: int, shape):
+        n_pool, batch_sizes, lrs, fomaml, pre_decay = shape
+        self.eng, self.n, self.shape, self.fomaml = eng, n, shape, fomaml
+        S, dev = eng.image_size, eng.device
+        self.old = torch.empty(eng.n_theta, dtype=torch.float32, device=dev)
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(n)]
+        self.x = [torch.empty(n_pool, S, S, 3, dtype=torch.float32, device=dev) for _ in range(n)]
+        self.y = [torch.empty(n_pool, S, S, 2, dtype=torch.float32, device=dev) for _ in range(n)]
+        self.xp = [torch.empty(n_pool, S, S, 3, dtype=torch.float32).pin_memory() for _ in range(n)]
+        self.yp = [torch.empty(n_pool, S, S, 2, dtype=torch.float32).pin_memory() for _ in range(n)]
+        self.idx = [[torch.zeros(b, dtype=torch.int32, device=dev) for b in batch_sizes] for _ in range(n)]
+        self.idxp = [[torch.zeros(b, dtype=torch.int32).pin_memory() for b in batch_sizes] for _ in range(n)]
+        self.dsum = [torch.zeros(eng.n_theta, dtype=torch.float32, device=dev) for _ in range(n)]
+        self.backup = [torch.empty(eng.n_theta, dtype=torch.float32, device=dev) if fomaml else None
+                       for _ in range(n)]
+        self.graphs = [None] * n
+        self.used = [False] * n
+        self._state_ready = False
+        self._lrs, self._pre_decay = lrs, pre_decay
+
+    def _body(self, s: int) -> None:
+        eng = self.eng
+        theta = eng.theta(s)
+        theta.copy_(self.old)
+        T = len(self._lrs)
+        for j in range(T):
+            if self.fomaml and j == T - 1:
+                self.backup[s].copy_(theta)                       # last_backup (reptile.py:635-636)
+            for k, step_lr in enumerate(self._lrs[j]):
+                eng.train_step(s, self.x[s], self.y[s], step_lr, index=self.idx[s][j],
+                               pre_decay_rate=self._pre_decay if k == 0 else 1.0, seed=1 + j)
+        eng.delta_accumulate(self.dsum[s], theta, self.backup[s] if self.fomaml else self.old, first=False)
+
+    def _capture(self, s: int) -> None:
+        st = self.streams[s]
+        with torch.cuda.stream(st):
+            self._body(s)            # warm-up outside the graph (one-time memsets / attribute calls); the slot's
+            st.synchronize()         # optimizer / BN state advances by one task: restored by begin() below
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            self._body(s)
+        self.graphs[s] = g
+
+    def begin(self, theta_master: torch.Tensor) -> None:
+        eng = self.eng
+        torch.cuda.synchronize()
+        self.old.copy_(theta_master)
+        if not self._state_ready:
+            # every slot starts from the master's full state (like ranks start from the same checkpoint)
+            for s in range(1, self.n):
+                eng.states[s].copy_(eng.states[0])
+            snap = [eng.states[s].clone() for s in range(self.n)]
+            for s in range(self.n):
+                self.x[s].zero_()
+                self.y[s].zero_()
+                self._capture(s)
+            torch.cuda.synchronize()
+            for s in range(self.n):
+                eng.states[s].copy_(snap[s])
+            self._state_ready = True
+        for s in range(self.n):
+            self.dsum[s].zero_()
+            self.used[s] = False
+        torch.cuda.synchronize()
+
+    def submit(self, s: int, images: np.ndarray, labels: np.ndarray, batches) -> None:
+        st = self.streams[s]
+        st.synchronize()                                   # the slot's pinned staging is free again
+        self.xp[s].copy_(torch.from_numpy(np.ascontiguousarray(images, np.float32)))
+        self.yp[s].copy_(torch.from_numpy(np.ascontiguousarray(labels, np.float32)))
+        for j, b in enumerate(batches):
+            self.idxp[s][j].copy_(torch.as_tensor(np.asarray(b, np.int32)))
+        with torch.cuda.stream(st):
+            self.x[s].copy_(self.xp[s], non_blocking=True)
+            self.y[s].copy_(self.yp[s], non_blocking=True)
+            for j in range(len(batches)):
+                self.idx[s][j].copy_(self.idxp[s][j], non_blocking=True)
+            self.graphs[s].replay()
+        self.used[s] = True
+
+    def finish(self) -> torch.Tensor:
+        """sum of the slot deltas; BN moving statistics averaged over the slots that ran and written back to all;
+        the master trainables (slot 0) restored to theta_old."""
+        eng = self.eng
+        torch.cuda.synchronize()
+        used = [s for s in range(self.n) if self.used[s]]
+        total = self.dsum[used[0]].clone()
+        for s in used[1:]:
+            total.add_(self.dsum[s])
+        bn = torch.stack([eng.bn_state(s) for s in used]).mean(0)
+        for s in range(self.n):
+            eng.bn_state(s).copy_(bn)
+        eng.theta(0).copy_(self.old)
+        return total
+
+
 def allreduce_meta(delta_sum: torch.Tensor, bn_state: Optional[torch.Tensor] = None) -> None:
     """The one exchange step of a meta-update: SUM of the per-rank task deltas (8.29 MB fp32) and, for world > 1,
     the average of the BN moving statistics."""

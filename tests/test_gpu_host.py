@@ -248,3 +248,40 @@ def test_tfrecord_tasks_equal_synthetic_tasks_on_the_device_fast_path(tmp_path):
                               test_shots=5, is_training_ph=m.is_training_ph, lr_ph=m.lr_ph, lr=1e-3))
     assert out[0][0] == out[1][0]
     assert list(out[0][1].values()) == list(out[1][1].values())
+
+
+@pytest.mark.parametrize("foml", [False, True])
+def test_slot_parallel_meta_step_equals_sequential_under_sgd(foml):
+    """meta_task_slots > 1: tasks of a meta-batch adapt concurrently on task slots (one CUDA graph per slot).  With
+    SGD the trainables do not depend on the order in which tasks ran (training-mode BN uses batch statistics), so
+    the meta-update must equal the sequential reference order up to summation order."""
+    from functools import partial
+    from mliis_b200.reptile import FOMLIS, Gecko
+    from mliis_b200.session import Session
+    out, bn = [], []
+    for slots in (1, 3):
+        m = _model(optimizer="sgd", task_slots=3)
+        sess = Session(m)
+        _warm(sess, m, 2)
+        tasks = _tasks(6, 800, n_examples=15)
+        random.seed(11)
+        if foml:
+            learner = FOMLIS(sess, train_shots=10, tail_shots=5, meta_task_slots=slots)
+            kw = dict(num_shots=10, inner_iters=3)
+        else:
+            learner = Gecko(sess, meta_task_slots=slots)
+            kw = dict(num_shots=5, inner_iters=3)
+        for _ in range(2):       # two meta-steps: the second replays the captured graphs
+            learner.train_step(tasks, m.input_ph, m.label_ph, m.minimize_op, num_classes=1, inner_batch_size=4,
+                               replacement=False, meta_step_size=0.5, meta_batch_size=4, lr_ph=m.lr_ph, lr=None, **kw)
+        eng = m.engine()
+        torch.cuda.synchronize()
+        out.append(eng.tf_order_vector(eng.theta(0)).double().cpu())
+        bn.append(eng.bn_state(0).double().cpu().clone())
+        after = random.random()
+        out.append(after)
+    (th_seq, r_seq, th_par, r_par) = out
+    assert r_seq == r_par                                       # identical consumption of the `random` stream
+    rel = ((th_par - th_seq).norm() / th_seq.norm()).item()
+    assert rel < 1e-5, rel
+    assert torch.isfinite(bn[1]).all()
