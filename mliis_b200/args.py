@@ -54,6 +54,9 @@ _FLAGS = [
     # ---- additions of this implementation (absent from the reference) ----
     ("--gemm_mode", _S, "fp32", {"help": "numeric mode of the dense contractions: fp32 | tf32 | tf32x3"}),
     ("--task_slots", _I, 8, {"help": "concurrent task slots per GPU on the device fast path"}),
+    ("--meta_task_slots", _I, 1, {"help": "meta-training: task slots adapting the tasks of a meta-batch concurrently "
+                                          "(1 = the reference's sequential order; S > 1 = per-slot optimizer state, "
+                                          "like S ranks)"}),
     ("--synthetic_tasks", _I, 0, {"help": "use N synthetic FSS-1000-shaped test tasks instead of tfrecord shards"}),
 ]
 

@@ -47,6 +47,7 @@ def main():
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("nccl")
 
+    os.environ["MLIIS_META_TASK_SLOTS"] = str(getattr(args, "meta_task_slots", 1))   # read by Gecko / FOMLIS
     random.seed(args.seed)          # the ONLY seed the reference sets (run_metasegnet.py:43)
     print("Defining model architecture:")
     mk = model_kwargs(args)

@@ -27,7 +27,7 @@ def test_cli_flags_match_reference():
             if spec.get("nargs"):
                 assert a.nargs == spec["nargs"], flag
     extra = set(actions) - set(gold)
-    assert extra == {"--gemm_mode", "--task_slots", "--synthetic_tasks"}
+    assert extra == {"--gemm_mode", "--task_slots", "--synthetic_tasks", "--meta_task_slots"}
 
 
 def test_run_sh_command_line_parses():
