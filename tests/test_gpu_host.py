@@ -64,14 +64,17 @@ def test_session_idioms_and_variable_state():
         sess.run(m.minimize_op, feed_dict={m.input_ph: [np.zeros((SIZE, SIZE))], m.label_ph: y})
 
 
-def test_evaluate_fast_path_equals_session_path():
+@pytest.mark.parametrize("shots", [5, 1])
+def test_evaluate_fast_path_equals_session_path(shots):
+    """5-shot and 1-shot (BASELINE config 2; with one support image every inner batch is that image repeated,
+    metaseg.py:288-302)."""
     from mliis_b200.reptile import Gecko
     from mliis_b200.session import Session
     m = _model()
     sess = Session(m)
     _warm(sess, m)
     tasks = _tasks(5, 100)
-    kw = dict(num_classes=1, num_shots=5, inner_batch_size=8, inner_iters=3, replacement=False, eval_all_tasks=True,
+    kw = dict(num_classes=1, num_shots=shots, inner_batch_size=8, inner_iters=3, replacement=False, eval_all_tasks=True,
               is_training_ph=m.is_training_ph, lr_ph=m.lr_ph)
     before = m.engine().states[0].clone()
     random.seed(11)
