@@ -201,3 +201,56 @@ def test_float32_mode_close_to_float64():
     l32, g32, _, _ = o32.loss_and_grad(theta.float(), bn.float(), x, y)
     assert abs(l64.item() - l32.item()) < 1e-4
     assert ((g32.double() - g64).norm() / g64.norm()).item() < 1e-3
+
+
+def test_multiclass_loss_restatement():
+    """The joint-training loss (efficientlab.py:294-327 with binary_iou_loss=False, :369-396): hand computation from
+    the formulas, the reduction to sparse labels used by the CUDA kernels, and a finite-difference check."""
+    torch.manual_seed(0)
+    B, H, C = 2, 6, 5
+    arch = Arch(n_out=C)
+    orc = EfficientLabOracle(arch, torch.float64, binary_iou_loss=False, l2=False, label_smoothing=0.1)
+    logits = torch.randn(B, H, H, C, dtype=torch.float64)
+    fg = (torch.rand(B, H, H) > 0.5)
+    cls = torch.tensor([2, 4])
+    t = torch.where(fg, cls[:, None, None].expand(B, H, H), torch.zeros(B, H, H, dtype=torch.long))
+    y = F.one_hot(t, C).double()
+    theta = torch.zeros(arch.n_params, dtype=torch.float64)
+    loss = orc.loss(theta, logits, y).item()
+    # by hand, pixel by pixel
+    p = torch.softmax(logits, -1)
+    ce = 0.0
+    for b in range(B):
+        for i in range(H):
+            for j in range(H):
+                ys = y[b, i, j] * 0.9 + 0.1 / C                      # tf.losses label_smoothing [TF-ext]
+                ce -= float((ys * torch.log(p[b, i, j])).sum())
+    ce /= B * H * H
+    ious = []
+    for b in range(B):
+        inter = float((p[b] * y[b]).sum())
+        den = float(p[b].sum() + y[b].sum()) - inter
+        ious.append((inter + 1e-7) / (den + 1e-7))
+    iou = sum(ious) / B
+    assert abs(loss - (ce - np.log(2 * iou / (iou + 1)))) < 1e-12
+    # sparse form used on the device: sum_c y = sum_c p = 1 per pixel  =>  IoU_b = (I_b + eps) / (2HW - I_b + eps)
+    I = p.gather(-1, t[..., None])[..., 0].reshape(B, -1).sum(1)
+    iou_sparse = ((I + 1e-7) / (2 * H * H - I + 1e-7)).mean().item()
+    assert abs(iou_sparse - iou) < 1e-12
+    # finite differences of d loss / d logits
+    z = logits.clone().requires_grad_(True)
+    (g,) = torch.autograd.grad(orc.loss(theta, z, y), z)
+    rng = np.random.default_rng(0)
+    for _ in range(12):
+        idx = tuple(int(rng.integers(0, n)) for n in logits.shape)
+        e = torch.zeros_like(logits)
+        e[idx] = 1e-6
+        fd = (orc.loss(theta, logits + e, y) - orc.loss(theta, logits - e, y)).item() / 2e-6
+        assert abs(fd - g[idx].item()) < 1e-7 + 1e-5 * abs(fd)
+    # binary_iou_loss=True on a 2-channel problem scores channel 1 only: a different number
+    arch2 = Arch()
+    l_bin = EfficientLabOracle(arch2, torch.float64, l2=False).loss(torch.zeros(arch2.n_params, dtype=torch.float64),
+                                                                   logits[..., :2], y[..., :2])
+    l_all = EfficientLabOracle(arch2, torch.float64, l2=False, binary_iou_loss=False).loss(
+        torch.zeros(arch2.n_params, dtype=torch.float64), logits[..., :2], y[..., :2])
+    assert abs(l_bin.item() - l_all.item()) > 1e-3
