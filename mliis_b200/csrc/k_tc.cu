@@ -11,8 +11,20 @@
 // * 1x1 convolutions / plain GEMMs are the taps == 1 case with a 2-D map {K, M} and a {32, 128} box.
 // * dgrad is the same kernel on a gradient tensor and re-laid-out weights (tc_prep_weights).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (each owns the TMEM lane quarter warp_id % 4).
+// Kernels in this file:
+//   tc_conv_kernel   generic implicit GEMM (1x1 layers, and 3x3 layers whose halo'd tile does not fit tc_conv3)
+//   tc_conv3_kernel  3x3 / dilated 3x3: one halo'd A box per (filter row, K chunk) serves the three horizontal taps,
+//                    two pixel tiles per CTA (forward and dgrad of the decoder convolutions)
+//   tc_wgrad_kernel  weight gradients: pixels are the MMA K dimension, both operands MN-major
+//                    (SWIZZLE_128B_BASE32B); 3x3 layers share one halo'd A box across the three horizontal taps
+//   tc_prep_*        weight operand preparation (re-layout, round-to-nearest TF32, hi/lo planes for 3xTF32)
+// 3xTF32 (fp32-class accuracy): a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo; where the hi and lo planes of the B
+// operand are adjacent in shared memory one N = 2*BN MMA forms the first and third product together.
+//
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2.. = operand transform
+// (TF32 rounding / hi-lo split / fused BN+swish+gate prologue, in shared memory, during the main loop) and then
+// epilogue (each warp owns the TMEM lane quarter warp_id % 4).  4 such warps in the conv kernels (192 threads),
+// 16 in tc_wgrad_kernel, which has to split both operands.
 // Reference ops replaced: tf.layers.conv2d of models/efficientlab.py:185-188, :218-224 and their
 // Conv2DBackpropInput [TF-ext].
 #include <cuda.h>
