@@ -51,7 +51,12 @@ def parse():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--sgd", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--shots", type=int, default=5, choices=[1, 5],
+                    help="support images per task (BASELINE config 2 sweeps 1-shot and 5-shot; the headline is 5-shot)")
+    a = ap.parse_args()
+    global N_SHOTS
+    N_SHOTS = a.shots
+    return a
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -185,7 +190,7 @@ def run_reference(args):
     total = float(np.sum(times))
     value = len(times) / total
     line = {
-        "impl": "reference", "metric": "meta-test adapted-tasks/s (5-shot, 224x224, EfficientLab-6-3, 5 inner Adam steps)",
+        "impl": "reference", "metric": "meta-test adapted-tasks/s (%d-shot, 224x224, EfficientLab-6-3, 5 inner Adam steps)" % N_SHOTS,
         "value": value, "unit": "tasks/s", "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
         "ms_per_step": 1e3 * total / max(1, len(times)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -357,7 +362,7 @@ def run_b200(args):
                "sample": "2 synthetic tasks after a 1-step warm-up; torch-CPU float32 restatement of the reference "
                          "graph (oracle/), not TF-1.15"}
     line = {
-        "metric": "meta-test adapted-tasks/s (5-shot, 224x224, EfficientLab-6-3, 5 inner Adam steps)",
+        "metric": "meta-test adapted-tasks/s (%d-shot, 224x224, EfficientLab-6-3, 5 inner Adam steps)" % N_SHOTS,
         "value": value, "unit": "tasks/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {N.GEMM_FP32: "f32", N.GEMM_TF32: "tf32", N.GEMM_TF32X3: "tf32x3 (fp32-class)"}[mode], "data": "synthetic",
