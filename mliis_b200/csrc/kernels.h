@@ -13,7 +13,10 @@ extern unsigned long long g_kernel_launches;
 // MLIIS_SKIP=<comma-separated substrings of launcher function names> drops those launches (bottleneck experiments
 // only: results are garbage); unset in every normal run.
 bool skip_launch(const char* launcher);
-#define MLIIS_COUNT() if (::mliis::skip_launch(__func__)) {} else ++::mliis::g_kernel_launches
+// usage: `MLIIS_COUNT(), kernel<<<grid, block, smem, stream>>>(...);`  (a one-trip for statement: safe inside un-braced
+// if / else bodies, unlike an if / else macro)
+#define MLIIS_COUNT() \
+  for (bool mliis_go_ = !::mliis::skip_launch(__func__); mliis_go_; mliis_go_ = false) ++::mliis::g_kernel_launches
 
 // ---------------- row-channel kernels (k_rowchan.cu) : HBM-bound ----------------
 enum BnVar { BN_PLAIN = 0, BN_SWISH = 1, BN_SWISH_SE = 2, BN_DEC = 3 };
