@@ -208,7 +208,7 @@ typedef struct mliis_task_args {
 int mliis_adapt_eval_task(mliis_ctx* ctx, int32_t slot, const mliis_task_args* args, void* stream);
 
 /* The same task as ONE CUDA graph: capture once per slot with pointers that stay valid (per-slot staging
- * buffers for the pool, index lists, learning rates and outputs), then replay per task.  ~2800 kernel
+ * buffers for the pool, index lists, learning rates and outputs), then replay per task.  ~2300 kernel
  * launches collapse into one graph launch; slots replay concurrently on their own streams.  `stream` must
  * be a non-default stream.  (With final-layer dropout the device RNG seed is frozen at capture time.) */
 int mliis_task_graph_capture(mliis_ctx* ctx, int32_t slot, const mliis_task_args* args, void* stream);
