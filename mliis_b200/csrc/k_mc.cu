@@ -166,12 +166,18 @@ __global__ void __launch_bounds__(256) mc_loss_finalize_kernel(McLossArgs a, int
                                                                int n_l2_partials) {
   __shared__ double s_ce[256], s_I[256];
   const double eps = 1e-7, D = 2.0 * (double)a.H * (double)a.W;
-  for (int b = threadIdx.x; b < a.B; b += blockDim.x) {
+  // warp w sums the cell partials of images w, w+8, ...: lanes stride over the cells, then a fixed-order butterfly
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = warp; b < a.B; b += 8) {
     double ce = 0.0, I = 0.0;
     const float* p = a.partials + (size_t)b * chunks * 2;
-    for (int g = 0; g < chunks; ++g) { ce += p[2 * g]; I += p[2 * g + 1]; }
-    s_ce[b] = ce;
-    s_I[b] = I;
+    for (int g = lane; g < chunks; g += 32) { ce += p[2 * g]; I += p[2 * g + 1]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ce += __shfl_xor_sync(0xffffffffu, ce, o);
+      I += __shfl_xor_sync(0xffffffffu, I, o);
+    }
+    if (lane == 0) { s_ce[b] = ce; s_I[b] = I; }
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
