@@ -254,9 +254,9 @@ class Gecko:
             random.shuffle(dataset)        # in place, like the reference (reptile.py:186-188)
             sampled_tasks = dataset[:num_tasks_to_sample]
         print("Evaluating {} {}-shot tasks.".format(len(sampled_tasks), num_shots))
-        if save_fine_tuned_checkpoints:
-            raise NotImplementedError("per-task fine-tuned checkpoints (utils/util.py:72-81) are out of scope")
-        device_ok = (self.fast_path and self._transductive and is_training_ph is not None and drop_rate is None
+        # per-task fine-tuned checkpoints need the adapted state of every task on the host: Session path
+        device_ok = (self.fast_path and not save_fine_tuned_checkpoints and self._transductive
+                     and is_training_ph is not None and drop_rate is None
                      and inner_iters > 0 and all(hasattr(t, "arrays") for t in sampled_tasks))
         if device_ok:
             ious, task_iou_map = self._evaluate_device(sampled_tasks, num_shots, test_shots, inner_batch_size,
@@ -270,7 +270,9 @@ class Gecko:
                 train_set, test_set = _split_train_test_segmentation(sampled, test_shots)
                 task_iou = self._evaluate(train_set, test_set, input_ph, label_ph, minimize_op, predictions,
                                           inner_batch_size, inner_iters, replacement, verbose=verbose,
-                                          is_training_ph=is_training_ph, lr_ph=lr_ph, lr=lr, task_name=task_name,
+                                          save_fine_tuned_checkpoints=save_fine_tuned_checkpoints,
+                                          save_fine_tuned_checkpoints_dir=save_fine_tuned_checkpoints_dir,
+                                          eval_sample_num=eval_sample_num, is_training_ph=is_training_ph, lr_ph=lr_ph, lr=lr, task_name=task_name,
                                           drop_rate_ph=drop_rate_ph, drop_rate=drop_rate, aug_rate=aug_rate)
                 ious.append(task_iou)
                 task_iou_map[task_name] = task_iou
@@ -342,6 +344,10 @@ class Gecko:
             elif (lr_ph is not None) and (self.lr_scheduler is not None):
                 feed[lr_ph] = self.lr_scheduler.cur_lr(cur_step=inner_iter)
             self.session.run(minimize_op, feed_dict=feed)
+        if save_fine_tuned_checkpoints:          # reptile.py:281-285
+            from .util import save_fine_tuned_checkpoint
+            save_fine_tuned_checkpoint(os.path.join(save_fine_tuned_checkpoints_dir, task_name), self.session,
+                                       step=inner_iters - 1, eval_sample_num=eval_sample_num)
         test_preds = self._test_predictions(train_set, test_set, input_ph, predictions, is_training_ph,
                                             task_name=task_name)
         class_iou = [self._iou(test_preds[j], test_set[j][1]) for j in range(len(test_preds))]

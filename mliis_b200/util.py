@@ -34,3 +34,16 @@ def validate_datasets(args, train_set, val_set, test_set):
 def ci95(a):
     """95% confidence half-width: 1.96 * std / sqrt(n)  (utils/util.py:133-136)."""
     return 1.96 * np.std(a) / np.sqrt(len(a))
+
+
+def save_fine_tuned_checkpoint(save_fine_tuned_checkpoint_dir, sess, step=None, eval_sample_num=None):
+    """utils/util.py:72-81: dump the adapted variables of ONE task as a TF bundle
+    <dir>[/<eval_sample_num>]/model.ckpt-<step>."""
+    from .checkpoint import Saver
+    if save_fine_tuned_checkpoint_dir is None:
+        raise ValueError("Must specify directory in which to save fine-tuned checkpoints if saving them.")
+    if eval_sample_num is not None:
+        save_fine_tuned_checkpoint_dir = os.path.join(save_fine_tuned_checkpoint_dir, str(eval_sample_num))
+    os.makedirs(save_fine_tuned_checkpoint_dir, exist_ok=True)
+    Saver(sess.model).save(sess, os.path.join(save_fine_tuned_checkpoint_dir, "model.ckpt"), global_step=step)
+    print("Saved fine-tuned checkpoint to {}.".format(save_fine_tuned_checkpoint_dir))

@@ -288,3 +288,39 @@ def test_slot_parallel_meta_step_equals_sequential_under_sgd(foml):
     rel = ((th_par - th_seq).norm() / th_seq.norm()).item()
     assert rel < 1e-5, rel
     assert torch.isfinite(bn[1]).all()
+
+
+def test_fine_tuned_checkpoints_per_task(tmp_path):
+    """--save_fine_tuned_checkpoints (reptile.py:281-285, utils/util.py:72-81): one TF bundle per adapted task."""
+    from mliis_b200.checkpoint import read_bundle
+    from mliis_b200.eval import evaluate_gecko
+    from mliis_b200.session import Session
+    m = _model()
+    sess = Session(m)
+    _warm(sess, m, 2)
+    base = m.engine().tf_order_vector(m.engine().theta(0)).cpu().numpy().copy()
+    tasks = _tasks(2, 950)
+    random.seed(0)
+    mean_iou, iou_map = evaluate_gecko(sess, m, tasks, num_shots=5, eval_inner_batch_size=4, eval_inner_iters=2,
+                                       num_samples=1, transductive=True, serially_eval_all_tasks=True,
+                                       save_fine_tuned_checkpoints=True, save_fine_tuned_checkpoints_dir=str(tmp_path))
+    assert len(iou_map) == 2
+    for t in tasks:
+        prefix = os.path.join(str(tmp_path), t.name, "0", "model.ckpt-1")
+        tensors = read_bundle(prefix)
+        k = tensors["decode/final_layer_weights/kernel"]
+        assert k.shape == (1, 1, 112, 2)
+        # the bundle holds the ADAPTED weights of that task, not the meta-learned initialisation ...
+        p = [q for q in m.params if q.name == "decode/final_layer_weights/kernel"][0]
+        assert not np.allclose(k.reshape(-1), base[_tf_offset(m, p.name):_tf_offset(m, p.name) + k.size])
+    # ... and the model itself is back at the initialisation afterwards
+    assert np.array_equal(m.engine().tf_order_vector(m.engine().theta(0)).cpu().numpy(), base)
+
+
+def _tf_offset(m, name):
+    off = 0
+    for q in m.params:
+        if q.name == name:
+            return off
+        off += q.size
+    raise KeyError(name)
