@@ -194,3 +194,38 @@ def test_count_examples_matches_gzip_stream(tmp_path):
     assert tfrecord.count_examples_in_tfrecords(paths) == 10
     raw = gzip.open(paths[0], "rb").read()
     assert len(raw) == 5 * (12 + 4 + len(tfrecord.make_example(np.zeros((8, 8, 3), np.uint8), np.zeros((8, 8), np.uint8))))
+
+
+def test_image_folders_to_shards_tool(tmp_path):
+    """tools/fss1000_to_tfrecords.py (the reference's data/fss_1000_image_to_tfrecord.py without TF / imageio)."""
+    import importlib.util
+    from PIL import Image
+    spec = importlib.util.spec_from_file_location(
+        "fss_tool", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools",
+                                 "fss1000_to_tfrecords.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    src, dst = tmp_path / "fewshot_data", tmp_path / "shards"
+    rng = np.random.default_rng(0)
+    truth = {}
+    for cls in ("ab_wheel", "zebra"):
+        (src / cls).mkdir(parents=True)
+        for k in range(1, 4):
+            size = 16 if not (cls == "zebra" and k == 3) else 12          # one wrongly sized pair is skipped
+            img = rng.integers(0, 256, (size, size, 3), dtype=np.uint8)
+            msk = (rng.random((size, size)) > 0.5).astype(np.uint8) * 255
+            Image.fromarray(img).save(str(src / cls / ("%d.png" % k)).replace(".png", ".bmp"))   # lossless stand-in
+            os.rename(str(src / cls / ("%d.bmp" % k)), str(src / cls / ("%d.jpg" % k)))
+            Image.fromarray(np.stack([msk] * 3, axis=2)).save(str(src / cls / ("%d.png" % k)))
+            if size == 16:
+                truth[(cls, img.tobytes())] = msk
+    random.seed(0)
+    tool.main(["prog", "--input_dir", str(src), "--tfrecord_dir", str(dst), "--image_dims", "16"])
+    tr, _, te, _, _, _ = fss1000.read_fss_1000_dataset(str(dst), test_task_ids=["zebra"], image_size=16)
+    assert [t.name for t in tr] == ["ab_wheel.tfrecord.gzip"] and [t.batch_size for t in tr] == [3]
+    assert [t.name for t in te] == ["zebra.tfrecord.gzip"] and [t.batch_size for t in te] == [2]
+    for task, cls in ((tr[0], "ab_wheel"), (te[0], "zebra")):
+        images, masks = task.arrays()
+        for im, mk in zip(images, masks):
+            want = truth[(cls, im.astype(np.uint8).tobytes())]               # pairs stay together
+            np.testing.assert_array_equal(mk[..., 1], want.astype(np.float32) / np.float32(255))
