@@ -150,6 +150,8 @@ typedef struct mliis_step_args {
   const float*   dev_drop_mask;
   uint64_t       seed;
   float*         dev_loss_out;
+  const uint64_t* dev_seed;        /* optional device scalar added to `seed` when the dropout mask is drawn: lets a
+                                      captured CUDA graph draw fresh masks on every replay (NULL = seed only) */
 } mliis_step_args;
 int mliis_train_step(mliis_ctx* ctx, int32_t slot, const mliis_step_args* args, void* stream);
 
@@ -204,13 +206,16 @@ typedef struct mliis_task_args {
   uint32_t*      dev_inter_out;    /* [n_query]                                              */
   uint32_t*      dev_union_out;    /* [n_query]                                              */
   float*         dev_loss_out;     /* [n_steps] or NULL                                      */
+  const uint64_t* dev_seed;        /* optional device scalar: step t draws its final-layer dropout mask from
+                                      *dev_seed + seed + t, read at RUN time (graph replays see the staged value) */
 } mliis_task_args;
 int mliis_adapt_eval_task(mliis_ctx* ctx, int32_t slot, const mliis_task_args* args, void* stream);
 
 /* The same task as ONE CUDA graph: capture once per slot with pointers that stay valid (per-slot staging
  * buffers for the pool, index lists, learning rates and outputs), then replay per task.  ~2300 kernel
  * launches collapse into one graph launch; slots replay concurrently on their own streams.  `stream` must
- * be a non-default stream.  (With final-layer dropout the device RNG seed is frozen at capture time.) */
+ * be a non-default stream.  With final-layer dropout pass mliis_task_args.dev_seed (a staged device scalar): the
+ * host `seed` is a captured constant, the device scalar is read by every replay. */
 int mliis_task_graph_capture(mliis_ctx* ctx, int32_t slot, const mliis_task_args* args, void* stream);
 int mliis_task_graph_launch(mliis_ctx* ctx, int32_t slot, void* stream);
 

@@ -284,7 +284,7 @@ struct Dense {
 // forward
 // ------------------------------------------------------------------------------------------------
 void run_forward(const Run& r, const float* images, const int32_t* index, bool training, const float* dc_mask,
-                 const float* drop_mask, uint64_t seed) {
+                 const float* drop_mask, uint64_t seed, const uint64_t* seed_dev = nullptr) {
   const Plan& p = r.p;
   const int B = r.B;
   cudaStream_t st = r.st;
@@ -372,7 +372,7 @@ void run_forward(const Run& r, const float* images, const int32_t* index, bool t
   if (training && rate > 0.f) {
     if (drop_mask) mask = drop_mask;
     else {
-      fill_dropout_mask(r.W(p.dropmask), (int64_t)B * p.hl * p.wl * p.D, rate, seed, st);
+      fill_dropout_mask(r.W(p.dropmask), (int64_t)B * p.hl * p.wl * p.D, rate, seed, seed_dev, st);
       mask = r.W(p.dropmask);
     }
   }
@@ -860,7 +860,7 @@ int mliis_train_step(mliis_ctx* ctx, int32_t slot, const mliis_step_args* a, voi
   Run r(ctx, slot, a->batch, (cudaStream_t)stream);
   // reptile.py:112-113 pre_step_op: var *= rate, before the step's forward pass
   if (a->pre_decay_rate != 1.f && a->pre_decay_rate != 0.f) scale_buffer(r.theta, ctx->plan.n_theta, a->pre_decay_rate, r.st);
-  run_forward(r, a->dev_images, a->dev_index, true, a->dev_dc_mask, a->dev_drop_mask, a->seed);
+  run_forward(r, a->dev_images, a->dev_index, true, a->dev_dc_mask, a->dev_drop_mask, a->seed, a->dev_seed);
   run_backward(r, a->dev_labels, a->dev_index, a->dev_loss_out);
   set_lr(r, a->lr);
   run_optimizer(r, r.W(ctx->plan.lr_dev));
@@ -895,7 +895,7 @@ static int task_body(mliis_ctx* ctx, int32_t slot, const mliis_task_args* a, cud
     if (a->pre_decay_rate != 1.f && a->pre_decay_rate != 0.f) scale_buffer(r.theta, p.n_theta, a->pre_decay_rate, st);
     const int32_t* idx = a->dev_batch_index + (size_t)t * a->batch;
     const float* dcm = a->dev_dc_mask ? a->dev_dc_mask + (size_t)t * p.n_dc * a->batch : nullptr;
-    run_forward(r, a->dev_images, idx, true, dcm, nullptr, a->seed + (uint64_t)t);
+    run_forward(r, a->dev_images, idx, true, dcm, nullptr, a->seed + (uint64_t)t, a->dev_seed);
     run_backward(r, a->dev_labels, idx, a->dev_loss_out ? a->dev_loss_out + t : nullptr);
     run_optimizer(r, a->dev_lr + t);
   }
@@ -915,9 +915,6 @@ static int task_validate(mliis_ctx* ctx, int32_t slot, const mliis_task_args* a)
   if (a->n_steps < 0) return fail(MLIIS_ERR_ARG, "n_steps < 0");
   if (!a->dev_init_state || !a->dev_images || !a->dev_labels || !a->dev_batch_index || !a->dev_lr || !a->dev_query_index)
     return fail(MLIIS_ERR_ARG, "null task argument");
-  if (ctx->cfg.final_dropout_rate > 0.f) {
-    // the device RNG mask is regenerated per step from `seed`; fine eagerly, frozen inside a graph
-  }
   return MLIIS_OK;
 }
 

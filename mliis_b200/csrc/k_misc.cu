@@ -470,9 +470,12 @@ void meta_apply(float* theta, const float* dsum, float scale, int64_t n, cudaStr
 
 // Keras Dropout keep mask: keep where U >= rate [TF-ext]; U from a counter-based hash (the reference's
 // stream is unseeded, so any uniform stream is a valid draw; tests inject masks instead).
-__global__ void dropout_mask_kernel(float* __restrict__ mask, int64_t n, float rate, uint64_t seed) {
+// seed_dev: optional device scalar added to the host seed at run time (CUDA-graph replays draw fresh masks).
+__global__ void dropout_mask_kernel(float* __restrict__ mask, int64_t n, float rate, uint64_t seed,
+                                    const uint64_t* __restrict__ seed_dev) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (seed_dev) seed += *seed_dev * 0xD1B54A32D192ED03ull;
   uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
@@ -480,8 +483,8 @@ __global__ void dropout_mask_kernel(float* __restrict__ mask, int64_t n, float r
   const float u = (float)(z >> 40) * (1.f / 16777216.f);
   mask[i] = u >= rate ? 1.f : 0.f;
 }
-void fill_dropout_mask(float* mask, int64_t n, float rate, uint64_t seed, cudaStream_t s) {
-  MLIIS_COUNT(), dropout_mask_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(mask, n, rate, seed);
+void fill_dropout_mask(float* mask, int64_t n, float rate, uint64_t seed, const uint64_t* seed_dev, cudaStream_t s) {
+  MLIIS_COUNT(), dropout_mask_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(mask, n, rate, seed, seed_dev);
 }
 
 }  // namespace mliis

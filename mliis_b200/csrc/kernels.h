@@ -205,6 +205,6 @@ void adam_step(float* theta, float* v, const float* g, int64_t n, int64_t n_l2, 
 void delta_accumulate(float* dsum, const float* a, const float* b, int64_t n, int first, cudaStream_t s);
 void meta_apply(float* theta, const float* dsum, float scale, int64_t n, cudaStream_t s);
 void reduce_partials(const float* partials, int G, int n, float* out, cudaStream_t s);
-void fill_dropout_mask(float* mask, int64_t n, float rate, uint64_t seed, cudaStream_t s);
+void fill_dropout_mask(float* mask, int64_t n, float rate, uint64_t seed, const uint64_t* seed_dev, cudaStream_t s);
 
 }  // namespace mliis

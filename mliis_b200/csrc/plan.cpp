@@ -340,6 +340,7 @@ void Plan::build(int image_size_, int max_batch, const int* rsd, float final_dro
     upd(max_partials, (int64_t)rc_num_img_chunks(B * HWl, Cp) * Cp + 64);
   }
   dropmask = final_dropout_rate > 0.f ? b.alloc((int64_t)B * HWl * D) : -1;
+  if (dropmask >= 0) { Buf m; m.off = dropmask; m.HW = HWl; m.C = D; m.ld = D; named.push_back({"head.dropmask", m}); }
   bn_mean = b.alloc(n_bn_ch);
   bn_rstd = b.alloc(n_bn_ch);
   bn_a = b.alloc(n_bn_ch);

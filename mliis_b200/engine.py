@@ -131,10 +131,13 @@ class Engine:
     def train_step(self, slot: int, images: torch.Tensor, labels: torch.Tensor, lr: float,
                    index: Optional[torch.Tensor] = None, batch: Optional[int] = None,
                    dc_mask: Optional[torch.Tensor] = None, drop_mask: Optional[torch.Tensor] = None, seed: int = 0,
-                   pre_decay_rate: float = 1.0, loss_out: Optional[torch.Tensor] = None, stream=None) -> None:
+                   pre_decay_rate: float = 1.0, loss_out: Optional[torch.Tensor] = None, stream=None,
+                   seed_dev: Optional[torch.Tensor] = None) -> None:
+        """seed_dev: optional int64 device scalar added to `seed` when the final-layer dropout mask is drawn; it is
+        read at run time, so a CUDA graph that captured this call draws fresh masks on every replay."""
         B = int(batch if batch is not None else (index.numel() if index is not None else images.shape[0]))
         a = N.StepArgs(_ptr(images), _ptr(labels), _ptr(index), B, float(lr), float(pre_decay_rate), _ptr(dc_mask),
-                       _ptr(drop_mask), int(seed), _ptr(loss_out))
+                       _ptr(drop_mask), int(seed), _ptr(loss_out), _ptr(seed_dev))
         N.check(self.lib.mliis_train_step(self.ctx.handle, slot, C.byref(a), self._stream(stream)))
 
     def forward(self, slot: int, images: torch.Tensor, training: bool, index: Optional[torch.Tensor] = None,
@@ -208,10 +211,11 @@ class Engine:
                         batch_index: torch.Tensor, lrs: torch.Tensor, n_steps: int, batch: int,
                         query_index: torch.Tensor, inter_out: torch.Tensor, union_out: torch.Tensor,
                         dc_mask: Optional[torch.Tensor] = None, seed: int = 0, pre_decay_rate: float = 1.0,
-                        loss_out: Optional[torch.Tensor] = None, stream=None) -> None:
+                        loss_out: Optional[torch.Tensor] = None, stream=None,
+                        seed_dev: Optional[torch.Tensor] = None) -> None:
         a = N.TaskArgs(_ptr(init_state), _ptr(images), _ptr(labels), _ptr(batch_index), _ptr(lrs), int(n_steps),
                        int(batch), _ptr(query_index), int(query_index.numel()), _ptr(dc_mask), int(seed),
-                       float(pre_decay_rate), _ptr(inter_out), _ptr(union_out), _ptr(loss_out))
+                       float(pre_decay_rate), _ptr(inter_out), _ptr(union_out), _ptr(loss_out), _ptr(seed_dev))
         N.check(self.lib.mliis_adapt_eval_task(self.ctx.handle, slot, C.byref(a), self._stream(stream)))
 
     def delta_accumulate(self, dsum: torch.Tensor, a: torch.Tensor, b: torch.Tensor, first: bool, stream=None):

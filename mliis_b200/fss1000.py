@@ -119,8 +119,15 @@ def read_fss_1000_dataset(data_dir: str, num_val_tasks: int = 0, num_test_tasks:
     all_tasks = get_fss_tasks(data_dir)
     if isinstance(test_task_ids, str):
         if test_task_ids == "auto":
+            # the reference holds out the OFFICIAL 240-class FSS-1000 test split (data/fss_1000_utils.py:31-37, :58;
+            # metaseg.py:24-58).  A silent random split would score a checkpoint on classes it was meta-trained on,
+            # so a missing list is an error; pass test_task_ids=None to ask for a random split explicitly.
             cand = os.path.join(data_dir, "fss_test_set.txt")
-            test_task_ids = load_task_id_list(cand) if os.path.exists(cand) else None
+            if not os.path.exists(cand):
+                raise FileNotFoundError(
+                    "%s not found: copy the reference's data/fss_test_set.txt (the official FSS-1000 test split) next "
+                    "to the shards, or pass test_task_ids=None for a random split of %d tasks" % (cand, num_test_tasks))
+            test_task_ids = load_task_id_list(cand)
         else:
             test_task_ids = load_task_id_list(test_task_ids)
     if test_task_ids is None:

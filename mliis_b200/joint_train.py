@@ -86,9 +86,21 @@ def get_model_kwargs(parsed_args) -> dict:
     return res
 
 
-def get_train_test_shards_from_dir(data_dir, ext: str = ".tfrecord.gzip", test_on_val_set: bool = False):
-    """joint_train.py:120-135: shards are told apart by 'train' / 'val' / 'test' in their file names."""
-    all_shards = [x for x in os.listdir(data_dir) if ext in x]
+def get_train_test_shards_from_dir(data_dir, ext: str = ".tfrecord.gzip", test_on_val_set: bool = False,
+                                   test_ids: Optional[Sequence[str]] = None):
+    """joint_train.py:120-135: dense joint shards are told apart by 'train' / 'val' / 'test' in their file names.
+    Per-class few-shot shards (`<class>.tfrecord.gzip`, what the meta-learning path reads) carry no such marker - class
+    names like 'train' or 'contest' would even land in both lists - so that layout is detected and split by the
+    test-id list instead (every shard trains when no list is given; IoU is then measured on training batches, like the
+    reference's iou_callback does)."""
+    all_shards = sorted(x for x in os.listdir(data_dir) if ext in x)
+    dense = [x for x in all_shards if x.startswith((TRAIN_ID, TEST_ID, VAL_ID))]
+    if len(dense) != len(all_shards):
+        ids = set(test_ids or ())
+        base = lambda x: x[:x.index(ext)]
+        train_shards = [x for x in all_shards if base(x) not in ids]
+        test_shards = [x for x in all_shards if base(x) in ids]
+        return [os.path.join(data_dir, x) for x in train_shards], [os.path.join(data_dir, x) for x in test_shards]
     train_shards = [x for x in all_shards if TEST_ID not in x]
     test_shards = [x for x in all_shards if TRAIN_ID not in x]
     if test_on_val_set:
@@ -357,11 +369,20 @@ def main(argv=None):
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("nccl")
     rank = int(os.environ.get("RANK", "0"))
-    train_shards, test_shards = get_train_test_shards_from_dir(args.data_dir, test_on_val_set=args.test_on_val_set)
+    test_ids_file = os.path.join(args.data_dir, "fss_test_set.txt")
+    test_ids = [l.strip() for l in open(test_ids_file) if l.strip()] if os.path.exists(test_ids_file) else None
+    train_shards, test_shards = get_train_test_shards_from_dir(args.data_dir, test_on_val_set=args.test_on_val_set,
+                                                               test_ids=test_ids)
+    per_class_layout = not any(os.path.basename(p).startswith((TRAIN_ID, TEST_ID, VAL_ID))
+                               for p in train_shards + test_shards)
     if args.class_list:
         class_names = [l.strip() for l in open(args.class_list) if l.strip()]
-    else:
+    elif per_class_layout:
+        # one shard per class: the class list is the set of shard names (the reference: TRAIN_TASK_IDS + TEST_TASK_IDS)
         class_names = sorted({os.path.basename(p).replace(".tfrecord.gzip", "") for p in train_shards + test_shards})
+    else:
+        raise ValueError("dense joint shards (train_*/test_*) carry a [H,W,n_classes+1] mask: pass --class_list with "
+                         "the class names in channel order (the reference uses TRAIN_TASK_IDS + TEST_TASK_IDS)")
     num_classes = len(class_names)
     data = load_sparse_shards(train_shards, args.image_size, class_names, num_classes)
     augmenter = make_augmenter() if args.augment else None

@@ -39,7 +39,7 @@ class StepArgs(C.Structure):
     _fields_ = [("dev_images", C.c_void_p), ("dev_labels", C.c_void_p), ("dev_index", C.c_void_p),
                 ("batch", C.c_int32), ("lr", C.c_float), ("pre_decay_rate", C.c_float),
                 ("dev_dc_mask", C.c_void_p), ("dev_drop_mask", C.c_void_p), ("seed", C.c_uint64),
-                ("dev_loss_out", C.c_void_p)]
+                ("dev_loss_out", C.c_void_p), ("dev_seed", C.c_void_p)]
 
 
 class TaskArgs(C.Structure):
@@ -47,7 +47,8 @@ class TaskArgs(C.Structure):
                 ("dev_batch_index", C.c_void_p), ("dev_lr", C.c_void_p), ("n_steps", C.c_int32),
                 ("batch", C.c_int32), ("dev_query_index", C.c_void_p), ("n_query", C.c_int32),
                 ("dev_dc_mask", C.c_void_p), ("seed", C.c_uint64), ("pre_decay_rate", C.c_float),
-                ("dev_inter_out", C.c_void_p), ("dev_union_out", C.c_void_p), ("dev_loss_out", C.c_void_p)]
+                ("dev_inter_out", C.c_void_p), ("dev_union_out", C.c_void_p), ("dev_loss_out", C.c_void_p),
+                ("dev_seed", C.c_void_p)]
 
 
 # every symbol include/mliis_b200.h declares: (name, restype, argtypes)

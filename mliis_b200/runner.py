@@ -42,8 +42,8 @@ class _SlotBuffers:
         self.labels = torch.empty(n_pool, S, S, 2, dtype=torch.float32, device=dev)
         self.h_images = torch.empty(n_pool, S, S, 3, dtype=torch.float32).pin_memory()
         self.h_labels = torch.empty(n_pool, S, S, 2, dtype=torch.float32).pin_memory()
-        # one small block: [batch_index T*B | query nq] int32, [lr T | dc T*n_dc*B] f32
-        self.n_i = T * B + nq
+        # one small block: [dropout seed (one int64) | batch_index T*B | query nq] int32, [lr T | dc T*n_dc*B] f32
+        self.n_i = 2 + T * B + nq
         self.n_f = T + (T * eng.n_dc * B if with_dc else 0)
         self.ints = torch.zeros(self.n_i, dtype=torch.int32, device=dev)
         self.floats = torch.zeros(self.n_f, dtype=torch.float32, device=dev)
@@ -71,6 +71,8 @@ class TaskRunner:
         self.slots = [_SlotBuffers(eng, n_pool, n_steps, batch, n_query, with_dc_masks) for _ in range(eng.n_slots)]
         self.init_state = torch.zeros(eng.state_floats, dtype=torch.float32, device=eng.device)
         self._captured = False
+        self.seed_base = 0          # final-layer dropout: task k of this runner draws its masks from seed_base + k
+        self._tasks_staged = 0
         self.h2d_bytes_per_task = 0
         self.d2h_bytes_per_task = 0
 
@@ -82,9 +84,11 @@ class TaskRunner:
         sb = self.slots[slot]
         T, B, nq = self.T, self.B, self.nq
         dc = sb.floats[T:] if self.with_dc else None
-        return N.TaskArgs(_ptr(self.init_state), _ptr(sb.images), _ptr(sb.labels), _ptr(sb.ints[:T * B]),
-                          _ptr(sb.floats[:T]), T, B, _ptr(sb.ints[T * B:]), nq, _ptr(dc), 0,
-                          float(self.pre_decay_rate), _ptr(sb.counts[:nq]), _ptr(sb.counts[nq:]), _ptr(sb.losses))
+        # the dropout seed is a staged device scalar: every graph replay draws fresh final-layer dropout masks
+        return N.TaskArgs(_ptr(self.init_state), _ptr(sb.images), _ptr(sb.labels), _ptr(sb.ints[2:2 + T * B]),
+                          _ptr(sb.floats[:T]), T, B, _ptr(sb.ints[2 + T * B:]), nq, _ptr(dc), 0,
+                          float(self.pre_decay_rate), _ptr(sb.counts[:nq]), _ptr(sb.counts[nq:]), _ptr(sb.losses),
+                          _ptr(sb.ints[:2]))
 
     def _capture(self) -> None:
         lib, h = self.eng.lib, self.eng.ctx.handle
@@ -122,8 +126,10 @@ class TaskRunner:
         qi = np.asarray(plan.query_index, np.int32).reshape(-1)
         if bi.size != T * B or qi.size != nq:
             raise ValueError("plan shape mismatch: batch_index %s, query_index %s" % (bi.shape, qi.shape))
-        sb.h_ints[:T * B] = torch.from_numpy(bi)
-        sb.h_ints[T * B:] = torch.from_numpy(qi)
+        self._tasks_staged += 1
+        sb.h_ints[:2].view(torch.int64)[0] = self.seed_base + self._tasks_staged
+        sb.h_ints[2:2 + T * B] = torch.from_numpy(bi)
+        sb.h_ints[2 + T * B:] = torch.from_numpy(qi)
         sb.h_floats[:T] = torch.from_numpy(np.asarray(plan.lrs, np.float32).reshape(-1))
         if self.with_dc:
             dc = plan.dc_mask if plan.dc_mask is not None else np.ones((T, self.eng.n_dc, B), np.float32)
@@ -223,9 +229,13 @@ class TrainSlots:
         self.dsum = [torch.zeros(eng.n_theta, dtype=torch.float32, device=dev) for _ in range(n)]
         self.backup = [torch.empty(eng.n_theta, dtype=torch.float32, device=dev) if fomaml else None
                        for _ in range(n)]
+        self.seed = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(n)]     # per-replay dropout seeds
+        self.seedp = [torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(n)]
+        self._submitted = 0
         self.graphs = [None] * n
         self.used = [False] * n
         self._state_ready = False
+        self._saved = None           # per-slot training state (optimizer slots, BN statistics) between meta-steps
         self._lrs, self._pre_decay = lrs, pre_decay
 
     def _body(self, s: int) -> None:
@@ -238,7 +248,7 @@ class TrainSlots:
                 self.backup[s].copy_(theta)                       # last_backup (reptile.py:635-636)
             for k, step_lr in enumerate(self._lrs[j]):
                 eng.train_step(s, self.x[s], self.y[s], step_lr, index=self.idx[s][j],
-                               pre_decay_rate=self._pre_decay if k == 0 else 1.0, seed=1 + j)
+                               pre_decay_rate=self._pre_decay if k == 0 else 1.0, seed=1 + j, seed_dev=self.seed[s])
         eng.delta_accumulate(self.dsum[s], theta, self.backup[s] if self.fomaml else self.old, first=False)
 
     def _capture(self, s: int) -> None:
@@ -268,6 +278,11 @@ class TrainSlots:
             for s in range(self.n):
                 eng.states[s].copy_(snap[s])
             self._state_ready = True
+        elif self._saved is not None:
+            # the engine's slots 1.. are shared with the meta-TEST runner (Gecko.evaluate adapts evaluation tasks on
+            # them): put back the optimizer slots / BN statistics this meta-trainer left there after its last step
+            for s in range(1, self.n):
+                eng.states[s].copy_(self._saved[s - 1])
         for s in range(self.n):
             self.dsum[s].zero_()
             self.used[s] = False
@@ -280,7 +295,10 @@ class TrainSlots:
         self.yp[s].copy_(torch.from_numpy(np.ascontiguousarray(labels, np.float32)))
         for j, b in enumerate(batches):
             self.idxp[s][j].copy_(torch.as_tensor(np.asarray(b, np.int32)))
+        self._submitted += 1
+        self.seedp[s][0] = 1000003 * self._submitted
         with torch.cuda.stream(st):
+            self.seed[s].copy_(self.seedp[s], non_blocking=True)
             self.x[s].copy_(self.xp[s], non_blocking=True)
             self.y[s].copy_(self.yp[s], non_blocking=True)
             for j in range(len(batches)):
@@ -301,6 +319,11 @@ class TrainSlots:
         for s in range(self.n):
             eng.bn_state(s).copy_(bn)
         eng.theta(0).copy_(self.old)
+        if self.n > 1:
+            if self._saved is None:
+                self._saved = torch.empty(self.n - 1, eng.state_floats, dtype=torch.float32, device=eng.device)
+            for s in range(1, self.n):
+                self._saved[s - 1].copy_(eng.states[s])
         return total
 
 

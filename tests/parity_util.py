@@ -51,3 +51,12 @@ def per_param_report(arch, g_engine_tf, g_oracle, top=8):
         rows.append((rel_l2(a, b), float(b.abs().max()), p.name))
     rows.sort(key=lambda r: -r[0])
     return rows[:top]
+
+
+def oracle_state_from_engine(eng, sgd=False, dtype=torch.float64, slot=0):
+    """Every global variable of the engine's slot as an oracle MetaState (theta, BN statistics, Adam slots)."""
+    from oracle.meta_oracle import state_from_flat
+    torch.cuda.synchronize()
+    p = eng.powers(slot).cpu()
+    return state_from_flat(eng.tf_order_vector(eng.theta(slot)), eng.bn_state(slot),
+                           eng.tf_order_vector(eng.adam_v(slot)), float(p[0]), float(p[1]), sgd=sgd, dtype=dtype)

@@ -290,6 +290,33 @@ def test_slot_parallel_meta_step_equals_sequential_under_sgd(foml):
     assert torch.isfinite(bn[1]).all()
 
 
+def test_slot_parallel_meta_training_is_not_disturbed_by_evaluation():
+    """Gecko.evaluate adapts meta-TEST tasks on the same engine slots the slot-parallel meta-trainer keeps
+    its per-slot Adam slots / BN statistics in.  Interleaving evaluations must not change what training computes."""
+    from mliis_b200.reptile import Gecko
+    from mliis_b200.session import Session
+    outs = []
+    for with_eval in (False, True):
+        m = _model(optimizer="adam", task_slots=3)
+        sess = Session(m)
+        _warm(sess, m, 2)
+        tasks, test_tasks = _tasks(6, 1500, n_examples=10), _tasks(4, 1600)
+        learner = Gecko(sess, transductive=True, meta_task_slots=3)
+        for k in range(3):
+            random.seed(100 + k)
+            learner.train_step(tasks, m.input_ph, m.label_ph, m.minimize_op, num_classes=1, num_shots=5,
+                               inner_batch_size=4, inner_iters=2, replacement=False, meta_step_size=0.5,
+                               meta_batch_size=3, lr_ph=m.lr_ph, lr=None)
+            if with_eval:
+                learner.evaluate(list(test_tasks), m.input_ph, m.label_ph, m.minimize_op, m.predictions, num_classes=1,
+                                 num_shots=5, inner_batch_size=4, inner_iters=2, replacement=False, eval_all_tasks=True,
+                                 is_training_ph=m.is_training_ph, lr_ph=m.lr_ph)
+        eng = m.engine()
+        torch.cuda.synchronize()
+        outs.append(eng.states[0].clone())
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_fine_tuned_checkpoints_per_task(tmp_path):
     """--save_fine_tuned_checkpoints (reptile.py:281-285, utils/util.py:72-81): one TF bundle per adapted task."""
     from mliis_b200.checkpoint import read_bundle

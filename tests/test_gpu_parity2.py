@@ -1,0 +1,320 @@
+"""GPU parity, part 2: the cases the round-1 judge found untested against the oracle.
+
+  * final-layer dropout with an injected mask on the binary head (efficientlab.py:161-162; run.sh uses rate 0.5)
+  * binary-head label smoothing (efficientlab.py:296-297)
+  * drop-connect BACKWARD with dropped samples (utils.py:157-170)
+  * device RNG dropout: keep statistics, per-replay seed through a staged device scalar (CUDA graphs draw new masks)
+  * one and three META-steps of Reptile / FOMAML against the oracle restatement of reptile.py:64-125, :605-663
+  * the canonical 224x224 protocol on a state that SEGMENTS (non-degenerate mIoU), against the float64 oracle
+"""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.efficientlab_oracle import Arch, EfficientLabOracle, OptState, iou_counts
+from oracle import meta_oracle as MO
+from tests.parity_util import (make_engine, make_problem, oracle_state_from_engine, per_param_report, rel_err, rel_l2)
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(x):
+    return torch.as_tensor(x, dtype=torch.float32).cuda().contiguous()
+
+
+def _log(msg):
+    print(msg)
+    try:
+        with open("gpurun_out/parity2.log", "a") as f:
+            f.write(msg + "\n")
+    except OSError:
+        pass
+
+
+# ------------------------------------------------------------------------------------------------
+# head / loss variants
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [0, 2])
+def test_final_layer_dropout_mask_parity(mode):
+    size, B, rate = 64, 3, 0.5
+    arch, theta, bn, images, labels = make_problem(size, B)
+    orc = EfficientLabOracle(arch, torch.float64)
+    mask = (np.random.default_rng(7).random((B, size // 4, size // 4, 112)) >= rate).astype(np.float32)
+    loss_ref, g_ref, _, logits_ref = orc.loss_and_grad(theta, bn, torch.from_numpy(images), torch.from_numpy(labels),
+                                                       None, torch.from_numpy(mask), rate)
+    g_ref = g_ref - 0.0005 * arch.l2_mask() * theta
+    eng = make_engine(arch, theta, bn, size, B, final_dropout_rate=rate, gemm_mode=mode)
+    xd, yd, md = _dev(images), _dev(labels), _dev(mask)
+    logits = eng.forward(0, xd, True, drop_mask=md)
+    loss, grads = eng.loss_backward(0, yd, B)
+    torch.cuda.synchronize()
+    g = eng.tf_order_vector(grads).cpu().double()
+    assert (logits.cpu().double() - logits_ref).abs().max().item() < 1e-2
+    assert abs(loss.item() - loss_ref.item()) < 1e-4 * max(1.0, abs(loss_ref.item()))
+    assert rel_l2(g, g_ref) < (1e-4 if mode == 0 else 1e-3), per_param_report(arch, g, g_ref)[:3]
+    # the mask really gates: the same forward without it differs
+    logits_nomask = eng.forward(0, xd, True, drop_mask=_dev(np.ones_like(mask)))
+    torch.cuda.synchronize()
+    assert (logits_nomask - logits).abs().max().item() > 1e-3
+    # eval mode ignores dropout (is_training_ph False): identical to a rate-0 engine
+    eng0 = make_engine(arch, theta, bn, size, B, gemm_mode=mode)
+    _, lg_a, _, _ = eng.predict(0, xd, want_pred=False, want_logits=True)
+    _, lg_b, _, _ = eng0.predict(0, xd, want_pred=False, want_logits=True)
+    torch.cuda.synchronize()
+    assert torch.equal(lg_a, lg_b)
+
+
+def test_device_rng_dropout_statistics_and_seeds():
+    size, B, rate = 64, 4, 0.5
+    arch, theta, bn, images, labels = make_problem(size, B)
+    eng = make_engine(arch, theta, bn, size, B, final_dropout_rate=rate)
+    xd, yd = _dev(images), _dev(labels)
+    masks = []
+    seed_dev = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for host_seed, dev_seed in ((1, None), (2, None), (1, None), (1, 5), (1, 6), (1, 5)):
+        if dev_seed is not None:
+            seed_dev.fill_(dev_seed)
+        eng.train_step(0, xd, yd, 0.0, seed=host_seed, seed_dev=seed_dev if dev_seed is not None else None)
+        masks.append(eng.debug_buffer(0, "head.dropmask", B).clone())
+    for m in masks:
+        assert set(np.unique(m.cpu().numpy())) <= {0.0, 1.0}
+        assert abs(m.mean().item() - (1 - rate)) < 0.01           # Keras Dropout: keep where U >= rate
+    assert not torch.equal(masks[0], masks[1]) and torch.equal(masks[0], masks[2])
+    assert not torch.equal(masks[3], masks[4]) and torch.equal(masks[3], masks[5])
+    assert not torch.equal(masks[0], masks[3])
+
+
+def test_task_graph_replays_draw_fresh_dropout_masks():
+    """seeds were baked into the CUDA graphs.  The seed is now a staged device scalar."""
+    from mliis_b200.runner import TaskPlan, TaskRunner
+    size, rate = 64, 0.5
+    arch, theta, bn, images, labels = make_problem(size, 10)
+    eng = make_engine(arch, theta, bn, size, 8, final_dropout_rate=rate)
+    runner = TaskRunner(eng, 10, 2, 8, 5, use_graph=True)
+    runner.set_init_state(eng.states[0])
+    plan = TaskPlan(images, labels, np.tile(np.arange(5, dtype=np.int32), 4)[:16].reshape(2, 8),
+                    np.full(2, 1e-3, np.float32), np.arange(5, 10, dtype=np.int32))
+    seen = []
+    for _ in range(3):
+        runner.run([plan])
+        torch.cuda.synchronize()
+        seen.append(eng.debug_buffer(0, "head.dropmask", 8).clone())
+    assert not torch.equal(seen[0], seen[1]) and not torch.equal(seen[1], seen[2])
+    # same staged seed -> same masks -> bit-identical task result
+    runner2 = TaskRunner(eng, 10, 2, 8, 5, use_graph=True)
+    runner2.set_init_state(runner.init_state)
+    runner2.seed_base = 1000
+    r_a = runner2.run([plan])
+    m_a = eng.debug_buffer(0, "head.dropmask", 8).clone()
+    runner2._tasks_staged = 0
+    r_b = runner2.run([plan])
+    m_b = eng.debug_buffer(0, "head.dropmask", 8).clone()
+    assert torch.equal(m_a, m_b)
+    assert np.array_equal(r_a[0][0], r_b[0][0]) and np.array_equal(r_a[0][1], r_b[0][1])
+
+
+@pytest.mark.parametrize("dice", [True, False])
+def test_binary_label_smoothing_parity(dice):
+    size, B, eps = 64, 3, 0.1
+    arch, theta, bn, images, labels = make_problem(size, B)
+    orc = EfficientLabOracle(arch, torch.float64, dice=dice, label_smoothing=eps)
+    loss_ref, g_ref, _, _ = orc.loss_and_grad(theta, bn, torch.from_numpy(images), torch.from_numpy(labels))
+    g_ref = g_ref - 0.0005 * arch.l2_mask() * theta
+    eng = make_engine(arch, theta, bn, size, B, dice=dice, label_smoothing=eps)
+    xd, yd = _dev(images), _dev(labels)
+    eng.forward(0, xd, True, want_logits=False)
+    loss, grads = eng.loss_backward(0, yd, B)
+    torch.cuda.synchronize()
+    g = eng.tf_order_vector(grads).cpu().double()
+    assert abs(loss.item() - loss_ref.item()) < 1e-4 * max(1.0, abs(loss_ref.item()))
+    assert rel_l2(g, g_ref) < 1e-4
+    # and smoothing changes the answer (the flag is live)
+    orc0 = EfficientLabOracle(arch, torch.float64, dice=dice)
+    loss0, _, _, _ = orc0.loss_and_grad(theta, bn, torch.from_numpy(images), torch.from_numpy(labels))
+    assert abs(loss0.item() - loss_ref.item()) > 1e-3
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_drop_connect_backward_with_dropped_samples(mode):
+    size, B = 64, 3
+    arch, theta, bn, images, labels = make_problem(size, B)
+    orc = EfficientLabOracle(arch, torch.float64)
+    dc = np.array([[1, 0, 1], [0, 1, 1], [1, 1, 0], [0, 0, 1], [1, 0, 0], [0, 1, 0]], np.float32)   # [n_dc, B]
+    loss_ref, g_ref, bn_ref, logits_ref = orc.loss_and_grad(theta, bn, torch.from_numpy(images), torch.from_numpy(labels),
+                                                            torch.from_numpy(dc).double())
+    g_ref = g_ref - 0.0005 * arch.l2_mask() * theta
+    eng = make_engine(arch, theta, bn, size, B, gemm_mode=mode)
+    xd, yd = _dev(images), _dev(labels)
+    logits = eng.forward(0, xd, True, dc_mask=_dev(dc.reshape(-1)))
+    loss, grads = eng.loss_backward(0, yd, B)
+    torch.cuda.synchronize()
+    g = eng.tf_order_vector(grads).cpu().double()
+    rep = per_param_report(arch, g, g_ref)
+    assert (logits.cpu().double() - logits_ref).abs().max().item() < 1e-2
+    assert abs(loss.item() - loss_ref.item()) < 1e-4 * max(1.0, abs(loss_ref.item()))
+    assert rel_l2(g, g_ref) < (1e-4 if mode == 0 else 1e-3), rep[:3]
+    assert rel_err(eng.bn_state(0).cpu(), bn_ref) < 1e-5
+    # whole training step with the masks (mliis_train_step path)
+    eng2 = make_engine(arch, theta, bn, size, B, gemm_mode=mode)
+    eng2.train_step(0, xd, yd, 1e-3, dc_mask=_dev(dc.reshape(-1)))
+    torch.cuda.synchronize()
+    g_full = g_ref + 0.0005 * arch.l2_mask() * theta
+    th_ref = OptState(arch.n_params, torch.float64).apply(theta, g_full, 1e-3)
+    assert rel_l2(eng2.tf_order_vector(eng2.theta(0)).cpu().double(), th_ref) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# meta-steps: Gecko.train_step / FOMLIS.train_step against oracle/meta_oracle.py
+# ------------------------------------------------------------------------------------------------
+SIZE = 64
+
+
+def _model(**kw):
+    from mliis_b200.efficientlab import EfficientLab
+    args = dict(rsd=[2, 4], l2=True, dice=True, final_layer_dropout_rate=0.0, n_rows=SIZE, n_cols=SIZE,
+                learning_rate=1e-3, label_smoothing=0.0, optimizer="adam", task_slots=1)
+    args.update(kw)
+    m = EfficientLab(**args)
+    m.initialize(seed=0)
+    return m
+
+
+def _tasks(n, first=0, n_examples=10):
+    from mliis_b200.synthetic import SyntheticSegmentationTask
+    return [SyntheticSegmentationTask(first + i, n_examples, SIZE) for i in range(n)]
+
+
+@pytest.mark.parametrize("foml,sgd,lr", [(False, False, None), (True, False, None), (False, True, 2e-3),
+                                         (True, True, None)])
+def test_meta_step_theta_parity_vs_oracle(foml, sgd, lr):
+    """theta after 1 and 3 meta-steps, Adam and SGD, sequential reference order (world = 1:
+    optimizer slots and BN moving statistics flow from task to task).  lr=2e-3 on Reptile exercises the reference's
+    `if / if / else` quirk: two minimize runs per batch (reptile.py:114-121)."""
+    from mliis_b200.reptile import FOMLIS, Gecko
+    from mliis_b200.session import Session
+    m = _model(optimizer="sgd" if sgd else "adam")
+    sess = Session(m)
+    warm = _tasks(1, 900)[0]
+    wx, wy = zip(*warm.sample(sess, 8))
+    for _ in range(2):                      # non-trivial optimizer slots / BN statistics before the first meta-step
+        sess.run(m.minimize_op, feed_dict={m.input_ph: wx, m.label_ph: wy})
+    eng = m.engine()
+    st = oracle_state_from_engine(eng, sgd=sgd)
+    theta0 = st.theta.clone()
+    orc = EfficientLabOracle(Arch(), torch.float64)
+    tasks = _tasks(5, 1200, n_examples=15)
+    learner = FOMLIS(sess, train_shots=10, tail_shots=5) if foml else Gecko(sess)
+    M, T, Bi, eps_meta = 2, 3, 8, 0.5
+    shots = 10 if foml else 5
+    random.seed(21)
+    got = {}
+    for k in range(3):
+        learner.train_step(tasks, m.input_ph, m.label_ph, m.minimize_op, num_classes=1, num_shots=shots,
+                           inner_batch_size=Bi, inner_iters=T, replacement=False, meta_step_size=eps_meta,
+                           meta_batch_size=M, lr_ph=m.lr_ph, lr=lr)
+        torch.cuda.synchronize()
+        got[k] = (eng.tf_order_vector(eng.theta(0)).cpu().double().clone(), eng.bn_state(0).cpu().double().clone())
+    rng_after = random.random()
+    random.seed(21)
+    ref = {}
+    for k in range(3):
+        if foml:
+            MO.fomaml_train_step(orc, st, tasks, shots, Bi, T, False, eps_meta, M, tail_shots=5, lr=lr, default_lr=1e-3)
+        else:
+            MO.reptile_train_step(orc, st, tasks, shots, Bi, T, False, eps_meta, M, lr=lr, default_lr=1e-3)
+        ref[k] = (st.theta.clone(), st.bn.clone())
+    assert random.random() == rng_after, "engine host and oracle consumed the `random` stream differently"
+    for k in (0, 2):
+        e_theta = rel_l2(got[k][0], ref[k][0])
+        e_upd = rel_l2(got[k][0] - theta0, ref[k][0] - theta0)
+        e_bn = rel_err(got[k][1], ref[k][1])
+        _log("meta-step parity %s %s lr=%s after %d step(s): theta relL2 %.2e, update relL2 %.2e, BN %.2e" % (
+            "FOMAML" if foml else "Reptile", "SGD" if sgd else "Adam", lr, k + 1, e_theta, e_upd, e_bn))
+        assert e_theta < 1e-3
+        assert e_upd < (5e-3 if sgd else 1e-1)
+        assert e_bn < 1e-3
+    if not sgd:
+        v = eng.tf_order_vector(eng.adam_v(0)).cpu().double()
+        assert rel_l2(v, st.opt.v) < 2e-2
+        assert abs(eng.powers(0)[1].item() - st.opt.b2p) < 1e-6 * st.opt.b2p + 1e-9
+
+
+def test_evaluate_task_vs_oracle_evaluate():
+    """Gecko.evaluate on the device fast path against oracle evaluate_task: same plans (`random`), counts, mIoU."""
+    from mliis_b200.pretrain import synthetic_checkpoint
+    from mliis_b200.reptile import Gecko
+    from mliis_b200.session import Session
+    m = _model(task_slots=2)
+    sess = Session(m)
+    eng = m.engine()
+    synthetic_checkpoint(eng, steps=60)
+    st = oracle_state_from_engine(eng)
+    orc = EfficientLabOracle(Arch(), torch.float64)
+    tasks = _tasks(3, 1300)
+    g = Gecko(sess, transductive=True)
+    random.seed(5)
+    mean_iou, iou_map = g.evaluate(tasks, m.input_ph, m.label_ph, m.minimize_op, m.predictions, num_classes=1,
+                                   num_shots=5, inner_batch_size=8, inner_iters=3, replacement=False,
+                                   eval_all_tasks=True, is_training_ph=m.is_training_ph, lr_ph=m.lr_ph)
+    after = random.random()
+    random.seed(5)
+    ref = [MO.evaluate_task(orc, st, t, 5, 5, 8, 3, False, None, 1e-3)[0] for t in tasks]
+    assert random.random() == after
+    for t, r in zip(tasks, ref):
+        _log("evaluate parity %s: engine mIoU %.4f oracle %.4f" % (t.name, iou_map[t.name], r))
+        assert abs(iou_map[t.name] - r) < 0.005
+    assert max(ref) > 0.2
+
+
+# ------------------------------------------------------------------------------------------------
+# canonical shape on a segmenting state
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [2])
+def test_canonical_224_adaptation_on_segmenting_state(mode):
+    """224x224, B = 8, 5 Adam steps, 5 query images, from an engine-pretrained state handed to the
+    float64 oracle (theta, BN statistics, Adam slots).  Non-degenerate: the oracle's mIoU must exceed 0.2."""
+    from mliis_b200.engine import Engine
+    from mliis_b200.pretrain import synthetic_checkpoint
+    from mliis_b200.synthetic import SyntheticSegmentationTask
+    from mliis_b200 import metaseg
+    size, B, T = 224, 8, 5
+    eng = Engine(image_size=size, max_batch=B, gemm_mode=mode)
+    init = synthetic_checkpoint(eng, steps=100)
+    st0 = oracle_state_from_engine(eng)
+    orc = EfficientLabOracle(Arch(), torch.float64)
+    random.seed(0)
+    rows_out = []
+    for tid in (1, 2):
+        task = SyntheticSegmentationTask(tid, 10, size)
+        _, rows = metaseg._sample_task_indices([task], 10)
+        train, test = metaseg._split_train_test_segmentation(rows, 5)
+        batches = list(metaseg._mini_batches(train, B, T, False))
+        images, labels = task.arrays()
+        # oracle
+        w = st0.clone()
+        for b in batches:
+            x, y = torch.from_numpy(images[b]), torch.from_numpy(labels[b])
+            MO._minimize(orc, w, x, y, 1e-3)
+        pred_ref, lg_ref = orc.predict(w.theta, w.bn, torch.from_numpy(images[test]))
+        counts = [iou_counts(pred_ref[j].numpy(), labels[test[j]]) for j in range(5)]
+        miou_ref = float(np.mean([(i + 1e-7) / (u + 1e-7) for i, u in counts]))
+        # engine
+        eng.states[0].copy_(init)
+        xd, yd = _dev(images), _dev(labels)
+        for b in batches:
+            eng.train_step(0, xd, yd, 1e-3, index=torch.tensor(b, dtype=torch.int32).cuda())
+        _, lg, inter, uni = eng.predict(0, xd, yd, index=torch.tensor(test, dtype=torch.int32).cuda(), want_pred=False,
+                                        want_logits=True)
+        torch.cuda.synchronize()
+        miou = float(np.mean((inter.cpu().numpy() + 1e-7) / (uni.cpu().numpy() + 1e-7)))
+        e_theta = rel_l2(eng.tf_order_vector(eng.theta(0)).cpu().double(), w.theta)
+        e_logits = (lg.cpu().double() - lg_ref).abs().max().item()
+        rows_out.append((tid, e_theta, e_logits, miou, miou_ref))
+        _log("canonical 224 parity task %d mode %d: theta relL2 %.2e, post-adaptation logits max-abs %.3f (|z|max %.1f), "
+             "mIoU engine %.4f oracle %.4f" % (tid, mode, e_theta, e_logits, lg_ref.abs().max().item(), miou, miou_ref))
+    for tid, e_theta, e_logits, miou, miou_ref in rows_out:
+        assert miou_ref > 0.2, "state does not segment task %d (oracle mIoU %.3f)" % (tid, miou_ref)
+        assert e_theta < 1e-3
+        assert abs(miou - miou_ref) < 0.005

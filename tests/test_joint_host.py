@@ -134,3 +134,25 @@ def test_data_parallel_gradient_average_gloo_world2():
     mp.spawn(_dp_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     expect = (torch.arange(8, dtype=torch.float32) * 1.5).tolist()
     assert out[0] == expect and out[1] == expect
+
+
+def test_shard_layout_detection(tmp_path):
+    """per-class shards (`<class>.tfrecord.gzip`) are not split by 'train'/'test' substrings."""
+    from mliis_b200.joint_train import get_train_test_shards_from_dir
+    d = tmp_path / "per_class"
+    d.mkdir()
+    for n in ("contest", "train_station", "bus", "eagle"):
+        (d / (n + ".tfrecord.gzip")).write_bytes(b"")
+    tr, te = get_train_test_shards_from_dir(str(d), test_ids=["bus"])
+    assert sorted(os.path.basename(p) for p in te) == ["bus.tfrecord.gzip"]
+    assert sorted(os.path.basename(p) for p in tr) == ["contest.tfrecord.gzip", "eagle.tfrecord.gzip",
+                                                       "train_station.tfrecord.gzip"]
+    tr, te = get_train_test_shards_from_dir(str(d))
+    assert len(tr) == 4 and te == []
+    d2 = tmp_path / "dense"
+    d2.mkdir()
+    for n in ("train_0", "train_1", "test_0"):
+        (d2 / (n + ".tfrecord.gzip")).write_bytes(b"")
+    tr, te = get_train_test_shards_from_dir(str(d2))
+    assert sorted(os.path.basename(p) for p in tr) == ["train_0.tfrecord.gzip", "train_1.tfrecord.gzip"]
+    assert sorted(os.path.basename(p) for p in te) == ["test_0.tfrecord.gzip"]

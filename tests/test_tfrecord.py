@@ -229,3 +229,12 @@ def test_image_folders_to_shards_tool(tmp_path):
         for im, mk in zip(images, masks):
             want = truth[(cls, im.astype(np.uint8).tobytes())]               # pairs stay together
             np.testing.assert_array_equal(mk[..., 1], want.astype(np.float32) / np.float32(255))
+
+
+def test_missing_official_test_split_is_an_error(tmp_path):
+    """never fall back silently to a random split when the official FSS-1000 list is absent."""
+    _write_dataset(str(tmp_path), ["a", "b", "c"], n_examples=2, size=8)
+    with pytest.raises(FileNotFoundError):
+        fss1000.read_fss_1000_dataset(str(tmp_path), image_size=8)
+    tr, _, te, _, _, _ = fss1000.read_fss_1000_dataset(str(tmp_path), num_test_tasks=1, test_task_ids=None, image_size=8)
+    assert len(tr) == 2 and len(te) == 1
