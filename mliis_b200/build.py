@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmliis_b200.so")
 HEADER = os.path.join(HERE, "..", "include", "mliis_b200.h")
-SOURCES = ["engine.cu", "k_rowchan.cu", "k_conv.cu", "k_gemm.cu", "k_misc.cu", "k_mc.cu", "k_tc.cu", "plan.cpp"]
+SOURCES = ["engine.cu", "k_rowchan.cu", "k_conv.cu", "k_gemm.cu", "k_misc.cu", "k_mc.cu", "k_tc.cu", "k_pool.cu", "plan.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "static"]
 

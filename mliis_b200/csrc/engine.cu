@@ -63,6 +63,7 @@ struct Slot {
   const float* fwd_drop_mask = nullptr;
   const int32_t* class_ids = nullptr;   // multi-class mode: per-example foreground class (mliis_set_class_ids)
   bool grads_zeroed = false;
+  bool folded[4] = {false, false, false, false};   // per RSD module: forward folded the pooled branch (k_pool.cu)
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
   unsigned long long graph_launches = 0;   // kernels inside the captured task graph
@@ -201,18 +202,33 @@ struct Dense {
   bool tc() const { return r.c->cfg.gemm_mode != MLIIS_GEMM_FP32; }
   int split() const { return (r.c->cfg.gemm_mode == MLIIS_GEMM_TF32 && decoder) ? 1 : 3; }
   // operand prepared by tc_prep_all at the start of the step (nullptr for a weight outside the plan's job table)
-  float* prepared(const float* w_hwio, int dgrad) const {
+  float* prepared(const float* w_hwio, int dgrad, int Cin) const {
     if (!r.c->d_prep_jobs) return nullptr;
     const int64_t off = w_hwio - r.theta;
     for (const Plan::PrepJob& j : r.p.prep_jobs)
-      if (j.w_off == off && j.dgrad == dgrad) return r.W(r.p.wcache + j.dst);
+      if (j.w_off == off && j.dgrad == dgrad && j.Ci == Cin) return r.W(r.p.wcache + j.dst);
     return nullptr;
   }
-  float* operand(const float* w_hwio, int taps, int Cin, int Cout, int dgrad) const {
-    if (float* wt = prepared(w_hwio, dgrad)) return wt;
+  // Cs: input channels per tap of the stored kernel when the operand only uses its first Cin (0 = Cin)
+  float* operand(const float* w_hwio, int taps, int Cin, int Cout, int dgrad, int Cs = 0) const {
+    if (float* wt = prepared(w_hwio, dgrad, Cin)) return wt;
     float* wt = r.W(r.p.wT);
-    tc_prep_weights(w_hwio, wt, taps, Cin, Cout, dgrad, split(), r.st);
+    tc_prep_weights(w_hwio, wt, taps, Cin, Cout, dgrad, split(), r.st, Cs);
     return wt;
+  }
+  // Folded pooled branch (k_pool.cu): is the 3x3 layer served by the kernel that adds the border-class bias?
+  bool fold() const {
+    static int off = -1;
+    if (off < 0) { const char* e = getenv("MLIIS_NO_FOLD"); off = e ? atoi(e) : 0; }
+    return tc() && !off;
+  }
+  // out = conv3x3(A[:, :Cin] ; first Cin of the Cs input channels of w) + bias + bias9[img][border class]
+  bool fwd_fold(const float* A, int lda, int H, int W, int Cin, int Cs, const float* w_hwio, const float* bias,
+                const float* bias9, float* out, int ldc, int Cout, int M) const {
+    if (!tc_supported(1, W, Cin, Cout)) return false;
+    float* wt = operand(w_hwio, 9, Cin, Cout, 0, Cs);
+    return tc_conv(A, lda, wt, bias, out, ldc, 1, M, r.B, H, W, Cin, 9, 1, Cout, 0, split(), r.st, nullptr, nullptr,
+                   nullptr, 0, bias9);
   }
   // forward: out[M, Cout] = conv(A[.., Cin]) + bias
   void fwd(const float* A, int lda, int conv, int H, int W, int Cin, int dil, const float* w_hwio, const float* bias,
@@ -241,13 +257,14 @@ struct Dense {
   // of A and G exchanged (MBConv expand conv: Cout = 6*Cin > 256 would not fit one N tile), then transpose.
   void wgrad(const float* A, int lda, int conv, int H, int W, int Cin, int dil, const float* G, int ldg, int Cout,
              float* dW, float* dbias, int M, int HW, const float* pa = nullptr, const float* pb = nullptr,
-             const float* gate = nullptr, bool swap = false) const {
+             const float* gate = nullptr, bool swap = false, int dw_tap_stride = 0) const {
     const int taps = conv ? 9 : 1;
     float* scratch = r.W(r.p.tn_scratch);
     bool done = false;
     if (tc()) {
       if (!swap && tc_wgrad_supported(conv, W, Cin, Cout)) {
-        done = tc_wgrad(A, lda, G, ldg, dW, scratch, conv, M, r.B, H, W, Cin, taps, dil, Cout, split(), r.st, pa, pb, gate, HW);
+        done = tc_wgrad(A, lda, G, ldg, dW, scratch, conv, M, r.B, H, W, Cin, taps, dil, Cout, split(), r.st, pa, pb, gate, HW,
+                        dw_tap_stride);
       } else if (swap && !conv && !pa && tc_wgrad_supported(0, W, Cout, Cin)) {
         float* tmp = r.W(r.p.wT);      // dW^T [Cout][Cin]
         done = tc_wgrad(G, ldg, A, lda, tmp, scratch, 0, M, r.B, H, W, Cout, 1, 1, Cin, split(), r.st);
@@ -263,11 +280,11 @@ struct Dense {
   }
   // dgrad: dA[M, Cin] (+)= conv^T(G[.., Cout])
   void dgrad(const float* G, int ldg, int conv, int H, int W, int Cin, int dil, const float* w_hwio, float* dA, int ldd,
-             int Cout, int M, int HW, int accumulate) const {
+             int Cout, int M, int HW, int accumulate, int Cs = 0) const {
     const int taps = conv ? 9 : 1;
     float* wt = r.W(r.p.wT);
     if (tc() && tc_supported(conv, W, Cout, Cin)) {
-      float* wtc = operand(w_hwio, taps, Cin, Cout, 1);
+      float* wtc = operand(w_hwio, taps, Cin, Cout, 1, Cs);
       if (tc_conv(G, ldg, wtc, nullptr, dA, ldd, conv, M, r.B, H, W, Cout, taps, dil, Cin, accumulate, split(), r.st)) return;
     }
     if (conv) {
@@ -356,11 +373,21 @@ void run_forward(const Run& r, const float* images, const int32_t* index, bool t
     dense.fwd(cat, d.catC, 1, d.h, d.w, d.catC, 2, r.T(d.w1), r.T(d.b1), r.W(d.c1.off), D, D, M, HW);
     if (training) r.bn_train(d.bn[1], r.W(d.c1.off), D, M, true);
     dec_bn_apply(r.W(d.c1.off), D, r.bn_a(d.bn[1]), r.bn_b(d.bn[1]), nullptr, 0, pyr + D, d.pyrC, M, D, st);
-    // branch_2: image-level mean, tiled (efficientlab.py:192-197)
+    // branch_2: image-level mean (efficientlab.py:192-197).  Tensor-core modes FOLD its tile into conv2d_2 as a
+    // per-image, per-border-class bias (k_pool.cu); the fp32 reference mode materialises it like the reference does.
     img_colsum(cat, d.catC, B, HW, d.catC, 1.f / (float)HW, r.W(p.partials), r.W(d.pooled), d.catC, st);
-    bcast_rows(r.W(d.pooled), d.catC, pyr + 2 * D, d.pyrC, B, HW, d.catC, st);
-    // 3x3 over the pyramid, + residual
-    dense.fwd(pyr, d.pyrC, 1, d.h, d.w, d.pyrC, 1, r.T(d.w2), r.T(d.b2), r.W(d.c2.off), D, D, M, HW);
+    bool folded = false;
+    if (dense.fold() && d.h >= 2 && d.w >= 2) {
+      pool_bias9(r.W(d.pooled), d.catC, r.T(d.w2), d.pyrC, 2 * D, d.catC, D, B, r.W(d.bias9), st);
+      folded = dense.fwd_fold(pyr, d.pyrC, d.h, d.w, 2 * D, d.pyrC, r.T(d.w2), r.T(d.b2), r.W(d.bias9), r.W(d.c2.off), D,
+                              D, M);
+    }
+    if (!folded) {
+      bcast_rows(r.W(d.pooled), d.catC, pyr + 2 * D, d.pyrC, B, HW, d.catC, st);
+      // 3x3 over the pyramid, + residual
+      dense.fwd(pyr, d.pyrC, 1, d.h, d.w, d.pyrC, 1, r.T(d.w2), r.T(d.b2), r.W(d.c2.off), D, D, M, HW);
+    }
+    r.sl->folded[&d - &p.rsds[0]] = folded;
     if (training) r.bn_train(d.bn[2], r.W(d.c2.off), D, M, true);
     dec_bn_apply(r.W(d.c2.off), D, r.bn_a(d.bn[2]), r.bn_b(d.bn[2]), cat, d.catC, r.W(d.out.off), D, M, D, st);
     deep = r.W(d.out.off);
@@ -488,12 +515,23 @@ void run_backward(const Run& r, const float* labels, const int32_t* index, float
     // out = BN2(swish(c2)) + up
     dec_bn_bwd(d.bn[2], r.W(d.c2.off), gOut, D, r.W(p.g_c));
     const Dense dense{r, true};
-    dense.wgrad(pyr, d.pyrC, 1, d.h, d.w, d.pyrC, 1, r.W(p.g_c), D, D, r.G(d.w2), r.G(d.b2), M, HW);
-    dense.dgrad(r.W(p.g_c), D, 1, d.h, d.w, d.pyrC, 1, r.T(d.w2), r.W(p.g_pyr), d.pyrC, D, M, HW, 0);
     const float* gpyr = r.W(p.g_pyr);
+    if (r.sl->folded[di]) {
+      // conv2d_2 over the 2D real channels; the pooled channels' weight / input gradients come from the region sums
+      // of dL/d(conv2d_2) (k_pool.cu)
+      dense.wgrad(pyr, d.pyrC, 1, d.h, d.w, 2 * D, 1, r.W(p.g_c), D, D, r.G(d.w2), r.G(d.b2), M, HW, nullptr, nullptr,
+                  nullptr, false, d.pyrC * D);
+      region_sums(r.W(p.g_c), D, B, d.h, d.w, 1, D, r.W(p.partials), r.W(d.S9), st);
+      pool_wgrad(r.W(d.pooled), d.catC, r.W(d.S9), B, d.pyrC, 2 * D, d.catC, D, r.G(d.w2), st);
+      dense.dgrad(r.W(p.g_c), D, 1, d.h, d.w, 2 * D, 1, r.T(d.w2), r.W(p.g_pyr), d.pyrC, D, M, HW, 0, d.pyrC);
+      pool_dgrad(r.W(d.S9), r.T(d.w2), d.pyrC, 2 * D, d.catC, D, B, 1.f / (float)HW, r.W(d.dpooled), d.catC, st);
+    } else {
+      dense.wgrad(pyr, d.pyrC, 1, d.h, d.w, d.pyrC, 1, r.W(p.g_c), D, D, r.G(d.w2), r.G(d.b2), M, HW);
+      dense.dgrad(r.W(p.g_c), D, 1, d.h, d.w, d.pyrC, 1, r.T(d.w2), r.W(p.g_pyr), d.pyrC, D, M, HW, 0);
+      img_colsum(gpyr + 2 * D, d.pyrC, B, HW, d.catC, 1.f / (float)HW, r.W(p.partials), r.W(d.dpooled), d.catC, st);
+    }
     dec_bn_bwd(d.bn[0], r.W(d.c0.off), gpyr, d.pyrC, r.W(p.g_c0));
     dec_bn_bwd(d.bn[1], r.W(d.c1.off), gpyr + D, d.pyrC, r.W(p.g_c1));
-    img_colsum(gpyr + 2 * D, d.pyrC, B, HW, d.catC, 1.f / (float)HW, r.W(p.partials), r.W(d.dpooled), d.catC, st);
     // branch_0 1x1
     dense.wgrad(cat, d.catC, 0, d.h, d.w, d.catC, 1, r.W(p.g_c0), D, D, r.G(d.w0), r.G(d.b0), M, HW);
     dense.dgrad(r.W(p.g_c0), D, 0, d.h, d.w, d.catC, 1, r.T(d.w0), r.W(p.g_cat), d.catC, D, M, HW, 0);
@@ -681,7 +719,7 @@ int mliis_ctx_create(const mliis_config* cfg, int device, mliis_ctx** out) {
       std::vector<TcPrepJob> jobs;
       for (const Plan::PrepJob& j : p.prep_jobs)
         jobs.push_back({(long long)j.w_off, (long long)j.dst, j.taps, j.Ci, j.Co, j.dgrad,
-                        (c->cfg.gemm_mode == MLIIS_GEMM_TF32 && j.decoder) ? 1 : 3, 0});
+                        (c->cfg.gemm_mode == MLIIS_GEMM_TF32 && j.decoder) ? 1 : 3, j.Cs});
       c->d_prep_jobs = upload(c, jobs);
     }
     c->tabs.resize(p.resize_pairs.size());

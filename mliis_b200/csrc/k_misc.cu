@@ -25,6 +25,26 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
   for (int j = 1; j < 8; ++j) s += red[j][threadIdx.x];
   out[i] = (float)s;
 }
+__global__ void __launch_bounds__(256) reduce_partials_strided_kernel(const float* __restrict__ partials, int G, int n,
+                                                                      int n_inner, float* __restrict__ out,
+                                                                      int64_t out_stride) {
+  __shared__ double red[8][33];
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  double s = 0.0;
+  if (i < n)
+    for (int g = threadIdx.y; g < G; g += 8) s += (double)partials[(size_t)g * n + i];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y != 0 || i >= n) return;
+  for (int j = 1; j < 8; ++j) s += red[j][threadIdx.x];
+  const int o = i / n_inner;
+  out[(size_t)o * out_stride + (i - o * n_inner)] = (float)s;
+}
+void reduce_partials_strided(const float* partials, int G, int n_inner, int n_outer, float* out, int64_t out_stride,
+                             cudaStream_t s) {
+  const int n = n_inner * n_outer;
+  MLIIS_COUNT(), reduce_partials_strided_kernel<<<cdiv(n, 32), dim3(32, 8), 0, s>>>(partials, G, n, n_inner, out, out_stride);
+}
 void reduce_partials(const float* partials, int G, int n, float* out, cudaStream_t s) {
   MLIIS_COUNT(), reduce_partials_kernel<<<cdiv(n, 32), dim3(32, 8), 0, s>>>(partials, G, n, out);
 }

@@ -122,8 +122,9 @@ struct TcParams {
   int tiles_per_image;
   int C;             // K per tap
   int taps, dil;
-  int N, BN, ldc, accumulate;
+  int N, BN, accumulate;
   int stages;
+  int region_bytes;  // shared memory of the stage ring (>= 32 KB: the epilogue reuses it as two 16 KB staging tiles)
   int a_box_bytes;   // bytes one A box delivers
   int split;         // 1: TF32 (operands rounded to nearest)  3: 3xTF32 (hi/lo split, fp32-class accuracy)
   // A-operand prologue applied by the transform warps (plain mode): a <- swish(pa[k]*a + pb[k]) * gate[img][k]
@@ -131,7 +132,10 @@ struct TcParams {
   int HW;
 };
 
-constexpr int kTcThreads = 192;
+constexpr int kTcXformWarps = 8;                       // operand transform during the main loop, then epilogue
+constexpr int kTcXformThreads = 32 * kTcXformWarps;    // 256
+constexpr int kTcThreads = 64 + kTcXformThreads;       // + TMA producer warp + MMA issuer warp
+constexpr int kC3Threads = 192;                        // tc_conv3_kernel: 4 transform / epilogue warps
 constexpr int kABytes = 128 * 128;   // 128 rows x 32 fp32
 
 // round to nearest TF32 (ties away from zero, same result as cvt.rna.tf32.f32) with two full-rate integer ops
@@ -142,11 +146,50 @@ __device__ __forceinline__ float4 rn_tf32_4(float4 v) { return f4(rn_tf32(v.x), 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// swish with the MUFU reciprocal (<= 2 ulp): x * 1/(1 + 2^(-x*log2 e)); the transform warps are ALU-bound
+__device__ __forceinline__ float swish_fast(float x) { return x * __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float4 swish_fast4(float4 v) {
+  return f4(swish_fast(v.x), swish_fast(v.y), swish_fast(v.z), swish_fast(v.w));
+}
+// barrier ids are immediates so that ptxas reserves only the barriers actually used
+__device__ __forceinline__ void named_bar_sync_half(int half) {
+  if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+  else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
+// TMA stores of one shared-memory tile (dense [rows][128 B], SWIZZLE_128B) into a global tensor; rows / columns
+// outside the tensor are clipped by the TMA unit.  `add`: out += tile (element-wise reduction in L2; every output
+// element is produced by exactly one CTA, so the result is deterministic).
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1, bool add) {
+  if (add)
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, bool add) {
+  if (add)
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-// Stage layout: [A (hi) 16 KB][A lo 16 KB if split==3][B hi BN*128][B lo BN*128 if split==3]
+// Shared memory: [stage ring: S x {A (hi) 16 KB | A lo 16 KB if split==3 | B hi BN*128 | B lo BN*128 if split==3}]
+//                [barriers][prologue coefficients: pa | pb | gate(image 0) | gate(image 1), Kp floats each]
+// Generic 1x1 / small 3x3 implicit GEMM, one 128-row tile per CTA.  Round-2 changes (round-1 ncu: 3.6 % of HBM on the
+// MBConv project convs, bound by 4 transform warps doing expf + a float division + an integer division + three global
+// coefficient loads per float4): 8 transform warps, every per-thread constant hoisted (a thread always owns the same
+// channel group and the same 4 rows, so the image index of its rows is computed once), coefficients and gates staged
+// in shared memory once per CTA, MUFU reciprocal; shared memory sized for 2 CTAs per SM where the stage is small; the
+// epilogue goes TMEM -> registers -> swizzled shared-memory tile -> one TMA store per 32 output columns (coalesced
+// 128-byte rows instead of 32 scattered 16-byte stores per warp instruction).
 __global__ void __launch_bounds__(kTcThreads)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const float* __restrict__ bias, float* __restrict__ out, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   if (p.debug & 16) return;   // experiment: cost of everything except the tensor-core kernels
   const uint32_t raw = smem_u32(smem_raw);
@@ -158,13 +201,19 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int a_off_lo = kABytes;
   const int b_off = x3 ? 2 * kABytes : kABytes;
   const int stage_bytes = b_off + (x3 ? 2 : 1) * b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
-  const uint32_t bar0 = base + (uint32_t)p.stages * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.region_bytes);
+  const uint32_t bar0 = base + (uint32_t)p.region_bytes;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };                      // TMA -> transform warps
   auto empty_bar = [&](int s) { return bar0 + 8u * (p.stages + s); };        // MMA -> TMA
   auto ready_bar = [&](int s) { return bar0 + 8u * (2 * p.stages + s); };    // transform warps -> MMA
   const uint32_t tmem_full_bar = bar0 + 8u * (3 * p.stages);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 1);
+  const int Kp = (p.C + 31) & ~31;
+  float* coef = reinterpret_cast<float*>(smem + p.region_bytes + ((8 * (3 * p.stages + 2) + 15) & ~15));
+  float* s_pa = coef;
+  float* s_pb = coef + Kp;
+  float* s_g0 = coef + 2 * Kp;
+  float* s_g1 = coef + 3 * Kp;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // wide: hi and lo weight planes are adjacent in the stage, so one N = 2*BN MMA forms a_hi*b_hi | a_hi*b_lo in two
@@ -174,27 +223,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const bool wide = x3 && 2 * p.BN <= 256 && !(p.debug & 8) && (p.taps * ((p.C + 31) / 32) >= 4 || 2 * p.BN <= 128);
   uint32_t ncols = 32;
   while ((int)ncols < (wide ? 2 : 1) * p.BN) ncols <<= 1;
-
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-      mbar_init(ready_bar(s), 128);
-    }
-    mbar_init(tmem_full_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_acc = *tmem_slot;
 
   // tile coordinates
   int img = 0, y0 = 0, m0 = 0;
@@ -207,6 +235,44 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int n0 = blockIdx.y * p.BN;
   const int kchunks = (p.C + 31) / 32;
   const int KB = p.taps * kchunks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(ready_bar(s), kTcXformThreads);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // prologue coefficients -> shared memory (zero beyond C: swish(0*x + 0) = 0 keeps the TMA zero fill).  A tile
+  // of 128 rows spans at most two images when HW >= 127; smaller images (tests) read their gates from global memory.
+  const int im0 = p.pa ? m0 / p.HW : 0;
+  const bool gate_smem = p.gate != nullptr && (min(m0 + 127, p.M - 1) / p.HW) <= im0 + 1;
+  if (p.pa) {
+    const int im1 = ((im0 + 1) * p.HW < p.M) ? im0 + 1 : im0;
+    for (int i = threadIdx.x; i < Kp; i += kTcThreads) {
+      const bool in = i < p.C;
+      s_pa[i] = in ? p.pa[i] : 0.f;
+      s_pb[i] = in ? p.pb[i] : 0.f;
+      if (gate_smem) {
+        s_g0[i] = in ? p.gate[(size_t)im0 * p.C + i] : 0.f;
+        s_g1[i] = in ? p.gate[(size_t)im1 * p.C + i] : 0.f;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -264,78 +330,117 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ---------------- operand transform (during the main loop), then epilogue ----------------
-    const int t = threadIdx.x - 64;   // 0..127
+    const int t = threadIdx.x - 64;   // 0..255
+    // float4 i = t + 256*j of the 16 KB A tile: row = i/8 = (t>>3) + 32*j, physical 16-byte chunk = t&7.
+    // SWIZZLE_128B: logical chunk = physical chunk XOR (row & 7); 32*j does not touch the low 3 row bits, so a
+    // thread owns ONE channel group for the whole kernel and the same four rows in every stage.
+    const int rl = t >> 3;
+    const int lc4 = (((t & 7) ^ (rl & 7)) << 2);
+    int sel[4];
+    size_t goff[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + rl + 32 * j;
+      const int im = (p.gate && m < p.M) ? m / p.HW : im0;
+      sel[j] = im - im0;
+      goff[j] = (size_t)im * p.C;
+    }
     for (int kb = 0; kb < KB && xform; ++kb) {
       const int s = kb % p.stages;
+      const int k = (kb % kchunks) * 32 + lc4;
+      float4 a4 = f4s(0.f), b4 = f4s(0.f), g4[4];
+      if (p.pa) {
+        a4 = ld4(s_pa + k);
+        b4 = ld4(s_pb + k);
+        if (p.gate) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (gate_smem) g4[j] = ld4((sel[j] ? s_g1 : s_g0) + k);
+            else g4[j] = k < p.C ? ld4(p.gate + goff[j] + k) : f4s(0.f);
+          }
+        }
+      }
       mbar_wait(full_bar(s), (kb / p.stages) & 1);
       float4* a_hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
       float4* a_lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + a_off_lo);
-      const int kc32 = (kb % kchunks) * 32;
+      if (!(p.debug & 1)) {
+        float4 v[4];
 #pragma unroll
-      for (int j = 0; j < 8 && !(p.debug & 1); ++j) {
-        const int i = t + 128 * j;     // float4 index inside the 16 KB A tile: row = i/8, physical 16-byte chunk = i%8
-        float4 v = a_hi[i];
-        if (p.pa) {
-          // SWIZZLE_128B: logical chunk = physical chunk XOR (row & 7)  ->  channel of this float4
-          const int row = i >> 3;
-          const int k = kc32 + (((i & 7) ^ (row & 7)) << 2);
-          if (k < p.C) {
-            v = swish4(affine4(v, ld4(p.pa + k), ld4(p.pb + k)));
-            if (p.gate) {
-              const int m = m0 + row;
-              const int im = m < p.M ? m / p.HW : 0;
-              v = v * ld4(p.gate + (size_t)im * p.C + k);
-            }
+        for (int j = 0; j < 4; ++j) v[j] = a_hi[t + kTcXformThreads * j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 x = v[j];
+          if (p.pa) {
+            x = swish_fast4(affine4(x, a4, b4));
+            if (p.gate) x = x * g4[j];
           }
+          const float4 h = rn_tf32_4(x);
+          a_hi[t + kTcXformThreads * j] = h;
+          if (x3) a_lo[t + kTcXformThreads * j] = rn_tf32_4(x - h);
         }
-        const float4 h = rn_tf32_4(v);
-        a_hi[i] = h;
-        if (x3) a_lo[i] = rn_tf32_4(v - h);
       }
       // generic-proxy writes must be visible to the async proxy (tcgen05.mma reads smem through it)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(ready_bar(s));
     }
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;          // accumulator row == TMEM lane
-    mbar_wait(tmem_full_bar, 0);
+    // ---- epilogue: TMEM lane quarter = warp & 3 (hardware rule); the two warps of a quarter split the 32-column
+    // chunks (half 0: even chunks, half 1: odd chunks); each half stages through its own 16 KB tile of the ring ----
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int r = quarter * 32 + lane;          // accumulator row == TMEM lane == row of the staging tile
+    const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
+    mbar_wait(tmem_full_bar, 0);                // every MMA has completed: the stage ring is free
     tc_fence_after();
-    bool valid;
-    size_t row;
-    if (p.conv) {
-      const int ly = r / p.W, lx = r - ly * p.W;
-      valid = r < p.BH * p.W && (y0 + ly) < p.H;
-      row = ((size_t)img * p.H + (y0 + ly)) * p.W + lx;
-    } else {
-      valid = m0 + r < p.M;
-      row = (size_t)m0 + r;
-    }
-    float* orow = out + row * p.ldc;
+    uint8_t* stg = smem + half * 16384;
+    const uint32_t stg_addr = base + (uint32_t)half * 16384u;
     const uint32_t tbase = tmem_acc + ((uint32_t)(quarter * 32) << 16);
-    for (int c = 0; c < p.BN; c += 16) {
-      uint32_t v[16];
+    const int nchunks = (p.BN + 31) / 32;
+    for (int ch = half; ch < nchunks; ch += 2) {
+      const int c = ch * 32, n = n0 + c;
+      if (n >= p.N) break;                      // uniform over the half: whole chunk outside the tensor
+      uint32_t v[32];
       __syncwarp();
-      tc_ld16(tbase + (uint32_t)c, v);          // warp-collective: executed by all 32 lanes, converged
-      if (wide) {
-        uint32_t w[16];
-        tc_ld16(tbase + (uint32_t)(p.BN + c), w);
+      {
+        uint32_t u[16];
+        tc_ld16(tbase + (uint32_t)c, u);        // warp-collective: executed by all 32 lanes, converged
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(w[q]));
-      }
-      if (valid) {
+        for (int q = 0; q < 16; ++q) v[q] = u[q];
+        if (c + 16 < p.BN) {
+          tc_ld16(tbase + (uint32_t)(c + 16), u);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int n = n0 + c + q * 4;
-          if (n < p.N) {
-            float4 o = f4(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
-                          __uint_as_float(v[q * 4 + 3]));
-            if (bias) o = o + ld4(bias + n);
-            if (p.accumulate) o = o + ld4(orow + n);
-            st4(orow + n, o);
+          for (int q = 0; q < 16; ++q) v[16 + q] = u[q];
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[16 + q] = 0u;
+        }
+        if (wide) {
+          tc_ld16(tbase + (uint32_t)(p.BN + c), u);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(u[q]));
+          if (c + 16 < p.BN) {
+            tc_ld16(tbase + (uint32_t)(p.BN + c + 16), u);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[16 + q] = __float_as_uint(__uint_as_float(v[16 + q]) + __uint_as_float(u[q]));
           }
         }
       }
+      if (leader) tma_store_wait_read();        // the previous store of this half has finished reading the tile
+      named_bar_sync_half(half);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 o = f4(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
+                      __uint_as_float(v[q * 4 + 3]));
+        if (bias && n + q * 4 < p.N) o = o + ld4(bias + n + q * 4);
+        *reinterpret_cast<float4*>(stg + r * 128 + ((q ^ (r & 7)) << 4)) = o;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      named_bar_sync_half(half);
+      if (leader) {
+        if (p.conv) tma_store_3d(&tmC, stg_addr, n, y0 * p.W, img, p.accumulate != 0);
+        else tma_store_2d(&tmC, stg_addr, n, m0, p.accumulate != 0);
+        tma_store_commit();
+      }
     }
+    if (leader) tma_store_wait_read();          // shared memory must stay valid until the TMA unit has read it
     tc_fence_before();
   }
   __syncthreads();
@@ -363,6 +468,7 @@ struct TcC3Params {
   int a_box_bytes, a_slot_bytes, b_plane_bytes;
   int boff;          // experiment knob: 1 = set the descriptor base_offset field for shifted starts, 0 = leave it 0
   int debug;         // MLIIS_TC_DEBUG bits: 1 skip operand transform, 2 skip MMA issue, 4 one tile per CTA, 8 no wide-B
+  const float* bias9;   // [B][9][N] per-image, per-border-class bias (folded pooled branch) or null
 };
 
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc_off(uint32_t smem_addr) {
@@ -370,7 +476,7 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc_off(uint32_t smem_add
   return make_kmajor_sw128_desc(smem_addr) | ((uint64_t)((smem_addr >> 7) & 7) << 49);
 }
 
-__global__ void __launch_bounds__(kTcThreads)
+__global__ void __launch_bounds__(kC3Threads)
 tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const float* __restrict__ bias, float* __restrict__ out, const TcC3Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -510,6 +616,11 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int y = y0 + tile * p.BH + ly;
       const bool valid = ly < p.BH && lx < p.W && y < p.H;
       float* orow = out + (((size_t)img * p.H + y) * p.W + lx) * p.ldc;
+      const float* b9 = nullptr;
+      if (p.bias9) {   // border class of this output pixel: which filter taps read inside the image (k_pool.cu)
+        const int cls = (y < p.dil ? 0 : (y >= p.H - p.dil ? 2 : 1)) * 3 + (lx < p.dil ? 0 : (lx >= p.W - p.dil ? 2 : 1));
+        b9 = p.bias9 + ((size_t)img * 9 + cls) * p.N;
+      }
       const uint32_t tbase = tmem_acc + (uint32_t)(tile * p.ncol_acc) + ((uint32_t)(quarter * 32) << 16);
       for (int c = 0; c < p.BN; c += 16) {
         uint32_t v[16];
@@ -529,6 +640,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               float4 o = f4(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
                             __uint_as_float(v[q * 4 + 3]));
               if (bias) o = o + ld4(bias + n);
+              if (b9) o = o + ld4(b9 + n);
               if (p.accumulate) o = o + ld4(orow + n);
               st4(orow + n, o);
             }
@@ -579,7 +691,9 @@ static bool encode(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* 
 int tc_pick_bn(int N) {
   int tiles = (N + 255) / 256;
   int bn = (N + tiles - 1) / tiles;
-  return (bn + 15) / 16 * 16;
+  // several N tiles: every tile must end on a 32-column boundary (the epilogue stores 32-column TMA boxes; a single
+  // tile may overhang N because the TMA unit clips at the tensor edge)
+  return tiles > 1 ? (bn + 31) / 32 * 32 : (bn + 15) / 16 * 16;
 }
 
 bool tc_supported(int conv, int W, int C, int N) {
@@ -590,7 +704,7 @@ bool tc_supported(int conv, int W, int C, int N) {
 
 // second-generation 3x3 path; returns false when the shape does not fit (caller uses tc_conv_kernel)
 static bool tc_conv3(const float* A, int lda, const float* Wt, const float* bias, float* out, int ldc, int B, int H, int W,
-                     int C, int dil, int N, int accumulate, int split, cudaStream_t s) {
+                     int C, int dil, int N, int accumulate, int split, cudaStream_t s, const float* bias9) {
   static int enabled = -1;
   if (enabled < 0) { const char* e = getenv("MLIIS_TC_CONV3"); enabled = e ? atoi(e) : 1; }
   if (!enabled) return false;
@@ -600,6 +714,7 @@ static bool tc_conv3(const float* A, int lda, const float* Wt, const float* bias
   if (dbg3 < 0) { const char* e = getenv("MLIIS_TC_DEBUG"); dbg3 = e ? atoi(e) : 0; }
   p.boff = boff;
   p.debug = dbg3;
+  p.bias9 = bias9;
   p.H = H; p.W = W; p.C = C; p.dil = dil; p.N = N; p.ldc = ldc; p.accumulate = accumulate;
   p.split = split == 3 ? 3 : 1;
   p.RW = W + 2 * dil;
@@ -651,14 +766,14 @@ static bool tc_conv3(const float* A, int lda, const float* Wt, const float* bias
     attr = true;
   }
   dim3 grid(B * p.groups_per_image, (N + p.BN - 1) / p.BN);
-  MLIIS_COUNT(), tc_conv3_kernel<<<grid, kTcThreads, smem, s>>>(tmA, tmB, bias, out, p);
+  MLIIS_COUNT(), tc_conv3_kernel<<<grid, kC3Threads, smem, s>>>(tmA, tmB, bias, out, p);
   return true;
 }
 
 // Wt layout expected by the kernel: [N][taps][C]  (K-major rows of B)
 bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float* out, int ldc, int conv, int M, int B,
              int H, int W, int C, int taps, int dil, int N, int accumulate, int split, cudaStream_t s,
-             const float* pa, const float* pb, const float* gate, int HW) {
+             const float* pa, const float* pb, const float* gate, int HW, const float* bias9) {
   TcParams p{};
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("MLIIS_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -666,12 +781,13 @@ bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float*
   p.split = split == 3 ? 3 : 1;
   if (pa && conv) return false;
   p.pa = pa; p.pb = pb; p.gate = gate; p.HW = HW > 0 ? HW : 1;
-  p.conv = conv; p.M = M; p.H = H; p.W = W; p.C = C; p.taps = taps; p.dil = dil; p.N = N; p.ldc = ldc;
+  p.conv = conv; p.M = M; p.H = H; p.W = W; p.C = C; p.taps = taps; p.dil = dil; p.N = N;
   p.accumulate = accumulate;
-  if (conv && taps == 9 && tc_conv3(A, lda, Wt, bias, out, ldc, B, H, W, C, dil, N, accumulate, p.split, s))
+  if (conv && taps == 9 && tc_conv3(A, lda, Wt, bias, out, ldc, B, H, W, C, dil, N, accumulate, p.split, s, bias9))
     return true;
+  if (bias9) return false;        // only tc_conv3_kernel adds the border-class bias
   p.BN = tc_pick_bn(N);
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
   int grid_x;
   if (conv) {
     p.BH = 128 / W;
@@ -683,6 +799,11 @@ bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float*
     cuuint32_t box[4] = {32, (cuuint32_t)W, (cuuint32_t)p.BH, 1};
     if (!encode(&tmA, A, 4, dims, str, box)) return false;
     grid_x = B * p.tiles_per_image;
+    // output [B, H*W, N]: one box = the BH*W pixels of the tile x 32 columns (rows past the image are clipped)
+    cuuint64_t cd[3] = {(cuuint64_t)N, (cuuint64_t)H * W, (cuuint64_t)B};
+    cuuint64_t cs[2] = {(cuuint64_t)ldc * 4, (cuuint64_t)H * W * ldc * 4};
+    cuuint32_t cb[3] = {32, (cuuint32_t)(p.BH * W), 1};
+    if (!encode(&tmC, out, 3, cd, cs, cb)) return false;
   } else {
     p.a_box_bytes = kABytes;
     cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)M};
@@ -690,6 +811,9 @@ bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float*
     cuuint32_t box[2] = {32, 128};
     if (!encode(&tmA, A, 2, dims, str, box)) return false;
     grid_x = (M + 127) / 128;
+    cuuint64_t cd[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    cuuint64_t cs[1] = {(cuuint64_t)ldc * 4};
+    if (!encode(&tmC, out, 2, cd, cs, box)) return false;
   }
   {
     // operand planes: [hi][N][taps][C] and, for split == 3, [lo][N][taps][C] right behind it
@@ -699,19 +823,28 @@ bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float*
     if (!encode(&tmB, Wt, 4, dims, str, box)) return false;
   }
   const int stage_bytes = (p.split == 3 ? 2 : 1) * (kABytes + p.BN * 128);
-  p.stages = (200 * 1024) / stage_bytes;
-  if (p.stages > 6) p.stages = 6;
   const int KB = taps * ((C + 31) / 32);
-  if (p.stages > KB) p.stages = KB;        // small-K problems: less shared memory -> several CTAs per SM
-  if (p.stages < 1) return false;
-  const size_t smem = (size_t)p.stages * stage_bytes + (3 * p.stages + 2) * 8 + 1024;
+  const int Kp = (C + 31) / 32 * 32;
+  const int tail_bytes = 8 * (3 * 6 + 2) + 16 + (pa ? 16 * Kp : 0) + 1024;
+  // small stages: size the ring so that two CTAs share an SM (their TMA round trips and fixed start-up costs overlap);
+  // big stages (BN >= 128 with both planes): one CTA per SM with a deeper ring
+  const int budget2 = (227 * 1024) / 2 - tail_bytes;
+  int stages = budget2 / stage_bytes;
+  if (stages < 3) stages = (200 * 1024 - tail_bytes) / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages > KB) stages = KB;        // small-K problems: less shared memory -> several CTAs per SM
+  if (stages < 1) return false;
+  p.stages = stages;
+  p.region_bytes = stages * stage_bytes;
+  if (p.region_bytes < 32768) p.region_bytes = 32768;
+  const size_t smem = (size_t)p.region_bytes + ((8 * (3 * stages + 2) + 15) & ~15) + (pa ? 16 * Kp : 0) + 1024;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
   dim3 grid(grid_x, (N + p.BN - 1) / p.BN);
-  MLIIS_COUNT(), tc_conv_kernel<<<grid, kTcThreads, smem, s>>>(tmA, tmB, bias, out, p);
+  MLIIS_COUNT(), tc_conv_kernel<<<grid, kTcThreads, smem, s>>>(tmA, tmB, tmC, bias, p);
   return true;
 }
 
@@ -885,29 +1018,40 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else {
     const int t = threadIdx.x - 64;
+    // A tile (plain mode): float4 i = t + 512*j, j = 0,1 -> 32-channel group (t>>8) + 2*j, pixel row (t&255)>>3 and
+    // 16-byte chunk t&7 are the same for both: the prologue coefficients of a thread never change (c0 is per CTA)
+    const int arow = (t & 255) >> 3, af = t & 7;
+    // SWIZZLE_128B_ATOM_32B: logical 32-byte chunk = physical chunk XOR (row & 3)
+    const int kk = ((((af >> 1) ^ (arow & 3)) << 1) | (af & 1)) << 2;
+    float4 pa4[2], pb4[2];
+    int kch[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      kch[j] = c0 + 32 * ((t >> 8) + 2 * j) + kk;
+      const bool in = p.pa != nullptr && kch[j] < p.C;
+      pa4[j] = in ? ld4(p.pa + kch[j]) : f4s(0.f);      // zero coefficients keep the TMA zero fill: swish(0) = 0
+      pb4[j] = in ? ld4(p.pb + kch[j]) : f4s(0.f);
+    }
     for (int kb = 0; kb < KB; ++kb) {
       const int s = kb % p.stages;
+      float4 gt[2];
+      if (p.gate) {
+        const int m = (t_beg + kb) * 32 + arow;
+        const int im = m < p.M ? m / p.HW : 0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) gt[j] = kch[j] < p.C ? ld4(p.gate + (size_t)im * p.C + kch[j]) : f4s(0.f);
+      }
       mbar_wait(full_bar(s), (kb / p.stages) & 1);
       uint8_t* st = smem + (size_t)s * stage_bytes;
       float4* a_hi = reinterpret_cast<float4*>(st);
       float4* a_lop = reinterpret_cast<float4*>(st + a_lo);
-      const int m0 = (t_beg + kb) * 32;
 #pragma unroll
       for (int j = 0; j < 1024 / kWgXformThreads && !(p.debug & 1); ++j) {            // A: 4 groups x 256 float4
         const int i = t + kWgXformThreads * j;
         float4 v = a_hi[i];
         if (p.pa) {
-          // SWIZZLE_128B_ATOM_32B: logical 32-byte chunk = physical chunk XOR (row & 3)
-          const int g = i >> 8, idx = i & 255, row = idx >> 3, f4i = idx & 7;
-          const int k = c0 + 32 * g + ((((((f4i >> 1) ^ (row & 3)) << 1) | (f4i & 1))) << 2);
-          if (k < p.C) {
-            v = swish4(affine4(v, ld4(p.pa + k), ld4(p.pb + k)));
-            if (p.gate) {
-              const int m = m0 + row;
-              const int im = m < p.M ? m / p.HW : 0;
-              v = v * ld4(p.gate + (size_t)im * p.C + k);
-            }
-          }
+          v = swish_fast4(affine4(v, pa4[j], pb4[j]));
+          if (p.gate) v = v * gt[j];
         }
         const float4 h = rn_tf32_4(v);
         a_hi[i] = h;
@@ -1006,7 +1150,7 @@ size_t tc_wgrad_scratch(int conv, int M, int B, int H, int W, int C, int N, int 
 // dW[taps*C, N] = sum A^T G ; scratch holds the per-split partials (tc_wgrad_scratch floats)
 bool tc_wgrad(const float* A, int lda, const float* G, int ldg, float* dW, float* scratch, int conv, int M, int B, int H,
               int W, int C, int taps, int dil, int N, int split, cudaStream_t s, const float* pa, const float* pb,
-              const float* gate, int HW) {
+              const float* gate, int HW, int dw_tap_stride) {
   TcWgParams p{};
   p.conv = conv; p.M = M; p.H = H; p.W = W; p.C = C; p.N = N; p.taps = taps; p.dil = dil;
   static int dbgw = -1;
@@ -1073,31 +1217,34 @@ bool tc_wgrad(const float* A, int lda, const float* G, int ldg, float* dW, float
   }
   dim3 grid(ctiles, grid_taps, p.splits);
   MLIIS_COUNT(), tc_wgrad_kernel<<<grid, kWgThreads, smem, s>>>(tmA, tmG, scratch, p);
-  reduce_partials(scratch, p.splits, taps * C * N, dW, s);
+  if (dw_tap_stride > 0 && dw_tap_stride != C * N)
+    reduce_partials_strided(scratch, p.splits, C * N, taps, dW, dw_tap_stride, s);
+  else
+    reduce_partials(scratch, p.splits, taps * C * N, dW, s);
   return true;
 }
 
 // weights W[tap][ci][co] (HWIO) -> forward operand Wt[co][tap][ci]   or   dgrad operand Wt[ci][taps-1-tap][co],
 // rounded to nearest TF32; split == 3 also writes the residual plane lo = rn(w - hi) behind the hi plane.
 __device__ __forceinline__ void prep_one(const float* __restrict__ w, float* __restrict__ wt, int i, int n, int taps,
-                                         int Ci, int Co, int dgrad, int split) {
+                                         int Ci, int Co, int dgrad, int split, int Cs) {
   float v;
   if (!dgrad) {
     const int co = i / (taps * Ci), rem = i - co * taps * Ci, tap = rem / Ci, ci = rem - tap * Ci;
-    v = w[((size_t)tap * Ci + ci) * Co + co];
+    v = w[((size_t)tap * Cs + ci) * Co + co];
   } else {
     const int ci = i / (taps * Co), rem = i - ci * taps * Co, tap = rem / Co, co = rem - tap * Co;
-    v = w[((size_t)(taps - 1 - tap) * Ci + ci) * Co + co];
+    v = w[((size_t)(taps - 1 - tap) * Cs + ci) * Co + co];
   }
   const float h = rn_tf32(v);
   wt[i] = h;
   if (split == 3) wt[(size_t)n + i] = rn_tf32(v - h);
 }
 __global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ wt, int taps, int Ci, int Co,
-                                       int dgrad, int split) {
+                                       int dgrad, int split, int Cs) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = taps * Ci * Co;
-  if (i < n) prep_one(w, wt, i, n, taps, Ci, Co, dgrad, split);
+  if (i < n) prep_one(w, wt, i, n, taps, Ci, Co, dgrad, split, Cs);
 }
 // every dense layer's forward and dgrad operand in ONE launch per step (blockIdx.y = job)
 __global__ void tc_prep_all_kernel(const float* __restrict__ theta, float* __restrict__ wcache,
@@ -1105,15 +1252,15 @@ __global__ void tc_prep_all_kernel(const float* __restrict__ theta, float* __res
   const TcPrepJob j = jobs[blockIdx.y];
   const int n = j.taps * j.Ci * j.Co;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    prep_one(theta + j.w_off, wcache + j.dst, i, n, j.taps, j.Ci, j.Co, j.dgrad, j.split);
+    prep_one(theta + j.w_off, wcache + j.dst, i, n, j.taps, j.Ci, j.Co, j.dgrad, j.split, j.Cs > 0 ? j.Cs : j.Ci);
 }
 void tc_prep_all(const float* theta, float* wcache, const TcPrepJob* dev_jobs, int n_jobs, cudaStream_t s) {
   if (n_jobs <= 0) return;
   MLIIS_COUNT(), tc_prep_all_kernel<<<dim3(24, n_jobs), 256, 0, s>>>(theta, wcache, dev_jobs);
 }
-void tc_prep_weights(const float* w, float* wt, int taps, int Ci, int Co, int dgrad, int split, cudaStream_t s) {
+void tc_prep_weights(const float* w, float* wt, int taps, int Ci, int Co, int dgrad, int split, cudaStream_t s, int Cs) {
   const int n = taps * Ci * Co;
-  MLIIS_COUNT(), tc_prep_weights_kernel<<<cdiv(n, 256), 256, 0, s>>>(w, wt, taps, Ci, Co, dgrad, split);
+  MLIIS_COUNT(), tc_prep_weights_kernel<<<cdiv(n, 256), 256, 0, s>>>(w, wt, taps, Ci, Co, dgrad, split, Cs > 0 ? Cs : Ci);
 }
 
 }  // namespace mliis

@@ -123,22 +123,40 @@ bool tc_supported(int conv, int W, int C, int N);
 // split = 1: TF32 with round-to-nearest operands; split = 3: 3xTF32 (hi/lo planes, fp32-class accuracy).
 // Optional A prologue (conv = 0 only): a <- swish(pa[k]*a + pb[k]) * gate[row / HW][k], applied in shared memory by
 // the transform warps (MBConv project conv: BN1 + swish + squeeze-excite gate never touch HBM).
+// bias9 (3x3 only): per-image, per-border-class bias [B][9][N] added in the epilogue (folded pooled branch, k_pool.cu);
+// returns false if the shape does not fit the kernel that implements it (tc_conv3_kernel).
 bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float* out, int ldc, int conv, int M, int B,
              int H, int W, int C, int taps, int dil, int N, int accumulate, int split, cudaStream_t s,
-             const float* pa = nullptr, const float* pb = nullptr, const float* gate = nullptr, int HW = 0);
+             const float* pa = nullptr, const float* pb = nullptr, const float* gate = nullptr, int HW = 0,
+             const float* bias9 = nullptr);
 // W[tap][ci][co] (HWIO) -> Wt[co][tap][ci] (dgrad=0)  or  Wt[ci][taps-1-tap][co] (dgrad=1), rn(tf32);
-// split == 3 appends the residual plane (wt must hold 2 * taps*Ci*Co floats)
-void tc_prep_weights(const float* w, float* wt, int taps, int Ci, int Co, int dgrad, int split, cudaStream_t s);
+// split == 3 appends the residual plane (wt must hold 2 * taps*Ci*Co floats).  Cs >= Ci: input channels per tap of
+// the SOURCE tensor (the operand uses its first Ci: conv2d_2 without the folded pooled channels); 0 = Ci.
+void tc_prep_weights(const float* w, float* wt, int taps, int Ci, int Co, int dgrad, int split, cudaStream_t s,
+                     int Cs = 0);
 // one launch per step: operand (re-layout + TF32 hi/lo split) of every dense layer, forward and dgrad
-struct TcPrepJob { long long w_off, dst; int taps, Ci, Co, dgrad, split, pad; };
+struct TcPrepJob { long long w_off, dst; int taps, Ci, Co, dgrad, split, Cs; };
 void tc_prep_all(const float* theta, float* wcache, const TcPrepJob* dev_jobs, int n_jobs, cudaStream_t s);
 
 // wgrad on tensor cores: dW[taps*C, N] = sum_pixels A[pixel+tap, c] * G[pixel, n]  (A, G channel-contiguous)
 bool tc_wgrad_supported(int conv, int W, int C, int N);
 size_t tc_wgrad_scratch(int conv, int M, int B, int H, int W, int C, int N, int taps);
+// dw_tap_stride: floats between consecutive taps of dW (0 = dense taps, C*N)
 bool tc_wgrad(const float* A, int lda, const float* G, int ldg, float* dW, float* scratch, int conv, int M, int B, int H,
               int W, int C, int taps, int dil, int N, int split, cudaStream_t s, const float* pa = nullptr,
-              const float* pb = nullptr, const float* gate = nullptr, int HW = 0);
+              const float* pb = nullptr, const float* gate = nullptr, int HW = 0, int dw_tap_stride = 0);
+
+// ---------------- folded image-pooling branch of the RSD decoder (k_pool.cu) ----------------
+// w_hwio: conv2d_2 kernel [9][Cs][D]; the pooled channels are rows c_first .. c_first+Cp of every tap.
+void pool_bias9(const float* pooled, int ldp, const float* w_hwio, int Cs, int c_first, int Cp, int D, int B,
+                float* bias9 /* [B][9][D] */, cudaStream_t s);
+int region_sums_chunks(int HW, int D);
+// S[b][tap][n] = sum of g over the output pixels at which `tap` reads inside the image; partial: [B][chunks][9][D]
+void region_sums(const float* g, int ldg, int B, int H, int W, int dil, int D, float* partial, float* S, cudaStream_t s);
+void pool_wgrad(const float* pooled, int ldp, const float* S, int B, int Cs, int c_first, int Cp, int D, float* dw,
+                cudaStream_t s);
+void pool_dgrad(const float* S, const float* w_hwio, int Cs, int c_first, int Cp, int D, int B, float scale,
+                float* dpooled, int ldo, cudaStream_t s);
 
 // ---------------- misc (k_misc.cu) ----------------
 struct ResizeTab { const int32_t* lo; const int32_t* hi; const float* lerp;   // [n_out]
@@ -205,6 +223,9 @@ void adam_step(float* theta, float* v, const float* g, int64_t n, int64_t n_l2, 
 void delta_accumulate(float* dsum, const float* a, const float* b, int64_t n, int first, cudaStream_t s);
 void meta_apply(float* theta, const float* dsum, float scale, int64_t n, cudaStream_t s);
 void reduce_partials(const float* partials, int G, int n, float* out, cudaStream_t s);
+// out[o * out_stride + i] = sum_g partials[g][o * n_inner + i]   (o < n_outer, i < n_inner)
+void reduce_partials_strided(const float* partials, int G, int n_inner, int n_outer, float* out, int64_t out_stride,
+                             cudaStream_t s);
 void fill_dropout_mask(float* mask, int64_t n, float rate, uint64_t seed, const uint64_t* seed_dev, cudaStream_t s);
 
 }  // namespace mliis

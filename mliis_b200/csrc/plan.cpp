@@ -286,6 +286,9 @@ void Plan::build(int image_size_, int max_batch, const int* rsd, float final_dro
     { Buf u = rp.cat; u.C = D; named.push_back({n + ".up", u}); }
     rp.pooled = b.alloc((int64_t)B * rp.catC);
     rp.dpooled = b.alloc((int64_t)B * rp.catC);
+    rp.bias9 = b.alloc((int64_t)B * 9 * D);
+    rp.S9 = b.alloc((int64_t)B * 9 * D);
+    upd(max_partials, (int64_t)B * region_sums_chunks(HW, D) * 9 * D);
     rp.tab = -1;
     if (!rp.identity_up) {
       rp.tab = (int)resize_pairs.size();
@@ -370,9 +373,9 @@ void Plan::build(int image_size_, int max_batch, const int* rsd, float final_dro
   tn_scratch = b.alloc(max_tn);
   {
     int64_t total = 0;
-    auto add = [&](int64_t w_off, int taps, int Ci, int Co, int decoder) {
+    auto add = [&](int64_t w_off, int taps, int Ci, int Co, int decoder, int Cs = 0) {
       for (int dgrad = 0; dgrad < 2; ++dgrad) {
-        prep_jobs.push_back({w_off, total, taps, Ci, Co, dgrad, decoder});
+        prep_jobs.push_back({w_off, total, taps, Ci, Co, dgrad, decoder, Cs > 0 ? Cs : Ci});
         total += ((int64_t)2 * taps * Ci * Co + 31) / 32 * 32;
       }
     };
@@ -383,7 +386,7 @@ void Plan::build(int image_size_, int max_batch, const int* rsd, float final_dro
     for (const RsdPlan& rp : rsds) {
       add(rp.w0, 1, rp.catC, D, 1);
       add(rp.w1, 9, rp.catC, D, 1);
-      add(rp.w2, 9, rp.pyrC, D, 1);
+      add(rp.w2, 9, 2 * D, D, 1, rp.pyrC);   // conv2d_2 WITHOUT the pooled channels (folded: k_pool.cu)
     }
     wcache = b.alloc(total);
     for (PrepJob& j : prep_jobs) j.dst += 0;   // offsets are relative to wcache

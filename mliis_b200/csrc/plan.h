@@ -60,6 +60,7 @@ struct RsdPlan {
   BnRef bn[3];
   Buf cat, c0, c1, pyr, c2, out;
   int64_t pooled, dpooled;   // [maxB][catC]
+  int64_t bias9, S9;         // folded pooled branch: [maxB][9][D] border-class bias / region sums of dL/d(conv2d_2)
   int tab;                   // resize table index (-1 when identity)
 };
 
@@ -92,7 +93,7 @@ struct Plan {
   int64_t g_out = 0, g_c = 0, g_c0 = 0, g_c1 = 0, g_pyr = 0, g_cat = 0, g_up = 0, g_skip = 0, g_deep = 0;
   int64_t partials = 0, partials_len = 0, wT = 0, tn_scratch = 0, dcs = 0, lr_dev = 0, loss_coef = 0;
   // tensor-core operand cache: every dense layer's forward / dgrad operand, rebuilt once per step (tc_prep_all)
-  struct PrepJob { int64_t w_off, dst; int taps, Ci, Co, dgrad, decoder; };
+  struct PrepJob { int64_t w_off, dst; int taps, Ci, Co, dgrad, decoder, Cs; };   // Cs: source channels per tap
   std::vector<PrepJob> prep_jobs;
   int64_t wcache = 0;
   int64_t ws_floats = 0;
