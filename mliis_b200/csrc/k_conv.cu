@@ -26,8 +26,10 @@ __device__ __forceinline__ void load_norm_pixel(const float* px, float& r, float
 __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__ images,
                                                         const int32_t* __restrict__ index,
                                                         const float* __restrict__ w, float* __restrict__ y, int B,
-                                                        int H, int W, int Ho, int Wo, int pad_t, int pad_l) {
+                                                        int H, int W, int Ho, int Wo, int pad_t, int pad_l,
+                                                        long long zs) {
   __shared__ __align__(16) float ws[27 * 32];
+  { const size_t zo = (size_t)blockIdx.z * zs; images += zo; index = zp(index, zo); w += zo; y += zo; }
   for (int i = threadIdx.x; i < 27 * 32; i += 256) ws[i] = w[i];
   __syncthreads();
   const int p = blockIdx.x * 64 + (threadIdx.x >> 2);
@@ -67,7 +69,8 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__
 
 void stem_fwd(const float* images, const int32_t* index, const float* w, float* y, int B, int H, int W, int Ho, int Wo,
               int pad_t, int pad_l, cudaStream_t s) {
-  MLIIS_COUNT(), stem_fwd_kernel<<<cdiv(B * Ho * Wo, 64), 256, 0, s>>>(images, index, w, y, B, H, W, Ho, Wo, pad_t, pad_l);
+  MLIIS_COUNT(), stem_fwd_kernel<<<dim3(cdiv(B * Ho * Wo, 64), 1, MLIIS_NZ), 256, 0, s>>>(images, index, w, y, B, H, W, Ho, Wo, pad_t,
+                                                                                         pad_l, MLIIS_ZS);
 }
 
 constexpr int kStemWgPix = 512;   // output pixels per CTA
@@ -77,8 +80,10 @@ int stem_wgrad_blocks(int B, int Ho, int Wo) { return cdiv(B * Ho * Wo, kStemWgP
 __global__ void __launch_bounds__(288) stem_wgrad_kernel(const float* __restrict__ images,
                                                           const int32_t* __restrict__ index,
                                                           const float* __restrict__ dy, float* __restrict__ partials,
-                                                          int B, int H, int W, int Ho, int Wo, int pad_t, int pad_l) {
+                                                          int B, int H, int W, int Ho, int Wo, int pad_t, int pad_l,
+                                                          long long zs) {
   __shared__ float xs[64][28];
+  { const size_t zo = (size_t)blockIdx.z * zs; images += zo; index = zp(index, zo); dy += zo; partials += zo; }
   __shared__ float gs[64][32];
   const int tid = threadIdx.x, co = tid & 31, kg = tid >> 5;
   const int total = B * Ho * Wo;
@@ -127,7 +132,8 @@ __global__ void __launch_bounds__(288) stem_wgrad_kernel(const float* __restrict
 void stem_wgrad(const float* images, const int32_t* index, const float* dy, float* partials, float* dw, int B, int H,
                 int W, int Ho, int Wo, int pad_t, int pad_l, cudaStream_t s) {
   int G = stem_wgrad_blocks(B, Ho, Wo);
-  MLIIS_COUNT(), stem_wgrad_kernel<<<G, 288, 0, s>>>(images, index, dy, partials, B, H, W, Ho, Wo, pad_t, pad_l);
+  MLIIS_COUNT(), stem_wgrad_kernel<<<dim3(G, 1, MLIIS_NZ), 288, 0, s>>>(images, index, dy, partials, B, H, W, Ho, Wo, pad_t, pad_l,
+                                                                       MLIIS_ZS);
   reduce_partials(partials, G, 864, dw, s);
 }
 
@@ -185,14 +191,16 @@ __global__ void __launch_bounds__(DwGeom<K, S>::NT) dw_fwd_kernel(const float* _
                                                                    const float* __restrict__ b,
                                                                    const float* __restrict__ w, float* __restrict__ y,
                                                                    int H, int W, int C, int Ho, int Wo, int pad_t,
-                                                                   int pad_l, int tiles_x) {
+                                                                   int pad_l, int tiles_x, int nB, long long zs) {
   using G = DwGeom<K, S>;
   extern __shared__ float4 smem4[];
   float4* tile = smem4;
   float4* wsm = smem4 + G::TI * G::TI * QC;
   const int tid = threadIdx.x, q = tid % QC, strip = tid / QC;
   const int ty0 = (blockIdx.x / tiles_x) * G::TO, tx0 = (blockIdx.x % tiles_x) * G::TO;
-  const int c0 = blockIdx.y * (QC * 4), img = blockIdx.z;
+  const int slot = blockIdx.z / nB;
+  const int c0 = blockIdx.y * (QC * 4), img = blockIdx.z - slot * nB;
+  { const size_t zo = (size_t)slot * zs; x += zo; a = zp(a, zo); b = zp(b, zo); w += zo; y += zo; }
   for (int i = tid; i < K * K * QC; i += G::NT) {
     const int qq = i % QC, tap = i / QC;
     const int src = FLIP ? (K * K - 1 - tap) : tap;
@@ -241,8 +249,9 @@ static void dw_fwd_launch(const float* x, const float* a, const float* b, const 
     attr_done = true;
   }
   const int tiles_x = cdiv(Wo, G::TO), tiles_y = cdiv(Ho, G::TO);
-  dim3 grid(tiles_x * tiles_y, cdiv(C, QC * 4), B);
-  MLIIS_COUNT(), dw_fwd_kernel<K, S, FLIP><<<grid, G::NT, G::smem_bytes(), s>>>(x, a, b, w, y, H, W, C, Ho, Wo, pad_t, pad_l, tiles_x);
+  dim3 grid(tiles_x * tiles_y, cdiv(C, QC * 4), B * MLIIS_NZ);
+  MLIIS_COUNT(), dw_fwd_kernel<K, S, FLIP><<<grid, G::NT, G::smem_bytes(), s>>>(x, a, b, w, y, H, W, C, Ho, Wo, pad_t, pad_l, tiles_x,
+                                                                               B, MLIIS_ZS);
 }
 
 void dw_fwd(const float* x, const float* a, const float* b, const float* w, float* y, int B, int H, int W, int C, int k,
@@ -265,14 +274,17 @@ struct DwBd2 {
 template <int K>
 __global__ void __launch_bounds__(224) dw_bwd_data_s2_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                               float* __restrict__ dx, int H, int W, int C, int Ho,
-                                                              int Wo, int pad_t, int pad_l, int tiles_x) {
+                                                              int Wo, int pad_t, int pad_l, int tiles_x, int nB,
+                                                              long long zs) {
   using G = DwBd2<K>;
   extern __shared__ float4 smem4[];
   float4* tile = smem4;
   float4* wsm = smem4 + G::TD * G::TD * QC;
   const int tid = threadIdx.x, q = tid % QC, strip = tid / QC;
   const int ty0 = (blockIdx.x / tiles_x) * G::TO, tx0 = (blockIdx.x % tiles_x) * G::TO;
-  const int c0 = blockIdx.y * (QC * 4), img = blockIdx.z;
+  const int slot = blockIdx.z / nB;
+  const int c0 = blockIdx.y * (QC * 4), img = blockIdx.z - slot * nB;
+  { const size_t zo = (size_t)slot * zs; dy += zo; w += zo; dx += zo; }
   const bool cvalid = c0 + q * 4 < C;
   for (int i = tid; i < K * K * QC; i += G::NT) {
     const int qq = i % QC, tap = i / QC;
@@ -325,8 +337,9 @@ static void dw_bwd_data_s2_launch(const float* dy, const float* w, float* dx, in
                                   int pad_t, int pad_l, cudaStream_t s) {
   using G = DwBd2<K>;
   const int tiles_x = cdiv(W, G::TO), tiles_y = cdiv(H, G::TO);
-  dim3 grid(tiles_x * tiles_y, cdiv(C, QC * 4), B);
-  MLIIS_COUNT(), dw_bwd_data_s2_kernel<K><<<grid, G::NT, G::smem_bytes(), s>>>(dy, w, dx, H, W, C, Ho, Wo, pad_t, pad_l, tiles_x);
+  dim3 grid(tiles_x * tiles_y, cdiv(C, QC * 4), B * MLIIS_NZ);
+  MLIIS_COUNT(), dw_bwd_data_s2_kernel<K><<<grid, G::NT, G::smem_bytes(), s>>>(dy, w, dx, H, W, C, Ho, Wo, pad_t, pad_l, tiles_x, B,
+                                                                              MLIIS_ZS);
 }
 
 void dw_bwd_data(const float* dy, const float* w, float* dx, int B, int H, int W, int C, int k, int stride, int Ho,
@@ -354,14 +367,16 @@ __global__ void __launch_bounds__(DwGeom<K, S>::NT) dw_wgrad_kernel(const float*
                                                                      const float* __restrict__ dy,
                                                                      float* __restrict__ partials, int H, int W, int C,
                                                                      int Ho, int Wo, int pad_t, int pad_l,
-                                                                     int tiles_x, int tiles) {
+                                                                     int tiles_x, int tiles, int nB, long long zs) {
   using G = DwGeom<K, S>;
   constexpr int NW = G::NT / 32;
   extern __shared__ float4 smem4[];
   float4* tile = smem4;
   const int tid = threadIdx.x, q = tid % QC, strip = tid / QC;
   const int ty0 = (blockIdx.x / tiles_x) * G::TO, tx0 = (blockIdx.x % tiles_x) * G::TO;
-  const int c0 = blockIdx.y * (QC * 4), img = blockIdx.z;
+  const int slot = blockIdx.z / nB;
+  const int c0 = blockIdx.y * (QC * 4), img = blockIdx.z - slot * nB;
+  { const size_t zo = (size_t)slot * zs; x += zo; a = zp(a, zo); b = zp(b, zo); dy += zo; partials += zo; }
   const bool cvalid = c0 + q * 4 < C;
   dw_stage_input<K, S>(tile, x, a, b, img, H, W, C, c0, ty0 * S - pad_t, tx0 * S - pad_l);
   __syncthreads();
@@ -429,9 +444,9 @@ static void dw_wgrad_launch(const float* x, const float* a, const float* b, cons
     attr_done = true;
   }
   const int tiles_x = cdiv(Wo, G::TO), tiles_y = cdiv(Ho, G::TO), tiles = tiles_x * tiles_y;
-  dim3 grid(tiles, cdiv(C, QC * 4), B);
+  dim3 grid(tiles, cdiv(C, QC * 4), B * MLIIS_NZ);
   MLIIS_COUNT(), dw_wgrad_kernel<K, S><<<grid, G::NT, G::wgrad_smem_bytes(), s>>>(x, a, b, dy, partials, H, W, C, Ho, Wo, pad_t, pad_l,
-                                                             tiles_x, tiles);
+                                                             tiles_x, tiles, B, MLIIS_ZS);
   reduce_partials(partials, B * tiles, K * K * C, dw, s);
 }
 

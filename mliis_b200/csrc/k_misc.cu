@@ -13,8 +13,9 @@ namespace mliis {
 // =============================================================================================
 // blockDim = (32 outputs, 8 partial lanes); coalesced over outputs, fixed-order combine over lanes.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int G, int n,
-                                                              float* __restrict__ out) {
+                                                              float* __restrict__ out, long long zs) {
   __shared__ double red[8][33];
+  { const size_t zo = (size_t)blockIdx.z * zs; partials += zo; out += zo; }
   const int i = blockIdx.x * 32 + threadIdx.x;
   double s = 0.0;
   if (i < n)
@@ -27,8 +28,9 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 }
 __global__ void __launch_bounds__(256) reduce_partials_strided_kernel(const float* __restrict__ partials, int G, int n,
                                                                       int n_inner, float* __restrict__ out,
-                                                                      int64_t out_stride) {
+                                                                      int64_t out_stride, long long zs) {
   __shared__ double red[8][33];
+  { const size_t zo = (size_t)blockIdx.z * zs; partials += zo; out += zo; }
   const int i = blockIdx.x * 32 + threadIdx.x;
   double s = 0.0;
   if (i < n)
@@ -43,17 +45,20 @@ __global__ void __launch_bounds__(256) reduce_partials_strided_kernel(const floa
 void reduce_partials_strided(const float* partials, int G, int n_inner, int n_outer, float* out, int64_t out_stride,
                              cudaStream_t s) {
   const int n = n_inner * n_outer;
-  MLIIS_COUNT(), reduce_partials_strided_kernel<<<cdiv(n, 32), dim3(32, 8), 0, s>>>(partials, G, n, n_inner, out, out_stride);
+  MLIIS_COUNT(), reduce_partials_strided_kernel<<<dim3(cdiv(n, 32), 1, MLIIS_NZ), dim3(32, 8), 0, s>>>(partials, G, n, n_inner, out,
+                                                                                                      out_stride, MLIIS_ZS);
 }
 void reduce_partials(const float* partials, int G, int n, float* out, cudaStream_t s) {
-  MLIIS_COUNT(), reduce_partials_kernel<<<cdiv(n, 32), dim3(32, 8), 0, s>>>(partials, G, n, out);
+  MLIIS_COUNT(), reduce_partials_kernel<<<dim3(cdiv(n, 32), 1, MLIIS_NZ), dim3(32, 8), 0, s>>>(partials, G, n, out, MLIIS_ZS);
 }
 
 // =============================================================================================
 // bilinear, align_corners=True.  out = top + (bottom - top) * ylerp ; top = tl + (tr - tl) * xlerp [TF-ext]
 // =============================================================================================
 __global__ void bilinear_fwd_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int B,
-                                    int Hi, int Wi, int Ho, int Wo, ResizeTab ty, ResizeTab tx, int rows_per_block) {
+                                    int Hi, int Wi, int Ho, int Wo, ResizeTab ty, ResizeTab tx, int rows_per_block,
+                                    long long zs) {
+  { const size_t zo = (size_t)blockIdx.z * zs; x += zo; y += zo; }
   const int cq = threadIdx.x;
   const int M = B * Ho * Wo;
   const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
@@ -75,7 +80,8 @@ void bilinear_fwd(const float* x, int ldx, float* y, int ldy, int B, int Hi, int
   if (R > 64) R = 64;
   dim3 blk(c4, R);
   int rpb = R * 4;
-  MLIIS_COUNT(), bilinear_fwd_kernel<<<cdiv(B * Ho * Wo, rpb), blk, 0, s>>>(x, ldx, y, ldy, B, Hi, Wi, Ho, Wo, ty, tx, rpb);
+  MLIIS_COUNT(), bilinear_fwd_kernel<<<dim3(cdiv(B * Ho * Wo, rpb), 1, MLIIS_NZ), blk, 0, s>>>(x, ldx, y, ldy, B, Hi, Wi, Ho, Wo, ty, tx,
+                                                                                              rpb, MLIIS_ZS);
 }
 
 __device__ __forceinline__ float gather_w(const ResizeTab& t, int o, int i) {
@@ -86,7 +92,9 @@ __device__ __forceinline__ float gather_w(const ResizeTab& t, int o, int i) {
 // gather form of the adjoint: dx[iy,ix] = sum_{oy,ox} wy(oy,iy) * wx(ox,ix) * dy[oy,ox]
 template <int VEC>
 __global__ void bilinear_bwd_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx, int B,
-                                    int Hi, int Wi, int Ho, int Wo, ResizeTab ty, ResizeTab tx, int rows_per_block) {
+                                    int Hi, int Wi, int Ho, int Wo, ResizeTab ty, ResizeTab tx, int rows_per_block,
+                                    long long zs) {
+  { const size_t zo = (size_t)blockIdx.z * zs; dy += zo; dx += zo; }
   const int cq = threadIdx.x;
   const int M = B * Hi * Wi;
   const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
@@ -123,14 +131,16 @@ void bilinear_bwd(const float* dy, int lddy, float* dx, int lddx, int B, int Hi,
   if (C == 2) {
     dim3 blk(1, 128);
     int rpb = 128;
-    MLIIS_COUNT(), bilinear_bwd_kernel<2><<<cdiv(B * Hi * Wi, rpb), blk, 0, s>>>(dy, lddy, dx, lddx, B, Hi, Wi, Ho, Wo, ty, tx, rpb);
+    MLIIS_COUNT(), bilinear_bwd_kernel<2><<<dim3(cdiv(B * Hi * Wi, rpb), 1, MLIIS_NZ), blk, 0, s>>>(dy, lddy, dx, lddx, B, Hi, Wi, Ho, Wo, ty,
+                                                                                                   tx, rpb, MLIIS_ZS);
   } else {
     int c4 = C / 4, R = 256 / c4;
     if (R < 1) R = 1;
     if (R > 64) R = 64;
     dim3 blk(c4, R);
     int rpb = R;
-    MLIIS_COUNT(), bilinear_bwd_kernel<4><<<cdiv(B * Hi * Wi, rpb), blk, 0, s>>>(dy, lddy, dx, lddx, B, Hi, Wi, Ho, Wo, ty, tx, rpb);
+    MLIIS_COUNT(), bilinear_bwd_kernel<4><<<dim3(cdiv(B * Hi * Wi, rpb), 1, MLIIS_NZ), blk, 0, s>>>(dy, lddy, dx, lddx, B, Hi, Wi, Ho, Wo, ty,
+                                                                                                   tx, rpb, MLIIS_ZS);
   }
 }
 
@@ -140,7 +150,8 @@ void bilinear_bwd(const float* dy, int lddy, float* dx, int lddx, int B, int Hi,
 __global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ x, int ldx,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
                                                         const float* __restrict__ mask, float keep_scale,
-                                                        float* __restrict__ z, int M, int C) {
+                                                        float* __restrict__ z, int M, int C, long long zs) {
+  { const size_t zo = (size_t)blockIdx.z * zs; x += zo; w += zo; bias += zo; mask = zp(mask, zo); z += zo; }
   const int l8 = threadIdx.x & 7;
   const int p = blockIdx.x * 32 + (threadIdx.x >> 3);
   float a0 = 0.f, a1 = 0.f;
@@ -162,15 +173,16 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__
 }
 void head_fwd(const float* x, int ldx, const float* w, const float* bias, const float* drop_mask, float keep_scale,
               float* z, int M, int C, cudaStream_t s) {
-  MLIIS_COUNT(), head_fwd_kernel<<<cdiv(M, 32), 256, 0, s>>>(x, ldx, w, bias, drop_mask, keep_scale, z, M, C);
+  MLIIS_COUNT(), head_fwd_kernel<<<dim3(cdiv(M, 32), 1, MLIIS_NZ), 256, 0, s>>>(x, ldx, w, bias, drop_mask, keep_scale, z, M, C, MLIIS_ZS);
 }
 
 // dx = (dz . w^T) * mask*scale ; dW[c][j] = sum_p xd[p,c] dz[p,j] ; db[j] = sum_p dz[p,j]
 __global__ void head_bwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
                                 const float* __restrict__ mask, float keep_scale, const float* __restrict__ dz,
                                 float* __restrict__ dx, int lddx, float* __restrict__ partials, int M, int C,
-                                int rows_per_chunk) {
+                                int rows_per_chunk, long long zs) {
   extern __shared__ float4 sm[];
+  { const size_t zo = (size_t)blockIdx.z * zs; x += zo; w += zo; mask = zp(mask, zo); dz += zo; dx += zo; partials += zo; }
   const int cq = threadIdx.x, C4 = blockDim.x, R = blockDim.y, ty = threadIdx.y;
   const float4 w0 = ld4(w + cq * 8), w1 = ld4(w + cq * 8 + 4);
   const float4 wj0 = f4(w0.x, w0.z, w1.x, w1.z), wj1 = f4(w0.y, w0.w, w1.y, w1.w);
@@ -222,12 +234,16 @@ void head_bwd(const float* x, int ldx, const float* w, const float* drop_mask, f
   if (G > 296) G = 296;
   dim3 blk(c4, R);
   size_t smem = 2 * (size_t)R * c4 * sizeof(float4) + 2 * R * sizeof(float);
-  MLIIS_COUNT(), head_bwd_kernel<<<G, blk, smem, s>>>(x, ldx, w, drop_mask, keep_scale, dz, dx, lddx, partials, M, C, cdiv(M, G));
+  MLIIS_COUNT(), head_bwd_kernel<<<dim3(G, 1, MLIIS_NZ), blk, smem, s>>>(x, ldx, w, drop_mask, keep_scale, dz, dx, lddx, partials, M, C,
+                                                                        cdiv(M, G), MLIIS_ZS);
   // partial rows are [C*2 | 2]; reduce into a staging area right after the partials, then scatter
   float* stage = partials + (size_t)G * (C * 2 + 2);
   reduce_partials(partials, G, C * 2 + 2, stage, s);
-  cudaMemcpyAsync(dw, stage, (size_t)C * 2 * sizeof(float), cudaMemcpyDeviceToDevice, s);
-  cudaMemcpyAsync(db, stage + C * 2, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  for (int z = 0; z < MLIIS_NZ; ++z) {
+    const size_t zo = (size_t)z * MLIIS_ZS;
+    cudaMemcpyAsync(dw + zo, stage + zo, (size_t)C * 2 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(db + zo, stage + zo + C * 2, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  }
 }
 
 // =============================================================================================
@@ -250,8 +266,15 @@ __device__ __forceinline__ Up2 upsample_logits(const float* __restrict__ z_lo, i
 
 constexpr int kLossChunks = 32;   // row chunks per image
 
-__global__ void __launch_bounds__(256) loss_fwd_kernel(LossArgs a) {
+__device__ __forceinline__ void loss_shift(LossArgs& a, long long zs) {
+  const size_t zo = (size_t)blockIdx.z * zs;
+  a.z_lo += zo; a.labels += zo; a.index = zp(a.index, zo); a.p1 += zo; a.partials += zo; a.coef += zo; a.dz_hi += zo;
+  a.loss_out = zp(a.loss_out, zo); a.theta = zp(a.theta, zo);
+}
+
+__global__ void __launch_bounds__(256) loss_fwd_kernel(LossArgs a, long long zs) {
   __shared__ float red[8][4];
+  loss_shift(a, zs);
   const int b = blockIdx.y, g = blockIdx.x;
   const int img = a.index ? a.index[b] : b;
   const int rows_per = (a.H + kLossChunks - 1) / kLossChunks;
@@ -286,8 +309,10 @@ __global__ void __launch_bounds__(256) loss_fwd_kernel(LossArgs a) {
   }
 }
 
-__global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out /*[gridDim.x]*/) {
+__global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out /*[gridDim.x]*/,
+                             long long zs) {
   __shared__ float red[8];
+  { const size_t zo = (size_t)blockIdx.z * zs; x += zo; out += zo; }
   float s = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     s = fmaf(x[i], x[i], s);
@@ -302,12 +327,14 @@ __global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, float* __re
 }
 
 void sumsq_partials(const float* x, int64_t n, float* out, int n_blocks, cudaStream_t s) {
-  MLIIS_COUNT(), sumsq_kernel<<<n_blocks, 256, 0, s>>>(x, n, out);
+  MLIIS_COUNT(), sumsq_kernel<<<dim3(n_blocks, 1, MLIIS_NZ), 256, 0, s>>>(x, n, out, MLIIS_ZS);
 }
 
 // single thread: per-image IoU, dice, loss value and the per-image gradient coefficients
-__global__ void loss_finalize_kernel(LossArgs a, const float* __restrict__ l2_partials, int n_l2_partials) {
+__global__ void loss_finalize_kernel(LossArgs a, const float* __restrict__ l2_partials, int n_l2_partials, long long zs) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  loss_shift(a, zs);
+  l2_partials += (size_t)blockIdx.z * zs;
   const double eps = 1e-7;
   double ce = 0.0, iou = 0.0;
   for (int b = 0; b < a.B; ++b) {
@@ -340,7 +367,8 @@ __global__ void loss_finalize_kernel(LossArgs a, const float* __restrict__ l2_pa
   }
 }
 
-__global__ void __launch_bounds__(256) loss_bwd_kernel(LossArgs a) {
+__global__ void __launch_bounds__(256) loss_bwd_kernel(LossArgs a, long long zs) {
+  loss_shift(a, zs);
   const int b = blockIdx.y;
   const int img = a.index ? a.index[b] : b;
   const float cI = a.coef[b * 2 + 0], cU = a.coef[b * 2 + 1];
@@ -361,15 +389,17 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(LossArgs a) {
 }
 
 void loss_fwd_bwd(const LossArgs& a, cudaStream_t s) {
-  MLIIS_COUNT(), loss_fwd_kernel<<<dim3(kLossChunks, a.B), 256, 0, s>>>(a);
+  const int nz = MLIIS_NZ;
+  const long long zs = MLIIS_ZS;
+  MLIIS_COUNT(), loss_fwd_kernel<<<dim3(kLossChunks, a.B, nz), 256, 0, s>>>(a, zs);
   float* l2p = a.partials + (size_t)a.B * kLossChunks * 4;
   int nl2 = 0;
   if (a.loss_out && a.l2_coef != 0.f && a.n_l2 > 0) {
     nl2 = 148;
-    MLIIS_COUNT(), sumsq_kernel<<<nl2, 256, 0, s>>>(a.theta, a.n_l2, l2p);
+    MLIIS_COUNT(), sumsq_kernel<<<dim3(nl2, 1, nz), 256, 0, s>>>(a.theta, a.n_l2, l2p, zs);
   }
-  MLIIS_COUNT(), loss_finalize_kernel<<<1, 32, 0, s>>>(a, l2p, nl2);
-  MLIIS_COUNT(), loss_bwd_kernel<<<dim3(cdiv(a.H * a.W, 256 * 4), a.B), 256, 0, s>>>(a);
+  MLIIS_COUNT(), loss_finalize_kernel<<<dim3(1, 1, nz), 32, 0, s>>>(a, l2p, nl2, zs);
+  MLIIS_COUNT(), loss_bwd_kernel<<<dim3(cdiv(a.H * a.W, 256 * 4), a.B, nz), 256, 0, s>>>(a, zs);
 }
 
 // =============================================================================================
@@ -379,8 +409,13 @@ __global__ void __launch_bounds__(256) predict_kernel(const float* __restrict__ 
                                                        const int32_t* __restrict__ index, int h, int w, int H, int W,
                                                        ResizeTab ty, ResizeTab tx, float* __restrict__ pred,
                                                        float* __restrict__ logits, uint32_t* __restrict__ inter,
-                                                       uint32_t* __restrict__ uni) {
+                                                       uint32_t* __restrict__ uni, long long zs) {
   __shared__ uint32_t red[8][2];
+  {
+    const size_t zo = (size_t)blockIdx.z * zs;
+    z_lo += zo; labels = zp(labels, zo); index = zp(index, zo); pred = zp(pred, zo); logits = zp(logits, zo);
+    inter = zp(inter, zo); uni = zp(uni, zo);
+  }
   const int b = blockIdx.y;
   const int img = index ? index[b] : b;
   const int npix = H * W;
@@ -421,30 +456,35 @@ void predict_mask_iou(const float* z_lo, const float* labels, const int32_t* ind
                       ResizeTab ty, ResizeTab tx, float* pred_out, float* logits_out, uint32_t* inter, uint32_t* uni,
                       cudaStream_t s) {
   if (inter) {
-    cudaMemsetAsync(inter, 0, B * sizeof(uint32_t), s);
-    cudaMemsetAsync(uni, 0, B * sizeof(uint32_t), s);
+    for (int z = 0; z < MLIIS_NZ; ++z) {
+      cudaMemsetAsync(inter + (size_t)z * MLIIS_ZS, 0, B * sizeof(uint32_t), s);
+      cudaMemsetAsync(uni + (size_t)z * MLIIS_ZS, 0, B * sizeof(uint32_t), s);
+    }
   }
-  MLIIS_COUNT(), predict_kernel<<<dim3(cdiv(H * W, 256 * 4), B), 256, 0, s>>>(z_lo, inter ? labels : nullptr, index, h, w, H, W, ty, tx,
-                                                              pred_out, logits_out, inter, uni);
+  MLIIS_COUNT(), predict_kernel<<<dim3(cdiv(H * W, 256 * 4), B, MLIIS_NZ), 256, 0, s>>>(z_lo, inter ? labels : nullptr, index, h, w, H, W,
+                                                                                       ty, tx, pred_out, logits_out, inter, uni,
+                                                                                       MLIIS_ZS);
 }
 
 // =============================================================================================
 // optimizer + meta-update over the flat parameter buffer
 // =============================================================================================
-__global__ void scale_kernel(float* __restrict__ x, int64_t n, float s) {
+__global__ void scale_kernel(float* __restrict__ x, int64_t n, float s, long long zs) {
+  x += (size_t)blockIdx.z * zs;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i * 4 + 3 < n) st4(x + i * 4, ld4(x + i * 4) * s);
   else for (int64_t j = i * 4; j < n; ++j) x[j] *= s;
 }
 void scale_buffer(float* x, int64_t n, float sc, cudaStream_t st) {
-  MLIIS_COUNT(), scale_kernel<<<(unsigned)cdiv64(cdiv64(n, 4), 256), 256, 0, st>>>(x, n, sc);
+  MLIIS_COUNT(), scale_kernel<<<dim3((unsigned)cdiv64(cdiv64(n, 4), 256), 1, MLIIS_NZ), 256, 0, st>>>(x, n, sc, MLIIS_ZS);
 }
 
 // TF ApplyAdam with beta1 = 0 (m == g) / ApplyGradientDescent.  g' = g + l2*theta on the first n_l2 floats
 // (gradient of 0.0005 * sum l2_loss(v), regularizers.py:4-10).  powers = {beta1_power, beta2_power}.
 __global__ void adam_kernel(float* __restrict__ theta, float* __restrict__ v, const float* __restrict__ g, int64_t n,
                             int64_t n_l2, const float* __restrict__ lr_dev, const float* __restrict__ powers,
-                            float l2_coef, int sgd) {
+                            float l2_coef, int sgd, long long zs) {
+  { const size_t zo = (size_t)blockIdx.z * zs; theta += zo; v += zo; g += zo; lr_dev += zo; powers += zo; }
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float lr = *lr_dev;
@@ -460,14 +500,16 @@ __global__ void adam_kernel(float* __restrict__ theta, float* __restrict__ v, co
     theta[i] = th - alpha * gi / (sqrtf(vi) + eps);
   }
 }
-__global__ void adam_finish_kernel(float* powers) {
+__global__ void adam_finish_kernel(float* powers, long long zs) {
+  powers += (size_t)blockIdx.z * zs;
   powers[0] *= 0.0f;      // beta1 = 0
   powers[1] *= 0.999f;
 }
 void adam_step(float* theta, float* v, const float* g, int64_t n, int64_t n_l2, const float* lr_dev, float* powers,
                float l2_coef, int sgd, cudaStream_t s) {
-  MLIIS_COUNT(), adam_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(theta, v, g, n, n_l2, lr_dev, powers, l2_coef, sgd);
-  if (!sgd) MLIIS_COUNT(), adam_finish_kernel<<<1, 1, 0, s>>>(powers);
+  MLIIS_COUNT(), adam_kernel<<<dim3((unsigned)cdiv64(n, 256), 1, MLIIS_NZ), 256, 0, s>>>(theta, v, g, n, n_l2, lr_dev, powers, l2_coef, sgd,
+                                                                                        MLIIS_ZS);
+  if (!sgd) MLIIS_COUNT(), adam_finish_kernel<<<dim3(1, 1, MLIIS_NZ), 1, 0, s>>>(powers, MLIIS_ZS);
 }
 
 __global__ void delta_acc_kernel(float* __restrict__ d, const float* __restrict__ a, const float* __restrict__ b,
@@ -492,7 +534,9 @@ void meta_apply(float* theta, const float* dsum, float scale, int64_t n, cudaStr
 // stream is unseeded, so any uniform stream is a valid draw; tests inject masks instead).
 // seed_dev: optional device scalar added to the host seed at run time (CUDA-graph replays draw fresh masks).
 __global__ void dropout_mask_kernel(float* __restrict__ mask, int64_t n, float rate, uint64_t seed,
-                                    const uint64_t* __restrict__ seed_dev) {
+                                    const uint64_t* __restrict__ seed_dev, long long zs) {
+  mask += (size_t)blockIdx.z * zs;
+  if (seed_dev) seed_dev += ((size_t)blockIdx.z * zs) / 2;       // zs is in floats; the seed is a 64-bit scalar
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (seed_dev) seed += *seed_dev * 0xD1B54A32D192ED03ull;
@@ -504,7 +548,7 @@ __global__ void dropout_mask_kernel(float* __restrict__ mask, int64_t n, float r
   mask[i] = u >= rate ? 1.f : 0.f;
 }
 void fill_dropout_mask(float* mask, int64_t n, float rate, uint64_t seed, const uint64_t* seed_dev, cudaStream_t s) {
-  MLIIS_COUNT(), dropout_mask_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, s>>>(mask, n, rate, seed, seed_dev);
+  MLIIS_COUNT(), dropout_mask_kernel<<<dim3((unsigned)cdiv64(n, 256), 1, MLIIS_NZ), 256, 0, s>>>(mask, n, rate, seed, seed_dev, MLIIS_ZS);
 }
 
 }  // namespace mliis

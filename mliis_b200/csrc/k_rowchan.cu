@@ -65,8 +65,9 @@ __device__ __forceinline__ void block_reduce1(float4& s0, float4* sm) {
 // ------------------------------------------------------------------------------------------------
 template <bool PRE_SWISH>
 __global__ void bn_stats_kernel(const float* __restrict__ x, int ld, int M, int C, int rows_per_chunk,
-                                float* __restrict__ partials) {
+                                float* __restrict__ partials, long long zs) {
   extern __shared__ float4 sm[];
+  { const size_t zo = (size_t)blockIdx.z * zs; x += zo; partials += zo; }
   const int cq = threadIdx.x;
   const int r0 = blockIdx.x * rows_per_chunk;
   const int r1 = min(M, r0 + rows_per_chunk);
@@ -101,9 +102,9 @@ void bn_stats(const float* x, int ld, int M, int C, bool pre_swish, float* parti
   dim3 blk = rc_block(C);
   size_t smem = 2 * blk.x * blk.y * sizeof(float4);
   if (pre_swish)
-    MLIIS_COUNT(), bn_stats_kernel<true><<<G, blk, smem, s>>>(x, ld, M, C, rpc, partials);
+    MLIIS_COUNT(), bn_stats_kernel<true><<<dim3(G, 1, MLIIS_NZ), blk, smem, s>>>(x, ld, M, C, rpc, partials, MLIIS_ZS);
   else
-    MLIIS_COUNT(), bn_stats_kernel<false><<<G, blk, smem, s>>>(x, ld, M, C, rpc, partials);
+    MLIIS_COUNT(), bn_stats_kernel<false><<<dim3(G, 1, MLIIS_NZ), blk, smem, s>>>(x, ld, M, C, rpc, partials, MLIIS_ZS);
 }
 
 // blockDim = (32 channels, 16 partial lanes): each thread sums every 16th partial in double, then the 16
@@ -112,8 +113,12 @@ __global__ void __launch_bounds__(512) bn_finalize_kernel(const float* __restric
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ mm, float* __restrict__ mv, int ema, int bessel,
                                    float* __restrict__ mean_o, float* __restrict__ rstd_o, float* __restrict__ a_o,
-                                   float* __restrict__ b_o) {
+                                   float* __restrict__ b_o, long long zs) {
   __shared__ double red[2][16][33];
+  {
+    const size_t zo = (size_t)blockIdx.z * zs;
+    partials += zo; gamma += zo; beta += zo; mm += zo; mv += zo; mean_o += zo; rstd_o += zo; a_o += zo; b_o += zo;
+  }
   const int c = blockIdx.x * 32 + threadIdx.x;
   double s = 0.0, ss = 0.0;
   if (c < C) {
@@ -147,14 +152,15 @@ __global__ void __launch_bounds__(512) bn_finalize_kernel(const float* __restric
 
 void bn_finalize(const float* partials, int G, int C, int M, const float* gamma, const float* beta, float* mm,
                  float* mv, int ema, int bessel, float* mean, float* rstd, float* a, float* b, cudaStream_t s) {
-  MLIIS_COUNT(), bn_finalize_kernel<<<cdiv(C, 32), dim3(32, 16), 0, s>>>(partials, G, C, M, gamma, beta, mm, mv, ema,
-                                                                        bessel, mean, rstd, a, b);
+  MLIIS_COUNT(), bn_finalize_kernel<<<dim3(cdiv(C, 32), 1, MLIIS_NZ), dim3(32, 16), 0, s>>>(partials, G, C, M, gamma, beta, mm, mv,
+                                                                                            ema, bessel, mean, rstd, a, b, MLIIS_ZS);
 }
 
 __global__ void bn_eval_coeffs_kernel(const float* __restrict__ theta, const int32_t* __restrict__ gi,
                                       const int32_t* __restrict__ bi, const float* __restrict__ mm,
                                       const float* __restrict__ mv, int n, float* __restrict__ a,
-                                      float* __restrict__ b) {
+                                      float* __restrict__ b, long long zs) {
+  { const size_t zo = (size_t)blockIdx.z * zs; theta += zo; mm += zo; mv += zo; a += zo; b += zo; }
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
   float inv = rsqrtf(mv[c] + kBnEps) * theta[gi[c]];
@@ -163,7 +169,7 @@ __global__ void bn_eval_coeffs_kernel(const float* __restrict__ theta, const int
 }
 void bn_eval_coeffs(const float* theta, const int32_t* gi, const int32_t* bi, const float* mm, const float* mv,
                     int n, float* a, float* b, cudaStream_t s) {
-  MLIIS_COUNT(), bn_eval_coeffs_kernel<<<cdiv(n, 256), 256, 0, s>>>(theta, gi, bi, mm, mv, n, a, b);
+  MLIIS_COUNT(), bn_eval_coeffs_kernel<<<dim3(cdiv(n, 256), 1, MLIIS_NZ), 256, 0, s>>>(theta, gi, bi, mm, mv, n, a, b, MLIIS_ZS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -171,7 +177,8 @@ void bn_eval_coeffs(const float* theta, const int32_t* gi, const int32_t* bi, co
 // ------------------------------------------------------------------------------------------------
 __global__ void dec_bn_apply_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ a,
                                     const float* __restrict__ b, const float* __restrict__ res, int ldres,
-                                    float* __restrict__ y, int ldy, int M, int rows_per_block) {
+                                    float* __restrict__ y, int ldy, int M, int rows_per_block, long long zs) {
+  { const size_t zo = (size_t)blockIdx.z * zs; x += zo; a += zo; b += zo; res = zp(res, zo); y += zo; }
   const int cq = threadIdx.x;
   const float4 av = ld4(a + cq * 4), bv = ld4(b + cq * 4);
   const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
@@ -185,13 +192,14 @@ void dec_bn_apply(const float* x, int ldx, const float* a, const float* b, const
                   int ldy, int M, int C, cudaStream_t s) {
   dim3 blk = rc_block(C);
   int rpb = blk.y * 4;
-  MLIIS_COUNT(), dec_bn_apply_kernel<<<cdiv(M, rpb), blk, 0, s>>>(x, ldx, a, b, res, ldres, y, ldy, M, rpb);
+  MLIIS_COUNT(), dec_bn_apply_kernel<<<dim3(cdiv(M, rpb), 1, MLIIS_NZ), blk, 0, s>>>(x, ldx, a, b, res, ldres, y, ldy, M, rpb, MLIIS_ZS);
 }
 
 __global__ void block_out_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ a,
                                  const float* __restrict__ b, const float* __restrict__ dcs,
                                  const float* __restrict__ res, int ldres, float* __restrict__ y, int ldy, int M,
-                                 int HW, int rows_per_block) {
+                                 int HW, int rows_per_block, long long zs) {
+  { const size_t zo = (size_t)blockIdx.z * zs; x += zo; a += zo; b += zo; dcs = zp(dcs, zo); res = zp(res, zo); y += zo; }
   const int cq = threadIdx.x;
   const float4 av = ld4(a + cq * 4), bv = ld4(b + cq * 4);
   const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
@@ -206,7 +214,8 @@ void block_out(const float* x, int ldx, const float* a, const float* b, const fl
                int ldres, float* y, int ldy, int M, int C, int HW, cudaStream_t s) {
   dim3 blk = rc_block(C);
   int rpb = blk.y * 4;
-  MLIIS_COUNT(), block_out_kernel<<<cdiv(M, rpb), blk, 0, s>>>(x, ldx, a, b, dcs, res, ldres, y, ldy, M, HW, rpb);
+  MLIIS_COUNT(), block_out_kernel<<<dim3(cdiv(M, rpb), 1, MLIIS_NZ), blk, 0, s>>>(x, ldx, a, b, dcs, res, ldres, y, ldy, M, HW, rpb,
+                                                                                 MLIIS_ZS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -218,8 +227,9 @@ void block_out(const float* x, int ldx, const float* a, const float* b, const fl
 template <int MODE>
 __global__ void img_reduce_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ g, int ldg,
                                   const float* __restrict__ a, const float* __restrict__ b, int HW, int C,
-                                  int rows_per_chunk, float* __restrict__ partial) {
+                                  int rows_per_chunk, float* __restrict__ partial, long long zs) {
   extern __shared__ float4 sm[];
+  { const size_t zo = (size_t)blockIdx.z * zs; x += zo; g = zp(g, zo); a = zp(a, zo); b = zp(b, zo); partial += zo; }
   const int cq = threadIdx.x, img = blockIdx.y, G = gridDim.x;
   float4 av = f4s(1.f), bv = f4s(0.f);
   if (MODE != 2) { av = ld4(a + cq * 4); bv = ld4(b + cq * 4); }
@@ -255,19 +265,20 @@ void se_pool(const float* x, int ldx, const float* a, const float* b, int B, int
              cudaStream_t s) {
   int G = rc_num_img_chunks(HW, C);
   dim3 blk = rc_block(C);
-  MLIIS_COUNT(), img_reduce_kernel<0><<<dim3(G, B), blk, blk.x * blk.y * sizeof(float4), s>>>(x, ldx, nullptr, 0, a, b, HW, C,
-                                                                               cdiv(HW, G), partial);
+  MLIIS_COUNT(), img_reduce_kernel<0><<<dim3(G, B, MLIIS_NZ), blk, blk.x * blk.y * sizeof(float4), s>>>(x, ldx, nullptr, 0, a, b, HW, C,
+                                                                               cdiv(HW, G), partial, MLIIS_ZS);
 }
 void se_bwd_reduce(const float* x, int ldx, const float* gup, int ldg, const float* a, const float* b, int B, int HW,
                    int C, float* partial, cudaStream_t s) {
   int G = rc_num_img_chunks(HW, C);
   dim3 blk = rc_block(C);
-  MLIIS_COUNT(), img_reduce_kernel<1><<<dim3(G, B), blk, blk.x * blk.y * sizeof(float4), s>>>(x, ldx, gup, ldg, a, b, HW, C,
-                                                                               cdiv(HW, G), partial);
+  MLIIS_COUNT(), img_reduce_kernel<1><<<dim3(G, B, MLIIS_NZ), blk, blk.x * blk.y * sizeof(float4), s>>>(x, ldx, gup, ldg, a, b, HW, C,
+                                                                               cdiv(HW, G), partial, MLIIS_ZS);
 }
 
 __global__ void img_colsum_finalize_kernel(const float* __restrict__ partial, int G, int C, float scale,
-                                           float* __restrict__ out, int ldo) {
+                                           float* __restrict__ out, int ldo, long long zs) {
+  { const size_t zo = (size_t)blockIdx.z * zs; partial += zo; out += zo; }
   int c = blockIdx.x * blockDim.x + threadIdx.x, img = blockIdx.y;
   if (c >= C) return;
   double s = 0.0;
@@ -278,9 +289,9 @@ void img_colsum(const float* x, int ldx, int B, int HW, int C, float scale, floa
                 cudaStream_t s) {
   int G = rc_num_img_chunks(HW, C);
   dim3 blk = rc_block(C);
-  MLIIS_COUNT(), img_reduce_kernel<2><<<dim3(G, B), blk, blk.x * blk.y * sizeof(float4), s>>>(x, ldx, nullptr, 0, nullptr, nullptr,
-                                                                               HW, C, cdiv(HW, G), partial);
-  MLIIS_COUNT(), img_colsum_finalize_kernel<<<dim3(cdiv(C, 128), B), 128, 0, s>>>(partial, G, C, scale, out, ldo);
+  MLIIS_COUNT(), img_reduce_kernel<2><<<dim3(G, B, MLIIS_NZ), blk, blk.x * blk.y * sizeof(float4), s>>>(x, ldx, nullptr, 0, nullptr, nullptr,
+                                                                               HW, C, cdiv(HW, G), partial, MLIIS_ZS);
+  MLIIS_COUNT(), img_colsum_finalize_kernel<<<dim3(cdiv(C, 128), B, MLIIS_NZ), 128, 0, s>>>(partial, G, C, scale, out, ldo, MLIIS_ZS);
 }
 
 // One block per image.  pool -> reduce FC (+bias, swish) -> expand FC (+bias) -> sigmoid.
@@ -288,8 +299,12 @@ __global__ void se_fc_fwd_kernel(const float* __restrict__ partial, int G, int H
                                  const float* __restrict__ w1, const float* __restrict__ b1,
                                  const float* __restrict__ w2, const float* __restrict__ b2,
                                  float* __restrict__ pool_o, float* __restrict__ hidpre_o,
-                                 float* __restrict__ gate_o) {
+                                 float* __restrict__ gate_o, long long zs) {
   extern __shared__ float smf[];
+  {
+    const size_t zo = (size_t)blockIdx.z * zs;
+    partial += zo; w1 += zo; b1 += zo; w2 += zo; b2 += zo; pool_o += zo; hidpre_o += zo; gate_o += zo;
+  }
   float* pool = smf;          // [C]
   float* hid = smf + C;       // [Cr]
   const int img = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
@@ -322,8 +337,8 @@ __global__ void se_fc_fwd_kernel(const float* __restrict__ partial, int G, int H
 }
 void se_fc_fwd(const float* partial, int G, int B, int HW, int C, int Cr, const float* w1, const float* b1,
                const float* w2, const float* b2, float* pool, float* hidpre, float* gate, cudaStream_t s) {
-  MLIIS_COUNT(), se_fc_fwd_kernel<<<B, 256, (C + Cr) * sizeof(float), s>>>(partial, G, HW, C, Cr, w1, b1, w2, b2, pool, hidpre,
-                                                            gate);
+  MLIIS_COUNT(), se_fc_fwd_kernel<<<dim3(B, 1, MLIIS_NZ), 256, (C + Cr) * sizeof(float), s>>>(partial, G, HW, C, Cr, w1, b1, w2, b2, pool,
+                                                                                hidpre, gate, MLIIS_ZS);
 }
 
 // SE FC backward, phase A (one block per image): d(gate pre-act), d(hidden pre-act), d(pool).
@@ -332,8 +347,13 @@ __global__ void __launch_bounds__(256) se_fc_bwd_img_kernel(const float* __restr
                                                              const float* __restrict__ w2,
                                                              const float* __restrict__ hidpre,
                                                              const float* __restrict__ gate, float* __restrict__ dgp_o,
-                                                             float* __restrict__ dhp_o, float* __restrict__ dpool) {
+                                                             float* __restrict__ dhp_o, float* __restrict__ dpool,
+                                                             long long zs) {
   extern __shared__ float smf[];
+  {
+    const size_t zo = (size_t)blockIdx.z * zs;
+    partial += zo; w1 += zo; w2 += zo; hidpre += zo; gate += zo; dgp_o += zo; dhp_o += zo; dpool += zo;
+  }
   float* dgp = smf;        // [C]
   float* dhp = smf + C;    // [Cr]
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
@@ -370,7 +390,12 @@ __global__ void __launch_bounds__(128) se_fc_bwd_w_kernel(int B, int C, int Cr, 
                                                            const float* __restrict__ hidpre,
                                                            const float* __restrict__ dgp, const float* __restrict__ dhp,
                                                            float* __restrict__ dw1, float* __restrict__ db1,
-                                                           float* __restrict__ dw2, float* __restrict__ db2) {
+                                                           float* __restrict__ dw2, float* __restrict__ db2,
+                                                           long long zs) {
+  {
+    const size_t zo = (size_t)blockIdx.z * zs;
+    pool += zo; hidpre += zo; dgp += zo; dhp += zo; dw1 += zo; db1 += zo; dw2 += zo; db2 += zo;
+  }
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     float sb = 0.f;
@@ -398,9 +423,10 @@ void se_fc_bwd(const float* partial, int G, int B, int HW, int C, int Cr, const 
   // scratch for dgp [B][C] and dhp [B][Cr] lives right after the dgate partials
   float* dgp = const_cast<float*>(partial) + (size_t)B * G * C;
   float* dhp = dgp + (size_t)B * C;
-  MLIIS_COUNT(), se_fc_bwd_img_kernel<<<B, 256, (C + Cr) * sizeof(float), s>>>(partial, G, HW, C, Cr, w1, w2, hidpre, gate, dgp,
-                                                                              dhp, dpool);
-  MLIIS_COUNT(), se_fc_bwd_w_kernel<<<cdiv(C, 128), 128, 0, s>>>(B, C, Cr, pool, hidpre, dgp, dhp, dw1, db1, dw2, db2);
+  MLIIS_COUNT(), se_fc_bwd_img_kernel<<<dim3(B, 1, MLIIS_NZ), 256, (C + Cr) * sizeof(float), s>>>(partial, G, HW, C, Cr, w1, w2, hidpre,
+                                                                                    gate, dgp, dhp, dpool, MLIIS_ZS);
+  MLIIS_COUNT(), se_fc_bwd_w_kernel<<<dim3(cdiv(C, 128), 1, MLIIS_NZ), 128, 0, s>>>(B, C, Cr, pool, hidpre, dgp, dhp, dw1, db1, dw2, db2,
+                                                                                   MLIIS_ZS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -430,9 +456,17 @@ __device__ __forceinline__ void bn_bwd_elem(const BnBwdArgs& p, size_t r, int cq
   }
 }
 
+__device__ __forceinline__ void bn_bwd_shift(BnBwdArgs& p, long long zs) {
+  const size_t zo = (size_t)blockIdx.z * zs;
+  p.x += zo; p.g += zo; p.dx += zo; p.mean += zo; p.rstd += zo; p.a += zo; p.b += zo; p.gamma += zo;
+  p.dcs = zp(p.dcs, zo); p.gate = zp(p.gate, zo); p.dpool = zp(p.dpool, zo);
+  p.partials += zo; p.k += zo; p.dgamma += zo; p.dbeta += zo;
+}
+
 template <int VAR>
-__global__ void bn_bwd_reduce_kernel(BnBwdArgs p, int rows_per_chunk) {
+__global__ void bn_bwd_reduce_kernel(BnBwdArgs p, int rows_per_chunk, long long zs) {
   extern __shared__ float4 sm[];
+  bn_bwd_shift(p, zs);
   const int cq = threadIdx.x;
   const float4 mean = ld4(p.mean + cq * 4), rstd = ld4(p.rstd + cq * 4);
   const float4 av = ld4(p.a + cq * 4), bv = ld4(p.b + cq * 4);
@@ -466,8 +500,9 @@ __global__ void bn_bwd_reduce_kernel(BnBwdArgs p, int rows_per_chunk) {
 
 __global__ void __launch_bounds__(512) bn_bwd_finalize_kernel(const float* __restrict__ partials, int G, int C, int M,
                                        float* __restrict__ k, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta) {
+                                       float* __restrict__ dbeta, long long zs) {
   __shared__ double red[2][16][33];
+  { const size_t zo = (size_t)blockIdx.z * zs; partials += zo; k += zo; dgamma += zo; dbeta += zo; }
   const int c = blockIdx.x * 32 + threadIdx.x;
   double s0 = 0.0, s1 = 0.0;
   if (c < C) {
@@ -488,7 +523,8 @@ __global__ void __launch_bounds__(512) bn_bwd_finalize_kernel(const float* __res
 }
 
 template <int VAR>
-__global__ void bn_bwd_apply_kernel(BnBwdArgs p, int rows_per_block) {
+__global__ void bn_bwd_apply_kernel(BnBwdArgs p, int rows_per_block, long long zs) {
+  bn_bwd_shift(p, zs);
   const int cq = threadIdx.x;
   const float4 mean = ld4(p.mean + cq * 4), rstd = ld4(p.rstd + cq * 4);
   const float4 av = ld4(p.a + cq * 4), bv = ld4(p.b + cq * 4);
@@ -521,10 +557,13 @@ template <int VAR>
 static void bn_bwd_t(const BnBwdArgs& p, cudaStream_t s) {
   int G = rc_num_chunks(p.M, p.C);
   dim3 blk = rc_block(p.C);
-  MLIIS_COUNT(), bn_bwd_reduce_kernel<VAR><<<G, blk, 2 * blk.x * blk.y * sizeof(float4), s>>>(p, cdiv(p.M, G));
-  MLIIS_COUNT(), bn_bwd_finalize_kernel<<<cdiv(p.C, 32), dim3(32, 16), 0, s>>>(p.partials, G, p.C, p.M, p.k, p.dgamma, p.dbeta);
+  const int nz = MLIIS_NZ;
+  const long long zs = MLIIS_ZS;
+  MLIIS_COUNT(), bn_bwd_reduce_kernel<VAR><<<dim3(G, 1, nz), blk, 2 * blk.x * blk.y * sizeof(float4), s>>>(p, cdiv(p.M, G), zs);
+  MLIIS_COUNT(), bn_bwd_finalize_kernel<<<dim3(cdiv(p.C, 32), 1, nz), dim3(32, 16), 0, s>>>(p.partials, G, p.C, p.M, p.k, p.dgamma,
+                                                                                           p.dbeta, zs);
   int rpb = blk.y * 4;
-  MLIIS_COUNT(), bn_bwd_apply_kernel<VAR><<<cdiv(p.M, rpb), blk, 0, s>>>(p, rpb);
+  MLIIS_COUNT(), bn_bwd_apply_kernel<VAR><<<dim3(cdiv(p.M, rpb), 1, nz), blk, 0, s>>>(p, rpb, zs);
 }
 void bn_bwd(int var, const BnBwdArgs& p, cudaStream_t s) {
   switch (var) {
@@ -539,7 +578,8 @@ void bn_bwd(int var, const BnBwdArgs& p, cudaStream_t s) {
 // concat / broadcast plumbing
 // ------------------------------------------------------------------------------------------------
 __global__ void bcast_rows_kernel(const float* __restrict__ pimg, int ldp, float* __restrict__ y, int ldy, int M,
-                                  int HW, int rows_per_block) {
+                                  int HW, int rows_per_block, long long zs) {
+  { const size_t zo = (size_t)blockIdx.z * zs; pimg += zo; y += zo; }
   const int cq = threadIdx.x;
   const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
   for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y)
@@ -548,12 +588,13 @@ __global__ void bcast_rows_kernel(const float* __restrict__ pimg, int ldp, float
 void bcast_rows(const float* pimg, int ldp, float* y, int ldy, int B, int HW, int C, cudaStream_t s) {
   dim3 blk = rc_block(C);
   int rpb = blk.y * 4, M = B * HW;
-  MLIIS_COUNT(), bcast_rows_kernel<<<cdiv(M, rpb), blk, 0, s>>>(pimg, ldp, y, ldy, M, HW, rpb);
+  MLIIS_COUNT(), bcast_rows_kernel<<<dim3(cdiv(M, rpb), 1, MLIIS_NZ), blk, 0, s>>>(pimg, ldp, y, ldy, M, HW, rpb, MLIIS_ZS);
 }
 
 __global__ void add3_kernel(float* __restrict__ dst, int ldd, const float* __restrict__ a, int lda,
                             const float* __restrict__ b, int ldb, const float* __restrict__ pimg, int ldp, int M,
-                            int HW, int rows_per_block) {
+                            int HW, int rows_per_block, long long zs) {
+  { const size_t zo = (size_t)blockIdx.z * zs; dst += zo; a += zo; b = zp(b, zo); pimg = zp(pimg, zo); }
   const int cq = threadIdx.x;
   const int r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
   for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
@@ -567,7 +608,7 @@ void add3(float* dst, int ldd, const float* a, int lda, const float* b, int ldb,
           int C, int HW, cudaStream_t s) {
   dim3 blk = rc_block(C);
   int rpb = blk.y * 4;
-  MLIIS_COUNT(), add3_kernel<<<cdiv(M, rpb), blk, 0, s>>>(dst, ldd, a, lda, b, ldb, pimg, ldp, M, HW, rpb);
+  MLIIS_COUNT(), add3_kernel<<<dim3(cdiv(M, rpb), 1, MLIIS_NZ), blk, 0, s>>>(dst, ldd, a, lda, b, ldb, pimg, ldp, M, HW, rpb, MLIIS_ZS);
 }
 
 }  // namespace mliis

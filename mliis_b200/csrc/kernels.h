@@ -18,6 +18,18 @@ bool skip_launch(const char* launcher);
 #define MLIIS_COUNT() \
   for (bool mliis_go_ = !::mliis::skip_launch(__func__); mliis_go_; mliis_go_ = false) ++::mliis::g_kernel_launches
 
+// Task-batched launches (common.cuh): the engine sets the group for the calling thread; every launcher multiplies
+// grid.z by nz and passes zs (floats between consecutive slots) to its kernel.  Default {1, 0} = one slot.
+struct ZGroup { int nz; long long zs; };
+ZGroup& zgroup();
+struct ZScope {
+  ZGroup saved;
+  ZScope(int nz, long long zs) : saved(zgroup()) { zgroup() = ZGroup{nz, zs}; }
+  ~ZScope() { zgroup() = saved; }
+};
+#define MLIIS_NZ (::mliis::zgroup().nz)
+#define MLIIS_ZS (::mliis::zgroup().zs)
+
 // ---------------- row-channel kernels (k_rowchan.cu) : HBM-bound ----------------
 enum BnVar { BN_PLAIN = 0, BN_SWISH = 1, BN_SWISH_SE = 2, BN_DEC = 3 };
 
