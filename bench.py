@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tasks-per-step", type=int, default=24)
     ap.add_argument("--slots", type=int, default=12)
+    ap.add_argument("--group", type=int, default=1, help="task slots per task-batched launch (must divide --slots)")
     ap.add_argument("--gemm-mode", default="auto", choices=["auto", "fp32", "tf32", "tf32x3"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -284,7 +285,7 @@ def run_b200(args):
     init_state = eng.states[0].clone()
     # the checkpoint keeps its optimizer slots: Gecko._full_state covers every global variable (reptile.py:35-36)
 
-    runner = TaskRunner(eng, POOL, INNER_STEPS, INNER_BATCH, N_QUERY, use_graph=not args.no_graph)
+    runner = TaskRunner(eng, POOL, INNER_STEPS, INNER_BATCH, N_QUERY, use_graph=not args.no_graph, group=args.group)
     runner.set_init_state(init_state)
 
     random.seed(0)
@@ -307,13 +308,13 @@ def run_b200(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         cur = torch.cuda.current_stream()
         e0.record(cur)
-        for sb in runner.slots:
-            sb.stream.wait_event(e0)
+        for g in runner.groups:
+            g.stream.wait_event(e0)
         res = None
         for _ in range(steps):
             res = runner.run(plans)
-        for sb in runner.slots:
-            cur.wait_stream(sb.stream)
+        for g in runner.groups:
+            cur.wait_stream(g.stream)
         e1.record(cur)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -369,7 +370,7 @@ def run_b200(args):
         "config": {"workload": "meta-test sweep, 5-shot 224x224 synthetic FSS-1000-shaped tasks: per task state reset, "
                                "5 inner %s steps (batch 8), transductive predict of 5 query images, IoU counts"
                                % ("SGD" if args.sgd else "Adam"),
-                   "tasks_per_step_per_gpu": tps, "slots": args.slots, "cuda_graph": not args.no_graph,
+                   "tasks_per_step_per_gpu": tps, "slots": args.slots, "group": args.group, "cuda_graph": not args.no_graph,
                    "l2": "inputs larger than L2 (%d MB of task pools + %.0f MB workspace per slot)"
                          % (tps * 10, eng.ctx.workspace_bytes / 2 ** 20),
                    "parallelism": "task-parallel x%d, no data-path collective" % world},

@@ -208,6 +208,14 @@ typedef struct mliis_task_args {
   float*         dev_loss_out;     /* [n_steps] or NULL                                      */
   const uint64_t* dev_seed;        /* optional device scalar: step t draws its final-layer dropout mask from
                                       *dev_seed + seed + t, read at RUN time (graph replays see the staged value) */
+  /* Task-batched execution: n_group consecutive slots (slot, slot+1, ...) adapt their
+   * tasks in LOCKSTEP - every kernel of the step is launched once with the task slot as a grid dimension, so the
+   * 14x14 / 28x28 layers of n_group tasks fill the SMs together.  0 or 1 = a single slot.  All per-slot memory must
+   * share one layout at a uniform stride: the state and workspace buffers bound to slot k (mliis_slot_bind) and
+   * every dev_* pointer of this struct except dev_init_state are the FIRST slot's; slot k uses
+   * pointer + k * group_stride_bytes (a multiple of 256).  Results are bit-identical to n_group single-slot calls. */
+  int32_t        n_group;
+  int64_t        group_stride_bytes;
 } mliis_task_args;
 int mliis_adapt_eval_task(mliis_ctx* ctx, int32_t slot, const mliis_task_args* args, void* stream);
 

@@ -22,6 +22,10 @@ using namespace mliis;
 
 namespace mliis {
 unsigned long long g_kernel_launches = 0;
+ZGroup& zgroup() {
+  thread_local ZGroup g{1, 0};
+  return g;
+}
 bool skip_launch(const char* launcher) {
   static const char* env = getenv("MLIIS_SKIP");
   if (!env || !*env) return false;
@@ -78,6 +82,7 @@ struct Tab {
 }  // namespace
 
 struct mliis_ctx {
+  bool group_fallback = false;   // a task-batched call reached a kernel that only serves one slot (fp32 FFMA GEMMs)
   mliis_config cfg;
   Plan plan;
   int device = -1;
@@ -136,7 +141,8 @@ int check_cuda(const char* where) {
 }
 
 __global__ void dcs_kernel(const float* __restrict__ mask, float* __restrict__ dcs, int n_dc, int B, int maxB,
-                           float k0, float k1, float k2, float k3, float k4, float k5, float k6, float k7) {
+                           float k0, float k1, float k2, float k3, float k4, float k5, float k6, float k7, long long zs) {
+  { const size_t zo = (size_t)blockIdx.z * zs; mask = zp(mask, zo); dcs += zo; }
   const float keep[8] = {k0, k1, k2, k3, k4, k5, k6, k7};
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_dc * B) return;
@@ -145,7 +151,7 @@ __global__ void dcs_kernel(const float* __restrict__ mask, float* __restrict__ d
   dcs[d * maxB + b] = (mask ? mask[i] : 1.f) / keep[d];
 }
 
-__global__ void set_scalar_kernel(float* p, float v) { *p = v; }
+__global__ void set_scalar_kernel(float* p, float v, long long zs) { p[(size_t)blockIdx.z * zs] = v; }
 
 struct Run {
   mliis_ctx* c;
@@ -238,6 +244,7 @@ struct Dense {
       float* wt = operand(w_hwio, taps, Cin, Cout, 0);
       if (tc_conv(A, lda, wt, bias, out, ldc, conv, M, r.B, H, W, Cin, taps, dil, Cout, 0, split(), r.st)) return;
     }
+    if (MLIIS_NZ > 1) r.c->group_fallback = true;
     GemmA a = conv ? convA(A, lda, H, W, Cin, dil) : plainA(A, lda);
     gemm_nn(a, w_hwio, bias, out, ldc, M, taps * Cin, Cout, HW, 0, r.st);
   }
@@ -249,6 +256,7 @@ struct Dense {
       if (tc_conv(A, lda, wt, nullptr, out, ldc, 0, M, r.B, 1, 1, Cin, 1, 1, Cout, 0, split(), r.st, pa, pb, gate, HW))
         return;
     }
+    if (MLIIS_NZ > 1) r.c->group_fallback = true;
     GemmA a = plainA(A, lda);
     a.pa = pa; a.pb = pb; a.gate = gate;
     gemm_nn(a, w_hwio, nullptr, out, ldc, M, Cin, Cout, HW, 0, r.st);
@@ -273,6 +281,7 @@ struct Dense {
       if (done && dbias) img_colsum(G, ldg, 1, M, Cout, 1.f, r.W(r.p.partials), dbias, Cout, r.st);
     }
     if (!done) {
+      if (MLIIS_NZ > 1) r.c->group_fallback = true;
       GemmA a = conv ? convA(A, lda, H, W, Cin, dil) : plainA(A, lda);
       a.pa = pa; a.pb = pb; a.gate = gate;
       gemm_tn(a, G, ldg, dW, dbias, scratch, M, taps * Cin, Cout, HW, r.st);
@@ -287,6 +296,7 @@ struct Dense {
       float* wtc = operand(w_hwio, taps, Cin, Cout, 1, Cs);
       if (tc_conv(G, ldg, wtc, nullptr, dA, ldd, conv, M, r.B, H, W, Cout, taps, dil, Cin, accumulate, split(), r.st)) return;
     }
+    if (MLIIS_NZ > 1) r.c->group_fallback = true;
     if (conv) {
       flip_transpose_w3x3(w_hwio, wt, Cin, Cout, r.st);
       gemm_nn(convA(G, ldg, H, W, Cout, dil), wt, nullptr, dA, ldd, M, 9 * Cout, Cin, HW, accumulate, r.st);
@@ -310,8 +320,8 @@ void run_forward(const Run& r, const float* images, const int32_t* index, bool t
     bn_eval_coeffs(r.theta, r.c->d_gamma_idx, r.c->d_beta_idx, r.mm, r.mv, p.n_bn_ch, r.W(p.bn_a), r.W(p.bn_b), st);
   if (training && p.n_dc > 0) {
     const float* k = r.c->keep;
-    MLIIS_COUNT(), dcs_kernel<<<cdiv(p.n_dc * B, 128), 128, 0, st>>>(dc_mask, r.W(p.dcs), p.n_dc, B, p.maxB, k[0], k[1], k[2], k[3],
-                                                      k[4], k[5], k[6], k[7]);
+    MLIIS_COUNT(), dcs_kernel<<<dim3(cdiv(p.n_dc * B, 128), 1, MLIIS_NZ), 128, 0, st>>>(dc_mask, r.W(p.dcs), p.n_dc, B, p.maxB, k[0], k[1],
+                                                                         k[2], k[3], k[4], k[5], k[6], k[7], MLIIS_ZS);
   }
   // stem (efficientnet_model.py:410-412); its BN+swish is fused into block 0's depthwise loader
   stem_fwd(images, index, r.T(p.w_stem), r.W(p.S0.off), B, p.image_size, p.image_size, p.Hs, p.Ws, p.stem_pad_t,
@@ -471,9 +481,12 @@ void run_backward(const Run& r, const float* labels, const int32_t* index, float
   const int B = r.B;
   cudaStream_t st = r.st;
   const Tab& tf = r.c->tabs[p.tab_final];
-  if (!r.sl->grads_zeroed) {   // padding holes of the flat gradient buffer must read as zero
-    cudaMemsetAsync(r.G(0), 0, p.n_theta * sizeof(float), st);
-    r.sl->grads_zeroed = true;
+  for (int z = 0; z < MLIIS_NZ; ++z) {   // padding holes of the flat gradient buffer must read as zero
+    Slot& sz = r.sl[z];
+    if (!sz.grads_zeroed) {
+      cudaMemsetAsync(r.G(0) + (size_t)z * MLIIS_ZS, 0, p.n_theta * sizeof(float), st);
+      sz.grads_zeroed = true;
+    }
   }
   if (p.n_out != 2) {
     run_backward_multiclass_head(r, labels, index, loss_out);
@@ -650,7 +663,7 @@ int validate(mliis_ctx* ctx, int slot, int batch) {
 }
 
 void set_lr(const Run& r, float lr) {
-  MLIIS_COUNT(), set_scalar_kernel<<<1, 1, 0, r.st>>>(r.W(r.p.lr_dev), lr);
+  MLIIS_COUNT(), set_scalar_kernel<<<dim3(1, 1, MLIIS_NZ), 1, 0, r.st>>>(r.W(r.p.lr_dev), lr, MLIIS_ZS);
 }
 
 void run_optimizer(const Run& r, const float* lr_dev) {
@@ -926,7 +939,12 @@ int mliis_predict(mliis_ctx* ctx, int32_t slot, const float* images, const float
 static int task_body(mliis_ctx* ctx, int32_t slot, const mliis_task_args* a, cudaStream_t st) {
   const Plan& p = ctx->plan;
   if (p.n_out != 2) return fail(MLIIS_ERR_STATE, "task adaptation runs on the binary head (n_classes <= 1)");
-  int rc = mliis_state_copy(ctx, ctx->slots[slot].state, a->dev_init_state, MLIIS_STATE_ALL, (void*)st);
+  const int ng = a->n_group > 1 ? a->n_group : 1;
+  ZScope zscope(ng, ng > 1 ? (long long)(a->group_stride_bytes / 4) : 0);   // every launch below serves ng slots
+  ctx->group_fallback = false;
+  int rc = MLIIS_OK;
+  for (int k = 0; k < ng && !rc; ++k)
+    rc = mliis_state_copy(ctx, ctx->slots[slot + k].state, a->dev_init_state, MLIIS_STATE_ALL, (void*)st);
   if (rc) return rc;
   for (int t = 0; t < a->n_steps; ++t) {
     Run r(ctx, slot, a->batch, st);
@@ -942,6 +960,9 @@ static int task_body(mliis_ctx* ctx, int32_t slot, const mliis_task_args* a, cud
   const Tab& tf = ctx->tabs[p.tab_final];
   predict_mask_iou(r.W(p.z_lo), a->dev_labels, a->dev_query_index, a->n_query, p.hl, p.wl, p.image_size, p.image_size,
                    tf.rt(), tf.rt(), nullptr, nullptr, a->dev_inter_out, a->dev_union_out, st);
+  if (ctx->group_fallback)
+    return fail(MLIIS_ERR_STATE, "task-batched execution needs the tensor-core modes (a layer fell back to the "
+                                 "single-slot fp32 GEMM kernels)");
   return MLIIS_OK;
 }
 
@@ -953,6 +974,19 @@ static int task_validate(mliis_ctx* ctx, int32_t slot, const mliis_task_args* a)
   if (a->n_steps < 0) return fail(MLIIS_ERR_ARG, "n_steps < 0");
   if (!a->dev_init_state || !a->dev_images || !a->dev_labels || !a->dev_batch_index || !a->dev_lr || !a->dev_query_index)
     return fail(MLIIS_ERR_ARG, "null task argument");
+  if (a->n_group > 1) {
+    if (ctx->cfg.gemm_mode == MLIIS_GEMM_FP32) return fail(MLIIS_ERR_ARG, "task-batched execution needs a tensor-core gemm_mode");
+    if (slot + a->n_group > (int)ctx->slots.size()) return fail(MLIIS_ERR_ARG, "group exceeds n_slots");
+    if (a->group_stride_bytes <= 0 || (a->group_stride_bytes & 255)) return fail(MLIIS_ERR_ARG, "group stride must be a positive multiple of 256");
+    const Slot& s0 = ctx->slots[slot];
+    for (int k = 1; k < a->n_group; ++k) {
+      const Slot& sk = ctx->slots[slot + k];
+      if (!sk.state || !sk.ws) return fail(MLIIS_ERR_STATE, "slot %d not bound", slot + k);
+      if ((const char*)sk.state - (const char*)s0.state != (ptrdiff_t)k * a->group_stride_bytes ||
+          (const char*)sk.ws - (const char*)s0.ws != (ptrdiff_t)k * a->group_stride_bytes)
+        return fail(MLIIS_ERR_ARG, "slots %d..%d are not laid out at the uniform group stride", slot, slot + a->n_group - 1);
+    }
+  }
   return MLIIS_OK;
 }
 
@@ -972,9 +1006,12 @@ int mliis_task_graph_capture(mliis_ctx* ctx, int32_t slot, const mliis_task_args
   Slot& sl = ctx->slots[slot];
   if (sl.graph_exec) { cudaGraphExecDestroy(sl.graph_exec); sl.graph_exec = nullptr; }
   if (sl.graph) { cudaGraphDestroy(sl.graph); sl.graph = nullptr; }
-  if (!sl.grads_zeroed) {   // memset outside the graph so that replays do not repeat it
-    cudaMemsetAsync(sl.ws + ctx->plan.grads, 0, ctx->plan.n_theta * sizeof(float), st);
-    sl.grads_zeroed = true;
+  for (int k = 0; k < (a->n_group > 1 ? a->n_group : 1); ++k) {   // memsets outside the graph: replays do not repeat them
+    Slot& sk = ctx->slots[slot + k];
+    if (!sk.grads_zeroed) {
+      cudaMemsetAsync(sk.ws + ctx->plan.grads, 0, ctx->plan.n_theta * sizeof(float), st);
+      sk.grads_zeroed = true;
+    }
   }
   cudaStreamSynchronize(st);
   const unsigned long long before = g_kernel_launches;

@@ -278,14 +278,15 @@ void gemm_tn(const GemmA& A, const float* G, int ldg, float* dW, float* dbias, f
 // ---------------------------------------------------------------------------------------------
 // small weight reshuffles for dgrad
 // ---------------------------------------------------------------------------------------------
-__global__ void transpose_w_kernel(const float* __restrict__ w, float* __restrict__ wt, int K, int N) {
+__global__ void transpose_w_kernel(const float* __restrict__ w, float* __restrict__ wt, int K, int N, long long zs) {
+  { const size_t zo = (size_t)blockIdx.z * zs; w += zo; wt += zo; }
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K * N) return;
   int n = i / K, k = i - n * K;   // wt[n][k]
   wt[i] = w[(size_t)k * N + n];
 }
 void transpose_w(const float* w, float* wt, int K, int N, cudaStream_t s) {
-  MLIIS_COUNT(), transpose_w_kernel<<<cdiv(K * N, 256), 256, 0, s>>>(w, wt, K, N);
+  MLIIS_COUNT(), transpose_w_kernel<<<dim3(cdiv(K * N, 256), 1, MLIIS_NZ), 256, 0, s>>>(w, wt, K, N, MLIIS_ZS);
 }
 // wt[tap][n][c] = w[8-tap][c][n]
 __global__ void flip_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int C, int N) {

@@ -26,8 +26,9 @@ __device__ __forceinline__ bool tap_valid(int tap, int cls) {
 
 // grid (9 classes, B); block (D, 4): threadIdx.y splits the pooled channels, fixed-order combine through smem.
 __global__ void pool_bias9_kernel(const float* __restrict__ pooled, int ldp, const float* __restrict__ w, int Cs,
-                                  int c_first, int Cp, int D, float* __restrict__ bias9) {
+                                  int c_first, int Cp, int D, float* __restrict__ bias9, long long zs) {
   extern __shared__ float smf[];
+  { const size_t zo = (size_t)blockIdx.z * zs; pooled += zo; w += zo; bias9 += zo; }
   const int cls = blockIdx.x, b = blockIdx.y, n = threadIdx.x, part = threadIdx.y, P = blockDim.y;
   float acc = 0.f;
   for (int tap = 0; tap < 9; ++tap) {
@@ -48,14 +49,15 @@ __global__ void pool_bias9_kernel(const float* __restrict__ pooled, int ldp, con
 
 void pool_bias9(const float* pooled, int ldp, const float* w_hwio, int Cs, int c_first, int Cp, int D, int B,
                 float* bias9, cudaStream_t s) {
-  MLIIS_COUNT(), pool_bias9_kernel<<<dim3(9, B), dim3(D, 4), 4 * D * sizeof(float), s>>>(pooled, ldp, w_hwio, Cs, c_first, Cp, D,
-                                                                                        bias9);
+  MLIIS_COUNT(), pool_bias9_kernel<<<dim3(9, B, MLIIS_NZ), dim3(D, 4), 4 * D * sizeof(float), s>>>(pooled, ldp, w_hwio, Cs, c_first, Cp,
+                                                                                                  D, bias9, MLIIS_ZS);
 }
 
 // Q partials: grid (G row chunks, B); block (D/4, R).  partial[b][g][cls][D]
 __global__ void region_sums_kernel(const float* __restrict__ g, int ldg, int H, int W, int dil, int D, int rows_per_chunk,
-                                   float* __restrict__ partial) {
+                                   float* __restrict__ partial, long long zs) {
   extern __shared__ float4 sm[];
+  { const size_t zo = (size_t)blockIdx.z * zs; g += zo; partial += zo; }
   const int cq = threadIdx.x, C4 = blockDim.x, R = blockDim.y, ty = threadIdx.y, b = blockIdx.y, G = gridDim.x;
   const int HW = H * W;
   const int r0 = blockIdx.x * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
@@ -84,7 +86,9 @@ __global__ void region_sums_kernel(const float* __restrict__ g, int ldg, int H, 
 }
 
 // S[b][tap][n] = sum over the classes in which the tap is valid of Q[b][cls][n];  grid B, block D
-__global__ void region_sums_finalize_kernel(const float* __restrict__ partial, int G, int D, float* __restrict__ S) {
+__global__ void region_sums_finalize_kernel(const float* __restrict__ partial, int G, int D, float* __restrict__ S,
+                                            long long zs) {
+  { const size_t zo = (size_t)blockIdx.z * zs; partial += zo; S += zo; }
   const int b = blockIdx.x, n = threadIdx.x;
   double q[9];
 #pragma unroll
@@ -119,14 +123,15 @@ void region_sums(const float* g, int ldg, int B, int H, int W, int dil, int D, f
   if (R > 16) R = 16;
   const int G = region_sums_chunks(H * W, D);
   dim3 blk(D / 4, R);
-  MLIIS_COUNT(), region_sums_kernel<<<dim3(G, B), blk, 9 * blk.x * blk.y * sizeof(float4), s>>>(g, ldg, H, W, dil, D, cdiv(H * W, G),
-                                                                                             partial);
-  MLIIS_COUNT(), region_sums_finalize_kernel<<<B, D, 0, s>>>(partial, G, D, S);
+  MLIIS_COUNT(), region_sums_kernel<<<dim3(G, B, MLIIS_NZ), blk, 9 * blk.x * blk.y * sizeof(float4), s>>>(g, ldg, H, W, dil, D,
+                                                                                                       cdiv(H * W, G), partial, MLIIS_ZS);
+  MLIIS_COUNT(), region_sums_finalize_kernel<<<dim3(B, 1, MLIIS_NZ), D, 0, s>>>(partial, G, D, S, MLIIS_ZS);
 }
 
 // dW[tap][c_first + c][n] = sum_b pooled[b][c] * S[b][tap][n];  grid (ceil(Cp/8), 9); block (D, 8)
 __global__ void pool_wgrad_kernel(const float* __restrict__ pooled, int ldp, const float* __restrict__ S, int B, int Cs,
-                                  int c_first, int Cp, int D, float* __restrict__ dw) {
+                                  int c_first, int Cp, int D, float* __restrict__ dw, long long zs) {
+  { const size_t zo = (size_t)blockIdx.z * zs; pooled += zo; S += zo; dw += zo; }
   const int n = threadIdx.x, c = blockIdx.x * blockDim.y + threadIdx.y, tap = blockIdx.y;
   if (c >= Cp) return;
   float s = 0.f;
@@ -135,13 +140,15 @@ __global__ void pool_wgrad_kernel(const float* __restrict__ pooled, int ldp, con
 }
 void pool_wgrad(const float* pooled, int ldp, const float* S, int B, int Cs, int c_first, int Cp, int D, float* dw,
                 cudaStream_t s) {
-  MLIIS_COUNT(), pool_wgrad_kernel<<<dim3(cdiv(Cp, 8), 9), dim3(D, 8), 0, s>>>(pooled, ldp, S, B, Cs, c_first, Cp, D, dw);
+  MLIIS_COUNT(), pool_wgrad_kernel<<<dim3(cdiv(Cp, 8), 9, MLIIS_NZ), dim3(D, 8), 0, s>>>(pooled, ldp, S, B, Cs, c_first, Cp, D, dw,
+                                                                                        MLIIS_ZS);
 }
 
 // dpooled[b][c] = scale * sum_{tap,n} S[b][tap][n] * W[tap][c_first + c][n];  grid (ceil(Cp/8), B); one warp per c
 __global__ void __launch_bounds__(256) pool_dgrad_kernel(const float* __restrict__ S, const float* __restrict__ w, int Cs,
                                                          int c_first, int Cp, int D, float scale,
-                                                         float* __restrict__ dpooled, int ldo) {
+                                                         float* __restrict__ dpooled, int ldo, long long zs) {
+  { const size_t zo = (size_t)blockIdx.z * zs; S += zo; w += zo; dpooled += zo; }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * 8 + warp, b = blockIdx.y;
   if (c >= Cp) return;
@@ -156,7 +163,8 @@ __global__ void __launch_bounds__(256) pool_dgrad_kernel(const float* __restrict
 }
 void pool_dgrad(const float* S, const float* w_hwio, int Cs, int c_first, int Cp, int D, int B, float scale,
                 float* dpooled, int ldo, cudaStream_t s) {
-  MLIIS_COUNT(), pool_dgrad_kernel<<<dim3(cdiv(Cp, 8), B), 256, 0, s>>>(S, w_hwio, Cs, c_first, Cp, D, scale, dpooled, ldo);
+  MLIIS_COUNT(), pool_dgrad_kernel<<<dim3(cdiv(Cp, 8), B, MLIIS_NZ), 256, 0, s>>>(S, w_hwio, Cs, c_first, Cp, D, scale, dpooled, ldo,
+                                                                                 MLIIS_ZS);
 }
 
 }  // namespace mliis

@@ -70,6 +70,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -159,13 +166,13 @@ __device__ __forceinline__ void named_bar_sync_half(int half) {
 // TMA stores of one shared-memory tile (dense [rows][128 B], SWIZZLE_128B) into a global tensor; rows / columns
 // outside the tensor are clipped by the TMA unit.  `add`: out += tile (element-wise reduction in L2; every output
 // element is produced by exactly one CTA, so the result is deterministic).
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1, bool add) {
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, bool add) {
   if (add)
-    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
   else
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, bool add) {
   if (add)
@@ -189,9 +196,11 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 // 128-byte rows instead of 32 scattered 16-byte stores per warp instruction).
 __global__ void __launch_bounds__(kTcThreads)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, TcParams p, long long zs) {
   extern __shared__ uint8_t smem_raw[];
   if (p.debug & 16) return;   // experiment: cost of everything except the tensor-core kernels
+  const int slot = blockIdx.z;      // task-batched launch: every tensor map has the slot as its outermost dimension
+  { const size_t zo = (size_t)slot * zs; bias = zp(bias, zo); p.pa = zp(p.pa, zo); p.pb = zp(p.pb, zo); p.gate = zp(p.gate, zo); }
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;              // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* smem = smem_raw + (base - raw);
@@ -285,12 +294,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_expect_tx(full_bar(s), (uint32_t)(p.a_box_bytes + (x3 ? 2 : 1) * b_bytes));
         if (p.conv) {
           const int dy = (tap / 3 - 1) * p.dil, dx = (tap % 3 - 1) * p.dil;
-          tma_load_4d(sa, &tmA, full_bar(s), kc * 32, dx, y0 + dy, img);
+          tma_load_5d(sa, &tmA, full_bar(s), kc * 32, dx, y0 + dy, img, slot);
         } else {
-          tma_load_2d(sa, &tmA, full_bar(s), kc * 32, m0);
+          tma_load_3d(sa, &tmA, full_bar(s), kc * 32, m0, slot);
         }
-        tma_load_4d(sb, &tmB, full_bar(s), kc * 32, tap, n0, 0);
-        if (x3) tma_load_4d(sb + b_bytes, &tmB, full_bar(s), kc * 32, tap, n0, 1);
+        tma_load_5d(sb, &tmB, full_bar(s), kc * 32, tap, n0, 0, slot);
+        if (x3) tma_load_5d(sb + b_bytes, &tmB, full_bar(s), kc * 32, tap, n0, 1, slot);
       }
     }
   } else if (warp == 1) {
@@ -435,8 +444,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       named_bar_sync_half(half);
       if (leader) {
-        if (p.conv) tma_store_3d(&tmC, stg_addr, n, y0 * p.W, img, p.accumulate != 0);
-        else tma_store_2d(&tmC, stg_addr, n, m0, p.accumulate != 0);
+        if (p.conv) tma_store_4d(&tmC, stg_addr, n, y0 * p.W, img, slot, p.accumulate != 0);
+        else tma_store_3d(&tmC, stg_addr, n, m0, slot, p.accumulate != 0);
         tma_store_commit();
       }
     }
@@ -478,9 +487,11 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc_off(uint32_t smem_add
 
 __global__ void __launch_bounds__(kC3Threads)
 tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const float* __restrict__ bias, float* __restrict__ out, const TcC3Params p) {
+                const float* __restrict__ bias, float* __restrict__ out, TcC3Params p, long long zs) {
   extern __shared__ uint8_t smem_raw[];
   if (p.debug & 16) return;   // experiment: cost of everything except the tensor-core kernels
+  const int slot = blockIdx.z;
+  { const size_t zo = (size_t)slot * zs; bias = zp(bias, zo); out += zo; p.bias9 = zp(p.bias9, zo); }
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
@@ -532,14 +543,14 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int sa = ia % p.SA;
         mbar_wait(a_empty(sa), ((ia / p.SA) & 1) ^ 1);
         mbar_expect_tx(a_full(sa), (uint32_t)p.a_box_bytes);
-        tma_load_4d(a_base + (uint32_t)sa * a_stage, &tmA, a_full(sa), kc * 32, -p.dil, y0 + (dy - 1) * p.dil, img);
+        tma_load_5d(a_base + (uint32_t)sa * a_stage, &tmA, a_full(sa), kc * 32, -p.dil, y0 + (dy - 1) * p.dil, img, slot);
         for (int dx = 0; dx < 3; ++dx, ++ib) {
           const int sb = ib % p.SB;
           mbar_wait(b_empty(sb), ((ib / p.SB) & 1) ^ 1);
           mbar_expect_tx(b_full(sb), (uint32_t)b_stage);
           const uint32_t dst = b_base + (uint32_t)sb * b_stage;
-          tma_load_4d(dst, &tmB, b_full(sb), kc * 32, dy * 3 + dx, n0, 0);
-          if (x3) tma_load_4d(dst + p.b_plane_bytes, &tmB, b_full(sb), kc * 32, dy * 3 + dx, n0, 1);
+          tma_load_5d(dst, &tmB, b_full(sb), kc * 32, dy * 3 + dx, n0, 0, slot);
+          if (x3) tma_load_5d(dst + p.b_plane_bytes, &tmB, b_full(sb), kc * 32, dy * 3 + dx, n0, 1, slot);
         }
       }
     }
@@ -688,6 +699,12 @@ static bool encode(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* 
   return r == CUDA_SUCCESS;
 }
 
+// outermost "task slot" dimension of every tensor map: nz slots, zs floats apart (one slot: any legal stride)
+static inline cuuint64_t slot_stride_bytes(cuuint64_t natural) {
+  if (MLIIS_NZ > 1) return (cuuint64_t)MLIIS_ZS * 4;
+  return (natural + 15) / 16 * 16;
+}
+
 int tc_pick_bn(int N) {
   int tiles = (N + 255) / 256;
   int bn = (N + tiles - 1) / tiles;
@@ -747,16 +764,18 @@ static bool tc_conv3(const float* A, int lda, const float* Wt, const float* bias
   if (p.SB < 2) return false;
   CUtensorMap tmA, tmB;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t str[3] = {(cuuint64_t)lda * 4, (cuuint64_t)W * lda * 4, (cuuint64_t)H * W * lda * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)p.RW, (cuuint32_t)(p.MT * p.BH), 1};
-    if (!encode(&tmA, A, 4, dims, str, box)) return false;
+    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)MLIIS_NZ};
+    cuuint64_t str[4] = {(cuuint64_t)lda * 4, (cuuint64_t)W * lda * 4, (cuuint64_t)H * W * lda * 4,
+                         slot_stride_bytes((cuuint64_t)B * H * W * lda * 4)};
+    cuuint32_t box[5] = {32, (cuuint32_t)p.RW, (cuuint32_t)(p.MT * p.BH), 1, 1};
+    if (!encode(&tmA, A, 5, dims, str, box)) return false;
   }
   {
-    cuuint64_t dims[4] = {(cuuint64_t)C, 9, (cuuint64_t)N, (cuuint64_t)planes};
-    cuuint64_t str[3] = {(cuuint64_t)C * 4, (cuuint64_t)9 * C * 4, (cuuint64_t)N * 9 * C * 4};
-    cuuint32_t box[4] = {32, 1, (cuuint32_t)p.BN, 1};
-    if (!encode(&tmB, Wt, 4, dims, str, box)) return false;
+    cuuint64_t dims[5] = {(cuuint64_t)C, 9, (cuuint64_t)N, (cuuint64_t)planes, (cuuint64_t)MLIIS_NZ};
+    cuuint64_t str[4] = {(cuuint64_t)C * 4, (cuuint64_t)9 * C * 4, (cuuint64_t)N * 9 * C * 4,
+                         slot_stride_bytes((cuuint64_t)planes * N * 9 * C * 4)};
+    cuuint32_t box[5] = {32, 1, (cuuint32_t)p.BN, 1, 1};
+    if (!encode(&tmB, Wt, 5, dims, str, box)) return false;
   }
   const size_t smem = (size_t)p.SA * planes * p.a_slot_bytes + (size_t)p.SB * planes * p.b_plane_bytes +
                       (3 * p.SA + 2 * p.SB + 2) * 8 + 1024;
@@ -765,8 +784,8 @@ static bool tc_conv3(const float* A, int lda, const float* Wt, const float* bias
     cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
-  dim3 grid(B * p.groups_per_image, (N + p.BN - 1) / p.BN);
-  MLIIS_COUNT(), tc_conv3_kernel<<<grid, kC3Threads, smem, s>>>(tmA, tmB, bias, out, p);
+  dim3 grid(B * p.groups_per_image, (N + p.BN - 1) / p.BN, MLIIS_NZ);
+  MLIIS_COUNT(), tc_conv3_kernel<<<grid, kC3Threads, smem, s>>>(tmA, tmB, bias, out, p, MLIIS_ZS);
   return true;
 }
 
@@ -794,33 +813,36 @@ bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float*
     if (p.BH > H) p.BH = H;
     p.tiles_per_image = (H + p.BH - 1) / p.BH;
     p.a_box_bytes = p.BH * W * 128;
-    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t str[3] = {(cuuint64_t)lda * 4, (cuuint64_t)W * lda * 4, (cuuint64_t)H * W * lda * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)W, (cuuint32_t)p.BH, 1};
-    if (!encode(&tmA, A, 4, dims, str, box)) return false;
+    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)MLIIS_NZ};
+    cuuint64_t str[4] = {(cuuint64_t)lda * 4, (cuuint64_t)W * lda * 4, (cuuint64_t)H * W * lda * 4,
+                         slot_stride_bytes((cuuint64_t)B * H * W * lda * 4)};
+    cuuint32_t box[5] = {32, (cuuint32_t)W, (cuuint32_t)p.BH, 1, 1};
+    if (!encode(&tmA, A, 5, dims, str, box)) return false;
     grid_x = B * p.tiles_per_image;
-    // output [B, H*W, N]: one box = the BH*W pixels of the tile x 32 columns (rows past the image are clipped)
-    cuuint64_t cd[3] = {(cuuint64_t)N, (cuuint64_t)H * W, (cuuint64_t)B};
-    cuuint64_t cs[2] = {(cuuint64_t)ldc * 4, (cuuint64_t)H * W * ldc * 4};
-    cuuint32_t cb[3] = {32, (cuuint32_t)(p.BH * W), 1};
-    if (!encode(&tmC, out, 3, cd, cs, cb)) return false;
+    // output [slot, B, H*W, N]: one box = the BH*W pixels of the tile x 32 columns (rows past the image are clipped)
+    cuuint64_t cd[4] = {(cuuint64_t)N, (cuuint64_t)H * W, (cuuint64_t)B, (cuuint64_t)MLIIS_NZ};
+    cuuint64_t cs[3] = {(cuuint64_t)ldc * 4, (cuuint64_t)H * W * ldc * 4, slot_stride_bytes((cuuint64_t)B * H * W * ldc * 4)};
+    cuuint32_t cb[4] = {32, (cuuint32_t)(p.BH * W), 1, 1};
+    if (!encode(&tmC, out, 4, cd, cs, cb)) return false;
   } else {
     p.a_box_bytes = kABytes;
-    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)M};
-    cuuint64_t str[1] = {(cuuint64_t)lda * 4};
-    cuuint32_t box[2] = {32, 128};
-    if (!encode(&tmA, A, 2, dims, str, box)) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)M, (cuuint64_t)MLIIS_NZ};
+    cuuint64_t str[2] = {(cuuint64_t)lda * 4, slot_stride_bytes((cuuint64_t)M * lda * 4)};
+    cuuint32_t box[3] = {32, 128, 1};
+    if (!encode(&tmA, A, 3, dims, str, box)) return false;
     grid_x = (M + 127) / 128;
-    cuuint64_t cd[2] = {(cuuint64_t)N, (cuuint64_t)M};
-    cuuint64_t cs[1] = {(cuuint64_t)ldc * 4};
-    if (!encode(&tmC, out, 2, cd, cs, box)) return false;
+    cuuint64_t cd[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)MLIIS_NZ};
+    cuuint64_t cs[2] = {(cuuint64_t)ldc * 4, slot_stride_bytes((cuuint64_t)M * ldc * 4)};
+    if (!encode(&tmC, out, 3, cd, cs, box)) return false;
   }
   {
     // operand planes: [hi][N][taps][C] and, for split == 3, [lo][N][taps][C] right behind it
-    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)taps, (cuuint64_t)N, (cuuint64_t)(p.split == 3 ? 2 : 1)};
-    cuuint64_t str[3] = {(cuuint64_t)C * 4, (cuuint64_t)taps * C * 4, (cuuint64_t)N * taps * C * 4};
-    cuuint32_t box[4] = {32, 1, (cuuint32_t)p.BN, 1};
-    if (!encode(&tmB, Wt, 4, dims, str, box)) return false;
+    const int planes = p.split == 3 ? 2 : 1;
+    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)taps, (cuuint64_t)N, (cuuint64_t)planes, (cuuint64_t)MLIIS_NZ};
+    cuuint64_t str[4] = {(cuuint64_t)C * 4, (cuuint64_t)taps * C * 4, (cuuint64_t)N * taps * C * 4,
+                         slot_stride_bytes((cuuint64_t)planes * N * taps * C * 4)};
+    cuuint32_t box[5] = {32, 1, (cuuint32_t)p.BN, 1, 1};
+    if (!encode(&tmB, Wt, 5, dims, str, box)) return false;
   }
   const int stage_bytes = (p.split == 3 ? 2 : 1) * (kABytes + p.BN * 128);
   const int KB = taps * ((C + 31) / 32);
@@ -843,8 +865,8 @@ bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float*
     cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
-  dim3 grid(grid_x, (N + p.BN - 1) / p.BN);
-  MLIIS_COUNT(), tc_conv_kernel<<<grid, kTcThreads, smem, s>>>(tmA, tmB, tmC, bias, p);
+  dim3 grid(grid_x, (N + p.BN - 1) / p.BN, MLIIS_NZ);
+  MLIIS_COUNT(), tc_conv_kernel<<<grid, kTcThreads, smem, s>>>(tmA, tmB, tmC, bias, p, MLIIS_ZS);
   return true;
 }
 
@@ -892,9 +914,11 @@ constexpr int kWgThreads = 64 + kWgXformThreads;
 
 __global__ void __launch_bounds__(kWgThreads)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmG,
-                float* __restrict__ partial, const TcWgParams p) {
+                float* __restrict__ partial, TcWgParams p, long long zs) {
   extern __shared__ uint8_t smem_raw[];
   if (p.debug & 16) return;   // experiment: cost of everything except the tensor-core kernels
+  const int slot = blockIdx.z / p.splits;      // grid.z = (task slot, pixel-range split)
+  { const size_t zo = (size_t)slot * zs; partial += zo; p.pa = zp(p.pa, zo); p.pb = zp(p.pb, zo); p.gate = zp(p.gate, zo); }
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
@@ -938,7 +962,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
 
-  const int c0 = blockIdx.x * 128, tap = blockIdx.y, split = blockIdx.z;
+  const int c0 = blockIdx.x * 128, tap = blockIdx.y, split = blockIdx.z - slot * p.splits;
   const int per = (p.tiles_total + p.splits - 1) / p.splits;
   const int t_beg = split * per, t_end = min(p.tiles_total, t_beg + per);
   const int KB = max(t_end - t_beg, 0);
@@ -957,12 +981,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int per_img = p.tiles_x * p.tiles_y;
           const int img = t / per_img, rem = t - img * per_img, ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
           const int x0 = tx * p.BX, y0 = ty * p.BY;
-          for (int g = 0; g < 4; ++g) tma_load_4d(sa + g * a_group, &tmA, full_bar(s), c0 + 32 * g, x0 + dx, y0 + dy, img);
-          for (int g = 0; g < p.NG; ++g) tma_load_4d(sg + g * kWgGroupBytes, &tmG, full_bar(s), 32 * g, x0, y0, img);
+          for (int g = 0; g < 4; ++g)
+            tma_load_5d(sa + g * a_group, &tmA, full_bar(s), c0 + 32 * g, x0 + dx, y0 + dy, img, slot);
+          for (int g = 0; g < p.NG; ++g) tma_load_5d(sg + g * kWgGroupBytes, &tmG, full_bar(s), 32 * g, x0, y0, img, slot);
         } else {
           const int m0 = t * 32;
-          for (int g = 0; g < 4; ++g) tma_load_2d(sa + g * kWgGroupBytes, &tmA, full_bar(s), c0 + 32 * g, m0);
-          for (int g = 0; g < p.NG; ++g) tma_load_2d(sg + g * kWgGroupBytes, &tmG, full_bar(s), 32 * g, m0);
+          for (int g = 0; g < 4; ++g) tma_load_3d(sa + g * kWgGroupBytes, &tmA, full_bar(s), c0 + 32 * g, m0, slot);
+          for (int g = 0; g < p.NG; ++g) tma_load_3d(sg + g * kWgGroupBytes, &tmG, full_bar(s), 32 * g, m0, slot);
         }
       }
     }
@@ -1176,28 +1201,30 @@ bool tc_wgrad(const float* A, int lda, const float* G, int ldg, float* dW, float
       const int ct = (C + 127) / 128, s3 = 296 / (ct * 3) > 0 ? 296 / (ct * 3) : 1;
       p.share = (share_on && taps == 9 && 3 * p.BN <= 512 && p.tiles_total / s3 >= 8) ? 1 : 0;
     }
-    cuuint32_t box[4] = {32, (cuuint32_t)p.BX, (cuuint32_t)p.BY, 1};
-    cuuint32_t boxA[4] = {32, (cuuint32_t)(p.BX + (p.share ? 2 * dil : 0)), (cuuint32_t)p.BY, 1};
+    cuuint32_t box[5] = {32, (cuuint32_t)p.BX, (cuuint32_t)p.BY, 1, 1};
+    cuuint32_t boxA[5] = {32, (cuuint32_t)(p.BX + (p.share ? 2 * dil : 0)), (cuuint32_t)p.BY, 1, 1};
     if (p.share) {
       const int rows = (p.BX + 2 * dil) * p.BY;
       p.a_tx_bytes = 4 * rows * 128;
       p.a_group_bytes = (rows * 128 + 511) / 512 * 512;        // slabs start on swizzle-atom (512 B) boundaries
     }
-    cuuint64_t dA[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t sA[3] = {(cuuint64_t)lda * 4, (cuuint64_t)W * lda * 4, (cuuint64_t)H * W * lda * 4};
-    if (!encode(&tmA, A, 4, dA, sA, boxA, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return false;
-    cuuint64_t dG[4] = {(cuuint64_t)N, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t sG[3] = {(cuuint64_t)ldg * 4, (cuuint64_t)W * ldg * 4, (cuuint64_t)H * W * ldg * 4};
-    if (!encode(&tmG, G, 4, dG, sG, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return false;
+    cuuint64_t dA[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)MLIIS_NZ};
+    cuuint64_t sA[4] = {(cuuint64_t)lda * 4, (cuuint64_t)W * lda * 4, (cuuint64_t)H * W * lda * 4,
+                        slot_stride_bytes((cuuint64_t)B * H * W * lda * 4)};
+    if (!encode(&tmA, A, 5, dA, sA, boxA, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return false;
+    cuuint64_t dG[5] = {(cuuint64_t)N, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)MLIIS_NZ};
+    cuuint64_t sG[4] = {(cuuint64_t)ldg * 4, (cuuint64_t)W * ldg * 4, (cuuint64_t)H * W * ldg * 4,
+                        slot_stride_bytes((cuuint64_t)B * H * W * ldg * 4)};
+    if (!encode(&tmG, G, 5, dG, sG, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return false;
   } else {
     p.tiles_total = (M + 31) / 32;
-    cuuint32_t box[2] = {32, 32};
-    cuuint64_t dA[2] = {(cuuint64_t)C, (cuuint64_t)M};
-    cuuint64_t sA[1] = {(cuuint64_t)lda * 4};
-    if (!encode(&tmA, A, 2, dA, sA, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return false;
-    cuuint64_t dG[2] = {(cuuint64_t)N, (cuuint64_t)M};
-    cuuint64_t sG[1] = {(cuuint64_t)ldg * 4};
-    if (!encode(&tmG, G, 2, dG, sG, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return false;
+    cuuint32_t box[3] = {32, 32, 1};
+    cuuint64_t dA[3] = {(cuuint64_t)C, (cuuint64_t)M, (cuuint64_t)MLIIS_NZ};
+    cuuint64_t sA[2] = {(cuuint64_t)lda * 4, slot_stride_bytes((cuuint64_t)M * lda * 4)};
+    if (!encode(&tmA, A, 3, dA, sA, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return false;
+    cuuint64_t dG[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)MLIIS_NZ};
+    cuuint64_t sG[2] = {(cuuint64_t)ldg * 4, slot_stride_bytes((cuuint64_t)M * ldg * 4)};
+    if (!encode(&tmG, G, 3, dG, sG, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return false;
   }
   const int ctiles = (C + 127) / 128;
   const int grid_taps = p.share ? 3 : taps;
@@ -1215,8 +1242,8 @@ bool tc_wgrad(const float* A, int lda, const float* G, int ldg, float* dW, float
     cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
-  dim3 grid(ctiles, grid_taps, p.splits);
-  MLIIS_COUNT(), tc_wgrad_kernel<<<grid, kWgThreads, smem, s>>>(tmA, tmG, scratch, p);
+  dim3 grid(ctiles, grid_taps, p.splits * MLIIS_NZ);
+  MLIIS_COUNT(), tc_wgrad_kernel<<<grid, kWgThreads, smem, s>>>(tmA, tmG, scratch, p, MLIIS_ZS);
   if (dw_tap_stride > 0 && dw_tap_stride != C * N)
     reduce_partials_strided(scratch, p.splits, C * N, taps, dW, dw_tap_stride, s);
   else
@@ -1241,14 +1268,16 @@ __device__ __forceinline__ void prep_one(const float* __restrict__ w, float* __r
   if (split == 3) wt[(size_t)n + i] = rn_tf32(v - h);
 }
 __global__ void tc_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ wt, int taps, int Ci, int Co,
-                                       int dgrad, int split, int Cs) {
+                                       int dgrad, int split, int Cs, long long zs) {
+  { const size_t zo = (size_t)blockIdx.z * zs; w += zo; wt += zo; }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = taps * Ci * Co;
   if (i < n) prep_one(w, wt, i, n, taps, Ci, Co, dgrad, split, Cs);
 }
 // every dense layer's forward and dgrad operand in ONE launch per step (blockIdx.y = job)
 __global__ void tc_prep_all_kernel(const float* __restrict__ theta, float* __restrict__ wcache,
-                                   const TcPrepJob* __restrict__ jobs) {
+                                   const TcPrepJob* __restrict__ jobs, long long zs) {
+  { const size_t zo = (size_t)blockIdx.z * zs; theta += zo; wcache += zo; }
   const TcPrepJob j = jobs[blockIdx.y];
   const int n = j.taps * j.Ci * j.Co;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -1256,11 +1285,12 @@ __global__ void tc_prep_all_kernel(const float* __restrict__ theta, float* __res
 }
 void tc_prep_all(const float* theta, float* wcache, const TcPrepJob* dev_jobs, int n_jobs, cudaStream_t s) {
   if (n_jobs <= 0) return;
-  MLIIS_COUNT(), tc_prep_all_kernel<<<dim3(24, n_jobs), 256, 0, s>>>(theta, wcache, dev_jobs);
+  MLIIS_COUNT(), tc_prep_all_kernel<<<dim3(24, n_jobs, MLIIS_NZ), 256, 0, s>>>(theta, wcache, dev_jobs, MLIIS_ZS);
 }
 void tc_prep_weights(const float* w, float* wt, int taps, int Ci, int Co, int dgrad, int split, cudaStream_t s, int Cs) {
   const int n = taps * Ci * Co;
-  MLIIS_COUNT(), tc_prep_weights_kernel<<<cdiv(n, 256), 256, 0, s>>>(w, wt, taps, Ci, Co, dgrad, split, Cs > 0 ? Cs : Ci);
+  MLIIS_COUNT(), tc_prep_weights_kernel<<<dim3(cdiv(n, 256), 1, MLIIS_NZ), 256, 0, s>>>(w, wt, taps, Ci, Co, dgrad, split,
+                                                                                       Cs > 0 ? Cs : Ci, MLIIS_ZS);
 }
 
 }  // namespace mliis

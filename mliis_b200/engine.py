@@ -26,7 +26,8 @@ class Engine:
 
     def __init__(self, image_size: int = 224, max_batch: int = 8, n_slots: int = 1, sgd: bool = False,
                  dice: bool = True, l2: bool = True, label_smoothing: float = 0.0, final_dropout_rate: float = 0.0,
-                 rsd: Sequence[int] = (2, 4), gemm_mode: int = N.GEMM_FP32, device: int = 0, n_classes: int = 1):
+                 rsd: Sequence[int] = (2, 4), gemm_mode: int = N.GEMM_FP32, device: int = 0, n_classes: int = 1,
+                 staging_bytes: Optional[int] = None):
         if not torch.cuda.is_available():
             raise N.MliisError(N.MLIIS_ERR_DEVICE, "no CUDA device: mliis_b200 has no CPU fallback")
         self.device = torch.device("cuda", device)
@@ -34,6 +35,7 @@ class Engine:
         flags = (N.LOSS_DICE if dice else 0) | (N.LOSS_L2 if l2 else 0)
         self.cfg = N.make_config(image_size, max_batch, n_slots, N.OPT_SGD if sgd else N.OPT_ADAM, flags, gemm_mode,
                                  label_smoothing, final_dropout_rate or 0.0, rsd, n_classes)
+        self.gemm_mode = gemm_mode
         self.n_classes = n_classes
         self.n_out = n_classes + 1 if n_classes > 1 else 2
         self.ctx = N.Context(self.cfg, device)
@@ -45,15 +47,21 @@ class Engine:
         self.n_bn = self.ctx.n_bn
         self.n_dc = self.ctx.n_dc
         self.state_floats = self.ctx.state_floats
-        self.states = torch.zeros(n_slots, self.state_floats, dtype=torch.float32, device=self.device)
-        self.workspaces = [torch.empty(self.ctx.workspace_bytes + 256, dtype=torch.uint8, device=self.device)
-                           for _ in range(n_slots)]
+        # ONE arena, one layout per slot at a uniform stride: [state | workspace | staging].  Task-batched launches
+        # (mliis_task_args.n_group) address slot k of a group as pointer + k * slot_stride for every per-slot pointer.
+        al = lambda n: (int(n) + 255) // 256 * 256
+        if staging_bytes is None:      # room for a 16-example task pool (images + 2-channel labels) + index / lr blocks
+            staging_bytes = 16 * image_size * image_size * 5 * 4 + (1 << 16)
+        self.state_bytes, self.ws_bytes, self.staging_bytes = al(self.state_floats * 4), al(self.ctx.workspace_bytes), al(staging_bytes)
+        self.slot_stride = self.state_bytes + self.ws_bytes + self.staging_bytes
+        self.arena = torch.zeros(n_slots * self.slot_stride + 256, dtype=torch.uint8, device=self.device)
+        self._arena_off = (-self.arena.data_ptr()) % 256
+        body = self.arena[self._arena_off:self._arena_off + n_slots * self.slot_stride]
+        self._slot_bytes = body.view(n_slots, self.slot_stride)
+        self.states = body.view(torch.float32).view(n_slots, self.slot_stride // 4)[:, :self.state_floats]
+        self.workspaces = [self._slot_bytes[s, self.state_bytes:self.state_bytes + self.ws_bytes] for s in range(n_slots)]
         for s in range(n_slots):
-            ws = self.workspaces[s]
-            base = (ws.data_ptr() + 255) // 256 * 256
-            N.check(self.lib.mliis_slot_bind(self.ctx.handle, s, _ptr(self.states[s]), C.c_void_p(base)))
-            self._ws_base = getattr(self, "_ws_base", {})
-            self._ws_base[s] = base
+            N.check(self.lib.mliis_slot_bind(self.ctx.handle, s, _ptr(self.states[s]), _ptr(self.workspaces[s])))
         self.o_bn = self.n_theta
         self.o_v = self.n_theta + 2 * self.n_bn
         self.o_pow = self.o_v + self.n_theta
@@ -62,6 +70,12 @@ class Engine:
         self._flat_index = torch.from_numpy(idx).to(self.device)
         self._sizes = [p.size for p in self.ctx.params]
         self._shapes = [p.shape for p in self.ctx.params]
+
+    def staging(self, slot: int) -> torch.Tensor:
+        """The slot's staging region (uint8 view of the arena): task inputs / outputs that a task-batched launch
+        must find at the uniform slot stride live here."""
+        o = self.state_bytes + self.ws_bytes
+        return self._slot_bytes[slot, o:o + self.staging_bytes]
 
     # ---- streams ----
     @staticmethod

@@ -48,7 +48,7 @@ class TaskArgs(C.Structure):
                 ("batch", C.c_int32), ("dev_query_index", C.c_void_p), ("n_query", C.c_int32),
                 ("dev_dc_mask", C.c_void_p), ("seed", C.c_uint64), ("pre_decay_rate", C.c_float),
                 ("dev_inter_out", C.c_void_p), ("dev_union_out", C.c_void_p), ("dev_loss_out", C.c_void_p),
-                ("dev_seed", C.c_void_p)]
+                ("dev_seed", C.c_void_p), ("n_group", C.c_int32), ("group_stride_bytes", C.c_int64)]
 
 
 # every symbol include/mliis_b200.h declares: (name, restype, argtypes)

@@ -36,39 +36,70 @@ class TaskPlan:
 
 
 class _SlotBuffers:
-    def __init__(self, eng: Engine, n_pool: int, T: int, B: int, nq: int, with_dc: bool):
-        S, dev = eng.image_size, eng.device
-        self.images = torch.empty(n_pool, S, S, 3, dtype=torch.float32, device=dev)
-        self.labels = torch.empty(n_pool, S, S, 2, dtype=torch.float32, device=dev)
-        self.h_images = torch.empty(n_pool, S, S, 3, dtype=torch.float32).pin_memory()
-        self.h_labels = torch.empty(n_pool, S, S, 2, dtype=torch.float32).pin_memory()
+    """Per-slot task inputs / outputs, carved out of the slot's staging region of the engine arena so that every slot
+    has them at the same offset (a task-batched launch addresses slot k as pointer + k * slot_stride)."""
+
+    def __init__(self, eng: Engine, slot: int, n_pool: int, T: int, B: int, nq: int, with_dc: bool):
+        S = eng.image_size
         # one small block: [dropout seed (one int64) | batch_index T*B | query nq] int32, [lr T | dc T*n_dc*B] f32
         self.n_i = 2 + T * B + nq
         self.n_f = T + (T * eng.n_dc * B if with_dc else 0)
-        self.ints = torch.zeros(self.n_i, dtype=torch.int32, device=dev)
-        self.floats = torch.zeros(self.n_f, dtype=torch.float32, device=dev)
+        stg = eng.staging(slot)
+        off = 0
+
+        def carve(n_elems, dtype):
+            nonlocal off
+            nbytes = n_elems * 4
+            if off + nbytes > stg.numel():
+                raise ValueError("the engine's per-slot staging region (%d bytes) is too small for this task shape; "
+                                 "create the Engine with a larger staging_bytes" % stg.numel())
+            t = stg[off:off + nbytes].view(dtype)
+            off = (off + nbytes + 255) // 256 * 256
+            return t
+        self.images = carve(n_pool * S * S * 3, torch.float32).view(n_pool, S, S, 3)
+        self.labels = carve(n_pool * S * S * 2, torch.float32).view(n_pool, S, S, 2)
+        self.ints = carve(self.n_i, torch.int32)
+        self.floats = carve(max(self.n_f, 1), torch.float32)[:self.n_f]
+        self.counts = carve(2 * nq, torch.int32)
+        self.losses = carve(T, torch.float32)
+        self.h_images = torch.empty(n_pool, S, S, 3, dtype=torch.float32).pin_memory()
+        self.h_labels = torch.empty(n_pool, S, S, 2, dtype=torch.float32).pin_memory()
         self.h_ints = torch.zeros(self.n_i, dtype=torch.int32).pin_memory()
         self.h_floats = torch.zeros(self.n_f, dtype=torch.float32).pin_memory()
-        self.counts = torch.zeros(2 * nq, dtype=torch.int32, device=dev)
         self.h_counts = torch.zeros(2 * nq, dtype=torch.int32).pin_memory()
-        self.losses = torch.zeros(T, dtype=torch.float32, device=dev)
-        self.stream = torch.cuda.Stream(device=dev)
+
+
+class _Group:
+    """`size` consecutive slots that adapt their tasks in lockstep: one stream, one CUDA graph."""
+
+    def __init__(self, eng: Engine, first: int, size: int):
+        self.first, self.size = first, size
+        self.stream = torch.cuda.Stream(device=eng.device)
         self.done = torch.cuda.Event()
         self.busy = False
-        self.tag = None
+        self.tags: List[Optional[int]] = []
 
 
 class TaskRunner:
     def __init__(self, eng: Engine, n_pool: int = 10, n_steps: int = 5, batch: int = 8, n_query: int = 5,
-                 use_graph: bool = True, with_dc_masks: bool = False, pre_decay_rate: float = 1.0):
+                 use_graph: bool = True, with_dc_masks: bool = False, pre_decay_rate: float = 1.0, group: int = 1):
+        """group: slots per task-batched launch (mliis_task_args.n_group).  group = 1: every slot replays its own
+        one-task graph (round-1 behaviour).  group = G > 1: G consecutive slots run in lockstep - each kernel is
+        launched once for G tasks - and n_slots / G groups are in flight concurrently.  Results are bit-identical."""
         if batch > eng.max_batch or n_query > eng.max_batch:
             raise ValueError("batch / n_query exceed the engine's max_batch")
+        if group < 1 or eng.n_slots % group:
+            raise ValueError("group (%d) must divide the engine's n_slots (%d)" % (group, eng.n_slots))
+        if group > 1 and eng.gemm_mode == N.GEMM_FP32:
+            raise ValueError("task-batched execution needs a tensor-core gemm_mode")
         self.eng = eng
         self.n_pool, self.T, self.B, self.nq = n_pool, n_steps, batch, n_query
         self.use_graph = use_graph
         self.with_dc = with_dc_masks
         self.pre_decay_rate = pre_decay_rate
-        self.slots = [_SlotBuffers(eng, n_pool, n_steps, batch, n_query, with_dc_masks) for _ in range(eng.n_slots)]
+        self.group = group
+        self.slots = [_SlotBuffers(eng, s, n_pool, n_steps, batch, n_query, with_dc_masks) for s in range(eng.n_slots)]
+        self.groups = [_Group(eng, g * group, group) for g in range(eng.n_slots // group)]
         self.init_state = torch.zeros(eng.state_floats, dtype=torch.float32, device=eng.device)
         self._captured = False
         self.seed_base = 0          # final-layer dropout: task k of this runner draws its masks from seed_base + k
@@ -80,46 +111,46 @@ class TaskRunner:
     def set_init_state(self, state: torch.Tensor) -> None:
         self.init_state.copy_(state)
 
-    def _task_args(self, slot: int) -> N.TaskArgs:
-        sb = self.slots[slot]
+    def _task_args(self, g: _Group) -> N.TaskArgs:
+        sb = self.slots[g.first]
         T, B, nq = self.T, self.B, self.nq
         dc = sb.floats[T:] if self.with_dc else None
         # the dropout seed is a staged device scalar: every graph replay draws fresh final-layer dropout masks
         return N.TaskArgs(_ptr(self.init_state), _ptr(sb.images), _ptr(sb.labels), _ptr(sb.ints[2:2 + T * B]),
                           _ptr(sb.floats[:T]), T, B, _ptr(sb.ints[2 + T * B:]), nq, _ptr(dc), 0,
                           float(self.pre_decay_rate), _ptr(sb.counts[:nq]), _ptr(sb.counts[nq:]), _ptr(sb.losses),
-                          _ptr(sb.ints[:2]))
+                          _ptr(sb.ints[:2]), g.size, self.eng.slot_stride if g.size > 1 else 0)
 
     def _capture(self) -> None:
         lib, h = self.eng.lib, self.eng.ctx.handle
-        for s, sb in enumerate(self.slots):
+        for sb in self.slots:
             # harmless defaults so that the warm-up run and the capture read valid indices
             sb.ints.zero_()
-            sb.floats.zero_()
+            if sb.n_f:
+                sb.floats.zero_()
             sb.images.zero_()
             sb.labels.zero_()
         torch.cuda.synchronize()
-        for s, sb in enumerate(self.slots):
-            a = self._task_args(s)
-            st = C.c_void_p(sb.stream.cuda_stream)
-            if s == 0:   # one eager warm-up sets function attributes before any capture
-                N.check(lib.mliis_adapt_eval_task(h, s, C.byref(a), st))
-                sb.stream.synchronize()
-            N.check(lib.mliis_task_graph_capture(h, s, C.byref(a), st))
+        for gi, g in enumerate(self.groups):
+            a = self._task_args(g)
+            st = C.c_void_p(g.stream.cuda_stream)
+            if gi == 0:   # one eager warm-up sets function attributes before any capture
+                N.check(lib.mliis_adapt_eval_task(h, g.first, C.byref(a), st))
+                g.stream.synchronize()
+            N.check(lib.mliis_task_graph_capture(h, g.first, C.byref(a), st))
         torch.cuda.synchronize()
         self._captured = True
 
-    def _launch(self, slot: int) -> None:
+    def _launch(self, g: _Group) -> None:
         lib, h = self.eng.lib, self.eng.ctx.handle
-        sb = self.slots[slot]
-        st = C.c_void_p(sb.stream.cuda_stream)
+        st = C.c_void_p(g.stream.cuda_stream)
         if self.use_graph:
-            N.check(lib.mliis_task_graph_launch(h, slot, st))
+            N.check(lib.mliis_task_graph_launch(h, g.first, st))
         else:
-            a = self._task_args(slot)
-            N.check(lib.mliis_adapt_eval_task(h, slot, C.byref(a), st))
+            a = self._task_args(g)
+            N.check(lib.mliis_adapt_eval_task(h, g.first, C.byref(a), st))
 
-    def _stage(self, slot: int, plan: TaskPlan) -> None:
+    def _stage(self, slot: int, plan: TaskPlan, stream) -> None:
         sb = self.slots[slot]
         T, B, nq = self.T, self.B, self.nq
         bi = np.asarray(plan.batch_index, np.int32).reshape(-1)
@@ -134,11 +165,12 @@ class TaskRunner:
         if self.with_dc:
             dc = plan.dc_mask if plan.dc_mask is not None else np.ones((T, self.eng.n_dc, B), np.float32)
             sb.h_floats[T:] = torch.from_numpy(np.asarray(dc, np.float32).reshape(-1))
-        with torch.cuda.stream(sb.stream):
+        with torch.cuda.stream(stream):
             h2d = 0
             if isinstance(plan.images, torch.Tensor) and plan.images.is_cuda:
-                sb.images.copy_(plan.images, non_blocking=True)     # resident pool: device-to-device
-                sb.labels.copy_(plan.labels, non_blocking=True)
+                n = plan.images.shape[0]
+                sb.images[:n].copy_(plan.images, non_blocking=True)     # resident pool: device-to-device
+                sb.labels[:n].copy_(plan.labels, non_blocking=True)
             else:
                 n = plan.images.shape[0]
                 sb.h_images[:n] = torch.from_numpy(np.ascontiguousarray(plan.images, np.float32))
@@ -147,38 +179,48 @@ class TaskRunner:
                 sb.labels[:n].copy_(sb.h_labels[:n], non_blocking=True)
                 h2d += sb.h_images[:n].numel() * 4 + sb.h_labels[:n].numel() * 4
             sb.ints.copy_(sb.h_ints, non_blocking=True)
-            sb.floats.copy_(sb.h_floats, non_blocking=True)
+            if sb.n_f:
+                sb.floats.copy_(sb.h_floats, non_blocking=True)
             h2d += sb.h_ints.numel() * 4 + sb.h_floats.numel() * 4
         self.h2d_bytes_per_task = h2d
         self.d2h_bytes_per_task = sb.h_counts.numel() * 4
 
-    def _collect(self, slot: int) -> Tuple[np.ndarray, np.ndarray]:
-        sb = self.slots[slot]
-        sb.done.synchronize()
-        c = sb.h_counts.numpy().copy()
-        sb.busy = False
-        return c[:self.nq].astype(np.int64), c[self.nq:].astype(np.int64)
+    def _collect(self, g: _Group, results) -> None:
+        g.done.synchronize()
+        for k, tag in enumerate(g.tags):
+            if tag is None:
+                continue
+            c = self.slots[g.first + k].h_counts.numpy().copy()
+            results[tag] = (c[:self.nq].astype(np.int64), c[self.nq:].astype(np.int64))
+        g.busy = False
 
     def run(self, plans: Sequence[TaskPlan]) -> List[Tuple[np.ndarray, np.ndarray]]:
         """Adapt + evaluate every plan; returns per task (intersection[n_query], union[n_query]) integer counts."""
         if self.use_graph and not self._captured:
             self._capture()
         results: List[Optional[Tuple[np.ndarray, np.ndarray]]] = [None] * len(plans)
-        ns = len(self.slots)
-        for i, plan in enumerate(plans):
-            s = i % ns
-            sb = self.slots[s]
-            if sb.busy:
-                results[sb.tag] = self._collect(s)
-            self._stage(s, plan)
-            self._launch(s)
-            with torch.cuda.stream(sb.stream):
-                sb.h_counts.copy_(sb.counts, non_blocking=True)
-                sb.done.record(sb.stream)
-            sb.busy, sb.tag = True, i
-        for s, sb in enumerate(self.slots):
-            if sb.busy:
-                results[sb.tag] = self._collect(s)
+        G, ng = self.group, len(self.groups)
+        for ci, i0 in enumerate(range(0, len(plans), G)):
+            g = self.groups[ci % ng]
+            if g.busy:
+                self._collect(g, results)
+            g.tags = []
+            for k in range(G):
+                i = i0 + k
+                # a short last chunk re-runs the previous plan in the idle slots of the group (result discarded)
+                plan = plans[i] if i < len(plans) else plans[len(plans) - 1]
+                self._stage(g.first + k, plan, g.stream)
+                g.tags.append(i if i < len(plans) else None)
+            self._launch(g)
+            with torch.cuda.stream(g.stream):
+                for k in range(G):
+                    sb = self.slots[g.first + k]
+                    sb.h_counts.copy_(sb.counts, non_blocking=True)
+                g.done.record(g.stream)
+            g.busy = True
+        for g in self.groups:
+            if g.busy:
+                self._collect(g, results)
         return results  # type: ignore
 
 
