@@ -238,6 +238,27 @@ int mliis_delta_accumulate(mliis_ctx* ctx, float* dev_delta_sum, const float* de
                            const float* dev_theta_b, int32_t first /* 1: overwrite */, void* stream);
 int mliis_meta_apply(mliis_ctx* ctx, float* dev_theta, const float* dev_delta_sum, float scale, void* stream);
 
+/* ---- the ONE exchange step of a meta-update when tasks are sharded over GPUs ----------------
+ * Replaces the host-side np.mean over per-task variable lists (meta_learners/variables.py:16-23 called at
+ * reptile.py:124, :646) across processes.  The exchanged buffer is
+ *   [ sum of this rank's task deltas (mliis_theta_floats) | sum of its slots' BN moving statistics (2*n_bn) |
+ *     number of contributing slots | 3 pad ]                                  = mliis_meta_buffer_floats() floats.
+ * mliis_meta_reduce builds it from n_rows per-slot delta sums (rows row_stride floats apart) and the BN statistics of
+ * slots first_slot.. ; mliis_allreduce_delta is ONE ncclAllReduce(sum) over NVLink (a no-op without a communicator);
+ * mliis_meta_finish applies theta += scale * delta_sum and writes the contributor-averaged BN statistics into n_slots
+ * slots.  Adam slots stay rank-local (documented semantics of SURVEY 8e; exact for --sgd).
+ * The communicator lives in the ctx: rank 0 calls mliis_comm_unique_id, the host broadcasts the 128 bytes over its own
+ * control plane (torch.distributed, MPI, a file), every rank calls mliis_comm_init.  NCCL is bound with dlopen. */
+int64_t mliis_meta_buffer_floats(const mliis_ctx* ctx);
+int mliis_comm_unique_id(uint8_t* out_id_128_bytes);
+int mliis_comm_init(mliis_ctx* ctx, const uint8_t* id_128_bytes, int32_t rank, int32_t world);
+int mliis_comm_destroy(mliis_ctx* ctx);
+int mliis_allreduce_delta(mliis_ctx* ctx, float* dev_buf, int64_t count, void* stream);
+int mliis_meta_reduce(mliis_ctx* ctx, float* dev_buf, const float* dev_delta_rows, int64_t row_stride_floats,
+                      int32_t first_slot, int32_t n_rows, void* stream);
+int mliis_meta_finish(mliis_ctx* ctx, float* dev_theta, const float* dev_buf, float scale, int32_t first_slot,
+                      int32_t n_slots, void* stream);
+
 /* ---- per-kernel entry points (unit tests / micro-benchmarks) --------------------------------- */
 int mliis_dwconv_fwd(const float* dev_x, const float* dev_w, float* dev_y, int32_t B, int32_t H, int32_t W,
                      int32_t C, int32_t k, int32_t stride, const float* dev_bn_a, const float* dev_bn_b,

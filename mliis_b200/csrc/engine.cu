@@ -4,6 +4,7 @@
 //
 // Reference call sites replaced: see include/mliis_b200.h.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cmath>
 #include <cstdarg>
@@ -34,8 +35,13 @@ bool skip_launch(const char* launcher) {
     const char* e = strchr(p, ',');
     const size_t n = e ? (size_t)(e - p) : strlen(p);
     if (n > 0) {
-      const std::string tok(p, n);
-      if (strstr(launcher, tok.c_str())) return true;
+      std::string tok(p, n);
+      if (tok.back() == '$') {        // "name$" = exact launcher name ("tc_conv$" does not match tc_conv3)
+        tok.pop_back();
+        if (tok == launcher) return true;
+      } else if (strstr(launcher, tok.c_str())) {
+        return true;
+      }
     }
     p += n + (e ? 1 : 0);
   }
@@ -81,7 +87,23 @@ struct Tab {
 
 }  // namespace
 
+// NCCL is bound at run time (dlopen): the library has no link-time dependency on it and single-GPU users never load
+// it.  Only the five entry points of the meta-update exchange are used.
+struct NcclId { char internal[128]; };     // ncclUniqueId
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /* ncclUniqueId by value: */ NcclId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+
 struct mliis_ctx {
+  void* nccl_comm = nullptr;     // ncclComm_t of the meta-update exchange (mliis_comm_init); null = single process
+  int comm_rank = 0, comm_world = 1;
   bool group_fallback = false;   // a task-batched call reached a kernel that only serves one slot (fp32 FFMA GEMMs)
   mliis_config cfg;
   Plan plan;
@@ -752,6 +774,7 @@ int mliis_ctx_destroy(mliis_ctx* ctx) {
     if (sl.graph) cudaGraphDestroy(sl.graph);
   }
   for (void* p : ctx->owned) cudaFree(p);
+  if (ctx->nccl_comm) mliis_comm_destroy(ctx);
   delete ctx;
   return MLIIS_OK;
 }
@@ -1051,6 +1074,151 @@ int mliis_meta_apply(mliis_ctx* ctx, float* theta, const float* dsum, float scal
   if (ctx->device < 0) return fail(MLIIS_ERR_DEVICE, "table-only ctx");
   meta_apply(theta, dsum, scale, ctx->plan.n_theta, (cudaStream_t)stream);
   return check_cuda("meta_apply");
+}
+
+// ---- meta-update exchange: [sum of task deltas | BN moving statistics | #contributors] ----
+namespace {
+struct RowPtrs { const float* p[32]; };
+// out[i] = sum_r rows[r][i] (i < P) ; out[P + j] = sum_r bn_r[j] (j < 2 n_bn) ; out[P + 2 n_bn] = n_rows
+__global__ void meta_reduce_kernel(float* __restrict__ out, RowPtrs dsum, RowPtrs bn, int n_rows, int64_t P, int64_t nbn2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P) {
+    float s = 0.f;
+    for (int r = 0; r < n_rows; ++r) s += dsum.p[r][i];
+    out[i] = s;
+  } else if (i < P + nbn2) {
+    float s = 0.f;
+    for (int r = 0; r < n_rows; ++r) s += bn.p[r][i - P];
+    out[i] = s;
+  } else if (i == P + nbn2) {
+    out[i] = (float)n_rows;
+  }
+}
+// theta += scale * buf[:P] ; every listed slot's BN statistics <- buf[P:P+2 n_bn] / buf[P + 2 n_bn]
+struct WPtrs { float* p[32]; };
+__global__ void meta_finish_kernel(float* __restrict__ theta, const float* __restrict__ buf, float scale, WPtrs bn,
+                                   int n_slots, int64_t P, int64_t nbn2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P) {
+    theta[i] = fmaf(scale, buf[i], theta[i]);
+  } else if (i < P + nbn2) {
+    const float cnt = buf[P + nbn2];
+    if (cnt > 0.f) {
+      const float v = buf[i] / cnt;
+      for (int s = 0; s < n_slots; ++s) bn.p[s][i - P] = v;
+    }
+  }
+}
+
+NcclApi& nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);      // the copy torch.distributed already loaded, if any
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (h) {
+      api.lib = h;
+      api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+      api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+      api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+      if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce) api.lib = nullptr;
+    }
+  }
+  return api;
+}
+}  // namespace
+
+int64_t mliis_meta_buffer_floats(const mliis_ctx* c) {
+  return c ? c->plan.n_theta + 2 * (int64_t)c->plan.n_bn_ch + 4 : -1;
+}
+
+int mliis_comm_unique_id(uint8_t* out128) {
+  if (!out128) return fail(MLIIS_ERR_ARG, "null argument");
+  NcclApi& n = nccl();
+  if (!n.lib) return fail(MLIIS_ERR_STATE, "libnccl.so.2 not found");
+  NcclId id;
+  int rc = n.GetUniqueId(&id);
+  if (rc) return fail(MLIIS_ERR_CUDA, "ncclGetUniqueId: %s", n.GetErrorString ? n.GetErrorString(rc) : "?");
+  memcpy(out128, id.internal, 128);
+  return MLIIS_OK;
+}
+
+int mliis_comm_init(mliis_ctx* ctx, const uint8_t* id128, int32_t rank, int32_t world) {
+  if (!ctx || !id128) return fail(MLIIS_ERR_ARG, "null argument");
+  if (ctx->device < 0) return fail(MLIIS_ERR_DEVICE, "table-only ctx (no sm_100 device): there is no CPU fallback");
+  if (world < 1 || rank < 0 || rank >= world) return fail(MLIIS_ERR_ARG, "bad rank / world");
+  if (ctx->nccl_comm) return fail(MLIIS_ERR_STATE, "communicator already initialised");
+  if (world == 1) { ctx->comm_rank = 0; ctx->comm_world = 1; return MLIIS_OK; }
+  NcclApi& n = nccl();
+  if (!n.lib) return fail(MLIIS_ERR_STATE, "libnccl.so.2 not found");
+  NcclId id;
+  memcpy(id.internal, id128, 128);
+  cudaSetDevice(ctx->device);
+  int rc = n.CommInitRank(&ctx->nccl_comm, world, id, rank);
+  if (rc) { ctx->nccl_comm = nullptr; return fail(MLIIS_ERR_CUDA, "ncclCommInitRank: %s", n.GetErrorString ? n.GetErrorString(rc) : "?"); }
+  ctx->comm_rank = rank;
+  ctx->comm_world = world;
+  return MLIIS_OK;
+}
+
+int mliis_comm_destroy(mliis_ctx* ctx) {
+  if (!ctx) return MLIIS_OK;
+  if (ctx->nccl_comm) { nccl().CommDestroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
+  ctx->comm_world = 1;
+  ctx->comm_rank = 0;
+  return MLIIS_OK;
+}
+
+int mliis_allreduce_delta(mliis_ctx* ctx, float* buf, int64_t count, void* stream) {
+  if (!ctx || !buf) return fail(MLIIS_ERR_ARG, "null argument");
+  if (ctx->device < 0) return fail(MLIIS_ERR_DEVICE, "table-only ctx");
+  if (count < 0) return fail(MLIIS_ERR_ARG, "count < 0");
+  if (!ctx->nccl_comm) return MLIIS_OK;            // single process: the local sum is the global sum
+  int rc = nccl().AllReduce(buf, buf, (size_t)count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, ctx->nccl_comm, (cudaStream_t)stream);
+  if (rc) return fail(MLIIS_ERR_CUDA, "ncclAllReduce: %s", nccl().GetErrorString ? nccl().GetErrorString(rc) : "?");
+  return MLIIS_OK;
+}
+
+int mliis_meta_reduce(mliis_ctx* ctx, float* buf, const float* dsum_rows, int64_t row_stride, int32_t first_slot,
+                      int32_t n_rows, void* stream) {
+  if (!ctx || !buf) return fail(MLIIS_ERR_ARG, "null argument");
+  if (ctx->device < 0) return fail(MLIIS_ERR_DEVICE, "table-only ctx");
+  if (n_rows < 0 || n_rows > 32) return fail(MLIIS_ERR_ARG, "n_rows must be in [0, 32]");
+  if (n_rows > 0 && !dsum_rows) return fail(MLIIS_ERR_ARG, "null rows");
+  if (first_slot < 0 || first_slot + n_rows > (int)ctx->slots.size()) return fail(MLIIS_ERR_ARG, "slot range");
+  const Plan& p = ctx->plan;
+  RowPtrs d{}, b{};
+  for (int r = 0; r < n_rows; ++r) {
+    if (!ctx->slots[first_slot + r].state) return fail(MLIIS_ERR_STATE, "slot %d not bound", first_slot + r);
+    d.p[r] = dsum_rows + (size_t)r * row_stride;
+    b.p[r] = ctx->slots[first_slot + r].state + p.n_theta;
+  }
+  const int64_t n = p.n_theta + 2 * (int64_t)p.n_bn_ch + 1;
+  MLIIS_COUNT(), meta_reduce_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, (cudaStream_t)stream>>>(buf, d, b, n_rows, p.n_theta,
+                                                                                               2 * (int64_t)p.n_bn_ch);
+  return check_cuda("meta_reduce");
+}
+
+int mliis_meta_finish(mliis_ctx* ctx, float* theta, const float* buf, float scale, int32_t first_slot, int32_t n_slots,
+                      void* stream) {
+  if (!ctx || !theta || !buf) return fail(MLIIS_ERR_ARG, "null argument");
+  if (ctx->device < 0) return fail(MLIIS_ERR_DEVICE, "table-only ctx");
+  if (n_slots < 0 || n_slots > 32 || first_slot < 0 || first_slot + n_slots > (int)ctx->slots.size())
+    return fail(MLIIS_ERR_ARG, "slot range");
+  const Plan& p = ctx->plan;
+  WPtrs b{};
+  for (int r = 0; r < n_slots; ++r) {
+    if (!ctx->slots[first_slot + r].state) return fail(MLIIS_ERR_STATE, "slot %d not bound", first_slot + r);
+    b.p[r] = ctx->slots[first_slot + r].state + p.n_theta;
+  }
+  const int64_t n = p.n_theta + 2 * (int64_t)p.n_bn_ch;
+  MLIIS_COUNT(), meta_finish_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, (cudaStream_t)stream>>>(theta, buf, scale, b, n_slots,
+                                                                                               p.n_theta, 2 * (int64_t)p.n_bn_ch);
+  return check_cuda("meta_finish");
 }
 
 // ---- per-kernel entry points ----

@@ -240,6 +240,43 @@ class Engine:
         N.check(self.lib.mliis_meta_apply(self.ctx.handle, _ptr(theta), _ptr(dsum), float(scale),
                                           self._stream(stream)))
 
+    # ---- the exchange step of a meta-update: ONE NCCL all-reduce through the C ABI ----
+    def init_comm(self) -> None:
+        """Creates the ctx's NCCL communicator when torch.distributed runs with world > 1 (torch.distributed is only
+        the control plane that carries the 128-byte unique id)."""
+        import torch.distributed as dist
+        if getattr(self, "_comm_ready", False):
+            return
+        self._comm_ready = True
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        rank, world = dist.get_rank(), dist.get_world_size()
+        buf = (C.c_uint8 * 128)()
+        if rank == 0:
+            N.check(self.lib.mliis_comm_unique_id(buf))
+        t = torch.tensor(list(buf), dtype=torch.uint8, device=self.device)
+        dist.broadcast(t, 0)
+        raw = (C.c_uint8 * 128)(*t.cpu().tolist())
+        N.check(self.lib.mliis_comm_init(self.ctx.handle, raw, rank, world))
+
+    def meta_buffer(self) -> torch.Tensor:
+        """[sum of task deltas | sum of BN moving statistics | #contributing slots | pad] (mliis_meta_buffer_floats)."""
+        n = int(self.lib.mliis_meta_buffer_floats(self.ctx.handle))
+        return torch.zeros(n, dtype=torch.float32, device=self.device)
+
+    def meta_reduce(self, buf: torch.Tensor, rows: Optional[torch.Tensor], row_stride: int, first_slot: int,
+                    n_rows: int, stream=None) -> None:
+        N.check(self.lib.mliis_meta_reduce(self.ctx.handle, _ptr(buf), _ptr(rows), int(row_stride), int(first_slot),
+                                           int(n_rows), self._stream(stream)))
+
+    def allreduce_delta(self, buf: torch.Tensor, stream=None) -> None:
+        N.check(self.lib.mliis_allreduce_delta(self.ctx.handle, _ptr(buf), buf.numel(), self._stream(stream)))
+
+    def meta_finish(self, theta: torch.Tensor, buf: torch.Tensor, scale: float, first_slot: int, n_slots: int,
+                    stream=None) -> None:
+        N.check(self.lib.mliis_meta_finish(self.ctx.handle, _ptr(theta), _ptr(buf), float(scale), int(first_slot),
+                                           int(n_slots), self._stream(stream)))
+
     # ---- debugging ----
     def debug_buffer(self, slot: int, name: str, batch: int) -> torch.Tensor:
         """Copy of a named activation buffer as [batch, rows_per_image, C] (tests only)."""

@@ -84,6 +84,13 @@ SYMBOLS = [
     ("mliis_launch_count", C.c_uint64, []),
     ("mliis_delta_accumulate", C.c_int, [_VP, _VP, _VP, _VP, _I32, _VP]),
     ("mliis_meta_apply", C.c_int, [_VP, _VP, _VP, _F, _VP]),
+    ("mliis_meta_buffer_floats", _I64, [_VP]),
+    ("mliis_comm_unique_id", C.c_int, [_VP]),
+    ("mliis_comm_init", C.c_int, [_VP, _VP, _I32, _I32]),
+    ("mliis_comm_destroy", C.c_int, [_VP]),
+    ("mliis_allreduce_delta", C.c_int, [_VP, _VP, _I64, _VP]),
+    ("mliis_meta_reduce", C.c_int, [_VP, _VP, _VP, _I64, _I32, _I32, _VP]),
+    ("mliis_meta_finish", C.c_int, [_VP, _VP, _VP, _F, _I32, _I32, _VP]),
     ("mliis_dwconv_fwd", C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP, _VP, _VP]),
     ("mliis_gemm_nn", C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP]),
     ("mliis_conv3x3_fwd", C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),

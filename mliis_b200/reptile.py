@@ -173,7 +173,12 @@ class Gecko:
                                           meta_step_size, meta_batch_size, lr_ph, lr, fomaml)
         theta = eng.theta(0)
         old = theta.clone()
-        dsum = torch.zeros_like(theta)
+        if world > 1:
+            eng.init_comm()
+        if getattr(self, "_meta_buf", None) is None:
+            self._meta_buf = eng.meta_buffer()
+        buf = self._meta_buf
+        dsum = buf[:eng.n_theta]                             # the delta sum is the head of the exchange buffer
         backup = torch.empty_like(theta) if fomaml else None
         n_local = 0
         for t in range(meta_batch_size):
@@ -196,16 +201,17 @@ class Gecko:
             eng.delta_accumulate(dsum, theta, backup if fomaml else old, first=(n_local == 0))
             n_local += 1
             theta.copy_(old)                                 # import_variables(old_vars): trainables only
-        from .runner import allreduce_meta
-        allreduce_meta(dsum, eng.bn_state(0))                # one all-reduce of P floats per meta-step
-        eng.meta_apply(theta, dsum, float(meta_step_size) / float(meta_batch_size))
+        # the ONE exchange step: [sum of deltas | BN statistics | count] -> ncclAllReduce -> theta += eps/M * sum
+        eng.meta_reduce(buf, dsum, eng.n_theta, 0, 1 if n_local else 0)
+        eng.allreduce_delta(buf)
+        eng.meta_finish(theta, buf, float(meta_step_size) / float(meta_batch_size), 0, 1)
 
     def _train_step_slots(self, dataset, num_shots, inner_batch_size, inner_iters, replacement, meta_step_size,
                           meta_batch_size, lr_ph, lr, fomaml: bool):
         """Slot-parallel meta-step: this rank's tasks are dealt round-robin to S task slots; every slot replays one
         CUDA graph per task (theta <- theta_old, the inner steps, delta accumulation) on its own stream."""
         import torch
-        from .runner import TrainSlots, allreduce_meta
+        from .runner import TrainSlots
         eng = self._model.engine()
         rank, world = _dist()
         plans = []
@@ -226,11 +232,20 @@ class Gecko:
             for i, (task, rows, batches) in enumerate(plans):
                 images, labels = task.arrays()
                 ts.submit(i % ts.n, images[:len(rows)], labels[:len(rows)], batches)
-            dsum = ts.finish()
+            buf = ts.finish()
+            n_write = ts.n
         else:
-            dsum = torch.zeros_like(eng.theta(0))
-        allreduce_meta(dsum, eng.bn_state(0))
-        eng.meta_apply(eng.theta(0), dsum, float(meta_step_size) / float(meta_batch_size))
+            if getattr(self, "_meta_buf", None) is None:
+                self._meta_buf = eng.meta_buffer()
+            buf = self._meta_buf
+            eng.meta_reduce(buf, None, eng.n_theta, 0, 0)     # this rank adapted no task of the meta-batch: zeros
+            ts, n_write = None, 1
+        if world > 1:
+            eng.init_comm()
+        eng.allreduce_delta(buf)                               # ONE ncclAllReduce over [deltas | BN statistics | count]
+        eng.meta_finish(eng.theta(0), buf, float(meta_step_size) / float(meta_batch_size), 0, n_write)
+        if ts is not None:
+            ts.save_states()
 
     def _fomaml_lrs(self, lr_ph, lr, n_batches):
         d = float(self._model.lr_ph.default)

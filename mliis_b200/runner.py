@@ -268,7 +268,9 @@ class TrainSlots:
         self.yp = [torch.empty(n_pool, S, S, 2, dtype=torch.float32).pin_memory() for _ in range(n)]
         self.idx = [[torch.zeros(b, dtype=torch.int32, device=dev) for b in batch_sizes] for _ in range(n)]
         self.idxp = [[torch.zeros(b, dtype=torch.int32).pin_memory() for b in batch_sizes] for _ in range(n)]
-        self.dsum = [torch.zeros(eng.n_theta, dtype=torch.float32, device=dev) for _ in range(n)]
+        self.dsum2d = torch.zeros(n, eng.n_theta, dtype=torch.float32, device=dev)     # per-slot delta sums (rows)
+        self.dsum = [self.dsum2d[s] for s in range(n)]
+        self.buf = eng.meta_buffer()                      # the exchanged buffer (mliis_meta_reduce / allreduce / finish)
         self.backup = [torch.empty(eng.n_theta, dtype=torch.float32, device=dev) if fomaml else None
                        for _ in range(n)]
         self.seed = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(n)]     # per-replay dropout seeds
@@ -349,29 +351,35 @@ class TrainSlots:
         self.used[s] = True
 
     def finish(self) -> torch.Tensor:
-        """sum of the slot deltas; BN moving statistics averaged over the slots that ran and written back to all;
-        the master trainables (slot 0) restored to theta_old."""
+        """Builds the exchange buffer of this rank on the current stream - [sum of the slot deltas | sum of the BN
+        moving statistics of the slots that ran | their count] (mliis_meta_reduce) - and restores the master
+        trainables (slot 0) to theta_old.  No host synchronisation, no torch arithmetic."""
         eng = self.eng
-        torch.cuda.synchronize()
-        used = [s for s in range(self.n) if self.used[s]]
-        total = self.dsum[used[0]].clone()
-        for s in used[1:]:
-            total.add_(self.dsum[s])
-        bn = torch.stack([eng.bn_state(s) for s in used]).mean(0)
+        cur = torch.cuda.current_stream()
+        n_used = 0
         for s in range(self.n):
-            eng.bn_state(s).copy_(bn)
+            if self.used[s]:
+                assert s == n_used, "slots are dealt round-robin from 0"
+                cur.wait_stream(self.streams[s])
+                n_used += 1
+        eng.meta_reduce(self.buf, self.dsum2d, eng.n_theta, 0, n_used)
         eng.theta(0).copy_(self.old)
+        return self.buf
+
+    def save_states(self) -> None:
+        """After mliis_meta_finish wrote the averaged BN statistics: remember the per-slot training state."""
+        eng = self.eng
         if self.n > 1:
             if self._saved is None:
                 self._saved = torch.empty(self.n - 1, eng.state_floats, dtype=torch.float32, device=eng.device)
             for s in range(1, self.n):
                 self._saved[s - 1].copy_(eng.states[s])
-        return total
 
 
 def allreduce_meta(delta_sum: torch.Tensor, bn_state: Optional[torch.Tensor] = None) -> None:
-    """The one exchange step of a meta-update: SUM of the per-rank task deltas (8.29 MB fp32) and, for world > 1,
-    the average of the BN moving statistics."""
+    """HOST-LOGIC reference of the exchange step (used by the CPU / gloo tests only): SUM of the per-rank task deltas
+    and the average of the BN moving statistics.  The GPU path does this with ONE ncclAllReduce
+    inside the C ABI: mliis_meta_reduce -> mliis_allreduce_delta -> mliis_meta_finish (Engine.allreduce_delta)."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return

@@ -48,6 +48,7 @@ def test_task_groups_are_bit_identical_to_single_slots(with_dc, dropout):
         torch.cuda.synchronize()
         out[G] = (res, eng.states.clone())
         # a short last chunk (6 plans on groups of 4) pads with a repeated plan and still returns every result
+        runner._tasks_staged = 0         # same staged dropout seeds as the first run
         res6 = runner.run(plans[:6])
         assert all(np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) for a, b in zip(res6, res[:6]))
     for G in (2, 4):
