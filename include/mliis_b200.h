@@ -284,6 +284,45 @@ int mliis_bilinear_fwd(const float* dev_x, float* dev_y, int32_t B, int32_t Hin,
 int mliis_adam_step(float* dev_theta, float* dev_v, const float* dev_grad, int64_t n, int64_t n_l2, float lr,
                     float beta2_power, float l2_coef, void* stream);
 
+/* Task-batched per-kernel calls: after mliis_kernel_group(n, stride) every per-kernel entry point called by this thread
+ * launches ONCE for n slot copies laid out `stride` bytes apart (all pointer arguments are slot 0's; n = 1 resets). */
+int mliis_kernel_group(int32_t n_group, int64_t group_stride_bytes);
+/* floats of scratch that is enough for any of the entry points below on a [B,H,W,C] tensor */
+int64_t mliis_kernel_scratch_floats(int32_t B, int32_t H, int32_t W, int32_t C);
+/* DepthwiseConv2dNative backward (efficientnet_model.py:190-196): dx and dw of y = dw(swish(bn_a*x+bn_b)) given dy */
+int mliis_dwconv_bwd(const float* dev_x, const float* dev_bn_a, const float* dev_bn_b, const float* dev_w,
+                     const float* dev_dy, float* dev_dx, float* dev_dw, float* dev_scratch, int32_t B, int32_t H, int32_t W,
+                     int32_t C, int32_t k, int32_t stride, void* stream);
+/* train-mode BatchNorm bookkeeping (models/efficientnet/utils.py:111-134; efficientlab.py:190): statistics of x [M,C]
+ * -> dev_stats = [mean | rstd | a = gamma*rstd | b = beta - mean*a], EMA of the moving statistics (fused=1: Bessel) */
+int mliis_bn_stats_fwd(const float* dev_x, const float* dev_gamma, const float* dev_beta, float* dev_moving_mean,
+                       float* dev_moving_var, float* dev_stats, float* dev_scratch, int32_t M, int32_t C, int32_t fused,
+                       void* stream);
+/* backward of swish(BN(x)) at the MBConv expand / stem sites: dgamma, dbeta, dx */
+int mliis_bn_swish_bwd(const float* dev_x, const float* dev_g, float* dev_dx, const float* dev_stats,
+                       const float* dev_gamma, float* dev_dgamma, float* dev_dbeta, float* dev_scratch, int32_t M,
+                       int32_t C, void* stream);
+/* squeeze-excite forward (efficientnet_model.py:238-251): gate [B,C] from the pre-BN depthwise output x [B,HW,C] */
+int mliis_se_fwd(const float* dev_x, const float* dev_bn_a, const float* dev_bn_b, const float* dev_w1,
+                 const float* dev_b1, const float* dev_w2, const float* dev_b2, float* dev_pool, float* dev_hidpre,
+                 float* dev_gate, float* dev_scratch, int32_t B, int32_t HW, int32_t C, int32_t Cr, void* stream);
+/* fused binary-head loss (efficientlab.py:294-327, :385-396): upsample, softmax-CE - ln(dice), IoU sums, d loss / d logits */
+int mliis_softmax_ce_iou(const float* dev_z_lo, const float* dev_labels, float* dev_p1, float* dev_dz_hi,
+                         float* dev_scratch, float* dev_loss_out, int32_t B, int32_t h, int32_t w, int32_t H, int32_t W,
+                         int32_t dice, float label_smoothing, void* stream);
+/* conv2d_2 of a residual skip decoder module with the image-pooling branch folded into a per-image, per-border-class
+ * bias (efficientlab.py:192-197, :220-224): operand over the first Cin of the Cs = Cin + Cp input channels */
+int mliis_tc_prep_weights_sub(const float* dev_w, float* dev_wt, int32_t taps, int32_t Cin, int32_t Cs, int32_t Cout,
+                              int32_t dgrad, int32_t mode, void* stream);
+int mliis_rsd_conv2_fwd(const float* dev_x, int32_t ldx, const float* dev_pooled, const float* dev_w_hwio,
+                        const float* dev_wt, const float* dev_bias, float* dev_bias9 /* [B,9,Cout] scratch */,
+                        float* dev_y, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cp, int32_t Cout, int32_t mode,
+                        void* stream);
+
+/* Measured tensor-pipe peak of the mode the dense kernels run in (tcgen05.mma kind::tf32, cta_group::1, M=128 N=256 K=8,
+ * operands resident in shared memory, no loads, every SM busy): the roofline denominator beside the bf16 cuBLAS one. */
+int mliis_tc_peak_tf32(int32_t iters, double* tflops_out, void* stream);
+
 /* ---- debugging: copy a named activation / gradient buffer of a slot (tests only) -------------- */
 int mliis_debug_buffer(mliis_ctx* ctx, int32_t slot, const char* name, const float** dev_ptr,
                        int64_t* rows_per_image, int32_t* channels, int32_t* ld);

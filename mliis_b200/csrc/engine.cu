@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -1240,10 +1241,22 @@ static int require_sm100() {
   return MLIIS_OK;
 }
 
+// Task-batched per-kernel calls: mliis_kernel_group(n, stride) makes every following per-kernel entry point of this
+// thread launch once for n slot copies laid out `stride` bytes apart (every pointer argument is slot 0's).
+static thread_local ZGroup t_kernel_group{1, 0};
+int mliis_kernel_group(int32_t n_group, int64_t group_stride_bytes) {
+  if (n_group < 1 || n_group > 1024) return fail(MLIIS_ERR_ARG, "n_group must be in [1, 1024]");
+  if (n_group > 1 && (group_stride_bytes <= 0 || (group_stride_bytes & 15))) return fail(MLIIS_ERR_ARG, "bad group stride");
+  t_kernel_group = ZGroup{n_group, n_group > 1 ? (long long)(group_stride_bytes / 4) : 0};
+  return MLIIS_OK;
+}
+#define KERNEL_GROUP() ZScope zscope_(t_kernel_group.nz, t_kernel_group.zs)
+
 int mliis_dwconv_fwd(const float* x, const float* w, float* y, int32_t B, int32_t H, int32_t W, int32_t C, int32_t k,
                      int32_t stride, const float* bn_a, const float* bn_b, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
+  KERNEL_GROUP();
   if ((k != 3 && k != 5) || (stride != 1 && stride != 2) || C % 4) return fail(MLIIS_ERR_ARG, "unsupported depthwise shape");
   int pt, pb;
   same_pad(H, k, stride, 1, &pt, &pb);
@@ -1300,6 +1313,7 @@ int mliis_tc_prep_weights(const float* w, float* wt, int32_t taps, int32_t Cin, 
                           int32_t mode, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
+  KERNEL_GROUP();
   if (mode == MLIIS_GEMM_FP32) return fail(MLIIS_ERR_ARG, "mode must be a tensor-core mode");
   tc_prep_weights(w, wt, taps, Cin, Cout, dgrad, mode == MLIIS_GEMM_TF32X3 ? 3 : 1, (cudaStream_t)stream);
   return check_cuda("tc_prep_weights");
@@ -1309,6 +1323,7 @@ int mliis_tc_conv(const float* x, const float* wt, const float* bias, float* y, 
                   int32_t Cin, int32_t Cout, int32_t taps, int32_t dilation, int32_t mode, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
+  KERNEL_GROUP();
   if (mode == MLIIS_GEMM_FP32 || (taps != 1 && taps != 9)) return fail(MLIIS_ERR_ARG, "bad mode / taps");
   const int conv = taps == 9;
   if (!tc_supported(conv, W, Cin, Cout)) return fail(MLIIS_ERR_ARG, "shape not supported by the tcgen05 path");
@@ -1353,6 +1368,7 @@ int mliis_adam_step(float* theta, float* v, const float* grad, int64_t n, int64_
                     float l2_coef, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
+  KERNEL_GROUP();
   float* tmp = nullptr;
   if (cudaMalloc(&tmp, 4 * sizeof(float)) != cudaSuccess) return fail(MLIIS_ERR_CUDA, "alloc");
   const float h[4] = {0.f, beta2_power, lr, 0.f};
@@ -1361,6 +1377,144 @@ int mliis_adam_step(float* theta, float* v, const float* grad, int64_t n, int64_
   cudaStreamSynchronize((cudaStream_t)stream);
   cudaFree(tmp);
   return check_cuda("adam_step");
+}
+
+// ---- HBM-bound kernels alone (unit tests / roofline micro-benchmarks) ----
+int64_t mliis_kernel_scratch_floats(int32_t B, int32_t H, int32_t W, int32_t C) {
+  // enough for any of the entry points below on a [B,H,W,C] tensor
+  int64_t n = (int64_t)rc_num_chunks(B * H * W, C) * 2 * C + 2 * 1024;
+  n = std::max<int64_t>(n, (int64_t)dw_wgrad_blocks(B, H, W, 1) * 25 * C);
+  n = std::max<int64_t>(n, (int64_t)B * rc_num_img_chunks(H * W, C) * C + (int64_t)B * 2 * C + 64);
+  n = std::max<int64_t>(n, (int64_t)B * 32 * 4 + 148 + 64);
+  return n + 1024;
+}
+
+int mliis_dwconv_bwd(const float* x, const float* bn_a, const float* bn_b, const float* w, const float* dy, float* dx,
+                     float* dw, float* scratch, int32_t B, int32_t H, int32_t W, int32_t C, int32_t k, int32_t stride,
+                     void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if ((k != 3 && k != 5) || (stride != 1 && stride != 2) || C % 4) return fail(MLIIS_ERR_ARG, "unsupported depthwise shape");
+  if (!x || !w || !dy || !dx || !dw || !scratch) return fail(MLIIS_ERR_ARG, "null argument");
+  KERNEL_GROUP();
+  int pt, pb, pl, pr;
+  same_pad(H, k, stride, 1, &pt, &pb);
+  same_pad(W, k, stride, 1, &pl, &pr);
+  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+  dw_bwd_weight(x, bn_a, bn_b, dy, scratch, dw, B, H, W, C, k, stride, Ho, Wo, pt, pl, (cudaStream_t)stream);
+  dw_bwd_data(dy, w, dx, B, H, W, C, k, stride, Ho, Wo, pt, pl, (cudaStream_t)stream);
+  return check_cuda("dwconv_bwd");
+}
+
+// train-mode BN forward bookkeeping of one layer: batch statistics of x [M,C] -> stats = [mean | rstd | a | b] (4*C),
+// EMA of the moving statistics (utils.py:111-134).  The normalise + swish itself is fused into the consumers.
+int mliis_bn_stats_fwd(const float* x, const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                       float* stats, float* scratch, int32_t M, int32_t C, int32_t fused, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (C % 4 || C > 1024 || M < 2) return fail(MLIIS_ERR_ARG, "C must be a multiple of 4 and <= 1024");
+  if (!x || !gamma || !beta || !moving_mean || !moving_var || !stats || !scratch) return fail(MLIIS_ERR_ARG, "null argument");
+  KERNEL_GROUP();
+  bn_stats(x, C, M, C, false, scratch, (cudaStream_t)stream);
+  bn_finalize(scratch, rc_num_chunks(M, C), C, M, gamma, beta, moving_mean, moving_var, 1, fused, stats, stats + C,
+              stats + 2 * C, stats + 3 * C, (cudaStream_t)stream);
+  return check_cuda("bn_stats_fwd");
+}
+
+// backward of y = swish(BN(x)) (the MBConv expand / stem sites): dgamma, dbeta, dx   (reduce + finalize + apply)
+int mliis_bn_swish_bwd(const float* x, const float* g, float* dx, const float* stats, const float* gamma, float* dgamma,
+                       float* dbeta, float* scratch, int32_t M, int32_t C, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (C % 4 || C > 1024) return fail(MLIIS_ERR_ARG, "C must be a multiple of 4 and <= 1024");
+  if (!x || !g || !dx || !stats || !gamma || !dgamma || !dbeta || !scratch) return fail(MLIIS_ERR_ARG, "null argument");
+  KERNEL_GROUP();
+  BnBwdArgs a{};
+  a.x = x; a.ldx = C; a.g = g; a.ldg = C; a.dx = dx; a.lddx = C; a.M = M; a.C = C; a.HW = M;
+  a.mean = stats; a.rstd = stats + C; a.a = stats + 2 * C; a.b = stats + 3 * C; a.gamma = gamma;
+  a.partials = scratch; a.k = scratch + (size_t)rc_num_chunks(M, C) * 2 * C; a.dgamma = dgamma; a.dbeta = dbeta;
+  bn_bwd(BN_SWISH, a, (cudaStream_t)stream);
+  return check_cuda("bn_swish_bwd");
+}
+
+// squeeze-excite forward (efficientnet_model.py:238-251) on the pre-BN depthwise output x [B,HW,C]: pooled
+// swish(a*x+b) -> FC -> swish -> FC -> sigmoid = gate [B,C] (the multiply lives in the project conv's loader)
+int mliis_se_fwd(const float* x, const float* bn_a, const float* bn_b, const float* w1, const float* b1, const float* w2,
+                 const float* b2, float* pool, float* hidpre, float* gate, float* scratch, int32_t B, int32_t HW,
+                 int32_t C, int32_t Cr, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (C % 4 || C > 1024 || Cr < 1) return fail(MLIIS_ERR_ARG, "bad SE shape");
+  if (!x || !bn_a || !bn_b || !w1 || !b1 || !w2 || !b2 || !pool || !hidpre || !gate || !scratch) return fail(MLIIS_ERR_ARG, "null argument");
+  KERNEL_GROUP();
+  se_pool(x, C, bn_a, bn_b, B, HW, C, scratch, (cudaStream_t)stream);
+  se_fc_fwd(scratch, rc_num_img_chunks(HW, C), B, HW, C, Cr, w1, b1, w2, b2, pool, hidpre, gate, (cudaStream_t)stream);
+  return check_cuda("se_fwd");
+}
+
+// fused loss of the binary head (efficientlab.py:294-327): bilinear upsample of the low-res logits, softmax-CE
+// (+ label smoothing) - ln(dice), per-image soft-IoU sums, and the gradient w.r.t. the FULL-resolution logits.
+int mliis_softmax_ce_iou(const float* z_lo, const float* labels, float* p1, float* dz_hi, float* scratch, float* loss_out,
+                         int32_t B, int32_t h, int32_t w, int32_t H, int32_t W, int32_t dice, float label_smoothing,
+                         void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (!z_lo || !labels || !p1 || !dz_hi || !scratch) return fail(MLIIS_ERR_ARG, "null argument");
+  static std::vector<std::pair<std::pair<int, int>, Tab>> cache;     // resize tables per (in, out), kept for the process
+  auto tab = [&](int n_in, int n_out) -> const Tab* {
+    for (auto& e : cache) if (e.first == std::make_pair(n_in, n_out)) return &e.second;
+    Tab t;
+    if (!make_tab(nullptr, n_in, n_out, &t)) return nullptr;
+    cache.push_back({{n_in, n_out}, t});
+    return &cache.back().second;
+  };
+  const Tab* ty = tab(h, H);
+  const Tab* tx = tab(w, W);
+  if (!ty || !tx) return fail(MLIIS_ERR_CUDA, "table alloc");
+  KERNEL_GROUP();
+  LossArgs la{};
+  la.z_lo = z_lo; la.labels = labels; la.index = nullptr; la.B = B; la.h = h; la.w = w; la.H = H; la.W = W;
+  la.ty = ty->rt(); la.tx = tx->rt(); la.dice = dice; la.label_smoothing = label_smoothing;
+  la.p1 = p1; la.partials = scratch; la.coef = scratch + (size_t)B * 32 * 4 + 148 + 64; la.dz_hi = dz_hi; la.loss_out = loss_out;
+  la.theta = nullptr; la.n_l2 = 0; la.l2_coef = 0.f;
+  loss_fwd_bwd(la, (cudaStream_t)stream);
+  return check_cuda("softmax_ce_iou");
+}
+
+// conv2d_2 of an RSD module with the image-pooling branch FOLDED (k_pool.cu): y = conv3x3(x[:, :Cin]) + bias +
+// bias9[img][border class], bias9 from pooled [B,Cp] and the kernel rows Cin..Cin+Cp of every tap.  dev_wt: the
+// operand prepared by mliis_tc_prep_weights_sub (first Cin of the Cin+Cp input channels).  Two launches.
+int mliis_tc_prep_weights_sub(const float* w, float* wt, int32_t taps, int32_t Cin, int32_t Cs, int32_t Cout, int32_t dgrad,
+                              int32_t mode, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (mode == MLIIS_GEMM_FP32 || Cs < Cin) return fail(MLIIS_ERR_ARG, "bad mode / Cs");
+  KERNEL_GROUP();
+  tc_prep_weights(w, wt, taps, Cin, Cout, dgrad, mode == MLIIS_GEMM_TF32X3 ? 3 : 1, (cudaStream_t)stream, Cs);
+  return check_cuda("tc_prep_weights_sub");
+}
+int mliis_rsd_conv2_fwd(const float* x, int32_t ldx, const float* pooled, const float* w_hwio, const float* wt,
+                        const float* bias, float* bias9, float* y, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cp,
+                        int32_t Cout, int32_t mode, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (mode == MLIIS_GEMM_FP32) return fail(MLIIS_ERR_ARG, "mode must be a tensor-core mode");
+  if (!x || !pooled || !w_hwio || !wt || !bias9 || !y) return fail(MLIIS_ERR_ARG, "null argument");
+  if (Cin % 4 || Cout % 4 || ldx % 4 || H < 2 || W < 2) return fail(MLIIS_ERR_ARG, "bad shape");
+  KERNEL_GROUP();
+  pool_bias9(pooled, Cp, w_hwio, Cin + Cp, Cin, Cp, Cout, B, bias9, (cudaStream_t)stream);
+  if (!tc_conv(x, ldx, wt, bias, y, Cout, 1, B * H * W, B, H, W, Cin, 9, 1, Cout, 0, mode == MLIIS_GEMM_TF32X3 ? 3 : 1,
+               (cudaStream_t)stream, nullptr, nullptr, nullptr, 0, bias9))
+    return fail(MLIIS_ERR_ARG, "shape not supported by the folded tcgen05 path");
+  return check_cuda("rsd_conv2_fwd");
+}
+
+int mliis_tc_peak_tf32(int32_t iters, double* tflops_out, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (!tflops_out || iters < 1) return fail(MLIIS_ERR_ARG, "bad argument");
+  *tflops_out = tc_peak_tf32(iters, (cudaStream_t)stream);
+  return check_cuda("tc_peak_tf32");
 }
 
 int mliis_debug_buffer(mliis_ctx* ctx, int32_t slot, const char* name, const float** dev_ptr, int64_t* rows_per_image,

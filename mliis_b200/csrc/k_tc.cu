@@ -1251,6 +1251,74 @@ bool tc_wgrad(const float* A, int lda, const float* G, int ldg, float* dW, float
   return true;
 }
 
+// =================================================================================================
+// Tensor-pipe peak of the mode the convolutions run in: kind::tf32, M = 128, N = 256, K = 8, cta_group::1, operands
+// resident in shared memory, no loads, one CTA per SM issuing back to back.  The roofline denominator that belongs to
+// these kernels (MEASURED_PEAKS.json only has the cuBLAS bf16 number; TF32 is nominally half of it).
+// =================================================================================================
+__global__ void __launch_bounds__(128) tc_peak_kernel(int iters) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bar = base + 48 * 1024;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 48 * 1024 + 16);
+  for (int i = threadIdx.x; i < 48 * 1024 / 16; i += 128) reinterpret_cast<float4*>(smem)[i] = f4s(0.f);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+  if (warp == 0 && lane == 0) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t da = make_kmajor_sw128_desc(base), db = make_kmajor_sw128_desc(base + 16 * 1024);
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tc_mma_tf32(tmem_acc, da + 2 * k, db + 2 * k, idesc, (it | k) ? 1u : 0u);
+    tc_commit(bar);
+    mbar_wait(bar, 0);
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(256u) : "memory");
+  }
+}
+// returns the algorithmic TFLOP/s of `iters` x 4 MMAs per CTA on every SM (CUDA events around the launch, after a warm-up)
+double tc_peak_tf32(int iters, cudaStream_t s) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t smem = 48 * 1024 + 64 + 1024;
+  cudaFuncSetAttribute(tc_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, s);
+    MLIIS_COUNT(), tc_peak_kernel<<<sms, 128, smem, s>>>(iters);
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double flops = (double)sms * iters * 4.0 * 2.0 * 128 * 256 * 8;
+  return flops / (best * 1e-3) / 1e12;
+}
+
 // weights W[tap][ci][co] (HWIO) -> forward operand Wt[co][tap][ci]   or   dgrad operand Wt[ci][taps-1-tap][co],
 // rounded to nearest TF32; split == 3 also writes the residual plane lo = rn(w - hi) behind the hi plane.
 __device__ __forceinline__ void prep_one(const float* __restrict__ w, float* __restrict__ wt, int i, int n, int taps,

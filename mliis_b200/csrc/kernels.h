@@ -150,6 +150,9 @@ void tc_prep_weights(const float* w, float* wt, int taps, int Ci, int Co, int dg
 struct TcPrepJob { long long w_off, dst; int taps, Ci, Co, dgrad, split, Cs; };
 void tc_prep_all(const float* theta, float* wcache, const TcPrepJob* dev_jobs, int n_jobs, cudaStream_t s);
 
+// measured kind::tf32 cta_group::1 tensor-pipe peak (TFLOP/s): operands resident in shared memory, no loads
+double tc_peak_tf32(int iters, cudaStream_t s);
+
 // wgrad on tensor cores: dW[taps*C, N] = sum_pixels A[pixel+tap, c] * G[pixel, n]  (A, G channel-contiguous)
 bool tc_wgrad_supported(int conv, int W, int C, int N);
 size_t tc_wgrad_scratch(int conv, int M, int B, int H, int W, int C, int N, int taps);

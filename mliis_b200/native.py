@@ -99,6 +99,17 @@ SYMBOLS = [
     ("mliis_tc_wgrad", C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     ("mliis_bilinear_fwd", C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     ("mliis_adam_step", C.c_int, [_VP, _VP, _VP, _I64, _I64, _F, _F, _F, _VP]),
+    ("mliis_kernel_group", C.c_int, [_I32, _I64]),
+    ("mliis_kernel_scratch_floats", _I64, [_I32, _I32, _I32, _I32]),
+    ("mliis_dwconv_bwd", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
+    ("mliis_bn_stats_fwd", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP]),
+    ("mliis_bn_swish_bwd", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _VP]),
+    ("mliis_se_fwd", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP]),
+    ("mliis_softmax_ce_iou", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _F, _VP]),
+    ("mliis_tc_prep_weights_sub", C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
+    ("mliis_rsd_conv2_fwd", C.c_int, [_VP, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32,
+                                      _VP]),
+    ("mliis_tc_peak_tf32", C.c_int, [_I32, C.POINTER(C.c_double), _VP]),
     ("mliis_debug_buffer", C.c_int, [_VP, _I32, C.c_char_p, C.POINTER(_VP), C.POINTER(_I64), C.POINTER(_I32),
                                      C.POINTER(_I32)]),
 ]
