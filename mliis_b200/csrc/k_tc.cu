@@ -668,6 +668,245 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+// =================================================================================================
+// CTA-PAIR variant of tc_conv3_kernel (tcgen05 cta_group::2).  Round-1 finding: in 3xTF32 the 3x3 kernels are bound by
+// the MMA issue rate of ONE SM's tensor pipe at cta_group::1 (a 128 x 112 x 8 TF32 MMA retires in ~113 clk = half the
+// pipe's rate).  Here two CTAs of a cluster (two SMs of a TPC) form one MMA of M = 256: CTA r owns the accumulator rows
+// of ITS pixel tiles (its own A ring, its own TMEM) and loads only HALF of every weight tile (rows
+// [r*BN/2, (r+1)*BN/2) of the hi and lo planes) - the tensor pipes of both SMs read A from their own shared memory and
+// B from both.  The leader (cluster rank 0) issues every MMA; completion is multicast to the barriers of both CTAs.
+//   a_full (TMA -> transform, local) ; a_ready (256 arrivals on the LEADER's barrier: 128 local + 128 remote transform
+//   threads) ; b_full (TMA -> local) ; b_peer (the peer's relay thread -> leader: "my half of B slot sb has landed") ;
+//   a_empty / b_empty / tmem_full: tcgen05.commit.cta_group::2 ... multicast::cluster to both CTAs.
+// The wide-B trick (one N = 2*BN MMA for hi|lo) does not combine with the N split and is not used: 3 MMAs per k-step.
+// =================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait with cluster-scope acquire (the arrivals come from the peer CTA)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 26)) asm volatile("trap;");
+  }
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {     // arrives on `bar` of BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kC3Threads)
+tc_conv3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const float* __restrict__ bias, float* __restrict__ out, TcC3Params p, long long zs, int n_ctas) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const int slot = blockIdx.z;
+  { const size_t zo = (size_t)slot * zs; bias = zp(bias, zo); out += zo; p.bias9 = zp(p.bias9, zo); }
+  const uint32_t rank = cluster_ctarank();               // 0 = leader (issues the MMAs)
+  const int a_stage = 2 * p.a_slot_bytes;                // [hi][lo]
+  const int b_stage = 2 * p.b_plane_bytes;               // [hi][lo], BN/2 rows each
+  const uint32_t a_base = base, b_base = base + (uint32_t)p.SA * a_stage;
+  const uint32_t bar0 = b_base + (uint32_t)p.SB * b_stage;
+  uint8_t* bars_ptr = smem + (size_t)p.SA * a_stage + (size_t)p.SB * b_stage;
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_ready = [&](int s) { return bar0 + 8u * (p.SA + s); };
+  auto a_empty = [&](int s) { return bar0 + 8u * (2 * p.SA + s); };
+  auto b_full = [&](int s) { return bar0 + 8u * (3 * p.SA + s); };
+  auto b_empty = [&](int s) { return bar0 + 8u * (3 * p.SA + p.SB + s); };
+  auto b_peer = [&](int s) { return bar0 + 8u * (3 * p.SA + 2 * p.SB + s); };
+  const uint32_t tmem_full_bar = bar0 + 8u * (3 * p.SA + 3 * p.SB);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_ptr + 8 * (3 * p.SA + 3 * p.SB + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ncols = (uint32_t)p.ncols_alloc;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < p.SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_ready(s), 256); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.SB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); mbar_init(b_peer(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {     // one warp of EACH CTA of the pair takes part in the cta_group::2 allocation
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();          // barriers of both CTAs are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  // this CTA's pixel tiles (CTAs past the end of the problem load zero-filled boxes and store nothing)
+  const int cta = blockIdx.x;
+  const bool live = cta < n_ctas;
+  const int img = live ? cta / p.groups_per_image : 0;
+  const int y0 = live ? (cta - img * p.groups_per_image) * p.MT * p.BH : 0;
+  const int n0 = blockIdx.y * p.BN;
+  const int nh = p.BN / 2;                 // weight rows this CTA loads
+  const int KC = (p.C + 31) / 32;
+  const int NA = 3 * KC;                   // A stages: (dy, kc)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int ib = 0;
+      for (int ia = 0; ia < NA; ++ia) {
+        const int dy = ia / KC, kc = ia - dy * KC;
+        const int sa = ia % p.SA;
+        mbar_wait(a_empty(sa), ((ia / p.SA) & 1) ^ 1);
+        mbar_expect_tx(a_full(sa), (uint32_t)p.a_box_bytes);
+        // a CTA past the end reads image index B (out of bounds -> zero fill): it still feeds the pair's MMA
+        tma_load_5d(a_base + (uint32_t)sa * a_stage, &tmA, a_full(sa), kc * 32, -p.dil, y0 + (dy - 1) * p.dil,
+                    live ? img : 0x3fffffff, slot);
+        for (int dx = 0; dx < 3; ++dx, ++ib) {
+          const int sb = ib % p.SB;
+          mbar_wait(b_empty(sb), ((ib / p.SB) & 1) ^ 1);
+          mbar_expect_tx(b_full(sb), (uint32_t)b_stage);
+          const uint32_t dst = b_base + (uint32_t)sb * b_stage;
+          tma_load_5d(dst, &tmB, b_full(sb), kc * 32, dy * 3 + dx, n0 + (int)rank * nh, 0, slot);
+          tma_load_5d(dst + p.b_plane_bytes, &tmB, b_full(sb), kc * 32, dy * 3 + dx, n0 + (int)rank * nh, 1, slot);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ---------------- MMA issuer (leader) ----------------
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((256u >> 4) << 24);
+      int ib = 0;
+      for (int ia = 0; ia < NA; ++ia) {
+        const int kc = ia % KC;
+        const int sa = ia % p.SA;
+        mbar_wait_cluster(a_ready(sa), (ia / p.SA) & 1);
+        const int rem = p.C - kc * 32;
+        const int nk = rem >= 32 ? 4 : (rem + 7) / 8;
+        const uint32_t a_hi = a_base + (uint32_t)sa * a_stage, a_lo = a_hi + p.a_slot_bytes;
+        for (int dx = 0; dx < 3; ++dx, ++ib) {
+          const int sb = ib % p.SB;
+          mbar_wait(b_full(sb), (ib / p.SB) & 1);
+          mbar_wait_cluster(b_peer(sb), (ib / p.SB) & 1);
+          tc_fence_after();
+          const uint32_t b_hi = b_base + (uint32_t)sb * b_stage, b_lo = b_hi + p.b_plane_bytes;
+          const uint64_t db = make_kmajor_sw128_desc(b_hi), dbl = make_kmajor_sw128_desc(b_lo);
+          for (int t = 0; t < p.MT; ++t) {
+            const uint32_t row_off = (uint32_t)((t * p.BH * p.RW + dx * p.dil) * 128);
+            const uint64_t da = make_kmajor_sw128_desc(a_hi + row_off), dal = make_kmajor_sw128_desc(a_lo + row_off);
+            const uint32_t acc = tmem_acc + (uint32_t)(t * p.ncol_acc);
+            for (int k = 0; k < nk; ++k) {
+              const uint64_t adv = (uint64_t)(2 * k);
+              tc_mma_tf32_pair(acc, da + adv, db + adv, idesc, (ia | dx | k) ? 1u : 0u);
+              tc_mma_tf32_pair(acc, dal + adv, db + adv, idesc, 1u);
+              tc_mma_tf32_pair(acc, da + adv, dbl + adv, idesc, 1u);
+            }
+          }
+          tc_commit_pair(b_empty(sb));
+        }
+        tc_commit_pair(a_empty(sa));
+      }
+      tc_commit_pair(tmem_full_bar);
+    } else if (lane == 0) {
+      // ---------------- relay (peer): tell the leader when this CTA's half of a weight slot has landed ----------------
+      const int NB = 3 * NA;
+      for (int ib = 0; ib < NB; ++ib) {
+        const int sb = ib % p.SB;
+        mbar_wait(b_full(sb), (ib / p.SB) & 1);
+        mbar_arrive_remote(map_to_cta(b_peer(sb), 0));
+      }
+    }
+  } else {
+    const int t = threadIdx.x - 64;
+    const int n4 = p.a_box_bytes / 16;
+    for (int ia = 0; ia < NA; ++ia) {
+      const int sa = ia % p.SA;
+      mbar_wait(a_full(sa), (ia / p.SA) & 1);
+      float4* hi = reinterpret_cast<float4*>(smem + (size_t)sa * a_stage);
+      float4* lo = reinterpret_cast<float4*>(smem + (size_t)sa * a_stage + p.a_slot_bytes);
+      for (int i = t; i < n4; i += 128) {
+        const float4 v = hi[i];
+        const float4 h = rn_tf32_4(v);
+        hi[i] = h;
+        lo[i] = rn_tf32_4(v - h);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive_remote(map_to_cta(a_ready(sa), 0));      // the leader's barrier counts both CTAs' transform threads
+    }
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    mbar_wait_cluster(tmem_full_bar, 0);
+    tc_fence_after();
+    const int ly = r / p.RW, lx = r - ly * p.RW;
+    for (int tile = 0; tile < p.MT; ++tile) {
+      const int y = y0 + tile * p.BH + ly;
+      const bool valid = live && ly < p.BH && lx < p.W && y < p.H;
+      float* orow = out + (((size_t)img * p.H + y) * p.W + lx) * p.ldc;
+      const float* b9 = nullptr;
+      if (p.bias9) {
+        const int cls = (y < p.dil ? 0 : (y >= p.H - p.dil ? 2 : 1)) * 3 + (lx < p.dil ? 0 : (lx >= p.W - p.dil ? 2 : 1));
+        b9 = p.bias9 + ((size_t)img * 9 + cls) * p.N;
+      }
+      const uint32_t tbase = tmem_acc + (uint32_t)(tile * p.ncol_acc) + ((uint32_t)(quarter * 32) << 16);
+      for (int c = 0; c < p.BN; c += 16) {
+        uint32_t v[16];
+        __syncwarp();
+        tc_ld16(tbase + (uint32_t)c, v);
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int n = n0 + c + q * 4;
+            if (n < p.N) {
+              float4 o = f4(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
+                            __uint_as_float(v[q * 4 + 3]));
+              if (bias) o = o + ld4(bias + n);
+              if (b9) o = o + ld4(b9 + n);
+              if (p.accumulate) o = o + ld4(orow + n);
+              st4(orow + n, o);
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  // neither CTA may leave (or free its TMEM) while the pair's MMAs / multicast arrivals can still touch it
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(ncols) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -745,7 +984,11 @@ static bool tc_conv3(const float* A, int lda, const float* Wt, const float* bias
   const int box_rows = p.MT * p.BH * p.RW;
   if (box_rows > 256 || p.MT * p.BH > 256) return false;
   p.BN = tc_pick_bn(N);
-  p.wide = p.split == 3 && 2 * p.BN <= 256 && 2 * p.BN * p.MT <= 512 && !(dbg3 & 8);
+  // CTA pairs (cta_group::2, M = 256): 3xTF32 only (the kernel these layers are MMA-issue-bound in), even BN halves
+  static int pair_on = -1;
+  if (pair_on < 0) { const char* e = getenv("MLIIS_TC_PAIR"); pair_on = e ? atoi(e) : 0; }
+  const bool pair = pair_on && p.split == 3 && p.BN % 16 == 0 && !(dbg3 & 3);
+  p.wide = !pair && p.split == 3 && 2 * p.BN <= 256 && 2 * p.BN * p.MT <= 512 && !(dbg3 & 8);
   p.ncol_acc = p.wide ? 2 * p.BN : p.BN;
   p.ncols_alloc = 32;
   while (p.ncols_alloc < p.ncol_acc * p.MT) p.ncols_alloc <<= 1;
@@ -755,7 +998,7 @@ static bool tc_conv3(const float* A, int lda, const float* Wt, const float* bias
   int slot_rows = (p.MT - 1) * p.BH * p.RW + 2 * dil + 128;
   if (slot_rows < box_rows) slot_rows = box_rows;
   p.a_slot_bytes = (slot_rows * 128 + 1023) / 1024 * 1024;
-  p.b_plane_bytes = p.BN * 128;
+  p.b_plane_bytes = (pair ? p.BN / 2 : p.BN) * 128;
   const int planes = p.split == 3 ? 2 : 1;
   const int budget = 216 * 1024;
   p.SA = p.split == 3 ? 2 : 3;
@@ -774,17 +1017,34 @@ static bool tc_conv3(const float* A, int lda, const float* Wt, const float* bias
     cuuint64_t dims[5] = {(cuuint64_t)C, 9, (cuuint64_t)N, (cuuint64_t)planes, (cuuint64_t)MLIIS_NZ};
     cuuint64_t str[4] = {(cuuint64_t)C * 4, (cuuint64_t)9 * C * 4, (cuuint64_t)N * 9 * C * 4,
                          slot_stride_bytes((cuuint64_t)planes * N * 9 * C * 4)};
-    cuuint32_t box[5] = {32, 1, (cuuint32_t)p.BN, 1, 1};
+    cuuint32_t box[5] = {32, 1, (cuuint32_t)(pair ? p.BN / 2 : p.BN), 1, 1};
     if (!encode(&tmB, Wt, 5, dims, str, box)) return false;
   }
   const size_t smem = (size_t)p.SA * planes * p.a_slot_bytes + (size_t)p.SB * planes * p.b_plane_bytes +
-                      (3 * p.SA + 2 * p.SB + 2) * 8 + 1024;
+                      (3 * p.SA + 3 * p.SB + 2) * 8 + 1024;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_conv3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
-  dim3 grid(B * p.groups_per_image, (N + p.BN - 1) / p.BN, MLIIS_NZ);
+  const int n_ctas = B * p.groups_per_image;
+  if (pair) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((n_ctas + 1) / 2 * 2, (N + p.BN - 1) / p.BN, MLIIS_NZ);
+    cfg.blockDim = dim3(kC3Threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const long long zs = MLIIS_ZS;
+    MLIIS_COUNT(), cudaLaunchKernelEx(&cfg, tc_conv3_pair_kernel, tmA, tmB, bias, out, p, zs, n_ctas);
+    return true;
+  }
+  dim3 grid(n_ctas, (N + p.BN - 1) / p.BN, MLIIS_NZ);
   MLIIS_COUNT(), tc_conv3_kernel<<<grid, kC3Threads, smem, s>>>(tmA, tmB, bias, out, p, MLIIS_ZS);
   return true;
 }
