@@ -323,6 +323,12 @@ int mliis_rsd_conv2_fwd(const float* dev_x, int32_t ldx, const float* dev_pooled
  * operands resident in shared memory, no loads, every SM busy): the roofline denominator beside the bf16 cuBLAS one. */
 int mliis_tc_peak_tf32(int32_t iters, double* tflops_out, void* stream);
 
+/* Issue-rate microbenchmark of the MMA patterns the convolutions use: SM clocks per k-step (K = 8 of TF32) on one SM's
+ * tensor pipe with every SM busy.  pattern 0: one M=128 x N=n MMA; 1: the 3xTF32 pair (N=2n with A_hi, N=n with A_lo);
+ * 2: pattern 1 alternating between two accumulators; 3: three N=n MMAs.  shift_rows: A start shifted by 128-byte rows. */
+int mliis_tc_mma_rate(int32_t iters, int32_t n, int32_t pattern, int32_t shift_rows, double* clk_per_kstep_out,
+                      void* stream);
+
 /* ---- debugging: copy a named activation / gradient buffer of a slot (tests only) -------------- */
 int mliis_debug_buffer(mliis_ctx* ctx, int32_t slot, const char* name, const float** dev_ptr,
                        int64_t* rows_per_image, int32_t* channels, int32_t* ld);

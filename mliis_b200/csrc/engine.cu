@@ -1368,14 +1368,10 @@ int mliis_adam_step(float* theta, float* v, const float* grad, int64_t n, int64_
                     float l2_coef, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
+  if (!theta || !v || !grad || n < 1) return fail(MLIIS_ERR_ARG, "bad argument");
+  if (((uintptr_t)theta | (uintptr_t)v | (uintptr_t)grad) & 15) return fail(MLIIS_ERR_ARG, "buffers must be 16-byte aligned");
   KERNEL_GROUP();
-  float* tmp = nullptr;
-  if (cudaMalloc(&tmp, 4 * sizeof(float)) != cudaSuccess) return fail(MLIIS_ERR_CUDA, "alloc");
-  const float h[4] = {0.f, beta2_power, lr, 0.f};
-  cudaMemcpy(tmp, h, sizeof h, cudaMemcpyHostToDevice);
-  adam_step(theta, v, grad, n, n_l2, tmp + 2, tmp, l2_coef, 0, (cudaStream_t)stream);
-  cudaStreamSynchronize((cudaStream_t)stream);
-  cudaFree(tmp);
+  adam_step(theta, v, grad, n, n_l2, nullptr, nullptr, l2_coef, 0, (cudaStream_t)stream, lr, beta2_power);
   return check_cuda("adam_step");
 }
 
@@ -1515,6 +1511,16 @@ int mliis_tc_peak_tf32(int32_t iters, double* tflops_out, void* stream) {
   if (!tflops_out || iters < 1) return fail(MLIIS_ERR_ARG, "bad argument");
   *tflops_out = tc_peak_tf32(iters, (cudaStream_t)stream);
   return check_cuda("tc_peak_tf32");
+}
+
+int mliis_tc_mma_rate(int32_t iters, int32_t n, int32_t pattern, int32_t shift_rows, double* clk_per_kstep_out, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (!clk_per_kstep_out || iters < 1) return fail(MLIIS_ERR_ARG, "bad argument");
+  const double v = tc_mma_rate(iters, n, pattern, shift_rows, (cudaStream_t)stream);
+  if (v < 0) return fail(MLIIS_ERR_ARG, "bad MMA shape / pattern");
+  *clk_per_kstep_out = v;
+  return check_cuda("tc_mma_rate");
 }
 
 int mliis_debug_buffer(mliis_ctx* ctx, int32_t slot, const char* name, const float** dev_ptr, int64_t* rows_per_image,

@@ -30,6 +30,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 
@@ -511,6 +512,9 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ncols = (uint32_t)p.ncols_alloc;
+  // MLIIS_TC_DEBUG bit 32: phase timestamps of CTA 0 (SM clocks since kernel entry), printed by each role's lane 0
+  const bool prof = (p.debug & 32) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  const long long t_entry = prof ? clock64() : 0;
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -538,24 +542,32 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0) {
     if (lane == 0) {
       int ib = 0;
+      long long w_a = 0, w_b = 0;
       for (int ia = 0; ia < NA; ++ia) {
         const int dy = ia / KC, kc = ia - dy * KC;
         const int sa = ia % p.SA;
+        long long t0 = prof ? clock64() : 0;
         mbar_wait(a_empty(sa), ((ia / p.SA) & 1) ^ 1);
+        if (prof) w_a += clock64() - t0;
         mbar_expect_tx(a_full(sa), (uint32_t)p.a_box_bytes);
         tma_load_5d(a_base + (uint32_t)sa * a_stage, &tmA, a_full(sa), kc * 32, -p.dil, y0 + (dy - 1) * p.dil, img, slot);
         for (int dx = 0; dx < 3; ++dx, ++ib) {
           const int sb = ib % p.SB;
+          t0 = prof ? clock64() : 0;
           mbar_wait(b_empty(sb), ((ib / p.SB) & 1) ^ 1);
+          if (prof) w_b += clock64() - t0;
           mbar_expect_tx(b_full(sb), (uint32_t)b_stage);
           const uint32_t dst = b_base + (uint32_t)sb * b_stage;
           tma_load_5d(dst, &tmB, b_full(sb), kc * 32, dy * 3 + dx, n0, 0, slot);
           if (x3) tma_load_5d(dst + p.b_plane_bytes, &tmB, b_full(sb), kc * 32, dy * 3 + dx, n0, 1, slot);
         }
       }
+      if (prof) printf("[c3 producer] NA %d SA %d SB %d | done issuing at %lld | waited a_empty %lld b_empty %lld\n", NA, p.SA,
+                       p.SB, clock64() - t_entry, w_a, w_b);
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      long long w_a = 0, w_b = 0, t_first = 0;
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
       // wide: the hi and lo weight planes sit back to back in the B slot, so one N = 2*BN MMA forms a_hi*b_hi and
       // a_hi*b_lo in adjacent accumulator column ranges (A is fetched from shared memory once for both products)
@@ -564,13 +576,17 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int ia = 0; ia < NA; ++ia) {
         const int kc = ia % KC;
         const int sa = ia % p.SA;
+        long long t0 = prof ? clock64() : 0;
         mbar_wait(x3 ? a_ready(sa) : a_full(sa), (ia / p.SA) & 1);
+        if (prof) { const long long t1 = clock64(); if (ia == 0) t_first = t1 - t_entry; else w_a += t1 - t0; }
         const int rem = p.C - kc * 32;
         const int nk = rem >= 32 ? 4 : (rem + 7) / 8;
         const uint32_t a_hi = a_base + (uint32_t)sa * a_stage, a_lo = a_hi + p.a_slot_bytes;
         for (int dx = 0; dx < 3; ++dx, ++ib) {
           const int sb = ib % p.SB;
+          t0 = prof ? clock64() : 0;
           mbar_wait(b_full(sb), (ib / p.SB) & 1);
+          if (prof) w_b += clock64() - t0;
           tc_fence_after();
           const uint32_t b_hi = b_base + (uint32_t)sb * b_stage, b_lo = b_hi + p.b_plane_bytes;
           const uint64_t db = make_kmajor_sw128_desc(b_hi), dbl = make_kmajor_sw128_desc(b_lo);
@@ -598,14 +614,23 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_commit(a_empty(sa));
       }
       tc_commit(tmem_full_bar);
+      if (prof) {
+        const long long t_iss = clock64() - t_entry;
+        mbar_wait(tmem_full_bar, 0);
+        printf("[c3 mma] first a_ready at %lld | all issued at %lld | accumulators complete at %lld | waited a_ready %lld "
+               "b_full %lld (after the first stage)\n", t_first, t_iss, clock64() - t_entry, w_a, w_b);
+      }
     }
   } else {
     const int t = threadIdx.x - 64;
+    long long w_x = 0, t_x = 0;
     if (x3) {
       const int n4 = p.a_box_bytes / 16;
       for (int ia = 0; ia < NA; ++ia) {
         const int sa = ia % p.SA;
+        const long long t0 = prof ? clock64() : 0;
         mbar_wait(a_full(sa), (ia / p.SA) & 1);
+        const long long t1 = prof ? clock64() : 0;
         float4* hi = reinterpret_cast<float4*>(smem + (size_t)sa * a_stage);
         float4* lo = reinterpret_cast<float4*>(smem + (size_t)sa * a_stage + p.a_slot_bytes);
         for (int i = t; i < n4 && !(p.debug & 1); i += 128) {
@@ -616,12 +641,15 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(a_ready(sa));
+        if (prof) { w_x += t1 - t0; t_x += clock64() - t1; }
       }
     }
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
+    const long long t_w0 = prof ? clock64() : 0;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    const long long t_e0 = prof ? clock64() : 0;
     const int ly = r / p.RW, lx = r - ly * p.RW;
     for (int tile = 0; tile < p.MT; ++tile) {
       const int y = y0 + tile * p.BH + ly;
@@ -659,6 +687,9 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
+    if (prof && t == 0)
+      printf("[c3 xform/epilogue] transform: waited a_full %lld, worked %lld | waited for the accumulators %lld | epilogue "
+             "%lld .. %lld (%lld clk)\n", w_x, t_x, t_e0 - t_w0, t_e0 - t_entry, clock64() - t_entry, clock64() - t_e0);
     tc_fence_before();
   }
   __syncthreads();
@@ -1577,6 +1608,91 @@ double tc_peak_tf32(int iters, cudaStream_t s) {
   cudaEventDestroy(e1);
   const double flops = (double)sms * iters * 4.0 * 2.0 * 128 * 256 * 8;
   return flops / (best * 1e-3) / 1e12;
+}
+
+// MMA issue-rate microbenchmark: what one SM's tensor pipe sustains for the instruction shapes the convolutions issue
+// (operands resident in shared memory, no loads, no transform).  pattern 0: one N = n MMA per k-step; 1: the 3xTF32
+// "wide" pair (N = 2n with A_hi, then N = n with A_lo, same accumulator range as tc_conv3_kernel); 2: pattern 1
+// alternating between two pixel tiles / accumulators (MT = 2); 3: three N = n MMAs per k-step.  shift_rows moves the A
+// descriptor start by whole 128-byte rows (the tap-shifted starts of tc_conv3_kernel).  Result: clocks per k-step.
+__global__ void __launch_bounds__(128) tc_rate_kernel(int iters, int n, int pattern, int shift_rows, float* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  constexpr int kA = 96 * 1024, kB = 64 * 1024;
+  const uint32_t bar = base + kA + kB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kA + kB + 16);
+  for (int i = threadIdx.x; i < (kA + kB) / 16; i += 128) reinterpret_cast<float4*>(smem)[i] = f4s(0.f);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+  if (warp == 0 && lane == 0) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc_w = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 2) << 17) | ((128u >> 4) << 24);
+    const uint32_t a_hi = base + (uint32_t)shift_rows * 128u, a_lo = a_hi + 48 * 1024;
+    const uint64_t db = make_kmajor_sw128_desc(base + kA), dbl = make_kmajor_sw128_desc(base + kA + 32 * 1024);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const int tile = pattern == 2 ? (it & 1) : 0;
+      const uint64_t da = make_kmajor_sw128_desc(a_hi + (uint32_t)tile * 16384u), dal = make_kmajor_sw128_desc(a_lo + (uint32_t)tile * 16384u);
+      const uint32_t acc = tmem_acc + (uint32_t)(tile * 256);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t adv = (uint64_t)(2 * k);
+        if (pattern == 0) {
+          tc_mma_tf32(acc, da + adv, db + adv, idesc, (it | k) ? 1u : 0u);
+        } else if (pattern == 3) {
+          tc_mma_tf32(acc, da + adv, db + adv, idesc, (it | k) ? 1u : 0u);
+          tc_mma_tf32(acc, dal + adv, db + adv, idesc, 1u);
+          tc_mma_tf32(acc, da + adv, dbl + adv, idesc, 1u);
+        } else {
+          tc_mma_tf32(acc, da + adv, db + adv, idesc_w, (it > 1 || k) ? 1u : 0u);
+          tc_mma_tf32(acc, dal + adv, db + adv, idesc, 1u);
+        }
+      }
+    }
+    tc_commit(bar);
+    mbar_wait(bar, 0);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = (float)((double)(t1 - t0) / ((double)iters * 4.0));
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(512u) : "memory");
+  }
+}
+// clocks per k-step (K = 8) of the given MMA pattern on every SM at once; < 0 on a bad argument
+double tc_mma_rate(int iters, int n, int pattern, int shift_rows, cudaStream_t s) {
+  if (n < 8 || n > 256 || (n & 7) || pattern < 0 || pattern > 3 || shift_rows < 0 || shift_rows > 64) return -1.0;
+  if ((pattern == 1 || pattern == 2) && 2 * n > 256) return -1.0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t smem = 160 * 1024 + 64 + 1024;
+  cudaFuncSetAttribute(tc_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  float* d = nullptr;
+  if (cudaMalloc(&d, sizeof(float)) != cudaSuccess) return -1.0;
+  float h = -1.f;
+  for (int rep = 0; rep < 2; ++rep) {
+    MLIIS_COUNT(), tc_rate_kernel<<<sms, 128, smem, s>>>(iters, n, pattern, shift_rows, d);
+    cudaStreamSynchronize(s);
+  }
+  cudaMemcpy(&h, d, sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return (double)h;
 }
 
 // weights W[tap][ci][co] (HWIO) -> forward operand Wt[co][tap][ci]   or   dgrad operand Wt[ci][taps-1-tap][co],

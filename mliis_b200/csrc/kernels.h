@@ -152,6 +152,7 @@ void tc_prep_all(const float* theta, float* wcache, const TcPrepJob* dev_jobs, i
 
 // measured kind::tf32 cta_group::1 tensor-pipe peak (TFLOP/s): operands resident in shared memory, no loads
 double tc_peak_tf32(int iters, cudaStream_t s);
+double tc_mma_rate(int iters, int n, int pattern, int shift_rows, cudaStream_t s);
 
 // wgrad on tensor cores: dW[taps*C, N] = sum_pixels A[pixel+tap, c] * G[pixel, n]  (A, G channel-contiguous)
 bool tc_wgrad_supported(int conv, int W, int C, int N);
@@ -234,7 +235,7 @@ void predict_mask_iou(const float* z_lo, const float* labels, const int32_t* ind
 // optimizer (ApplyAdam beta1=0 / ApplyGradientDescent) over the flat buffer; hyper = {b1p, b2p} device scalars
 void scale_buffer(float* x, int64_t n, float s, cudaStream_t st);
 void adam_step(float* theta, float* v, const float* g, int64_t n, int64_t n_l2, const float* lr_dev, float* powers,
-               float l2_coef, int sgd, cudaStream_t s);
+               float l2_coef, int sgd, cudaStream_t s, float lr_imm = 0.f, float b2p_imm = 0.f);
 void delta_accumulate(float* dsum, const float* a, const float* b, int64_t n, int first, cudaStream_t s);
 void meta_apply(float* theta, const float* dsum, float scale, int64_t n, cudaStream_t s);
 void reduce_partials(const float* partials, int G, int n, float* out, cudaStream_t s);

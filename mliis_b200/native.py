@@ -110,6 +110,7 @@ SYMBOLS = [
     ("mliis_rsd_conv2_fwd", C.c_int, [_VP, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32,
                                       _VP]),
     ("mliis_tc_peak_tf32", C.c_int, [_I32, C.POINTER(C.c_double), _VP]),
+    ("mliis_tc_mma_rate", C.c_int, [_I32, _I32, _I32, _I32, C.POINTER(C.c_double), _VP]),
     ("mliis_debug_buffer", C.c_int, [_VP, _I32, C.c_char_p, C.POINTER(_VP), C.POINTER(_I64), C.POINTER(_I32),
                                      C.POINTER(_I32)]),
 ]

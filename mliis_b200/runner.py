@@ -200,6 +200,12 @@ class TaskRunner:
             self._capture()
         results: List[Optional[Tuple[np.ndarray, np.ndarray]]] = [None] * len(plans)
         G, ng = self.group, len(self.groups)
+        # the group streams are non-blocking: order them after whatever the caller queued on its stream (the copy into
+        # init_state, a meta-update still waiting for the training slots) - otherwise a task graph could reset and
+        # adapt a slot that a meta-training graph is still running on
+        cur = torch.cuda.current_stream()
+        for g in self.groups:
+            g.stream.wait_stream(cur)
         for ci, i0 in enumerate(range(0, len(plans), G)):
             g = self.groups[ci % ng]
             if g.busy:
