@@ -376,6 +376,27 @@ def hbm_rooflines(n_group, peak_gbs, flush):
                                                  H, H, 1, 0.0, st)), 3)
     N.check(lib.mliis_kernel_group(1, 0))
     del ar
+    # the MBConv pointwise convolutions (tcgen05 path; HBM-bound by bytes at these K): expand 24->144 and project
+    # 144->24 of blocks_2 (56x56), project 672->112 of blocks_9/10 (14x14).  The project conv reads the pre-BN
+    # depthwise output and applies BN + swish + SE gate in its operand loader (nothing activated is ever stored).
+    for (HWs, Cin, Cout, fused) in ((56 * 56, 24, 144, False), (56 * 56, 144, 24, True), (14 * 14, 672, 112, True)):
+        M = B * HWs
+        ar = _Arena(n_group, dict(x=M * Cin, w=Cin * Cout, wt=2 * Cin * Cout, a=Cin, b=Cin, gate=B * Cin, y=M * Cout))
+        N.check(lib.mliis_kernel_group(n_group, ar.stride * 4))
+        N.check(lib.mliis_tc_prep_weights(ar.p("w"), ar.p("wt"), 1, Cin, Cout, 0, N.GEMM_TF32X3, st))
+        if fused:
+            fn = lambda: N.check(lib.mliis_tc_project_conv(ar.p("x"), ar.p("wt"), ar.p("a"), ar.p("b"), ar.p("gate"), ar.p("y"),
+                                                           B, HWs, Cin, Cout, N.GEMM_TF32X3, st))
+            name = "tc_conv 1x1 project %d->%d M=%d (BN+swish+gate prologue)" % (Cin, Cout, M)
+            ref = "project conv of MBConvBlock (efficientnet_model.py:225-232, :266, :271-273)"
+        else:
+            fn = lambda: N.check(lib.mliis_tc_conv(ar.p("x"), ar.p("wt"), None, ar.p("y"), B, 1, HWs, Cin, Cout, 1, 1,
+                                                   N.GEMM_TF32X3, st))
+            name = "tc_conv 1x1 expand %d->%d M=%d" % (Cin, Cout, M)
+            ref = "expand conv of MBConvBlock (efficientnet_model.py:183-188)"
+        add(name, ref, 4.0 * n_group * (M * Cin + M * Cout), fn, 1)
+        N.check(lib.mliis_kernel_group(1, 0))
+        del ar
     # multi-tensor Adam over the flat parameter buffer (reads g, theta, v; writes theta, v)
     P = 2071724
     ar = _Arena(n_group, dict(theta=P, v=P, g=P))

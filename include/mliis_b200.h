@@ -275,6 +275,12 @@ int mliis_tc_prep_weights(const float* dev_w, float* dev_wt, int32_t taps, int32
                           int32_t mode, void* stream);
 int mliis_tc_conv(const float* dev_x, const float* dev_wt, const float* dev_bias, float* dev_y, int32_t B, int32_t H,
                   int32_t W, int32_t Cin, int32_t Cout, int32_t taps, int32_t dilation, int32_t mode, void* stream);
+/* MBConv project conv with its fused prologue (efficientnet_model.py:225-232, :266, :271-273):
+ * y[B*HW, Cout] = (swish(bn_a[c] * x[m, c] + bn_b[c]) * gate[image(m), c]) * W   (gate may be null; dev_wt from
+ * mliis_tc_prep_weights with taps = 1).  The activated / gated tensor is never written to memory. */
+int mliis_tc_project_conv(const float* dev_x, const float* dev_wt, const float* dev_bn_a, const float* dev_bn_b,
+                          const float* dev_gate /* [B, Cin] or null */, float* dev_y, int32_t B, int32_t HW, int32_t Cin,
+                          int32_t Cout, int32_t mode, void* stream);
 /* Weight gradient on the tensor cores: dev_dw[taps*Cin, Cout] = sum over pixels of a[pixel+tap, :]^T g[pixel, :]
  * (a: [B,H,W,Cin], g: [B,H,W,Cout]; taps = 9 for a 3x3 SAME conv with `dilation`, 1 for a 1x1 conv). */
 int mliis_tc_wgrad(const float* dev_a, const float* dev_g, float* dev_dw, int32_t B, int32_t H, int32_t W, int32_t Cin,

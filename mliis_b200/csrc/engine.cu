@@ -1333,6 +1333,22 @@ int mliis_tc_conv(const float* x, const float* wt, const float* bias, float* y, 
   return check_cuda("tc_conv");
 }
 
+// MBConv project conv (efficientnet_model.py:271-273 after :225-232, :266): y[M, Cout] = (swish(bn_a*x + bn_b) * gate[img]) * W.
+// The normalised, activated, SE-gated tensor never exists in HBM: the prologue runs in the operand loader.
+int mliis_tc_project_conv(const float* x, const float* wt, const float* bn_a, const float* bn_b, const float* gate, float* y,
+                          int32_t B, int32_t HW, int32_t Cin, int32_t Cout, int32_t mode, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (!x || !wt || !bn_a || !bn_b || !y) return fail(MLIIS_ERR_ARG, "null argument");
+  if (mode == MLIIS_GEMM_FP32) return fail(MLIIS_ERR_ARG, "mode must be a tensor-core mode");
+  if (!tc_supported(0, 0, Cin, Cout)) return fail(MLIIS_ERR_ARG, "shape not supported by the tcgen05 path");
+  KERNEL_GROUP();
+  if (!tc_conv(x, Cin, wt, nullptr, y, Cout, 0, B * HW, B, 1, 1, Cin, 1, 1, Cout, 0, mode == MLIIS_GEMM_TF32X3 ? 3 : 1,
+               (cudaStream_t)stream, bn_a, bn_b, gate, HW))
+    return fail(MLIIS_ERR_CUDA, "tc_conv setup failed (tensor map encode)");
+  return check_cuda("tc_project_conv");
+}
+
 int mliis_tc_wgrad(const float* a, const float* g, float* dw, int32_t B, int32_t H, int32_t W, int32_t Cin,
                    int32_t Cout, int32_t taps, int32_t dilation, int32_t mode, void* stream) {
   int rc = require_sm100();

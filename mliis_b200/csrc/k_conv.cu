@@ -144,37 +144,45 @@ constexpr int QC = 8;  // float4 channel groups per CTA (32 channels)
 
 template <int K, int S>
 struct DwGeom {
-  static constexpr int TO = (S == 1) ? 14 : 7;          // output tile edge
-  static constexpr int SPR = TO / 7;                    // strips per tile row
-  static constexpr int NSTRIP = TO * SPR;               // 28 | 7
-  static constexpr int NT = (S == 1) ? 224 : 64;        // threads (S=2: 56 active + 8 idle, warp aligned)
-  static constexpr int TI = (TO - 1) * S + K;           // staged input tile edge
+  static constexpr int TOX = 14;                        // output tile: 14 x 14 (stride 1), 14 x 7 (stride 2)
+  static constexpr int TOY = (S == 1) ? 14 : 7;
+  static constexpr int SPR = TOX / 7;                   // strips (7 outputs along x) per tile row
+  static constexpr int NSTRIP = TOY * SPR;              // 28 | 14
+  static constexpr int NT = 224;                        // every thread stages; NSTRIP * QC threads compute
+  static constexpr int TIX = (TOX - 1) * S + K;         // staged input tile
+  static constexpr int TIY = (TOY - 1) * S + K;
   static constexpr int NIN = 6 * S + K;                 // inputs per strip row
-  static constexpr size_t smem_bytes() { return (size_t)(TI * TI + K * K) * QC * sizeof(float4); }
-  static constexpr size_t wgrad_smem_bytes() { return (size_t)(TI * TI + K * K * (NT / 32)) * QC * sizeof(float4); }
+  static constexpr int NPIX = TIX * TIY;
+  static constexpr size_t smem_bytes() { return (size_t)(NPIX + K * K) * QC * sizeof(float4); }
+  static constexpr size_t wgrad_smem_bytes() { return (size_t)(NPIX + K * K * (NT / 32)) * QC * sizeof(float4); }
 };
 
-// stage swish(a*x+b) (or x when a == null) of the input tile into shared memory
+// stage swish(a*x+b) (or x when a == null) of the input tile into shared memory.  HBM-bound: a thread issues ALL of its
+// global loads (U <= 12 float4) before the first one is consumed, so one memory round trip stages the whole tile.
 template <int K, int S>
 __device__ __forceinline__ void dw_stage_input(float4* tile, const float* __restrict__ x,
                                                const float* __restrict__ a, const float* __restrict__ b, int img,
                                                int H, int W, int C, int c0, int iy0, int ix0) {
   using G = DwGeom<K, S>;
-  constexpr int TOT = G::TI * G::TI * QC, U = 4;
+  constexpr int TOT = G::NPIX * QC;
+  constexpr int PER = (TOT + G::NT - 1) / G::NT;
+  constexpr int U = PER <= 12 ? PER : (PER + 1) / 2;       // loads in flight per thread per round
   const int tid = threadIdx.x, q = tid % QC;     // NT is a multiple of QC: q is the same for every i of a thread
   const bool cvalid = c0 + q * 4 < C;
   float4 av = f4s(1.f), bv = f4s(0.f);
   if (a && cvalid) { av = ld4(a + c0 + q * 4); bv = ld4(b + c0 + q * 4); }
+  const float* xb = x + (size_t)img * H * W * C + c0 + q * 4;
+#pragma unroll 1
   for (int i0 = tid; i0 < TOT; i0 += U * G::NT) {
     float4 v[U];
     bool ok[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {      // issue the U global loads before any of them is consumed
+    for (int u = 0; u < U; ++u) {
       const int i = i0 + u * G::NT;
-      const int pix = i / QC, ly = pix / G::TI, lx = pix - ly * G::TI;
+      const int pix = i / QC, ly = pix / G::TIX, lx = pix - ly * G::TIX;
       const int gy = iy0 + ly, gx = ix0 + lx;
       ok[u] = i < TOT && cvalid && gy >= 0 && gy < H && gx >= 0 && gx < W;
-      v[u] = ok[u] ? ld4(x + (((size_t)img * H + gy) * W + gx) * C + c0 + q * 4) : f4s(0.f);
+      v[u] = ok[u] ? ld4(xb + ((size_t)gy * W + gx) * C) : f4s(0.f);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -186,7 +194,7 @@ __device__ __forceinline__ void dw_stage_input(float4* tile, const float* __rest
 
 // FLIP: use w[K-1-ky][K-1-kx] (stride-1 dgrad == correlation with the flipped filter)
 template <int K, int S, bool FLIP>
-__global__ void __launch_bounds__(DwGeom<K, S>::NT) dw_fwd_kernel(const float* __restrict__ x,
+__global__ void __launch_bounds__(DwGeom<K, S>::NT, 4) dw_fwd_kernel(const float* __restrict__ x,
                                                                    const float* __restrict__ a,
                                                                    const float* __restrict__ b,
                                                                    const float* __restrict__ w, float* __restrict__ y,
@@ -195,9 +203,9 @@ __global__ void __launch_bounds__(DwGeom<K, S>::NT) dw_fwd_kernel(const float* _
   using G = DwGeom<K, S>;
   extern __shared__ float4 smem4[];
   float4* tile = smem4;
-  float4* wsm = smem4 + G::TI * G::TI * QC;
+  float4* wsm = smem4 + G::NPIX * QC;
   const int tid = threadIdx.x, q = tid % QC, strip = tid / QC;
-  const int ty0 = (blockIdx.x / tiles_x) * G::TO, tx0 = (blockIdx.x % tiles_x) * G::TO;
+  const int ty0 = (blockIdx.x / tiles_x) * G::TOY, tx0 = (blockIdx.x % tiles_x) * G::TOX;
   const int slot = blockIdx.z / nB;
   const int c0 = blockIdx.y * (QC * 4), img = blockIdx.z - slot * nB;
   { const size_t zo = (size_t)slot * zs; x += zo; a = zp(a, zo); b = zp(b, zo); w += zo; y += zo; }
@@ -215,7 +223,7 @@ __global__ void __launch_bounds__(DwGeom<K, S>::NT) dw_fwd_kernel(const float* _
   for (int j = 0; j < 7; ++j) acc[j] = f4s(0.f);
 #pragma unroll
   for (int ky = 0; ky < K; ++ky) {
-    const float4* row = tile + ((size_t)(oy * S + ky) * G::TI + ox0 * S) * QC + q;
+    const float4* row = tile + ((size_t)(oy * S + ky) * G::TIX + ox0 * S) * QC + q;
     float4 wv[K];
 #pragma unroll
     for (int kx = 0; kx < K; ++kx) wv[kx] = wsm[(ky * K + kx) * QC + q];
@@ -248,7 +256,7 @@ static void dw_fwd_launch(const float* x, const float* a, const float* b, const 
     cudaFuncSetAttribute(dw_fwd_kernel<K, S, FLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes());
     attr_done = true;
   }
-  const int tiles_x = cdiv(Wo, G::TO), tiles_y = cdiv(Ho, G::TO);
+  const int tiles_x = cdiv(Wo, G::TOX), tiles_y = cdiv(Ho, G::TOY);
   dim3 grid(tiles_x * tiles_y, cdiv(C, QC * 4), B * MLIIS_NZ);
   MLIIS_COUNT(), dw_fwd_kernel<K, S, FLIP><<<grid, G::NT, G::smem_bytes(), s>>>(x, a, b, w, y, H, W, C, Ho, Wo, pad_t, pad_l, tiles_x,
                                                                                B, MLIIS_ZS);
@@ -356,12 +364,11 @@ void dw_bwd_data(const float* dy, const float* w, float* dx, int B, int H, int W
 
 // ---- wgrad: dW[ky,kx,c] = sum_{b,oy,ox} act(x)[oy*S-pad+ky, ox*S-pad+kx, c] * dy[oy,ox,c]
 int dw_wgrad_blocks(int B, int Ho, int Wo, int stride) {
-  const int TO = stride == 1 ? 14 : 7;
-  return B * cdiv(Ho, TO) * cdiv(Wo, TO);
+  return B * cdiv(Ho, stride == 1 ? 14 : 7) * cdiv(Wo, 14);
 }
 
 template <int K, int S>
-__global__ void __launch_bounds__(DwGeom<K, S>::NT) dw_wgrad_kernel(const float* __restrict__ x,
+__global__ void __launch_bounds__(DwGeom<K, S>::NT, 4) dw_wgrad_kernel(const float* __restrict__ x,
                                                                      const float* __restrict__ a,
                                                                      const float* __restrict__ b,
                                                                      const float* __restrict__ dy,
@@ -373,16 +380,16 @@ __global__ void __launch_bounds__(DwGeom<K, S>::NT) dw_wgrad_kernel(const float*
   extern __shared__ float4 smem4[];
   float4* tile = smem4;
   const int tid = threadIdx.x, q = tid % QC, strip = tid / QC;
-  const int ty0 = (blockIdx.x / tiles_x) * G::TO, tx0 = (blockIdx.x % tiles_x) * G::TO;
+  const int ty0 = (blockIdx.x / tiles_x) * G::TOY, tx0 = (blockIdx.x % tiles_x) * G::TOX;
   const int slot = blockIdx.z / nB;
   const int c0 = blockIdx.y * (QC * 4), img = blockIdx.z - slot * nB;
   { const size_t zo = (size_t)slot * zs; x += zo; a = zp(a, zo); b = zp(b, zo); dy += zo; partials += zo; }
   const bool cvalid = c0 + q * 4 < C;
   dw_stage_input<K, S>(tile, x, a, b, img, H, W, C, c0, ty0 * S - pad_t, tx0 * S - pad_l);
   __syncthreads();
-  float4* red = smem4 + G::TI * G::TI * QC;  // [K*K][NW][QC]
+  float4* red = smem4 + G::NPIX * QC;  // [K*K][NW][QC]
   const int warp = tid >> 5, lane = tid & 31;
-  const bool active = strip < G::NSTRIP;     // S == 2: the last 8 threads only take part in the shuffles
+  const bool active = strip < G::NSTRIP;     // S == 2: the upper half of the block only stages and shuffles zeros
   const int oy = active ? strip / G::SPR : 0, ox0 = active ? (strip % G::SPR) * 7 : 0;
   float4 g[7];
   {
@@ -396,7 +403,7 @@ __global__ void __launch_bounds__(DwGeom<K, S>::NT) dw_wgrad_kernel(const float*
   }
 #pragma unroll
   for (int ky = 0; ky < K; ++ky) {
-    const float4* row = tile + ((size_t)(oy * S + ky) * G::TI + ox0 * S) * QC + q;
+    const float4* row = tile + ((size_t)(oy * S + ky) * G::TIX + ox0 * S) * QC + q;
     float4 wrow[K];
 #pragma unroll
     for (int kx = 0; kx < K; ++kx) wrow[kx] = f4s(0.f);
@@ -443,7 +450,7 @@ static void dw_wgrad_launch(const float* x, const float* a, const float* b, cons
     cudaFuncSetAttribute(dw_wgrad_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::wgrad_smem_bytes());
     attr_done = true;
   }
-  const int tiles_x = cdiv(Wo, G::TO), tiles_y = cdiv(Ho, G::TO), tiles = tiles_x * tiles_y;
+  const int tiles_x = cdiv(Wo, G::TOX), tiles_y = cdiv(Ho, G::TOY), tiles = tiles_x * tiles_y;
   dim3 grid(tiles, cdiv(C, QC * 4), B * MLIIS_NZ);
   MLIIS_COUNT(), dw_wgrad_kernel<K, S><<<grid, G::NT, G::wgrad_smem_bytes(), s>>>(x, a, b, dy, partials, H, W, C, Ho, Wo, pad_t, pad_l,
                                                              tiles_x, tiles, B, MLIIS_ZS);

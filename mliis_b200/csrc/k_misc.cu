@@ -18,8 +18,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
   { const size_t zo = (size_t)blockIdx.z * zs; partials += zo; out += zo; }
   const int i = blockIdx.x * 32 + threadIdx.x;
   double s = 0.0;
-  if (i < n)
-    for (int g = threadIdx.y; g < G; g += 8) s += (double)partials[(size_t)g * n + i];
+  if (i < n) s = strided_sum_d(partials + i, G, (size_t)n, threadIdx.y, 8);
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y != 0 || i >= n) return;
@@ -33,8 +32,7 @@ __global__ void __launch_bounds__(256) reduce_partials_strided_kernel(const floa
   { const size_t zo = (size_t)blockIdx.z * zs; partials += zo; out += zo; }
   const int i = blockIdx.x * 32 + threadIdx.x;
   double s = 0.0;
-  if (i < n)
-    for (int g = threadIdx.y; g < G; g += 8) s += (double)partials[(size_t)g * n + i];
+  if (i < n) s = strided_sum_d(partials + i, G, (size_t)n, threadIdx.y, 8);
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y != 0 || i >= n) return;
@@ -282,21 +280,37 @@ __global__ void __launch_bounds__(256) loss_fwd_kernel(LossArgs a, long long zs)
   const float ls = a.label_smoothing;
   float s_ce = 0.f, s_i = 0.f, s_p = 0.f, s_y = 0.f;
   const int npix = (Y1 - Y0) * a.W;
-  for (int i = threadIdx.x; i < npix; i += 256) {
-    const int Y = Y0 + i / a.W, X = i - (i / a.W) * a.W;
-    const Up2 z = upsample_logits(a.z_lo, b, a.h, a.w, Y, X, a.ty, a.tx);
-    const float m = fmaxf(z.z0, z.z1);
-    const float e0 = expf(z.z0 - m), e1 = expf(z.z1 - m);
-    const float sum = e0 + e1;
-    const float p1 = e1 / sum;
-    const float lse = m + logf(sum);
-    const float2 y = *reinterpret_cast<const float2*>(a.labels + (((size_t)img * a.H + Y) * a.W + X) * 2);
-    const float yc0 = y.x * (1.f - ls) + 0.5f * ls, yc1 = y.y * (1.f - ls) + 0.5f * ls;
-    s_ce += yc0 * (lse - z.z0) + yc1 * (lse - z.z1);
-    s_i += p1 * y.y;
-    s_p += p1;
-    s_y += y.y;
-    a.p1[((size_t)b * a.H + Y) * a.W + X] = p1;
+  constexpr int U = 4;      // pixels in flight per thread: all gathers / label loads of a batch are issued before the
+  for (int i0 = threadIdx.x; i0 < npix; i0 += U * 256) {      // first store (the stores would otherwise fence them)
+    Up2 z[U];
+    float2 y[U];
+    size_t po[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * 256;
+      if (i < npix) {
+        const int Y = Y0 + i / a.W, X = i - (i / a.W) * a.W;
+        z[u] = upsample_logits(a.z_lo, b, a.h, a.w, Y, X, a.ty, a.tx);
+        y[u] = *reinterpret_cast<const float2*>(a.labels + (((size_t)img * a.H + Y) * a.W + X) * 2);
+        po[u] = ((size_t)b * a.H + Y) * a.W + X;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u * 256 < npix) {
+        const float m = fmaxf(z[u].z0, z[u].z1);
+        const float e0 = expf(z[u].z0 - m), e1 = expf(z[u].z1 - m);
+        const float sum = e0 + e1;
+        const float p1 = e1 / sum;
+        const float lse = m + logf(sum);
+        const float yc0 = y[u].x * (1.f - ls) + 0.5f * ls, yc1 = y[u].y * (1.f - ls) + 0.5f * ls;
+        s_ce += yc0 * (lse - z[u].z0) + yc1 * (lse - z[u].z1);
+        s_i += p1 * y[u].y;
+        s_p += p1;
+        s_y += y[u].y;
+        a.p1[po[u]] = p1;
+      }
+    }
   }
   s_ce = warp_sum(s_ce); s_i = warp_sum(s_i); s_p = warp_sum(s_p); s_y = warp_sum(s_y);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -330,24 +344,41 @@ void sumsq_partials(const float* x, int64_t n, float* out, int n_blocks, cudaStr
   MLIIS_COUNT(), sumsq_kernel<<<dim3(n_blocks, 1, MLIIS_NZ), 256, 0, s>>>(x, n, out, MLIIS_ZS);
 }
 
-// single thread: per-image IoU, dice, loss value and the per-image gradient coefficients
-__global__ void loss_finalize_kernel(LossArgs a, const float* __restrict__ l2_partials, int n_l2_partials, long long zs) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// one warp: per-image IoU, dice, loss value and the per-image gradient coefficients.  Lane g owns row chunk g of every
+// image (kLossChunks == 32): one float4 load per image, the four sums by a fixed xor-shuffle tree in double (every lane
+// ends up with the same totals; deterministic).  The first version was ONE thread walking 1024 dependent loads (19 us).
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__global__ void __launch_bounds__(32) loss_finalize_kernel(LossArgs a, const float* __restrict__ l2_partials,
+                                                           int n_l2_partials, long long zs) {
+  static_assert(kLossChunks == 32, "lane == row chunk");
+  __shared__ double sI[256], sU[256];
+  if (blockIdx.x != 0) return;
   loss_shift(a, zs);
   l2_partials += (size_t)blockIdx.z * zs;
+  const int lane = threadIdx.x;
   const double eps = 1e-7;
   double ce = 0.0, iou = 0.0;
-  for (int b = 0; b < a.B; ++b) {
-    double I = 0.0, P = 0.0, Yv = 0.0;
-    for (int g = 0; g < kLossChunks; ++g) {
-      const float* p = a.partials + ((size_t)b * kLossChunks + g) * 4;
-      ce += p[0]; I += p[1]; P += p[2]; Yv += p[3];
+  for (int b0 = 0; b0 < a.B; b0 += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (b0 + u < a.B) v[u] = ld4(a.partials + ((size_t)(b0 + u) * kLossChunks + lane) * 4);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (b0 + u < a.B) {
+        ce += warp_sum_d((double)v[u].x);
+        const double I = warp_sum_d((double)v[u].y), P = warp_sum_d((double)v[u].z), Yv = warp_sum_d((double)v[u].w);
+        const double U = P + Yv - I;
+        iou += (I + eps) / (U + eps);
+        if (lane == 0 && b0 + u < 256) { sI[b0 + u] = I; sU[b0 + u] = U; }
+      }
     }
-    const double U = P + Yv - I;
-    iou += (I + eps) / (U + eps);
-    a.coef[b * 2 + 0] = (float)I;     // stash, rewritten below
-    a.coef[b * 2 + 1] = (float)U;
   }
+  __syncwarp();
   iou /= a.B;
   double loss = ce / ((double)a.B * a.H * a.W);
   double dLdiou = 0.0;
@@ -355,15 +386,16 @@ __global__ void loss_finalize_kernel(LossArgs a, const float* __restrict__ l2_pa
     loss -= log(2.0 * iou / (iou + 1.0));
     dLdiou = -1.0 / (iou * (iou + 1.0));
   }
-  for (int b = 0; b < a.B; ++b) {
-    const double I = a.coef[b * 2 + 0], U = a.coef[b * 2 + 1];
+  for (int b = lane; b < a.B; b += 32) {
+    const double I = sI[b], U = sU[b];
     a.coef[b * 2 + 0] = (float)(dLdiou / (a.B * (U + eps)));                       // d loss / d I_b
     a.coef[b * 2 + 1] = (float)(-dLdiou * (I + eps) / (a.B * (U + eps) * (U + eps)));  // d loss / d U_b
   }
   if (a.loss_out) {
     double l2 = 0.0;
-    for (int i = 0; i < n_l2_partials; ++i) l2 += l2_partials[i];
-    *a.loss_out = (float)(loss + 0.5 * (double)a.l2_coef * l2);
+    for (int i = lane; i < n_l2_partials; i += 32) l2 += (double)l2_partials[i];
+    l2 = warp_sum_d(l2);
+    if (lane == 0) *a.loss_out = (float)(loss + 0.5 * (double)a.l2_coef * l2);
   }
 }
 
@@ -375,16 +407,34 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(LossArgs a, long long zs)
   const float inv = 1.f / ((float)a.B * (float)a.H * (float)a.W);
   const float ls = a.label_smoothing;
   const int npix = a.H * a.W;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < npix; i += gridDim.x * 256) {
-    const float p1 = a.p1[(size_t)b * npix + i];
-    const float2 y = *reinterpret_cast<const float2*>(a.labels + ((size_t)img * npix + i) * 2);
-    const float yc0 = y.x * (1.f - ls) + 0.5f * ls, yc1 = y.y * (1.f - ls) + 0.5f * ls;
-    // d loss / d p1 = cI * y1 + cU * (1 - y1)      (dI/dp1 = y1, dU/dp1 = 1 - y1)
-    const float t = (cI * y.y + cU * (1.f - y.y)) * p1 * (1.f - p1);
-    // TF SoftmaxCrossEntropyWithLogits backprop = softmax - labels  [TF-ext]
-    const float d1 = (p1 - yc1) * inv + t;
-    const float d0 = ((1.f - p1) - yc0) * inv - t;
-    *reinterpret_cast<float2*>(a.dz_hi + ((size_t)b * npix + i) * 2) = make_float2(d0, d1);
+  constexpr int U = 4;
+  const int step = gridDim.x * 256;
+  for (int i0 = blockIdx.x * 256 + threadIdx.x; i0 < npix; i0 += U * step) {
+    float p1v[U];
+    float2 yv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * step;
+      if (i < npix) {
+        p1v[u] = a.p1[(size_t)b * npix + i];
+        yv[u] = *reinterpret_cast<const float2*>(a.labels + ((size_t)img * npix + i) * 2);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * step;
+      if (i < npix) {
+        const float p1 = p1v[u];
+        const float2 y = yv[u];
+        const float yc0 = y.x * (1.f - ls) + 0.5f * ls, yc1 = y.y * (1.f - ls) + 0.5f * ls;
+        // d loss / d p1 = cI * y1 + cU * (1 - y1)      (dI/dp1 = y1, dU/dp1 = 1 - y1)
+        const float t = (cI * y.y + cU * (1.f - y.y)) * p1 * (1.f - p1);
+        // TF SoftmaxCrossEntropyWithLogits backprop = softmax - labels  [TF-ext]
+        const float d1 = (p1 - yc1) * inv + t;
+        const float d0 = ((1.f - p1) - yc0) * inv - t;
+        *reinterpret_cast<float2*>(a.dz_hi + ((size_t)b * npix + i) * 2) = make_float2(d0, d1);
+      }
+    }
   }
 }
 

@@ -4,7 +4,8 @@
 // conv2d_2 is a per-image vector per filter tap, summed over the taps that fall inside the image - with TF's zero
 // SAME padding that depends only on the BORDER CLASS of the output pixel (3 row classes x 3 column classes):
 //
-//   forward   out[b,y,x,n] += bias9[b][cls(y,x)][n],   bias9[b][cls][n] = sum_{tap valid in cls} sum_c p[b,c] W[tap][2D+c][n]
+//   forward   out[b,y,x,n] += bias9[b][cls(y,x)][n],   bias9[b][cls][n] = sum_{tap valid in cls} tap9[b][tap][n],
+//             tap9[b][tap][n] = sum_c p[b,c] W[tap][2D+c][n]   (pool_taps_kernel; the class sums: tc_conv3_kernel)
 //   wgrad     dW[tap][2D+c][n] = sum_b p[b,c] S[b][tap][n],   S[b][tap][n] = sum_{cls where tap valid} Q[b][cls][n],
 //             Q[b][cls][n] = sum of the output gradient over the pixels of class cls
 //   dgrad     dp[b,c] = sum_{tap,n} S[b][tap][n] W[tap][2D+c][n]       (then / HW onto every pixel of `concat`)
@@ -24,33 +25,37 @@ __device__ __forceinline__ bool tap_valid(int tap, int cls) {
   return !((ty == 0 && ry == 0) || (ty == 2 && ry == 2) || (tx == 0 && rx == 0) || (tx == 2 && rx == 2));
 }
 
-// grid (9 classes, B); block (D, 4): threadIdx.y splits the pooled channels, fixed-order combine through smem.
-__global__ void pool_bias9_kernel(const float* __restrict__ pooled, int ldp, const float* __restrict__ w, int Cs,
-                                  int c_first, int Cp, int D, float* __restrict__ bias9, long long zs) {
-  extern __shared__ float smf[];
-  { const size_t zo = (size_t)blockIdx.z * zs; pooled += zo; w += zo; bias9 += zo; }
-  const int cls = blockIdx.x, b = blockIdx.y, n = threadIdx.x, part = threadIdx.y, P = blockDim.y;
-  float acc = 0.f;
-  for (int tap = 0; tap < 9; ++tap) {
-    if (!tap_valid(tap, cls)) continue;
-    const float* wr = w + ((size_t)tap * Cs + c_first) * D + n;
-    const float* pr = pooled + (size_t)b * ldp;
-    float s = 0.f;
-    for (int c = part; c < Cp; c += P) s = fmaf(pr[c], wr[(size_t)c * D], s);
-    acc += s;
-  }
-  smf[part * D + n] = acc;
+// Per-tap vectors of the folded branch: tap9[b][tap][n] = sum_c p[b,c] W[tap][c_first + c][n].  grid (9 taps, B);
+// block (D, 8): threadIdx.y splits the pooled channels (<= Cp/8 coalesced weight loads per thread), fixed-order combine
+// through shared memory.  The border-class sums bias9[cls] = sum of the taps valid in cls are formed by the consumer
+// (tc_conv3_kernel prologue, in shared memory), so this launch is 72 small CTAs instead of 8 long ones.
+__global__ void __launch_bounds__(1024) pool_taps_kernel(const float* __restrict__ pooled, int ldp,
+                                                         const float* __restrict__ w, int Cs, int c_first, int Cp, int D,
+                                                         float* __restrict__ tap9, long long zs) {
+  extern __shared__ float smf[];       // partial[P][D] | p[Cp]
+  { const size_t zo = (size_t)blockIdx.z * zs; pooled += zo; w += zo; tap9 += zo; }
+  const int tap = blockIdx.x, b = blockIdx.y, n = threadIdx.x, part = threadIdx.y, P = blockDim.y;
+  float* ps = smf + P * D;
+  for (int c = part * D + n; c < Cp; c += P * D) ps[c] = pooled[(size_t)b * ldp + c];
+  __syncthreads();
+  const float* wr = w + ((size_t)tap * Cs + c_first) * D + n;
+  float s = 0.f;
+  for (int c = part; c < Cp; c += P) s = fmaf(ps[c], wr[(size_t)c * D], s);
+  smf[part * D + n] = s;
   __syncthreads();
   if (part == 0) {
-    for (int j = 1; j < P; ++j) acc += smf[j * D + n];
-    bias9[((size_t)b * 9 + cls) * D + n] = acc;
+    for (int j = 1; j < P; ++j) s += smf[j * D + n];
+    tap9[((size_t)b * 9 + tap) * D + n] = s;
   }
 }
 
 void pool_bias9(const float* pooled, int ldp, const float* w_hwio, int Cs, int c_first, int Cp, int D, int B,
-                float* bias9, cudaStream_t s) {
-  MLIIS_COUNT(), pool_bias9_kernel<<<dim3(9, B, MLIIS_NZ), dim3(D, 4), 4 * D * sizeof(float), s>>>(pooled, ldp, w_hwio, Cs, c_first, Cp,
-                                                                                                  D, bias9, MLIIS_ZS);
+                float* tap9, cudaStream_t s) {
+  int P = 1024 / D;
+  if (P > 8) P = 8;
+  if (P < 1) P = 1;
+  MLIIS_COUNT(), pool_taps_kernel<<<dim3(9, B, MLIIS_NZ), dim3(D, P), (P * D + Cp) * sizeof(float), s>>>(pooled, ldp, w_hwio, Cs, c_first,
+                                                                                                    Cp, D, tap9, MLIIS_ZS);
 }
 
 // Q partials: grid (G row chunks, B); block (D/4, R).  partial[b][g][cls][D]
@@ -92,10 +97,13 @@ __global__ void region_sums_finalize_kernel(const float* __restrict__ partial, i
   const int b = blockIdx.x, n = threadIdx.x;
   double q[9];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    double s = 0.0;
-    for (int gch = 0; gch < G; ++gch) s += (double)partial[(((size_t)b * G + gch) * 9 + k) * D + n];
-    q[k] = s;
+  for (int k = 0; k < 9; ++k) q[k] = 0.0;
+  for (int gch = 0; gch < G; ++gch) {       // the 9 loads of a chunk are independent: all in flight together
+    float v[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) v[k] = partial[(((size_t)b * G + gch) * 9 + k) * D + n];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) q[k] += (double)v[k];
   }
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {

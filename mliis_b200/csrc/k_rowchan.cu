@@ -72,7 +72,7 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int ld, int M, int 
   const int r0 = blockIdx.x * rows_per_chunk;
   const int r1 = min(M, r0 + rows_per_chunk);
   float4 s = f4s(0.f), ss = f4s(0.f);
-  constexpr int U = 4;   // rows in flight per thread (loads issued before any is consumed; same summation order)
+  constexpr int U = 8;   // rows in flight per thread (loads issued before any is consumed; same summation order)
   for (int rb = r0 + threadIdx.y; rb < r1; rb += U * blockDim.y) {
     float4 v[U];
 #pragma unroll
@@ -122,10 +122,8 @@ __global__ void __launch_bounds__(512) bn_finalize_kernel(const float* __restric
   const int c = blockIdx.x * 32 + threadIdx.x;
   double s = 0.0, ss = 0.0;
   if (c < C) {
-    for (int g = threadIdx.y; g < G; g += 16) {
-      s += (double)partials[((size_t)g * 2 + 0) * C + c];
-      ss += (double)partials[((size_t)g * 2 + 1) * C + c];
-    }
+    s = strided_sum_d(partials + c, G, 2 * (size_t)C, threadIdx.y, 16);
+    ss = strided_sum_d(partials + C + c, G, 2 * (size_t)C, threadIdx.y, 16);
   }
   red[0][threadIdx.y][threadIdx.x] = s;
   red[1][threadIdx.y][threadIdx.x] = ss;
@@ -235,7 +233,7 @@ __global__ void img_reduce_kernel(const float* __restrict__ x, int ldx, const fl
   if (MODE != 2) { av = ld4(a + cq * 4); bv = ld4(b + cq * 4); }
   const int r0 = blockIdx.x * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
   float4 s = f4s(0.f);
-  constexpr int U = 4;
+  constexpr int U = MODE == 1 ? 4 : 8;
   for (int rb = r0 + threadIdx.y; rb < r1; rb += U * blockDim.y) {
     float4 v[U], gv[U];
 #pragma unroll
@@ -281,8 +279,7 @@ __global__ void img_colsum_finalize_kernel(const float* __restrict__ partial, in
   { const size_t zo = (size_t)blockIdx.z * zs; partial += zo; out += zo; }
   int c = blockIdx.x * blockDim.x + threadIdx.x, img = blockIdx.y;
   if (c >= C) return;
-  double s = 0.0;
-  for (int g = 0; g < G; ++g) s += (double)partial[((size_t)img * G + g) * C + c];
+  const double s = strided_sum_d(partial + (size_t)img * G * C + c, G, (size_t)C);
   out[(size_t)img * ldo + c] = (float)(s * (double)scale);
 }
 void img_colsum(const float* x, int ldx, int B, int HW, int C, float scale, float* partial, float* out, int ldo,
@@ -310,8 +307,7 @@ __global__ void se_fc_fwd_kernel(const float* __restrict__ partial, int G, int H
   const int img = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const float inv = 1.f / (float)HW;
   for (int c = tid; c < C; c += nt) {
-    float s = 0.f;
-    for (int g = 0; g < G; ++g) s += partial[((size_t)img * G + g) * C + c];
+    float s = strided_sum_f(partial + (size_t)img * G * C + c, G, (size_t)C);
     s *= inv;
     pool[c] = s;
     pool_o[(size_t)img * C + c] = s;
@@ -358,8 +354,7 @@ __global__ void __launch_bounds__(256) se_fc_bwd_img_kernel(const float* __restr
   float* dhp = smf + C;    // [Cr]
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   for (int c = tid; c < C; c += nt) {
-    float s = 0.f;
-    for (int g = 0; g < G; ++g) s += partial[((size_t)b * G + g) * C + c];
+    const float s = strided_sum_f(partial + (size_t)b * G * C + c, G, (size_t)C);
     const float gt = gate[(size_t)b * C + c];
     const float v = s * gt * (1.f - gt);
     dgp[c] = v;
@@ -506,10 +501,8 @@ __global__ void __launch_bounds__(512) bn_bwd_finalize_kernel(const float* __res
   const int c = blockIdx.x * 32 + threadIdx.x;
   double s0 = 0.0, s1 = 0.0;
   if (c < C) {
-    for (int g = threadIdx.y; g < G; g += 16) {
-      s0 += (double)partials[((size_t)g * 2 + 0) * C + c];
-      s1 += (double)partials[((size_t)g * 2 + 1) * C + c];
-    }
+    s0 = strided_sum_d(partials + c, G, 2 * (size_t)C, threadIdx.y, 16);
+    s1 = strided_sum_d(partials + C + c, G, 2 * (size_t)C, threadIdx.y, 16);
   }
   red[0][threadIdx.y][threadIdx.x] = s0;
   red[1][threadIdx.y][threadIdx.x] = s1;

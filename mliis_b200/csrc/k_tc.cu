@@ -114,6 +114,21 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// the same load without the wait: issue several, then tc_ld_wait() once, then tc_ld_fence() on every destination array
+// (an empty asm that "modifies" the registers, so that no use of them can be scheduled above the wait)
+__device__ __forceinline__ void tc_ld16_nw(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld_fence(uint32_t (&v)[16]) {
+  asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                    "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]));
+}
+
 // K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 //   [0,14) start address >> 4 | [16,30) LBO >> 4 (ignored for swizzled K-major, set to 1) |
 //   [32,46) SBO >> 4 = 1024 B between 8-row groups | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
@@ -154,8 +169,8 @@ __device__ __forceinline__ float4 rn_tf32_4(float4 v) { return f4(rn_tf32(v.x), 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// swish with the MUFU reciprocal (<= 2 ulp): x * 1/(1 + 2^(-x*log2 e)); the transform warps are ALU-bound
-__device__ __forceinline__ float swish_fast(float x) { return x * __fdividef(1.f, 1.f + __expf(-x)); }
+// swish: x * 1/(1 + 2^(-x*log2 e)) with the MUFU reciprocal + one Newton step; the transform warps are ALU-bound
+__device__ __forceinline__ float swish_fast(float x) { return x * sigmoid_f(x); }      // common.cuh: MUFU rcp + Newton
 __device__ __forceinline__ float4 swish_fast4(float4 v) {
   return f4(swish_fast(v.x), swish_fast(v.y), swish_fast(v.z), swish_fast(v.w));
 }
@@ -195,7 +210,7 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 // in shared memory once per CTA, MUFU reciprocal; shared memory sized for 2 CTAs per SM where the stage is small; the
 // epilogue goes TMEM -> registers -> swizzled shared-memory tile -> one TMA store per 32 output columns (coalesced
 // 128-byte rows instead of 32 scattered 16-byte stores per warp instruction).
-__global__ void __launch_bounds__(kTcThreads)
+__global__ void __launch_bounds__(kTcThreads, 2)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, TcParams p, long long zs) {
   extern __shared__ uint8_t smem_raw[];
@@ -246,6 +261,24 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kchunks = (p.C + 31) / 32;
   const int KB = p.taps * kchunks;
 
+  // TMA producer step kb.  The first min(stages, KB) steps are issued by the thread that initialises the barriers,
+  // before the block-wide sync: the first global-memory round trip overlaps the TMEM allocation and the sync.
+  auto produce = [&](int kb) {
+    const int s = kb % p.stages;
+    mbar_wait(empty_bar(s), ((kb / p.stages) & 1) ^ 1);
+    const int tap = kb / kchunks, kc = kb - tap * kchunks;
+    const uint32_t sa = base + (uint32_t)s * stage_bytes, sb = sa + b_off;
+    mbar_expect_tx(full_bar(s), (uint32_t)(p.a_box_bytes + (x3 ? 2 : 1) * b_bytes));
+    if (p.conv) {
+      const int dy = (tap / 3 - 1) * p.dil, dx = (tap % 3 - 1) * p.dil;
+      tma_load_5d(sa, &tmA, full_bar(s), kc * 32, dx, y0 + dy, img, slot);
+    } else {
+      tma_load_3d(sa, &tmA, full_bar(s), kc * 32, m0, slot);
+    }
+    tma_load_5d(sb, &tmB, full_bar(s), kc * 32, tap, n0, 0, slot);
+    if (x3) tma_load_5d(sb + b_bytes, &tmB, full_bar(s), kc * 32, tap, n0, 1, slot);
+  };
+  const int n_pre = min(p.stages, KB);
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -257,6 +290,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // barrier words (generic proxy) -> TMA (async proxy)
+    for (int kb = 0; kb < n_pre; ++kb) produce(kb);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
@@ -287,21 +322,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % p.stages;
-        mbar_wait(empty_bar(s), ((kb / p.stages) & 1) ^ 1);
-        const int tap = kb / kchunks, kc = kb - tap * kchunks;
-        const uint32_t sa = base + (uint32_t)s * stage_bytes, sb = sa + b_off;
-        mbar_expect_tx(full_bar(s), (uint32_t)(p.a_box_bytes + (x3 ? 2 : 1) * b_bytes));
-        if (p.conv) {
-          const int dy = (tap / 3 - 1) * p.dil, dx = (tap % 3 - 1) * p.dil;
-          tma_load_5d(sa, &tmA, full_bar(s), kc * 32, dx, y0 + dy, img, slot);
-        } else {
-          tma_load_3d(sa, &tmA, full_bar(s), kc * 32, m0, slot);
-        }
-        tma_load_5d(sb, &tmB, full_bar(s), kc * 32, tap, n0, 0, slot);
-        if (x3) tma_load_5d(sb + b_bytes, &tmB, full_bar(s), kc * 32, tap, n0, 1, slot);
-      }
+      for (int kb = n_pre; kb < KB; ++kb) produce(kb);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -407,40 +428,36 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int ch = half; ch < nchunks; ch += 2) {
       const int c = ch * 32, n = n0 + c;
       if (n >= p.N) break;                      // uniform over the half: whole chunk outside the tensor
-      uint32_t v[32];
-      __syncwarp();
-      {
-        uint32_t u[16];
-        tc_ld16(tbase + (uint32_t)c, u);        // warp-collective: executed by all 32 lanes, converged
-#pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = u[q];
-        if (c + 16 < p.BN) {
-          tc_ld16(tbase + (uint32_t)(c + 16), u);
-#pragma unroll
-          for (int q = 0; q < 16; ++q) v[16 + q] = u[q];
-        } else {
-#pragma unroll
-          for (int q = 0; q < 16; ++q) v[16 + q] = 0u;
-        }
-        if (wide) {
-          tc_ld16(tbase + (uint32_t)(p.BN + c), u);
-#pragma unroll
-          for (int q = 0; q < 16; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(u[q]));
-          if (c + 16 < p.BN) {
-            tc_ld16(tbase + (uint32_t)(p.BN + c + 16), u);
-#pragma unroll
-            for (int q = 0; q < 16; ++q) v[16 + q] = __float_as_uint(__uint_as_float(v[16 + q]) + __uint_as_float(u[q]));
-          }
-        }
-      }
       if (leader) tma_store_wait_read();        // the previous store of this half has finished reading the tile
       named_bar_sync_half(half);
+      // two 16-column halves: per half the accumulator (and, for 3xTF32 "wide", its a_hi*b_lo partner range) leaves
+      // TMEM with ONE wait; the bias loads are issued first.  Register budget: the kernel must keep 2 CTAs per SM.
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float4 o = f4(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
-                      __uint_as_float(v[q * 4 + 3]));
-        if (bias && n + q * 4 < p.N) o = o + ld4(bias + n + q * 4);
-        *reinterpret_cast<float4*>(stg + r * 128 + ((q ^ (r & 7)) << 4)) = o;
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int cc = c + 16 * h2;
+        const bool live = cc < p.BN;              // uniform
+        float4 add[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) add[q] = (bias && n + 16 * h2 + q * 4 < p.N) ? ld4(bias + n + 16 * h2 + q * 4) : f4s(0.f);
+        uint32_t v0[16], w0[16];
+        __syncwarp();
+        if (live) {
+          tc_ld16_nw(tbase + (uint32_t)cc, v0);   // warp-collective: executed by all 32 lanes, converged
+          if (wide) tc_ld16_nw(tbase + (uint32_t)(p.BN + cc), w0);
+          tc_ld_wait();
+        }
+        tc_ld_fence(v0); tc_ld_fence(w0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 o = f4s(0.f);
+          if (live) {
+            o = f4(__uint_as_float(v0[q * 4 + 0]), __uint_as_float(v0[q * 4 + 1]), __uint_as_float(v0[q * 4 + 2]),
+                   __uint_as_float(v0[q * 4 + 3]));
+            if (wide) o = o + f4(__uint_as_float(w0[q * 4 + 0]), __uint_as_float(w0[q * 4 + 1]), __uint_as_float(w0[q * 4 + 2]),
+                                 __uint_as_float(w0[q * 4 + 3]));
+          }
+          *reinterpret_cast<float4*>(stg + r * 128 + (((4 * h2 + q) ^ (r & 7)) << 4)) = o + add[q];
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       named_bar_sync_half(half);
@@ -471,6 +488,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //  * A and B live in separate rings (A: 2-3 slots of 32 KB, B: up to 8 slots), so the pipeline is deeper.
 // Tile rows are r = ly*(W+2d) + lx; rows with lx >= W are halo pixels whose outputs are discarded.
 // =================================================================================================
+// which filter taps read inside the image for an output pixel of border class cls = 3*ry + rx (k_pool.cu)
+__device__ __forceinline__ bool c3_tap_valid(int tap, int cls) {
+  const int ty = tap / 3, tx = tap - ty * 3, ry = cls / 3, rx = cls - ry * 3;
+  return !((ty == 0 && ry == 0) || (ty == 2 && ry == 2) || (tx == 0 && rx == 0) || (tx == 2 && rx == 2));
+}
+
 struct TcC3Params {
   int H, W, RW, BH, MT, tiles_per_image, groups_per_image;
   int C, dil, N, BN, ldc, accumulate;
@@ -478,7 +501,7 @@ struct TcC3Params {
   int a_box_bytes, a_slot_bytes, b_plane_bytes;
   int boff;          // experiment knob: 1 = set the descriptor base_offset field for shifted starts, 0 = leave it 0
   int debug;         // MLIIS_TC_DEBUG bits: 1 skip operand transform, 2 skip MMA issue, 4 one tile per CTA, 8 no wide-B
-  const float* bias9;   // [B][9][N] per-image, per-border-class bias (folded pooled branch) or null
+  const float* bias9;   // [B][9 taps][N] per-image tap vectors of the folded pooled branch (pool_taps_kernel) or null
 };
 
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc_off(uint32_t smem_addr) {
@@ -488,11 +511,11 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc_off(uint32_t smem_add
 
 __global__ void __launch_bounds__(kC3Threads)
 tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const float* __restrict__ bias, float* __restrict__ out, TcC3Params p, long long zs) {
+                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, TcC3Params p, long long zs) {
   extern __shared__ uint8_t smem_raw[];
   if (p.debug & 16) return;   // experiment: cost of everything except the tensor-core kernels
   const int slot = blockIdx.z;
-  { const size_t zo = (size_t)slot * zs; bias = zp(bias, zo); out += zo; p.bias9 = zp(p.bias9, zo); }
+  { const size_t zo = (size_t)slot * zs; bias = zp(bias, zo); p.bias9 = zp(p.bias9, zo); }
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
@@ -509,19 +532,54 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   auto b_empty = [&](int s) { return bar0 + 8u * (3 * p.SA + p.SB + s); };
   const uint32_t tmem_full_bar = bar0 + 8u * (3 * p.SA + 2 * p.SB);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_ptr + 8 * (3 * p.SA + 2 * p.SB + 1));
+  float* b9s = reinterpret_cast<float*>(bars_ptr + ((8 * (3 * p.SA + 2 * p.SB + 1) + 4 + 15) & ~15));   // [9 classes][BN] (bias9 only), 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ncols = (uint32_t)p.ncols_alloc;
   // MLIIS_TC_DEBUG bit 32: phase timestamps of CTA 0 (SM clocks since kernel entry), printed by each role's lane 0
   const bool prof = (p.debug & 32) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   const long long t_entry = prof ? clock64() : 0;
+  const int img = blockIdx.x / p.groups_per_image;
+  const int y0 = (blockIdx.x - img * p.groups_per_image) * p.MT * p.BH;
+  const int n0 = blockIdx.y * p.BN;
+  const int KC = (p.C + 31) / 32;
+  const int NA = 3 * KC;                 // A stages: (dy, kc)
+  // producer work item j = 4*ia + w: w == 0 loads the halo'd A box of stage ia = (dy, kc), w = 1..3 the weight tile of
+  // tap (dy, dx = w-1).  Items [0, n_pre) are issued by the thread that initialises the barriers, BEFORE the block-wide
+  // sync (every slot is free then): the first global-memory round trip overlaps the TMEM allocation and the sync.
+  long long w_pa = 0, w_pb = 0;
+  auto produce = [&](int j) {
+    const int ia = j >> 2, w = j & 3;
+    const int dy = ia / KC, kc = ia - dy * KC;
+    if (w == 0) {
+      const int sa = ia % p.SA;
+      const long long t0 = prof ? clock64() : 0;
+      mbar_wait(a_empty(sa), ((ia / p.SA) & 1) ^ 1);
+      if (prof) w_pa += clock64() - t0;
+      mbar_expect_tx(a_full(sa), (uint32_t)p.a_box_bytes);
+      tma_load_5d(a_base + (uint32_t)sa * a_stage, &tmA, a_full(sa), kc * 32, -p.dil, y0 + (dy - 1) * p.dil, img, slot);
+    } else {
+      const int dx = w - 1, ib = 3 * ia + dx, sb = ib % p.SB;
+      const long long t0 = prof ? clock64() : 0;
+      mbar_wait(b_empty(sb), ((ib / p.SB) & 1) ^ 1);
+      if (prof) w_pb += clock64() - t0;
+      mbar_expect_tx(b_full(sb), (uint32_t)b_stage);
+      const uint32_t dst = b_base + (uint32_t)sb * b_stage;
+      tma_load_5d(dst, &tmB, b_full(sb), kc * 32, dy * 3 + dx, n0, 0, slot);
+      if (x3) tma_load_5d(dst + p.b_plane_bytes, &tmB, b_full(sb), kc * 32, dy * 3 + dx, n0, 1, slot);
+    }
+  };
+  const int n_pre = min(4 * NA, 1 + min(p.SB, 3));
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     for (int s = 0; s < p.SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_ready(s), 128); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < p.SB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // barrier words (generic proxy) -> TMA (async proxy)
+    for (int j = 0; j < n_pre; ++j) produce(j);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
@@ -533,35 +591,10 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
 
-  const int img = blockIdx.x / p.groups_per_image;
-  const int y0 = (blockIdx.x - img * p.groups_per_image) * p.MT * p.BH;
-  const int n0 = blockIdx.y * p.BN;
-  const int KC = (p.C + 31) / 32;
-  const int NA = 3 * KC;                 // A stages: (dy, kc)
-
   if (warp == 0) {
     if (lane == 0) {
-      int ib = 0;
-      long long w_a = 0, w_b = 0;
-      for (int ia = 0; ia < NA; ++ia) {
-        const int dy = ia / KC, kc = ia - dy * KC;
-        const int sa = ia % p.SA;
-        long long t0 = prof ? clock64() : 0;
-        mbar_wait(a_empty(sa), ((ia / p.SA) & 1) ^ 1);
-        if (prof) w_a += clock64() - t0;
-        mbar_expect_tx(a_full(sa), (uint32_t)p.a_box_bytes);
-        tma_load_5d(a_base + (uint32_t)sa * a_stage, &tmA, a_full(sa), kc * 32, -p.dil, y0 + (dy - 1) * p.dil, img, slot);
-        for (int dx = 0; dx < 3; ++dx, ++ib) {
-          const int sb = ib % p.SB;
-          t0 = prof ? clock64() : 0;
-          mbar_wait(b_empty(sb), ((ib / p.SB) & 1) ^ 1);
-          if (prof) w_b += clock64() - t0;
-          mbar_expect_tx(b_full(sb), (uint32_t)b_stage);
-          const uint32_t dst = b_base + (uint32_t)sb * b_stage;
-          tma_load_5d(dst, &tmB, b_full(sb), kc * 32, dy * 3 + dx, n0, 0, slot);
-          if (x3) tma_load_5d(dst + p.b_plane_bytes, &tmB, b_full(sb), kc * 32, dy * 3 + dx, n0, 1, slot);
-        }
-      }
+      for (int j = n_pre; j < 4 * NA; ++j) produce(j);
+      const long long w_a = w_pa, w_b = w_pb;
       if (prof) printf("[c3 producer] NA %d SA %d SB %d | done issuing at %lld | waited a_empty %lld b_empty %lld\n", NA, p.SA,
                        p.SB, clock64() - t_entry, w_a, w_b);
     }
@@ -624,6 +657,24 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     const int t = threadIdx.x - 64;
     long long w_x = 0, t_x = 0;
+    if (p.bias9) {
+      // border-class biases of this image into shared memory while the first loads are in flight: thread j owns output
+      // column n0 + j, reads its 9 tap values (one coalesced round trip) and forms the 9 class sums in tap order
+      for (int j = t; j < p.BN; j += 128) {
+        float tv[9];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) tv[tap] = n0 + j < p.N ? p.bias9[((size_t)img * 9 + tap) * p.N + n0 + j] : 0.f;
+#pragma unroll
+        for (int cls = 0; cls < 9; ++cls) {
+          float acc = 0.f;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap)
+            if (c3_tap_valid(tap, cls)) acc += tv[tap];
+          b9s[cls * p.BN + j] = acc;
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     if (x3) {
       const int n4 = p.a_box_bytes / 16;
       for (int ia = 0; ia < NA; ++ia) {
@@ -644,49 +695,80 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (prof) { w_x += t1 - t0; t_x += clock64() - t1; }
       }
     }
+    // ---- epilogue: TMEM -> registers (+ bias, + border-class bias) -> swizzled shared-memory tile holding only the
+    // tile's real pixels (halo rows dropped: packed row = ly * W + lx) -> one TMA store per 32 output columns.  Two
+    // staging tiles alternate in the (now idle) stage ring; the TMA unit clips rows past the image and columns past N.
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
+    const bool leader = threadIdx.x == 64;
     const long long t_w0 = prof ? clock64() : 0;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const long long t_e0 = prof ? clock64() : 0;
     const int ly = r / p.RW, lx = r - ly * p.RW;
+    const bool rowok = ly < p.BH && lx < p.W;
+    const int pr = ly * p.W + lx;                       // packed pixel row of the staging tile
+    const int nchunks = (p.BN + 31) / 32;
+    int it = 0;
     for (int tile = 0; tile < p.MT; ++tile) {
-      const int y = y0 + tile * p.BH + ly;
-      const bool valid = ly < p.BH && lx < p.W && y < p.H;
-      float* orow = out + (((size_t)img * p.H + y) * p.W + lx) * p.ldc;
+      const int yt = y0 + tile * p.BH;
+      if (yt >= p.H) break;                             // uniform: the whole tile lies below the image
+      const int y = yt + ly;
       const float* b9 = nullptr;
       if (p.bias9) {   // border class of this output pixel: which filter taps read inside the image (k_pool.cu)
-        const int cls = (y < p.dil ? 0 : (y >= p.H - p.dil ? 2 : 1)) * 3 + (lx < p.dil ? 0 : (lx >= p.W - p.dil ? 2 : 1));
-        b9 = p.bias9 + ((size_t)img * 9 + cls) * p.N;
+        const int yy = min(y, p.H - 1), xx = min(lx, p.W - 1);
+        const int cls = (yy < p.dil ? 0 : (yy >= p.H - p.dil ? 2 : 1)) * 3 + (xx < p.dil ? 0 : (xx >= p.W - p.dil ? 2 : 1));
+        b9 = b9s + cls * p.BN;     // shared memory, indexed by the column inside this CTA's N tile
       }
       const uint32_t tbase = tmem_acc + (uint32_t)(tile * p.ncol_acc) + ((uint32_t)(quarter * 32) << 16);
-      for (int c = 0; c < p.BN; c += 16) {
-        uint32_t v[16];
-        __syncwarp();
-        tc_ld16(tbase + (uint32_t)c, v);
-        if (p.wide) {
-          uint32_t w[16];
-          tc_ld16(tbase + (uint32_t)(p.BN + c), w);
+      for (int ch = 0; ch < nchunks; ++ch, ++it) {
+        const int c = ch * 32, n = n0 + c;
+        if (n >= p.N) break;                            // uniform
+        // per-column additive terms first (global loads in flight while the accumulator comes out of TMEM)
+        float4 add[8];
 #pragma unroll
-          for (int q = 0; q < 16; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(w[q]));
-        }
-        if (valid) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int n = n0 + c + q * 4;
-            if (n < p.N) {
-              float4 o = f4(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
-                            __uint_as_float(v[q * 4 + 3]));
-              if (bias) o = o + ld4(bias + n);
-              if (b9) o = o + ld4(b9 + n);
-              if (p.accumulate) o = o + ld4(orow + n);
-              st4(orow + n, o);
-            }
+        for (int q = 0; q < 8; ++q) {
+          add[q] = f4s(0.f);
+          if (n + q * 4 < p.N) {
+            if (bias) add[q] = ld4(bias + n + q * 4);
+            if (b9 && c + q * 4 < p.BN) add[q] = add[q] + ld4(b9 + c + q * 4);
           }
+        }
+        uint32_t v0[16], v1[16], w0[16], w1[16];
+        const bool second = c + 16 < p.BN;       // uniform
+        __syncwarp();
+        tc_ld16_nw(tbase + (uint32_t)c, v0);     // warp-collective: executed by all 32 lanes, converged
+        if (second) tc_ld16_nw(tbase + (uint32_t)(c + 16), v1);
+        if (p.wide) {
+          tc_ld16_nw(tbase + (uint32_t)(p.BN + c), w0);
+          if (second) tc_ld16_nw(tbase + (uint32_t)(p.BN + c + 16), w1);
+        }
+        tc_ld_wait();
+        tc_ld_fence(v0); tc_ld_fence(v1); tc_ld_fence(w0); tc_ld_fence(w1);
+        float o[32];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          o[q] = __uint_as_float(v0[q]) + (p.wide ? __uint_as_float(w0[q]) : 0.f);
+          o[16 + q] = second ? __uint_as_float(v1[q]) + (p.wide ? __uint_as_float(w1[q]) : 0.f) : 0.f;
+        }
+        uint8_t* stg = smem + (it & 1) * 16384;
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last read this tile is done
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (rowok) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(stg + pr * 128 + ((q ^ (pr & 7)) << 4)) =
+                f4(o[q * 4 + 0], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]) + add[q];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (leader) {
+          tma_store_4d(&tmC, base + (uint32_t)(it & 1) * 16384u, n, yt * p.W, img, slot, p.accumulate != 0);
+          tma_store_commit();
         }
       }
     }
+    if (leader) tma_store_wait_read();          // shared memory must stay valid until the TMA unit has read it
     if (prof && t == 0)
       printf("[c3 xform/epilogue] transform: waited a_full %lld, worked %lld | waited for the accumulators %lld | epilogue "
              "%lld .. %lld (%lld clk)\n", w_x, t_x, t_e0 - t_w0, t_e0 - t_entry, clock64() - t_entry, clock64() - t_e0);
@@ -1051,8 +1133,16 @@ static bool tc_conv3(const float* A, int lda, const float* Wt, const float* bias
     cuuint32_t box[5] = {32, 1, (cuuint32_t)(pair ? p.BN / 2 : p.BN), 1, 1};
     if (!encode(&tmB, Wt, 5, dims, str, box)) return false;
   }
+  CUtensorMap tmC;
+  if (!pair) {
+    // output [slot, B, H*W, N]: one box = the BH*W pixels of a tile x 32 columns (rows past the image are clipped)
+    cuuint64_t cd[4] = {(cuuint64_t)N, (cuuint64_t)H * W, (cuuint64_t)B, (cuuint64_t)MLIIS_NZ};
+    cuuint64_t cs[3] = {(cuuint64_t)ldc * 4, (cuuint64_t)H * W * ldc * 4, slot_stride_bytes((cuuint64_t)B * H * W * ldc * 4)};
+    cuuint32_t cb[4] = {32, (cuuint32_t)(p.BH * W), 1, 1};
+    if (p.BH * W > 128 || !encode(&tmC, out, 4, cd, cs, cb)) return false;
+  }
   const size_t smem = (size_t)p.SA * planes * p.a_slot_bytes + (size_t)p.SB * planes * p.b_plane_bytes +
-                      (3 * p.SA + 3 * p.SB + 2) * 8 + 1024;
+                      (3 * p.SA + 3 * p.SB + 2) * 8 + 32 + (bias9 ? 9 * p.BN * 4 : 0) + 1024;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1076,7 +1166,7 @@ static bool tc_conv3(const float* A, int lda, const float* Wt, const float* bias
     return true;
   }
   dim3 grid(n_ctas, (N + p.BN - 1) / p.BN, MLIIS_NZ);
-  MLIIS_COUNT(), tc_conv3_kernel<<<grid, kC3Threads, smem, s>>>(tmA, tmB, bias, out, p, MLIIS_ZS);
+  MLIIS_COUNT(), tc_conv3_kernel<<<grid, kC3Threads, smem, s>>>(tmA, tmB, tmC, bias, p, MLIIS_ZS);
   return true;
 }
 
@@ -1236,12 +1326,42 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int ntap = p.share ? 3 : 1;
   uint32_t ncols = 32;
   while ((int)ncols < (p.share ? 3 * p.BN : (wide ? 2 * wide_off : p.BN))) ncols <<= 1;
+  const int c0 = blockIdx.x * 128, tap = blockIdx.y, split = blockIdx.z - slot * p.splits;
+  const int per = (p.tiles_total + p.splits - 1) / p.splits;
+  const int t_beg = split * per, t_end = min(p.tiles_total, t_beg + per);
+  const int KB = max(t_end - t_beg, 0);
+  const int dy = p.conv ? ((p.share ? tap : tap / 3) - 1) * p.dil : 0;
+  const int dx = p.conv ? (p.share ? -p.dil : (tap % 3 - 1) * p.dil) : 0;       // share: left edge of the halo box
+
+  // TMA producer step kb; the first min(stages, KB) steps are issued before the block-wide sync (see tc_conv_kernel)
+  auto produce = [&](int kb) {
+    const int s = kb % p.stages;
+    mbar_wait(empty_bar(s), ((kb / p.stages) & 1) ^ 1);
+    const uint32_t sa = base + (uint32_t)s * stage_bytes, sg = sa + g_off;
+    mbar_expect_tx(full_bar(s), (uint32_t)((p.share ? p.a_tx_bytes : a_bytes) + g_bytes));
+    const int t = t_beg + kb;
+    if (p.conv) {
+      const int per_img = p.tiles_x * p.tiles_y;
+      const int img = t / per_img, rem = t - img * per_img, ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int x0 = tx * p.BX, y0 = ty * p.BY;
+      for (int g = 0; g < 4; ++g)
+        tma_load_5d(sa + g * a_group, &tmA, full_bar(s), c0 + 32 * g, x0 + dx, y0 + dy, img, slot);
+      for (int g = 0; g < p.NG; ++g) tma_load_5d(sg + g * kWgGroupBytes, &tmG, full_bar(s), 32 * g, x0, y0, img, slot);
+    } else {
+      const int m0 = t * 32;
+      for (int g = 0; g < 4; ++g) tma_load_3d(sa + g * kWgGroupBytes, &tmA, full_bar(s), c0 + 32 * g, m0, slot);
+      for (int g = 0; g < p.NG; ++g) tma_load_3d(sg + g * kWgGroupBytes, &tmG, full_bar(s), 32 * g, m0, slot);
+    }
+  };
+  const int n_pre = min(p.stages, KB);
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(ready_bar(s), kWgXformThreads); }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // barrier words (generic proxy) -> TMA (async proxy)
+    for (int kb = 0; kb < n_pre; ++kb) produce(kb);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
@@ -1253,34 +1373,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
 
-  const int c0 = blockIdx.x * 128, tap = blockIdx.y, split = blockIdx.z - slot * p.splits;
-  const int per = (p.tiles_total + p.splits - 1) / p.splits;
-  const int t_beg = split * per, t_end = min(p.tiles_total, t_beg + per);
-  const int KB = max(t_end - t_beg, 0);
-  const int dy = p.conv ? ((p.share ? tap : tap / 3) - 1) * p.dil : 0;
-  const int dx = p.conv ? (p.share ? -p.dil : (tap % 3 - 1) * p.dil) : 0;       // share: left edge of the halo box
-
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % p.stages;
-        mbar_wait(empty_bar(s), ((kb / p.stages) & 1) ^ 1);
-        const uint32_t sa = base + (uint32_t)s * stage_bytes, sg = sa + g_off;
-        mbar_expect_tx(full_bar(s), (uint32_t)((p.share ? p.a_tx_bytes : a_bytes) + g_bytes));
-        const int t = t_beg + kb;
-        if (p.conv) {
-          const int per_img = p.tiles_x * p.tiles_y;
-          const int img = t / per_img, rem = t - img * per_img, ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-          const int x0 = tx * p.BX, y0 = ty * p.BY;
-          for (int g = 0; g < 4; ++g)
-            tma_load_5d(sa + g * a_group, &tmA, full_bar(s), c0 + 32 * g, x0 + dx, y0 + dy, img, slot);
-          for (int g = 0; g < p.NG; ++g) tma_load_5d(sg + g * kWgGroupBytes, &tmG, full_bar(s), 32 * g, x0, y0, img, slot);
-        } else {
-          const int m0 = t * 32;
-          for (int g = 0; g < 4; ++g) tma_load_3d(sa + g * kWgGroupBytes, &tmA, full_bar(s), c0 + 32 * g, m0, slot);
-          for (int g = 0; g < p.NG; ++g) tma_load_3d(sg + g * kWgGroupBytes, &tmG, full_bar(s), 32 * g, m0, slot);
-        }
-      }
+      for (int kb = n_pre; kb < KB; ++kb) produce(kb);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -1441,8 +1536,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 static int wg_splits(int ctiles, int taps, int tiles_total) {
+  // CTAs per launch the pixel range is split for.  One CTA per SM: every split writes a full [taps*C, N] fp32 partial
+  // that reduce_partials reads back, so 296 (two waves at one resident CTA per SM) doubled that traffic for nothing -
+  // measured on the whole job: 296 -> 104.5, 222 -> 107.2, 148 -> 109.2 tasks/s (MLIIS_WG_TARGET overrides).
+  static int target = -1;
+  if (target < 0) { const char* e = getenv("MLIIS_WG_TARGET"); target = e ? atoi(e) : 148; }
   int base = ctiles * taps;
-  int S = 296 / base;
+  int S = target / base;
   if (S < 1) S = 1;
   if (S > tiles_total / 2) S = tiles_total / 2;   // at least 2 pixel tiles (64 pixels) per CTA
   if (S > 148) S = 148;

@@ -135,7 +135,8 @@ bool tc_supported(int conv, int W, int C, int N);
 // split = 1: TF32 with round-to-nearest operands; split = 3: 3xTF32 (hi/lo planes, fp32-class accuracy).
 // Optional A prologue (conv = 0 only): a <- swish(pa[k]*a + pb[k]) * gate[row / HW][k], applied in shared memory by
 // the transform warps (MBConv project conv: BN1 + swish + squeeze-excite gate never touch HBM).
-// bias9 (3x3 only): per-image, per-border-class bias [B][9][N] added in the epilogue (folded pooled branch, k_pool.cu);
+// bias9 (3x3 only): per-image, per-TAP vectors [B][9][N] of the folded pooled branch (k_pool.cu); the kernel sums the taps
+// valid in each border class and adds that class bias in the epilogue;
 // returns false if the shape does not fit the kernel that implements it (tc_conv3_kernel).
 bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float* out, int ldc, int conv, int M, int B,
              int H, int W, int C, int taps, int dil, int N, int accumulate, int split, cudaStream_t s,
@@ -165,7 +166,8 @@ bool tc_wgrad(const float* A, int lda, const float* G, int ldg, float* dW, float
 // ---------------- folded image-pooling branch of the RSD decoder (k_pool.cu) ----------------
 // w_hwio: conv2d_2 kernel [9][Cs][D]; the pooled channels are rows c_first .. c_first+Cp of every tap.
 void pool_bias9(const float* pooled, int ldp, const float* w_hwio, int Cs, int c_first, int Cp, int D, int B,
-                float* bias9 /* [B][9][D] */, cudaStream_t s);
+                float* tap9 /* [B][9 taps][D]: per-tap vectors, folded into border-class biases by tc_conv3_kernel */,
+                cudaStream_t s);
 int region_sums_chunks(int HW, int D);
 // S[b][tap][n] = sum of g over the output pixels at which `tap` reads inside the image; partial: [B][chunks][9][D]
 void region_sums(const float* g, int ldg, int B, int H, int W, int dil, int D, float* partial, float* S, cudaStream_t s);

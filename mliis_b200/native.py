@@ -96,6 +96,7 @@ SYMBOLS = [
     ("mliis_conv3x3_fwd", C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     ("mliis_tc_prep_weights", C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
     ("mliis_tc_conv", C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
+    ("mliis_tc_project_conv", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP]),
     ("mliis_tc_wgrad", C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     ("mliis_bilinear_fwd", C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     ("mliis_adam_step", C.c_int, [_VP, _VP, _VP, _I64, _I64, _F, _F, _F, _VP]),

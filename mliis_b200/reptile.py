@@ -41,6 +41,29 @@ def _dist():
     return 0, 1
 
 
+class _ExamplePool:
+    """The distinct (image, mask) arrays one task feeds to the device, in first-use order.  An example the augmenter
+    returned untouched is the support example itself (same array objects) and shares its row; every augmented copy is
+    a new row.  Inner batches / the query set are then rows of this pool (TaskPlan.batch_index / query_index)."""
+
+    def __init__(self):
+        self.images, self.labels, self._row = [], [], {}
+
+    def row(self, image, label) -> int:
+        key = (id(image), id(label))
+        r = self._row.get(key)
+        if r is None:
+            r = len(self.images)
+            self._row[key] = r
+            self.images.append(image)      # keeps the arrays alive: ids stay unique
+            self.labels.append(label)
+        return r
+
+    def arrays(self):
+        return (np.stack([np.asarray(a, np.float32) for a in self.images]),
+                np.stack([np.asarray(a, np.float32) for a in self.labels]))
+
+
 class Gecko:
     """A meta-learning session for image segmentation that extends Reptile (reptile.py:23-62)."""
 
@@ -57,11 +80,10 @@ class Gecko:
         self.eval_sample_number = 0
         self.lr_scheduler = lr_scheduler
         if augment:
-            # host numpy augmentations (reptile.py:48-52): every batch goes through host arrays, so the Session path
-            # is used; the device fast path is for un-augmented (parity / benchmark) configurations
+            # host numpy augmentations (reptile.py:48-52), drawn with the reference's RNG call order.  The device fast
+            # path stays on: every augmented example becomes a row of the task's example pool (_ExamplePool below)
             from .np_augmenters import Augmenter
             self.augmenter = Augmenter()
-            fast_path = False
         else:
             self.augmenter = None
         self.aug_rate = aug_rate
@@ -115,7 +137,7 @@ class Gecko:
     def train_step(self, dataset, input_ph, label_ph, minimize_op, num_classes, num_shots, inner_batch_size,
                    inner_iters, replacement, meta_step_size, meta_batch_size, lr_ph=None, lr=None, verbose=False):
         num_classes = 1      # hardcoded binary Gecko (reptile.py:99-100)
-        if self.fast_path:
+        if self.fast_path and self.augmenter is None:      # augmented meta-TRAINING batches go through the Session path
             return self._train_step_device(dataset, num_shots, inner_batch_size, inner_iters, replacement,
                                            meta_step_size, meta_batch_size, lr_ph, lr, fomaml=False)
         old_vars = self._model_state.export_variables()
@@ -275,7 +297,7 @@ class Gecko:
                      and inner_iters > 0 and all(hasattr(t, "arrays") for t in sampled_tasks))
         if device_ok:
             ious, task_iou_map = self._evaluate_device(sampled_tasks, num_shots, test_shots, inner_batch_size,
-                                                       inner_iters, replacement, lr_ph, lr)
+                                                       inner_iters, replacement, lr_ph, lr, aug_rate)
         else:
             ious, task_iou_map = [], {}
             for sampled_task in sampled_tasks:
@@ -298,39 +320,64 @@ class Gecko:
         return mean_iou_score, task_iou_map
 
     def _evaluate_device(self, sampled_tasks, num_shots, test_shots, inner_batch_size, inner_iters, replacement,
-                         lr_ph, lr):
+                         lr_ph, lr, aug_rate=None):
         """All tasks of one evaluation pass on the device, sharded over slots and ranks.  The host draws the
-        plans sequentially (same `random` consumption as the reference), the device adapts them concurrently."""
-        from .runner import TaskPlan, iou_from_counts
-        import torch
+        plans sequentially (same `random` / `np.random` consumption as the reference), the device adapts them
+        concurrently.  With an augmenter (run.sh: --augment --aug_rate 0.5) every inner batch consists of freshly
+        augmented copies (metaseg.py:258-302, np_augmenters.py:135-160): they are produced on the host by the
+        bit-exact numpy mirror, in the reference's draw order, and staged as extra rows of the task's example pool;
+        tasks are then drawn and run in chunks of n_slots so that only a few pools are alive at a time."""
+        from .runner import TaskPlan, gather_owned, iou_from_counts
         rank, world = _dist()
-        plans, names = [], []
-        for task in sampled_tasks:
+        eng = self._model.engine()
+        names, owned, task_plans = [], [], []
+        n_pool = num_shots + test_shots
+        if self.augmenter is not None:
+            n_pool += inner_iters * inner_batch_size
+        runner = self._get_runner(n_pool, inner_iters, inner_batch_size, test_shots)
+        runner.set_init_state(eng.states[0])          # old_vars = _full_state.export_variables() (reptile.py:258)
+        ious_local = np.full(len(sampled_tasks), np.nan, np.float64)
+
+        def flush():
+            for i, (inter, uni) in zip(owned, runner.run(task_plans)):
+                ious_local[i] = iou_from_counts(inter, uni)
+            owned.clear()
+            task_plans.clear()
+
+        for i, task in enumerate(sampled_tasks):
             obj, rows = _sample_task_indices([task], num_shots + test_shots)
             names.append(obj.name)
             print("Evaluating {}".format(obj.name))
-            train, test = _split_train_test_segmentation(rows, test_shots)
-            batches = list(_mini_batches(train, inner_batch_size, inner_iters, replacement, augmenter=None))
-            lrs = [self._inner_lr(lr_ph, lr, s, True) for s in range(inner_iters)]
-            plans.append((obj, np.asarray(batches, np.int32), np.asarray(lrs, np.float32), np.asarray(test, np.int32)))
-        n_pool = num_shots + test_shots
-        runner = self._get_runner(n_pool, inner_iters, inner_batch_size, test_shots)
-        eng = self._model.engine()
-        runner.set_init_state(eng.states[0])          # old_vars = _full_state.export_variables() (reptile.py:258)
-        from .runner import gather_owned, owned_indices
-        mine = owned_indices(len(plans), rank, world)
-        task_plans = []
-        for i in mine:
-            obj, bi, lrs, qi = plans[i]
-            images, labels = obj.arrays()
-            task_plans.append(TaskPlan(images[:n_pool], labels[:n_pool], bi, lrs, qi, None, obj.name))
-        results = runner.run(task_plans)
+            lrs = np.asarray([self._inner_lr(lr_ph, lr, s, True) for s in range(inner_iters)], np.float32)
+            mine = i % world == rank
+            if self.augmenter is None:
+                train, test = _split_train_test_segmentation(rows, test_shots)
+                batches = list(_mini_batches(train, inner_batch_size, inner_iters, replacement, augmenter=None))
+                if mine:
+                    images, labels = obj.arrays()
+                    task_plans.append(TaskPlan(images[:n_pool], labels[:n_pool], np.asarray(batches, np.int32), lrs,
+                                               np.asarray(test, np.int32), None, obj.name))
+            else:
+                # every rank runs the augmenter for every task: the two global RNG streams stay rank-identical
+                images, labels = obj.arrays()
+                samples = [[images[r], labels[r]] for r in rows]           # == task.sample(sess, n)
+                train, test = _split_train_test_segmentation(samples, test_shots)
+                pool = _ExamplePool()
+                batches = [[pool.row(ex[0], ex[1]) for ex in batch]
+                           for batch in _mini_batches(train, inner_batch_size, inner_iters, replacement,
+                                                      augmenter=self.augmenter, aug_rate=aug_rate)]
+                query = [pool.row(ex[0], ex[1]) for ex in test]
+                if mine:
+                    pi, pl = pool.arrays()
+                    task_plans.append(TaskPlan(pi, pl, np.asarray(batches, np.int32), lrs, np.asarray(query, np.int32),
+                                               None, obj.name))
+            if mine:
+                owned.append(i)
+            if self.augmenter is not None and len(task_plans) >= eng.n_slots:
+                flush()
+        flush()
         eng.states[0].copy_(runner.init_state)        # slot 0 doubles as a task slot: put the model state back
-        ious_local = np.full(len(plans), np.nan, np.float64)
-        for i, (inter, uni) in zip(mine, results):
-            ious_local[i] = iou_from_counts(inter, uni)
-        ious_local = gather_owned(ious_local, eng.device)
-        ious = [float(v) for v in ious_local]
+        ious = [float(v) for v in gather_owned(ious_local, eng.device)]
         for n, v in zip(names, ious):
             print("Mean task IoU: {}".format(v))
         # the engine state was never touched (tasks ran on slot copies): _full_state.import_variables is a no-op
@@ -590,7 +637,7 @@ class FOMLIS(Gecko):
 
     def train_step(self, dataset, input_ph, label_ph, minimize_op, num_classes, num_shots, inner_batch_size,
                    inner_iters, replacement, meta_step_size, meta_batch_size, verbose=False, lr_ph=None, lr=None):
-        if self.fast_path:
+        if self.fast_path and self.augmenter is None:      # augmented meta-TRAINING batches go through the Session path
             return self._train_step_device(dataset, num_shots, inner_batch_size, inner_iters, replacement,
                                            meta_step_size, meta_batch_size, lr_ph, lr, fomaml=True)
         old_vars = self._model_state.export_variables()

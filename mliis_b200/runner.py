@@ -39,7 +39,8 @@ class _SlotBuffers:
     """Per-slot task inputs / outputs, carved out of the slot's staging region of the engine arena so that every slot
     has them at the same offset (a task-batched launch addresses slot k as pointer + k * slot_stride)."""
 
-    def __init__(self, eng: Engine, slot: int, n_pool: int, T: int, B: int, nq: int, with_dc: bool):
+    def __init__(self, eng: Engine, slot: int, n_pool: int, T: int, B: int, nq: int, with_dc: bool,
+                 standalone: bool = False):
         S = eng.image_size
         # one small block: [dropout seed (one int64) | batch_index T*B | query nq] int32, [lr T | dc T*n_dc*B] f32
         self.n_i = 2 + T * B + nq
@@ -56,17 +57,39 @@ class _SlotBuffers:
             t = stg[off:off + nbytes].view(dtype)
             off = (off + nbytes + 255) // 256 * 256
             return t
-        self.images = carve(n_pool * S * S * 3, torch.float32).view(n_pool, S, S, 3)
-        self.labels = carve(n_pool * S * S * 2, torch.float32).view(n_pool, S, S, 2)
+        pool_bytes = n_pool * S * S * 5 * 4
+        if standalone and pool_bytes + (1 << 16) > stg.numel():
+            # a pool larger than the arena's staging region (augmented tasks: every inner batch brings its own images);
+            # only single-slot launches may keep it outside the uniform-stride arena
+            self.images = torch.empty(n_pool, S, S, 3, dtype=torch.float32, device=eng.device)
+            self.labels = torch.empty(n_pool, S, S, 2, dtype=torch.float32, device=eng.device)
+        else:
+            self.images = carve(n_pool * S * S * 3, torch.float32).view(n_pool, S, S, 3)
+            self.labels = carve(n_pool * S * S * 2, torch.float32).view(n_pool, S, S, 2)
         self.ints = carve(self.n_i, torch.int32)
         self.floats = carve(max(self.n_f, 1), torch.float32)[:self.n_f]
         self.counts = carve(2 * nq, torch.int32)
         self.losses = carve(T, torch.float32)
-        self.h_images = torch.empty(n_pool, S, S, 3, dtype=torch.float32).pin_memory()
-        self.h_labels = torch.empty(n_pool, S, S, 2, dtype=torch.float32).pin_memory()
-        self.h_ints = torch.zeros(self.n_i, dtype=torch.int32).pin_memory()
-        self.h_floats = torch.zeros(self.n_f, dtype=torch.float32).pin_memory()
+        # two pinned host sets per slot: a staging worker fills one while the H2D copies of the other are in flight
+        self.host = [_HostSet(S, self.n_i, self.n_f), _HostSet(S, self.n_i, self.n_f)]
         self.h_counts = torch.zeros(2 * nq, dtype=torch.int32).pin_memory()
+
+
+class _HostSet:
+    """Pinned host staging of one task's inputs (example pool grown to the largest pool seen)."""
+
+    def __init__(self, S: int, n_i: int, n_f: int):
+        self._S = S
+        self.images = self.labels = None
+        self.ints = torch.zeros(n_i, dtype=torch.int32).pin_memory()
+        self.floats = torch.zeros(n_f, dtype=torch.float32).pin_memory()
+        self.h2d_done: Optional[torch.cuda.Event] = None      # recorded after the set's H2D copies were queued
+
+    def ensure(self, n: int) -> None:
+        if self.images is None or self.images.shape[0] < n:
+            S = self._S
+            self.images = torch.empty(n, S, S, 3, dtype=torch.float32).pin_memory()
+            self.labels = torch.empty(n, S, S, 2, dtype=torch.float32).pin_memory()
 
 
 class _Group:
@@ -98,12 +121,15 @@ class TaskRunner:
         self.with_dc = with_dc_masks
         self.pre_decay_rate = pre_decay_rate
         self.group = group
-        self.slots = [_SlotBuffers(eng, s, n_pool, n_steps, batch, n_query, with_dc_masks) for s in range(eng.n_slots)]
+        self.slots = [_SlotBuffers(eng, s, n_pool, n_steps, batch, n_query, with_dc_masks, standalone=group == 1)
+                      for s in range(eng.n_slots)]
         self.groups = [_Group(eng, g * group, group) for g in range(eng.n_slots // group)]
         self.init_state = torch.zeros(eng.state_floats, dtype=torch.float32, device=eng.device)
         self._captured = False
         self.seed_base = 0          # final-layer dropout: task k of this runner draws its masks from seed_base + k
         self._tasks_staged = 0
+        from concurrent.futures import ThreadPoolExecutor
+        self._pool = ThreadPoolExecutor(max_workers=3, thread_name_prefix="mliis-stage")
         self.h2d_bytes_per_task = 0
         self.d2h_bytes_per_task = 0
 
@@ -150,38 +176,54 @@ class TaskRunner:
             a = self._task_args(g)
             N.check(lib.mliis_adapt_eval_task(h, g.first, C.byref(a), st))
 
-    def _stage(self, slot: int, plan: TaskPlan, stream) -> None:
+    def _fill_host(self, slot: int, which: int, plan: TaskPlan, seed: int) -> None:
+        """Host arrays -> the slot's pinned set `which` (runs on a staging worker thread; numpy / torch copies release
+        the GIL, so this overlaps the main thread's launches)."""
+        torch.cuda.set_device(self.eng.device)       # worker threads start on device 0: pin / wait on the engine's GPU
         sb = self.slots[slot]
+        hs = sb.host[which]
         T, B, nq = self.T, self.B, self.nq
         bi = np.asarray(plan.batch_index, np.int32).reshape(-1)
         qi = np.asarray(plan.query_index, np.int32).reshape(-1)
         if bi.size != T * B or qi.size != nq:
             raise ValueError("plan shape mismatch: batch_index %s, query_index %s" % (bi.shape, qi.shape))
-        self._tasks_staged += 1
-        sb.h_ints[:2].view(torch.int64)[0] = self.seed_base + self._tasks_staged
-        sb.h_ints[2:2 + T * B] = torch.from_numpy(bi)
-        sb.h_ints[2 + T * B:] = torch.from_numpy(qi)
-        sb.h_floats[:T] = torch.from_numpy(np.asarray(plan.lrs, np.float32).reshape(-1))
+        if hs.h2d_done is not None:
+            hs.h2d_done.synchronize()          # the copies that last read this set have left the host
+        hs.ints[:2].view(torch.int64)[0] = seed
+        hs.ints[2:2 + T * B] = torch.from_numpy(bi)
+        hs.ints[2 + T * B:] = torch.from_numpy(qi)
+        hs.floats[:T] = torch.from_numpy(np.asarray(plan.lrs, np.float32).reshape(-1))
         if self.with_dc:
             dc = plan.dc_mask if plan.dc_mask is not None else np.ones((T, self.eng.n_dc, B), np.float32)
-            sb.h_floats[T:] = torch.from_numpy(np.asarray(dc, np.float32).reshape(-1))
+            hs.floats[T:] = torch.from_numpy(np.asarray(dc, np.float32).reshape(-1))
+        if not (isinstance(plan.images, torch.Tensor) and plan.images.is_cuda):
+            n = plan.images.shape[0]
+            if n > self.n_pool:
+                raise ValueError("task pool of %d examples exceeds the runner's n_pool (%d)" % (n, self.n_pool))
+            hs.ensure(n)
+            hs.images[:n] = torch.from_numpy(np.ascontiguousarray(plan.images, np.float32))
+            hs.labels[:n] = torch.from_numpy(np.ascontiguousarray(plan.labels, np.float32))
+
+    def _enqueue_h2d(self, slot: int, which: int, plan: TaskPlan, stream) -> None:
+        sb = self.slots[slot]
+        hs = sb.host[which]
         with torch.cuda.stream(stream):
             h2d = 0
+            n = plan.images.shape[0]
             if isinstance(plan.images, torch.Tensor) and plan.images.is_cuda:
-                n = plan.images.shape[0]
                 sb.images[:n].copy_(plan.images, non_blocking=True)     # resident pool: device-to-device
                 sb.labels[:n].copy_(plan.labels, non_blocking=True)
             else:
-                n = plan.images.shape[0]
-                sb.h_images[:n] = torch.from_numpy(np.ascontiguousarray(plan.images, np.float32))
-                sb.h_labels[:n] = torch.from_numpy(np.ascontiguousarray(plan.labels, np.float32))
-                sb.images[:n].copy_(sb.h_images[:n], non_blocking=True)
-                sb.labels[:n].copy_(sb.h_labels[:n], non_blocking=True)
-                h2d += sb.h_images[:n].numel() * 4 + sb.h_labels[:n].numel() * 4
-            sb.ints.copy_(sb.h_ints, non_blocking=True)
+                sb.images[:n].copy_(hs.images[:n], non_blocking=True)
+                sb.labels[:n].copy_(hs.labels[:n], non_blocking=True)
+                h2d += hs.images[:n].numel() * 4 + hs.labels[:n].numel() * 4
+            sb.ints.copy_(hs.ints, non_blocking=True)
             if sb.n_f:
-                sb.floats.copy_(sb.h_floats, non_blocking=True)
-            h2d += sb.h_ints.numel() * 4 + sb.h_floats.numel() * 4
+                sb.floats.copy_(hs.floats, non_blocking=True)
+            h2d += hs.ints.numel() * 4 + hs.floats.numel() * 4
+            if hs.h2d_done is None:
+                hs.h2d_done = torch.cuda.Event()
+            hs.h2d_done.record(stream)
         self.h2d_bytes_per_task = h2d
         self.d2h_bytes_per_task = sb.h_counts.numel() * 4
 
@@ -206,16 +248,40 @@ class TaskRunner:
         cur = torch.cuda.current_stream()
         for g in self.groups:
             g.stream.wait_stream(cur)
-        for ci, i0 in enumerate(range(0, len(plans), G)):
+        # host staging runs AHEAD of the launches on worker threads: while chunk ci is being launched, the pinned sets
+        # of the next `ng` chunks (one per group, the set the group is not reading from) are already being filled
+        chunks = list(range(0, len(plans), G))
+
+        def plan_of(i):     # a short last chunk re-runs the previous plan in the idle slots of the group (discarded)
+            return plans[i] if i < len(plans) else plans[len(plans) - 1]
+
+        fills = {}
+
+        def submit_fill(ci):
+            g = self.groups[ci % ng]
+            which = (ci // ng) & 1      # successive tasks of a group alternate between its two pinned sets
+            futs = []
+            for k in range(G):
+                self._tasks_staged += 1
+                futs.append(self._pool.submit(self._fill_host, g.first + k, which, plan_of(chunks[ci] + k),
+                                              self.seed_base + self._tasks_staged))
+            fills[ci] = (which, futs)
+
+        n_ahead = ng
+        for ci in range(min(n_ahead, len(chunks))):
+            submit_fill(ci)
+        for ci, i0 in enumerate(chunks):
             g = self.groups[ci % ng]
             if g.busy:
                 self._collect(g, results)
+            if ci + n_ahead < len(chunks):
+                submit_fill(ci + n_ahead)
+            which, futs = fills.pop(ci)
             g.tags = []
             for k in range(G):
+                futs[k].result()                       # re-raises a worker's exception
                 i = i0 + k
-                # a short last chunk re-runs the previous plan in the idle slots of the group (result discarded)
-                plan = plans[i] if i < len(plans) else plans[len(plans) - 1]
-                self._stage(g.first + k, plan, g.stream)
+                self._enqueue_h2d(g.first + k, which, plan_of(i), g.stream)
                 g.tags.append(i if i < len(plans) else None)
             self._launch(g)
             with torch.cuda.stream(g.stream):

@@ -208,21 +208,38 @@ def test_early_stopping_k_shot_curves_and_uho(tmp_path):
     assert any(f.startswith("GP_val-set_hyper_param_search_results_5-shot") for f in os.listdir(str(tmp_path)))
 
 
-def test_augmented_adaptation_runs_on_the_session_path():
+def test_augmented_evaluation_on_the_device_fast_path_equals_the_session_path():
+    """run.sh evaluates with --augment --aug_rate 0.5 (np_augmenters.py:135-160 through metaseg.py:258-302): the host
+    draws the augmentations with the reference's call order on both RNG streams, every augmented copy becomes a row of
+    the task's example pool, and the task still runs as one CUDA graph.  Same IoUs and same RNG consumption as the
+    Session path; with more tasks than slots the chunked staging is exercised too."""
+    from mliis_b200 import np_augmenters
     from mliis_b200.reptile import Gecko
     from mliis_b200.session import Session
     m = _model()
     sess = Session(m)
     _warm(sess, m, 2)
-    g = Gecko(sess, transductive=True, augment=True, aug_rate=0.5)
-    assert g.augmenter is not None and not g.fast_path
-    random.seed(0)
-    np.random.seed(0)
-    mean_iou, iou_map = g.evaluate(_tasks(2, 600), m.input_ph, m.label_ph, m.minimize_op, m.predictions,
-                                   num_classes=1, num_shots=5, inner_batch_size=4, inner_iters=2, replacement=False,
-                                   eval_all_tasks=True, test_shots=5, is_training_ph=m.is_training_ph, lr_ph=m.lr_ph,
-                                   lr=1e-3)
-    assert len(iou_map) == 2 and 0.0 <= mean_iou <= 1.0
+    order = list(np_augmenters.cur_aug_funcs)
+    before = m.engine().states[0].clone()
+    out = []
+    for fast in (True, False):
+        np_augmenters.cur_aug_funcs[:] = order      # the reference shuffles this module-level list in place
+        g = Gecko(sess, transductive=True, augment=True, aug_rate=0.5, fast_path=fast)
+        assert g.augmenter is not None and g.fast_path == fast
+        random.seed(0)
+        np.random.seed(0)
+        mean_iou, iou_map = g.evaluate(_tasks(5, 600), m.input_ph, m.label_ph, m.minimize_op, m.predictions,
+                                       num_classes=1, num_shots=5, inner_batch_size=4, inner_iters=3, replacement=False,
+                                       eval_all_tasks=True, test_shots=5, is_training_ph=m.is_training_ph,
+                                       lr_ph=m.lr_ph, lr=1e-3)
+        out.append((mean_iou, iou_map, random.random(), float(np.random.rand())))
+        assert torch.equal(before, m.engine().states[0])
+    (mf, mapf, rf, nf), (ms, maps, rs, ns) = out
+    assert rf == rs and nf == ns
+    assert list(mapf.keys()) == list(maps.keys()) and len(mapf) == 5
+    for k in mapf:
+        assert abs(mapf[k] - maps[k]) < 1e-12, (k, mapf[k], maps[k])
+    assert abs(mf - ms) < 1e-12 and 0.0 <= mf <= 1.0
 
 
 def test_tfrecord_tasks_equal_synthetic_tasks_on_the_device_fast_path(tmp_path):

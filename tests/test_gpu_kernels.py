@@ -218,3 +218,31 @@ def test_rsd_conv2_folded_forward(H, Cin, Cp, B):
     torch.cuda.synchronize()
     for s in range(n):
         assert rel_err(ar.t("y", s).view(B, H, H, Cout), refs[s]) < 1e-4, s
+
+
+@pytest.mark.parametrize("HW,Cin,Cout,B", [(56 * 56, 144, 24, 2), (14 * 14, 672, 112, 3), (49, 96, 16, 4)])
+def test_project_conv_with_fused_prologue(HW, Cin, Cout, B):
+    """mliis_tc_project_conv == (swish(a*x+b) * gate[img]) @ W   (efficientnet_model.py:225-232, :266, :271-273); M tiles
+    that straddle two images (HW = 49) read both gates."""
+    N, lib = _lib()
+    g = torch.Generator().manual_seed(HW + Cin)
+    n = 2
+    ar = Arena(n, dict(x=B * HW * Cin, w=Cin * Cout, wt=2 * Cin * Cout, a=Cin, b=Cin, gate=B * Cin, y=B * HW * Cout))
+    refs = []
+    for s in range(n):
+        x = torch.randn(B, HW, Cin, generator=g, dtype=torch.float64)
+        w = torch.randn(Cin, Cout, generator=g, dtype=torch.float64) * 0.1
+        a = torch.rand(Cin, generator=g, dtype=torch.float64) + 0.5
+        b = torch.randn(Cin, generator=g, dtype=torch.float64) * 0.3
+        gate = torch.rand(B, Cin, generator=g, dtype=torch.float64)
+        refs.append((swish(x * a + b) * gate[:, None, :]) @ w)
+        for name, v in (("x", x), ("w", w), ("a", a), ("b", b), ("gate", gate)):
+            ar.t(name, s).copy_(v.reshape(-1).float())
+    N.check(lib.mliis_kernel_group(n, ar.stride_bytes))
+    N.check(lib.mliis_tc_prep_weights(ar.p("w"), ar.p("wt"), 1, Cin, Cout, 0, N.GEMM_TF32X3, None))
+    N.check(lib.mliis_tc_project_conv(ar.p("x"), ar.p("wt"), ar.p("a"), ar.p("b"), ar.p("gate"), ar.p("y"), B, HW, Cin, Cout,
+                                      N.GEMM_TF32X3, None))
+    N.check(lib.mliis_kernel_group(1, 0))
+    torch.cuda.synchronize()
+    for s in range(n):
+        assert rel_err(ar.t("y", s).view(B, HW, Cout), refs[s]) < 1e-4, s
