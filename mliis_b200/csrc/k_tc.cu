@@ -1097,6 +1097,14 @@ static bool tc_conv3(const float* A, int lda, const float* Wt, const float* bias
   const int box_rows = p.MT * p.BH * p.RW;
   if (box_rows > 256 || p.MT * p.BH > 256) return false;
   p.BN = tc_pick_bn(N);
+  // one N tile too wide for the rings (the dgrad of conv2d_2: N = 224 leaves room for ONE 56 KB weight slot): fall back
+  // to 128-column tiles (grid.y = ceil(N / 128); the TMA unit zero-fills weight rows and clips output columns past N)
+  // instead of giving the layer to the generic one-box-per-tap kernel (113 us there)
+  if (p.split == 3 && p.BN > 128 && p.MT == 2) {
+    const int slot_rows_w = (p.MT - 1) * p.BH * p.RW + 2 * dil + 128;
+    const int a_bytes_w = ((slot_rows_w > box_rows ? slot_rows_w : box_rows) * 128 + 1023) / 1024 * 1024;
+    if ((216 * 1024 - 2 * 2 * a_bytes_w) / (2 * p.BN * 128) < 2) p.BN = 128;
+  }
   // CTA pairs (cta_group::2, M = 256): 3xTF32 only (the kernel these layers are MMA-issue-bound in), even BN halves
   static int pair_on = -1;
   if (pair_on < 0) { const char* e = getenv("MLIIS_TC_PAIR"); pair_on = e ? atoi(e) : 0; }
@@ -1231,9 +1239,12 @@ bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float*
   const int tail_bytes = 8 * (3 * 6 + 2) + 16 + (pa ? 16 * Kp : 0) + 1024;
   // small stages: size the ring so that two CTAs share an SM (their TMA round trips and fixed start-up costs overlap);
   // big stages (BN >= 128 with both planes): one CTA per SM with a deeper ring
+  // Short-K layers (the MBConv pointwise convolutions: KB <= 8 k-blocks) are bound by per-CTA latency, not by the depth
+  // of the ring: two stages and two CTAs per SM beat five stages and one (project 144->24 at 56x56, 6 slots per launch:
+  // 96 us with one resident CTA).  Long-K layers keep the >= 3 stage rule.
   const int budget2 = (227 * 1024) / 2 - tail_bytes;
   int stages = budget2 / stage_bytes;
-  if (stages < 3) stages = (200 * 1024 - tail_bytes) / stage_bytes;
+  if (stages < (KB <= 8 ? 2 : 3)) stages = (200 * 1024 - tail_bytes) / stage_bytes;
   if (stages > 6) stages = 6;
   if (stages > KB) stages = KB;        // small-K problems: less shared memory -> several CTAs per SM
   if (stages < 1) return false;
