@@ -260,7 +260,7 @@ def _time_launch(fn, flush, reps=8, warm=3):
 def time_dominant_kernel(mode, flush):
     """conv2d_2 of decode_skip_connections_1 (efficientlab.py:224): 3x3, 360->112 at 56x56, B=8 - 57 % of the forward
     FLOPs.  Algorithmic work = the reference op: 2*8*56*56*9*360*112 = 18.21 GFLOP.  As built: the 136 image-pooling
-    channels are folded into a per-image, per-border-class bias (pool_bias9 kernel) and the implicit GEMM runs over
+    channels are folded into a per-image, per-border-class bias (pool_taps kernel + the conv's prologue) and the implicit GEMM runs over
     the 224 real channels; both launches are inside the timed region."""
     import torch
     from mliis_b200 import native as N
@@ -588,7 +588,7 @@ def run_b200(args):
     achieved = k_flops / (k_ms * 1e-3) / 1e12
     tpk = tensor_peaks(peaks) if mode != N.GEMM_FP32 else None
     roof = {"bound": "tensor", "kernel": "conv2d_2 3x3 360->112 @56x56 B=8 (implicit GEMM M=25088 N=112 K=3240; as built: "
-                                         "pool_bias9 + tc_conv3_kernel over the 224 real channels, the 136 pooled channels folded)",
+                                         "pool_taps + tc_conv3_kernel over the 224 real channels, the 136 pooled channels folded into border-class biases)",
             "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
             # dram__bytes_read.sum + dram__bytes_write.sum of the launches: profiles/r02*_ncu_*.md
             "traffic": None, "peak_source": "%s bf16 cuBLAS burst (kernel timed alone)" % peak_src,

@@ -198,6 +198,8 @@ struct Run {
     adam_v = mv + p.n_bn_ch;
     powers = adam_v + p.n_theta;
   }
+  // the self-resetting ticket word of the clustered reductions: the last floats of the partials area (slack)
+  unsigned* ticket() const { return reinterpret_cast<unsigned*>(W(p.partials + p.partials_len - 16)); }
   float* bn_a(const BnRef& r) const { return W(p.bn_a + r.off); }
   float* bn_b(const BnRef& r) const { return W(p.bn_b + r.off); }
   float* bn_mean(const BnRef& r) const { return W(p.bn_mean + r.off); }
@@ -205,9 +207,8 @@ struct Run {
 
   // train-mode batch statistics of one BN layer (+ EMA of the moving statistics)
   void bn_train(const BnRef& r, const float* x, int ld, int M, bool pre_swish) const {
-    bn_stats(x, ld, M, r.C, pre_swish, W(p.partials), st);
-    bn_finalize(W(p.partials), rc_num_chunks(M, r.C), r.C, M, T(r.gamma), T(r.beta), mm + r.off, mv + r.off, 1,
-                r.fused, bn_mean(r), bn_rstd(r), bn_a(r), bn_b(r), st);
+    bn_stats_finalize(x, ld, M, r.C, pre_swish, W(p.partials), ticket(), T(r.gamma), T(r.beta), mm + r.off, mv + r.off, 1,
+                      r.fused, bn_mean(r), bn_rstd(r), bn_a(r), bn_b(r), st);
   }
 };
 
@@ -545,7 +546,7 @@ void run_backward(const Run& r, const float* labels, const int32_t* index, float
       BnBwdArgs a{};
       a.x = x; a.ldx = D; a.g = g; a.ldg = ldg; a.dx = dx; a.lddx = D; a.M = M; a.C = D; a.HW = HW;
       a.mean = r.bn_mean(bn); a.rstd = r.bn_rstd(bn); a.a = r.bn_a(bn); a.b = r.bn_b(bn); a.gamma = r.T(bn.gamma);
-      a.partials = r.W(p.partials); a.k = r.W(p.bn_k); a.dgamma = r.G(bn.gamma); a.dbeta = r.G(bn.beta);
+      a.partials = r.W(p.partials); a.k = r.W(p.bn_k); a.ticket = r.ticket(); a.dgamma = r.G(bn.gamma); a.dbeta = r.G(bn.beta);
       bn_bwd(BN_DEC, a, st);
     };
     // out = BN2(swish(c2)) + up
@@ -617,7 +618,7 @@ void run_backward(const Run& r, const float* labels, const int32_t* index, float
       a.mean = r.bn_mean(b.bn2); a.rstd = r.bn_rstd(b.bn2); a.a = r.bn_a(b.bn2); a.b = r.bn_b(b.bn2);
       a.gamma = r.T(b.bn2.gamma);
       a.dcs = b.dc_idx >= 0 ? r.W(p.dcs + (int64_t)b.dc_idx * p.maxB) : nullptr;
-      a.partials = r.W(p.partials); a.k = r.W(p.bn_k); a.dgamma = r.G(b.bn2.gamma); a.dbeta = r.G(b.bn2.beta);
+      a.partials = r.W(p.partials); a.k = r.W(p.bn_k); a.ticket = r.ticket(); a.dgamma = r.G(b.bn2.gamma); a.dbeta = r.G(b.bn2.beta);
       bn_bwd(BN_PLAIN, a, st);
     }
     // project conv: wgrad on swish(BN1(D))*gate (recomputed), dgrad into gD
@@ -635,7 +636,7 @@ void run_backward(const Run& r, const float* labels, const int32_t* index, float
       a.M = Mo; a.C = b.ce; a.HW = HWo;
       a.mean = r.bn_mean(b.bn1); a.rstd = r.bn_rstd(b.bn1); a.a = r.bn_a(b.bn1); a.b = r.bn_b(b.bn1);
       a.gamma = r.T(b.bn1.gamma); a.gate = r.W(b.gate); a.dpool = r.W(b.dpool);
-      a.partials = r.W(p.partials); a.k = r.W(p.bn_k); a.dgamma = r.G(b.bn1.gamma); a.dbeta = r.G(b.bn1.beta);
+      a.partials = r.W(p.partials); a.k = r.W(p.bn_k); a.ticket = r.ticket(); a.dgamma = r.G(b.bn1.gamma); a.dbeta = r.G(b.bn1.beta);
       bn_bwd(BN_SWISH_SE, a, st);
     }
     // depthwise
@@ -652,7 +653,7 @@ void run_backward(const Run& r, const float* labels, const int32_t* index, float
       a.x = dw_in; a.ldx = b.ce; a.g = r.W(p.gE); a.ldg = b.ce; a.dx = r.W(p.gE); a.lddx = b.ce;
       a.M = Mi; a.C = b.ce; a.HW = HWi;
       a.mean = r.bn_mean(bnin); a.rstd = r.bn_rstd(bnin); a.a = dw_a; a.b = dw_b; a.gamma = r.T(bnin.gamma);
-      a.partials = r.W(p.partials); a.k = r.W(p.bn_k); a.dgamma = r.G(bnin.gamma); a.dbeta = r.G(bnin.beta);
+      a.partials = r.W(p.partials); a.k = r.W(p.bn_k); a.ticket = r.ticket(); a.dgamma = r.G(bnin.gamma); a.dbeta = r.G(bnin.beta);
       bn_bwd(BN_SWISH, a, st);
     }
     if (b.expand) {
@@ -826,6 +827,10 @@ int mliis_slot_bind(mliis_ctx* ctx, int32_t slot, float* dev_state, void* dev_wo
   ctx->slots[slot] = Slot();
   ctx->slots[slot].state = dev_state;
   ctx->slots[slot].ws = (float*)dev_workspace;
+  if (ctx->device >= 0) {      // the ticket words of the clustered reductions start at zero (they reset themselves afterwards)
+    const Plan& p = ctx->plan;
+    cudaMemset((float*)dev_workspace + p.partials + p.partials_len - 16, 0, 16 * sizeof(float));
+  }
   return MLIIS_OK;
 }
 
@@ -1418,6 +1423,20 @@ int mliis_dwconv_bwd(const float* x, const float* bn_a, const float* bn_b, const
   return check_cuda("dwconv_bwd");
 }
 
+// The clustered reductions elect their finalizing CTA with a ticket word that must start at zero and resets itself.  The
+// engine keeps it in the workspace (zeroed at mliis_slot_bind); a per-kernel entry point takes it from the caller's scratch
+// and clears it the first time it sees that scratch pointer (every slot copy of the current kernel group).
+static unsigned* entry_ticket(float* where, cudaStream_t st) {
+  static thread_local const void* cleared = nullptr;
+  static thread_local int cleared_nz = 0;
+  if (cleared != where || cleared_nz != MLIIS_NZ) {
+    for (int z = 0; z < MLIIS_NZ; ++z) cudaMemsetAsync(where + (size_t)z * MLIIS_ZS, 0, 16 * sizeof(float), st);
+    cleared = where;
+    cleared_nz = MLIIS_NZ;
+  }
+  return reinterpret_cast<unsigned*>(where);
+}
+
 // train-mode BN forward bookkeeping of one layer: batch statistics of x [M,C] -> stats = [mean | rstd | a | b] (4*C),
 // EMA of the moving statistics (utils.py:111-134).  The normalise + swish itself is fused into the consumers.
 int mliis_bn_stats_fwd(const float* x, const float* gamma, const float* beta, float* moving_mean, float* moving_var,
@@ -1427,9 +1446,9 @@ int mliis_bn_stats_fwd(const float* x, const float* gamma, const float* beta, fl
   if (C % 4 || C > 1024 || M < 2) return fail(MLIIS_ERR_ARG, "C must be a multiple of 4 and <= 1024");
   if (!x || !gamma || !beta || !moving_mean || !moving_var || !stats || !scratch) return fail(MLIIS_ERR_ARG, "null argument");
   KERNEL_GROUP();
-  bn_stats(x, C, M, C, false, scratch, (cudaStream_t)stream);
-  bn_finalize(scratch, rc_num_chunks(M, C), C, M, gamma, beta, moving_mean, moving_var, 1, fused, stats, stats + C,
-              stats + 2 * C, stats + 3 * C, (cudaStream_t)stream);
+  unsigned* ticket = entry_ticket(scratch + (size_t)rc_num_chunks(M, C) * 2 * C + 2 * C, (cudaStream_t)stream);
+  bn_stats_finalize(x, C, M, C, false, scratch, ticket, gamma, beta, moving_mean, moving_var, 1, fused, stats, stats + C,
+                    stats + 2 * C, stats + 3 * C, (cudaStream_t)stream);
   return check_cuda("bn_stats_fwd");
 }
 
@@ -1445,6 +1464,7 @@ int mliis_bn_swish_bwd(const float* x, const float* g, float* dx, const float* s
   a.x = x; a.ldx = C; a.g = g; a.ldg = C; a.dx = dx; a.lddx = C; a.M = M; a.C = C; a.HW = M;
   a.mean = stats; a.rstd = stats + C; a.a = stats + 2 * C; a.b = stats + 3 * C; a.gamma = gamma;
   a.partials = scratch; a.k = scratch + (size_t)rc_num_chunks(M, C) * 2 * C; a.dgamma = dgamma; a.dbeta = dbeta;
+  a.ticket = entry_ticket(a.k + 2 * C, (cudaStream_t)stream);
   bn_bwd(BN_SWISH, a, (cudaStream_t)stream);
   return check_cuda("bn_swish_bwd");
 }

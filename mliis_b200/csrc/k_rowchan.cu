@@ -10,10 +10,18 @@
 //
 // Reference semantics: models/efficientnet/utils.py:87-134 (non-fused BN), efficientnet_model.py:238-290
 // (SE, block tail), models/efficientlab.py:185-197 (decoder conv->swish->BN, pooled features).
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
+namespace cg = cooperative_groups;
+
 namespace mliis {
+
+constexpr int kRcCluster = 8;     // CTAs per cluster in the whole-tensor reductions (portable maximum)
 
 static inline int rc_R(int C) {
   int c4 = C / 4;
@@ -60,14 +68,134 @@ __device__ __forceinline__ void block_reduce1(float4& s0, float4* sm) {
     for (int j = 1; j < R; ++j) s0 = s0 + sm[j * C4 + cq];
 }
 
+// Whole-tensor reduction of two per-channel sums WITHOUT a second launch (round 2 experiment, opt-in: see bn_clustered();
+// the separate finalize kernels are 9-13 us of pure latency each, ~80 per step).  The row chunks are launched as clusters of 8 CTAs:
+//   1. every CTA leaves its (s0, s1) float4 per channel quad in its own shared memory; cluster barrier;
+//   2. rank 0 adds the eight partials through distributed shared memory (rank order, double) and writes ONE partial row
+//      per cluster to global memory; cluster barrier (the peers' shared memory may go away now);
+//   3. rank 0 takes a ticket; the CTA that draws the last one sums the n_clusters rows - thread (cq, ty) takes rows
+//      ty, ty + R, ... with four rows in flight, the R lanes are combined in ty order through shared memory, in double.
+// Fixed orders everywhere: deterministic.  The ticket resets itself for the next launch on the stream.
+// Returns true in the finalizing CTA; there the threads with threadIdx.y == 0 hold the totals of their quad in t0 / t1.
+// `sm` must hold blockDim.x * blockDim.y * 64 bytes.
+__device__ __forceinline__ bool cluster_total2(float4 s0, float4 s1, float4* sm, float* __restrict__ partials, int C,
+                                               unsigned* ticket, double (&t0)[4], double (&t1)[4]) {
+  __shared__ int s_last;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C4 = blockDim.x, R = blockDim.y, cq = threadIdx.x, ty = threadIdx.y;
+  const unsigned rank = cluster.block_rank();
+  const int cluster_id = blockIdx.x / kRcCluster, n_clusters = gridDim.x / kRcCluster;
+  __syncthreads();                                    // block_reduce2 has finished reading sm
+  if (ty == 0) { sm[cq] = s0; sm[C4 + cq] = s1; }
+  cluster.sync();
+  if (rank == 0 && ty == 0) {
+    double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < kRcCluster; ++r) {
+      const float4* remote = cluster.map_shared_rank(sm, r);
+      const float4 u = remote[cq], v = remote[C4 + cq];
+      a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w;
+      b[0] += v.x; b[1] += v.y; b[2] += v.z; b[3] += v.w;
+    }
+    st4(partials + ((size_t)cluster_id * 2 + 0) * C + cq * 4, f4((float)a[0], (float)a[1], (float)a[2], (float)a[3]));
+    st4(partials + ((size_t)cluster_id * 2 + 1) * C + cq * 4, f4((float)b[0], (float)b[1], (float)b[2], (float)b[3]));
+  }
+  cluster.sync();
+  if (rank != 0) return false;
+  __threadfence();                                    // this CTA's partial row is visible device-wide before the ticket
+  __syncthreads();
+  if (cq == 0 && ty == 0) {
+    const unsigned t = atomicAdd(ticket, 1u);
+    s_last = (t == (unsigned)n_clusters - 1u);
+    if (s_last) atomicExch(ticket, 0u);
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+  for (int g = ty; g < n_clusters; g += 4 * R) {      // four rows (8 float4) in flight per thread; +0.0 tails are exact
+    float4 u[4], v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int gi = g + k * R;
+      u[k] = gi < n_clusters ? __ldcg(reinterpret_cast<const float4*>(partials + ((size_t)gi * 2 + 0) * C + cq * 4)) : f4s(0.f);
+      v[k] = gi < n_clusters ? __ldcg(reinterpret_cast<const float4*>(partials + ((size_t)gi * 2 + 1) * C + cq * 4)) : f4s(0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      a[0] += u[k].x; a[1] += u[k].y; a[2] += u[k].z; a[3] += u[k].w;
+      b[0] += v[k].x; b[1] += v[k].y; b[2] += v[k].z; b[3] += v[k].w;
+    }
+  }
+  double* sd = reinterpret_cast<double*>(sm);
+  double* mine = sd + ((size_t)ty * C4 + cq) * 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { mine[i] = a[i]; mine[4 + i] = b[i]; }
+  __syncthreads();
+  if (ty != 0) return true;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { t0[i] = a[i]; t1[i] = b[i]; }
+  for (int j = 1; j < R; ++j) {
+    const double* o = sd + ((size_t)j * C4 + cq) * 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { t0[i] += o[i]; t1[i] += o[4 + i]; }
+  }
+  return true;
+}
+
+// launch helper: grid.x = row chunks rounded up to whole clusters (the padding CTAs see no rows and add zeros)
+template <typename Kern, typename... Args>
+static void launch_clustered(Kern kern, int G, int nz, dim3 blk, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((G + kRcCluster - 1) / kRcCluster * kRcCluster), 1, (unsigned)nz);
+  cfg.blockDim = blk;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kRcCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 // ------------------------------------------------------------------------------------------------
 // BN statistics
 // ------------------------------------------------------------------------------------------------
-template <bool PRE_SWISH>
+struct BnFin {      // what the finalizing CTA needs (all per-slot pointers)
+  const float* gamma; const float* beta; float* mm; float* mv;
+  float* mean_o; float* rstd_o; float* a_o; float* b_o;
+  int M, ema, bessel;
+};
+// one channel of bn_finalize (double statistics, float outputs, EMA of the moving statistics)
+__device__ __forceinline__ void bn_finalize_channel(const BnFin& f, int c, double s, double ss) {
+  const double mean = s / f.M;
+  double var = ss / f.M - mean * mean;   // biased (tf.nn.moments)
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)kBnEps));
+  const float a = f.gamma[c] * rstd;
+  f.mean_o[c] = (float)mean;
+  f.rstd_o[c] = rstd;
+  f.a_o[c] = a;
+  f.b_o[c] = f.beta[c] - (float)mean * a;
+  if (f.ema) {
+    // moving -= (moving - batch) * (1 - momentum)   [TF-ext assign_moving_average, no zero-debias]
+    const float bv = (float)(f.bessel ? var * ((double)f.M / (double)(f.M - 1)) : var);
+    const float m0 = f.mm[c], v0 = f.mv[c];
+    f.mm[c] = m0 - (m0 - (float)mean) * (1.f - kBnMomentum);
+    f.mv[c] = v0 - (v0 - bv) * (1.f - kBnMomentum);
+  }
+}
+
+template <bool PRE_SWISH, bool CL>
 __global__ void bn_stats_kernel(const float* __restrict__ x, int ld, int M, int C, int rows_per_chunk,
-                                float* __restrict__ partials, long long zs) {
+                                float* __restrict__ partials, unsigned* ticket, BnFin fin, long long zs) {
   extern __shared__ float4 sm[];
-  { const size_t zo = (size_t)blockIdx.z * zs; x += zo; partials += zo; }
+  {
+    const size_t zo = (size_t)blockIdx.z * zs;
+    x += zo; partials += zo; ticket += zo;
+    fin.gamma += zo; fin.beta += zo; fin.mm += zo; fin.mv += zo; fin.mean_o += zo; fin.rstd_o += zo; fin.a_o += zo; fin.b_o += zo;
+  }
   const int cq = threadIdx.x;
   const int r0 = blockIdx.x * rows_per_chunk;
   const int r1 = min(M, r0 + rows_per_chunk);
@@ -90,21 +218,18 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int ld, int M, int 
     }
   }
   block_reduce2(s, ss, sm);
-  if (threadIdx.y == 0) {
-    st4(partials + ((size_t)blockIdx.x * 2 + 0) * C + cq * 4, s);
-    st4(partials + ((size_t)blockIdx.x * 2 + 1) * C + cq * 4, ss);
+  if (!CL) {      // MLIIS_BN_CLUSTER=0: one partial row per CTA, finalized by a second launch (round-1 structure)
+    if (threadIdx.y == 0) {
+      st4(partials + ((size_t)blockIdx.x * 2 + 0) * C + cq * 4, s);
+      st4(partials + ((size_t)blockIdx.x * 2 + 1) * C + cq * 4, ss);
+    }
+    return;
   }
-}
-
-void bn_stats(const float* x, int ld, int M, int C, bool pre_swish, float* partials, cudaStream_t s) {
-  int G = rc_num_chunks(M, C);
-  int rpc = cdiv(M, G);
-  dim3 blk = rc_block(C);
-  size_t smem = 2 * blk.x * blk.y * sizeof(float4);
-  if (pre_swish)
-    MLIIS_COUNT(), bn_stats_kernel<true><<<dim3(G, 1, MLIIS_NZ), blk, smem, s>>>(x, ld, M, C, rpc, partials, MLIIS_ZS);
-  else
-    MLIIS_COUNT(), bn_stats_kernel<false><<<dim3(G, 1, MLIIS_NZ), blk, smem, s>>>(x, ld, M, C, rpc, partials, MLIIS_ZS);
+  double t0[4], t1[4];
+  if (cluster_total2(s, ss, sm, partials, C, ticket, t0, t1) && threadIdx.y == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bn_finalize_channel(fin, cq * 4 + i, t0[i], t1[i]);
+  }
 }
 
 // blockDim = (32 channels, 16 partial lanes): each thread sums every 16th partial in double, then the 16
@@ -148,10 +273,40 @@ __global__ void __launch_bounds__(512) bn_finalize_kernel(const float* __restric
   }
 }
 
-void bn_finalize(const float* partials, int G, int C, int M, const float* gamma, const float* beta, float* mm,
-                 float* mv, int ema, int bessel, float* mean, float* rstd, float* a, float* b, cudaStream_t s) {
-  MLIIS_COUNT(), bn_finalize_kernel<<<dim3(cdiv(C, 32), 1, MLIIS_NZ), dim3(32, 16), 0, s>>>(partials, G, C, M, gamma, beta, mm, mv,
-                                                                                            ema, bessel, mean, rstd, a, b, MLIIS_ZS);
+
+// MEASURED (round 2, B200): the single-launch clustered reduction is SLOWER than reduce + finalize as two launches - whole
+// job 105.4 vs 110.4 tasks/s, bn_stats + finalize at 14x14x672 30.2 vs 23.4 us - although it saves 390 launches per task
+// (2502 -> 2112): the 8-CTA clusters constrain scheduling next to the other slots' kernels, three cluster barriers sit
+// in every CTA's path and the finalize runs on one CTA while its grid drains.  It stays available (MLIIS_BN_CLUSTER=1) as
+// a measured negative result; the default is the two-launch structure.
+static bool bn_clustered() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("MLIIS_BN_CLUSTER"); on = e ? atoi(e) : 0; }
+  return on != 0;
+}
+
+// train-mode batch statistics + finalize (mean, rstd, the affine coefficients a/b, EMA of the moving statistics) in ONE
+// launch.  partials: rc_num_chunks(M, C) / 8 rows of [2][C]; ticket: one zero-initialised word per slot (self-resetting).
+void bn_stats_finalize(const float* x, int ld, int M, int C, bool pre_swish, float* partials, unsigned* ticket,
+                       const float* gamma, const float* beta, float* mm, float* mv, int ema, int bessel, float* mean,
+                       float* rstd, float* a, float* b, cudaStream_t s) {
+  const int G = rc_num_chunks(M, C);
+  const int rpc = cdiv(M, G);
+  const dim3 blk = rc_block(C);
+  const size_t smem = (size_t)blk.x * blk.y * 64;
+  BnFin fin{gamma, beta, mm, mv, mean, rstd, a, b, M, ema, bessel};
+  const long long zs = MLIIS_ZS;
+  if (!bn_clustered()) {
+    if (pre_swish) MLIIS_COUNT(), bn_stats_kernel<true, false><<<dim3(G, 1, MLIIS_NZ), blk, smem, s>>>(x, ld, M, C, rpc, partials, ticket, fin, zs);
+    else MLIIS_COUNT(), bn_stats_kernel<false, false><<<dim3(G, 1, MLIIS_NZ), blk, smem, s>>>(x, ld, M, C, rpc, partials, ticket, fin, zs);
+    MLIIS_COUNT(), bn_finalize_kernel<<<dim3(cdiv(C, 32), 1, MLIIS_NZ), dim3(32, 16), 0, s>>>(partials, G, C, M, gamma, beta, mm, mv,
+                                                                                            ema, bessel, mean, rstd, a, b, zs);
+    return;
+  }
+  if (pre_swish)
+    MLIIS_COUNT(), launch_clustered(bn_stats_kernel<true, true>, G, MLIIS_NZ, blk, smem, s, x, ld, M, C, rpc, partials, ticket, fin, zs);
+  else
+    MLIIS_COUNT(), launch_clustered(bn_stats_kernel<false, true>, G, MLIIS_NZ, blk, smem, s, x, ld, M, C, rpc, partials, ticket, fin, zs);
 }
 
 __global__ void bn_eval_coeffs_kernel(const float* __restrict__ theta, const int32_t* __restrict__ gi,
@@ -455,10 +610,10 @@ __device__ __forceinline__ void bn_bwd_shift(BnBwdArgs& p, long long zs) {
   const size_t zo = (size_t)blockIdx.z * zs;
   p.x += zo; p.g += zo; p.dx += zo; p.mean += zo; p.rstd += zo; p.a += zo; p.b += zo; p.gamma += zo;
   p.dcs = zp(p.dcs, zo); p.gate = zp(p.gate, zo); p.dpool = zp(p.dpool, zo);
-  p.partials += zo; p.k += zo; p.dgamma += zo; p.dbeta += zo;
+  p.partials += zo; p.k += zo; p.dgamma += zo; p.dbeta += zo; p.ticket += zo;
 }
 
-template <int VAR>
+template <int VAR, bool CL>
 __global__ void bn_bwd_reduce_kernel(BnBwdArgs p, int rows_per_chunk, long long zs) {
   extern __shared__ float4 sm[];
   bn_bwd_shift(p, zs);
@@ -487,9 +642,23 @@ __global__ void bn_bwd_reduce_kernel(BnBwdArgs p, int rows_per_chunk, long long 
     }
   }
   block_reduce2(s0, s1, sm);
-  if (threadIdx.y == 0) {
-    st4(p.partials + ((size_t)blockIdx.x * 2 + 0) * p.C + cq * 4, s0);
-    st4(p.partials + ((size_t)blockIdx.x * 2 + 1) * p.C + cq * 4, s1);
+  if (!CL) {
+    if (threadIdx.y == 0) {
+      st4(p.partials + ((size_t)blockIdx.x * 2 + 0) * p.C + cq * 4, s0);
+      st4(p.partials + ((size_t)blockIdx.x * 2 + 1) * p.C + cq * 4, s1);
+    }
+    return;
+  }
+  double t0[4], t1[4];
+  if (cluster_total2(s0, s1, sm, p.partials, p.C, p.ticket, t0, t1) && threadIdx.y == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {       // dbeta = sum g, dgamma = sum g*xhat, and their means for the apply pass
+      const int c = cq * 4 + i;
+      p.dbeta[c] = (float)t0[i];
+      p.dgamma[c] = (float)t1[i];
+      p.k[c] = (float)(t0[i] / p.M);
+      p.k[p.C + c] = (float)(t1[i] / p.M);
+    }
   }
 }
 
@@ -552,9 +721,13 @@ static void bn_bwd_t(const BnBwdArgs& p, cudaStream_t s) {
   dim3 blk = rc_block(p.C);
   const int nz = MLIIS_NZ;
   const long long zs = MLIIS_ZS;
-  MLIIS_COUNT(), bn_bwd_reduce_kernel<VAR><<<dim3(G, 1, nz), blk, 2 * blk.x * blk.y * sizeof(float4), s>>>(p, cdiv(p.M, G), zs);
-  MLIIS_COUNT(), bn_bwd_finalize_kernel<<<dim3(cdiv(p.C, 32), 1, nz), dim3(32, 16), 0, s>>>(p.partials, G, p.C, p.M, p.k, p.dgamma,
-                                                                                           p.dbeta, zs);
+  if (bn_clustered()) {
+    MLIIS_COUNT(), launch_clustered(bn_bwd_reduce_kernel<VAR, true>, G, nz, blk, (size_t)blk.x * blk.y * 64, s, p, cdiv(p.M, G), zs);
+  } else {
+    MLIIS_COUNT(), bn_bwd_reduce_kernel<VAR, false><<<dim3(G, 1, nz), blk, (size_t)blk.x * blk.y * 64, s>>>(p, cdiv(p.M, G), zs);
+    MLIIS_COUNT(), bn_bwd_finalize_kernel<<<dim3(cdiv(p.C, 32), 1, nz), dim3(32, 16), 0, s>>>(p.partials, G, p.C, p.M, p.k, p.dgamma,
+                                                                                             p.dbeta, zs);
+  }
   int rpb = blk.y * 4;
   MLIIS_COUNT(), bn_bwd_apply_kernel<VAR><<<dim3(cdiv(p.M, rpb), 1, nz), blk, 0, s>>>(p, rpb, zs);
 }

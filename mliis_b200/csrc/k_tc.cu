@@ -147,7 +147,7 @@ struct TcParams {
   int taps, dil;
   int N, BN, accumulate;
   int stages;
-  int region_bytes;  // shared memory of the stage ring (>= 32 KB: the epilogue reuses it as two 16 KB staging tiles)
+  int region_bytes;  // shared memory of the stage ring (>= 64 KB: the epilogue reuses it as four 16 KB staging tiles)
   int a_box_bytes;   // bytes one A box delivers
   int split;         // 1: TF32 (operands rounded to nearest)  3: 3xTF32 (hi/lo split, fp32-class accuracy)
   // A-operand prologue applied by the transform warps (plain mode): a <- swish(pa[k]*a + pb[k]) * gate[img][k]
@@ -241,6 +241,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* s_g1 = coef + 3 * Kp;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // MLIIS_TC_DEBUG bit 32: phase timestamps (SM clocks since kernel entry) of one CTA, printed by transform thread 0
+  const bool prof = (p.debug & 32) && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0;
+  const long long t_entry = prof ? clock64() : 0;
   // wide: hi and lo weight planes are adjacent in the stage, so one N = 2*BN MMA forms a_hi*b_hi | a_hi*b_lo in two
   // accumulator column ranges that the epilogue adds (A is fetched from shared memory twice per k-step, not three times)
   // (short-K layers are latency-bound, not MMA-bound: they keep the narrow accumulator so that more CTAs fit the
@@ -362,6 +365,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ---------------- operand transform (during the main loop), then epilogue ----------------
     const int t = threadIdx.x - 64;   // 0..255
+    const long long t_sync = prof ? clock64() - t_entry : 0;
+    long long t_first = 0, t_xf = 0;
     // float4 i = t + 256*j of the 16 KB A tile: row = i/8 = (t>>3) + 32*j, physical 16-byte chunk = t&7.
     // SWIZZLE_128B: logical chunk = physical chunk XOR (row & 7); 32*j does not touch the low 3 row bits, so a
     // thread owns ONE channel group for the whole kernel and the same four rows in every stage.
@@ -392,6 +397,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       mbar_wait(full_bar(s), (kb / p.stages) & 1);
+      if (prof && kb == 0) t_first = clock64() - t_entry;
       float4* a_hi = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
       float4* a_lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + a_off_lo);
       if (!(p.debug & 1)) {
@@ -419,16 +425,20 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quarter = warp & 3, half = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;          // accumulator row == TMEM lane == row of the staging tile
     const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
+    if (prof) t_xf = clock64() - t_entry;
     mbar_wait(tmem_full_bar, 0);                // every MMA has completed: the stage ring is free
     tc_fence_after();
-    uint8_t* stg = smem + half * 16384;
-    const uint32_t stg_addr = base + (uint32_t)half * 16384u;
+    const long long t_acc = prof ? clock64() - t_entry : 0;
     const uint32_t tbase = tmem_acc + ((uint32_t)(quarter * 32) << 16);
     const int nchunks = (p.BN + 31) / 32;
-    for (int ch = half; ch < nchunks; ch += 2) {
+    int nst = 0;                                // stores issued by this half: two staging tiles alternate
+    for (int ch = half; ch < nchunks; ch += 2, ++nst) {
       const int c = ch * 32, n = n0 + c;
       if (n >= p.N) break;                      // uniform over the half: whole chunk outside the tensor
-      if (leader) tma_store_wait_read();        // the previous store of this half has finished reading the tile
+      uint8_t* stg = smem + (half * 2 + (nst & 1)) * 16384;
+      const uint32_t stg_addr = base + (uint32_t)(half * 2 + (nst & 1)) * 16384u;
+      // the store that last read THIS tile (two stores ago) is done; the previous one may still be in flight
+      if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
       named_bar_sync_half(half);
       // two 16-column halves: per half the accumulator (and, for 3xTF32 "wide", its a_hi*b_lo partner range) leaves
       // TMEM with ONE wait; the bias loads are issued first.  Register budget: the kernel must keep 2 CTAs per SM.
@@ -466,6 +476,272 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else tma_store_3d(&tmC, stg_addr, n, m0, slot, p.accumulate != 0);
         tma_store_commit();
       }
+    }
+    if (leader) tma_store_wait_read();          // shared memory must stay valid until the TMA unit has read it
+    if (prof && t == 0)
+      printf("[tc_conv] grid %d x %d  KB %d stages %d BN %d wide %d | after sync %lld | first stage landed %lld | transforms "
+             "done %lld | accumulator complete %lld | epilogue done %lld\n", gridDim.x, gridDim.y, KB, p.stages, p.BN,
+             (int)wide, t_sync, t_first, t_xf, t_acc, clock64() - t_entry);
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(ncols) : "memory");
+  }
+}
+
+// =================================================================================================
+// PERSISTENT pointwise convolution (round 2; VERDICT r1 "kernel furthest below its roofline").  The MBConv 1x1 layers at
+// 112x112 / 56x56 have 196-784 row tiles of 128 pixels and K <= 160: in tc_conv_kernel every tile is its own CTA and
+// pays 5-7 us of SERIAL fixed work (barrier init, TMEM allocation, first TMA round trip, transform, MMA, TMEM -> smem ->
+// TMA-store epilogue) for < 1 us of streaming.  Here one CTA per SM walks the tiles:
+//   * the weight operand (all K, hi and lo planes) is loaded ONCE and stays resident in shared memory;
+//   * the ring holds A stages only; the producer runs ahead across tile boundaries;
+//   * TWO TMEM accumulators: the epilogue warps drain tile i while the transform warps and the MMA work on tile i+1;
+//   * roles: warp 0 TMA producer, warp 1 MMA issuer, 8 transform warps, 8 epilogue warps (own staging tiles, outside
+//     the ring).  Barriers: b_full | a_full / a_ready / a_empty per stage | acc_full / acc_empty per accumulator.
+// Same arithmetic, same order of accumulation per output as tc_conv_kernel (bit-identical results).
+// =================================================================================================
+struct TcPwParams {
+  int M, C, N, BN, n_tiles, KB, SA, split, wide, ncol_acc, ncols_alloc, accumulate;
+  int b_res_bytes;      // resident weight operand: KB x planes x BN x 128
+  const float* pa; const float* pb; const float* gate;
+  int HW;
+  int debug;
+};
+constexpr int kPwXformThreads = 512, kPwEpiThreads = 256;   // 16 transform warps: the fused BN+swish+gate prologue is ALU-bound
+constexpr int kPwNJ = 1024 / kPwXformThreads;                // float4 of a 16 KB A tile per transform thread
+constexpr int kPwThreads = 64 + kPwXformThreads + kPwEpiThreads;
+
+__global__ void __launch_bounds__(kPwThreads, 1)
+tc_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, TcPwParams p, long long zs) {
+  extern __shared__ uint8_t smem_raw[];
+  if (p.debug & 16) return;
+  const int slot = blockIdx.z;
+  { const size_t zo = (size_t)slot * zs; bias = zp(bias, zo); p.pa = zp(p.pa, zo); p.pb = zp(p.pb, zo); p.gate = zp(p.gate, zo); }
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const bool x3 = p.split == 3;
+  const int planes = x3 ? 2 : 1;
+  const int b_bytes = p.BN * 128;
+  const int a_stage = planes * kABytes;
+  // [weights KB x (hi|lo)] [A ring SA x (hi|lo)] [staging 4 x 16 KB] [barriers] [pa | pb]
+  const uint32_t b_base = base, a_base = base + (uint32_t)p.b_res_bytes;
+  const uint32_t stg_base = a_base + (uint32_t)p.SA * a_stage;
+  const uint32_t bar0 = stg_base + 4u * 16384u;
+  uint8_t* bars_ptr = smem + p.b_res_bytes + (size_t)p.SA * a_stage + 4 * 16384;
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_ready = [&](int s) { return bar0 + 8u * (p.SA + s); };
+  auto a_empty = [&](int s) { return bar0 + 8u * (2 * p.SA + s); };
+  const uint32_t b_full = bar0 + 8u * (3 * p.SA);
+  auto acc_full = [&](int b) { return bar0 + 8u * (3 * p.SA + 1 + b); };
+  auto acc_empty = [&](int b) { return bar0 + 8u * (3 * p.SA + 3 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_ptr + 8 * (3 * p.SA + 5));
+  const int Kp = (p.C + 31) & ~31;
+  float* s_pa = reinterpret_cast<float*>(bars_ptr + ((8 * (3 * p.SA + 5) + 4 + 15) & ~15));
+  float* s_pb = s_pa + Kp;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ncols = (uint32_t)p.ncols_alloc;
+  const int KB = p.KB;
+  // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    for (int s = 0; s < p.SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_ready(s), kPwXformThreads); mbar_init(a_empty(s), 1); }
+    mbar_init(b_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), kPwEpiThreads / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // the resident weight operand: every k-block, hi plane then lo plane, back to back
+    mbar_expect_tx(b_full, (uint32_t)p.b_res_bytes);
+    for (int kb = 0; kb < KB; ++kb)
+      for (int pl = 0; pl < planes; ++pl)
+        tma_load_5d(b_base + (uint32_t)((kb * planes + pl) * b_bytes), &tmB, b_full, kb * 32, 0, 0, pl, slot);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (p.pa) {
+    for (int i = threadIdx.x; i < Kp; i += kPwThreads) {
+      const bool in = i < p.C;
+      s_pa[i] = in ? p.pa[i] : 0.f;        // zero beyond C: swish(0*x + 0) = 0 keeps the TMA zero fill
+      s_pb[i] = in ? p.pb[i] : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer: A stages, across tile boundaries ----------------
+      int it = 0;
+      for (int tl = 0; tl < n_my; ++tl) {
+        const int m0 = ((int)blockIdx.x + tl * (int)gridDim.x) * 128;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % p.SA;
+          mbar_wait(a_empty(s), ((it / p.SA) & 1) ^ 1);
+          mbar_expect_tx(a_full(s), (uint32_t)kABytes);
+          tma_load_3d(a_base + (uint32_t)s * a_stage, &tmA, a_full(s), kb * 32, m0, slot);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc_w = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 2) << 17) | ((128u >> 4) << 24);
+      mbar_wait(b_full, 0);
+      int it = 0;
+      for (int tl = 0; tl < n_my; ++tl) {
+        const int buf = tl & 1;
+        mbar_wait(acc_empty(buf), ((tl >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t acc = tmem_acc + (uint32_t)(buf * p.ncol_acc);
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % p.SA;
+          mbar_wait(a_ready(s), (it / p.SA) & 1);
+          tc_fence_after();
+          const int rem = p.C - kb * 32;
+          const int nk = rem >= 32 ? 4 : (rem + 7) / 8;
+          const uint32_t sa = a_base + (uint32_t)s * a_stage, sb = b_base + (uint32_t)(kb * planes * b_bytes);
+          const uint64_t da = make_kmajor_sw128_desc(sa), db = make_kmajor_sw128_desc(sb);
+          const uint64_t dal = make_kmajor_sw128_desc(sa + kABytes), dbl = make_kmajor_sw128_desc(sb + b_bytes);
+          for (int k = 0; k < nk; ++k) {
+            const uint64_t adv = (uint64_t)(2 * k);
+            if (p.wide) {
+              tc_mma_tf32(acc, da + adv, db + adv, idesc_w, (kb | k) ? 1u : 0u);
+              tc_mma_tf32(acc, dal + adv, db + adv, idesc, 1u);
+            } else {
+              tc_mma_tf32(acc, da + adv, db + adv, idesc, (kb | k) ? 1u : 0u);
+              if (x3) {
+                tc_mma_tf32(acc, dal + adv, db + adv, idesc, 1u);
+                tc_mma_tf32(acc, da + adv, dbl + adv, idesc, 1u);
+              }
+            }
+          }
+          tc_commit(a_empty(s));
+        }
+        tc_commit(acc_full(buf));
+      }
+    }
+  } else if (warp < 2 + kPwXformThreads / 32) {
+    // ---------------- operand transform (8 warps): TF32 rounding, hi/lo split, fused BN + swish + gate ----------------
+    const int t = threadIdx.x - 64;   // float4 i = t + kPwXformThreads*j: row (t>>3) + (kPwXformThreads/8)*j, 16-byte chunk t&7
+    const int rl = t >> 3;
+    const int lc4 = (((t & 7) ^ (rl & 7)) << 2);
+    int it = 0;
+    for (int tl = 0; tl < n_my; ++tl) {
+      const int m0 = ((int)blockIdx.x + tl * (int)gridDim.x) * 128;
+      size_t goff[kPwNJ];
+#pragma unroll
+      for (int j = 0; j < kPwNJ; ++j) {
+        const int m = min(m0 + rl + (kPwXformThreads / 8) * j, p.M - 1);
+        goff[j] = p.gate ? (size_t)(m / p.HW) * p.C : 0;
+      }
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const int s = it % p.SA;
+        const int k = kb * 32 + lc4;
+        float4 a4 = f4s(0.f), b4 = f4s(0.f), g4[kPwNJ];
+        if (p.pa) {
+          a4 = ld4(s_pa + k);
+          b4 = ld4(s_pb + k);
+          if (p.gate) {
+#pragma unroll
+            for (int j = 0; j < kPwNJ; ++j) g4[j] = k < p.C ? ld4(p.gate + goff[j] + k) : f4s(0.f);
+          }
+        }
+        mbar_wait(a_full(s), (it / p.SA) & 1);
+        float4* a_hi = reinterpret_cast<float4*>(smem + p.b_res_bytes + (size_t)s * a_stage);
+        float4* a_lo = a_hi + kABytes / 16;
+        float4 v[kPwNJ];
+#pragma unroll
+        for (int j = 0; j < kPwNJ; ++j) v[j] = a_hi[t + kPwXformThreads * j];
+#pragma unroll
+        for (int j = 0; j < kPwNJ; ++j) {
+          float4 x = v[j];
+          if (p.pa) {
+            x = swish_fast4(affine4(x, a4, b4));
+            if (p.gate) x = x * g4[j];
+          }
+          const float4 h = rn_tf32_4(x);
+          a_hi[t + kPwXformThreads * j] = h;
+          if (x3) a_lo[t + kPwXformThreads * j] = rn_tf32_4(x - h);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(a_ready(s));
+      }
+    }
+  } else {
+    // ---------------- epilogue (8 warps): TMEM -> registers (+ bias) -> swizzled smem tile -> TMA store ----------------
+    const int ew = warp - (2 + kPwXformThreads / 32);      // 0..7
+    const int quarter = warp & 3, half = ew >> 2;          // TMEM lane quarter = warp % 4 (hardware rule)
+    const int r = quarter * 32 + lane;
+    const bool leader = (ew & 3) == 0 && lane == 0;
+    const int nchunks = (p.BN + 31) / 32;
+    int nst = 0;                                           // stores issued by this half: staging tile = nst & 1
+    for (int tl = 0; tl < n_my; ++tl) {
+      const int buf = tl & 1;
+      const int m0 = ((int)blockIdx.x + tl * (int)gridDim.x) * 128;
+      mbar_wait(acc_full(buf), (tl >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tbase = tmem_acc + (uint32_t)(buf * p.ncol_acc) + ((uint32_t)(quarter * 32) << 16);
+      for (int ch = half; ch < nchunks; ch += 2) {
+        const int c = ch * 32, n = c;
+        if (n >= p.N) break;                               // uniform over the half
+        const uint32_t stg_off = (uint32_t)((half * 2 + (nst & 1)) * 16384);
+        uint8_t* stg = smem + p.b_res_bytes + (size_t)p.SA * a_stage + stg_off;
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last read this tile
+        named_bar_sync_half(half);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int cc = c + 16 * h2;
+          const bool live = cc < p.BN;                     // uniform
+          float4 add[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) add[q] = (bias && n + 16 * h2 + q * 4 < p.N) ? ld4(bias + n + 16 * h2 + q * 4) : f4s(0.f);
+          uint32_t v0[16], w0[16];
+          __syncwarp();
+          if (live) {
+            tc_ld16_nw(tbase + (uint32_t)cc, v0);
+            if (p.wide) tc_ld16_nw(tbase + (uint32_t)(p.BN + cc), w0);
+            tc_ld_wait();
+          }
+          tc_ld_fence(v0); tc_ld_fence(w0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 o = f4s(0.f);
+            if (live) {
+              o = f4(__uint_as_float(v0[q * 4 + 0]), __uint_as_float(v0[q * 4 + 1]), __uint_as_float(v0[q * 4 + 2]),
+                     __uint_as_float(v0[q * 4 + 3]));
+              if (p.wide) o = o + f4(__uint_as_float(w0[q * 4 + 0]), __uint_as_float(w0[q * 4 + 1]),
+                                     __uint_as_float(w0[q * 4 + 2]), __uint_as_float(w0[q * 4 + 3]));
+            }
+            *reinterpret_cast<float4*>(stg + r * 128 + (((4 * h2 + q) ^ (r & 7)) << 4)) = o + add[q];
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        named_bar_sync_half(half);
+        if (leader) {
+          tma_store_3d(&tmC, stg_base + stg_off, n, m0, slot, p.accumulate != 0);
+          tma_store_commit();
+        }
+        ++nst;
+      }
+      // every tcgen05.ld of this warp on the accumulator has completed (wait::ld above): hand it back to the MMA
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));
     }
     if (leader) tma_store_wait_read();          // shared memory must stay valid until the TMA unit has read it
     tc_fence_before();
@@ -1178,6 +1454,66 @@ static bool tc_conv3(const float* A, int lda, const float* Wt, const float* bias
   return true;
 }
 
+// persistent pointwise path; returns false when the shape does not qualify (caller uses tc_conv_kernel)
+static bool tc_pw(const float* A, int lda, const float* Wt, const float* bias, float* out, int ldc, int M, int C, int N,
+                  int accumulate, int split, cudaStream_t s, const float* pa, const float* pb, const float* gate, int HW) {
+  static int enabled = -1, dbg = -1;
+  if (enabled < 0) { const char* e = getenv("MLIIS_TC_PW"); enabled = e ? atoi(e) : 1; }
+  if (dbg < 0) { const char* e = getenv("MLIIS_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+  if (!enabled || (dbg & 3)) return false;
+  TcPwParams p{};
+  p.debug = dbg;
+  p.M = M; p.C = C; p.N = N; p.accumulate = accumulate; p.split = split == 3 ? 3 : 1;
+  p.pa = pa; p.pb = pb; p.gate = gate; p.HW = HW > 0 ? HW : 1;
+  p.BN = tc_pick_bn(N);
+  if (p.BN < N) return false;                      // one N tile only
+  p.KB = (C + 31) / 32;
+  if (p.KB > 8) return false;
+  p.n_tiles = (M + 127) / 128;
+  int sms = 148;
+  const int per_slot = sms / MLIIS_NZ > 0 ? sms / MLIIS_NZ : 1;
+  if (p.n_tiles < 2 * per_slot) return false;      // fewer than two tiles per CTA: nothing to pipeline
+  const int planes = p.split == 3 ? 2 : 1;
+  p.wide = p.split == 3 && 2 * p.BN <= 256;
+  p.ncol_acc = p.wide ? 2 * p.BN : p.BN;
+  p.ncols_alloc = 32;
+  while (p.ncols_alloc < 2 * p.ncol_acc) p.ncols_alloc <<= 1;
+  if (p.ncols_alloc > 512) return false;
+  p.b_res_bytes = p.KB * planes * p.BN * 128;
+  const int a_stage = planes * kABytes;
+  const int Kp = (C + 31) / 32 * 32;
+  const int tail = 8 * (3 * 6 + 5) + 32 + 8 * Kp + 1024;
+  p.SA = (220 * 1024 - p.b_res_bytes - 4 * 16384 - tail) / a_stage;
+  if (p.SA > 6) p.SA = 6;
+  if (p.SA < 2) return false;
+  CUtensorMap tmA, tmB, tmC;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)M, (cuuint64_t)MLIIS_NZ};
+    cuuint64_t str[2] = {(cuuint64_t)lda * 4, slot_stride_bytes((cuuint64_t)M * lda * 4)};
+    cuuint32_t box[3] = {32, 128, 1};
+    if (!encode(&tmA, A, 3, dims, str, box)) return false;
+    cuuint64_t cd[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)MLIIS_NZ};
+    cuuint64_t cs[2] = {(cuuint64_t)ldc * 4, slot_stride_bytes((cuuint64_t)M * ldc * 4)};
+    if (!encode(&tmC, out, 3, cd, cs, box)) return false;
+  }
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)C, 1, (cuuint64_t)N, (cuuint64_t)planes, (cuuint64_t)MLIIS_NZ};
+    cuuint64_t str[4] = {(cuuint64_t)C * 4, (cuuint64_t)C * 4, (cuuint64_t)N * C * 4,
+                         slot_stride_bytes((cuuint64_t)planes * N * C * 4)};
+    cuuint32_t box[5] = {32, 1, (cuuint32_t)p.BN, 1, 1};
+    if (!encode(&tmB, Wt, 5, dims, str, box)) return false;
+  }
+  const size_t smem = (size_t)p.b_res_bytes + (size_t)p.SA * a_stage + 4 * 16384 + 8 * (3 * p.SA + 5) + 32 + 8 * Kp + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(tc_pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr = true;
+  }
+  const int gx = p.n_tiles < per_slot ? p.n_tiles : per_slot;
+  MLIIS_COUNT(), tc_pw_kernel<<<dim3(gx, 1, MLIIS_NZ), kPwThreads, smem, s>>>(tmA, tmB, tmC, bias, p, MLIIS_ZS);
+  return true;
+}
+
 // Wt layout expected by the kernel: [N][taps][C]  (K-major rows of B)
 bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float* out, int ldc, int conv, int M, int B,
              int H, int W, int C, int taps, int dil, int N, int accumulate, int split, cudaStream_t s,
@@ -1194,6 +1530,7 @@ bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float*
   if (conv && taps == 9 && tc_conv3(A, lda, Wt, bias, out, ldc, B, H, W, C, dil, N, accumulate, p.split, s, bias9))
     return true;
   if (bias9) return false;        // only tc_conv3_kernel adds the border-class bias
+  if (!conv && taps == 1 && tc_pw(A, lda, Wt, bias, out, ldc, M, C, N, accumulate, p.split, s, pa, pb, gate, HW)) return true;
   p.BN = tc_pick_bn(N);
   CUtensorMap tmA, tmB, tmC;
   int grid_x;
@@ -1250,7 +1587,7 @@ bool tc_conv(const float* A, int lda, const float* Wt, const float* bias, float*
   if (stages < 1) return false;
   p.stages = stages;
   p.region_bytes = stages * stage_bytes;
-  if (p.region_bytes < 32768) p.region_bytes = 32768;
+  if (p.region_bytes < 65536) p.region_bytes = 65536;     // the epilogue reuses the ring as four 16 KB staging tiles
   const size_t smem = (size_t)p.region_bytes + ((8 * (3 * stages + 2) + 15) & ~15) + (pa ? 16 * Kp : 0) + 1024;
   static bool attr = false;
   if (!attr) {

@@ -37,11 +37,11 @@ int rc_num_chunks(int M, int C);              // #row chunks used by the whole-t
 int rc_num_img_chunks(int HW, int C);         // #row chunks per image used by the per-image reductions
 
 // batch statistics of x (pre_swish: of swish(x)) -> partials [G][2][C]
-void bn_stats(const float* x, int ld, int M, int C, bool pre_swish, float* partials, cudaStream_t s);
-// partials -> mean,rstd,a,b (+EMA into moving_mean/var when ema != 0; bessel: n/(n-1) corrected variance)
-void bn_finalize(const float* partials, int G, int C, int M, const float* gamma, const float* beta,
-                 float* moving_mean, float* moving_var, int ema, int bessel, float* mean, float* rstd, float* a,
-                 float* b, cudaStream_t s);
+// train-mode batch statistics AND their finalize (mean, rstd, affine coefficients, EMA of the moving statistics) in one
+// launch: clusters of 8 row-chunk CTAs reduce through distributed shared memory, the last cluster leader finalizes
+void bn_stats_finalize(const float* x, int ld, int M, int C, bool pre_swish, float* partials, unsigned* ticket,
+                       const float* gamma, const float* beta, float* mm, float* mv, int ema, int bessel, float* mean,
+                       float* rstd, float* a, float* b, cudaStream_t s);
 // eval mode coefficients for ALL layers at once: a = gamma*rsqrt(mv+eps), b = beta - mm*a
 void bn_eval_coeffs(const float* theta, const int32_t* gamma_idx, const int32_t* beta_idx, const float* moving_mean,
                     const float* moving_var, int n_ch, float* a, float* b, cudaStream_t s);
@@ -75,7 +75,8 @@ struct BnBwdArgs {
   const float* dcs;             // [B] or null (BN_PLAIN)
   const float* gate;            // [B][C] (BN_SWISH_SE)
   const float* dpool;           // [B][C] (BN_SWISH_SE)
-  float* partials;              // [G][2][C]
+  float* partials;              // [G/8][2][C] (one row per cluster of row chunks)
+  unsigned* ticket;             // one zero-initialised word per slot (self-resetting): elects the finalizing CTA
   float* k;                     // [2][C]  mean(g), mean(g*xhat)
   float* dgamma; float* dbeta;  // [C] gradient outputs
 };

@@ -137,7 +137,7 @@ class Gecko:
     def train_step(self, dataset, input_ph, label_ph, minimize_op, num_classes, num_shots, inner_batch_size,
                    inner_iters, replacement, meta_step_size, meta_batch_size, lr_ph=None, lr=None, verbose=False):
         num_classes = 1      # hardcoded binary Gecko (reptile.py:99-100)
-        if self.fast_path and self.augmenter is None:      # augmented meta-TRAINING batches go through the Session path
+        if self.fast_path:
             return self._train_step_device(dataset, num_shots, inner_batch_size, inner_iters, replacement,
                                            meta_step_size, meta_batch_size, lr_ph, lr, fomaml=False)
         old_vars = self._model_state.export_variables()
@@ -166,6 +166,34 @@ class Gecko:
     def _task_batches_for_training(self, rows, inner_batch_size, inner_iters, replacement):
         """Index batches of one meta-training task; overridden by FOMLIS (tail batch)."""
         return list(_mini_batches(rows, inner_batch_size, inner_iters, replacement, augmenter=None))
+
+    def _array_batches_for_training(self, samples, inner_batch_size, inner_iters, replacement):
+        """Array-space twin of `_task_batches_for_training` (reptile.py:108): Gecko passes no aug_rate here, so the
+        Augmenter falls back to its own prob_to_return_original; overridden by FOMLIS (tail batch, aug_rate)."""
+        return _mini_batches(samples, inner_batch_size, inner_iters, replacement, augmenter=self.augmenter)
+
+    def _train_plan(self, task, rows, inner_batch_size, inner_iters, replacement, build: bool = True):
+        """(images, labels, batches) of one meta-training task for the device path; batches are rows of `images`.
+        Without an augmenter the pool is the task's first len(rows) records.  With one (run.sh: --augment) every inner
+        batch holds freshly augmented copies drawn on the host with the reference's RNG order; they become extra rows
+        of the pool (_ExamplePool).  build=False only consumes the RNG streams (tasks owned by another rank)."""
+        if self.augmenter is None:
+            batches = self._task_batches_for_training(rows, inner_batch_size, inner_iters, replacement)
+            if not build:
+                return None, None, batches
+            images, labels = task.arrays()
+            return images[:len(rows)], labels[:len(rows)], batches
+        images, labels = task.arrays()
+        samples = [[images[r], labels[r]] for r in rows]
+        pool = _ExamplePool()
+        for ex in samples:                       # the support examples first: rows 0..n-1 like the plain path
+            pool.row(ex[0], ex[1])
+        batches = [[pool.row(ex[0], ex[1]) for ex in batch]
+                   for batch in self._array_batches_for_training(samples, inner_batch_size, inner_iters, replacement)]
+        if not build:
+            return None, None, batches
+        pi, pl = pool.arrays()
+        return pi, pl, batches
 
     def _train_lrs(self, lr_ph, lr, n_batches) -> List[List[float]]:
         """Per batch, the learning rates of the minimize runs the reference performs (reptile.py:114-121)."""
@@ -206,12 +234,12 @@ class Gecko:
         for t in range(meta_batch_size):
             # every rank draws every task so that the `random` stream stays identical across ranks
             task, rows = _sample_task_indices(dataset, num_shots)
-            batches = self._task_batches_for_training(rows, inner_batch_size, inner_iters, replacement)
-            if t % world != rank:
+            mine = t % world == rank
+            images, labels, batches = self._train_plan(task, rows, inner_batch_size, inner_iters, replacement, build=mine)
+            if not mine:
                 continue
-            images, labels = task.arrays()
-            x = torch.from_numpy(images[:len(rows)]).to(eng.device, non_blocking=True)
-            y = torch.from_numpy(labels[:len(rows)]).to(eng.device, non_blocking=True)
+            x = torch.from_numpy(np.ascontiguousarray(images)).to(eng.device, non_blocking=True)
+            y = torch.from_numpy(np.ascontiguousarray(labels)).to(eng.device, non_blocking=True)
             lrs = self._fomaml_lrs(lr_ph, lr, len(batches)) if fomaml else self._train_lrs(lr_ph, lr, len(batches))
             for j, batch in enumerate(batches):
                 idx = torch.tensor(batch, dtype=torch.int32, device=eng.device)
@@ -239,21 +267,24 @@ class Gecko:
         plans = []
         for t in range(meta_batch_size):
             task, rows = _sample_task_indices(dataset, num_shots)        # every rank draws every task
-            batches = self._task_batches_for_training(rows, inner_batch_size, inner_iters, replacement)
-            if t % world == rank:
-                plans.append((task, rows, batches))
+            mine = t % world == rank
+            images, labels, batches = self._train_plan(task, rows, inner_batch_size, inner_iters, replacement, build=mine)
+            if mine:
+                plans.append((images, labels, batches))
         if plans:
             n_batches = len(plans[0][2])
             lrs = self._fomaml_lrs(lr_ph, lr, n_batches) if fomaml else self._train_lrs(lr_ph, lr, n_batches)
-            shape = (len(plans[0][1]), tuple(len(b) for b in plans[0][2]), tuple(tuple(l) for l in lrs), fomaml,
+            n_rows = len(plans[0][0])
+            if self.augmenter is not None:           # room for one fresh copy per batch element
+                n_rows = num_shots + sum(len(b) for b in plans[0][2])
+            shape = (n_rows, tuple(len(b) for b in plans[0][2]), tuple(tuple(l) for l in lrs), fomaml,
                      self._pre_decay())
             if self._train_slots is None or self._train_slots.shape != shape:
                 self._train_slots = TrainSlots(eng, min(self.meta_task_slots, eng.n_slots), shape)
             ts = self._train_slots
             ts.begin(eng.theta(0))
-            for i, (task, rows, batches) in enumerate(plans):
-                images, labels = task.arrays()
-                ts.submit(i % ts.n, images[:len(rows)], labels[:len(rows)], batches)
+            for i, (images, labels, batches) in enumerate(plans):
+                ts.submit(i % ts.n, images, labels, batches)
             buf = ts.finish()
             n_write = ts.n
         else:
@@ -637,7 +668,7 @@ class FOMLIS(Gecko):
 
     def train_step(self, dataset, input_ph, label_ph, minimize_op, num_classes, num_shots, inner_batch_size,
                    inner_iters, replacement, meta_step_size, meta_batch_size, verbose=False, lr_ph=None, lr=None):
-        if self.fast_path and self.augmenter is None:      # augmented meta-TRAINING batches go through the Session path
+        if self.fast_path:
             return self._train_step_device(dataset, num_shots, inner_batch_size, inner_iters, replacement,
                                            meta_step_size, meta_batch_size, lr_ph, lr, fomaml=True)
         old_vars = self._model_state.export_variables()
@@ -678,3 +709,6 @@ class FOMLIS(Gecko):
 
     def _task_batches_for_training(self, rows, inner_batch_size, inner_iters, replacement):
         return list(self._mini_batches(rows, inner_batch_size, inner_iters, replacement))
+
+    def _array_batches_for_training(self, samples, inner_batch_size, inner_iters, replacement):
+        return self._mini_batches(samples, inner_batch_size, inner_iters, replacement)

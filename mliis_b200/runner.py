@@ -407,16 +407,19 @@ class TrainSlots:
     def submit(self, s: int, images: np.ndarray, labels: np.ndarray, batches) -> None:
         st = self.streams[s]
         st.synchronize()                                   # the slot's pinned staging is free again
-        self.xp[s].copy_(torch.from_numpy(np.ascontiguousarray(images, np.float32)))
-        self.yp[s].copy_(torch.from_numpy(np.ascontiguousarray(labels, np.float32)))
+        n = images.shape[0]                                # <= n_pool (augmented pools vary in size)
+        if n > self.xp[s].shape[0]:
+            raise ValueError("task pool of %d examples exceeds the slot's capacity (%d)" % (n, self.xp[s].shape[0]))
+        self.xp[s][:n].copy_(torch.from_numpy(np.ascontiguousarray(images, np.float32)))
+        self.yp[s][:n].copy_(torch.from_numpy(np.ascontiguousarray(labels, np.float32)))
         for j, b in enumerate(batches):
             self.idxp[s][j].copy_(torch.as_tensor(np.asarray(b, np.int32)))
         self._submitted += 1
         self.seedp[s][0] = 1000003 * self._submitted
         with torch.cuda.stream(st):
             self.seed[s].copy_(self.seedp[s], non_blocking=True)
-            self.x[s].copy_(self.xp[s], non_blocking=True)
-            self.y[s].copy_(self.yp[s], non_blocking=True)
+            self.x[s][:n].copy_(self.xp[s][:n], non_blocking=True)
+            self.y[s][:n].copy_(self.yp[s][:n], non_blocking=True)
             for j in range(len(batches)):
                 self.idx[s][j].copy_(self.idxp[s][j], non_blocking=True)
             self.graphs[s].replay()

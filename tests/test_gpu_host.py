@@ -120,6 +120,37 @@ def test_meta_train_step_fast_equals_session_path(foml):
     assert ((bf - bs).abs().max() / bs.abs().max()).item() < 1e-5
 
 
+@pytest.mark.parametrize("foml,slots", [(False, 1), (True, 1), (True, 3)])
+def test_augmented_meta_train_step_fast_equals_session_path(foml, slots):
+    """run.sh trains with --augment: the device path stages the augmented copies as pool rows (sequential and
+    slot-parallel); same trainables as the Session path under --sgd, same consumption of both RNG streams."""
+    from mliis_b200 import np_augmenters
+    from mliis_b200.reptile import FOMLIS, Gecko
+    from mliis_b200.session import Session
+    order = list(np_augmenters.cur_aug_funcs)
+    results = []
+    for fast in (True, False):
+        np_augmenters.cur_aug_funcs[:] = order
+        m = _model(optimizer="sgd")
+        sess = Session(m)
+        tasks = _tasks(6, 250, n_examples=15)
+        random.seed(3)
+        np.random.seed(3)
+        kw = dict(augment=True, aug_rate=0.5, fast_path=fast, meta_task_slots=slots if fast else 1)
+        learner = FOMLIS(sess, train_shots=10, tail_shots=5, **kw) if foml else Gecko(sess, **kw)
+        for _ in range(2):
+            learner.train_step(tasks, m.input_ph, m.label_ph, m.minimize_op, num_classes=1, num_shots=10 if foml else 5,
+                               inner_batch_size=4, inner_iters=3, replacement=False, meta_step_size=0.5,
+                               meta_batch_size=3, lr_ph=m.lr_ph, lr=None)
+        eng = m.engine()
+        torch.cuda.synchronize()
+        results.append((eng.tf_order_vector(eng.theta(0)).cpu().double(), random.random(), float(np.random.rand())))
+    (tf_, rf, nf), (ts, rs, ns) = results
+    assert rf == rs and nf == ns
+    rel = ((tf_ - ts).norm() / ts.norm()).item()
+    assert rel < 1e-5, rel
+
+
 def test_evaluate_gecko_and_train_gecko_with_checkpoints(tmp_path):
     from mliis_b200.checkpoint import Saver, read_index
     from mliis_b200.eval import evaluate_gecko

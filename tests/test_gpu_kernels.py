@@ -220,10 +220,12 @@ def test_rsd_conv2_folded_forward(H, Cin, Cp, B):
         assert rel_err(ar.t("y", s).view(B, H, H, Cout), refs[s]) < 1e-4, s
 
 
-@pytest.mark.parametrize("HW,Cin,Cout,B", [(56 * 56, 144, 24, 2), (14 * 14, 672, 112, 3), (49, 96, 16, 4)])
+@pytest.mark.parametrize("HW,Cin,Cout,B", [(56 * 56, 144, 24, 2), (14 * 14, 672, 112, 3), (49, 96, 16, 4),
+                                           (112 * 112, 96, 24, 3), (100 * 100 + 3, 40, 136, 4)])
 def test_project_conv_with_fused_prologue(HW, Cin, Cout, B):
     """mliis_tc_project_conv == (swish(a*x+b) * gate[img]) @ W   (efficientnet_model.py:225-232, :266, :271-273); M tiles
-    that straddle two images (HW = 49) read both gates."""
+    that straddle two images (HW = 49) read both gates.  The two large-M cases run on the persistent tile-loop kernel
+    (tc_pw_kernel: >= 2 row tiles per CTA), the last one with a ragged M, a K tail (40 = 32 + 8) and a non-wide N."""
     N, lib = _lib()
     g = torch.Generator().manual_seed(HW + Cin)
     n = 2
@@ -246,3 +248,29 @@ def test_project_conv_with_fused_prologue(HW, Cin, Cout, B):
     torch.cuda.synchronize()
     for s in range(n):
         assert rel_err(ar.t("y", s).view(B, HW, Cout), refs[s]) < 1e-4, s
+
+
+@pytest.mark.parametrize("M,K,N,bias", [(37632, 16, 96, False), (40003, 24, 144, True), (6272, 24, 144, True)])
+def test_pointwise_conv(M, K, N, bias):
+    """mliis_tc_conv with taps = 1 (MBConv expand conv / any plain GEMM) on both pointwise kernels: the persistent tile
+    loop (large M) and one CTA per tile (small M)."""
+    Nn, lib = _lib()
+    g = torch.Generator().manual_seed(M + K)
+    n = 2
+    ar = Arena(n, dict(x=M * K, w=K * N, wt=2 * K * N, b=N, y=M * N))
+    refs = []
+    for s in range(n):
+        x = torch.randn(M, K, generator=g, dtype=torch.float64)
+        w = torch.randn(K, N, generator=g, dtype=torch.float64) * 0.2
+        b = torch.randn(N, generator=g, dtype=torch.float64)
+        refs.append(x @ w + (b if bias else 0.0))
+        for name, v in (("x", x), ("w", w), ("b", b)):
+            ar.t(name, s).copy_(v.reshape(-1).float())
+    Nn.check(lib.mliis_kernel_group(n, ar.stride_bytes))
+    Nn.check(lib.mliis_tc_prep_weights(ar.p("w"), ar.p("wt"), 1, K, N, 0, Nn.GEMM_TF32X3, None))
+    Nn.check(lib.mliis_tc_conv(ar.p("x"), ar.p("wt"), ar.p("b") if bias else None, ar.p("y"), 1, 1, M, K, N, 1, 1,
+                               Nn.GEMM_TF32X3, None))
+    Nn.check(lib.mliis_kernel_group(1, 0))
+    torch.cuda.synchronize()
+    for s in range(n):
+        assert rel_err(ar.t("y", s).view(M, N), refs[s]) < 1e-4, s

@@ -1,17 +1,14 @@
-timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_parity.py -q -x 2>&1 | tail -3
-python bench.py --steps 5 --warmup 3 --skip-cpu-baseline --skip-meta-train > gpurun_out/r02p_bench.json 2> gpurun_out/r02p_bench.err; python - <<'PY'
+timeout 1800 python -m pytest tests -q -m gpu 2>&1 | tail -4
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+python bench.py > gpurun_out/r02v_bench.json 2> gpurun_out/r02v_bench.err; python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/r02p_bench.json').read().strip().splitlines()[-1])
-print('value', d['value'], 'e2e', d['e2e']['value'], 'roofline', d['roofline']['frac'], d['roofline']['kernel_ms'], 'launches', d['gpu_launches'])
+d=json.loads(open('gpurun_out/r02v_bench.json').read().strip().splitlines()[-1])
+print('value', d['value'], 'e2e', d['e2e']['value'], 'roofline', d['roofline']['frac'], d['roofline']['kernel_ms'], 'launches', d['gpu_launches'], 'steps', d['steps'])
+print('meta', {k:(v['meta_steps_per_s'], v['tasks_per_s']) for k,v in d['meta_train'].items()})
+print('miou', d['miou_vs_oracle']['max_abs_diff'], d['miou_vs_oracle']['mean_abs_diff'], 'cpu', d['cpu_baseline']['value'])
 for o in d['roofline_hbm']: print('%-66s %8.1f GB/s  frac %.3f  %.1f us' % (o['kernel'], o['GBps'], o['frac'], o['ms']*1e3))
 PY
-tail -3 gpurun_out/r02p_bench.err
-echo "--- ncu: HBM kernels, 6 slots per launch"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'dw_|bn_|img_reduce|se_fc|loss_|adam_kernel|tc_conv_kernel|reduce_partials' -c 80 -f -o gpurun_out/r02p_hbm python tools/prof_hbm.py > gpurun_out/r02p_hbm.log 2>&1; tail -2 gpurun_out/r02p_hbm.log
-ncu -i gpurun_out/r02p_hbm.ncu-rep --page raw --csv > gpurun_out/r02p_hbm.raw.csv 2>/dev/null; python tools/ncu_summary.py < gpurun_out/r02p_hbm.raw.csv > gpurun_out/r02p_hbm.md; head -60 gpurun_out/r02p_hbm.md
-echo "--- ncu: dominant conv"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'tc_conv3|pool_taps' -c 6 -f -o gpurun_out/r02p_conv3 python tools/prof_dominant.py > gpurun_out/r02p_conv3.log 2>&1; tail -2 gpurun_out/r02p_conv3.log
-ncu -i gpurun_out/r02p_conv3.ncu-rep --page raw --csv > gpurun_out/r02p_conv3.raw.csv 2>/dev/null; python tools/ncu_summary.py < gpurun_out/r02p_conv3.raw.csv
-echo "--- SM time of one step"
-timeout 900 ncu --metrics gpu__time_duration.sum,sm__cycles_active.sum,launch__grid_size --clock-control none --csv --log-file gpurun_out/r02p_smtime.csv python tools/prof_step.py --gemm-mode tf32x3 > gpurun_out/r02p_smtime.log 2>&1; python tools/sm_time.py gpurun_out/r02p_smtime.csv > gpurun_out/r02p_smtime.md; head -30 gpurun_out/r02p_smtime.md
-rm -f gpurun_out/r02p_hbm.ncu-rep
+tail -2 gpurun_out/r02v_bench.err
+python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | cut -c1-400
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r02v_launches_bench.csv python bench.py --steps 2 --warmup 1 --skip-cpu-baseline --skip-meta-train --skip-kernels --slots 2 --tasks-per-step 2 > gpurun_out/r02v_ncu_bench.log 2>&1; tail -2 gpurun_out/r02v_ncu_bench.log | cut -c1-300
+python tools/summarize_launches.py gpurun_out/r02v_launches_bench.csv > gpurun_out/r02v_launches_bench.md; head -30 gpurun_out/r02v_launches_bench.md
