@@ -52,8 +52,10 @@ _FLAGS = [
     ("--sample_foml_train_val_with_replacement", "flag", False, {}), ("--aug_rate", _F, 0.5, {}),
     ("--uho_results_csv_name", _S, "val-set_hyper_param_search_results.csv", {}), ("--uho_estimator", _S, "GP", {}),
     # ---- additions of this implementation (absent from the reference) ----
-    ("--gemm_mode", _S, "fp32", {"help": "numeric mode of the dense contractions: fp32 | tf32 | tf32x3"}),
-    ("--task_slots", _I, 8, {"help": "concurrent task slots per GPU on the device fast path"}),
+    ("--gemm_mode", _S, "tf32x3", {"help": "numeric mode of the dense contractions: tf32x3 (tcgen05, fp32-class accuracy; "
+                                          "default) | tf32 | fp32 (FFMA reference mode)"}),
+    ("--task_slots", _I, 16, {"help": "concurrent task slots per GPU on the device fast path (launched in task-batched "
+                                       "groups of up to 8)"}),
     ("--meta_task_slots", _I, 1, {"help": "meta-training: task slots adapting the tasks of a meta-batch concurrently "
                                           "(1 = the reference's sequential order; S > 1 = per-slot optimizer state, "
                                           "like S ranks)"}),
@@ -106,8 +108,8 @@ def model_kwargs(pa) -> dict:
     kw["n_unet_encoding_stacks"] = pa.n_unet_encoding_stacks
     kw["start_num_feature_maps_power"] = pa.start_num_feature_maps_power
     kw["n_rows"] = kw["n_cols"] = pa.image_size
-    kw["gemm_mode"] = getattr(pa, "gemm_mode", "fp32")
-    kw["task_slots"] = getattr(pa, "task_slots", 8)
+    kw["gemm_mode"] = getattr(pa, "gemm_mode", "tf32x3")
+    kw["task_slots"] = getattr(pa, "task_slots", 16)
     return kw
 
 

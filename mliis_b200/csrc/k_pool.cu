@@ -90,21 +90,30 @@ __global__ void region_sums_kernel(const float* __restrict__ g, int ldg, int H, 
   }
 }
 
-// S[b][tap][n] = sum over the classes in which the tap is valid of Q[b][cls][n];  grid B, block D
-__global__ void region_sums_finalize_kernel(const float* __restrict__ partial, int G, int D, float* __restrict__ S,
-                                            long long zs) {
+// S[b][tap][n] = sum over the classes in which the tap is valid of Q[b][cls][n];  grid B, block (D, 4): lane y sums the
+// chunks y, y + 4, ... of the nine class partials (nine independent loads in flight), the lanes are combined in order
+__global__ void __launch_bounds__(1024) region_sums_finalize_kernel(const float* __restrict__ partial, int G, int D,
+                                                                    float* __restrict__ S, long long zs) {
+  extern __shared__ double sdq[];      // [L][D][9]
   { const size_t zo = (size_t)blockIdx.z * zs; partial += zo; S += zo; }
-  const int b = blockIdx.x, n = threadIdx.x;
+  const int b = blockIdx.x, n = threadIdx.x, ly = threadIdx.y, L = blockDim.y;
   double q[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) q[k] = 0.0;
-  for (int gch = 0; gch < G; ++gch) {       // the 9 loads of a chunk are independent: all in flight together
+  for (int gch = ly; gch < G; gch += L) {
     float v[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) v[k] = partial[(((size_t)b * G + gch) * 9 + k) * D + n];
 #pragma unroll
     for (int k = 0; k < 9; ++k) q[k] += (double)v[k];
   }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) sdq[((size_t)ly * D + n) * 9 + k] = q[k];
+  __syncthreads();
+  if (ly != 0) return;
+  for (int j = 1; j < L; ++j)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) q[k] += sdq[((size_t)j * D + n) * 9 + k];
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
     double s = 0.0;
@@ -133,7 +142,11 @@ void region_sums(const float* g, int ldg, int B, int H, int W, int dil, int D, f
   dim3 blk(D / 4, R);
   MLIIS_COUNT(), region_sums_kernel<<<dim3(G, B, MLIIS_NZ), blk, 9 * blk.x * blk.y * sizeof(float4), s>>>(g, ldg, H, W, dil, D,
                                                                                                        cdiv(H * W, G), partial, MLIIS_ZS);
-  MLIIS_COUNT(), region_sums_finalize_kernel<<<dim3(B, 1, MLIIS_NZ), D, 0, s>>>(partial, G, D, S, MLIIS_ZS);
+  int L = 1024 / D;
+  if (L > 4) L = 4;                      // L * D * 72 bytes of shared memory: stays under the 48 KB default
+  if (L < 1) L = 1;
+  MLIIS_COUNT(), region_sums_finalize_kernel<<<dim3(B, 1, MLIIS_NZ), dim3(D, L), (size_t)L * D * 9 * sizeof(double), s>>>(partial, G, D, S,
+                                                                                                                   MLIIS_ZS);
 }
 
 // dW[tap][c_first + c][n] = sum_b pooled[b][c] * S[b][tap][n];  grid (ceil(Cp/8), 9); block (D, 8)

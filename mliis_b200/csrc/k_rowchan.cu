@@ -446,6 +446,26 @@ void img_colsum(const float* x, int ldx, int B, int HW, int C, float scale, floa
   MLIIS_COUNT(), img_colsum_finalize_kernel<<<dim3(cdiv(C, 128), B, MLIIS_NZ), 128, 0, s>>>(partial, G, C, scale, out, ldo, MLIIS_ZS);
 }
 
+// s += sum_i v[i0 + i*vstep] * w[(i0 + i*vstep) * wstride]  for i0 + i*vstep < n, in that order; the global loads of a batch of 8
+// are issued before the first fma (these one-CTA-per-image kernels are pure latency: one round trip per 8 terms)
+__device__ __forceinline__ float dot_strided(const float* v, const float* __restrict__ w, int i0, int vstep, int n,
+                                             size_t wstride, float s) {
+  for (int i = i0; i < n; i += 8 * vstep) {
+    float wv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = i + u * vstep;
+      wv[u] = k < n ? w[(size_t)k * wstride] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = i + u * vstep;
+      if (k < n) s = fmaf(v[k], wv[u], s);
+    }
+  }
+  return s;
+}
+
 // One block per image.  pool -> reduce FC (+bias, swish) -> expand FC (+bias) -> sigmoid.
 __global__ void se_fc_fwd_kernel(const float* __restrict__ partial, int G, int HW, int C, int Cr,
                                  const float* __restrict__ w1, const float* __restrict__ b1,
@@ -470,8 +490,7 @@ __global__ void se_fc_fwd_kernel(const float* __restrict__ partial, int G, int H
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   for (int r = warp; r < Cr; r += nw) {
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s = fmaf(pool[c], w1[(size_t)c * Cr + r], s);
+    float s = dot_strided(pool, w1 + r, lane, 32, C, (size_t)Cr, 0.f);
     s = warp_sum(s);
     if (lane == 0) {
       s += b1[r];
@@ -481,8 +500,7 @@ __global__ void se_fc_fwd_kernel(const float* __restrict__ partial, int G, int H
   }
   __syncthreads();
   for (int c = tid; c < C; c += nt) {
-    float s = b2[c];
-    for (int r = 0; r < Cr; ++r) s = fmaf(hid[r], w2[(size_t)r * C + c], s);
+    const float s = dot_strided(hid, w2 + c, 0, 1, Cr, (size_t)C, b2[c]);
     gate_o[(size_t)img * C + c] = sigmoid_f(s);
   }
 }
@@ -518,8 +536,7 @@ __global__ void __launch_bounds__(256) se_fc_bwd_img_kernel(const float* __restr
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   for (int r = warp; r < Cr; r += nw) {
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s = fmaf(w2[(size_t)r * C + c], dgp[c], s);
+    float s = dot_strided(dgp, w2 + (size_t)r * C, lane, 32, C, 1, 0.f);
     s = warp_sum(s);
     if (lane == 0) {
       const float v = s * swish_grad_f(hidpre[(size_t)b * Cr + r]);
@@ -530,8 +547,7 @@ __global__ void __launch_bounds__(256) se_fc_bwd_img_kernel(const float* __restr
   __syncthreads();
   const float inv = 1.f / (float)HW;
   for (int c = tid; c < C; c += nt) {
-    float s = 0.f;
-    for (int r = 0; r < Cr; ++r) s = fmaf(w1[(size_t)c * Cr + r], dhp[r], s);
+    const float s = dot_strided(dhp, w1 + (size_t)c * Cr, 0, 1, Cr, 1, 0.f);
     dpool[(size_t)b * C + c] = s * inv;
   }
 }
@@ -546,6 +562,13 @@ __global__ void __launch_bounds__(128) se_fc_bwd_w_kernel(int B, int C, int Cr, 
     const size_t zo = (size_t)blockIdx.z * zs;
     pool += zo; hidpre += zo; dgp += zo; dhp += zo; dw1 += zo; db1 += zo; dw2 += zo; db2 += zo;
   }
+  // the per-image hidden activations / gradients are shared by every channel thread: staged once in shared memory
+  // (the first version re-evaluated swish(hidpre) and re-read both vectors from global memory for every (c, r, b))
+  extern __shared__ float smw[];
+  float* sh = smw;               // [B][Cr] swish(hidden pre-activation)
+  float* sd = smw + B * Cr;      // [B][Cr] d(hidden pre-activation)
+  for (int i = threadIdx.x; i < B * Cr; i += blockDim.x) { sh[i] = swish_f(hidpre[i]); sd[i] = dhp[i]; }
+  __syncthreads();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     float sb = 0.f;
@@ -554,8 +577,8 @@ __global__ void __launch_bounds__(128) se_fc_bwd_w_kernel(int B, int C, int Cr, 
     for (int r = 0; r < Cr; ++r) {
       float s2 = 0.f, s1 = 0.f;
       for (int b = 0; b < B; ++b) {
-        s2 = fmaf(swish_f(hidpre[(size_t)b * Cr + r]), dgp[(size_t)b * C + c], s2);
-        s1 = fmaf(pool[(size_t)b * C + c], dhp[(size_t)b * Cr + r], s1);
+        s2 = fmaf(sh[b * Cr + r], dgp[(size_t)b * C + c], s2);
+        s1 = fmaf(pool[(size_t)b * C + c], sd[b * Cr + r], s1);
       }
       dw2[(size_t)r * C + c] = s2;
       dw1[(size_t)c * Cr + r] = s1;
@@ -575,7 +598,7 @@ void se_fc_bwd(const float* partial, int G, int B, int HW, int C, int Cr, const 
   float* dhp = dgp + (size_t)B * C;
   MLIIS_COUNT(), se_fc_bwd_img_kernel<<<dim3(B, 1, MLIIS_NZ), 256, (C + Cr) * sizeof(float), s>>>(partial, G, HW, C, Cr, w1, w2, hidpre,
                                                                                     gate, dgp, dhp, dpool, MLIIS_ZS);
-  MLIIS_COUNT(), se_fc_bwd_w_kernel<<<dim3(cdiv(C, 128), 1, MLIIS_NZ), 128, 0, s>>>(B, C, Cr, pool, hidpre, dgp, dhp, dw1, db1, dw2, db2,
+  MLIIS_COUNT(), se_fc_bwd_w_kernel<<<dim3(cdiv(C, 128), 1, MLIIS_NZ), 128, 2 * B * Cr * sizeof(float), s>>>(B, C, Cr, pool, hidpre, dgp, dhp, dw1, db1, dw2, db2,
                                                                                    MLIIS_ZS);
 }
 
