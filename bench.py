@@ -595,8 +595,10 @@ def run_b200(args):
     roof = {"bound": "tensor", "kernel": "conv2d_2 3x3 360->112 @56x56 B=8 (implicit GEMM M=25088 N=112 K=3240; as built: "
                                          "pool_taps + tc_conv3_kernel over the 224 real channels, the 136 pooled channels folded into border-class biases)",
             "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-            # dram__bytes_read.sum + dram__bytes_write.sum of the launches: profiles/r02*_ncu_*.md
-            "traffic": None, "peak_source": "%s bf16 cuBLAS burst (kernel timed alone)" % peak_src,
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this very
+            # call (profiles/r02p_prof_tc_conv3.raw.csv.gz: tc_conv3_kernel 24.36 MB read + pool_taps_kernel 0.56 MB;
+            # the 11.2 MB output is still in L2 when the kernel ends); algorithmic: 22.5 MB in + 1.8 MB weights + 11.2 MB out
+            "traffic": 24.92e6, "traffic_unit": "bytes per launch", "peak_source": "%s bf16 cuBLAS burst (kernel timed alone)" % peak_src,
             "kernel_ms": k_ms, "algorithmic_gflop": k_flops / 1e9,
             "frac_of_measured_tf32_peak": (achieved / tpk["tf32_tcgen05_cta_group1_tflops"]) if tpk else None,
             "numeric_mode": {N.GEMM_FP32: "fp32 FFMA", N.GEMM_TF32: "tcgen05 tf32", N.GEMM_TF32X3: "tcgen05 3xtf32"}[mode]}
