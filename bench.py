@@ -581,7 +581,7 @@ def run_b200(args):
 
     meta = None
     if not args.skip_meta_train and mode == N.GEMM_TF32X3 and not args.sgd:
-        meta = meta_train_bench(eng, world, rank, steps=max(2, min(args.steps, 6)), warmup=2, slots=min(8, args.slots))
+        meta = meta_train_bench(eng, world, rank, steps=max(2, min(args.steps, 6)), warmup=2, slots=min(16, args.slots))
 
     if rank != 0:
         if world > 1:

@@ -153,6 +153,8 @@ typedef struct mliis_step_args {
   const uint64_t* dev_seed;        /* optional device scalar added to `seed` when the dropout mask is drawn: lets a
                                       captured CUDA graph draw fresh masks on every replay (NULL = seed only) */
 } mliis_step_args;
+/* After mliis_kernel_group(n, stride) (below) the step runs for the n slots slot .. slot+n-1 in lockstep - one launch per
+ * kernel; every dev_* pointer of args is the first slot's, slot k uses pointer + k*stride (task-batched meta-training). */
 int mliis_train_step(mliis_ctx* ctx, int32_t slot, const mliis_step_args* args, void* stream);
 
 /* The pieces of a step, exposed for parity tests (same buffers as mliis_train_step). */

@@ -28,6 +28,8 @@ ZGroup& zgroup() {
   thread_local ZGroup g{1, 0};
   return g;
 }
+// the group set by mliis_kernel_group for the calling thread (per-kernel entry points and mliis_train_step)
+static thread_local ZGroup t_kernel_group{1, 0};
 bool skip_launch(const char* launcher) {
   static const char* env = getenv("MLIIS_SKIP");
   if (!env || !*env) return false;
@@ -930,6 +932,12 @@ int mliis_optimizer_step(mliis_ctx* ctx, int32_t slot, float lr, float pre_decay
   return check_cuda("optimizer_step");
 }
 
+static int group_validate(mliis_ctx* ctx, int32_t slot, int32_t n_group, int64_t stride_bytes);
+
+// After mliis_kernel_group(n, stride) the step runs for the n slots slot .. slot + n - 1 in LOCKSTEP (one launch per
+// kernel, the slot as a grid dimension): every dev_* pointer of the args is the first slot's, slot k uses pointer +
+// k * stride; lr, pre_decay_rate and the host seed are shared.  This is how the slot-parallel meta-TRAINING path
+// batches the tasks of a meta-batch (runner.TrainSlots); bit-identical to n single-slot calls.
 int mliis_train_step(mliis_ctx* ctx, int32_t slot, const mliis_step_args* a, void* stream) {
   if (!a) return fail(MLIIS_ERR_ARG, "null args");
   int rc = validate(ctx, slot, a->batch);
@@ -937,6 +945,12 @@ int mliis_train_step(mliis_ctx* ctx, int32_t slot, const mliis_step_args* a, voi
   if (!a->dev_images || !a->dev_labels) return fail(MLIIS_ERR_ARG, "null images/labels");
   if (ctx->plan.n_out != 2 && !ctx->slots[slot].class_ids)
     return fail(MLIIS_ERR_STATE, "multi-class head: call mliis_set_class_ids first (labels = masks [n,H,W])");
+  const int ng = t_kernel_group.nz > 1 ? t_kernel_group.nz : 1;
+  if (ng > 1 && ctx->plan.n_out != 2) return fail(MLIIS_ERR_STATE, "task-batched steps run on the binary head");
+  rc = group_validate(ctx, slot, ng, t_kernel_group.zs * 4);
+  if (rc) return rc;
+  ZScope zscope(ng, ng > 1 ? t_kernel_group.zs : 0);
+  ctx->group_fallback = false;
   Run r(ctx, slot, a->batch, (cudaStream_t)stream);
   // reptile.py:112-113 pre_step_op: var *= rate, before the step's forward pass
   if (a->pre_decay_rate != 1.f && a->pre_decay_rate != 0.f) scale_buffer(r.theta, ctx->plan.n_theta, a->pre_decay_rate, r.st);
@@ -944,6 +958,9 @@ int mliis_train_step(mliis_ctx* ctx, int32_t slot, const mliis_step_args* a, voi
   run_backward(r, a->dev_labels, a->dev_index, a->dev_loss_out);
   set_lr(r, a->lr);
   run_optimizer(r, r.W(ctx->plan.lr_dev));
+  if (ctx->group_fallback)
+    return fail(MLIIS_ERR_STATE, "task-batched execution needs the tensor-core modes (a layer fell back to the "
+                                 "single-slot fp32 GEMM kernels)");
   return check_cuda("train_step");
 }
 
@@ -995,6 +1012,23 @@ static int task_body(mliis_ctx* ctx, int32_t slot, const mliis_task_args* a, cud
   return MLIIS_OK;
 }
 
+// a task-batched call on slots slot .. slot + n_group - 1: tensor-core mode, all bound, one layout at a uniform stride
+static int group_validate(mliis_ctx* ctx, int32_t slot, int32_t n_group, int64_t stride_bytes) {
+  if (n_group <= 1) return MLIIS_OK;
+  if (ctx->cfg.gemm_mode == MLIIS_GEMM_FP32) return fail(MLIIS_ERR_ARG, "task-batched execution needs a tensor-core gemm_mode");
+  if (slot + n_group > (int)ctx->slots.size()) return fail(MLIIS_ERR_ARG, "group exceeds n_slots");
+  if (stride_bytes <= 0 || (stride_bytes & 255)) return fail(MLIIS_ERR_ARG, "group stride must be a positive multiple of 256");
+  const Slot& s0 = ctx->slots[slot];
+  for (int k = 1; k < n_group; ++k) {
+    const Slot& sk = ctx->slots[slot + k];
+    if (!sk.state || !sk.ws) return fail(MLIIS_ERR_STATE, "slot %d not bound", slot + k);
+    if ((const char*)sk.state - (const char*)s0.state != (ptrdiff_t)k * stride_bytes ||
+        (const char*)sk.ws - (const char*)s0.ws != (ptrdiff_t)k * stride_bytes)
+      return fail(MLIIS_ERR_ARG, "slots %d..%d are not laid out at the uniform group stride", slot, slot + n_group - 1);
+  }
+  return MLIIS_OK;
+}
+
 static int task_validate(mliis_ctx* ctx, int32_t slot, const mliis_task_args* a) {
   if (!a) return fail(MLIIS_ERR_ARG, "null args");
   int rc = validate(ctx, slot, a->batch);
@@ -1003,20 +1037,7 @@ static int task_validate(mliis_ctx* ctx, int32_t slot, const mliis_task_args* a)
   if (a->n_steps < 0) return fail(MLIIS_ERR_ARG, "n_steps < 0");
   if (!a->dev_init_state || !a->dev_images || !a->dev_labels || !a->dev_batch_index || !a->dev_lr || !a->dev_query_index)
     return fail(MLIIS_ERR_ARG, "null task argument");
-  if (a->n_group > 1) {
-    if (ctx->cfg.gemm_mode == MLIIS_GEMM_FP32) return fail(MLIIS_ERR_ARG, "task-batched execution needs a tensor-core gemm_mode");
-    if (slot + a->n_group > (int)ctx->slots.size()) return fail(MLIIS_ERR_ARG, "group exceeds n_slots");
-    if (a->group_stride_bytes <= 0 || (a->group_stride_bytes & 255)) return fail(MLIIS_ERR_ARG, "group stride must be a positive multiple of 256");
-    const Slot& s0 = ctx->slots[slot];
-    for (int k = 1; k < a->n_group; ++k) {
-      const Slot& sk = ctx->slots[slot + k];
-      if (!sk.state || !sk.ws) return fail(MLIIS_ERR_STATE, "slot %d not bound", slot + k);
-      if ((const char*)sk.state - (const char*)s0.state != (ptrdiff_t)k * a->group_stride_bytes ||
-          (const char*)sk.ws - (const char*)s0.ws != (ptrdiff_t)k * a->group_stride_bytes)
-        return fail(MLIIS_ERR_ARG, "slots %d..%d are not laid out at the uniform group stride", slot, slot + a->n_group - 1);
-    }
-  }
-  return MLIIS_OK;
+  return group_validate(ctx, slot, a->n_group, a->group_stride_bytes);
 }
 
 int mliis_adapt_eval_task(mliis_ctx* ctx, int32_t slot, const mliis_task_args* a, void* stream) {
@@ -1248,7 +1269,6 @@ static int require_sm100() {
 
 // Task-batched per-kernel calls: mliis_kernel_group(n, stride) makes every following per-kernel entry point of this
 // thread launch once for n slot copies laid out `stride` bytes apart (every pointer argument is slot 0's).
-static thread_local ZGroup t_kernel_group{1, 0};
 int mliis_kernel_group(int32_t n_group, int64_t group_stride_bytes) {
   if (n_group < 1 || n_group > 1024) return fail(MLIIS_ERR_ARG, "n_group must be in [1, 1024]");
   if (n_group > 1 && (group_stride_bytes <= 0 || (group_stride_bytes & 15))) return fail(MLIIS_ERR_ARG, "bad group stride");

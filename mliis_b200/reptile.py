@@ -291,12 +291,25 @@ class Gecko:
                 n_rows = num_shots + sum(len(b) for b in plans[0][2])
             shape = (n_rows, tuple(len(b) for b in plans[0][2]), tuple(tuple(l) for l in lrs), fomaml,
                      self._pre_decay())
+            n_max = min(self.meta_task_slots, eng.n_slots)
+            # task-batched groups of slots when the rank's tasks fill whole groups (Reptile meta-batch 40 on 16 slots:
+            # 5 chunks of 8); augmented pools live outside the uniform-stride arena, fp32 mode has no batched kernels
+            group = 1
+            if self.augmenter is None and eng.gemm_mode != N_GEMM_FP32:
+                for g in (8, 4, 2):
+                    if len(plans) % g == 0 and n_max % g == 0:
+                        group = g
+                        break
+            shape = shape + (group,)
             if self._train_slots is None or self._train_slots.shape != shape:
-                self._train_slots = TrainSlots(eng, min(self.meta_task_slots, eng.n_slots), shape)
+                try:
+                    self._train_slots = TrainSlots(eng, n_max, shape[:-1], group=group)
+                except ValueError:               # the pool does not fit the arena's staging region: single-slot launches
+                    self._train_slots = TrainSlots(eng, n_max, shape[:-1], group=1)
+                self._train_slots.shape = shape
             ts = self._train_slots
             ts.begin(eng.theta(0))
-            for i, (images, labels, batches) in enumerate(plans):
-                ts.submit(i % ts.n, images, labels, batches)
+            ts.run_tasks(plans)
             buf = ts.finish()
             n_write = ts.n
         else:

@@ -328,25 +328,53 @@ class TrainSlots:
     dsum_s += theta_s - theta_ref (theta_ref = theta_old for Reptile, the weights before the last step for FOMAML).
     Inputs live in per-slot staging buffers so that the graph can be replayed for every task."""
 
-    def __init__(self, eng: Engine, n: int, shape):
+    def __init__(self, eng: Engine, n: int, shape, group: int = 1):
+        """group = G > 1: G consecutive slots adapt their tasks in LOCKSTEP - one graph per group whose inner steps are
+        task-batched launches (mliis_kernel_group + mliis_train_step: every kernel serves G tasks).  The per-slot inputs
+        then live in the slots' staging regions of the engine arena (uniform stride).  Bit-identical to group = 1."""
         n_pool, batch_sizes, lrs, fomaml, pre_decay = shape
-        self.eng, self.n, self.shape, self.fomaml = eng, n, shape, fomaml
+        if group < 1 or n % group:
+            raise ValueError("group (%d) must divide the number of training slots (%d)" % (group, n))
+        self.eng, self.n, self.shape, self.fomaml, self.group = eng, n, shape, fomaml, group
         S, dev = eng.image_size, eng.device
         self.old = torch.empty(eng.n_theta, dtype=torch.float32, device=dev)
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(n)]
-        self.x = [torch.empty(n_pool, S, S, 3, dtype=torch.float32, device=dev) for _ in range(n)]
-        self.y = [torch.empty(n_pool, S, S, 2, dtype=torch.float32, device=dev) for _ in range(n)]
-        self.xp = [torch.empty(n_pool, S, S, 3, dtype=torch.float32).pin_memory() for _ in range(n)]
-        self.yp = [torch.empty(n_pool, S, S, 2, dtype=torch.float32).pin_memory() for _ in range(n)]
-        self.idx = [[torch.zeros(b, dtype=torch.int32, device=dev) for b in batch_sizes] for _ in range(n)]
-        self.idxp = [[torch.zeros(b, dtype=torch.int32).pin_memory() for b in batch_sizes] for _ in range(n)]
+        if group == 1:
+            self.x = [torch.empty(n_pool, S, S, 3, dtype=torch.float32, device=dev) for _ in range(n)]
+            self.y = [torch.empty(n_pool, S, S, 2, dtype=torch.float32, device=dev) for _ in range(n)]
+            self.idx = [[torch.zeros(b, dtype=torch.int32, device=dev) for b in batch_sizes] for _ in range(n)]
+            self.seed = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(n)]   # per-replay dropout seeds
+        else:
+            self.x, self.y, self.idx, self.seed = [], [], [], []
+            for s_ in range(n):          # the same carve in every slot: one offset serves the whole group
+                stg, off = eng.staging(s_), 0
+
+                def carve(n_elems, dtype):
+                    nonlocal off
+                    nbytes = n_elems * 4
+                    if off + nbytes > stg.numel():
+                        raise ValueError("the engine's per-slot staging region is too small for this task shape")
+                    t = stg[off:off + nbytes].view(dtype)
+                    off = (off + nbytes + 255) // 256 * 256
+                    return t
+                self.x.append(carve(n_pool * S * S * 3, torch.float32).view(n_pool, S, S, 3))
+                self.y.append(carve(n_pool * S * S * 2, torch.float32).view(n_pool, S, S, 2))
+                self.idx.append([carve(b, torch.int32) for b in batch_sizes])
+                self.seed.append(carve(2, torch.int32).view(torch.int64))
+        # two pinned host sets per slot: staging workers fill the set of the slot's NEXT task while the current one runs
+        self.xp = [[torch.empty(n_pool, S, S, 3, dtype=torch.float32).pin_memory() for _ in range(2)] for _ in range(n)]
+        self.yp = [[torch.empty(n_pool, S, S, 2, dtype=torch.float32).pin_memory() for _ in range(2)] for _ in range(n)]
+        self.idxp = [[[torch.zeros(b, dtype=torch.int32).pin_memory() for b in batch_sizes] for _ in range(2)]
+                     for _ in range(n)]
         self.dsum2d = torch.zeros(n, eng.n_theta, dtype=torch.float32, device=dev)     # per-slot delta sums (rows)
         self.dsum = [self.dsum2d[s] for s in range(n)]
         self.buf = eng.meta_buffer()                      # the exchanged buffer (mliis_meta_reduce / allreduce / finish)
         self.backup = [torch.empty(eng.n_theta, dtype=torch.float32, device=dev) if fomaml else None
                        for _ in range(n)]
-        self.seed = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(n)]     # per-replay dropout seeds
-        self.seedp = [torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(n)]
+        self.seedp = [[torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(2)] for _ in range(n)]
+        self.h2d_done = [[None, None] for _ in range(n)]      # cuda events: the set's copies have left the host
+        from concurrent.futures import ThreadPoolExecutor
+        self._pool = ThreadPoolExecutor(max_workers=3, thread_name_prefix="mliis-train-stage")
         self._submitted = 0
         self.graphs = [None] * n
         self.used = [False] * n
@@ -355,22 +383,32 @@ class TrainSlots:
         self._lrs, self._pre_decay = lrs, pre_decay
 
     def _body(self, s: int) -> None:
-        eng = self.eng
-        theta = eng.theta(s)
-        theta.copy_(self.old)
+        """One task on each of the slots s .. s + group - 1 (s is the first slot of its group)."""
+        eng, G = self.eng, self.group
+        thetas = [eng.theta(s + k) for k in range(G)]
+        for th in thetas:
+            th.copy_(self.old)
         T = len(self._lrs)
         for j in range(T):
             if self.fomaml and j == T - 1:
-                self.backup[s].copy_(theta)                       # last_backup (reptile.py:635-636)
+                for k in range(G):
+                    self.backup[s + k].copy_(thetas[k])           # last_backup (reptile.py:635-636)
             for k, step_lr in enumerate(self._lrs[j]):
-                eng.train_step(s, self.x[s], self.y[s], step_lr, index=self.idx[s][j],
-                               pre_decay_rate=self._pre_decay if k == 0 else 1.0, seed=1 + j, seed_dev=self.seed[s])
-        eng.delta_accumulate(self.dsum[s], theta, self.backup[s] if self.fomaml else self.old, first=False)
+                if G > 1:
+                    N.check(eng.lib.mliis_kernel_group(G, eng.slot_stride))
+                try:
+                    eng.train_step(s, self.x[s], self.y[s], step_lr, index=self.idx[s][j],
+                                   pre_decay_rate=self._pre_decay if k == 0 else 1.0, seed=1 + j, seed_dev=self.seed[s])
+                finally:
+                    if G > 1:
+                        N.check(eng.lib.mliis_kernel_group(1, 0))
+        for k in range(G):
+            eng.delta_accumulate(self.dsum[s + k], thetas[k], self.backup[s + k] if self.fomaml else self.old, first=False)
 
     def _capture(self, s: int) -> None:
         st = self.streams[s]
         with torch.cuda.stream(st):
-            self._body(s)            # warm-up outside the graph (one-time memsets / attribute calls); the slot's
+            self._body(s)            # warm-up outside the graph (one-time memsets / attribute calls); the slots'
             st.synchronize()         # optimizer / BN state advances by one task: restored by begin() below
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=st):
@@ -389,6 +427,11 @@ class TrainSlots:
             for s in range(self.n):
                 self.x[s].zero_()
                 self.y[s].zero_()
+                for t_ in self.idx[s]:
+                    t_.zero_()
+                self.seed[s].zero_()
+            torch.cuda.synchronize()
+            for s in range(0, self.n, self.group):
                 self._capture(s)
             torch.cuda.synchronize()
             for s in range(self.n):
@@ -404,26 +447,76 @@ class TrainSlots:
             self.used[s] = False
         torch.cuda.synchronize()
 
-    def submit(self, s: int, images: np.ndarray, labels: np.ndarray, batches) -> None:
-        st = self.streams[s]
-        st.synchronize()                                   # the slot's pinned staging is free again
+    def _fill(self, s: int, w: int, images: np.ndarray, labels: np.ndarray, batches, seed: int) -> int:
+        """Host arrays -> pinned set w of slot s (runs on a staging worker thread)."""
+        torch.cuda.set_device(self.eng.device)
+        if self.h2d_done[s][w] is not None:
+            self.h2d_done[s][w].synchronize()              # the copies that last read this set have left the host
         n = images.shape[0]                                # <= n_pool (augmented pools vary in size)
-        if n > self.xp[s].shape[0]:
-            raise ValueError("task pool of %d examples exceeds the slot's capacity (%d)" % (n, self.xp[s].shape[0]))
-        self.xp[s][:n].copy_(torch.from_numpy(np.ascontiguousarray(images, np.float32)))
-        self.yp[s][:n].copy_(torch.from_numpy(np.ascontiguousarray(labels, np.float32)))
+        if n > self.xp[s][w].shape[0]:
+            raise ValueError("task pool of %d examples exceeds the slot's capacity (%d)" % (n, self.xp[s][w].shape[0]))
+        self.xp[s][w][:n].copy_(torch.from_numpy(np.ascontiguousarray(images, np.float32)))
+        self.yp[s][w][:n].copy_(torch.from_numpy(np.ascontiguousarray(labels, np.float32)))
         for j, b in enumerate(batches):
-            self.idxp[s][j].copy_(torch.as_tensor(np.asarray(b, np.int32)))
-        self._submitted += 1
-        self.seedp[s][0] = 1000003 * self._submitted
+            self.idxp[s][w][j].copy_(torch.as_tensor(np.asarray(b, np.int32)))
+        self.seedp[s][w][0] = seed
+        return n
+
+    def _launch(self, s: int, w: int, counts, n_batches: int) -> None:
+        """H2D of the pinned sets of the slots s .. s + group - 1 + ONE graph replay on the group's stream.  No host
+        synchronisation: the stream orders the copies after the group's previous tasks (which read the same buffers)."""
+        st = self.streams[s]
         with torch.cuda.stream(st):
-            self.seed[s].copy_(self.seedp[s], non_blocking=True)
-            self.x[s][:n].copy_(self.xp[s][:n], non_blocking=True)
-            self.y[s][:n].copy_(self.yp[s][:n], non_blocking=True)
-            for j in range(len(batches)):
-                self.idx[s][j].copy_(self.idxp[s][j], non_blocking=True)
+            for k, n in enumerate(counts):
+                q = s + k
+                self.seed[q].copy_(self.seedp[q][w], non_blocking=True)
+                self.x[q][:n].copy_(self.xp[q][w][:n], non_blocking=True)
+                self.y[q][:n].copy_(self.yp[q][w][:n], non_blocking=True)
+                for j in range(n_batches):
+                    self.idx[q][j].copy_(self.idxp[q][w][j], non_blocking=True)
+                if self.h2d_done[q][w] is None:
+                    self.h2d_done[q][w] = torch.cuda.Event()
+                self.h2d_done[q][w].record(st)
+                self.used[q] = True
             self.graphs[s].replay()
-        self.used[s] = True
+
+    def run_tasks(self, plans) -> None:
+        """plans: [(images, labels, batches)] of this rank's tasks of one meta-batch, dealt in chunks of `group` tasks
+        round-robin to the groups of slots.  Host staging runs one round AHEAD of the launches (round r uses pinned
+        set r & 1 of every slot)."""
+        G = self.group
+        if len(plans) % G:
+            raise ValueError("%d tasks do not fill groups of %d slots" % (len(plans), G))
+        n_chunks, n_units = len(plans) // G, self.n // G
+        # balanced rounds: 10 chunks on 8 units would run as 8 + 2; use ceil(chunks / rounds) units instead (5 + 5)
+        rounds = (n_chunks + n_units - 1) // n_units
+        nu = (n_chunks + rounds - 1) // rounds if n_chunks else n_units
+        futs = {}
+
+        def submit_fill(c):
+            s0, w = (c % nu) * G, (c // nu) & 1
+            fl = []
+            for k in range(G):
+                images, labels, batches = plans[c * G + k]
+                self._submitted += 1
+                fl.append(self._pool.submit(self._fill, s0 + k, w, images, labels, batches, 1000003 * self._submitted))
+            futs[c] = fl
+
+        for c in range(min(nu, n_chunks)):
+            submit_fill(c)
+        for c in range(n_chunks):
+            counts = [f.result() for f in futs.pop(c)]
+            self._launch((c % nu) * G, (c // nu) & 1, counts, len(plans[c * G][2]))
+            if c + nu < n_chunks:
+                submit_fill(c + nu)
+
+    def submit(self, s: int, images: np.ndarray, labels: np.ndarray, batches) -> None:
+        """One task on slot s, staged synchronously (kept for callers that feed tasks one by one)."""
+        if self.group != 1:
+            raise ValueError("submit() feeds single slots; use run_tasks() with grouped slots")
+        self._submitted += 1
+        cnt = self._fill(s, 0, images, labels, batches, 1000003 * self._submitted)
+        self._launch(s, 0, [cnt], len(batches))
 
     def finish(self) -> torch.Tensor:
         """Builds the exchange buffer of this rank on the current stream - [sum of the slot deltas | sum of the BN

@@ -301,8 +301,8 @@ def test_tfrecord_tasks_equal_synthetic_tasks_on_the_device_fast_path(tmp_path):
     assert list(out[0][1].values()) == list(out[1][1].values())
 
 
-@pytest.mark.parametrize("foml", [False, True])
-def test_slot_parallel_meta_step_equals_sequential_under_sgd(foml):
+@pytest.mark.parametrize("foml,gemm,nslots", [(False, "fp32", 3), (True, "fp32", 3), (False, "tf32x3", 4), (True, "tf32x3", 4)])
+def test_slot_parallel_meta_step_equals_sequential_under_sgd(foml, gemm, nslots):
     """meta_task_slots > 1: tasks of a meta-batch adapt concurrently on task slots (one CUDA graph per slot).  With
     SGD the trainables do not depend on the order in which tasks ran (training-mode BN uses batch statistics), so
     the meta-update must equal the sequential reference order up to summation order."""
@@ -310,8 +310,10 @@ def test_slot_parallel_meta_step_equals_sequential_under_sgd(foml):
     from mliis_b200.reptile import FOMLIS, Gecko
     from mliis_b200.session import Session
     out, bn = [], []
-    for slots in (1, 3):
-        m = _model(optimizer="sgd", task_slots=3)
+    # tf32x3 with 4 slots and a meta-batch of 4: the four tasks run as ONE task-batched group (mliis_kernel_group +
+    # mliis_train_step, every kernel launched once for the four slots)
+    for slots in (1, nslots):
+        m = _model(optimizer="sgd", task_slots=nslots, gemm_mode=gemm)
         sess = Session(m)
         _warm(sess, m, 2)
         tasks = _tasks(6, 800, n_examples=15)
