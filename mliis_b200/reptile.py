@@ -296,14 +296,16 @@ class Gecko:
             # 5 chunks of 8); augmented pools live outside the uniform-stride arena, fp32 mode has no batched kernels
             group = 1
             if self.augmenter is None and eng.gemm_mode != N_GEMM_FP32:
-                for g in (8, 4, 2):
-                    if len(plans) % g == 0 and n_max % g == 0:
+                # at least two groups in flight: ONE lockstep group is a single serial chain of kernels (measured: FOMAML
+                # meta-batch 5 as one group of five 19.0 meta-steps/s, as five single-slot graphs 20.5)
+                for g in range(min(8, n_max, len(plans) // 2), 1, -1):
+                    if len(plans) % g == 0:
                         group = g
                         break
             shape = shape + (group,)
             if self._train_slots is None or self._train_slots.shape != shape:
                 try:
-                    self._train_slots = TrainSlots(eng, n_max, shape[:-1], group=group)
+                    self._train_slots = TrainSlots(eng, (n_max // group) * group, shape[:-1], group=group)
                 except ValueError:               # the pool does not fit the arena's staging region: single-slot launches
                     self._train_slots = TrainSlots(eng, n_max, shape[:-1], group=1)
                 self._train_slots.shape = shape

@@ -1,4 +1,10 @@
-timeout 1800 python -m pytest tests/test_gpu_host.py tests/test_gpu_parity2.py -q -x 2>&1 | tail -4
-python bench.py --steps 6 --warmup 3 --skip-cpu-baseline --skip-kernels 2>gpurun_out/r02zd_bench.err | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('value %.2f e2e %.2f' % (d['value'], d['e2e']['value'])); print('meta', {k:(round(v['meta_steps_per_s'],3), round(v['tasks_per_s'],1), v['task_slots_per_rank']) for k,v in d['meta_train'].items()})"
-tail -3 gpurun_out/r02zd_bench.err
+timeout 1800 python -m pytest tests -q -m gpu 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | cut -c1-200
+python bench.py > gpurun_out/r02zf_bench.json 2> gpurun_out/r02zf_bench.err; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r02zf_bench.json').read().strip().splitlines()[-1])
+print('value', d['value'], 'e2e', d['e2e']['value'], 'roofline', d['roofline']['frac'], d['roofline']['kernel_ms'], 'launches', d['gpu_launches'], 'steps', d['steps'], 'ms/step', d['ms_per_step'])
+print('meta', {k:(round(v['meta_steps_per_s'],3), round(v['tasks_per_s'],1)) for k,v in d['meta_train'].items()})
+print('miou', d['miou_vs_oracle']['max_abs_diff'], d['miou_vs_oracle']['mean_abs_diff'], 'cpu', d['cpu_baseline']['value'])
+PY
+tail -2 gpurun_out/r02zf_bench.err
