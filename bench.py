@@ -258,34 +258,38 @@ def _time_launch(fn, flush, reps=8, warm=3):
     return float(np.mean(times))
 
 
-def time_dominant_kernel(mode, flush):
+def time_dominant_kernel(mode, flush, n_group=1):
     """conv2d_2 of decode_skip_connections_1 (efficientlab.py:224): 3x3, 360->112 at 56x56, B=8 - 57 % of the forward
-    FLOPs.  Algorithmic work = the reference op: 2*8*56*56*9*360*112 = 18.21 GFLOP.  As built: the 136 image-pooling
-    channels are folded into a per-image, per-border-class bias (pool_taps kernel + the conv's prologue) and the implicit GEMM runs over
-    the 224 real channels; both launches are inside the timed region."""
+    FLOPs.  Algorithmic work = the reference op: 2*8*56*56*9*360*112 = 18.21 GFLOP per task slot.  As built: the 136
+    image-pooling channels are folded into a per-image, per-border-class bias (pool_taps kernel + the conv's prologue) and
+    the implicit GEMM runs over the 224 real channels; both launches are inside the timed region.  n_group > 1: the
+    task-batched launch the bench's graphs issue (one launch serves n_group slots, each with its own weights)."""
     import torch
     from mliis_b200 import native as N
     B, H, Cin, Cp, Cout = INNER_BATCH, 56, 224, 136, 112
-    g = torch.Generator(device="cuda").manual_seed(0)
-    x = torch.randn(B, H, H, Cin, device="cuda", generator=g)
-    pooled = torch.randn(B, Cp, device="cuda", generator=g)
-    w = torch.randn(3, 3, Cin + Cp, Cout, device="cuda", generator=g) * 0.02
-    bias = torch.zeros(Cout, device="cuda")
-    y = torch.empty(B, H, H, Cout, device="cuda")
-    b9 = torch.empty(B, 9, Cout, device="cuda")
     lib = N.lib()
     st = torch.cuda.current_stream().cuda_stream
-    flops = 2.0 * B * H * H * 9 * (Cin + Cp) * Cout
+    flops = 2.0 * B * H * H * 9 * (Cin + Cp) * Cout * n_group
     if mode == N.GEMM_FP32:
-        xf = torch.cat([x, pooled.view(B, 1, 1, Cp).expand(B, H, H, Cp)], -1).contiguous()
+        g = torch.Generator(device="cuda").manual_seed(0)
+        xf = torch.randn(B, H, H, Cin + Cp, device="cuda", generator=g)
+        w = torch.randn(3, 3, Cin + Cp, Cout, device="cuda", generator=g) * 0.02
+        bias = torch.zeros(Cout, device="cuda")
+        y = torch.empty(B, H, H, Cout, device="cuda")
         ms = _time_launch(lambda: N.check(lib.mliis_conv3x3_fwd(xf.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), B,
                                                                 H, H, Cin + Cp, Cout, 1, mode, st)), flush)
-        return ms, flops
-    wt = torch.empty(2 * 9 * Cin * Cout, device="cuda")
-    N.check(lib.mliis_tc_prep_weights_sub(w.data_ptr(), wt.data_ptr(), 9, Cin, Cin + Cp, Cout, 0, mode, st))
-    ms = _time_launch(lambda: N.check(lib.mliis_rsd_conv2_fwd(x.data_ptr(), Cin, pooled.data_ptr(), w.data_ptr(), wt.data_ptr(),
-                                                              bias.data_ptr(), b9.data_ptr(), y.data_ptr(), B, H, H, Cin, Cp,
-                                                              Cout, mode, st)), flush)
+        return ms, flops / n_group
+    ar = _Arena(n_group, dict(x=B * H * H * Cin, pooled=B * Cp, w=9 * (Cin + Cp) * Cout, wt=2 * 9 * Cin * Cout, bias=Cout,
+                              b9=B * 9 * Cout, y=B * H * H * Cout))
+    ar.buf[:, ar.off["w"]:ar.off["w"] + 9 * (Cin + Cp) * Cout] *= 0.04
+    N.check(lib.mliis_kernel_group(n_group, ar.stride * 4))
+    try:
+        N.check(lib.mliis_tc_prep_weights_sub(ar.p("w"), ar.p("wt"), 9, Cin, Cin + Cp, Cout, 0, mode, st))
+        ms = _time_launch(lambda: N.check(lib.mliis_rsd_conv2_fwd(ar.p("x"), Cin, ar.p("pooled"), ar.p("w"), ar.p("wt"),
+                                                                  ar.p("bias"), ar.p("b9"), ar.p("y"), B, H, H, Cin, Cp,
+                                                                  Cout, mode, st)), flush)
+    finally:
+        N.check(lib.mliis_kernel_group(1, 0))
     return ms, flops
 
 
@@ -589,18 +593,31 @@ def run_b200(args):
         return
     peaks, peak_src = measured_peaks()
     flush = _Flusher()
-    k_ms, k_flops = time_dominant_kernel(mode, flush)
+    n_grp = max(1, args.group) if mode != N.GEMM_FP32 else 1
+    k_ms, k_flops = time_dominant_kernel(mode, flush, n_grp)          # the launch as the bench's graphs issue it
+    k1_ms, k1_flops = time_dominant_kernel(mode, flush, 1) if n_grp > 1 else (k_ms, k_flops)
     achieved = k_flops / (k_ms * 1e-3) / 1e12
     tpk = tensor_peaks(peaks) if mode != N.GEMM_FP32 else None
-    roof = {"bound": "tensor", "kernel": "conv2d_2 3x3 360->112 @56x56 B=8 (implicit GEMM M=25088 N=112 K=3240; as built: "
-                                         "pool_taps + tc_conv3_kernel over the 224 real channels, the 136 pooled channels folded into border-class biases)",
+    # tensor-pipe work actually ISSUED per slot: 224 two-row pixel tiles (128 MMA rows for 112 pixels) x 252 k-steps of 8
+    # channels x (one 128x224x8 + one 128x112x8 MMA in 3xTF32, one 128x112x8 in TF32)
+    issued = 2.0 * 224 * 252 * 128 * 8 * (336 if mode == N.GEMM_TF32X3 else 112) * n_grp
+    roof = {"bound": "tensor", "kernel": "conv2d_2 3x3 360->112 @56x56 B=8 (implicit GEMM M=25088 N=112 K=3240 per task slot; as built: "
+                                         "pool_taps + tc_conv3_kernel over the 224 real channels, the 136 pooled channels folded into border-class biases), "
+                                         "task-batched launch over %d slots as the bench's graphs issue it" % n_grp,
             "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this very
+            "slots_per_launch": n_grp,
+            # dram__bytes_read.sum + dram__bytes_write.sum per slot from the `ncu --set full` capture of the single-slot
             # call (profiles/r02p_prof_tc_conv3.raw.csv.gz: tc_conv3_kernel 24.36 MB read + pool_taps_kernel 0.56 MB;
             # the 11.2 MB output is still in L2 when the kernel ends); algorithmic: 22.5 MB in + 1.8 MB weights + 11.2 MB out
-            "traffic": 24.92e6, "traffic_unit": "bytes per launch", "peak_source": "%s bf16 cuBLAS burst (kernel timed alone)" % peak_src,
+            "traffic": 24.92e6 * n_grp, "traffic_unit": "bytes per launch (single-slot capture x slots)",
+            "peak_source": "%s bf16 cuBLAS burst (kernel timed alone)" % peak_src,
             "kernel_ms": k_ms, "algorithmic_gflop": k_flops / 1e9,
             "frac_of_measured_tf32_peak": (achieved / tpk["tf32_tcgen05_cta_group1_tflops"]) if tpk else None,
+            "tensor_pipe_issued_tflops": (issued / (k_ms * 1e-3) / 1e12) if mode != N.GEMM_FP32 else None,
+            "tensor_pipe_issued_frac_of_tf32_peak": (issued / (k_ms * 1e-3) / 1e12 / tpk["tf32_tcgen05_cta_group1_tflops"]) if tpk else None,
+            "single_slot": {"kernel_ms": k1_ms, "achieved": k1_flops / (k1_ms * 1e-3) / 1e12,
+                            "frac": k1_flops / (k1_ms * 1e-3) / 1e12 / peaks["bf16_tflops"],
+                            "note": "one slot per launch: 112 CTAs on 148 SMs"},
             "numeric_mode": {N.GEMM_FP32: "fp32 FFMA", N.GEMM_TF32: "tcgen05 tf32", N.GEMM_TF32X3: "tcgen05 3xtf32"}[mode]}
     hbm = None
     if not args.skip_kernels and mode != N.GEMM_FP32:

@@ -28,6 +28,10 @@ ZGroup& zgroup() {
   thread_local ZGroup g{1, 0};
   return g;
 }
+int partition_nz() {
+  const char* e = getenv("MLIIS_GROUP_CANONICAL");
+  return (e && atoi(e) != 0) ? 1 : zgroup().nz;
+}
 // the group set by mliis_kernel_group for the calling thread (per-kernel entry points and mliis_train_step)
 static thread_local ZGroup t_kernel_group{1, 0};
 bool skip_launch(const char* launcher) {

@@ -46,7 +46,30 @@ void reduce_partials_strided(const float* partials, int G, int n_inner, int n_ou
   MLIIS_COUNT(), reduce_partials_strided_kernel<<<dim3(cdiv(n, 32), 1, MLIIS_NZ), dim3(32, 8), 0, s>>>(partials, G, n, n_inner, out,
                                                                                                       out_stride, MLIIS_ZS);
 }
+// G <= 8 partials (task-batched launches split every slot's reduction a few times only): one float4 of outputs per
+// thread, the partials added in index order in double - the same order as the lane version, where every lane then holds
+// at most one partial.
+__global__ void __launch_bounds__(256) reduce_partials_small_kernel(const float* __restrict__ partials, int G, int n4,
+                                                                    float* __restrict__ out, long long zs) {
+  { const size_t zo = (size_t)blockIdx.z * zs; partials += zo; out += zo; }
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n4) return;
+  float4 v[8];
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    if (g < G) v[g] = ld4(partials + ((size_t)g * n4 + i) * 4);
+  double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    if (g < G) { a += (double)v[g].x; b += (double)v[g].y; c += (double)v[g].z; d += (double)v[g].w; }
+  st4(out + (size_t)i * 4, f4((float)a, (float)b, (float)c, (float)d));
+}
 void reduce_partials(const float* partials, int G, int n, float* out, cudaStream_t s) {
+  if (G <= 8 && n % 4 == 0 && (reinterpret_cast<uintptr_t>(partials) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+      (MLIIS_ZS % 4) == 0) {
+    MLIIS_COUNT(), reduce_partials_small_kernel<<<dim3(cdiv(n / 4, 256), 1, MLIIS_NZ), 256, 0, s>>>(partials, G, n / 4, out, MLIIS_ZS);
+    return;
+  }
   MLIIS_COUNT(), reduce_partials_kernel<<<dim3(cdiv(n, 32), 1, MLIIS_NZ), dim3(32, 8), 0, s>>>(partials, G, n, out, MLIIS_ZS);
 }
 

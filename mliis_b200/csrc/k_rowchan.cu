@@ -32,17 +32,26 @@ static inline int rc_R(int C) {
 }
 static inline dim3 rc_block(int C) { return dim3(C / 4, rc_R(C)); }
 
+// Row chunks = CTAs (and partial rows) per slot.  Task-batched launches (nz slots per launch) keep about the same number
+// of CTAs per LAUNCH - 1184 = 8 resident 256-thread CTAs per SM - so every slot gets nz times fewer, longer chunks and
+// its finalize kernel reads nz times fewer partials (partition_nz(), kernels.h).
 int rc_num_chunks(int M, int C) {
   int R = rc_R(C);
   int G = cdiv(M, R * 8);
-  if (G > 296) G = 296;
+  int cap = 1184 / partition_nz();
+  if (cap > 296) cap = 296;
+  if (cap < 37) cap = 37;
+  if (G > cap) G = cap;
   if (G < 1) G = 1;
   return G;
 }
 int rc_num_img_chunks(int HW, int C) {
   int R = rc_R(C);
   int G = cdiv(HW, R * 8);
-  if (G > 32) G = 32;
+  int cap = 128 / partition_nz();
+  if (cap > 32) cap = 32;
+  if (cap < 8) cap = 8;
+  if (G > cap) G = cap;
   if (G < 1) G = 1;
   return G;
 }

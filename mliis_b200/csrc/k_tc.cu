@@ -1887,9 +1887,12 @@ static int wg_splits(int ctiles, int taps, int tiles_total) {
   // CTAs per launch the pixel range is split for.  One CTA per SM: every split writes a full [taps*C, N] fp32 partial
   // that reduce_partials reads back, so 296 (two waves at one resident CTA per SM) doubled that traffic for nothing -
   // measured on the whole job: 296 -> 104.5, 222 -> 107.2, 148 -> 109.2 tasks/s (MLIIS_WG_TARGET overrides).
+  // Task-batched launches (nz slots per launch) split every slot's range nz times less: the target is CTAs per LAUNCH.
+  // Measured at 16 slots per launch: 148 splits per slot (2368 CTAs of 2-21 K-blocks each) 122.0 tasks/s, 37 -> 131.7,
+  // 19 -> 134.5, 10 -> 135.5.  The summation tree of dW therefore depends on the group size (partition_nz()).
   static int target = -1;
   if (target < 0) { const char* e = getenv("MLIIS_WG_TARGET"); target = e ? atoi(e) : 148; }
-  int base = ctiles * taps;
+  int base = ctiles * taps * partition_nz();
   int S = target / base;
   if (S < 1) S = 1;
   if (S > tiles_total / 2) S = tiles_total / 2;   // at least 2 pixel tiles (64 pixels) per CTA

@@ -28,6 +28,12 @@ struct ZScope {
   ~ZScope() { zgroup() = saved; }
 };
 #define MLIIS_NZ (::mliis::zgroup().nz)
+// How many slots share the launch when a launcher sizes its reduction partials (wgrad pixel-range splits, row chunks of
+// the BN / SE sums): nz, so that a task-batched launch keeps about the same number of CTAs - and nz times fewer
+// partials per slot - as a single-slot one.  The summation tree then depends on the group size (results stay
+// deterministic for a given group size).  MLIIS_GROUP_CANONICAL=1 (read at every call) returns 1: the single-slot
+// partition for every group size, which makes task-batched launches BIT-IDENTICAL to single-slot ones (tests).
+int partition_nz();
 #define MLIIS_ZS (::mliis::zgroup().zs)
 
 // ---------------- row-channel kernels (k_rowchan.cu) : HBM-bound ----------------

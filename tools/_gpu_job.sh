@@ -1,10 +1,4 @@
-timeout 1800 python -m pytest tests -q -m gpu 2>&1 | tail -3
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | cut -c1-200
-python bench.py > gpurun_out/r02zf_bench.json 2> gpurun_out/r02zf_bench.err; python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r02zf_bench.json').read().strip().splitlines()[-1])
-print('value', d['value'], 'e2e', d['e2e']['value'], 'roofline', d['roofline']['frac'], d['roofline']['kernel_ms'], 'launches', d['gpu_launches'], 'steps', d['steps'], 'ms/step', d['ms_per_step'])
-print('meta', {k:(round(v['meta_steps_per_s'],3), round(v['tasks_per_s'],1)) for k,v in d['meta_train'].items()})
-print('miou', d['miou_vs_oracle']['max_abs_diff'], d['miou_vs_oracle']['mean_abs_diff'], 'cpu', d['cpu_baseline']['value'])
-PY
-tail -2 gpurun_out/r02zf_bench.err
+timeout 1500 python -m pytest tests/test_gpu_group.py tests/test_gpu_kernels.py tests/test_gpu_host.py -q -x -s 2>&1 | grep -v "^$" | tail -8
+ncu --metrics gpu__time_duration.sum,sm__cycles_active.sum,launch__grid_size --clock-control none --csv \
+    --log-file gpurun_out/r02zj_smtime_g16.csv python tools/prof_step.py --gemm-mode tf32x3 --group 16 > gpurun_out/r02zj_prof.log 2>&1
+python tools/sm_time.py gpurun_out/r02zj_smtime_g16.csv > gpurun_out/r02zj_sm_time_g16.md; head -30 gpurun_out/r02zj_sm_time_g16.md
