@@ -50,15 +50,16 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--tasks-per-step", type=int, default=64)
-    ap.add_argument("--slots", type=int, default=32)
-    ap.add_argument("--group", type=int, default=16, help="task slots per task-batched launch (must divide --slots); measured on\n"
-                    "B200: 12 x 1 -> 111, 16 x 4 -> 115, 32 x 8 -> 120, 32 x 16 -> 122 tasks/s")
+    ap.add_argument("--tasks-per-step", type=int, default=96)
+    ap.add_argument("--slots", type=int, default=48)
+    ap.add_argument("--group", type=int, default=24, help="task slots per task-batched launch (must divide --slots); measured on\n"
+                    "B200 (slots x group): 32 x 8 -> 134.7, 32 x 16 -> 140.1, 48 x 16 -> 139.9, 48 x 24 -> 143.2, 64 x 32 -> 143.3 tasks/s")
     ap.add_argument("--gemm-mode", default="auto", choices=["auto", "fp32", "tf32", "tf32x3"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-meta-train", action="store_true")
+    ap.add_argument("--meta-slots", type=int, default=20, help="task slots of the meta-training measurement")
     ap.add_argument("--skip-kernels", action="store_true", help="skip the per-kernel roofline micro-benchmarks")
     ap.add_argument("--cpu-tasks", type=int, default=CPU_TASKS)
     ap.add_argument("--sgd", action="store_true")
@@ -585,7 +586,7 @@ def run_b200(args):
 
     meta = None
     if not args.skip_meta_train and mode == N.GEMM_TF32X3 and not args.sgd:
-        meta = meta_train_bench(eng, world, rank, steps=max(2, min(args.steps, 6)), warmup=2, slots=min(16, args.slots))
+        meta = meta_train_bench(eng, world, rank, steps=max(2, min(args.steps, 6)), warmup=2, slots=min(args.meta_slots, args.slots))
 
     if rank != 0:
         if world > 1:

@@ -76,37 +76,54 @@ void stem_fwd(const float* images, const int32_t* index, const float* w, float* 
 constexpr int kStemWgPix = 512;   // output pixels per CTA
 int stem_wgrad_blocks(int B, int Ho, int Wo) { return cdiv(B * Ho * Wo, kStemWgPix); }
 
-// dW[k = tap*3+ci][co] partial per CTA.  288 threads: co = t%32, kg = t/32 -> k = kg*3 + {0,1,2}.
+// dW[k = tap*3+ci][co] partial per CTA.  288 threads = 3 k-thirds (9 of the 27 k each) x 3 pixel groups x 32 output
+// channels: per staged pixel a thread loads one gradient and its 9 inputs (three 16-byte broadcast loads of a row padded to
+// 12 floats per third) for 9 FMAs.  The first version (thread = 3 k x 1 channel over all 64 pixels: 4 shared loads per 3
+// FMAs) was bound by the shared-memory pipe: 435 us for a 16-slot launch against 40 us of HBM time.
 __global__ void __launch_bounds__(288) stem_wgrad_kernel(const float* __restrict__ images,
                                                           const int32_t* __restrict__ index,
                                                           const float* __restrict__ dy, float* __restrict__ partials,
                                                           int B, int H, int W, int Ho, int Wo, int pad_t, int pad_l,
                                                           long long zs) {
-  __shared__ float xs[64][28];
-  { const size_t zo = (size_t)blockIdx.z * zs; images += zo; index = zp(index, zo); dy += zo; partials += zo; }
+  __shared__ __align__(16) float xs[64][36];
   __shared__ float gs[64][32];
-  const int tid = threadIdx.x, co = tid & 31, kg = tid >> 5;
+  __shared__ float red[3][27][32];
+  __shared__ int4 pix[64];
+  { const size_t zo = (size_t)blockIdx.z * zs; images += zo; index = zp(index, zo); dy += zo; partials += zo; }
+  const int tid = threadIdx.x, co = tid & 31, wv = tid >> 5, kq = wv / 3, pg = wv - kq * 3;
   const int total = B * Ho * Wo;
   const int p_begin = blockIdx.x * kStemWgPix;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+  float acc[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) acc[j] = 0.f;
   for (int base = p_begin; base < min(total, p_begin + kStemWgPix); base += 64) {
-    for (int i = tid; i < 64 * 27; i += 288) {
-      const int lp = i / 27, k = i - lp * 27;
-      const int p = base + lp;
-      float v = 0.f;
+    // pixel coordinates once per pixel (two divisions by run-time values), not once per staged element: the staging
+    // loop below only divides by constants.  The per-element version spent most of the kernel's issue slots there.
+    if (tid < 64) {
+      const int p = base + tid;
+      int4 d = make_int4(-1, 0, 0, 0);
       if (p < total) {
         const int b = p / (Ho * Wo), rem = p - b * (Ho * Wo), oy = rem / Wo, ox = rem - oy * Wo;
+        d = make_int4(index ? index[b] : b, oy * 2 - pad_t, ox * 2 - pad_l, 0);
+      }
+      pix[tid] = d;
+    }
+    __syncthreads();
+    for (int i = tid; i < 64 * 27; i += 288) {
+      const int lp = i / 27, k = i - lp * 27;
+      const int4 d = pix[lp];
+      float v = 0.f;
+      if (d.x >= 0) {
         const int tap = k / 3, ci = k - tap * 3, ky = tap / 3, kx = tap - ky * 3;
-        const int iy = oy * 2 - pad_t + ky, ix = ox * 2 - pad_l + kx;
+        const int iy = d.y + ky, ix = d.z + kx;
         if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-          const int img = index ? index[b] : b;
-          const float raw = images[(((size_t)img * H + iy) * W + ix) * 3 + ci];
+          const float raw = images[(((size_t)d.x * H + iy) * W + ix) * 3 + ci];
           const float mean = ci == 0 ? kMeanR : (ci == 1 ? kMeanG : kMeanB);
           const float sd = ci == 0 ? kStdR : (ci == 1 ? kStdG : kStdB);
           v = (raw - mean) / sd;
         }
       }
-      xs[lp][k] = v;
+      xs[lp][(k / 9) * 12 + k % 9] = v;
     }
     for (int i = tid; i < 64 * 32; i += 288) {
       const int lp = i >> 5, c = i & 31;
@@ -114,19 +131,25 @@ __global__ void __launch_bounds__(288) stem_wgrad_kernel(const float* __restrict
       gs[lp][c] = p < total ? dy[(size_t)p * 32 + c] : 0.f;
     }
     __syncthreads();
-#pragma unroll 8
-    for (int lp = 0; lp < 64; ++lp) {
+#pragma unroll 2
+    for (int lp = pg; lp < 64; lp += 3) {
       const float g = gs[lp][co];
-      acc0 = fmaf(xs[lp][kg * 3 + 0], g, acc0);
-      acc1 = fmaf(xs[lp][kg * 3 + 1], g, acc1);
-      acc2 = fmaf(xs[lp][kg * 3 + 2], g, acc2);
+      const float4 x0 = ld4(&xs[lp][kq * 12]), x1 = ld4(&xs[lp][kq * 12 + 4]);
+      const float x8 = xs[lp][kq * 12 + 8];
+      acc[0] = fmaf(x0.x, g, acc[0]); acc[1] = fmaf(x0.y, g, acc[1]); acc[2] = fmaf(x0.z, g, acc[2]);
+      acc[3] = fmaf(x0.w, g, acc[3]); acc[4] = fmaf(x1.x, g, acc[4]); acc[5] = fmaf(x1.y, g, acc[5]);
+      acc[6] = fmaf(x1.z, g, acc[6]); acc[7] = fmaf(x1.w, g, acc[7]); acc[8] = fmaf(x8, g, acc[8]);
     }
     __syncthreads();
   }
+#pragma unroll
+  for (int j = 0; j < 9; ++j) red[pg][kq * 9 + j][co] = acc[j];
+  __syncthreads();
   float* o = partials + (size_t)blockIdx.x * 864;
-  o[(kg * 3 + 0) * 32 + co] = acc0;
-  o[(kg * 3 + 1) * 32 + co] = acc1;
-  o[(kg * 3 + 2) * 32 + co] = acc2;
+  for (int i = tid; i < 864; i += 288) {
+    const int k = i >> 5, c = i & 31;
+    o[i] = (red[0][k][c] + red[1][k][c]) + red[2][k][c];      // fixed order over the pixel groups
+  }
 }
 
 void stem_wgrad(const float* images, const int32_t* index, const float* dy, float* partials, float* dw, int B, int H,

@@ -169,6 +169,13 @@ __device__ __forceinline__ float4 rn_tf32_4(float4 v) { return f4(rn_tf32(v.x), 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// One arrival per WARP: every lane has fenced its own shared-memory writes (fence.proxy.async) before the call, the warp
+// barrier orders them before lane 0's arrive (release).  The barrier is initialised with the number of warps: 512
+// per-thread arrivals on one barrier word per 600-clk wgrad stage were a serial cost of their own.
+__device__ __forceinline__ void mbar_arrive_warp(uint32_t bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 // swish: x * 1/(1 + 2^(-x*log2 e)) with the MUFU reciprocal + one Newton step; the transform warps are ALU-bound
 __device__ __forceinline__ float swish_fast(float x) { return x * sigmoid_f(x); }      // common.cuh: MUFU rcp + Newton
 __device__ __forceinline__ float4 swish_fast4(float4 v) {
@@ -289,7 +296,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
-      mbar_init(ready_bar(s), kTcXformThreads);
+      mbar_init(ready_bar(s), kTcXformThreads / 32);
     }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -418,7 +425,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       // generic-proxy writes must be visible to the async proxy (tcgen05.mma reads smem through it)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(ready_bar(s));
+      mbar_arrive_warp(ready_bar(s));
     }
     // ---- epilogue: TMEM lane quarter = warp & 3 (hardware rule); the two warps of a quarter split the 32-column
     // chunks (half 0: even chunks, half 1: odd chunks); each half stages through its own 16 KB tile of the ring ----
@@ -554,7 +561,7 @@ tc_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
-    for (int s = 0; s < p.SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_ready(s), kPwXformThreads); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_ready(s), kPwXformThreads / 32); mbar_init(a_empty(s), 1); }
     mbar_init(b_full, 1);
     for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), kPwEpiThreads / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -679,7 +686,7 @@ tc_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (x3) a_lo[t + kPwXformThreads * j] = rn_tf32_4(x - h);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(a_ready(s));
+        mbar_arrive_warp(a_ready(s));
       }
     }
   } else {
@@ -850,7 +857,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
-    for (int s = 0; s < p.SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_ready(s), 128); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_ready(s), 128 / 32); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < p.SB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -967,7 +974,7 @@ tc_conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           lo[i] = rn_tf32_4(v - h);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(a_ready(sa));
+        mbar_arrive_warp(a_ready(sa));
         if (prof) { w_x += t1 - t0; t_x += clock64() - t1; }
       }
     }
@@ -1333,6 +1340,13 @@ static inline cuuint64_t slot_stride_bytes(cuuint64_t natural) {
   return (natural + 15) / 16 * 16;
 }
 
+// Shared-memory budget of the one-CTA-per-SM tensor-core kernels (rings of operand stages).  MLIIS_TC_SMEM_KB < 216 leaves
+// room for CTAs of the HBM-bound kernels of ANOTHER task group on the same SM (experiment knob, read once).
+static int tc_smem_budget() {
+  static int kb = -1;
+  if (kb < 0) { const char* e = getenv("MLIIS_TC_SMEM_KB"); kb = e ? atoi(e) : 216; if (kb < 96 || kb > 216) kb = 216; }
+  return kb * 1024;
+}
 int tc_pick_bn(int N) {
   int tiles = (N + 255) / 256;
   int bn = (N + tiles - 1) / tiles;
@@ -1379,7 +1393,7 @@ static bool tc_conv3(const float* A, int lda, const float* Wt, const float* bias
   if (p.split == 3 && p.BN > 128 && p.MT == 2) {
     const int slot_rows_w = (p.MT - 1) * p.BH * p.RW + 2 * dil + 128;
     const int a_bytes_w = ((slot_rows_w > box_rows ? slot_rows_w : box_rows) * 128 + 1023) / 1024 * 1024;
-    if ((216 * 1024 - 2 * 2 * a_bytes_w) / (2 * p.BN * 128) < 2) p.BN = 128;
+    if ((tc_smem_budget() - 2 * 2 * a_bytes_w) / (2 * p.BN * 128) < 2) p.BN = 128;
   }
   // CTA pairs (cta_group::2, M = 256): 3xTF32 only (the kernel these layers are MMA-issue-bound in), even BN halves
   static int pair_on = -1;
@@ -1397,7 +1411,7 @@ static bool tc_conv3(const float* A, int lda, const float* Wt, const float* bias
   p.a_slot_bytes = (slot_rows * 128 + 1023) / 1024 * 1024;
   p.b_plane_bytes = (pair ? p.BN / 2 : p.BN) * 128;
   const int planes = p.split == 3 ? 2 : 1;
-  const int budget = 216 * 1024;
+  const int budget = tc_smem_budget();
   p.SA = p.split == 3 ? 2 : 3;
   p.SB = (budget - p.SA * planes * p.a_slot_bytes) / (planes * p.b_plane_bytes);
   if (p.SB > 8) p.SB = 8;
@@ -1483,7 +1497,7 @@ static bool tc_pw(const float* A, int lda, const float* Wt, const float* bias, f
   const int a_stage = planes * kABytes;
   const int Kp = (C + 31) / 32 * 32;
   const int tail = 8 * (3 * 6 + 5) + 32 + 8 * Kp + 1024;
-  p.SA = (220 * 1024 - p.b_res_bytes - 4 * 16384 - tail) / a_stage;
+  p.SA = (tc_smem_budget() + 4 * 1024 - p.b_res_bytes - 4 * 16384 - tail) / a_stage;
   if (p.SA > 6) p.SA = 6;
   if (p.SA < 2) return false;
   CUtensorMap tmA, tmB, tmC;
@@ -1675,6 +1689,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint32_t ncols = 32;
   while ((int)ncols < (p.share ? 3 * p.BN : (wide ? 2 * wide_off : p.BN))) ncols <<= 1;
   const int c0 = blockIdx.x * 128, tap = blockIdx.y, split = blockIdx.z - slot * p.splits;
+  // 32-channel groups of the A tile that hold real channels: the others are never loaded or transformed - their shared
+  // memory is zeroed once below and the MMAs read zero rows (C = 16 .. 96 layers used to move three or two all-zero boxes
+  // per stage through TMA and the transform)
+  const int nga = min(4, (p.C - c0 + 31) / 32);
   const int per = (p.tiles_total + p.splits - 1) / p.splits;
   const int t_beg = split * per, t_end = min(p.tiles_total, t_beg + per);
   const int KB = max(t_end - t_beg, 0);
@@ -1686,18 +1704,18 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int s = kb % p.stages;
     mbar_wait(empty_bar(s), ((kb / p.stages) & 1) ^ 1);
     const uint32_t sa = base + (uint32_t)s * stage_bytes, sg = sa + g_off;
-    mbar_expect_tx(full_bar(s), (uint32_t)((p.share ? p.a_tx_bytes : a_bytes) + g_bytes));
+    mbar_expect_tx(full_bar(s), (uint32_t)((p.share ? (p.a_tx_bytes >> 2) : kWgGroupBytes) * nga + g_bytes));
     const int t = t_beg + kb;
     if (p.conv) {
       const int per_img = p.tiles_x * p.tiles_y;
       const int img = t / per_img, rem = t - img * per_img, ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       const int x0 = tx * p.BX, y0 = ty * p.BY;
-      for (int g = 0; g < 4; ++g)
+      for (int g = 0; g < nga; ++g)
         tma_load_5d(sa + g * a_group, &tmA, full_bar(s), c0 + 32 * g, x0 + dx, y0 + dy, img, slot);
       for (int g = 0; g < p.NG; ++g) tma_load_5d(sg + g * kWgGroupBytes, &tmG, full_bar(s), 32 * g, x0, y0, img, slot);
     } else {
       const int m0 = t * 32;
-      for (int g = 0; g < 4; ++g) tma_load_3d(sa + g * kWgGroupBytes, &tmA, full_bar(s), c0 + 32 * g, m0, slot);
+      for (int g = 0; g < nga; ++g) tma_load_3d(sa + g * kWgGroupBytes, &tmA, full_bar(s), c0 + 32 * g, m0, slot);
       for (int g = 0; g < p.NG; ++g) tma_load_3d(sg + g * kWgGroupBytes, &tmG, full_bar(s), 32 * g, m0, slot);
     }
   };
@@ -1705,7 +1723,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(ready_bar(s), kWgXformThreads); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(ready_bar(s), kWgXformThreads / 32); }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // barrier words (generic proxy) -> TMA (async proxy)
@@ -1715,6 +1733,17 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (nga < 4 && threadIdx.x >= 64) {
+    const int z0 = nga * a_group / 16, z1 = a_bytes / 16;          // float4 range of the unused groups in a plane
+    for (int s = 0; s < p.stages; ++s) {
+      float4* st = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
+      for (int i = z0 + (int)threadIdx.x - 64; i < z1; i += kWgXformThreads) {
+        st[i] = f4s(0.f);
+        if (x3) st[a_lo / 16 + i] = f4s(0.f);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zeros -> tensor-core operand reads
   }
   tc_fence_before();
   __syncthreads();
@@ -1791,6 +1820,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       pa4[j] = in ? ld4(p.pa + kch[j]) : f4s(0.f);      // zero coefficients keep the TMA zero fill: swish(0) = 0
       pb4[j] = in ? ld4(p.pb + kch[j]) : f4s(0.f);
     }
+    const int a_valid4 = nga * a_group / 16;           // float4 of a plane that hold loaded data
     for (int kb = 0; kb < KB; ++kb) {
       const int s = kb % p.stages;
       float4 gt[2];
@@ -1807,6 +1837,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
       for (int j = 0; j < 1024 / kWgXformThreads && !(p.debug & 1); ++j) {            // A: 4 groups x 256 float4
         const int i = t + kWgXformThreads * j;
+        if (i >= a_valid4) continue;                 // plain mode: group (t >> 8) + 2 * j holds no real channel
         float4 v = a_hi[i];
         if (p.pa) {
           v = swish_fast4(affine4(v, pa4[j], pb4[j]));
@@ -1817,8 +1848,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (x3) a_lop[i] = rn_tf32_4(v - h);
       }
       if (p.share) {       // halo slab (no prologue in conv mode): 4 groups x a_group bytes, plain hi/lo split
-        const int na4 = a_bytes / 16;
-        for (int i = t + 1024; i < na4 && !(p.debug & 1); i += kWgXformThreads) {
+        for (int i = t + 1024; i < a_valid4 && !(p.debug & 1); i += kWgXformThreads) {
           const float4 v = a_hi[i];
           const float4 h = rn_tf32_4(v);
           a_hi[i] = h;
@@ -1835,7 +1865,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (x3) g_lop[i] = rn_tf32_4(v - h);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(ready_bar(s));
+      mbar_arrive_warp(ready_bar(s));
     }
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
@@ -1895,8 +1925,17 @@ static int wg_splits(int ctiles, int taps, int tiles_total) {
   int base = ctiles * taps * partition_nz();
   int S = target / base;
   if (S < 1) S = 1;
-  if (S > tiles_total / 2) S = tiles_total / 2;   // at least 2 pixel tiles (64 pixels) per CTA
-  if (S > 148) S = 148;
+  const int s_max = tiles_total / 2 < 148 ? tiles_total / 2 : 148;   // at least 2 pixel tiles (64 pixels) per CTA
+  if (target == 148 && base * S != 148) {
+    // one resident CTA per SM: prefer the split count whose CTAs fill whole waves of 148 (16-slot launch of the decoder
+    // wgrad: 96 CTAs of the whole pixel range = 0.65 of one wave, 1607 us; 3 splits = 288 CTAs = 0.97 of two waves)
+    auto eff = [&](int s) { const int n = base * s; return (double)n / (double)(((n + 147) / 148) * 148); };
+    int best = S;
+    for (int c = S + 1; c <= 2 * S + 1 && c <= s_max; ++c)
+      if (eff(c) > eff(best) + 0.1) best = c;
+    S = best;
+  }
+  if (S > s_max) S = s_max;
   if (S < 1) S = 1;
   return S;
 }
@@ -1973,7 +2012,7 @@ bool tc_wgrad(const float* A, int lda, const float* G, int ldg, float* dW, float
   p.splits = wg_splits(ctiles, grid_taps, p.tiles_total);
   const int planes = p.split == 3 ? 2 : 1;
   const int stage_bytes = planes * ((p.share ? 4 * p.a_group_bytes : 4 * kWgGroupBytes) + p.NG * kWgGroupBytes);
-  p.stages = (216 * 1024) / stage_bytes;
+  p.stages = tc_smem_budget() / stage_bytes;
   if (p.stages > 6) p.stages = 6;
   const int per = (p.tiles_total + p.splits - 1) / p.splits;
   if (p.stages > per) p.stages = per;

@@ -298,10 +298,14 @@ class Gecko:
             if self.augmenter is None and eng.gemm_mode != N_GEMM_FP32:
                 # at least two groups in flight: ONE lockstep group is a single serial chain of kernels (measured: FOMAML
                 # meta-batch 5 as one group of five 19.0 meta-steps/s, as five single-slot graphs 20.5)
-                for g in range(min(8, n_max, len(plans) // 2), 1, -1):
+                # (Reptile meta-batch 40: 16 slots as 2 groups of 8 3.29 meta-steps/s, 20 slots as 2 groups of 10 3.47)
+                for g in range(min(12, n_max // 2, len(plans) // 2), 1, -1):
                     if len(plans) % g == 0:
                         group = g
                         break
+                forced = int(os.environ.get("MLIIS_TRAIN_GROUP", "0"))       # experiments: force the group size
+                if forced >= 1 and forced <= n_max and len(plans) % forced == 0:
+                    group = forced
             shape = shape + (group,)
             if self._train_slots is None or self._train_slots.shape != shape:
                 try:
