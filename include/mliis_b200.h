@@ -215,7 +215,9 @@ typedef struct mliis_task_args {
    * 14x14 / 28x28 layers of n_group tasks fill the SMs together.  0 or 1 = a single slot.  All per-slot memory must
    * share one layout at a uniform stride: the state and workspace buffers bound to slot k (mliis_slot_bind) and
    * every dev_* pointer of this struct except dev_init_state are the FIRST slot's; slot k uses
-   * pointer + k * group_stride_bytes (a multiple of 256).  Results are bit-identical to n_group single-slot calls. */
+   * pointer + k * group_stride_bytes (a multiple of 256).  Results equal n_group single-slot calls to fp32 rounding
+   * (the reduction partials are sized by the launch: deterministic for a given n_group); with MLIIS_GROUP_CANONICAL=1 in
+   * the environment the single-slot partition is kept and the results are bit-identical. */
   int32_t        n_group;
   int64_t        group_stride_bytes;
 } mliis_task_args;

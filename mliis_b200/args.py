@@ -54,8 +54,8 @@ _FLAGS = [
     # ---- additions of this implementation (absent from the reference) ----
     ("--gemm_mode", _S, "tf32x3", {"help": "numeric mode of the dense contractions: tf32x3 (tcgen05, fp32-class accuracy; "
                                           "default) | tf32 | fp32 (FFMA reference mode)"}),
-    ("--task_slots", _I, 16, {"help": "concurrent task slots per GPU on the device fast path (launched in task-batched "
-                                       "groups of up to 8)"}),
+    ("--task_slots", _I, 32, {"help": "concurrent task slots per GPU on the device fast path (launched as two or more "
+                                       "task-batched groups: 32 -> 2 x 16; 0.56 GB of workspace per slot at 224x224)"}),
     ("--meta_task_slots", _I, 1, {"help": "meta-training: task slots adapting the tasks of a meta-batch concurrently "
                                           "(1 = the reference's sequential order; S > 1 = per-slot optimizer state, "
                                           "like S ranks)"}),
@@ -109,7 +109,7 @@ def model_kwargs(pa) -> dict:
     kw["start_num_feature_maps_power"] = pa.start_num_feature_maps_power
     kw["n_rows"] = kw["n_cols"] = pa.image_size
     kw["gemm_mode"] = getattr(pa, "gemm_mode", "tf32x3")
-    kw["task_slots"] = getattr(pa, "task_slots", 16)
+    kw["task_slots"] = getattr(pa, "task_slots", 32)
     return kw
 
 

@@ -1633,6 +1633,7 @@ struct TcWgParams {
   // share: conv mode, one CTA makes the 3 horizontal taps of a filter row from ONE halo'd A box {32 ch, BX+2*dil, BY}
   // (tap dx = the same slab read through a descriptor start shifted by dx*dil pixel rows); grid.y = 3 filter rows
   int share, a_group_bytes, a_tx_bytes;
+  int nga_alloc;               // 32-channel groups of A that a stage holds (4, or ceil(C/32) when C < 128)
   int debug;                   // MLIIS_TC_DEBUG bits (bottleneck experiments only): 1 skip transform, 2 skip MMA
   const float* pa; const float* pb; const float* gate;   // A prologue (plain mode), as in tc_conv_kernel
   int HW;
@@ -1667,7 +1668,11 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* smem = smem_raw + (base - raw);
   const bool x3 = p.split == 3;
   const int a_group = p.share ? p.a_group_bytes : kWgGroupBytes;
-  const int a_bytes = 4 * a_group, g_bytes = p.NG * kWgGroupBytes;
+  // a stage holds only the channel groups that exist (C = 16..96: 1-3 of 4).  The M = 128 MMAs still read four groups
+  // (LBO apart): the rows past nga_alloc alias the following planes, give garbage accumulator rows c >= C and are never
+  // stored.  Smaller stages = more loads in flight per SM (these layers are bound by the load round trip, not by the
+  // MMAs or the transform: skip experiments of profiles/r02zn) and two CTAs per SM.
+  const int a_bytes = p.nga_alloc * a_group, g_bytes = p.NG * kWgGroupBytes;
   const int a_lo = a_bytes;                                  // offset of the A lo plane (x3)
   const int g_off = x3 ? 2 * a_bytes : a_bytes;
   const int g_lo = g_off + g_bytes;
@@ -1734,7 +1739,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (nga < 4 && threadIdx.x >= 64) {
+  if (nga < p.nga_alloc && threadIdx.x >= 64) {
     const int z0 = nga * a_group / 16, z1 = a_bytes / 16;          // float4 range of the unused groups in a plane
     for (int s = 0; s < p.stages; ++s) {
       float4* st = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
@@ -1913,7 +1918,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-static int wg_splits(int ctiles, int taps, int tiles_total) {
+static int wg_splits(int ctiles, int taps, int tiles_total, int ctas_per_sm = 1) {
   // CTAs per launch the pixel range is split for.  One CTA per SM: every split writes a full [taps*C, N] fp32 partial
   // that reduce_partials reads back, so 296 (two waves at one resident CTA per SM) doubled that traffic for nothing -
   // measured on the whole job: 296 -> 104.5, 222 -> 107.2, 148 -> 109.2 tasks/s (MLIIS_WG_TARGET overrides).
@@ -1922,14 +1927,15 @@ static int wg_splits(int ctiles, int taps, int tiles_total) {
   // 19 -> 134.5, 10 -> 135.5.  The summation tree of dW therefore depends on the group size (partition_nz()).
   static int target = -1;
   if (target < 0) { const char* e = getenv("MLIIS_WG_TARGET"); target = e ? atoi(e) : 148; }
+  const int wave = 148 * ctas_per_sm;
   int base = ctiles * taps * partition_nz();
-  int S = target / base;
+  int S = (target == 148 ? wave : target) / base;
   if (S < 1) S = 1;
   const int s_max = tiles_total / 2 < 148 ? tiles_total / 2 : 148;   // at least 2 pixel tiles (64 pixels) per CTA
-  if (target == 148 && base * S != 148) {
+  if (target == 148 && base * S != wave) {
     // one resident CTA per SM: prefer the split count whose CTAs fill whole waves of 148 (16-slot launch of the decoder
     // wgrad: 96 CTAs of the whole pixel range = 0.65 of one wave, 1607 us; 3 splits = 288 CTAs = 0.97 of two waves)
-    auto eff = [&](int s) { const int n = base * s; return (double)n / (double)(((n + 147) / 148) * 148); };
+    auto eff = [&](int s) { const int n = base * s; return (double)n / (double)(((n + wave - 1) / wave) * wave); };
     int best = S;
     for (int c = S + 1; c <= 2 * S + 1 && c <= s_max; ++c)
       if (eff(c) > eff(best) + 0.1) best = c;
@@ -1949,8 +1955,9 @@ size_t tc_wgrad_scratch(int conv, int M, int B, int H, int W, int C, int N, int 
   int tiles;
   if (conv) { int BX = W > 16 ? 32 : 16, BY = 32 / BX; tiles = B * ((W + BX - 1) / BX) * ((H + BY - 1) / BY); }
   else tiles = (M + 31) / 32;
-  int S = wg_splits((C + 127) / 128, taps == 9 ? 3 : taps, tiles);   // 3x3: the tap-shared grid has 3 filter rows
-  return (size_t)S * taps * C * N;
+  const int gt = taps == 9 ? 3 : taps;                                // 3x3: the tap-shared grid has 3 filter rows
+  const int S1 = wg_splits((C + 127) / 128, gt, tiles, 1), S2 = wg_splits((C + 127) / 128, gt, tiles, 2);
+  return (size_t)(S1 > S2 ? S1 : S2) * taps * C * N;                  // small-channel layers run two CTAs per SM
 }
 
 // dW[taps*C, N] = sum A^T G ; scratch holds the per-split partials (tc_wgrad_scratch floats)
@@ -2009,18 +2016,29 @@ bool tc_wgrad(const float* A, int lda, const float* G, int ldg, float* dW, float
   }
   const int ctiles = (C + 127) / 128;
   const int grid_taps = p.share ? 3 : taps;
-  p.splits = wg_splits(ctiles, grid_taps, p.tiles_total);
   const int planes = p.split == 3 ? 2 : 1;
-  const int stage_bytes = planes * ((p.share ? 4 * p.a_group_bytes : 4 * kWgGroupBytes) + p.NG * kWgGroupBytes);
-  p.stages = tc_smem_budget() / stage_bytes;
-  if (p.stages > 6) p.stages = 6;
+  p.nga_alloc = (!p.share && ctiles == 1) ? ((C + 31) / 32 < 4 ? (C + 31) / 32 : 4) : 4;
+  const int stage_bytes = planes * ((p.share ? 4 * p.a_group_bytes : p.nga_alloc * kWgGroupBytes) + p.NG * kWgGroupBytes);
+  // compact stages: the MMAs of the last stage read up to 16 KB + one plane past its start (garbage rows, see the kernel)
+  int pad = 0;
+  if (p.nga_alloc < 4) {
+    const int reach = (planes == 2 ? p.nga_alloc * kWgGroupBytes : 0) + 4 * kWgGroupBytes;   // of the lo (hi) plane's MMA
+    pad = reach > stage_bytes ? reach - stage_bytes + 1024 : 0;
+  }
+  // two CTAs per SM when three stages of each fit: two independent load -> transform -> MMA chains hide each other's
+  // round trips (C = 32, N = 16 at 112x112, 16 slots: 374 -> 292 us)
+  const int ctas_per_sm = (!p.share && 3 * stage_bytes + pad + 2048 <= 112 * 1024) ? 2 : 1;
+  p.splits = wg_splits(ctiles, grid_taps, p.tiles_total, ctas_per_sm);
+  p.stages = ((ctas_per_sm == 2 ? 110 * 1024 : tc_smem_budget()) - pad) / stage_bytes;
+  if (p.stages > 8) p.stages = 8;
   const int per = (p.tiles_total + p.splits - 1) / p.splits;
   if (p.stages > per) p.stages = per;
   if (p.stages < 1) return false;
-  const size_t smem = (size_t)p.stages * stage_bytes + (3 * p.stages + 2) * 8 + 1024;
+  const size_t smem = (size_t)p.stages * stage_bytes + (3 * p.stages + 2) * 8 + 1024 + pad;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr = true;
   }
   dim3 grid(ctiles, grid_taps, p.splits * MLIIS_NZ);

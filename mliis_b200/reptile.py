@@ -131,12 +131,13 @@ class Gecko:
         if self._runner is None or self._runner[0] != key:
             eng = self._model.engine()
             # task-batched launches (several slots per kernel launch) when at least two groups stay in flight; measured
-            # on B200: 12 slots x 1 -> 111, 16 x 4 -> 115, 32 x 8 -> 120 tasks/s.  Bit-identical results.  Augmented
+            # on B200: 12 slots x 1 -> 111, 16 x 4 -> 115, 32 x 8 -> 120 tasks/s.  Same results to fp32 rounding.  Augmented
             # pools live outside the uniform-stride arena, which single-slot launches only can address.
             group = 1
             if self.augmenter is None and eng.gemm_mode != N_GEMM_FP32:
-                for g in (8, 4, 2):
-                    if eng.n_slots % g == 0 and eng.n_slots // g >= 2:
+                # (with the partials sized per launch: 32 x 8 -> 134.7, 32 x 16 -> 140.1, 48 x 24 -> 143.2 tasks/s)
+                for g in range(min(32, eng.n_slots // 2), 1, -1):
+                    if eng.n_slots % g == 0:
                         group = g
                         break
             self._runner = (key, TaskRunner(eng, n_pool, n_steps, batch, n_query, use_graph=True,

@@ -108,7 +108,8 @@ class TaskRunner:
                  use_graph: bool = True, with_dc_masks: bool = False, pre_decay_rate: float = 1.0, group: int = 1):
         """group: slots per task-batched launch (mliis_task_args.n_group).  group = 1: every slot replays its own
         one-task graph (round-1 behaviour).  group = G > 1: G consecutive slots run in lockstep - each kernel is
-        launched once for G tasks - and n_slots / G groups are in flight concurrently.  Results are bit-identical."""
+        launched once for G tasks - and n_slots / G groups are in flight concurrently.  Results equal single-slot runs to fp32 rounding
+        (bit-identical with MLIIS_GROUP_CANONICAL=1: csrc/kernels.h partition_nz)."""
         if batch > eng.max_batch or n_query > eng.max_batch:
             raise ValueError("batch / n_query exceed the engine's max_batch")
         if group < 1 or eng.n_slots % group:
@@ -331,7 +332,7 @@ class TrainSlots:
     def __init__(self, eng: Engine, n: int, shape, group: int = 1):
         """group = G > 1: G consecutive slots adapt their tasks in LOCKSTEP - one graph per group whose inner steps are
         task-batched launches (mliis_kernel_group + mliis_train_step: every kernel serves G tasks).  The per-slot inputs
-        then live in the slots' staging regions of the engine arena (uniform stride).  Bit-identical to group = 1."""
+        then live in the slots' staging regions of the engine arena (uniform stride).  Equal to group = 1 to fp32 rounding."""
         n_pool, batch_sizes, lrs, fomaml, pre_decay = shape
         if group < 1 or n % group:
             raise ValueError("group (%d) must divide the number of training slots (%d)" % (group, n))

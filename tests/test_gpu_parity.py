@@ -365,7 +365,10 @@ def test_tc_conv3x3(H, Cin, Cout, dil, B):
 
 @pytest.mark.parametrize("H,Cin,Cout,taps,dil,B", [(56, 136, 112, 9, 2, 2), (56, 360, 112, 9, 1, 1), (14, 224, 112, 9, 2, 3),
                                                    (14, 448, 112, 9, 1, 2), (56, 136, 112, 1, 1, 2), (28, 240, 40, 1, 1, 2),
-                                                   (112, 96, 16, 1, 1, 1), (14, 672, 112, 1, 1, 8), (20, 40, 16, 9, 1, 2)])
+                                                   (112, 96, 16, 1, 1, 1), (14, 672, 112, 1, 1, 8), (20, 40, 16, 9, 1, 2),
+                                                   # compact stages: 1-3 channel groups of A, two CTAs per SM
+                                                   (56, 16, 96, 1, 1, 2), (56, 32, 16, 1, 1, 2), (28, 72, 24, 1, 1, 3),
+                                                   (28, 40, 240, 1, 1, 2)])
 def test_tc_wgrad(H, Cin, Cout, taps, dil, B):
     from mliis_b200 import native as N
     g = torch.Generator().manual_seed(H + Cin + Cout + taps)
