@@ -607,10 +607,11 @@ def run_b200(args):
                                          "task-batched launch over %d slots as the bench's graphs issue it" % n_grp,
             "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
             "slots_per_launch": n_grp,
-            # dram__bytes_read.sum + dram__bytes_write.sum per slot from the `ncu --set full` capture of the single-slot
-            # call (profiles/r02p_prof_tc_conv3.raw.csv.gz: tc_conv3_kernel 24.36 MB read + pool_taps_kernel 0.56 MB;
-            # the 11.2 MB output is still in L2 when the kernel ends); algorithmic: 22.5 MB in + 1.8 MB weights + 11.2 MB out
-            "traffic": 24.92e6 * n_grp, "traffic_unit": "bytes per launch (single-slot capture x slots)",
+            # dram__bytes_read.sum + dram__bytes_write.sum of the `ncu --set full` capture of this very call at 24 slots per
+            # launch (profiles/r02zr_prof_conv3_24slots.raw.csv.gz: tc_conv3_kernel 585.5 MB read + 245.3 MB written,
+            # pool_taps_kernel 13.3 MB read = 35.17 MB per slot); algorithmic: 22.5 MB in + 1.8 MB weights + 11.2 MB out
+            # = 35.5 MB per slot - nothing is read twice
+            "traffic": 35.17e6 * n_grp, "traffic_unit": "bytes per launch (24-slot ncu capture, per slot x slots)",
             "peak_source": "%s bf16 cuBLAS burst (kernel timed alone)" % peak_src,
             "kernel_ms": k_ms, "algorithmic_gflop": k_flops / 1e9,
             "frac_of_measured_tf32_peak": (achieved / tpk["tf32_tcgen05_cta_group1_tflops"]) if tpk else None,

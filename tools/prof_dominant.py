@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """The dominant decoder convolution as the engine runs it (pool_taps + tc_conv3_kernel over the 224 real channels), a
-few launches - the target of `ncu --set full -k regex:'tc_conv3|pool_taps'`."""
+few launches - the target of `ncu --set full -k regex:'tc_conv3|pool_taps'`.  usage: prof_dominant.py [slots per launch = 24]"""
 import os
 import sys
 
@@ -12,6 +12,7 @@ from mliis_b200 import native as N
 
 bench._time_launch.__defaults__ = (2, 1)
 flush = bench._Flusher()
-ms, fl = bench.time_dominant_kernel(N.GEMM_TF32X3, flush)
-print("dominant conv: %.1f us  %.1f TFLOP/s" % (ms * 1e3, fl / ms / 1e9))
+G = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+ms, fl = bench.time_dominant_kernel(N.GEMM_TF32X3, flush, G)
+print("dominant conv x%d slots: %.1f us  %.1f TFLOP/s" % (G, ms * 1e3, fl / ms / 1e9))
 torch.cuda.synchronize()
