@@ -61,6 +61,9 @@ def parse():
     ap.add_argument("--skip-meta-train", action="store_true")
     ap.add_argument("--meta-slots", type=int, default=20, help="task slots of the meta-training measurement")
     ap.add_argument("--skip-kernels", action="store_true", help="skip the per-kernel roofline micro-benchmarks")
+    ap.add_argument("--profile-region", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed region of the device-resident run: `ncu --profile-from-start "
+                         "off ...` then lists the launches of the timed steps only (not the checkpoint synthesis / capture)")
     ap.add_argument("--cpu-tasks", type=int, default=CPU_TASKS)
     ap.add_argument("--sgd", action="store_true")
     ap.add_argument("--shots", type=int, default=5, choices=[1, 5],
@@ -571,6 +574,12 @@ def run_b200(args):
     time.sleep(0.3)
     ms, res, launches = timed(dev_plans, args.steps, max(3, args.warmup))
     sampler.stop()
+    if args.profile_region:            # one more step under the profiler (its numbers are not the bench's)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        runner.run(dev_plans)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     value = world * tps * args.steps / (ms / 1e3)
     mious = [iou_from_counts(i, u) for (i, u) in res]
 

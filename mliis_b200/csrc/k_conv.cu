@@ -302,11 +302,38 @@ struct DwBd2 {
   static constexpr size_t smem_bytes() { return (size_t)(TD * TD + K * K) * QC * sizeof(float4); }
 };
 
+// One strip = the 7 outputs of one dx row that share the parity of (ix + pad_l): for them the contributing taps are the
+// compile-time sets ky = RP, RP+2, .. and kx = XP, XP+2, .., consecutive outputs read consecutive dy columns, and the
+// inner loops carry no parity tests.  (The first version walked 7 consecutive outputs per thread and tested the parity
+// of every (tap, output) pair at run time: 63 predicated index computations per thread, 26 % of the DRAM peak.)
+template <int K, int RP, int XP>
+__device__ __forceinline__ void dwbd2_strip(const float4* __restrict__ tile, const float4* __restrict__ wsm, int q, int ly0,
+                                            int lx0, float4 (&acc)[7]) {
+  constexpr int TD = DwBd2<K>::TD;
+  constexpr int NM = (K - RP + 1) / 2, NN = (K - XP + 1) / 2;      // taps of this parity class per column / per row
+#pragma unroll
+  for (int m = 0; m < NM; ++m) {
+    const float4* row = tile + ((size_t)(ly0 - m) * TD + (lx0 - (NN - 1))) * QC + q;
+    float4 wv[NN];
+#pragma unroll
+    for (int n = 0; n < NN; ++n) wv[n] = wsm[((RP + 2 * m) * K + XP + 2 * n) * QC + q];
+#pragma unroll
+    for (int i = 0; i < 7 + NN - 1; ++i) {       // dy column lx0 - (NN-1) + i feeds output j through tap n = j - i + NN - 1
+      const float4 v = row[i * QC];
+#pragma unroll
+      for (int n = 0; n < NN; ++n) {
+        const int j = i + n - (NN - 1);
+        if (j >= 0 && j < 7) fma4(acc[j], v, wv[n]);
+      }
+    }
+  }
+}
+
 template <int K>
-__global__ void __launch_bounds__(224) dw_bwd_data_s2_kernel(const float* __restrict__ dy, const float* __restrict__ w,
-                                                              float* __restrict__ dx, int H, int W, int C, int Ho,
-                                                              int Wo, int pad_t, int pad_l, int tiles_x, int nB,
-                                                              long long zs) {
+__global__ void __launch_bounds__(224, 4) dw_bwd_data_s2_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                                 float* __restrict__ dx, int H, int W, int C, int Ho,
+                                                                 int Wo, int pad_t, int pad_l, int tiles_x, int nB,
+                                                                 long long zs) {
   using G = DwBd2<K>;
   extern __shared__ float4 smem4[];
   float4* tile = smem4;
@@ -323,41 +350,40 @@ __global__ void __launch_bounds__(224) dw_bwd_data_s2_kernel(const float* __rest
   }
   // first dy row/col that any dx of this tile can touch (floor division, may be negative)
   const int oy_lo = (ty0 + pad_t - (K - 1)) >> 1, ox_lo = (tx0 + pad_l - (K - 1)) >> 1;
-  for (int i = tid; i < G::TD * G::TD * QC; i += G::NT) {
-    const int pix = i / QC, ly = pix / G::TD, lx = pix - ly * G::TD;
-    const int gy = oy_lo + ly, gx = ox_lo + lx;
-    float4 v = f4s(0.f);
-    if (cvalid && gy >= 0 && gy < Ho && gx >= 0 && gx < Wo)
-      v = ld4(dy + (((size_t)img * Ho + gy) * Wo + gx) * C + c0 + q * 4);
-    tile[i] = v;
+  {
+    constexpr int TOT = G::TD * G::TD * QC, U = (TOT + G::NT - 1) / G::NT;     // 4: every load in flight before the stores
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = tid + u * G::NT;
+      const int pix = i / QC, ly = pix / G::TD, lx = pix - ly * G::TD;
+      const int gy = oy_lo + ly, gx = ox_lo + lx;
+      v[u] = f4s(0.f);
+      if (i < TOT && cvalid && gy >= 0 && gy < Ho && gx >= 0 && gx < Wo)
+        v[u] = ld4(dy + (((size_t)img * Ho + gy) * Wo + gx) * C + c0 + q * 4);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (tid + u * G::NT < TOT) tile[tid + u * G::NT] = v[u];
   }
   __syncthreads();
-  const int iy = ty0 + strip / 2, ix0 = tx0 + (strip & 1) * 7;
+  // 28 strips = 4 parity classes x 7 rows (the tile origin is even: the class of a local row / column is fixed).
+  // strips of a class are consecutive, so five of the seven warps run one class and two run two.
+  const int cls = strip / 7, k = strip - cls * 7, rp = cls >> 1, xp = cls & 1;
+  const int ry = 2 * k + (rp ^ (pad_t & 1)), rx0 = xp ^ (pad_l & 1);       // local row, first local column of the strip
+  const int iy = ty0 + ry, ix0 = tx0 + rx0;
+  const int ly0 = ((iy + pad_t - rp) >> 1) - oy_lo, lx0 = ((ix0 + pad_l - xp) >> 1) - ox_lo;
   float4 acc[7];
 #pragma unroll
   for (int j = 0; j < 7; ++j) acc[j] = f4s(0.f);
-#pragma unroll
-  for (int ky = 0; ky < K; ++ky) {
-    const int t = iy + pad_t - ky;
-    if (t & 1) continue;
-    const int ly = (t >> 1) - oy_lo;
-#pragma unroll
-    for (int kx = 0; kx < K; ++kx) {
-      const float4 wv = wsm[(ky * K + kx) * QC + q];
-#pragma unroll
-      for (int j = 0; j < 7; ++j) {
-        const int u = ix0 + j + pad_l - kx;
-        if ((u & 1) == 0) {
-          const int lx = (u >> 1) - ox_lo;
-          fma4(acc[j], tile[((size_t)ly * G::TD + lx) * QC + q], wv);
-        }
-      }
-    }
-  }
+  if (cls == 0) dwbd2_strip<K, 0, 0>(tile, wsm, q, ly0, lx0, acc);
+  else if (cls == 1) dwbd2_strip<K, 0, 1>(tile, wsm, q, ly0, lx0, acc);
+  else if (cls == 2) dwbd2_strip<K, 1, 0>(tile, wsm, q, ly0, lx0, acc);
+  else dwbd2_strip<K, 1, 1>(tile, wsm, q, ly0, lx0, acc);
   if (iy < H && cvalid) {
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
-      const int gx = ix0 + j;
+      const int gx = ix0 + 2 * j;
       if (gx < W) st4(dx + (((size_t)img * H + iy) * W + gx) * C + c0 + q * 4, acc[j]);
     }
   }
