@@ -635,7 +635,7 @@ def run_b200(args):
         hbm = hbm_rooflines(max(args.group, 6), peaks["hbm_gbs"], flush)
     del flush
     cpu, parity = None, None
-    if not args.skip_cpu_baseline:
+    if not args.skip_cpu_baseline and world == 1:       # the CPU arm is timed at N = 1 only (rank 0 would hold the job up)
         threads = os.cpu_count() or 1
         from oracle.meta_oracle import state_from_flat
         eng.states[0].copy_(init_state)
