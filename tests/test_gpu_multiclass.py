@@ -200,7 +200,9 @@ def test_joint_trainer_end_to_end(tmp_path):
         trainer.__init__(model)
         fixed = batcher.next_batch()
         losses = [trainer.train_step(*fixed, lr=5e-3, seed=s) for s in range(8)]
-        assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+        # every step draws a fresh final-layer dropout mask (rate 0.2), so the trajectory is noisy: the steps must reach
+        # a clearly lower loss, not end on one (the last loss depends on rounding-level details of the kernels)
+        assert all(np.isfinite(losses)) and min(losses[1:]) < 0.8 * losses[0]
         ious = jt.train(sess, model, batcher, epochs=3, steps_per_epoch=2, save_dir=save_dir,
                         lr_fn=lambda i: jt.linear_lr(i, 3, 5e-3, 5e-7), val_batches=2, eval_interval=2)
         assert len(ious) == 2 and all(0.0 <= v <= 1.0 for v in ious)
