@@ -21,3 +21,4 @@ def test_two_rank_nccl_meta_test_and_meta_step():
     for rank in (0, 1):
         assert "[rank %d] sharded meta-test == single-rank meta-test" % rank in r.stdout
         assert "[rank %d] sharded FOMAML step + NCCL all-reduce == single-rank step" % rank in r.stdout
+        assert "[rank %d] slot-parallel meta-steps with idle ranks" % rank in r.stdout

@@ -83,5 +83,28 @@ t = res[0].clone()
 dist.broadcast(t, 0)
 assert torch.equal(t, res[0])
 print("[rank %d] sharded FOMAML step + NCCL all-reduce == single-rank step (rel L2 %.1e); theta identical across ranks" % (rank, rel))
+
+# ---- 3. slot-parallel meta-steps where some ranks own NO task of the meta-batch (8 GPUs on FOMAML's meta-batch of 5) ----
+# meta-batch 1 on >= 2 ranks: rank 0 adapts the task on its training slots, every other rank contributes zeros to the ONE
+# all-reduce and applies the same update; then a meta-batch of world + 1 (rank 0: two tasks, the others one each).
+m = model("adam")
+sess = Session(m)
+random.seed(11)
+learner = Gecko(sess, meta_task_slots=3)
+for mb in (1, world + 1, 1):
+    learner.train_step(tasks, m.input_ph, m.label_ph, m.minimize_op, num_classes=1, num_shots=5, inner_batch_size=4,
+                       inner_iters=2, replacement=False, meta_step_size=0.5, meta_batch_size=mb, lr_ph=m.lr_ph, lr=None)
+eng = m.engine()
+torch.cuda.synchronize()
+th = eng.tf_order_vector(eng.theta(0)).clone()
+assert torch.isfinite(th).all()
+t = th.clone()
+dist.broadcast(t, 0)
+assert torch.equal(t, th), "theta diverged between ranks after meta-steps with idle ranks"
+bn = eng.bn_state(0).clone()
+t = bn.clone()
+dist.broadcast(t, 0)
+assert torch.equal(t, bn), "BN statistics diverged between ranks"
+print("[rank %d] slot-parallel meta-steps with idle ranks: theta and BN statistics identical across ranks" % rank)
 dist.barrier()
 dist.destroy_process_group()
