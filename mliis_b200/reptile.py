@@ -307,12 +307,22 @@ class Gecko:
                 forced = int(os.environ.get("MLIIS_TRAIN_GROUP", "0"))       # experiments: force the group size
                 if forced >= 1 and forced <= n_max and len(plans) % forced == 0:
                     group = forced
-            shape = shape + (group,)
+            # no uniform group divides the rank's task count (FOMAML's meta-batch of 5; Reptile's 40 on 8 GPUs): two
+            # lockstep groups of ceil / floor(n / 2) slots - kernels that serve 2-3 tasks, two chains that fill each
+            # other's tails - instead of n single-slot graphs (MLIIS_TRAIN_SPLIT=0 keeps the single-slot graphs)
+            sizes = None
+            if (group == 1 and self.augmenter is None and eng.gemm_mode != N_GEMM_FP32 and 4 <= len(plans) <= n_max
+                    and os.environ.get("MLIIS_TRAIN_SPLIT", "1") != "0"):
+                sizes = ((len(plans) + 1) // 2, len(plans) // 2)
+            shape = shape + (group, sizes)
             if self._train_slots is None or self._train_slots.shape != shape:
                 try:
-                    self._train_slots = TrainSlots(eng, (n_max // group) * group, shape[:-1], group=group)
+                    if sizes is not None:
+                        self._train_slots = TrainSlots(eng, len(plans), shape[:-2], group_sizes=sizes)
+                    else:
+                        self._train_slots = TrainSlots(eng, (n_max // group) * group, shape[:-2], group=group)
                 except ValueError:               # the pool does not fit the arena's staging region: single-slot launches
-                    self._train_slots = TrainSlots(eng, n_max, shape[:-1], group=1)
+                    self._train_slots = TrainSlots(eng, n_max, shape[:-2], group=1)
                 self._train_slots.shape = shape
             ts = self._train_slots
             ts.begin(eng.theta(0))

@@ -329,14 +329,29 @@ class TrainSlots:
     dsum_s += theta_s - theta_ref (theta_ref = theta_old for Reptile, the weights before the last step for FOMAML).
     Inputs live in per-slot staging buffers so that the graph can be replayed for every task."""
 
-    def __init__(self, eng: Engine, n: int, shape, group: int = 1):
+    def __init__(self, eng: Engine, n: int, shape, group: int = 1, group_sizes=None):
         """group = G > 1: G consecutive slots adapt their tasks in LOCKSTEP - one graph per group whose inner steps are
         task-batched launches (mliis_kernel_group + mliis_train_step: every kernel serves G tasks).  The per-slot inputs
-        then live in the slots' staging regions of the engine arena (uniform stride).  Equal to group = 1 to fp32 rounding."""
+        then live in the slots' staging regions of the engine arena (uniform stride).  Equal to group = 1 to fp32 rounding.
+        group_sizes = [G0, G1, ..] (sum == n): groups of DIFFERENT sizes on consecutive slots, for task counts that no
+        uniform group divides (a meta-batch of 5 as 3 + 2); run_tasks() then takes exactly one task per slot."""
         n_pool, batch_sizes, lrs, fomaml, pre_decay = shape
-        if group < 1 or n % group:
+        if group_sizes is not None:
+            group_sizes = [int(g) for g in group_sizes]
+            if min(group_sizes) < 1 or sum(group_sizes) != n:
+                raise ValueError("group_sizes %r must be positive and sum to the number of training slots (%d)" % (group_sizes, n))
+            group = max(group_sizes)
+        elif group < 1 or n % group:
             raise ValueError("group (%d) must divide the number of training slots (%d)" % (group, n))
+        else:
+            group_sizes = [group] * (n // group)
         self.eng, self.n, self.shape, self.fomaml, self.group = eng, n, shape, fomaml, group
+        self.uniform = len(set(group_sizes)) == 1
+        self.units, s0 = [], 0                     # (first slot, slots in lockstep) of every group
+        for g in group_sizes:
+            self.units.append((s0, g))
+            s0 += g
+        self._unit_size = {u[0]: u[1] for u in self.units}
         S, dev = eng.image_size, eng.device
         self.old = torch.empty(eng.n_theta, dtype=torch.float32, device=dev)
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(n)]
@@ -384,8 +399,8 @@ class TrainSlots:
         self._lrs, self._pre_decay = lrs, pre_decay
 
     def _body(self, s: int) -> None:
-        """One task on each of the slots s .. s + group - 1 (s is the first slot of its group)."""
-        eng, G = self.eng, self.group
+        """One task on each of the slots s .. s + G - 1 (s is the first slot of its group of G)."""
+        eng, G = self.eng, self._unit_size[s]
         thetas = [eng.theta(s + k) for k in range(G)]
         for th in thetas:
             th.copy_(self.old)
@@ -432,7 +447,7 @@ class TrainSlots:
                     t_.zero_()
                 self.seed[s].zero_()
             torch.cuda.synchronize()
-            for s in range(0, self.n, self.group):
+            for s, _ in self.units:
                 self._capture(s)
             torch.cuda.synchronize()
             for s in range(self.n):
@@ -485,6 +500,20 @@ class TrainSlots:
         """plans: [(images, labels, batches)] of this rank's tasks of one meta-batch, dealt in chunks of `group` tasks
         round-robin to the groups of slots.  Host staging runs one round AHEAD of the launches (round r uses pinned
         set r & 1 of every slot)."""
+        if not self.uniform:             # groups of different sizes: one round, one task per slot
+            if len(plans) != self.n:
+                raise ValueError("%d tasks for %d slots in groups of %r" % (len(plans), self.n, [u[1] for u in self.units]))
+            futs = []
+            for s0, g in self.units:
+                fl = []
+                for k in range(g):
+                    images, labels, batches = plans[s0 + k]
+                    self._submitted += 1
+                    fl.append(self._pool.submit(self._fill, s0 + k, 0, images, labels, batches, 1000003 * self._submitted))
+                futs.append(fl)
+            for (s0, g), fl in zip(self.units, futs):
+                self._launch(s0, 0, [f.result() for f in fl], len(plans[s0][2]))
+            return
         G = self.group
         if len(plans) % G:
             raise ValueError("%d tasks do not fill groups of %d slots" % (len(plans), G))

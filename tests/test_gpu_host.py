@@ -301,7 +301,8 @@ def test_tfrecord_tasks_equal_synthetic_tasks_on_the_device_fast_path(tmp_path):
     assert list(out[0][1].values()) == list(out[1][1].values())
 
 
-@pytest.mark.parametrize("foml,gemm,nslots", [(False, "fp32", 3), (True, "fp32", 3), (False, "tf32x3", 4), (True, "tf32x3", 4)])
+@pytest.mark.parametrize("foml,gemm,nslots", [(False, "fp32", 3), (True, "fp32", 3), (False, "tf32x3", 4), (True, "tf32x3", 4),
+                                              (True, "tf32x3", 5)])     # 5: two lockstep groups of 3 + 2 slots
 def test_slot_parallel_meta_step_equals_sequential_under_sgd(foml, gemm, nslots):
     """meta_task_slots > 1: tasks of a meta-batch adapt concurrently on task slots (one CUDA graph per slot).  With
     SGD the trainables do not depend on the order in which tasks ran (training-mode BN uses batch statistics), so
@@ -326,9 +327,12 @@ def test_slot_parallel_meta_step_equals_sequential_under_sgd(foml, gemm, nslots)
             kw = dict(num_shots=5, inner_iters=3)
         for _ in range(2):       # two meta-steps: the second replays the captured graphs
             learner.train_step(tasks, m.input_ph, m.label_ph, m.minimize_op, num_classes=1, inner_batch_size=4,
-                               replacement=False, meta_step_size=0.5, meta_batch_size=4, lr_ph=m.lr_ph, lr=None, **kw)
+                               replacement=False, meta_step_size=0.5, meta_batch_size=5 if nslots == 5 else 4, lr_ph=m.lr_ph,
+                               lr=None, **kw)
         eng = m.engine()
         torch.cuda.synchronize()
+        if slots == 5:
+            assert [u[1] for u in learner._train_slots.units] == [3, 2]
         out.append(eng.tf_order_vector(eng.theta(0)).double().cpu())
         bn.append(eng.bn_state(0).double().cpu().clone())
         after = random.random()
