@@ -11,8 +11,9 @@ collective ("weak" scaling: per-GPU work is fixed).
 
 JSON keys follow the driver contract.  `value` = device-resident throughput (task pools already in HBM); `e2e` = the
 same through TaskRunner with HOST task arrays (pinned staging, H2D of every pool, D2H of the counts inside the timed
-region); `roofline` = the dominant kernel (conv2d_2 of decode_skip_connections_1) timed alone; `roofline_hbm` = the
-HBM-bound kernels timed alone, task-batched, L2 flushed; `tensor_peaks` = the measured bf16 (cuBLAS) and kind::tf32
+region); `roofline` = the dominant kernel (conv2d_2 of decode_skip_connections_1) timed alone as the task-batched
+launch the graphs issue (`--group` slots per launch; `single_slot` keeps the one-slot launch beside it); `roofline_hbm` =
+the HBM-bound kernels timed alone, task-batched, L2 flushed; `tensor_peaks` = the measured bf16 (cuBLAS) and kind::tf32
 (own tcgen05 loop) tensor-pipe peaks; `cpu_baseline` = the oracle (a torch-CPU restatement of the reference graph -
 TF-1.15 cannot run here) on this box's host cores, on the SAME tasks from the SAME checkpoint, which also gives
 `miou_vs_oracle`; `meta_train` = meta-steps/s of FOMAML (meta-batch 5) and Reptile (meta-batch 40) with the ONE
