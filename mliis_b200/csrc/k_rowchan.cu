@@ -168,6 +168,60 @@ static void launch_clustered(Kern kern, int G, int nz, dim3 blk, size_t smem, cu
   cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
+// The same finalize-in-the-reduction WITHOUT clusters (task-batched launches, where every slot has few, long row chunks):
+// every CTA writes its partial row, takes a ticket, and the CTA that draws the slot's last ticket sums the gridDim.x
+// rows (thread (cq, ty): rows ty, ty + R, .. with eight rows in flight; lanes combined in ty order, in double: a fixed
+// order, whichever CTA comes last).  Returns true in that CTA; threads with threadIdx.y == 0 then hold the totals.
+__device__ __forceinline__ bool ticket_total2(float4 s0, float4 s1, float4* sm, float* __restrict__ partials, int C,
+                                              unsigned* ticket, double (&t0)[4], double (&t1)[4]) {
+  __shared__ int s_last;
+  const int C4 = blockDim.x, R = blockDim.y, cq = threadIdx.x, ty = threadIdx.y;
+  const int n_rows = gridDim.x;
+  if (ty == 0) {
+    st4(partials + ((size_t)blockIdx.x * 2 + 0) * C + cq * 4, s0);
+    st4(partials + ((size_t)blockIdx.x * 2 + 1) * C + cq * 4, s1);
+  }
+  __threadfence();                                    // this CTA's partial row is visible device-wide before the ticket
+  __syncthreads();                                    // (and block_reduce2 has finished reading sm)
+  if (cq == 0 && ty == 0) {
+    const unsigned t = atomicAdd(ticket, 1u);
+    s_last = (t == (unsigned)n_rows - 1u);
+    if (s_last) atomicExch(ticket, 0u);               // self-resetting: the next launch on the stream starts from zero
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+  for (int g = ty; g < n_rows; g += 8 * R) {          // eight rows (16 float4) in flight per thread; +0.0 tails are exact
+    float4 u[8], v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int gi = g + k * R;
+      u[k] = gi < n_rows ? __ldcg(reinterpret_cast<const float4*>(partials + ((size_t)gi * 2 + 0) * C + cq * 4)) : f4s(0.f);
+      v[k] = gi < n_rows ? __ldcg(reinterpret_cast<const float4*>(partials + ((size_t)gi * 2 + 1) * C + cq * 4)) : f4s(0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      a[0] += u[k].x; a[1] += u[k].y; a[2] += u[k].z; a[3] += u[k].w;
+      b[0] += v[k].x; b[1] += v[k].y; b[2] += v[k].z; b[3] += v[k].w;
+    }
+  }
+  double* sd = reinterpret_cast<double*>(sm);
+  double* mine = sd + ((size_t)ty * C4 + cq) * 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { mine[i] = a[i]; mine[4 + i] = b[i]; }
+  __syncthreads();
+  if (ty != 0) return true;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { t0[i] = a[i]; t1[i] = b[i]; }
+  for (int j = 1; j < R; ++j) {
+    const double* o = sd + ((size_t)j * C4 + cq) * 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { t0[i] += o[i]; t1[i] += o[4 + i]; }
+  }
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 // BN statistics
 // ------------------------------------------------------------------------------------------------
@@ -196,7 +250,8 @@ __device__ __forceinline__ void bn_finalize_channel(const BnFin& f, int c, doubl
   }
 }
 
-template <bool PRE_SWISH, bool CL>
+// MODE 0: partial row per CTA, finalized by a second launch; 1: clusters + ticket (measured slower); 2: ticket
+template <bool PRE_SWISH, int MODE>
 __global__ void bn_stats_kernel(const float* __restrict__ x, int ld, int M, int C, int rows_per_chunk,
                                 float* __restrict__ partials, unsigned* ticket, BnFin fin, long long zs) {
   extern __shared__ float4 sm[];
@@ -227,7 +282,7 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int ld, int M, int 
     }
   }
   block_reduce2(s, ss, sm);
-  if (!CL) {      // MLIIS_BN_CLUSTER=0: one partial row per CTA, finalized by a second launch (round-1 structure)
+  if (MODE == 0) {      // one partial row per CTA, finalized by a second launch (round-1 structure)
     if (threadIdx.y == 0) {
       st4(partials + ((size_t)blockIdx.x * 2 + 0) * C + cq * 4, s);
       st4(partials + ((size_t)blockIdx.x * 2 + 1) * C + cq * 4, ss);
@@ -235,7 +290,9 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, int ld, int M, int 
     return;
   }
   double t0[4], t1[4];
-  if (cluster_total2(s, ss, sm, partials, C, ticket, t0, t1) && threadIdx.y == 0) {
+  const bool last = MODE == 1 ? cluster_total2(s, ss, sm, partials, C, ticket, t0, t1)
+                              : ticket_total2(s, ss, sm, partials, C, ticket, t0, t1);
+  if (last && threadIdx.y == 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) bn_finalize_channel(fin, cq * 4 + i, t0[i], t1[i]);
   }
@@ -288,6 +345,17 @@ __global__ void __launch_bounds__(512) bn_finalize_kernel(const float* __restric
 // (2502 -> 2112): the 8-CTA clusters constrain scheduling next to the other slots' kernels, three cluster barriers sit
 // in every CTA's path and the finalize runs on one CTA while its grid drains.  It stays available (MLIIS_BN_CLUSTER=1) as
 // a measured negative result; the default is the two-launch structure.
+// Finalize inside the reduction through a per-slot ticket (no clusters), for task-batched launches where a slot has few
+// row chunks (37-148).  MEASURED (round 2, B200, 48 slots in groups of 24): correct (kernel, group, meta-step parity tests)
+// and 16 % fewer launches (42240 vs 50040 per 480 tasks) - and SLOWER, like the clustered variant: 144.5 vs 145.3
+// tasks/s, FOMAML 20.4 vs 21.5, Reptile 3.48 vs 3.55 meta-steps/s.  The last CTA's serial sum holds back every kernel
+// that depends on the statistics, while the separate finalize launch spreads the same sum over 100-500 CTAs.  Opt-in
+// (MLIIS_BN_TICKET=1) as a measured negative result; the default stays reduce + finalize as two launches.
+static bool bn_ticket() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("MLIIS_BN_TICKET"); on = e ? atoi(e) : 0; }
+  return on != 0 && partition_nz() >= 2;
+}
 static bool bn_clustered() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("MLIIS_BN_CLUSTER"); on = e ? atoi(e) : 0; }
@@ -305,17 +373,22 @@ void bn_stats_finalize(const float* x, int ld, int M, int C, bool pre_swish, flo
   const size_t smem = (size_t)blk.x * blk.y * 64;
   BnFin fin{gamma, beta, mm, mv, mean, rstd, a, b, M, ema, bessel};
   const long long zs = MLIIS_ZS;
+  if (bn_ticket()) {      // task-batched launch: finalize in the CTA that finishes the slot's reduction (no second launch)
+    if (pre_swish) MLIIS_COUNT(), bn_stats_kernel<true, 2><<<dim3(G, 1, MLIIS_NZ), blk, smem, s>>>(x, ld, M, C, rpc, partials, ticket, fin, zs);
+    else MLIIS_COUNT(), bn_stats_kernel<false, 2><<<dim3(G, 1, MLIIS_NZ), blk, smem, s>>>(x, ld, M, C, rpc, partials, ticket, fin, zs);
+    return;
+  }
   if (!bn_clustered()) {
-    if (pre_swish) MLIIS_COUNT(), bn_stats_kernel<true, false><<<dim3(G, 1, MLIIS_NZ), blk, smem, s>>>(x, ld, M, C, rpc, partials, ticket, fin, zs);
-    else MLIIS_COUNT(), bn_stats_kernel<false, false><<<dim3(G, 1, MLIIS_NZ), blk, smem, s>>>(x, ld, M, C, rpc, partials, ticket, fin, zs);
+    if (pre_swish) MLIIS_COUNT(), bn_stats_kernel<true, 0><<<dim3(G, 1, MLIIS_NZ), blk, smem, s>>>(x, ld, M, C, rpc, partials, ticket, fin, zs);
+    else MLIIS_COUNT(), bn_stats_kernel<false, 0><<<dim3(G, 1, MLIIS_NZ), blk, smem, s>>>(x, ld, M, C, rpc, partials, ticket, fin, zs);
     MLIIS_COUNT(), bn_finalize_kernel<<<dim3(cdiv(C, 32), 1, MLIIS_NZ), dim3(32, 16), 0, s>>>(partials, G, C, M, gamma, beta, mm, mv,
                                                                                             ema, bessel, mean, rstd, a, b, zs);
     return;
   }
   if (pre_swish)
-    MLIIS_COUNT(), launch_clustered(bn_stats_kernel<true, true>, G, MLIIS_NZ, blk, smem, s, x, ld, M, C, rpc, partials, ticket, fin, zs);
+    MLIIS_COUNT(), launch_clustered(bn_stats_kernel<true, 1>, G, MLIIS_NZ, blk, smem, s, x, ld, M, C, rpc, partials, ticket, fin, zs);
   else
-    MLIIS_COUNT(), launch_clustered(bn_stats_kernel<false, true>, G, MLIIS_NZ, blk, smem, s, x, ld, M, C, rpc, partials, ticket, fin, zs);
+    MLIIS_COUNT(), launch_clustered(bn_stats_kernel<false, 1>, G, MLIIS_NZ, blk, smem, s, x, ld, M, C, rpc, partials, ticket, fin, zs);
 }
 
 __global__ void bn_eval_coeffs_kernel(const float* __restrict__ theta, const int32_t* __restrict__ gi,
@@ -645,7 +718,7 @@ __device__ __forceinline__ void bn_bwd_shift(BnBwdArgs& p, long long zs) {
   p.partials += zo; p.k += zo; p.dgamma += zo; p.dbeta += zo; p.ticket += zo;
 }
 
-template <int VAR, bool CL>
+template <int VAR, int MODE>
 __global__ void bn_bwd_reduce_kernel(BnBwdArgs p, int rows_per_chunk, long long zs) {
   extern __shared__ float4 sm[];
   bn_bwd_shift(p, zs);
@@ -674,7 +747,7 @@ __global__ void bn_bwd_reduce_kernel(BnBwdArgs p, int rows_per_chunk, long long 
     }
   }
   block_reduce2(s0, s1, sm);
-  if (!CL) {
+  if (MODE == 0) {
     if (threadIdx.y == 0) {
       st4(p.partials + ((size_t)blockIdx.x * 2 + 0) * p.C + cq * 4, s0);
       st4(p.partials + ((size_t)blockIdx.x * 2 + 1) * p.C + cq * 4, s1);
@@ -682,7 +755,9 @@ __global__ void bn_bwd_reduce_kernel(BnBwdArgs p, int rows_per_chunk, long long 
     return;
   }
   double t0[4], t1[4];
-  if (cluster_total2(s0, s1, sm, p.partials, p.C, p.ticket, t0, t1) && threadIdx.y == 0) {
+  const bool last = MODE == 1 ? cluster_total2(s0, s1, sm, p.partials, p.C, p.ticket, t0, t1)
+                              : ticket_total2(s0, s1, sm, p.partials, p.C, p.ticket, t0, t1);
+  if (last && threadIdx.y == 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {       // dbeta = sum g, dgamma = sum g*xhat, and their means for the apply pass
       const int c = cq * 4 + i;
@@ -753,10 +828,12 @@ static void bn_bwd_t(const BnBwdArgs& p, cudaStream_t s) {
   dim3 blk = rc_block(p.C);
   const int nz = MLIIS_NZ;
   const long long zs = MLIIS_ZS;
-  if (bn_clustered()) {
-    MLIIS_COUNT(), launch_clustered(bn_bwd_reduce_kernel<VAR, true>, G, nz, blk, (size_t)blk.x * blk.y * 64, s, p, cdiv(p.M, G), zs);
+  if (bn_ticket()) {
+    MLIIS_COUNT(), bn_bwd_reduce_kernel<VAR, 2><<<dim3(G, 1, nz), blk, (size_t)blk.x * blk.y * 64, s>>>(p, cdiv(p.M, G), zs);
+  } else if (bn_clustered()) {
+    MLIIS_COUNT(), launch_clustered(bn_bwd_reduce_kernel<VAR, 1>, G, nz, blk, (size_t)blk.x * blk.y * 64, s, p, cdiv(p.M, G), zs);
   } else {
-    MLIIS_COUNT(), bn_bwd_reduce_kernel<VAR, false><<<dim3(G, 1, nz), blk, (size_t)blk.x * blk.y * 64, s>>>(p, cdiv(p.M, G), zs);
+    MLIIS_COUNT(), bn_bwd_reduce_kernel<VAR, 0><<<dim3(G, 1, nz), blk, (size_t)blk.x * blk.y * 64, s>>>(p, cdiv(p.M, G), zs);
     MLIIS_COUNT(), bn_bwd_finalize_kernel<<<dim3(cdiv(p.C, 32), 1, nz), dim3(32, 16), 0, s>>>(p.partials, G, p.C, p.M, p.k, p.dgamma,
                                                                                              p.dbeta, zs);
   }
