@@ -1,2 +1,4 @@
-timeout 170 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_group.py -q -x 2>&1 | tail -2
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | cut -c1-160
+# standard validation job: `gpurun --timeout 1500 -- bash tools/_gpu_job.sh`
+timeout 1200 python -m pytest tests -q -m gpu 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | cut -c1-200
+python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 1200 gpurun_out/bench.json
