@@ -234,6 +234,12 @@ int mliis_task_graph_launch(mliis_ctx* ctx, int32_t slot, void* stream);
 /* Kernels launched by this library in this process (graph replays count their captured kernels). */
 uint64_t mliis_launch_count(void);
 
+/* CRC-32C (Castagnoli) of a HOST buffer, continuing from `crc` (0 to start): the checksum of the TF V2 checkpoint
+ * bundle entries and of the TFRecord framing (mliis_b200/checkpoint.py, tfrecord.py; the reference gets it from
+ * TensorFlow's C++ runtime through tf.train.Saver / tf.data, run_metasegnet.py:125-133, data/input_fn.py:68-110).
+ * Host code only: works without a GPU. */
+uint32_t mliis_crc32c(const void* data, uint64_t n_bytes, uint32_t crc);
+
 /* ---- meta-update (meta_learners/variables.py:9-45; reptile.py:122-125, :644-647) --------------
  * delta_sum += (theta_a - theta_b)             [Reptile: a = adapted, b = old; FOMAML: a = theta_T, b = theta_{T-1}]
  * theta     += scale * delta_sum               [scale = meta_step_size / meta_batch_size]

@@ -43,14 +43,24 @@ def _crc_table():
     return _CRC_TABLE
 
 
-def crc32c(data: bytes) -> int:
-    """Byte-at-a-time CRC32C; large buffers are folded with a numpy-vectorised 4-way interleave-free loop."""
+def _crc32c_py(data: bytes) -> int:
+    """Byte-at-a-time CRC32C in Python (small buffers, and the cross-check of the native routine in the tests)."""
     t = _crc_table()
     c = 0xFFFFFFFF
     tl = t.tolist()
     for b in data:
         c = tl[(c ^ b) & 0xFF] ^ (c >> 8)
     return c ^ 0xFFFFFFFF
+
+
+def crc32c(data) -> int:
+    """CRC-32C of a bytes-like object.  Buffers of 256 bytes and more go through the library's slicing-by-8 routine
+    (mliis_crc32c, host code: ~1 GB/s, which is what makes per-tensor data CRCs affordable for 8 MB of weights)."""
+    if len(data) < 256:
+        return _crc32c_py(bytes(data))
+    from . import native
+    buf = data if isinstance(data, bytes) else bytes(data)
+    return int(native.lib().mliis_crc32c(buf, len(buf), 0))
 
 
 def _mask(crc: int) -> int:
@@ -222,9 +232,10 @@ def read_index(path: str, verify_crc: bool = True) -> Dict[str, dict]:
     return entries
 
 
-def read_bundle(prefix: str, names: Optional[Callable[[str], bool]] = None, verify_crc: bool = False
+def read_bundle(prefix: str, names: Optional[Callable[[str], bool]] = None, verify_crc: bool = True
                 ) -> Dict[str, np.ndarray]:
-    """Load the float32 tensors of a V2 bundle `prefix` (= .../model.ckpt-N)."""
+    """Load the float32 tensors of a V2 bundle `prefix` (= .../model.ckpt-N).  Per-tensor CRC-32Cs are verified as
+    TensorFlow's BundleReader does; an entry whose stored CRC is 0 (bundles of older versions of this writer) is not."""
     index = read_index(prefix + ".index")
     header = index.pop("", {"num_shards": 1, "endianness": 0})
     if header.get("endianness", 0) != 0:
@@ -243,15 +254,15 @@ def read_bundle(prefix: str, names: Optional[Callable[[str], bool]] = None, veri
         if sid not in shards:
             shards[sid] = np.memmap("%s.data-%05d-of-%05d" % (prefix, sid, n_shards), dtype=np.uint8, mode="r")
         raw = bytes(shards[sid][e["offset"]:e["offset"] + e["size"]])
-        if verify_crc and _unmask(e["crc32c"]) != crc32c(raw):
+        if verify_crc and e["crc32c"] != 0 and _unmask(e["crc32c"]) != crc32c(raw):
             raise ValueError("tensor %s: CRC mismatch" % name)
         out[name] = np.frombuffer(raw, dtype="<f4").reshape(e["shape"]).copy()
     return out
 
 
-def write_bundle(prefix: str, tensors: Dict[str, np.ndarray], with_data_crc: bool = False) -> None:
-    """Write float32 tensors as a single-shard V2 bundle.  Index blocks carry valid CRCs; per-tensor data CRCs
-    are computed only when with_data_crc (pure-Python CRC32C is slow for multi-MB tensors)."""
+def write_bundle(prefix: str, tensors: Dict[str, np.ndarray], with_data_crc: bool = True) -> None:
+    """Write float32 tensors as a single-shard V2 bundle.  Index blocks and, by default, every tensor entry carry valid
+    masked CRC-32Cs (TensorFlow's BundleReader::GetValue verifies the per-tensor one; ADVICE r1)."""
     names = sorted(tensors.keys())
     data = bytearray()
     entries = [(b"", _field(1, 0, _put_varint(1)) + _field(2, 0, _put_varint(0)) +
@@ -319,15 +330,27 @@ def model_tensors(model) -> Dict[str, np.ndarray]:
     return {v.name: np.asarray(a, np.float32) for v, a in zip(variables, vals)}
 
 
+def with_adam_m_slots(tensors: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+    """TF's AdamOptimizer also owns a first-moment slot `<var>/Adam` per variable.  With beta1 = 0 it is dead (m == g)
+    and the engine does not keep it, but tf.train.Saver().restore is strict on names: write it as zeros next to every
+    second-moment slot `<var>/Adam_1`."""
+    out = dict(tensors)
+    for name in tensors:
+        if name.endswith("/Adam_1"):
+            out.setdefault(name[:-2], np.zeros_like(tensors[name]))
+    return out
+
+
 class _SessionOf:
     def __init__(self, model):
         self.model = model
 
 
 def restore_into_engine(model, ckpt_dir_or_prefix: str, keep: Optional[Callable[[str], bool]] = None,
-                        strict: bool = True) -> int:
+                        strict: bool = True, warn_missing: bool = False) -> int:
     """Restore variables by name.  strict=True mirrors tf.train.Saver().restore: every global variable of the model
-    must exist in the checkpoint (run_metasegnet.py:131-133) - Adam slots included when the model uses Adam."""
+    must exist in the checkpoint (run_metasegnet.py:131-133) - Adam slots included when the model uses Adam.
+    strict=False keeps the initial value of a variable the checkpoint lacks; warn_missing then says so loudly."""
     from .util import latest_checkpoint
     from .variables import VariableState
     prefix = ckpt_dir_or_prefix
@@ -338,6 +361,11 @@ def restore_into_engine(model, ckpt_dir_or_prefix: str, keep: Optional[Callable[
     missing = [v.name for v in variables if v.name not in tensors]
     if missing and strict:
         raise KeyError("checkpoint %s lacks %d variables, e.g. %s" % (prefix, len(missing), missing[:3]))
+    if missing and warn_missing:
+        import warnings
+        warnings.warn("checkpoint %s lacks %d of the %d selected variables (e.g. %s): they keep their initial values; the "
+                      "reference's Saver(var_dict).restore would have failed here (efficientlab.py:398-443)"
+                      % (prefix, len(missing), len(variables), missing[:3]))
     present = [v for v in variables if v.name in tensors]
     for v in present:
         if tuple(tensors[v.name].shape) != tuple(v.shape):
@@ -357,7 +385,13 @@ class Saver:
 
     def save(self, sess, save_path: str, global_step: Optional[int] = None) -> str:
         prefix = save_path if global_step is None else "%s-%d" % (save_path, global_step)
-        write_bundle(prefix, model_tensors(self.model))
+        try:                               # one writer per job: the trainables are replicated, the files are shared
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_rank() != 0:
+                return prefix
+        except ImportError:
+            pass
+        write_bundle(prefix, with_adam_m_slots(model_tensors(self.model)))
         self._kept.append(prefix)
         while self.max_to_keep and len(self._kept) > self.max_to_keep:
             old = self._kept.pop(0)

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -1093,6 +1094,34 @@ int mliis_task_graph_launch(mliis_ctx* ctx, int32_t slot, void* stream) {
 }
 
 uint64_t mliis_launch_count(void) { return g_kernel_launches; }
+
+// CRC-32C, slicing-by-8 (reflected polynomial 0x82F63B78); host code
+uint32_t mliis_crc32c(const void* data, uint64_t n_bytes, uint32_t crc) {
+  static uint32_t T[8][256];
+  static std::once_flag once;
+  std::call_once(once, [] {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      T[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) T[t][i] = (T[t - 1][i] >> 8) ^ T[0][T[t - 1][i] & 0xFFu];
+  });
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  uint32_t c = ~crc;
+  while (n_bytes >= 8) {
+    uint64_t w;
+    std::memcpy(&w, p, 8);                       // little-endian host (x86-64 / aarch64)
+    w ^= c;
+    c = T[7][w & 0xFF] ^ T[6][(w >> 8) & 0xFF] ^ T[5][(w >> 16) & 0xFF] ^ T[4][(w >> 24) & 0xFF] ^
+        T[3][(w >> 32) & 0xFF] ^ T[2][(w >> 40) & 0xFF] ^ T[1][(w >> 48) & 0xFF] ^ T[0][(w >> 56) & 0xFF];
+    p += 8;
+    n_bytes -= 8;
+  }
+  while (n_bytes--) c = T[0][(c ^ *p++) & 0xFFu] ^ (c >> 8);
+  return ~c;
+}
 
 int mliis_delta_accumulate(mliis_ctx* ctx, float* dsum, const float* ta, const float* tb, int32_t first, void* stream) {
   if (!ctx || !dsum || !ta || !tb) return fail(MLIIS_ERR_ARG, "null argument");

@@ -187,7 +187,7 @@ class EfficientLab:
             if filter_to_scopes is not None:
                 return any(name.startswith(x) for x in filter_to_scopes)
             return True
-        n = restore_into_engine(self, ckpt_dir, keep=keep, strict=False)
+        n = restore_into_engine(self, ckpt_dir, keep=keep, strict=False, warn_missing=True)
         self.variables_initialized = True
         print("Variables initialized")
         print("{} variables restored".format(n))

@@ -82,6 +82,7 @@ SYMBOLS = [
     ("mliis_task_graph_capture", C.c_int, [_VP, _I32, C.POINTER(TaskArgs), _VP]),
     ("mliis_task_graph_launch", C.c_int, [_VP, _I32, _VP]),
     ("mliis_launch_count", C.c_uint64, []),
+    ("mliis_crc32c", C.c_uint32, [_VP, C.c_uint64, C.c_uint32]),
     ("mliis_delta_accumulate", C.c_int, [_VP, _VP, _VP, _VP, _I32, _VP]),
     ("mliis_meta_apply", C.c_int, [_VP, _VP, _VP, _F, _VP]),
     ("mliis_meta_buffer_floats", _I64, [_VP]),

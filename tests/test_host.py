@@ -186,3 +186,35 @@ def test_model_surface_without_gpu():
         EfficientLab(rsd=[2, 4], feature_extractor_name="efficientnet-b3", learning_rate=1e-3, label_smoothing=0.0)
     with pytest.raises(NotImplementedError):
         EfficientLab(rsd=[2, 4], spatial_pyramid_pooling=True, learning_rate=1e-3, label_smoothing=0.0)
+
+
+def test_native_crc32c_and_bundle_data_checksums(tmp_path):
+    """mliis_crc32c (host code of the C library) against the byte-at-a-time Python routine and the CRC-32C check value;
+    bundles carry per-tensor CRCs by default and a corrupted data shard is detected; Adam first-moment slots are written
+    as zeros so that a strict TF restore finds every name."""
+    from mliis_b200 import native
+    from mliis_b200.checkpoint import _crc32c_py, crc32c, read_bundle, read_index, with_adam_m_slots, write_bundle
+    rng = np.random.default_rng(0)
+    lib = native.lib()
+    assert lib.mliis_crc32c(b"123456789", 9, 0) == 0xE3069283
+    for n in (0, 1, 7, 8, 9, 63, 255, 256, 257, 1000, 4099, 65539):
+        b = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert crc32c(b) == _crc32c_py(b) == lib.mliis_crc32c(b, n, 0), n
+        k = n // 3                                             # continuation from a running value
+        assert lib.mliis_crc32c(b[k:], n - k, lib.mliis_crc32c(b[:k], k, 0)) == _crc32c_py(b), n
+    t = with_adam_m_slots({"a/kernel": rng.standard_normal((3, 5)).astype("f4"),
+                           "a/kernel/Adam_1": np.abs(rng.standard_normal((3, 5))).astype("f4"),
+                           "beta2_power": np.float32(0.5)})
+    assert set(t) == {"a/kernel", "a/kernel/Adam", "a/kernel/Adam_1", "beta2_power"} and not t["a/kernel/Adam"].any()
+    prefix = str(tmp_path / "model.ckpt-3")
+    write_bundle(prefix, t)
+    assert all(e["crc32c"] != 0 for k, e in read_index(prefix + ".index").items() if k)
+    r = read_bundle(prefix)
+    assert all(np.array_equal(r[k], t[k]) for k in t)
+    with open(prefix + ".data-00000-of-00001", "r+b") as f:     # flip one bit of the first tensor
+        f.seek(5)
+        b = f.read(1)
+        f.seek(5)
+        f.write(bytes([b[0] ^ 0x10]))
+    with pytest.raises(ValueError):
+        read_bundle(prefix)
